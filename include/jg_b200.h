@@ -1,0 +1,109 @@
+/*
+ * jg_b200.h — C ABI of libjg_b200.so: hand-written sm_100a kernels for the joliGEN training
+ * inner loop (Palette diffusion UNet + GAN generator/discriminator), see DESIGN.md.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, <0 on error (JG_ERR_*); the message is available
+ *     from jg_last_error() (thread-local).  There is NO CPU fallback: unsupported shapes are errors.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; memory is borrowed for the
+ *     duration of the call (the caller's allocator owns it); launches are asynchronous on `stream`.
+ *   - activations are NHWC bf16 ("channels-last"); `ld*` arguments are channel strides in ELEMENTS
+ *     so that an operand may be a channel slice of a wider (concatenated) buffer.  Channel counts,
+ *     channel offsets and ld* must be multiples of 8 (16-byte TMA alignment).
+ *   - weights: fp32 master copies stay in the reference layout (OIHW, what joliGEN's
+ *     state_dict holds); the kernels consume bf16 packed copies produced by jg_pack_conv_weight.
+ *
+ * Each function cites the reference code (joliGEN @ /root/reference) whose arithmetic it replaces.
+ */
+#ifndef JG_B200_H
+#define JG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* jg_stream_t; /* cudaStream_t */
+
+enum {
+  JG_OK = 0,
+  JG_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  JG_ERR_CUDA = -2,        /* CUDA runtime / driver error */
+  JG_ERR_UNSUPPORTED = -3, /* device is not sm_100 */
+};
+
+enum { JG_ACT_NONE = 0, JG_ACT_RELU = 1, JG_ACT_LRELU02 = 2, JG_ACT_TANH = 3, JG_ACT_SILU = 4 };
+
+const char* jg_last_error(void);
+int jg_version(void);
+/* 0 if the current device can run the library (compute capability 10.x), JG_ERR_UNSUPPORTED otherwise */
+int jg_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution as implicit GEMM on tcgen05 tensor cores (TMA-staged NHWC tiles, fp32 accumulation
+ * in TMEM).  Replaces nn.Conv2d / nn.Conv1d(k=1) / nn.Linear on feature maps:
+ *   models/modules/unet_generator_attn/unet_generator_attn.py:186-190,208-220,481-483,639-643
+ *   (ResBlock convs, skip 1x1, UNet in/out convs), :298,:305 (attention qkv / proj_out),
+ *   models/modules/resnet_architecture/resnet_generator.py:11-95, models/modules/discriminators.py:10-117.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int N, H, W;      /* input batch / height / width */
+  int Cin, ldx;     /* input channels and channel stride of x */
+  int Ho, Wo;       /* output height / width */
+  int Cout, ldy;    /* output channels and channel stride of y */
+  int R, S;         /* filter height / width */
+  int stride;       /* 1 or 2 (same in h and w) */
+  int pad;          /* zero padding (same in h and w) */
+  int up2x;         /* 1: the conv reads a virtual nearest-2x-upsampled x (H,W are the upsampled dims) — reserved */
+  int act;          /* JG_ACT_* applied after bias (+ residual) */
+  int ldres;        /* channel stride of the residual operand (0 = none) */
+  float res_scale;  /* y = act(conv + bias + res_scale * residual) */
+} jg_conv_desc;
+
+/* y[N,Ho,Wo,Cout] = act(conv(x, w) + bias + res_scale*residual).
+ * w_packed: bf16 [Cout][R*S][Cin8] with Cin8 = round_up(Cin, 8) (jg_pack_conv_weight, fwd layout).
+ * bias: fp32 [Cout] or NULL.  residual: bf16 NHWC like y with stride ldres, or NULL.
+ * Also used for dgrad of stride-1 convolutions (pass the dgrad-packed weights; Cin/Cout swapped). */
+int jg_conv2d_fwd(const jg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                  const void* residual, void* y, jg_stream_t stream);
+
+/* dw[Cout][R*S][Cin] (fp32, OHWI) += sum over pixels dy (x) x.  The caller zeroes dw beforehand
+ * (split-K partial sums are accumulated with fp32 atomics).  d describes the FORWARD conv. */
+int jg_conv2d_wgrad(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* dw_ohwi,
+                    jg_stream_t stream);
+
+/* fp32 OIHW master weight -> bf16 packed copies.
+ *   w_fwd   [Cout][R*S][Cin8]   (B operand of the forward implicit GEMM)
+ *   w_dgrad [Cin][R*S][Cout8]   taps flipped (B operand of the stride-1 dgrad), may be NULL */
+int jg_pack_conv_weight(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int R, int S,
+                        jg_stream_t stream);
+/* fp32 OHWI wgrad accumulator -> fp32 OIHW gradient (dst = beta*dst + src). */
+int jg_unpack_conv_wgrad(const float* dw_ohwi, float* dw_oihw, int Cout, int Cin, int R, int S, float beta,
+                         jg_stream_t stream);
+/* db[c] = sum over rows of dy[rows][ld] (bias gradient), fp32, overwritten. */
+int jg_bias_grad(const void* dy, int64_t rows, int C, int ld, float* db, jg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Boundary / layout kernels (HBM-bound).
+ * ------------------------------------------------------------------------------------------- */
+/* NCHW fp32 (reference layout, e.g. UNet.compute_feats input `h = input.type(torch.float32)`,
+ * unet_generator_attn.py:670) -> NHWC bf16 with channel stride ld (channels C..ld-1 zero-filled). */
+int jg_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W, int ld,
+                             jg_stream_t stream);
+int jg_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int ld,
+                             jg_stream_t stream);
+/* dst[row][0..C) (=|+=) src[row][0..C): channel-slice copy; torch.cat([h, hs.pop()], dim=1)
+ * (unet_generator_attn.py:687) and its backward. */
+int jg_copy_channels(const void* src, int lds, void* dst, int ldd, int64_t rows, int C, int accumulate,
+                     jg_stream_t stream);
+/* mode 0: F.interpolate(x, scale_factor=2, mode="nearest") (Upsample, unet_generator_attn.py:84-93)
+ * mode 1: nn.AvgPool2d(2,2) (Downsample, :125-140); mode 2 / 3: their backward passes. */
+int jg_resample2x(const void* src, int lds, void* dst, int ldd, int N, int Hs, int Ws, int C, int mode,
+                  jg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JG_B200_H */

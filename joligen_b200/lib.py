@@ -1,0 +1,93 @@
+"""ctypes binding of libjg_b200.so (the C ABI declared in include/jg_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+Tensors are passed as raw device pointers; every call runs on torch's current CUDA stream.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libjg_b200.so")
+
+_lib = None
+
+c_int = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_f = ctypes.c_float
+c_p = ctypes.c_void_p
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of jg_conv_desc."""
+    _fields_ = [
+        ("N", c_int), ("H", c_int), ("W", c_int),
+        ("Cin", c_int), ("ldx", c_int),
+        ("Ho", c_int), ("Wo", c_int),
+        ("Cout", c_int), ("ldy", c_int),
+        ("R", c_int), ("S", c_int),
+        ("stride", c_int), ("pad", c_int), ("up2x", c_int), ("act", c_int),
+        ("ldres", c_int), ("res_scale", c_f),
+    ]
+
+
+ACT_NONE, ACT_RELU, ACT_LRELU02, ACT_TANH, ACT_SILU = 0, 1, 2, 3, 4
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES)
+_SIGNATURES = {
+    "jg_version": [],
+    "jg_check_device": [],
+    "jg_conv2d_fwd": [ctypes.POINTER(ConvDesc), c_p, c_p, c_p, c_p, c_p, c_p],
+    "jg_conv2d_wgrad": [ctypes.POINTER(ConvDesc), c_p, c_p, c_int, c_p, c_p],
+    "jg_pack_conv_weight": [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],
+    "jg_unpack_conv_wgrad": [c_p, c_p, c_int, c_int, c_int, c_int, c_f, c_p],
+    "jg_bias_grad": [c_p, c_i64, c_int, c_int, c_p, c_p],
+    "jg_nchw_f32_to_nhwc_bf16": [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_nhwc_bf16_to_nchw_f32": [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_copy_channels": [c_p, c_int, c_p, c_int, c_i64, c_int, c_int, c_p],
+    "jg_resample2x": [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
+}
+
+
+def exported_symbols():
+    """Every symbol include/jg_b200.h declares (used by the CPU test that checks the .so exports)."""
+    return sorted(list(_SIGNATURES.keys()) + ["jg_last_error"])
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libjg_b200.so not found at %s — run `python -m joligen_b200.build` (there is no fallback path)"
+            % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.jg_last_error.restype = ctypes.c_char_p
+    lib.jg_last_error.argtypes = []
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load().jg_last_error()
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def call(name, *args):
+    lib = load()
+    _check(getattr(lib, name)(*args), name)
