@@ -103,6 +103,25 @@ int jg_copy_channels(const void* src, int lds, void* dst, int ldd, int64_t rows,
 int jg_resample2x(const void* src, int lds, void* dst, int ldd, int N, int Hs, int Ws, int C, int mode,
                   jg_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * GroupNorm (+ FiLM scale/shift) (+ SiLU), NHWC bf16, fp32 statistics.  HBM-bound.
+ *   unet_attn_utils.py:42-48 (GroupNorm wrapper, fp32 compute, eps 1e-5),
+ *   unet_generator_attn.py:186-189 (GN -> SiLU), :250-258 (out_norm(h)*(1+scale)+shift -> SiLU),
+ *   unet_attn_utils.py:60-66,116-117 (attention InstanceNorm1d: groups == C, gamma/beta NULL).
+ * film: fp32 [N][2C] = (scale | shift) = emb_layers output (torch.chunk(emb_out, 2, dim=1)) or NULL.
+ * stats [N][groups][2] = (mean, rstd) and ab [N][C][2] are outputs of fwd and inputs of bwd.
+ * ------------------------------------------------------------------------------------------- */
+size_t jg_groupnorm_fwd_ws_floats(int N, int C, int groups);
+size_t jg_groupnorm_bwd_ws_floats(int N, int C, int groups);
+int jg_groupnorm_fwd(const void* x, int ldx, void* y, int ldy, int N, int HW, int C, int groups, float eps,
+                     const float* gamma, const float* beta, const float* film, int act, float* stats, float* ab,
+                     float* ws, jg_stream_t stream);
+/* dx (=|+=) d/dx; dgamma/dbeta [C] overwritten (may be NULL); dfilm [N][2C] overwritten (may be NULL). */
+int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int accumulate, int N,
+                     int HW, int C, int groups, const float* gamma, const float* beta, const float* film, int act,
+                     const float* stats, const float* ab, float* dgamma, float* dbeta, float* dfilm, float* ws,
+                     jg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,395 @@
+// GroupNorm (+FiLM scale/shift) (+SiLU) forward / backward on NHWC bf16 with fp32 statistics.
+// HBM-bound: 16-byte vector loads, per-thread channel accumulators, shared-memory then global fp32
+// atomics for the per-(image, channel) sums.  Also covers the attention block's InstanceNorm1d
+// (groups == C, no affine, no activation).
+//
+// Reference arithmetic:
+//   GroupNorm wrapper (fp32 compute)     unet_attn_utils.py:42-48
+//   ResBlock FiLM: out_norm(h)*(1+scale)+shift -> SiLU    unet_generator_attn.py:250-258
+//   in_layers: GroupNorm -> SiLU         unet_generator_attn.py:186-189
+//   normalization1d = InstanceNorm1d     unet_attn_utils.py:60-66,116-117
+//
+// forward:   y = act(x*a[n,c] + b[n,c]),   a = rstd*gamma*(1+scale),  b = (beta - mean*rstd*gamma)*(1+scale) + shift
+// backward:  du = dy*act'(u);  A[n,c] = sum du, B[n,c] = sum du*x;  everything else (dgamma, dbeta, dscale,
+//            dshift, the two group means) is a function of A,B;  dx = k1[n,c]*du + k2[n,g]*x + k3[n,g].
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace jg {
+
+constexpr int kNormThreads = 256;
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+__device__ __forceinline__ float silu_f(float u) { return u / (1.f + __expf(-u)); }
+__device__ __forceinline__ float silu_grad(float u) {
+  const float s = 1.f / (1.f + __expf(-u));
+  return s * (1.f + u * (1.f - s));
+}
+
+// ---- pass 1 (fwd): per-(n, group) sum and sum of squares --------------------------------------
+// grid (chunks, N); smem: 2*C floats.
+__global__ void __launch_bounds__(kNormThreads)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int groups, int rows_per_block,
+                float* __restrict__ sums /*[N][groups][2]*/) {
+  extern __shared__ float sm[];
+  float* csum = sm;
+  float* csq = sm + C;
+  const int n = blockIdx.y;
+  const int vecs = C / 8;
+  const int rstep = kNormThreads / vecs;
+  const int v = threadIdx.x % vecs;
+  const int rl = threadIdx.x / vecs;
+  for (int i = threadIdx.x; i < 2 * C; i += kNormThreads) sm[i] = 0.f;
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, HW);
+  if (rl < rstep) {
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const __nv_bfloat16* base = x + ((size_t)n * HW) * ldx + v * 8;
+    for (int r = r0 + rl; r < r1; r += rstep) {
+      float f[8];
+      load8(base + (size_t)r * ldx, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        q[j] += f[j] * f[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&csum[v * 8 + j], s[j]);
+      atomicAdd(&csq[v * 8 + j], q[j]);
+    }
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += kNormThreads) {
+    float s = 0.f, q = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      s += csum[c];
+      q += csq[c];
+    }
+    atomicAdd(&sums[((size_t)n * groups + g) * 2 + 0], s);
+    atomicAdd(&sums[((size_t)n * groups + g) * 2 + 1], q);
+  }
+}
+
+// ---- pass 2 (fwd): mean/rstd and the per-(n,c) affine coefficients -----------------------------
+// grid N, threads over C.
+__global__ void gn_finalize_fwd_kernel(const float* __restrict__ sums, int HW, int C, int groups, float eps,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       const float* __restrict__ film /*[N][2C]*/, float* __restrict__ stats,
+                                       float* __restrict__ ab /*[N][C][2]*/) {
+  const int n = blockIdx.x;
+  const int cpg = C / groups;
+  const float cnt = (float)cpg * (float)HW;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float s = sums[((size_t)n * groups + g) * 2 + 0];
+    const float q = sums[((size_t)n * groups + g) * 2 + 1];
+    const float mean = s / cnt;
+    const float var = fmaxf(q / cnt - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    if (c == g * cpg) {
+      stats[((size_t)n * groups + g) * 2 + 0] = mean;
+      stats[((size_t)n * groups + g) * 2 + 1] = rstd;
+    }
+    const float ga = gamma ? gamma[c] : 1.f;
+    const float be = beta ? beta[c] : 0.f;
+    float a = rstd * ga;
+    float b = be - mean * a;
+    if (film) {
+      const float sc = 1.f + film[(size_t)n * 2 * C + c];
+      const float sh = film[(size_t)n * 2 * C + C + c];
+      a *= sc;
+      b = b * sc + sh;
+    }
+    ab[((size_t)n * C + c) * 2 + 0] = a;
+    ab[((size_t)n * C + c) * 2 + 1] = b;
+  }
+}
+
+// ---- pass 3 (fwd): y = act(x*a + b) -------------------------------------------------------------
+__global__ void __launch_bounds__(kNormThreads)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy, int HW, int C,
+                int rows_per_block, const float* __restrict__ ab, int act) {
+  const int n = blockIdx.y;
+  const int vecs = C / 8;
+  const int rstep = kNormThreads / vecs;
+  const int v = threadIdx.x % vecs;
+  const int rl = threadIdx.x / vecs;
+  if (rl >= rstep) return;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = ab[((size_t)n * C + v * 8 + j) * 2 + 0];
+    b[j] = ab[((size_t)n * C + v * 8 + j) * 2 + 1];
+  }
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, HW);
+  const __nv_bfloat16* xb = x + ((size_t)n * HW) * ldx + v * 8;
+  __nv_bfloat16* yb = y + ((size_t)n * HW) * ldy + v * 8;
+  for (int r = r0 + rl; r < r1; r += rstep) {
+    float f[8];
+    load8(xb + (size_t)r * ldx, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float u = f[j] * a[j] + b[j];
+      f[j] = act == JG_ACT_SILU ? silu_f(u) : u;
+    }
+    store8(yb + (size_t)r * ldy, f);
+  }
+}
+
+// ---- bwd pass 1: A[n,c] = sum du, B[n,c] = sum du*x ------------------------------------------
+// grid (chunks, N); smem 2*C floats (block-level reduction before the global atomics).
+__global__ void __launch_bounds__(kNormThreads)
+gn_bwd_sums_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy, int lddy,
+                   int HW, int C, int rows_per_block, const float* __restrict__ ab, int act,
+                   float* __restrict__ AB /*[N][C][2]*/) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y;
+  const int vecs = C / 8;
+  const int rstep = kNormThreads / vecs;
+  const int v = threadIdx.x % vecs;
+  const int rl = threadIdx.x / vecs;
+  for (int i = threadIdx.x; i < 2 * C; i += kNormThreads) sm[i] = 0.f;
+  __syncthreads();
+  if (rl < rstep) {
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] = ab[((size_t)n * C + v * 8 + j) * 2 + 0];
+      b[j] = ab[((size_t)n * C + v * 8 + j) * 2 + 1];
+    }
+    float sa[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, HW);
+    const __nv_bfloat16* xb = x + ((size_t)n * HW) * ldx + v * 8;
+    const __nv_bfloat16* db = dy + ((size_t)n * HW) * lddy + v * 8;
+    for (int r = r0 + rl; r < r1; r += rstep) {
+      float f[8], d[8];
+      load8(xb + (size_t)r * ldx, f);
+      load8(db + (size_t)r * lddy, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float du = d[j];
+        if (act == JG_ACT_SILU) du *= silu_grad(f[j] * a[j] + b[j]);
+        sa[j] += du;
+        sb[j] += du * f[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sm[(v * 8 + j) * 2 + 0], sa[j]);
+      atomicAdd(&sm[(v * 8 + j) * 2 + 1], sb[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += kNormThreads) atomicAdd(&AB[(size_t)n * C * 2 + i], sm[i]);
+}
+
+// ---- bwd pass 2: coefficients, dFiLM ---------------------------------------------------------------
+// grid N; smem 2*C floats.  K: [N][C] k1, then [N][groups][2] (k2,k3).
+__global__ void gn_finalize_bwd_kernel(const float* __restrict__ AB, int HW, int C, int groups,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       const float* __restrict__ film, const float* __restrict__ stats,
+                                       float* __restrict__ k1, float* __restrict__ k23,
+                                       float* __restrict__ dfilm /*[N][2C] or null*/,
+                                       float* __restrict__ gAB /*[N][C][2]: (1+scale)*A, (1+scale)*Bhat*/) {
+  extern __shared__ float sm[];
+  float* t1 = sm;      // gamma_eff * A
+  float* t2 = sm + C;  // gamma_eff * Bhat
+  const int n = blockIdx.x;
+  const int cpg = C / groups;
+  const float cnt = (float)cpg * (float)HW;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = stats[((size_t)n * groups + g) * 2 + 0];
+    const float rstd = stats[((size_t)n * groups + g) * 2 + 1];
+    const float A = AB[((size_t)n * C + c) * 2 + 0];
+    const float Bx = AB[((size_t)n * C + c) * 2 + 1];
+    const float Bh = rstd * (Bx - mean * A);
+    const float ga = gamma ? gamma[c] : 1.f;
+    const float be = beta ? beta[c] : 0.f;
+    const float sc = film ? 1.f + film[(size_t)n * 2 * C + c] : 1.f;
+    const float ge = ga * sc;
+    t1[c] = ge * A;
+    t2[c] = ge * Bh;
+    k1[(size_t)n * C + c] = rstd * ge;
+    if (dfilm) {
+      dfilm[(size_t)n * 2 * C + c] = ga * Bh + be * A;  // d scale
+      dfilm[(size_t)n * 2 * C + C + c] = A;             // d shift
+    }
+    gAB[((size_t)n * C + c) * 2 + 0] = sc * A;
+    gAB[((size_t)n * C + c) * 2 + 1] = sc * Bh;
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      s1 += t1[c];
+      s2 += t2[c];
+    }
+    const float mean = stats[((size_t)n * groups + g) * 2 + 0];
+    const float rstd = stats[((size_t)n * groups + g) * 2 + 1];
+    const float m1 = s1 / cnt, m2 = s2 / cnt;
+    k23[((size_t)n * groups + g) * 2 + 0] = -rstd * rstd * m2;
+    k23[((size_t)n * groups + g) * 2 + 1] = rstd * rstd * m2 * mean - rstd * m1;
+  }
+}
+
+// dgamma[c] = sum_n (1+scale)*Bhat, dbeta[c] = sum_n (1+scale)*A
+__global__ void gn_param_grad_kernel(const float* __restrict__ gAB, int N, int C, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sa = 0.f, sb = 0.f;
+  for (int n = 0; n < N; ++n) {
+    sa += gAB[((size_t)n * C + c) * 2 + 0];
+    sb += gAB[((size_t)n * C + c) * 2 + 1];
+  }
+  if (dbeta) dbeta[c] = sa;
+  if (dgamma) dgamma[c] = sb;
+}
+
+// ---- bwd pass 3: dx = k1*du + k2*x + k3 ----------------------------------------------------------
+__global__ void __launch_bounds__(kNormThreads)
+gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy, int lddy,
+                    __nv_bfloat16* __restrict__ dx, int lddx, int HW, int C, int groups, int rows_per_block,
+                    const float* __restrict__ ab, int act, const float* __restrict__ k1,
+                    const float* __restrict__ k23, int accumulate) {
+  const int n = blockIdx.y;
+  const int vecs = C / 8;
+  const int rstep = kNormThreads / vecs;
+  const int v = threadIdx.x % vecs;
+  const int rl = threadIdx.x / vecs;
+  if (rl >= rstep) return;
+  const int cpg = C / groups;
+  float a[8], b[8], c1[8], c2[8], c3[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = v * 8 + j;
+    const int g = c / cpg;
+    a[j] = ab[((size_t)n * C + c) * 2 + 0];
+    b[j] = ab[((size_t)n * C + c) * 2 + 1];
+    c1[j] = k1[(size_t)n * C + c];
+    c2[j] = k23[((size_t)n * groups + g) * 2 + 0];
+    c3[j] = k23[((size_t)n * groups + g) * 2 + 1];
+  }
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, HW);
+  const __nv_bfloat16* xb = x + ((size_t)n * HW) * ldx + v * 8;
+  const __nv_bfloat16* db = dy + ((size_t)n * HW) * lddy + v * 8;
+  __nv_bfloat16* ob = dx + ((size_t)n * HW) * lddx + v * 8;
+  for (int r = r0 + rl; r < r1; r += rstep) {
+    float f[8], d[8], o[8];
+    load8(xb + (size_t)r * ldx, f);
+    load8(db + (size_t)r * lddy, d);
+    if (accumulate) load8(ob + (size_t)r * lddx, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float du = d[j];
+      if (act == JG_ACT_SILU) du *= silu_grad(f[j] * a[j] + b[j]);
+      const float val = c1[j] * du + c2[j] * f[j] + c3[j];
+      o[j] = accumulate ? o[j] + val : val;
+    }
+    store8(ob + (size_t)r * lddx, o);
+  }
+}
+
+static int rows_per_block_for(int HW, int N) {
+  // ~4 waves of blocks over the SMs, at least 32 rows per block
+  const int target_blocks = num_sms() * 8;
+  int chunks = target_blocks / (N > 0 ? N : 1);
+  if (chunks < 1) chunks = 1;
+  int rpb = (HW + chunks - 1) / chunks;
+  if (rpb < 32) rpb = 32;
+  return rpb;
+}
+
+static int check_norm_args(int N, int HW, int C, int groups, int ldx) {
+  JG_CHECK(N > 0 && HW > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldx >= C, JG_ERR_INVALID,
+           "groupnorm: bad dims N=%d HW=%d C=%d ld=%d", N, HW, C, ldx);
+  JG_CHECK(groups > 0 && C % groups == 0, JG_ERR_INVALID, "groupnorm: C=%d not divisible by groups=%d", C, groups);
+  JG_CHECK(C / 8 <= kNormThreads, JG_ERR_INVALID, "groupnorm: C=%d too large", C);
+  return JG_OK;
+}
+
+}  // namespace jg
+
+using namespace jg;
+
+extern "C" size_t jg_groupnorm_fwd_ws_floats(int N, int C, int groups) { return (size_t)N * groups * 2; }
+extern "C" size_t jg_groupnorm_bwd_ws_floats(int N, int C, int groups) {
+  return (size_t)N * C * 2 /*AB*/ + (size_t)N * C /*k1*/ + (size_t)N * groups * 2 /*k23*/ + (size_t)N * C * 2 /*gAB*/;
+}
+
+extern "C" int jg_groupnorm_fwd(const void* x, int ldx, void* y, int ldy, int N, int HW, int C, int groups, float eps,
+                                const float* gamma, const float* beta, const float* film, int act, float* stats,
+                                float* ab, float* ws, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_norm_args(N, HW, C, groups, ldx);
+  if (rc) return rc;
+  JG_CHECK(x && y && stats && ab && ws, JG_ERR_INVALID, "groupnorm_fwd: null pointer");
+  JG_CHECK(ldy % 8 == 0 && ldy >= C, JG_ERR_INVALID, "groupnorm_fwd: bad ldy");
+  JG_CHECK(act == JG_ACT_NONE || act == JG_ACT_SILU, JG_ERR_INVALID, "groupnorm_fwd: act %d unsupported", act);
+  JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)N * groups * 2, stream));
+  const int rpb = rows_per_block_for(HW, N);
+  dim3 grid((HW + rpb - 1) / rpb, N);
+  gn_stats_kernel<<<grid, kNormThreads, 2 * C * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,
+                                                                         HW, C, groups, rpb, ws);
+  JG_LAUNCH_CHECK();
+  gn_finalize_fwd_kernel<<<N, 256, 0, stream>>>(ws, HW, C, groups, eps, gamma, beta, film, stats, ab);
+  JG_LAUNCH_CHECK();
+  gn_apply_kernel<<<grid, kNormThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,
+                                                     static_cast<__nv_bfloat16*>(y), ldy, HW, C, rpb, ab, act);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
+extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int accumulate,
+                                int N, int HW, int C, int groups, const float* gamma, const float* beta,
+                                const float* film, int act, const float* stats, const float* ab, float* dgamma,
+                                float* dbeta, float* dfilm, float* ws, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_norm_args(N, HW, C, groups, ldx);
+  if (rc) return rc;
+  JG_CHECK(x && dy && dx && stats && ab && ws, JG_ERR_INVALID, "groupnorm_bwd: null pointer");
+  JG_CHECK(lddy % 8 == 0 && lddy >= C && lddx % 8 == 0 && lddx >= C, JG_ERR_INVALID, "groupnorm_bwd: bad ld");
+  float* AB = ws;
+  float* k1 = AB + (size_t)N * C * 2;
+  float* k23 = k1 + (size_t)N * C;
+  float* gAB = k23 + (size_t)N * groups * 2;
+  JG_CUDA(cudaMemsetAsync(AB, 0, sizeof(float) * (size_t)N * C * 2, stream));
+  const int rpb = rows_per_block_for(HW, N);
+  dim3 grid((HW + rpb - 1) / rpb, N);
+  gn_bwd_sums_kernel<<<grid, kNormThreads, 2 * C * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,
+                                                        static_cast<const __nv_bfloat16*>(dy), lddy, HW, C, rpb, ab,
+                                                        act, AB);
+  JG_LAUNCH_CHECK();
+  gn_finalize_bwd_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(AB, HW, C, groups, gamma, beta, film, stats, k1,
+                                                                    k23, dfilm, gAB);
+  JG_LAUNCH_CHECK();
+  if (dgamma || dbeta) {
+    gn_param_grad_kernel<<<(C + 127) / 128, 128, 0, stream>>>(gAB, N, C, dgamma, dbeta);
+    JG_LAUNCH_CHECK();
+  }
+  gn_bwd_apply_kernel<<<grid, kNormThreads, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(dy), lddy,
+      static_cast<__nv_bfloat16*>(dx), lddx, HW, C, groups, rpb, ab, act, k1, k23, accumulate);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
