@@ -122,6 +122,62 @@ int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx,
                      const float* stats, const float* ab, float* dgamma, float* dbeta, float* dfilm, float* ws,
                      jg_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Spatial self-attention (flash style, T x T never materialised), bf16, fp32 softmax.
+ *   QKVAttentionLegacy.forward, unet_generator_attn.py:331-347 (per-head interleaved q|k|v channels,
+ *   scale ch^-1/4 on q and k, softmax in fp32).  qkv NHWC [N][T][3*heads*ch]; out [N][T][heads*ch];
+ *   lse fp32 [N*heads][T] (log2 domain) is saved for the backward.  T % 64 == 0, ch in {16,32,64}.
+ * ------------------------------------------------------------------------------------------- */
+int jg_attn_fwd(const void* qkv, int ldqkv, void* out, int ldo, float* lse, int N, int T, int heads, int ch,
+                jg_stream_t stream);
+/* ws: N*heads*T floats.  dqkv has the layout of qkv. */
+int jg_attn_bwd(const void* qkv, int ldqkv, const void* out, int ldo, const void* d_out, int lddo, const float* lse,
+                void* dqkv, int lddqkv, float* ws, int N, int T, int heads, int ch, jg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small fp32 Linear on [B, I] embeddings with optional SiLU on the input / output:
+ *   ResBlock.emb_layers = SiLU -> Linear (unet_generator_attn.py:201-207),
+ *   DiffusionGenerator.cond_embed = Linear -> SiLU -> Linear (diffusion_generator.py:72-76).
+ * ------------------------------------------------------------------------------------------- */
+int jg_linear_fwd(const float* x, const float* w, const float* bias, float* y, int B, int I, int O, int act_in,
+                  int act_out, jg_stream_t stream);
+/* dx (=|+=) (may be NULL), dw [O][I] and db [O] overwritten (may be NULL). act_in as in the forward. */
+int jg_linear_bwd(const float* x, const float* w, const float* dy, float* dx, int dx_accumulate, float* dw, float* db,
+                  int B, int I, int O, int act_in, jg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DiffusionGenerator.forward prologue (diffusion_generator.py:480-491): q_sample + mask blend +
+ * cat([y_cond, y_noisy]) written as NHWC bf16 (channel stride ld, zero padded).  y0 / ycond / noise
+ * fp32 NCHW [B,C,H,W]; mask [B,1,H,W] as fp32 or int64 (either may be NULL; clamp(mask,0,1) is
+ * bit-exact); gammas fp32 [B] = sample_gammas.
+ * ------------------------------------------------------------------------------------------- */
+int jg_noise_pack_fwd(const float* y0, const float* ycond, const float* noise, const float* mask_f32,
+                      const int64_t* mask_i64, const float* gammas, void* out, int B, int C, int H, int W, int ld,
+                      jg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PaletteModel.compute_palette_loss (palette_model.py:596-620):
+ *   loss = lambda_G * mean_{b,c,h,w} (w_b * clamp(mask,0,1) * (noise - noise_hat))^2   (l1: |.|)
+ * noise fp32 NCHW, noise_hat NHWC bf16 (stride ld); w_b fp32 [B] (min-SNR weight) or NULL.
+ * loss: fp32 scalar on device (overwritten).  bwd writes d loss/d noise_hat * (*grad_out).
+ * ------------------------------------------------------------------------------------------- */
+int jg_palette_loss_fwd(const float* noise, const void* noise_hat, int ld, const float* mask_f32,
+                        const int64_t* mask_i64, const float* w_b, int B, int C, int HW, float lambda_g, int l1,
+                        float* loss, jg_stream_t stream);
+int jg_palette_loss_bwd(const float* noise, const void* noise_hat, int ld, const float* mask_f32,
+                        const int64_t* mask_i64, const float* w_b, int B, int C, int HW, float lambda_g, int l1,
+                        const float* grad_out, void* d_noise_hat, int ldd, jg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused Adam(W) + EMA over flat fp32 buffers: torch.optim.AdamW / Adam update (train.py:51-62,
+ * base_model.py:1268-1274) followed by ema_step (base_model.py:1284-1297).  g is multiplied by
+ * grad_scale first (1/world_size after a SUM all-reduce, 1/iter_size...).  ema may be NULL;
+ * ema_init != 0 reproduces the first ema_step (deep copy of the updated net).
+ * ------------------------------------------------------------------------------------------- */
+int jg_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int adamw, int step, float grad_scale,
+                      float ema_beta, int ema_init, jg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

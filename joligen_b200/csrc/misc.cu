@@ -1,0 +1,271 @@
+// Small fused kernels around the UNet: timestep-embedding Linear (+SiLU on the input), the
+// DiffusionGenerator noising prologue, the Palette masked eps-loss (forward + backward in one pass
+// each), and the fused multi-tensor AdamW + EMA update.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace jg {
+
+__device__ __forceinline__ float silu_f(float u) { return u / (1.f + __expf(-u)); }
+__device__ __forceinline__ float silu_g(float u) {
+  const float s = 1.f / (1.f + __expf(-u));
+  return s * (1.f + u * (1.f - s));
+}
+
+// y[b][o] = sum_i act(x[b][i]) * w[o][i] + bias[o]        (emb_layers: SiLU -> Linear,
+// unet_generator_attn.py:201-207; cond_embed MLP, diffusion_generator.py:72-76)
+__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                  const float* __restrict__ bias, float* __restrict__ y, int B, int I, int O,
+                                  int act_in, int act_out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * O) return;
+  const int b = idx / O, o = idx % O;
+  float acc = bias ? bias[o] : 0.f;
+  for (int i = 0; i < I; ++i) {
+    float xv = x[b * I + i];
+    if (act_in == JG_ACT_SILU) xv = silu_f(xv);
+    acc += xv * w[(size_t)o * I + i];
+  }
+  if (act_out == JG_ACT_SILU) acc = silu_f(acc);
+  y[idx] = acc;
+}
+// dx[b][i] = act'(x[b][i]) * sum_o dy[b][o] w[o][i]
+__global__ void linear_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                     const float* __restrict__ dy, float* __restrict__ dx, int B, int I, int O,
+                                     int act_in, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * I) return;
+  const int b = idx / I, i = idx % I;
+  float acc = 0.f;
+  for (int o = 0; o < O; ++o) acc += dy[(size_t)b * O + o] * w[(size_t)o * I + i];
+  if (act_in == JG_ACT_SILU) acc *= silu_g(x[idx]);
+  dx[idx] = accumulate ? dx[idx] + acc : acc;
+}
+// dw[o][i] = sum_b dy[b][o] act(x[b][i]);  db[o] = sum_b dy[b][o]
+__global__ void linear_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                                     float* __restrict__ db, int B, int I, int O, int act_in) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= O * I) return;
+  const int o = idx / I, i = idx % I;
+  float acc = 0.f, accb = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float xv = x[b * I + i];
+    if (act_in == JG_ACT_SILU) xv = silu_f(xv);
+    const float d = dy[(size_t)b * O + o];
+    acc += d * xv;
+    accb += d;
+  }
+  dw[idx] = acc;
+  if (db && i == 0) db[o] = accb;
+}
+
+// DiffusionGenerator.forward prologue (diffusion_generator.py:480-491):
+//   y_noisy = sqrt(g)*y0 + sqrt(1-g)*noise;  y_noisy = y_noisy*m + (1-m)*y0, m = clamp(mask,0,1);
+//   input = cat([y_cond, y_noisy], dim=1)  ->  NHWC bf16 with channel stride ld (zero padded).
+__global__ void noise_pack_kernel(const float* __restrict__ y0, const float* __restrict__ ycond,
+                                  const float* __restrict__ noise, const float* __restrict__ maskf,
+                                  const long long* __restrict__ maski, const float* __restrict__ gammas,
+                                  __nv_bfloat16* __restrict__ out, int B, int C, int HW, int ld) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * HW) return;
+  const int b = (int)(idx / HW);
+  const int p = (int)(idx % HW);
+  const float g = gammas[b];
+  const float sg = sqrtf(g), s1 = sqrtf(1.f - g);
+  float m = 1.f;
+  bool has_mask = false;
+  if (maskf) {
+    m = fminf(fmaxf(maskf[idx], 0.f), 1.f);
+    has_mask = true;
+  } else if (maski) {
+    const long long mv = maski[idx];
+    m = mv < 0 ? 0.f : (mv > 1 ? 1.f : (float)mv);
+    has_mask = true;
+  }
+  __nv_bfloat16* o = out + idx * ld;
+  for (int c = 0; c < C; ++c) {
+    const size_t src = ((size_t)b * C + c) * HW + p;
+    const float y = y0[src];
+    float yn = sg * y + s1 * noise[src];
+    if (has_mask) yn = yn * m + (1.f - m) * y;
+    o[c] = __float2bfloat16(ycond[src]);
+    o[C + c] = __float2bfloat16(yn);
+  }
+  for (int c = 2 * C; c < ld; ++c) o[c] = __float2bfloat16(0.f);
+}
+
+// Palette loss (palette_model.py:596-620): loss = lambda * mean_{b,c,p} (w_b*m*(noise - noise_hat))^2  (MSE)
+//                                      or   lambda * mean |w_b*m*(noise - noise_hat)|              (L1)
+// noise fp32 NCHW, noise_hat NHWC bf16 (channel stride ld).  One pass: block partial sums -> atomicAdd(loss).
+__global__ void palette_loss_fwd_kernel(const float* __restrict__ noise, const __nv_bfloat16* __restrict__ nh, int ld,
+                                        const float* __restrict__ maskf, const long long* __restrict__ maski,
+                                        const float* __restrict__ wb, int B, int C, int HW, float coef, int l1,
+                                        float* __restrict__ loss) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  if (idx < (long long)B * HW) {
+    const int b = (int)(idx / HW);
+    const int p = (int)(idx % HW);
+    float m = 1.f;
+    if (maskf) m = fminf(fmaxf(maskf[idx], 0.f), 1.f);
+    else if (maski) {
+      const long long mv = maski[idx];
+      m = mv < 0 ? 0.f : (mv > 1 ? 1.f : (float)mv);
+    }
+    const float wm = (wb ? wb[b] : 1.f) * m;
+    for (int c = 0; c < C; ++c) {
+      const float e = noise[((size_t)b * C + c) * HW + p];
+      const float eh = __bfloat162float(nh[idx * ld + c]);
+      const float d = wm * (e - eh);
+      acc += l1 ? fabsf(d) : d * d;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += part[i];
+    atomicAdd(loss, s * coef);
+  }
+}
+// d loss / d noise_hat, NHWC bf16 (channels C..ld-1 zero), scaled by the upstream scalar *gout.
+__global__ void palette_loss_bwd_kernel(const float* __restrict__ noise, const __nv_bfloat16* __restrict__ nh, int ld,
+                                        const float* __restrict__ maskf, const long long* __restrict__ maski,
+                                        const float* __restrict__ wb, int B, int C, int HW, float coef, int l1,
+                                        const float* __restrict__ gout, __nv_bfloat16* __restrict__ dnh, int ldd) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * HW) return;
+  const int b = (int)(idx / HW);
+  const int p = (int)(idx % HW);
+  float m = 1.f;
+  if (maskf) m = fminf(fmaxf(maskf[idx], 0.f), 1.f);
+  else if (maski) {
+    const long long mv = maski[idx];
+    m = mv < 0 ? 0.f : (mv > 1 ? 1.f : (float)mv);
+  }
+  const float wm = (wb ? wb[b] : 1.f) * m;
+  const float gs = (gout ? *gout : 1.f) * coef;
+  for (int c = 0; c < C; ++c) {
+    const float e = noise[((size_t)b * C + c) * HW + p];
+    const float eh = __bfloat162float(nh[idx * ld + c]);
+    const float d = wm * (eh - e);
+    const float gr = l1 ? (d > 0.f ? wm : (d < 0.f ? -wm : 0.f)) : 2.f * wm * d;
+    dnh[idx * ldd + c] = __float2bfloat16(gs * gr);
+  }
+  for (int c = C; c < ldd; ++c) dnh[idx * ldd + c] = __float2bfloat16(0.f);
+}
+
+// Fused AdamW / Adam + EMA over flat fp32 buffers (torch.optim.AdamW semantics, train.py:57-58;
+// ema_step, base_model.py:1284-1297: p_ema = p + beta*(p_ema - p)).
+__global__ void adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, float* __restrict__ ema, long long n, float lr, float beta1,
+                                 float beta2, float eps, float wd, int adamw, float bc1, float bc2_sqrt,
+                                 float grad_scale, float ema_beta, int ema_init) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float pv = p[i];
+    float gv = g[i] * grad_scale;
+    if (!adamw && wd != 0.f) gv += wd * pv;
+    if (adamw) pv *= 1.f - lr * wd;
+    const float mv = beta1 * m[i] + (1.f - beta1) * gv;
+    const float vv = beta2 * v[i] + (1.f - beta2) * gv * gv;
+    m[i] = mv;
+    v[i] = vv;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pv -= (lr / bc1) * (mv / denom);
+    p[i] = pv;
+    if (ema) {
+      const float e = ema_init ? pv : ema[i];
+      ema[i] = pv + ema_beta * (e - pv);
+    }
+  }
+}
+
+}  // namespace jg
+
+using namespace jg;
+
+extern "C" int jg_linear_fwd(const float* x, const float* w, const float* bias, float* y, int B, int I, int O,
+                             int act_in, int act_out, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  JG_CHECK(x && w && y && B > 0 && I > 0 && O > 0, JG_ERR_INVALID, "linear_fwd: bad args");
+  linear_fwd_kernel<<<(B * O + 127) / 128, 128, 0, stream>>>(x, w, bias, y, B, I, O, act_in, act_out);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
+extern "C" int jg_linear_bwd(const float* x, const float* w, const float* dy, float* dx, int dx_accumulate, float* dw,
+                             float* db, int B, int I, int O, int act_in, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  JG_CHECK(x && w && dy && B > 0 && I > 0 && O > 0, JG_ERR_INVALID, "linear_bwd: bad args");
+  if (dx) {
+    linear_bwd_dx_kernel<<<(B * I + 127) / 128, 128, 0, stream>>>(x, w, dy, dx, B, I, O, act_in, dx_accumulate);
+    JG_LAUNCH_CHECK();
+  }
+  if (dw) {
+    linear_bwd_dw_kernel<<<(O * I + 127) / 128, 128, 0, stream>>>(x, dy, dw, db, B, I, O, act_in);
+    JG_LAUNCH_CHECK();
+  }
+  return JG_OK;
+}
+
+extern "C" int jg_noise_pack_fwd(const float* y0, const float* ycond, const float* noise, const float* mask_f32,
+                                 const int64_t* mask_i64, const float* gammas, void* out, int B, int C, int H, int W,
+                                 int ld, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  JG_CHECK(y0 && ycond && noise && gammas && out && B > 0 && C > 0 && ld >= 2 * C && ld % 8 == 0, JG_ERR_INVALID,
+           "noise_pack_fwd: bad args");
+  const long long total = (long long)B * H * W;
+  noise_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      y0, ycond, noise, mask_f32, reinterpret_cast<const long long*>(mask_i64), gammas,
+      static_cast<__nv_bfloat16*>(out), B, C, H * W, ld);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
+extern "C" int jg_palette_loss_fwd(const float* noise, const void* noise_hat, int ld, const float* mask_f32,
+                                   const int64_t* mask_i64, const float* w_b, int B, int C, int HW, float lambda_g,
+                                   int l1, float* loss, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  JG_CHECK(noise && noise_hat && loss && B > 0 && C > 0 && ld >= C, JG_ERR_INVALID, "palette_loss_fwd: bad args");
+  JG_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+  const long long total = (long long)B * HW;
+  const float coef = lambda_g / ((float)B * (float)C * (float)HW);
+  palette_loss_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      noise, static_cast<const __nv_bfloat16*>(noise_hat), ld, mask_f32, reinterpret_cast<const long long*>(mask_i64),
+      w_b, B, C, HW, coef, l1, loss);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
+extern "C" int jg_palette_loss_bwd(const float* noise, const void* noise_hat, int ld, const float* mask_f32,
+                                   const int64_t* mask_i64, const float* w_b, int B, int C, int HW, float lambda_g,
+                                   int l1, const float* grad_out, void* d_noise_hat, int ldd, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  JG_CHECK(noise && noise_hat && d_noise_hat && B > 0 && C > 0 && ld >= C && ldd >= C, JG_ERR_INVALID,
+           "palette_loss_bwd: bad args");
+  const long long total = (long long)B * HW;
+  const float coef = lambda_g / ((float)B * (float)C * (float)HW);
+  palette_loss_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      noise, static_cast<const __nv_bfloat16*>(noise_hat), ld, mask_f32, reinterpret_cast<const long long*>(mask_i64),
+      w_b, B, C, HW, coef, l1, grad_out, static_cast<__nv_bfloat16*>(d_noise_hat), ldd);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
+extern "C" int jg_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr,
+                                 float beta1, float beta2, float eps, float weight_decay, int adamw, int step,
+                                 float grad_scale, float ema_beta, int ema_init, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  JG_CHECK(p && g && m && v && n > 0 && step > 0, JG_ERR_INVALID, "adamw_ema_step: bad args");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  adamw_ema_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay,
+                                                         adamw, bc1, sqrtf(bc2), grad_scale, ema_beta, ema_init);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}

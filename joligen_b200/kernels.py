@@ -36,12 +36,15 @@ def make_conv_desc(x, cout, r, s, stride=1, pad=None, ldy=None, act=L.ACT_NONE, 
 
 
 def pack_conv_weight(w_oihw, want_dgrad=True):
-    """fp32 OIHW -> (bf16 [Cout][RS][Cin8], bf16 [Cin][RS][Cout8] or None)."""
+    """fp32 OIHW -> (bf16 [Cout8][RS][Cin8], bf16 [Cin8][RS][Cout8] or None)."""
     cout, cin, r, s = w_oihw.shape
     w = w_oihw.detach().contiguous().float()
     cin8, cout8 = (cin + 7) // 8 * 8, (cout + 7) // 8 * 8
-    wf = torch.empty((cout, r * s, cin8), dtype=torch.bfloat16, device=w.device)
-    wd = torch.empty((cin, r * s, cout8), dtype=torch.bfloat16, device=w.device) if want_dgrad else None
+    # rows cout..cout8-1 of wf stay zero (the kernels see round_up(Cout, 8) output channels)
+    alloc = torch.zeros if cout8 != cout else torch.empty
+    wf = alloc((cout8, r * s, cin8), dtype=torch.bfloat16, device=w.device)
+    alloc_d = torch.zeros if cin8 != cin else torch.empty
+    wd = alloc_d((cin8, r * s, cout8), dtype=torch.bfloat16, device=w.device) if want_dgrad else None
     L.call("jg_pack_conv_weight", L.ptr(w), L.ptr(wf), L.ptr(wd), cout, cin, r, s, L.stream())
     return wf, wd
 
@@ -116,3 +119,125 @@ def resample2x(x, mode):
     out = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=x.device)
     L.call("jg_resample2x", L.ptr(x), _ld(x), L.ptr(out), c, n, h, w, c, mode, L.stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# GroupNorm (+FiLM)(+SiLU)
+# ---------------------------------------------------------------------------------------------
+def groupnorm_fwd(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5, out=None):
+    """x NHWC bf16.  Returns (y, stats[N,G,2], ab[N,C,2])."""
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x.device)
+    ab = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
+    ws = torch.empty((n * groups * 2,), dtype=torch.float32, device=x.device)
+    L.call("jg_groupnorm_fwd", L.ptr(x), _ld(x), L.ptr(out), _ld(out), n, h * w, c, groups, eps, L.ptr(gamma),
+           L.ptr(beta), L.ptr(film), act, L.ptr(stats), L.ptr(ab), L.ptr(ws), L.stream())
+    return out, stats, ab
+
+
+def groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab, need_param_grads=True, need_film_grad=False,
+                  dx=None, accumulate=False):
+    n, h, w, c = x.shape
+    if dx is None:
+        dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+        accumulate = False
+    dgamma = torch.empty((c,), dtype=torch.float32, device=x.device) if need_param_grads else None
+    dbeta = torch.empty((c,), dtype=torch.float32, device=x.device) if need_param_grads else None
+    dfilm = torch.empty((n, 2 * c), dtype=torch.float32, device=x.device) if need_film_grad else None
+    nws = n * c * 2 + n * c + n * groups * 2 + n * c * 2
+    ws = torch.empty((nws,), dtype=torch.float32, device=x.device)
+    L.call("jg_groupnorm_bwd", L.ptr(x), _ld(x), L.ptr(dy), _ld(dy), L.ptr(dx), _ld(dx), int(accumulate), n, h * w, c,
+           groups, L.ptr(gamma), L.ptr(beta), L.ptr(film), act, L.ptr(stats), L.ptr(ab), L.ptr(dgamma), L.ptr(dbeta),
+           L.ptr(dfilm), L.ptr(ws), L.stream())
+    return dx, dgamma, dbeta, dfilm
+
+
+# ---------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------
+def attn_fwd(qkv, heads, ch):
+    """qkv NHWC [N,H,W,3*heads*ch] (legacy per-head q|k|v interleave). Returns (out [N,H,W,heads*ch], lse)."""
+    n, h, w, _ = qkv.shape
+    t = h * w
+    out = torch.empty((n, h, w, heads * ch), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((n * heads, t), dtype=torch.float32, device=qkv.device)
+    L.call("jg_attn_fwd", L.ptr(qkv), _ld(qkv), L.ptr(out), _ld(out), L.ptr(lse), n, t, heads, ch, L.stream())
+    return out, lse
+
+
+def attn_bwd(qkv, out, d_out, lse, heads, ch):
+    n, h, w, c3 = qkv.shape
+    t = h * w
+    dqkv = torch.empty((n, h, w, c3), dtype=torch.bfloat16, device=qkv.device)
+    ws = torch.empty((n * heads * t,), dtype=torch.float32, device=qkv.device)
+    L.call("jg_attn_bwd", L.ptr(qkv), _ld(qkv), L.ptr(out), _ld(out), L.ptr(d_out), _ld(d_out), L.ptr(lse),
+           L.ptr(dqkv), _ld(dqkv), L.ptr(ws), n, t, heads, ch, L.stream())
+    return dqkv
+
+
+# ---------------------------------------------------------------------------------------------
+# small fp32 linear, prologue, loss, optimiser
+# ---------------------------------------------------------------------------------------------
+def linear_fwd(x, w, b, act_in=L.ACT_NONE, act_out=L.ACT_NONE):
+    bsz, i = x.shape
+    o = w.shape[0]
+    y = torch.empty((bsz, o), dtype=torch.float32, device=x.device)
+    L.call("jg_linear_fwd", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), bsz, i, o, act_in, act_out, L.stream())
+    return y
+
+
+def linear_bwd(x, w, dy, act_in=L.ACT_NONE, need_dx=True):
+    bsz, i = x.shape
+    o = w.shape[0]
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty_like(w)
+    db = torch.empty((o,), dtype=torch.float32, device=x.device)
+    L.call("jg_linear_bwd", L.ptr(x), L.ptr(w), L.ptr(dy), L.ptr(dx), 0, L.ptr(dw), L.ptr(db), bsz, i, o, act_in,
+           L.stream())
+    return dx, dw, db
+
+
+def _mask_ptrs(mask):
+    if mask is None:
+        return 0, 0
+    assert mask.is_contiguous()
+    if mask.dtype == torch.int64:
+        return 0, mask.data_ptr()
+    assert mask.dtype == torch.float32, "mask must be int64 or float32"
+    return mask.data_ptr(), 0
+
+
+def noise_pack(y0, ycond, noise, mask, gammas, ld=8):
+    b, c, h, w = y0.shape
+    out = torch.empty((b, h, w, ld), dtype=torch.bfloat16, device=y0.device)
+    mf, mi = _mask_ptrs(mask)
+    L.call("jg_noise_pack_fwd", L.ptr(y0), L.ptr(ycond), L.ptr(noise), mf, mi, L.ptr(gammas), L.ptr(out), b, c, h, w,
+           ld, L.stream())
+    return out
+
+
+def palette_loss_fwd(noise, noise_hat, mask, w_b, lambda_g=1.0, l1=False):
+    b, c, h, w = noise.shape
+    loss = torch.empty((), dtype=torch.float32, device=noise.device)
+    mf, mi = _mask_ptrs(mask)
+    L.call("jg_palette_loss_fwd", L.ptr(noise), L.ptr(noise_hat), _ld(noise_hat), mf, mi, L.ptr(w_b), b, c, h * w,
+           float(lambda_g), int(l1), L.ptr(loss), L.stream())
+    return loss
+
+
+def palette_loss_bwd(noise, noise_hat, mask, w_b, grad_out, lambda_g=1.0, l1=False):
+    b, c, h, w = noise.shape
+    d = torch.empty(noise_hat.shape, dtype=torch.bfloat16, device=noise.device)
+    mf, mi = _mask_ptrs(mask)
+    L.call("jg_palette_loss_bwd", L.ptr(noise), L.ptr(noise_hat), _ld(noise_hat), mf, mi, L.ptr(w_b), b, c, h * w,
+           float(lambda_g), int(l1), L.ptr(grad_out), L.ptr(d), _ld(d), L.stream())
+    return d
+
+
+def adamw_ema_step(p, g, m, v, ema, lr, beta1, beta2, eps, weight_decay, adamw, step, grad_scale=1.0, ema_beta=0.999,
+                   ema_init=False):
+    L.call("jg_adamw_ema_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), L.ptr(ema), p.numel(), float(lr),
+           float(beta1), float(beta2), float(eps), float(weight_decay), int(adamw), int(step), float(grad_scale),
+           float(ema_beta), int(ema_init), L.stream())

@@ -1,0 +1,452 @@
+"""B200-backed mirrors of the reference's hot-path nn.Modules.
+
+Same constructor arguments, same sub-module names and therefore the same `state_dict` keys as
+
+    models/modules/unet_generator_attn/unet_generator_attn.py  (UNet, ResBlock, AttentionBlock, EmbedSequential)
+    models/modules/unet_generator_attn/unet_attn_utils.py      (GroupNorm wrapper, normalization)
+    models/modules/palette_denoise_fn.py                       (PaletteDenoiseFn)
+    models/modules/diffusion_generator.py                      (DiffusionGenerator)
+
+Parameters live in ordinary nn.Conv2d / nn.GroupNorm / nn.Linear containers (fp32, reference layout);
+their `forward` is never used: the blocks call the sm_100a kernels through joligen_b200.ops on NHWC
+bf16 activations.  `accelerate.accelerate()` swaps a reference-built tree for these classes while
+SHARING the nn.Parameter objects.  There is no CPU path: calling forward without CUDA raises.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+from . import lib as L
+from . import ops
+
+# bumped by anything that rewrites parameters behind torch's back (fused optimizer, load_state_dict)
+_PACK_EPOCH = [0]
+
+
+def invalidate_packed_weights():
+    _PACK_EPOCH[0] += 1
+
+
+class ConvPack:
+    """bf16 implicit-GEMM copies of one conv's fp32 master weight, refreshed when the weight changes."""
+
+    def __init__(self, conv):
+        self.conv = conv
+        self.key = None
+        self.packed = None
+
+    def get(self):
+        w = self.conv.weight
+        b = self.conv.bias
+        key = (w._version, _PACK_EPOCH[0], w.data_ptr(), None if b is None else (b._version, b.data_ptr()))
+        if key != self.key:
+            w4 = w.detach()
+            if w4.dim() == 3:  # Conv1d k=1
+                w4 = w4.unsqueeze(-1)
+            wf, wd = K.pack_conv_weight(w4, want_dgrad=True)
+            bias_p = None
+            if b is not None:
+                cout = b.shape[0]
+                cout8 = (cout + 7) // 8 * 8
+                if cout8 != cout:
+                    bias_p = torch.zeros(cout8, dtype=torch.float32, device=b.device)
+                    bias_p[:cout] = b.detach()
+                else:
+                    bias_p = b.detach()  # aliases the parameter storage: always current
+            self.packed = (wf, wd, bias_p)
+            self.key = key
+        return self.packed
+
+
+def _conv(x, conv, pack, residual=None, res_scale=1.0):
+    w = conv.weight
+    if w.dim() == 3:
+        w = w.unsqueeze(-1)
+    return ops.conv2d(x, w, conv.bias, pack.get(), stride=conv.stride[0], pad=conv.padding[0], residual=residual,
+                      res_scale=res_scale)
+
+
+class GroupNorm(nn.Module):
+    """unet_attn_utils.GroupNorm: holds `self.norm = nn.GroupNorm(groups, channels)` (fp32 statistics)."""
+
+    def __init__(self, group_size, channels):
+        super().__init__()
+        self.norm = nn.GroupNorm(group_size, channels)
+
+    def forward_nhwc(self, x, film=None, act=L.ACT_NONE):
+        return ops.group_norm(x, self.norm.weight, self.norm.bias, self.norm.num_groups, film=film, act=act)
+
+
+def normalization(channels, norm="groupnorm32"):
+    if "groupnorm" in norm:
+        return GroupNorm(int(norm.split("groupnorm")[1]), channels)
+    if norm == "instancenorm":
+        return GroupNorm(channels, channels)
+    if norm == "layernorm":
+        return GroupNorm(1, channels)
+    raise ValueError("%s is not implemented in the B200 UNet (groupnorm / instancenorm / layernorm only)" % norm)
+
+
+class EmbedBlock(nn.Module):
+    pass
+
+
+class EmbedSequential(nn.Sequential, EmbedBlock):
+    def forward_nhwc(self, x, emb):
+        for layer in self:
+            x = layer.forward_nhwc(x, emb) if isinstance(layer, EmbedBlock) else layer.forward_nhwc(x)
+        return x
+
+
+class _Resample(nn.Module):
+    """Upsample / Downsample with use_conv=False (what ResBlock(up=/down=) instantiates)."""
+
+    def __init__(self, up):
+        super().__init__()
+        self.up = up
+
+    def forward_nhwc(self, x):
+        return ops.upsample2x(x) if self.up else ops.avgpool2x(x)
+
+
+class ConvIn(nn.Conv2d):
+    """The first 3x3 conv of the UNet (input_blocks[0][0]), kept as an nn.Conv2d for its state_dict keys."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._pack = ConvPack(self)
+
+    def forward_nhwc(self, x):
+        return _conv(x, self, self._pack)
+
+
+class ResBlock(EmbedBlock):
+    """unet_generator_attn.ResBlock (lines 143-266): GN->SiLU->[up/down]->conv3x3, FiLM GN->SiLU->conv3x3,
+    skip 1x1 conv, residual add fused into the second conv's epilogue."""
+
+    def __init__(self, channels, emb_channels, dropout, norm, out_channel=None, use_conv=False,
+                 use_scale_shift_norm=False, use_checkpoint=False, up=False, down=False, efficient=False,
+                 freq_space=False):
+        super().__init__()
+        if freq_space or use_conv or use_checkpoint:
+            raise NotImplementedError("B200 ResBlock: freq_space / use_conv / use_checkpoint are not supported")
+        if dropout:
+            raise NotImplementedError("B200 ResBlock: dropout > 0 is not supported")
+        self.channels = channels
+        self.emb_channels = emb_channels
+        self.out_channel = out_channel or channels
+        self.use_scale_shift_norm = use_scale_shift_norm
+        self.up, self.down = up, down
+        self.updown = up or down
+        self.efficient = efficient
+        if efficient and up:
+            raise NotImplementedError("B200 ResBlock: efficient up-blocks are not supported")
+        self.in_layers = nn.Sequential(normalization(channels, norm), nn.SiLU(),
+                                       nn.Conv2d(channels, self.out_channel, 3, padding=1))
+        if up or down:
+            self.h_upd = _Resample(up)
+            self.x_upd = _Resample(up)
+        else:
+            self.h_upd = self.x_upd = nn.Identity()
+        self.emb_layers = nn.Sequential(
+            nn.SiLU(), nn.Linear(emb_channels, 2 * self.out_channel if use_scale_shift_norm else self.out_channel))
+        self.out_layers = nn.Sequential(normalization(self.out_channel, norm), nn.SiLU(), nn.Dropout(p=dropout),
+                                        nn.Conv2d(self.out_channel, self.out_channel, 3, padding=1))
+        if self.out_channel == channels:
+            self.skip_connection = nn.Identity()
+        else:
+            self.skip_connection = nn.Conv2d(channels, self.out_channel, 1)
+        self._pack_in = ConvPack(self.in_layers[2])
+        self._pack_out = ConvPack(self.out_layers[3])
+        self._pack_skip = ConvPack(self.skip_connection) if isinstance(self.skip_connection, nn.Conv2d) else None
+
+    def forward_nhwc(self, x, emb):
+        h = self.in_layers[0].forward_nhwc(x, act=L.ACT_SILU)
+        if self.updown:
+            h = self.h_upd.forward_nhwc(h)
+            x = self.x_upd.forward_nhwc(x)
+        h = _conv(h, self.in_layers[2], self._pack_in)
+        lin = self.emb_layers[1]
+        emb_out = ops.linear(emb, lin.weight, lin.bias, act_in=L.ACT_SILU)  # [N, 2C] = (scale | shift)
+        if self.use_scale_shift_norm:
+            h = self.out_layers[0].forward_nhwc(h, film=emb_out, act=L.ACT_SILU)
+        else:
+            # h + emb_out then GN -> SiLU: express the add as FiLM-free shift before the norm
+            raise NotImplementedError("B200 ResBlock: use_scale_shift_norm=False is not supported yet")
+        skipw = 1.0 / math.sqrt(2) if self.efficient else 1.0
+        if self._pack_skip is not None:
+            x = _conv(x, self.skip_connection, self._pack_skip)
+        return _conv(h, self.out_layers[3], self._pack_out, residual=x, res_scale=skipw)
+
+    def forward(self, x, emb):
+        """Drop-in NCHW fp32 signature of the reference block."""
+        y = self.forward_nhwc(ops.to_nhwc(x), emb)
+        return ops.to_nchw(y, self.out_channel)
+
+
+class _NoAffineInstanceNorm1d(nn.Module):
+    """normalization1d(): InstanceNorm1d over T without affine (no parameters, unet_attn_utils.py:60-66)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.channels = channels
+
+
+class AttentionBlock(nn.Module):
+    """unet_generator_attn.AttentionBlock (lines 269-319) with QKVAttentionLegacy."""
+
+    def __init__(self, channels, num_heads=1, num_head_channels=-1, use_checkpoint=False,
+                 use_new_attention_order=False, use_transformer=False):
+        super().__init__()
+        if use_new_attention_order or use_transformer or use_checkpoint:
+            raise NotImplementedError("B200 AttentionBlock: only the legacy attention order is supported")
+        self.channels = channels
+        if num_head_channels == -1:
+            self.num_heads = num_heads
+        else:
+            assert channels % num_head_channels == 0
+            self.num_heads = channels // num_head_channels
+        self.norm = _NoAffineInstanceNorm1d(channels)
+        self.qkv = nn.Conv1d(channels, channels * 3, 1)
+        self.proj_out = nn.Conv1d(channels, channels, 1)
+        self._pack_qkv = ConvPack(self.qkv)
+        self._pack_proj = ConvPack(self.proj_out)
+
+    def forward_nhwc(self, x):
+        c = self.channels
+        xn = ops.group_norm(x, None, None, c, film=None, act=L.ACT_NONE)  # per-(n, c) statistics over T
+        qkv = _conv(xn, self.qkv, self._pack_qkv)
+        a = ops.attention(qkv, self.num_heads, c // self.num_heads)
+        return _conv(a, self.proj_out, self._pack_proj, residual=x, res_scale=1.0)
+
+    def forward(self, x):
+        y = self.forward_nhwc(ops.to_nhwc(x))
+        return ops.to_nchw(y, self.channels)
+
+
+class _OutHead(nn.Sequential):
+    pass
+
+
+class UNet(nn.Module):
+    """unet_generator_attn.UNet (lines 390-705), same constructor; forward(input NCHW fp32, embed_gammas)."""
+
+    def __init__(self, image_size, in_channel, inner_channel, out_channel, res_blocks, attn_res, tanh,
+                 n_timestep_train, n_timestep_test, norm, group_norm_size, cond_embed_dim, dropout=0,
+                 channel_mults=(1, 2, 4, 8), conv_resample=True, use_checkpoint=False, use_fp16=False, num_heads=1,
+                 num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=True, resblock_updown=True,
+                 use_new_attention_order=False, efficient=False, freq_space=False):
+        super().__init__()
+        if tanh or freq_space or not resblock_updown or use_fp16:
+            raise NotImplementedError("B200 UNet: tanh / freq_space / conv resampling / fp16 are not supported")
+        if num_heads_upsample == -1:
+            num_heads_upsample = num_heads
+        self.image_size = image_size
+        self.in_channel = in_channel
+        self.inner_channel = inner_channel
+        self.out_channel = out_channel
+        self.res_blocks = res_blocks
+        self.attn_res = attn_res
+        self.channel_mults = channel_mults
+        self.num_heads = num_heads
+        self.num_head_channels = num_head_channels
+        self.cond_embed_dim = cond_embed_dim
+        if norm == "groupnorm":
+            norm = norm + str(group_norm_size)
+        rb = dict(use_scale_shift_norm=use_scale_shift_norm, norm=norm, efficient=efficient)
+        ch = input_ch = int(channel_mults[0] * inner_channel)
+        self.input_blocks = nn.ModuleList([EmbedSequential(ConvIn(in_channel, ch, 3, padding=1))])
+        input_block_chans = [ch]
+        ds = 1
+        for level, mult in enumerate(channel_mults):
+            for _ in range(res_blocks[level]):
+                layers = [ResBlock(ch, cond_embed_dim, 0.0, out_channel=int(mult * inner_channel), **rb)]
+                ch = int(mult * inner_channel)
+                if ds in attn_res:
+                    layers.append(AttentionBlock(ch, num_heads=num_heads, num_head_channels=num_head_channels))
+                self.input_blocks.append(EmbedSequential(*layers))
+                input_block_chans.append(ch)
+            if level != len(channel_mults) - 1:
+                self.input_blocks.append(
+                    EmbedSequential(ResBlock(ch, cond_embed_dim, 0.0, out_channel=ch, down=True, **rb)))
+                input_block_chans.append(ch)
+                ds *= 2
+        self.middle_block = EmbedSequential(
+            ResBlock(ch, cond_embed_dim, dropout, **rb),
+            AttentionBlock(ch, num_heads=num_heads, num_head_channels=num_head_channels),
+            ResBlock(ch, cond_embed_dim, dropout, **rb))
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mults))[::-1]:
+            for i in range(res_blocks[level] + 1):
+                ich = input_block_chans.pop()
+                layers = [ResBlock(ch + ich, cond_embed_dim, 0.0, out_channel=int(inner_channel * mult), **rb)]
+                ch = int(inner_channel * mult)
+                if ds in attn_res:
+                    layers.append(AttentionBlock(ch, num_heads=num_heads_upsample,
+                                                 num_head_channels=num_head_channels))
+                if level and i == res_blocks[level]:
+                    layers.append(ResBlock(ch, cond_embed_dim, 0.0, out_channel=ch, up=True, **rb))
+                    ds //= 2
+                self.output_blocks.append(EmbedSequential(*layers))
+        self.out = _OutHead(normalization(ch, norm), nn.SiLU(), nn.Conv2d(input_ch, out_channel, 3, padding=1))
+        self._pack_outconv = ConvPack(self.out[2])
+        self.beta_schedule = {
+            "train": {"schedule": "linear", "n_timestep": n_timestep_train, "linear_start": 1e-6,
+                      "linear_end": 0.01},
+            "test": {"schedule": "linear", "n_timestep": n_timestep_test, "linear_start": 1e-4, "linear_end": 0.09},
+        }
+
+    # -- NHWC bf16 fast path -------------------------------------------------------------------
+    def forward_nhwc(self, x, emb):
+        """x: NHWC bf16 [N,H,W,round_up(in_channel,8)] -> NHWC bf16 [N,H,W,round_up(out_channel,8)]."""
+        hs = []
+        h = x
+        for module in self.input_blocks:
+            h = module.forward_nhwc(h, emb)
+            hs.append(h)
+        h = self.middle_block.forward_nhwc(h, emb)
+        for module in self.output_blocks:
+            h = ops.cat_channels(h, hs.pop())
+            h = module.forward_nhwc(h, emb)
+        h = self.out[0].forward_nhwc(h, act=L.ACT_SILU)
+        return _conv(h, self.out[2], self._pack_outconv)
+
+    def forward(self, input, embed_gammas=None):
+        if embed_gammas is None:
+            embed_gammas = torch.ones((input.shape[0], self.cond_embed_dim), device=input.device)
+        y = self.forward_nhwc(ops.to_nhwc(input), embed_gammas)
+        return ops.to_nchw(y, self.out_channel)
+
+
+def set_new_noise_schedule(model, phase):
+    """diffusion_utils.set_new_noise_schedule (lines 79-119), linear schedule only: registers the same 7
+    buffers per phase on `model` so that state_dict keys match the reference."""
+    sched = model.beta_schedule[phase]
+    assert sched["schedule"] == "linear"
+    betas = np.linspace(sched["linear_start"], sched["linear_end"], sched["n_timestep"], dtype=np.float64)
+    alphas = 1.0 - betas
+    setattr(model, "num_timesteps_" + phase, int(betas.shape[0]))
+    gammas = np.cumprod(alphas, axis=0)
+    gammas_prev = np.append(1.0, gammas[:-1])
+    param = next(model.parameters(), None)
+    device = param.device if param is not None else torch.device("cpu")
+    t = lambda a: torch.tensor(a, dtype=torch.float32, device=device)
+    model.register_buffer("gammas_" + phase, t(gammas))
+    model.register_buffer("gammas_prev_" + phase, t(gammas_prev))
+    model.register_buffer("sqrt_recip_gammas_" + phase, t(np.sqrt(1.0 / gammas)))
+    model.register_buffer("sqrt_recipm1_gammas_" + phase, t(np.sqrt(1.0 / gammas - 1)))
+    posterior_variance = betas * (1.0 - gammas_prev) / (1.0 - gammas)
+    model.register_buffer("posterior_log_variance_clipped_" + phase, t(np.log(np.maximum(posterior_variance, 1e-20))))
+    model.register_buffer("posterior_mean_coef1_" + phase, t(betas * np.sqrt(gammas_prev) / (1.0 - gammas)))
+    model.register_buffer("posterior_mean_coef2_" + phase, t((1.0 - gammas_prev) * np.sqrt(alphas) / (1.0 - gammas)))
+
+
+def gamma_embedding(gammas, dim, max_period=10000):
+    """diffusion_utils.gamma_embedding for [B,1] gammas (host-side O(B) work, stays in torch)."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(gammas.device)
+    args = gammas[:, 0:1].float() * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+    return emb
+
+
+class PaletteDenoiseFn(nn.Module):
+    """palette_denoise_fn.PaletteDenoiseFn restricted to conditioning == "" (no class / mask / ref embedding)."""
+
+    def __init__(self, model, cond_embed_dim, ref_embed_net="", conditioning="", nclasses=2):
+        super().__init__()
+        if conditioning:
+            raise NotImplementedError("B200 PaletteDenoiseFn: conditioning %r is not supported yet" % conditioning)
+        self.model = model
+        self.cond_embed_dim = cond_embed_dim
+        self.conditioning = conditioning
+
+    def forward(self, input, embed_noise_level, cls=None, mask=None, ref=None):
+        return self.model(input, embed_noise_level)
+
+
+class DiffusionGenerator(nn.Module):
+    """diffusion_generator.DiffusionGenerator: training forward (lines 457-528) on the B200 kernels."""
+
+    def __init__(self, denoise_fn, sampling_method="ddpm", image_size=256, G_ngf=64,
+                 loading_backward_compatibility=False):
+        super().__init__()
+        if loading_backward_compatibility:
+            raise NotImplementedError("B200 DiffusionGenerator: backward-compatibility embedding is not supported")
+        self.denoise_fn = denoise_fn
+        self.sampling_method = sampling_method
+        self.image_size = image_size
+        set_new_noise_schedule(self.denoise_fn.model, "train")
+        set_new_noise_schedule(self.denoise_fn.model, "test")
+        e = self.denoise_fn.cond_embed_dim
+        self.cond_embed_dim = e
+        self.cond_embed_gammas = e
+        self.cond_embed_gammas_in = e
+        self.cond_embed = nn.Sequential(nn.Linear(e, e), nn.SiLU(), nn.Linear(e, e))
+
+    def compute_gammas(self, gammas):
+        emb = gamma_embedding(gammas, self.cond_embed_gammas_in)
+        emb = ops.linear(emb, self.cond_embed[0].weight, self.cond_embed[0].bias)
+        return ops.linear(emb, self.cond_embed[2].weight, self.cond_embed[2].bias, act_in=L.ACT_SILU)
+
+    def sample_noise_level(self, b, device, t=None, u=None):
+        """t ~ randint(1, T), gamma ~ U(gamma_{t-1}, gamma_t) (lines 467-478).  Index gathers are bit exact."""
+        model = self.denoise_fn.model
+        if t is None:
+            t = torch.randint(1, model.num_timesteps_train, (b,), device=device).long()
+        if u is None:
+            u = torch.rand((b, 1), device=device)
+        gammas = model.gammas_train
+        g1 = gammas.gather(-1, t - 1).reshape(b, 1)
+        g2 = gammas.gather(-1, t).reshape(b, 1)
+        sample_gammas = ((g2 - g1) * u + g1).view(b, -1)
+        snr1 = model.sqrt_recip_gammas_train.gather(-1, t)
+        snr2 = model.sqrt_recipm1_gammas_train.gather(-1, t)
+        snr = torch.pow(snr1 / snr2, 2)
+        w = torch.stack([snr, 5.0 * torch.ones_like(t)], dim=1).min(dim=1)[0] / snr
+        return t, sample_gammas, w
+
+    def forward_nhwc(self, y_0, y_cond, mask, noise, t=None, u=None):
+        """Returns (noise, noise_hat NHWC bf16 [B,H,W,8], min_snr_w [B])."""
+        b = y_0.shape[0]
+        if noise is None:
+            noise = torch.randn_like(y_0)
+        _, sample_gammas, w = self.sample_noise_level(b, y_0.device, t, u)
+        emb = self.compute_gammas(sample_gammas)
+        x = K.noise_pack(y_0.contiguous().float(), y_cond.contiguous().float(), noise.contiguous().float(),
+                         None if mask is None else mask.contiguous(), sample_gammas.reshape(b).contiguous(),
+                         ld=(2 * y_0.shape[1] + 7) // 8 * 8)
+        noise_hat = self.denoise_fn.model.forward_nhwc(x, emb)
+        return noise, noise_hat, w
+
+    def forward(self, y_0, y_cond, mask, noise, cls=None, ref=None, dropout_prob=0.0, t=None, u=None):
+        if y_0.dim() != 4:
+            raise NotImplementedError("B200 DiffusionGenerator: video (5-D) inputs are not supported yet")
+        noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u)
+        return noise, ops.to_nchw(noise_hat, y_0.shape[1]), w.view(-1, 1, 1, 1)
+
+    def forward_loss(self, y_0, y_cond, mask, noise=None, lambda_G=1.0, use_minsnr=False, l1=False, t=None, u=None):
+        """compute_palette_loss fused: the UNet output stays NHWC bf16 and feeds the eps-loss kernel directly."""
+        noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u)
+        return ops.palette_loss(noise_hat, noise.contiguous().float(), None if mask is None else mask.contiguous(),
+                                w.contiguous() if use_minsnr else None, lambda_G, l1)
+
+
+def build_palette_generator(image_size=256, in_channel=6, inner_channel=64, out_channel=3, res_blocks=(2, 2, 2, 2),
+                            attn_res=(16,), channel_mults=(1, 2, 4, 8), num_heads=1, num_head_channels=32,
+                            group_norm_size=32, cond_embed_dim=32, n_timestep_train=2000, n_timestep_test=1000,
+                            efficient=False):
+    """What diffusion_networks.define_G(model_type="palette", G_netG="unet_mha", ...) builds
+    (models/diffusion_networks.py:114-139, 361-376), on the B200 modules."""
+    unet = UNet(image_size=image_size, in_channel=in_channel, inner_channel=inner_channel, out_channel=out_channel,
+                res_blocks=list(res_blocks), attn_res=list(attn_res), tanh=False, n_timestep_train=n_timestep_train,
+                n_timestep_test=n_timestep_test, norm="groupnorm", group_norm_size=group_norm_size,
+                cond_embed_dim=cond_embed_dim, channel_mults=tuple(channel_mults), num_heads=num_heads,
+                num_head_channels=num_head_channels, efficient=efficient)
+    dn = PaletteDenoiseFn(model=unet, cond_embed_dim=cond_embed_dim, conditioning="")
+    return DiffusionGenerator(denoise_fn=dn, sampling_method="ddpm", image_size=image_size, G_ngf=inner_channel)

@@ -1,0 +1,232 @@
+"""torch.autograd.Function wrappers: each op's forward AND backward run in libjg_b200.so.
+
+All feature-map tensors are NHWC bf16.  Parameter gradients are returned in the reference layout
+(fp32 OIHW / [C]) so that `.grad`, DDP, `state_dict` and optimisers see what joliGEN expects.
+"""
+import torch
+
+from . import kernels as K
+from . import lib as L
+
+
+def _needs(ctx, i):
+    return ctx.needs_input_grad[i]
+
+
+class Conv2dFn(torch.autograd.Function):
+    """y = conv(x, W) + b (+ res_scale*residual).  x NHWC bf16 with channels padded to a multiple of 8;
+    W fp32 OIHW (its bf16 packed copies wf / wd and the 8-padded bias are passed in).  The output has
+    round_up(Cout, 8) channels (padding channels are exactly zero)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, wf, wd, bias_p, stride, pad, res_scale):
+        cout, cin, r, s = weight.shape
+        cout8 = (cout + 7) // 8 * 8
+        y = K.conv2d_fwd(x, wf, bias_p, cout8, r, s, stride=stride, pad=pad, residual=residual, res_scale=res_scale)
+        ctx.save_for_backward(x, wd)
+        ctx.geom = (cout, cin, r, s, stride, pad, res_scale, bias is not None, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wd = ctx.saved_tensors
+        cout, cin, r, s, stride, pad, res_scale, has_bias, has_res = ctx.geom
+        cout8 = (cout + 7) // 8 * 8
+        dy = dy.contiguous()
+        dx = dw = db = dres = None
+        if _needs(ctx, 0):
+            if stride != 1:
+                raise RuntimeError("Conv2dFn: dgrad for stride %d is not implemented" % stride)
+            dx = K.conv2d_fwd(dy, wd, None, x.shape[-1], r, s, stride=1, pad=r - 1 - pad)
+        if _needs(ctx, 1):
+            dw = K.conv2d_wgrad(x, dy, cout8, r, s, stride=stride, pad=pad)
+            if dw.shape[0] != cout or dw.shape[1] != cin:  # zero-padded channels (e.g. 6 -> 8, 3 -> 8)
+                dw = dw[:cout, :cin].contiguous()
+        if has_bias and _needs(ctx, 2):
+            db = K.bias_grad(dy)
+            if cout8 != cout:
+                db = db[:cout].contiguous()
+        if has_res and _needs(ctx, 3):
+            dres = dy if res_scale == 1.0 else (dy.float() * res_scale).to(torch.bfloat16)
+        return dx, dw, db, dres, None, None, None, None, None, None
+
+
+class GroupNormFn(torch.autograd.Function):
+    """y = act(GN(x; gamma, beta) * (1 + scale) + shift), film = [N, 2C] fp32 (scale | shift) or None."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, film, groups, act):
+        y, stats, ab = K.groupnorm_fwd(x, gamma, beta, groups, film=film, act=act)
+        ctx.save_for_backward(x, gamma, beta, film, stats, ab)
+        ctx.cfg = (groups, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, film, stats, ab = ctx.saved_tensors
+        groups, act = ctx.cfg
+        dy = dy.contiguous()
+        need_p = gamma is not None and (_needs(ctx, 1) or _needs(ctx, 2))
+        need_f = film is not None and _needs(ctx, 3)
+        dx, dgamma, dbeta, dfilm = K.groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab,
+                                                   need_param_grads=need_p, need_film_grad=need_f)
+        return dx, dgamma, dbeta, dfilm, None, None
+
+
+class AttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, heads, ch):
+        out, lse = K.attn_fwd(qkv, heads, ch)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.cfg = (heads, ch)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkv, out, lse = ctx.saved_tensors
+        heads, ch = ctx.cfg
+        return K.attn_bwd(qkv, out, d_out.contiguous(), lse, heads, ch), None, None
+
+
+class LinearFn(torch.autograd.Function):
+    """fp32 y = act_out(act_in(x) @ W^T + b) on [B, I] embeddings (act_out only without grad)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act_in):
+        x = x.contiguous().float()
+        y = K.linear_fwd(x, weight, bias, act_in=act_in)
+        ctx.save_for_backward(x, weight)
+        ctx.act_in = act_in
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dx, dw, db = K.linear_bwd(x, weight, dy.contiguous().float(), act_in=ctx.act_in, need_dx=_needs(ctx, 0))
+        return dx, dw, db, None
+
+
+class Resample2xFn(torch.autograd.Function):
+    """mode 0: nearest 2x upsample; mode 1: 2x2 average pool."""
+
+    @staticmethod
+    def forward(ctx, x, mode):
+        ctx.mode = mode
+        return K.resample2x(x, mode)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.resample2x(dy.contiguous(), 2 if ctx.mode == 0 else 3), None
+
+
+class CatChannelsFn(torch.autograd.Function):
+    """torch.cat([a, b], dim=channel) for NHWC tensors."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        n, h, w, ca = a.shape
+        cb = b.shape[-1]
+        out = torch.empty((n, h, w, ca + cb), dtype=torch.bfloat16, device=a.device)
+        K.copy_channels(a, out[..., :ca])
+        K.copy_channels(b, out[..., ca:])
+        ctx.split = (ca, cb)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        ca, cb = ctx.split
+        n, h, w, _ = d.shape
+        da = torch.empty((n, h, w, ca), dtype=torch.bfloat16, device=d.device)
+        db = torch.empty((n, h, w, cb), dtype=torch.bfloat16, device=d.device)
+        K.copy_channels(d[..., :ca], da)
+        K.copy_channels(d[..., ca:], db)
+        return da, db
+
+
+class ToNHWCFn(torch.autograd.Function):
+    """fp32 NCHW -> bf16 NHWC (channels zero-padded to a multiple of 8)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.c = x.shape[1]
+        return K.nchw_to_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, d):
+        return K.nhwc_to_nchw(d.contiguous(), ctx.c)
+
+
+class ToNCHWFn(torch.autograd.Function):
+    """bf16 NHWC -> fp32 NCHW, keeping the first c channels."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.ld = x.shape[-1]
+        return K.nhwc_to_nchw(x, c)
+
+    @staticmethod
+    def backward(ctx, d):
+        return K.nchw_to_nhwc(d, ctx.ld), None
+
+
+class PaletteLossFn(torch.autograd.Function):
+    """lambda * mean((w*m*(noise - noise_hat))^2) with noise_hat NHWC bf16 (only it receives a gradient)."""
+
+    @staticmethod
+    def forward(ctx, noise_hat, noise, mask, w_b, lambda_g, l1):
+        loss = K.palette_loss_fwd(noise, noise_hat, mask, w_b, lambda_g, l1)
+        ctx.save_for_backward(noise_hat, noise, mask, w_b)
+        ctx.cfg = (lambda_g, l1)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        noise_hat, noise, mask, w_b = ctx.saved_tensors
+        lambda_g, l1 = ctx.cfg
+        g = g.contiguous().float()
+        return K.palette_loss_bwd(noise, noise_hat, mask, w_b, g, lambda_g, l1), None, None, None, None, None
+
+
+def conv2d(x, weight, bias, packed, stride=1, pad=None, residual=None, res_scale=1.0):
+    """packed = (wf, wd, bias_padded) from nets.ConvPack.get()."""
+    r = weight.shape[2]
+    if pad is None:
+        pad = (r - 1) // 2
+    wf, wd, bias_p = packed
+    return Conv2dFn.apply(x, weight, bias, residual, wf, wd, bias_p, stride, pad, res_scale)
+
+
+def group_norm(x, gamma, beta, groups, film=None, act=L.ACT_NONE):
+    return GroupNormFn.apply(x, gamma, beta, film, groups, act)
+
+
+def attention(qkv, heads, ch):
+    return AttentionFn.apply(qkv, heads, ch)
+
+
+def linear(x, weight, bias, act_in=L.ACT_NONE):
+    return LinearFn.apply(x, weight, bias, act_in)
+
+
+def upsample2x(x):
+    return Resample2xFn.apply(x, 0)
+
+
+def avgpool2x(x):
+    return Resample2xFn.apply(x, 1)
+
+
+def cat_channels(a, b):
+    return CatChannelsFn.apply(a, b)
+
+
+def to_nhwc(x):
+    return ToNHWCFn.apply(x)
+
+
+def to_nchw(x, c):
+    return ToNCHWFn.apply(x, c)
+
+
+def palette_loss(noise_hat, noise, mask, w_b=None, lambda_g=1.0, l1=False):
+    return PaletteLossFn.apply(noise_hat, noise, mask, w_b, lambda_g, l1)

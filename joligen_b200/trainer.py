@@ -1,0 +1,131 @@
+"""Palette training inner loop on the B200 kernels.
+
+Mirrors the part of joliGEN that runs every iteration (train.py:268-282):
+
+    model.set_input(data)            palette_model.py:287-556   (device placement of A / B / mask)
+    model.optimize_parameters()      base_model.py:1302-1377    (group loop: compute_palette_loss ->
+                                     backward -> compute_step (optimizer) -> ema_step)
+
+with the same attribute names (`netG_A`, `loss_G_tot`, `optimizer_G` semantics) but:
+  * parameters, gradients, Adam moments and the EMA copy live in FLAT fp32 buffers (the nn.Parameters
+    are views), so the gradient all-reduce is one NCCL call and Adam(W)+EMA is one kernel launch;
+  * the eps-loss consumes the UNet's NHWC bf16 output directly.
+Data parallelism = one process per GPU, batch sharded by the caller, SUM all-reduce of the flat
+gradient scaled by 1/world inside the optimizer kernel (DDP's mean, base_model.py:725-737).
+"""
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+from . import nets
+
+
+class FlatParams:
+    """Re-point every parameter of `module` at a slice of one flat fp32 buffer (same for .grad)."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters()]
+        self.names = [n for n, _ in module.named_parameters()]
+        # 64-element (256 B) aligned slices keep every tensor 16-byte aligned for vector / TMA access
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 63) // 64 * 64
+        self.total = off
+        dev = self.params[0].device
+        self.data = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, self.offsets):
+            n = p.numel()
+            self.data[o:o + n].copy_(p.detach().reshape(-1).float())
+            p.data = self.data[o:o + n].view(p.shape)
+            p.grad = self.grad[o:o + n].view(p.shape)
+        nets.invalidate_packed_weights()
+
+    def rebind_grads(self):
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def unflatten(self, flat):
+        return {n: flat[o:o + p.numel()].view(p.shape) for n, p, o in zip(self.names, self.params, self.offsets)}
+
+
+class PaletteTrainer:
+    def __init__(self, netG_A, lr=2e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, optim="adamw",
+                 ema=True, ema_beta=0.999, iter_size=1, lambda_G=1.0, use_minsnr=False, loss="MSE",
+                 device=None, process_group=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("joligen_b200.PaletteTrainer needs a CUDA device (there is no CPU path)")
+        self.device = torch.device(device if device is not None else "cuda")
+        self.netG_A = netG_A.to(self.device)
+        self.flat = FlatParams(self.netG_A)
+        self.exp_avg = torch.zeros_like(self.flat.data)
+        self.exp_avg_sq = torch.zeros_like(self.flat.data)
+        self.ema = torch.zeros_like(self.flat.data) if ema else None
+        self.ema_started = False
+        self.hp = dict(lr=lr, beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay, adamw=(optim == "adamw"))
+        if optim not in ("adamw", "adam"):
+            raise NotImplementedError("optimizer %r (adam / adamw are implemented)" % optim)
+        self.ema_beta = ema_beta
+        self.iter_size = iter_size
+        self.lambda_G = lambda_G
+        self.use_minsnr = use_minsnr
+        self.l1 = (loss == "L1")
+        if loss not in ("MSE", "L1"):
+            raise NotImplementedError("alg_palette_loss %r" % loss)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.niter = 0
+        self.step = 0
+        self.loss_G_tot = None
+        self.gpu_launch_estimate = 0
+
+    # -- data -----------------------------------------------------------------------------------
+    def set_input(self, data, non_blocking=True):
+        """data: {"A": cond image y_t, "B": ground truth, "B_label_mask": int64/float mask [B,1,H,W]}"""
+        self.y_t = data["A"].to(self.device, non_blocking=non_blocking)
+        self.gt_image = data["B"].to(self.device, non_blocking=non_blocking)
+        m = data.get("B_label_mask")
+        self.mask = None if m is None else m.to(self.device, non_blocking=non_blocking)
+        self.cond_image = self.y_t
+
+    def broadcast_parameters(self):
+        if self.world > 1:
+            dist.broadcast(self.flat.data, src=0, group=self.pg)
+            nets.invalidate_packed_weights()
+
+    # -- step -----------------------------------------------------------------------------------
+    def compute_palette_loss(self, noise=None, t=None, u=None):
+        self.loss_G_tot = self.netG_A.forward_loss(self.gt_image, self.cond_image, self.mask, noise=noise,
+                                                   lambda_G=self.lambda_G, use_minsnr=self.use_minsnr, l1=self.l1,
+                                                   t=t, u=u)
+        return self.loss_G_tot
+
+    def optimize_parameters(self, noise=None, t=None, u=None):
+        self.niter += 1
+        self.flat.rebind_grads()
+        loss = self.compute_palette_loss(noise=noise, t=t, u=u)
+        (loss / self.iter_size).backward()
+        if self.niter % self.iter_size == 0:
+            if self.world > 1:
+                dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            self.step += 1
+            K.adamw_ema_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.ema,
+                             step=self.step, grad_scale=1.0 / self.world, ema_beta=self.ema_beta,
+                             ema_init=not self.ema_started, **self.hp)
+            self.ema_started = True
+            self.flat.grad.zero_()
+            nets.invalidate_packed_weights()
+        return loss
+
+    # -- state ----------------------------------------------------------------------------------
+    def ema_state_dict(self):
+        """state_dict of netG_A_ema (base_model.py:1284-1297) — parameters from the flat EMA buffer,
+        buffers copied from the live net."""
+        sd = {k: v.clone() for k, v in self.netG_A.state_dict().items()}
+        if self.ema is not None and self.ema_started:
+            for k, v in self.flat.unflatten(self.ema).items():
+                sd[k] = v.clone()
+        return sd

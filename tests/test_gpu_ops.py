@@ -1,0 +1,240 @@
+"""GPU parity of each sm_100a kernel against the CPU oracle's arithmetic (plain fp32 torch ops on the
+same bf16-rounded operands).  Tolerances: bf16 storage => 1e-2 relative to the tensor's max (north star:
+"1e-2 bf16"); fp32 paths (weight gradients, small linears, loss) 1e-3; index / mask handling bit exact.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from joligen_b200 import kernels
+    from joligen_b200 import lib
+    assert lib.load().jg_check_device() == 0, lib.load().jg_last_error()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return kernels
+
+
+def rel(a, b):
+    return float((a.float().cpu() - b.float().cpu()).abs().max()) / (float(b.abs().max()) + 1e-12)
+
+
+def bf16_round(x):
+    return x.to(torch.bfloat16).float()
+
+
+def to_dev_nhwc(K, x_nchw_cpu):
+    return K.nchw_to_nhwc(x_nchw_cpu.cuda())
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, pad
+    (2, 16, 16, 64, 64, 3, 1),
+    (2, 32, 32, 128, 256, 3, 1),
+    (1, 32, 32, 192, 64, 3, 1),
+    (2, 16, 16, 384, 128, 1, 0),
+    (2, 32, 32, 6, 64, 3, 1),     # first UNet conv: 6 input channels, zero-padded to 8
+    (2, 32, 32, 64, 3, 3, 1),     # last UNet conv: 3 output channels, padded to 8
+    (3, 8, 8, 512, 512, 3, 1),    # several images per M tile
+    (1, 30, 30, 64, 128, 4, 1),   # ragged tiles (NLayerDiscriminator stride-1 layers)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(K, case):
+    n, h, w, cin, cout, k, pad = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    b = 0.1 * torch.randn(cout, generator=g)
+    wb = bf16_round(wt)
+    xr = x.clone().requires_grad_(True)
+    wr = wb.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, br, padding=pad)
+    dy = bf16_round(torch.randn(ref.shape, generator=g))
+    ref.backward(dy)
+
+    cout8 = (cout + 7) // 8 * 8
+    x_d = to_dev_nhwc(K, x)
+    wf, wd = K.pack_conv_weight(wt.cuda())
+    bias_p = torch.zeros(cout8, device="cuda")
+    bias_p[:cout] = b.cuda()
+    y = K.conv2d_fwd(x_d, wf, bias_p, cout8, k, k, pad=pad)
+    assert rel(K.nhwc_to_nchw(y, cout), ref.detach()) < 1e-2
+    if cout8 != cout:
+        assert float(y[..., cout:].float().abs().max()) == 0.0  # padding channels are exactly zero
+    dy_d = to_dev_nhwc(K, dy)
+    dx = K.conv2d_fwd(dy_d, wd, None, x_d.shape[-1], k, k, pad=k - 1 - pad)
+    assert rel(K.nhwc_to_nchw(dx, cin), xr.grad) < 1e-2
+    dw = K.conv2d_wgrad(x_d, dy_d, cout8, k, k, pad=pad)[:cout, :cin]
+    assert rel(dw, wr.grad) < 1e-3
+    db = K.bias_grad(dy_d)[:cout]
+    assert rel(db, br.grad) < 1e-3
+
+
+def test_conv_residual_epilogue_and_stride2(K):
+    g = torch.Generator().manual_seed(5)
+    x = bf16_round(torch.randn(2, 64, 32, 32, generator=g))
+    wt = torch.randn(128, 64, 3, 3, generator=g) / 24.0
+    r = bf16_round(torch.randn(2, 128, 32, 32, generator=g))
+    wf, _ = K.pack_conv_weight(wt.cuda())
+    y = K.conv2d_fwd(to_dev_nhwc(K, x), wf, None, 128, 3, 3, pad=1, residual=to_dev_nhwc(K, r),
+                     res_scale=1.0 / math.sqrt(2))
+    ref = F.conv2d(x, bf16_round(wt), padding=1) + r / math.sqrt(2)
+    assert rel(K.nhwc_to_nchw(y), ref) < 1e-2
+    y2 = K.conv2d_fwd(to_dev_nhwc(K, x), wf, None, 128, 3, 3, stride=2, pad=1)
+    assert rel(K.nhwc_to_nchw(y2), F.conv2d(x, bf16_round(wt), stride=2, padding=1)) < 1e-2
+
+
+GN_CASES = [
+    # n, hw, c, groups, film, silu
+    (2, 16, 64, 32, False, True),
+    (2, 16, 192, 32, True, True),    # 6 channels per group: groups straddle 8-channel vectors
+    (3, 8, 512, 32, True, True),
+    (2, 16, 128, 128, False, False),  # attention InstanceNorm1d: one group per channel, no affine
+    (1, 32, 1024, 32, True, True),
+]
+
+
+@pytest.mark.parametrize("case", GN_CASES)
+def test_groupnorm_film_silu_fwd_bwd(K, case):
+    n, hw, c, groups, use_film, silu = case
+    from joligen_b200 import lib as L
+    g = torch.Generator().manual_seed(c + groups)
+    x = bf16_round(torch.randn(n, c, hw, hw, generator=g) * 1.5 + 0.3)
+    affine = groups != c
+    gamma = (1 + 0.2 * torch.randn(c, generator=g)) if affine else None
+    beta = (0.1 * torch.randn(c, generator=g)) if affine else None
+    film = 0.3 * torch.randn(n, 2 * c, generator=g) if use_film else None
+    xr = x.clone().requires_grad_(True)
+    gr = gamma.clone().requires_grad_(True) if affine else None
+    br = beta.clone().requires_grad_(True) if affine else None
+    fr = film.clone().requires_grad_(True) if use_film else None
+    h = F.group_norm(xr, groups, gr, br, eps=1e-5)
+    if use_film:
+        scale, shift = torch.chunk(fr[:, :, None, None], 2, dim=1)
+        h = h * (1 + scale) + shift
+    ref = F.silu(h) if silu else h
+    dy = bf16_round(torch.randn(ref.shape, generator=g))
+    ref.backward(dy)
+
+    act = L.ACT_SILU if silu else L.ACT_NONE
+    dev = lambda t: None if t is None else t.cuda()
+    x_d = to_dev_nhwc(K, x)
+    y, stats, ab = K.groupnorm_fwd(x_d, dev(gamma), dev(beta), groups, film=dev(film), act=act)
+    assert rel(K.nhwc_to_nchw(y), ref.detach()) < 1e-2
+    dx, dgamma, dbeta, dfilm = K.groupnorm_bwd(x_d, to_dev_nhwc(K, dy), dev(gamma), dev(beta), groups, dev(film), act,
+                                               stats, ab, need_param_grads=affine, need_film_grad=use_film)
+    assert rel(K.nhwc_to_nchw(dx), xr.grad) < 1e-2
+    if affine:
+        assert rel(dgamma, gr.grad) < 2e-3
+        assert rel(dbeta, br.grad) < 2e-3
+    if use_film:
+        assert rel(dfilm, fr.grad) < 2e-3
+
+
+@pytest.mark.parametrize("case", [(2, 256, 4, 16), (2, 64, 16, 32), (1, 1024, 2, 32), (1, 128, 2, 64)])
+def test_attention_fwd_bwd(K, case):
+    from oracle.palette_oracle import qkv_attention_legacy
+    n, t, heads, ch = case
+    c = heads * ch
+    g = torch.Generator().manual_seed(t + ch)
+    side = int(math.isqrt(t))
+    hh, ww = (side, side) if side * side == t else (t // 8, 8)
+    qkv = bf16_round(torch.randn(n, 3 * c, t, generator=g))
+    qr = qkv.clone().requires_grad_(True)
+    ref = qkv_attention_legacy(qr, heads)  # [n, c, t]
+    do = bf16_round(torch.randn(ref.shape, generator=g))
+    ref.backward(do)
+    qkv_d = K.nchw_to_nhwc(qkv.reshape(n, 3 * c, hh, ww).cuda())
+    out, lse = K.attn_fwd(qkv_d, heads, ch)
+    assert rel(K.nhwc_to_nchw(out).reshape(n, c, t), ref.detach()) < 1e-2
+    do_d = K.nchw_to_nhwc(do.reshape(n, c, hh, ww).cuda())
+    dqkv = K.attn_bwd(qkv_d, out, do_d, lse, heads, ch)
+    assert rel(K.nhwc_to_nchw(dqkv).reshape(n, 3 * c, t), qr.grad) < 1.5e-2
+
+
+def test_layout_resample_concat_bit_exact(K):
+    g = torch.Generator().manual_seed(1)
+    x = bf16_round(torch.randn(2, 24, 16, 16, generator=g))
+    x_d = to_dev_nhwc(K, x)
+    assert torch.equal(K.nhwc_to_nchw(x_d).cpu(), x)
+    up = K.nhwc_to_nchw(K.resample2x(x_d, 0)).cpu()
+    assert torch.equal(up, F.interpolate(x, scale_factor=2, mode="nearest"))
+    pool = K.nhwc_to_nchw(K.resample2x(x_d, 1)).cpu()
+    assert rel(pool, F.avg_pool2d(x, 2, 2)) < 4e-3
+    y = bf16_round(torch.randn(2, 40, 16, 16, generator=g))
+    from joligen_b200 import ops
+    cat = ops.cat_channels(x_d, to_dev_nhwc(K, y))
+    assert torch.equal(K.nhwc_to_nchw(cat).cpu(), torch.cat([x, y], dim=1))
+
+
+def test_linear_noise_pack_loss_adam(K):
+    from joligen_b200 import lib as L
+    from oracle import palette_oracle as O
+    g = torch.Generator().manual_seed(3)
+    # emb_layers: SiLU -> Linear
+    x = torch.randn(4, 32, generator=g)
+    w = torch.randn(256, 32, generator=g) / 6
+    b = torch.randn(256, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.linear(F.silu(xr), wr, br)
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy)
+    y = K.linear_fwd(x.cuda(), w.cuda(), b.cuda(), act_in=L.ACT_SILU)
+    assert rel(y, ref.detach()) < 1e-5
+    dx, dw, db = K.linear_bwd(x.cuda(), w.cuda(), dy.cuda(), act_in=L.ACT_SILU)
+    assert rel(dx, xr.grad) < 1e-5 and rel(dw, wr.grad) < 1e-5 and rel(db, br.grad) < 1e-5
+
+    # prologue: q_sample + mask blend + cat, mask clamp bit exact (int64 masks with values outside {0,1})
+    data = O.synthetic_batch(2, 32, 9)
+    mask = data["mask"].clone()
+    mask[0, 0, :2] = 3
+    mask[1, 0, :2] = -1
+    noise = torch.randn(2, 3, 32, 32, generator=g)
+    gam = torch.tensor([0.3, 0.9])
+    packed = K.noise_pack(data["gt"].cuda(), data["cond"].cuda(), noise.cuda(), mask.cuda(), gam.cuda())
+    g4 = gam.view(-1, 1, 1, 1)
+    yn = g4.sqrt() * data["gt"] + (1 - g4).sqrt() * noise
+    m = torch.clamp(mask, min=0.0, max=1.0)
+    yn = yn * m + (1.0 - m) * data["gt"]
+    ref_in = torch.cat([data["cond"], yn], dim=1)
+    got = K.nhwc_to_nchw(packed, 6).cpu()
+    assert torch.equal(got, bf16_round(ref_in))  # elementwise fp32 math + one bf16 rounding: bit exact
+    assert float(packed[..., 6:].float().abs().max()) == 0.0
+
+    # eps-loss forward / backward
+    nh = bf16_round(torch.randn(2, 3, 32, 32, generator=g))
+    nhr = nh.clone().requires_grad_(True)
+    wsnr = torch.tensor([0.7, 1.0])
+    ref_loss = O.palette_loss(noise, nhr, mask, wsnr.view(-1, 1, 1, 1), lambda_G=2.0, use_minsnr=True)
+    ref_loss.backward()
+    nh_d = K.nchw_to_nhwc(nh.cuda())
+    loss = K.palette_loss_fwd(noise.cuda(), nh_d, mask.cuda(), wsnr.cuda(), lambda_g=2.0)
+    assert abs(float(loss) - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
+    gout = torch.tensor(0.5, device="cuda")
+    dnh = K.palette_loss_bwd(noise.cuda(), nh_d, mask.cuda(), wsnr.cuda(), gout, lambda_g=2.0)
+    assert rel(K.nhwc_to_nchw(dnh, 3), 0.5 * nhr.grad) < 1e-2
+
+    # fused AdamW + EMA against the oracle's restatement of torch.optim.AdamW + ema_step, 3 steps
+    p0 = torch.randn(1000, generator=g)
+    st = O.TrainState(params={"p": p0.clone()})
+    oc = O.OptimCfg(lr=1e-2, weight_decay=0.05, ema_beta=0.9)
+    p = p0.clone().cuda()
+    m_, v_, e_ = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        gr = torch.randn(1000, generator=g)
+        O.adam_update(st, {"p": gr}, oc)
+        K.adamw_ema_step(p, (2 * gr).cuda(), m_, v_, e_, lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.05,
+                         adamw=True, step=step, grad_scale=0.5, ema_beta=0.9, ema_init=(step == 1))
+    assert rel(p, st.params["p"]) < 1e-5
+    assert rel(e_, st.ema["p"]) < 1e-5
