@@ -163,20 +163,19 @@ def main():
     from joligen_b200 import kernels as K
     from joligen_b200 import lib as L
     from joligen_b200 import nets
+    from joligen_b200 import synthetic
     from joligen_b200.trainer import PaletteTrainer
-    from oracle import palette_oracle as O  # synthetic batch + seeded de-zeroed init only (not timed)
 
     L.load()
     assert L.load().jg_check_device() == 0, L.load().jg_last_error()
-    cfg = make_cfg(O, args.size)
     net = nets.build_palette_generator(image_size=args.size)
-    net.load_state_dict(O.init_params(cfg, 1234), strict=False)
+    synthetic.dezero_init_(net, 1234)
     tr = PaletteTrainer(net, lr=1e-4, optim="adamw", ema=True, ema_beta=0.999, device="cuda")
     tr.broadcast_parameters()
 
     B = args.batch
-    host = O.synthetic_batch(B, args.size, 1234 + rank)
-    host = {"A": host["cond"].pin_memory(), "B": host["gt"].pin_memory(), "B_label_mask": host["mask"].pin_memory()}
+    host = synthetic.synthetic_batch(B, args.size, 1234 + rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
     dev = {k: v.cuda() for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
@@ -215,27 +214,46 @@ def main():
     run(1, True)
     ms_e2e, last_loss = run(args.steps, True)
 
-    # instrumented pass: CUDA events around every implicit-GEMM conv launch (fwd / dgrad / wgrad)
+    # instrumented pass: CUDA events around every C-ABI call; conv launches carry their FLOPs
     recs = []
+    allrecs = []
 
     @contextlib.contextmanager
     def hook(name, cargs):
-        if name not in ("jg_conv2d_fwd", "jg_conv2d_wgrad"):
-            yield
-            return
-        d = cargs[0]._obj
-        flops = 2.0 * d.N * d.Ho * d.Wo * d.Cout * d.Cin * d.R * d.S
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         yield
         e1.record()
-        recs.append((name, flops, e0, e1))
+        if name in ("jg_conv2d_fwd", "jg_conv2d_wgrad"):
+            d = cargs[0]._obj
+            flops = 2.0 * d.N * d.Ho * d.Wo * d.Cout * d.Cin * d.R * d.S
+            recs.append((name, flops, e0, e1))
+            allrecs.append((name, (d.N, d.H, d.W, d.Cin, d.Cout, d.R, d.stride), flops, e0, e1))
+        else:
+            allrecs.append((name, None, 0.0, e0, e1))
 
     L.call_hook[0] = hook
     tr.set_input(dev)
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_a.record()
     tr.optimize_parameters()
+    ev_b.record()
     torch.cuda.synchronize()
     L.call_hook[0] = None
+    if rank == 0 and os.environ.get("JG_BREAKDOWN"):
+        agg = {}
+        for name, shape, flops, e0, e1 in allrecs:
+            key = name if shape is None else "%s %s" % (name, list(shape))
+            a = agg.setdefault(key, {"calls": 0, "ms": 0.0, "flops": 0.0})
+            a["calls"] += 1
+            a["ms"] += e0.elapsed_time(e1)
+            a["flops"] += flops
+        rows = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
+        with open(os.environ["JG_BREAKDOWN"], "w") as f:
+            json.dump({"instrumented_step_ms": ev_a.elapsed_time(ev_b),
+                       "sum_call_ms": sum(v["ms"] for _, v in rows),
+                       "rows": [dict(key=k, tflops=(v["flops"] / v["ms"] / 1e9 if v["ms"] > 0 else 0), **v)
+                                for k, v in rows]}, f, indent=1)
     conv_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in recs)
     conv_flops_padded = sum(f for _, f, _, _ in recs)
     alg_flops_step = 3 * 2 * FWD_GMAC_PER_IMG_256 * 1e9 * B * (args.size / 256.0) ** 2

@@ -1,0 +1,95 @@
+"""Drop-in swap: replace the hot-path modules of a REFERENCE-built network (joliGEN's own
+`diffusion_networks.define_G` / `models.modules.*` objects) by their B200 mirrors, in place.
+
+    netG_A = diffusion_networks.define_G(**vars(opt))      # joliGEN, unchanged
+    netG_A = joligen_b200.accelerate(netG_A)               # this module
+
+The swap is structural, not textual: reference classes are recognised by class name, rebuilt from
+their own hyper-parameters, and the new module ADOPTS the reference's nn.Parameter / buffer objects
+(no copy), so optimisers, DDP, `state_dict()`, `save_networks` / `load_networks`
+(base_model.py:824-868, 957-1103) and `ema_step` (base_model.py:1284-1297) keep working on the same
+tensors under the same names.  Modules that are not on the hot path are left untouched.
+"""
+import torch.nn as nn
+
+from . import nets
+
+
+def _adopt(dst: nn.Module, src: nn.Module):
+    """Make dst's parameters/buffers BE src's (same objects), matched by qualified name."""
+    src_params = dict(src.named_parameters())
+    src_bufs = dict(src.named_buffers())
+    dst_names = [n for n, _ in dst.named_parameters()]
+    if sorted(dst_names) != sorted(src_params.keys()):
+        missing = set(src_params) ^ set(dst_names)
+        raise RuntimeError("accelerate: parameter names differ between reference and B200 module: %s"
+                           % sorted(missing)[:6])
+    for name in dst_names:
+        mod, leaf = _resolve(dst, name)
+        if mod._parameters[leaf].shape != src_params[name].shape:
+            raise RuntimeError("accelerate: shape mismatch for %s" % name)
+        mod._parameters[leaf] = src_params[name]
+    for name, buf in src_bufs.items():
+        mod, leaf = _resolve(dst, name, create=True)
+        mod._buffers[leaf] = buf
+    nets.invalidate_packed_weights()
+
+
+def _resolve(root, name, create=False):
+    parts = name.split(".")
+    mod = root
+    for p in parts[:-1]:
+        mod = getattr(mod, p)
+    return mod, parts[-1]
+
+
+def _norm_spec(gn_wrapper):
+    g = gn_wrapper.norm
+    return "groupnorm%d" % g.num_groups
+
+
+def _unet_from_reference(ref):
+    first_res = ref.input_blocks[1][0]
+    norm = _norm_spec(first_res.in_layers[0])
+    return nets.UNet(
+        image_size=ref.image_size, in_channel=ref.in_channel, inner_channel=ref.inner_channel,
+        out_channel=ref.out_channel, res_blocks=list(ref.res_blocks), attn_res=list(ref.attn_res), tanh=False,
+        n_timestep_train=ref.beta_schedule["train"]["n_timestep"],
+        n_timestep_test=ref.beta_schedule["test"]["n_timestep"], norm=norm, group_norm_size=32,
+        cond_embed_dim=ref.cond_embed_dim, channel_mults=tuple(ref.channel_mults), num_heads=ref.num_heads,
+        num_head_channels=ref.num_head_channels, num_heads_upsample=ref.num_heads_upsample,
+        use_scale_shift_norm=first_res.use_scale_shift_norm, efficient=first_res.efficient,
+        freq_space=getattr(ref, "freq_space", False))
+
+
+def accelerate(module: nn.Module) -> nn.Module:
+    """Returns the accelerated module (the same object with children swapped, or a new root when the
+    root itself is a hot-path class)."""
+    cls = type(module).__name__
+    if isinstance(module, (nets.UNet, nets.DiffusionGenerator, nets.ResBlock, nets.AttentionBlock)):
+        return module
+    if cls == "DiffusionGenerator":
+        ref_unet = module.denoise_fn.model
+        if type(ref_unet).__name__ != "UNet":
+            raise NotImplementedError("accelerate: DiffusionGenerator backbone %s is not on the B200 path yet"
+                                      % type(ref_unet).__name__)
+        if getattr(module.denoise_fn, "conditioning", ""):
+            raise NotImplementedError("accelerate: conditioning %r is not supported yet"
+                                      % module.denoise_fn.conditioning)
+        unet = _unet_from_reference(ref_unet)
+        dn = nets.PaletteDenoiseFn(model=unet, cond_embed_dim=module.denoise_fn.cond_embed_dim, conditioning="")
+        new = nets.DiffusionGenerator(denoise_fn=dn, sampling_method=module.sampling_method,
+                                      image_size=module.image_size)
+        _adopt(new, module)
+        new.train(module.training)
+        return new
+    if cls == "UNet" and hasattr(module, "input_blocks") and hasattr(module, "middle_block"):
+        new = _unet_from_reference(module)
+        _adopt(new, module)
+        new.train(module.training)
+        return new
+    for name, child in list(module.named_children()):
+        swapped = accelerate(child)
+        if swapped is not child:
+            setattr(module, name, swapped)
+    return module

@@ -14,8 +14,8 @@ Data parallelism = one process per GPU, batch sharded by the caller, SUM all-red
 gradient scaled by 1/world inside the optimizer kernel (DDP's mean, base_model.py:725-737).
 """
 import torch
-import torch.distributed as dist
 
+from . import dp
 from . import kernels as K
 from . import nets
 
@@ -76,7 +76,7 @@ class PaletteTrainer:
         if loss not in ("MSE", "L1"):
             raise NotImplementedError("alg_palette_loss %r" % loss)
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world = dp.world_size(process_group)
         self.niter = 0
         self.step = 0
         self.loss_G_tot = None
@@ -92,9 +92,8 @@ class PaletteTrainer:
         self.cond_image = self.y_t
 
     def broadcast_parameters(self):
-        if self.world > 1:
-            dist.broadcast(self.flat.data, src=0, group=self.pg)
-            nets.invalidate_packed_weights()
+        dp.broadcast_(self.flat.data, self.pg)
+        nets.invalidate_packed_weights()
 
     # -- step -----------------------------------------------------------------------------------
     def compute_palette_loss(self, noise=None, t=None, u=None):
@@ -109,11 +108,10 @@ class PaletteTrainer:
         loss = self.compute_palette_loss(noise=noise, t=t, u=u)
         (loss / self.iter_size).backward()
         if self.niter % self.iter_size == 0:
-            if self.world > 1:
-                dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            grad_scale = dp.allreduce_sum_(self.flat.grad, self.pg)
             self.step += 1
             K.adamw_ema_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.ema,
-                             step=self.step, grad_scale=1.0 / self.world, ema_beta=self.ema_beta,
+                             step=self.step, grad_scale=grad_scale, ema_beta=self.ema_beta,
                              ema_init=not self.ema_started, **self.hp)
             self.ema_started = True
             self.flat.grad.zero_()

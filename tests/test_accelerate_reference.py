@@ -1,0 +1,32 @@
+"""accelerate() on a network built by the UNMODIFIED reference (only where /root/reference exists,
+i.e. in the build container): the swapped tree shares the reference's Parameter objects and keeps
+its state_dict keys.  (CPU only: no kernels are launched.)"""
+import os
+
+import pytest
+import torch
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_accelerate_adopts_reference_parameters():
+    from oracle import ref_stubs
+    ref_stubs.install()
+    from oracle import gen_golden
+    from oracle import palette_oracle as O
+    from joligen_b200 import accelerate, nets
+    cfg = O.UNetCfg(**gen_golden.SMALL)
+    ref_net = gen_golden.build_reference_generator(cfg)
+    ref_params = dict(ref_net.named_parameters())
+    ref_keys = list(ref_net.state_dict().keys())
+    fast = accelerate(ref_net)
+    assert isinstance(fast, nets.DiffusionGenerator)
+    assert list(fast.state_dict().keys()) == ref_keys
+    for k, p in fast.named_parameters():
+        assert p is ref_params[k]  # same Parameter objects: optimizers / DDP built on the reference still apply
+    # a reference wrapper that merely CONTAINS a UNet gets the child swapped in place
+    holder = torch.nn.Module()
+    holder.netG = gen_golden.build_reference_generator(cfg).denoise_fn.model
+    accelerate(holder)
+    assert isinstance(holder.netG, nets.UNet)
