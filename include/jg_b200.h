@@ -172,11 +172,13 @@ int jg_palette_loss_bwd(const float* noise, const void* noise_hat, int ld, const
  * Fused Adam(W) + EMA over flat fp32 buffers: torch.optim.AdamW / Adam update (train.py:51-62,
  * base_model.py:1268-1274) followed by ema_step (base_model.py:1284-1297).  g is multiplied by
  * grad_scale first (1/world_size after a SUM all-reduce, 1/iter_size...).  ema may be NULL;
- * ema_init != 0 reproduces the first ema_step (deep copy of the updated net).
+ * ema_init != 0 reproduces the first ema_step (deep copy of the updated net).  step is the 1-based
+ * optimizer step on the host, or — when step_dev != NULL — a device counter that this call increments
+ * and reads (CUDA-graph replay; ema_init is then derived as step == 1).
  * ------------------------------------------------------------------------------------------- */
 int jg_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr, float beta1,
-                      float beta2, float eps, float weight_decay, int adamw, int step, float grad_scale,
-                      float ema_beta, int ema_init, jg_stream_t stream);
+                      float beta2, float eps, float weight_decay, int adamw, int step, int* step_dev,
+                      float grad_scale, float ema_beta, int ema_init, jg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -41,26 +41,34 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
   dst[i] = beta == 0.f ? v : beta * dst[i] + v;
 }
 
-// db[c] += sum_rows dy[row][c]; one warp-row-slab per block, 8 channels per thread.
-__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, long long rows, int C, int ld,
-                                 float* __restrict__ db, int rows_per_block) {
+// db[c] += sum_rows dy[row][c]: 8 channels per thread, block-level reduction in shared memory, then
+// ONE global atomic per channel per block (grid ~ a few waves of the SMs).
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, long long rows, int C, int ld, float* __restrict__ db,
+                 long long rows_per_block) {
+  extern __shared__ float sm[];  // C floats
   const int vecs = C / 8;
   const int tid = threadIdx.x;
   const int v = tid % vecs;
   const int rlane = tid / vecs;
   const int rstep = blockDim.x / vecs;
-  if (rlane >= rstep) return;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  const long long r1 = min(r0 + rows_per_block, rows);
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long r = r0 + rlane; r < r1; r += rstep) {
-    const uint4 u = *reinterpret_cast<const uint4*>(dy + r * ld + v * 8);
-    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
-    acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
-  }
+  for (int i = tid; i < C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  if (rlane < rstep) {
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(r0 + rows_per_block, rows);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long r = r0 + rlane; r < r1; r += rstep) {
+      const uint4 u = *reinterpret_cast<const uint4*>(dy + r * ld + v * 8);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(db + v * 8 + j, acc[j]);
+    for (int j = 0; j < 8; ++j) atomicAdd(&sm[v * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int i = tid; i < C; i += blockDim.x) atomicAdd(db + i, sm[i]);
 }
 
 // NCHW fp32 -> NHWC bf16 (channels >= C zero-filled up to ld), 32x32 smem transpose tiles.
@@ -228,10 +236,12 @@ extern "C" int jg_bias_grad(const void* dy, int64_t rows, int C, int ld, float* 
   JG_CHECK(dy && db && rows > 0 && C > 0 && C % 8 == 0 && ld % 8 == 0 && C / 8 <= 256, JG_ERR_INVALID,
            "bias_grad: bad args (C=%d ld=%d)", C, ld);
   JG_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, stream));
-  const int rows_per_block = 512;
+  long long blocks = (long long)num_sms() * 8;
+  long long rows_per_block = (rows + blocks - 1) / blocks;
+  if (rows_per_block < 64) rows_per_block = 64;
   const int grid = (int)((rows + rows_per_block - 1) / rows_per_block);
-  bias_grad_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), rows, C, ld, db,
-                                             rows_per_block);
+  bias_grad_kernel<<<grid, 256, C * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(dy), rows, C, ld, db,
+                                                             rows_per_block);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }

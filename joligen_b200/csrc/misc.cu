@@ -159,10 +159,17 @@ __global__ void palette_loss_bwd_kernel(const float* __restrict__ noise, const _
 
 // Fused AdamW / Adam + EMA over flat fp32 buffers (torch.optim.AdamW semantics, train.py:57-58;
 // ema_step, base_model.py:1284-1297: p_ema = p + beta*(p_ema - p)).
+__global__ void step_increment_kernel(int* step) { *step += 1; }
+
 __global__ void adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, float* __restrict__ ema, long long n, float lr, float beta1,
-                                 float beta2, float eps, float wd, int adamw, float bc1, float bc2_sqrt,
-                                 float grad_scale, float ema_beta, int ema_init) {
+                                 float beta2, float eps, float wd, int adamw, int step_host,
+                                 const int* __restrict__ step_dev, float grad_scale, float ema_beta, int ema_init) {
+  // The step count may live on the device (CUDA-graph replay: host scalars would be frozen at capture).
+  const int step = step_dev ? *step_dev : step_host;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  if (step_dev) ema_init = (step == 1);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float pv = p[i];
     float gv = g[i] * grad_scale;
@@ -256,16 +263,19 @@ extern "C" int jg_palette_loss_bwd(const float* noise, const void* noise_hat, in
 
 extern "C" int jg_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr,
                                  float beta1, float beta2, float eps, float weight_decay, int adamw, int step,
-                                 float grad_scale, float ema_beta, int ema_init, jg_stream_t stream_) {
+                                 int* step_dev, float grad_scale, float ema_beta, int ema_init,
+                                 jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  JG_CHECK(p && g && m && v && n > 0 && step > 0, JG_ERR_INVALID, "adamw_ema_step: bad args");
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2 = 1.f - powf(beta2, (float)step);
+  JG_CHECK(p && g && m && v && n > 0 && (step > 0 || step_dev), JG_ERR_INVALID, "adamw_ema_step: bad args");
+  if (step_dev) {
+    step_increment_kernel<<<1, 1, 0, stream>>>(step_dev);
+    JG_LAUNCH_CHECK();
+  }
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   adamw_ema_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay,
-                                                         adamw, bc1, sqrtf(bc2), grad_scale, ema_beta, ema_init);
+                                                         adamw, step, step_dev, grad_scale, ema_beta, ema_init);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }

@@ -237,7 +237,8 @@ def palette_loss_bwd(noise, noise_hat, mask, w_b, grad_out, lambda_g=1.0, l1=Fal
 
 
 def adamw_ema_step(p, g, m, v, ema, lr, beta1, beta2, eps, weight_decay, adamw, step, grad_scale=1.0, ema_beta=0.999,
-                   ema_init=False):
+                   ema_init=False, step_dev=None):
+    """step_dev: optional int32 device scalar holding the step count (incremented by the call)."""
     L.call("jg_adamw_ema_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), L.ptr(ema), p.numel(), float(lr),
-           float(beta1), float(beta2), float(eps), float(weight_decay), int(adamw), int(step), float(grad_scale),
-           float(ema_beta), int(ema_init), L.stream())
+           float(beta1), float(beta2), float(eps), float(weight_decay), int(adamw), int(step), L.ptr(step_dev),
+           float(grad_scale), float(ema_beta), int(ema_init), L.stream())

@@ -55,7 +55,7 @@ class FlatParams:
 class PaletteTrainer:
     def __init__(self, netG_A, lr=2e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, optim="adamw",
                  ema=True, ema_beta=0.999, iter_size=1, lambda_G=1.0, use_minsnr=False, loss="MSE",
-                 device=None, process_group=None):
+                 device=None, process_group=None, cuda_graph=False, graph_warmup=3):
         if not torch.cuda.is_available():
             raise RuntimeError("joligen_b200.PaletteTrainer needs a CUDA device (there is no CPU path)")
         self.device = torch.device(device if device is not None else "cuda")
@@ -80,14 +80,34 @@ class PaletteTrainer:
         self.niter = 0
         self.step = 0
         self.loss_G_tot = None
-        self.gpu_launch_estimate = 0
+        # CUDA-graph replay of the step (static shapes): graph 1 = prologue + forward + loss + backward,
+        # [eager NCCL all-reduce of the flat gradient], graph 2 = Adam(W)+EMA + gradient zeroing.
+        self.use_graph = bool(cuda_graph)
+        if self.use_graph and iter_size != 1:
+            raise NotImplementedError("cuda_graph=True requires train_iter_size == 1")
+        self.graph_warmup = graph_warmup
+        self._graph_fb = None
+        self._graph_opt = None
+        self._static = None
+        self._eager_steps = 0
+        self.step_dev = torch.zeros((), dtype=torch.int32, device=self.device)
 
     # -- data -----------------------------------------------------------------------------------
     def set_input(self, data, non_blocking=True):
         """data: {"A": cond image y_t, "B": ground truth, "B_label_mask": int64/float mask [B,1,H,W]}"""
+        m = data.get("B_label_mask")
+        if self._static is not None:
+            # graph mode: refill the captured input buffers in place
+            st = self._static
+            if tuple(data["A"].shape) != tuple(st["A"].shape) or (m is None) != (st["M"] is None):
+                raise RuntimeError("cuda_graph=True: input shapes must stay fixed after capture")
+            st["A"].copy_(data["A"], non_blocking=non_blocking)
+            st["B"].copy_(data["B"], non_blocking=non_blocking)
+            if m is not None:
+                st["M"].copy_(m, non_blocking=non_blocking)
+            return
         self.y_t = data["A"].to(self.device, non_blocking=non_blocking)
         self.gt_image = data["B"].to(self.device, non_blocking=non_blocking)
-        m = data.get("B_label_mask")
         self.mask = None if m is None else m.to(self.device, non_blocking=non_blocking)
         self.cond_image = self.y_t
 
@@ -102,20 +122,57 @@ class PaletteTrainer:
                                                    t=t, u=u)
         return self.loss_G_tot
 
-    def optimize_parameters(self, noise=None, t=None, u=None):
-        self.niter += 1
+    def _forward_backward(self, noise=None, t=None, u=None):
         self.flat.rebind_grads()
         loss = self.compute_palette_loss(noise=noise, t=t, u=u)
         (loss / self.iter_size).backward()
+        return loss
+
+    def _optimizer_step(self):
+        grad_scale = 1.0 / self.world
+        self.step += 1
+        K.adamw_ema_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.ema, step=self.step,
+                         step_dev=self.step_dev, grad_scale=grad_scale, ema_beta=self.ema_beta,
+                         ema_init=not self.ema_started, **self.hp)
+        self.ema_started = True
+        self.flat.grad.zero_()
+        nets.invalidate_packed_weights()
+
+    def _capture(self):
+        """Capture the step into CUDA graphs (called once, after `graph_warmup` eager steps)."""
+        self._static = {"A": self.y_t.clone(), "B": self.gt_image.clone(),
+                        "M": None if self.mask is None else self.mask.clone()}
+        self.y_t = self.cond_image = self._static["A"]
+        self.gt_image = self._static["B"]
+        self.mask = self._static["M"]
+        torch.cuda.synchronize()
+        self._graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_fb):
+            self._static_loss = self._forward_backward()
+        self._graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_opt):
+            self._optimizer_step()
+        # the capture itself did not execute: undo its host-side bookkeeping
+        self.step -= 1
+
+    def optimize_parameters(self, noise=None, t=None, u=None):
+        self.niter += 1
+        explicit = noise is not None or t is not None or u is not None
+        if self.use_graph and not explicit:
+            if self._graph_fb is None and self._eager_steps >= self.graph_warmup:
+                self._capture()
+            if self._graph_fb is not None:
+                self._graph_fb.replay()
+                dp.allreduce_sum_(self.flat.grad, self.pg)
+                self._graph_opt.replay()
+                self.step += 1
+                self.loss_G_tot = self._static_loss
+                return self._static_loss
+        loss = self._forward_backward(noise=noise, t=t, u=u)
         if self.niter % self.iter_size == 0:
-            grad_scale = dp.allreduce_sum_(self.flat.grad, self.pg)
-            self.step += 1
-            K.adamw_ema_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.ema,
-                             step=self.step, grad_scale=grad_scale, ema_beta=self.ema_beta,
-                             ema_init=not self.ema_started, **self.hp)
-            self.ema_started = True
-            self.flat.grad.zero_()
-            nets.invalidate_packed_weights()
+            dp.allreduce_sum_(self.flat.grad, self.pg)
+            self._optimizer_step()
+        self._eager_steps += 1
         return loss
 
     # -- state ----------------------------------------------------------------------------------

@@ -219,6 +219,38 @@ def gamma_embedding(gammas: torch.Tensor, dim: int, max_period=10000) -> torch.T
 # --------------------------------------------------------------------------------------------
 # forward restatements
 # --------------------------------------------------------------------------------------------
+# Precision emulation (default OFF = the reference's fp32 arithmetic).  With EMULATE_BF16[0] = True the
+# restatement rounds to bf16 exactly where the B200 path stores bf16 (every feature map written to HBM,
+# conv weights), keeping fp32 statistics / accumulation — used by the GPU tests to separate "precision
+# of bf16 storage" from "kernel bug": CUDA vs this emulation must agree far tighter than CUDA vs fp32.
+EMULATE_BF16 = [False]
+
+
+class _RoundBF16(torch.autograd.Function):
+    """bf16 storage of a feature map: the value is rounded on the way forward and its gradient on the
+    way back (the B200 path keeps both in bf16 NHWC buffers)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+def _r(x):
+    return _RoundBF16.apply(x) if EMULATE_BF16[0] else x
+
+
+def _rw(w):  # conv weights are consumed as bf16 copies; their gradients stay fp32
+    return w + (w.to(torch.bfloat16).float() - w).detach() if EMULATE_BF16[0] else w
+
+
+def _conv2d(x, w, b, padding=0):
+    return F.conv2d(x, _rw(w), b, padding=padding)
+
+
 def group_norm(x, w, b, groups):
     # unet_attn_utils.py:42-48 — nn.GroupNorm(groups, C) computed in fp32, eps 1e-5
     return F.group_norm(x.float(), groups, w, b, eps=1e-5).type(x.dtype)
@@ -226,30 +258,30 @@ def group_norm(x, w, b, groups):
 
 def res_block(sd, name, x, emb, b: BlockSpec, cfg: UNetCfg):
     """ResBlock._forward, unet_generator_attn.py:233-266."""
-    h = F.silu(group_norm(x, sd[name + ".in_layers.0.norm.weight"], sd[name + ".in_layers.0.norm.bias"],
-                          cfg.group_norm_size))
+    h = _r(F.silu(group_norm(x, sd[name + ".in_layers.0.norm.weight"], sd[name + ".in_layers.0.norm.bias"],
+                             cfg.group_norm_size)))
     if b.up:
         h = F.interpolate(h, scale_factor=2, mode="nearest")
         x = F.interpolate(x, scale_factor=2, mode="nearest")
     elif b.down:
-        h = F.avg_pool2d(h, 2, 2)
-        x = F.avg_pool2d(x, 2, 2)
-    h = F.conv2d(h, sd[name + ".in_layers.2.weight"], sd[name + ".in_layers.2.bias"], padding=1)
+        h = _r(F.avg_pool2d(h, 2, 2))
+        x = _r(F.avg_pool2d(x, 2, 2))
+    h = _r(_conv2d(h, sd[name + ".in_layers.2.weight"], sd[name + ".in_layers.2.bias"], padding=1))
     emb_out = F.linear(F.silu(emb), sd[name + ".emb_layers.1.weight"], sd[name + ".emb_layers.1.bias"])
     emb_out = emb_out[:, :, None, None]
     gn_w, gn_b = sd[name + ".out_layers.0.norm.weight"], sd[name + ".out_layers.0.norm.bias"]
     if cfg.use_scale_shift_norm:
         scale, shift = torch.chunk(emb_out, 2, dim=1)
         h = group_norm(h, gn_w, gn_b, cfg.group_norm_size) * (1 + scale) + shift
-        h = F.silu(h)
+        h = _r(F.silu(h))
     else:
         h = h + emb_out
-        h = F.silu(group_norm(h, gn_w, gn_b, cfg.group_norm_size))
-    h = F.conv2d(h, sd[name + ".out_layers.3.weight"], sd[name + ".out_layers.3.bias"], padding=1)
+        h = _r(F.silu(group_norm(h, gn_w, gn_b, cfg.group_norm_size)))
+    h = _conv2d(h, sd[name + ".out_layers.3.weight"], sd[name + ".out_layers.3.bias"], padding=1)
     if b.cin != b.cout:
-        x = F.conv2d(x, sd[name + ".skip_connection.weight"], sd[name + ".skip_connection.bias"])
+        x = _r(_conv2d(x, sd[name + ".skip_connection.weight"], sd[name + ".skip_connection.bias"]))
     skipw = 1.0 / math.sqrt(2) if cfg.efficient else 1.0
-    return skipw * x + h
+    return _r(skipw * x + h)
 
 
 def qkv_attention_legacy(qkv, n_heads):
@@ -268,18 +300,18 @@ def attention_block(sd, name, x, b: BlockSpec):
     """AttentionBlock._forward, unet_generator_attn.py:310-319 (norm = InstanceNorm1d, no affine)."""
     bsz, c, hh, ww = x.shape
     xf = x.reshape(bsz, c, -1)
-    xn = F.instance_norm(xf.float(), eps=1e-5).type(xf.dtype)
-    qkv = F.conv1d(xn, sd[name + ".qkv.weight"], sd[name + ".qkv.bias"])
-    h = qkv_attention_legacy(qkv, b.heads)
-    h = F.conv1d(h, sd[name + ".proj_out.weight"], sd[name + ".proj_out.bias"])
-    return (xf + h).reshape(bsz, c, hh, ww)
+    xn = _r(F.instance_norm(xf.float(), eps=1e-5).type(xf.dtype))
+    qkv = _r(F.conv1d(xn, _rw(sd[name + ".qkv.weight"]), sd[name + ".qkv.bias"]))
+    h = _r(qkv_attention_legacy(qkv, b.heads))
+    h = F.conv1d(h, _rw(sd[name + ".proj_out.weight"]), sd[name + ".proj_out.bias"])
+    return _r(xf + h).reshape(bsz, c, hh, ww)
 
 
 def _run_block(sd, name, layers, h, emb, cfg):
     for j, b in enumerate(layers):
         n = "%s.%d" % (name, j)
         if b.kind == "conv":
-            h = F.conv2d(h, sd[n + ".weight"], sd[n + ".bias"], padding=1)
+            h = _r(_conv2d(h, sd[n + ".weight"], sd[n + ".bias"], padding=1))
         elif b.kind == "res":
             h = res_block(sd, n, h, emb, b, cfg)
         else:
@@ -291,7 +323,7 @@ def unet_forward(sd, x, emb, cfg: UNetCfg, prefix="denoise_fn.model.", return_fe
     """UNet.forward, unet_generator_attn.py:660-695."""
     inp, mid, outb = unet_structure(cfg)
     hs = []
-    h = x.float()
+    h = _r(x.float())
     for i, layers in enumerate(inp):
         h = _run_block(sd, prefix + "input_blocks.%d" % i, layers, h, emb, cfg)
         hs.append(h)
@@ -300,8 +332,9 @@ def unet_forward(sd, x, emb, cfg: UNetCfg, prefix="denoise_fn.model.", return_fe
     for i, layers in enumerate(outb):
         h = torch.cat([h, hs.pop()], dim=1)
         h = _run_block(sd, prefix + "output_blocks.%d" % i, layers, h, emb, cfg)
-    h = F.silu(group_norm(h, sd[prefix + "out.0.norm.weight"], sd[prefix + "out.0.norm.bias"], cfg.group_norm_size))
-    out = F.conv2d(h, sd[prefix + "out.2.weight"], sd[prefix + "out.2.bias"], padding=1)
+    h = _r(F.silu(group_norm(h, sd[prefix + "out.0.norm.weight"], sd[prefix + "out.0.norm.bias"],
+                             cfg.group_norm_size)))
+    out = _r(_conv2d(h, sd[prefix + "out.2.weight"], sd[prefix + "out.2.bias"], padding=1))
     if return_feats:
         return out, feats
     return out
