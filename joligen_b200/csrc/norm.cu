@@ -24,6 +24,18 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
   const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+// streaming 16-byte load (read once: do not allocate in L1)
+__device__ __forceinline__ uint4 ldg_stream(const __nv_bfloat16* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   uint4 o;
   o.x = pack_bf16x2(f[0], f[1]);
@@ -58,7 +70,24 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int
   if (rl < rstep) {
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const __nv_bfloat16* base = x + ((size_t)n * HW) * ldx + v * 8;
-    for (int r = r0 + rl; r < r1; r += rstep) {
+    // 4 independent 16-byte loads in flight per thread
+    int r = r0 + rl;
+    for (; r + 3 * rstep < r1; r += 4 * rstep) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = ldg_stream(base + (size_t)(r + k * rstep) * ldx);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += f[j];
+          q[j] += f[j] * f[j];
+        }
+      }
+    }
+    for (; r < r1; r += rstep) {
       float f[8];
       load8(base + (size_t)r * ldx, f);
 #pragma unroll
@@ -141,7 +170,24 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __r
   const int r1 = min(r0 + rows_per_block, HW);
   const __nv_bfloat16* xb = x + ((size_t)n * HW) * ldx + v * 8;
   __nv_bfloat16* yb = y + ((size_t)n * HW) * ldy + v * 8;
-  for (int r = r0 + rl; r < r1; r += rstep) {
+  int r = r0 + rl;
+  for (; r + 3 * rstep < r1; r += 4 * rstep) {
+    uint4 u4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u4[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8(u4[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float u = f[j] * a[j] + b[j];
+        f[j] = act == JG_ACT_SILU ? silu_f(u) : u;
+      }
+      store8(yb + (size_t)(r + k * rstep) * ldy, f);
+    }
+  }
+  for (; r < r1; r += rstep) {
     float f[8];
     load8(xb + (size_t)r * ldx, f);
 #pragma unroll
@@ -179,7 +225,29 @@ gn_bwd_sums_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bflo
     const int r1 = min(r0 + rows_per_block, HW);
     const __nv_bfloat16* xb = x + ((size_t)n * HW) * ldx + v * 8;
     const __nv_bfloat16* db = dy + ((size_t)n * HW) * lddy + v * 8;
-    for (int r = r0 + rl; r < r1; r += rstep) {
+    int r = r0 + rl;
+    for (; r + rstep < r1; r += 2 * rstep) {
+      uint4 ux[2], ud[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        ux[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
+        ud[k] = ldg_stream(db + (size_t)(r + k * rstep) * lddy);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        float f[8], d[8];
+        unpack8(ux[k], f);
+        unpack8(ud[k], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float du = d[j];
+          if (act == JG_ACT_SILU) du *= silu_grad(f[j] * a[j] + b[j]);
+          sa[j] += du;
+          sb[j] += du * f[j];
+        }
+      }
+    }
+    for (; r < r1; r += rstep) {
       float f[8], d[8];
       load8(xb + (size_t)r * ldx, f);
       load8(db + (size_t)r * lddy, d);
@@ -294,7 +362,29 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfl
   const __nv_bfloat16* xb = x + ((size_t)n * HW) * ldx + v * 8;
   const __nv_bfloat16* db = dy + ((size_t)n * HW) * lddy + v * 8;
   __nv_bfloat16* ob = dx + ((size_t)n * HW) * lddx + v * 8;
-  for (int r = r0 + rl; r < r1; r += rstep) {
+  int r = r0 + rl;
+  for (; r + rstep < r1 && !accumulate; r += 2 * rstep) {
+    uint4 ux[2], ud[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      ux[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
+      ud[k] = ldg_stream(db + (size_t)(r + k * rstep) * lddy);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float f[8], d[8], o[8];
+      unpack8(ux[k], f);
+      unpack8(ud[k], d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float du = d[j];
+        if (act == JG_ACT_SILU) du *= silu_grad(f[j] * a[j] + b[j]);
+        o[j] = c1[j] * du + c2[j] * f[j] + c3[j];
+      }
+      store8(ob + (size_t)(r + k * rstep) * lddx, o);
+    }
+  }
+  for (; r < r1; r += rstep) {
     float f[8], d[8], o[8];
     load8(xb + (size_t)r * ldx, f);
     load8(db + (size_t)r * lddy, d);

@@ -347,7 +347,8 @@ def set_new_noise_schedule(model, phase):
 def gamma_embedding(gammas, dim, max_period=10000):
     """diffusion_utils.gamma_embedding for [B,1] gammas (host-side O(B) work, stays in torch)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(gammas.device)
+    # built on the target device: no host->device copy inside the step (CUDA-graph capturable)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=gammas.device) / half)
     args = gammas[:, 0:1].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
