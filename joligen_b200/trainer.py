@@ -126,7 +126,10 @@ class PaletteTrainer:
         self.flat.rebind_grads()
         loss = self.compute_palette_loss(noise=noise, t=t, u=u)
         (loss / self.iter_size).backward()
-        return loss
+        # hand out a graph-free scalar: a retained autograd graph would keep this iteration's
+        # AccumulateGrad nodes (and their stream binding) alive across iterations / graph capture
+        self.loss_G_tot = loss.detach()
+        return self.loss_G_tot
 
     def _optimizer_step(self):
         grad_scale = 1.0 / self.world
@@ -145,6 +148,9 @@ class PaletteTrainer:
         self.y_t = self.cond_image = self._static["A"]
         self.gt_image = self._static["B"]
         self.mask = self._static["M"]
+        self.loss_G_tot = None
+        import gc
+        gc.collect()
         torch.cuda.synchronize()
         self._graph_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_fb):

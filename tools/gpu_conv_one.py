@@ -1,0 +1,32 @@
+"""Run one conv shape a few times (for ncu captures / quick timing).
+    python tools/gpu_conv_one.py N H W Cin Cout K [what=fwd|wgrad] [reps]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from joligen_b200 import kernels as K  # noqa: E402
+
+n, h, w, cin, cout, k = [int(v) for v in sys.argv[1:7]]
+what = sys.argv[7] if len(sys.argv) > 7 else "fwd"
+reps = int(sys.argv[8]) if len(sys.argv) > 8 else 5
+g = torch.Generator(device="cuda").manual_seed(0)
+x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
+wt = torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5
+bias = torch.zeros(cout, device="cuda")
+wf, wd = K.pack_conv_weight(wt)
+dy = torch.randn(n, h, w, cout, device="cuda", generator=g).to(torch.bfloat16)
+fn = (lambda: K.conv2d_fwd(x, wf, bias, cout, k, k)) if what == "fwd" else (lambda: K.conv2d_wgrad(x, dy, cout, k, k))
+for _ in range(3):
+    fn()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    fn()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print("%s %s: %.3f ms  %.1f TFLOP/s" % (what, sys.argv[1:7], ms, 2.0 * n * h * w * cin * cout * k * k / ms / 1e9))
