@@ -1,0 +1,95 @@
+// Shared pieces of the implicit-GEMM convolution kernels (conv_igemm.cu, conv_halo.cu).
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace jg {
+
+constexpr int kThreads = 192;
+constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+
+struct ConvFwdParams {
+  int N, Ho, Wo;
+  int Cout;
+  int RS, S, pad, stride;
+  int TW, TH, TN;
+  int tiles_w, tiles_h, tiles_n;
+  int n_tiles;    // ceil(Cout / BLOCK_N)
+  int kc_blocks;  // ceil(Cin / 64)
+  int total_tiles;
+  int ldy, ldres;
+  int act;
+  float res_scale;
+  const float* bias;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* y;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case JG_ACT_RELU: return v > 0.f ? v : 0.f;
+    case JG_ACT_LRELU02: return v > 0.f ? v : 0.2f * v;
+    case JG_ACT_TANH: return tanhf(v);
+    case JG_ACT_SILU: return v / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+
+
+// Epilogue of one 128 x BLOCK_N output tile held in TMEM: bias + res_scale*residual + activation -> bf16 ->
+// 16-byte global stores.  Called by the 4 epilogue warps (q = TMEM lane quarter of the calling warp).
+template <int BLOCK_N>
+__device__ __forceinline__ void conv_epilogue_tile(const ConvFwdParams& p, uint32_t t_acc, int q, int n_tile,
+                                                   bool valid, size_t pix) {
+  const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N; c += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32(t_row + c, v);
+    tmem_ld_wait();
+    const int co0 = n_tile * BLOCK_N + c;
+    if (valid && co0 < p.Cout) {
+      __nv_bfloat16* yp = p.y + pix * p.ldy + co0;
+      const __nv_bfloat16* rp = p.res ? p.res + pix * p.ldres + co0 : nullptr;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {  // 8 channels per 16-byte store
+        if (co0 + g * 8 < p.Cout) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+          if (p.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + g * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + g * 8 + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          }
+          if (rp) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(rp + g * 8);
+            const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y);
+            const float2 r2 = unpack_bf16x2(rv.z), r3 = unpack_bf16x2(rv.w);
+            f[0] += p.res_scale * r0.x; f[1] += p.res_scale * r0.y;
+            f[2] += p.res_scale * r1.x; f[3] += p.res_scale * r1.y;
+            f[4] += p.res_scale * r2.x; f[5] += p.res_scale * r2.y;
+            f[6] += p.res_scale * r3.x; f[7] += p.res_scale * r3.y;
+          }
+          if (p.act != JG_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
+          }
+          uint4 o;
+          o.x = pack_bf16x2(f[0], f[1]);
+          o.y = pack_bf16x2(f[2], f[3]);
+          o.z = pack_bf16x2(f[4], f[5]);
+          o.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(yp + g * 8) = o;
+        }
+      }
+    }
+  }
+}
+
+// Launch of the halo-reuse 3x3 kernel (conv_halo.cu); returns JG_ERR_UNSUPPORTED when the shape does not qualify.
+int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                     const void* residual, void* y, cudaStream_t stream);
+
+}  // namespace jg

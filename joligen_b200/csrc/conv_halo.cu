@@ -1,0 +1,296 @@
+// 3x3 (generally RxS, stride 1) implicit-GEMM convolution with shared-memory HALO REUSE across taps.
+//
+// conv_igemm.cu stages the A operand once per (tap, 64-channel slab): the same input patch is pulled
+// from L2 R*S times.  Here ONE 4-D TMA box of (TH+R-1) x (TW+S-1) pixels x 64 channels is staged per
+// slab, and the R*S tap operands are shifted WINDOWS of that patch: the UMMA descriptor for tap (r,s)
+// starts at byte ((r*PW + s) * 128) of the patch with SBO = PW*128 (8-pixel row groups of a TW = 8 wide
+// tile are PW = TW+S-1 pixels apart).  tools/umma_probe.cu established on B200 that tcgen05.mma applies
+// the 128B swizzle to absolute shared-memory address bits, so a window whose start is only 128-byte
+// aligned and whose 8-row groups are 1280 bytes apart reads exactly what TMA wrote (base_offset = 0).
+// L2->SM traffic for A drops by R*S*128/180 = 6.4x for 3x3.
+//
+// B (weights): streamed per (slab, tap) through its own smem ring, or — when all R*S*ceil(Cin/64) tiles
+// fit (Cin = 64 layers, the 256^2-level convs) — loaded ONCE per CTA and kept resident.
+//
+// Same warp roles / TMEM double buffering / epilogue as conv_igemm.cu.
+#include "conv_common.cuh"
+
+namespace jg {
+
+constexpr int kHaloTW = 8, kHaloTH = 16;
+
+struct HaloParams {
+  ConvFwdParams c;  // TW/TH/TN = 8/16/1
+  int R, PW, PH;    // filter rows, patch width / height in pixels
+  int a_stage_bytes;
+};
+
+template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const HaloParams hp) {
+  const ConvFwdParams& p = hp.c;
+  constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + SA * hp.a_stage_bytes;
+  const int k_slabs = p.kc_blocks;
+  const int b_tiles = B_RESIDENT ? p.RS * k_slabs : SB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + static_cast<size_t>(b_tiles) * B_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + SA;
+  uint64_t* b_full = bars + 2 * SA;           // SB entries (entry 0 only when resident)
+  uint64_t* b_empty = bars + 2 * SA + SB;
+  uint64_t* tfull = bars + 2 * SA + 2 * SB;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < SA; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < SB; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      if (B_RESIDENT) {
+        // all weight tiles of this CTA's (single) N tile, once
+        mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(p.RS * k_slabs * B_BYTES));
+        for (int kc = 0; kc < k_slabs; ++kc)
+          for (int tap = 0; tap < p.RS; ++tap)
+            tma_load_3d(smB + (kc * p.RS + tap) * B_BYTES, &tmB, &b_full[0], kc * 64, tap, 0);
+      }
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * kHaloTW - p.pad;
+        const int h0 = th * kHaloTH - p.pad;
+        for (int kc = 0; kc < k_slabs; ++kc) {
+          mbar_wait(&a_empty[sa], pha ^ 1);
+          mbar_arrive_expect_tx(&a_full[sa], static_cast<uint32_t>(hp.PW * hp.PH * 128));
+          tma_load_4d(smA + sa * hp.a_stage_bytes, &tmA, &a_full[sa], kc * 64, w0, h0, tn);
+          if (++sa == SA) {
+            sa = 0;
+            pha ^= 1;
+          }
+          if (!B_RESIDENT) {
+            for (int tap = 0; tap < p.RS; ++tap) {
+              mbar_wait(&b_empty[sb], phb ^ 1);
+              mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
+              tma_load_3d(smB + sb * B_BYTES, &tmB, &b_full[sb], kc * 64, tap, n_tile * BLOCK_N);
+              if (++sb == SB) {
+                sb = 0;
+                phb ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      const uint32_t sbo_a = static_cast<uint32_t>(hp.PW * 128);
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      if (B_RESIDENT) {
+        mbar_wait(&b_full[0], 0);
+        tc_fence_after();
+      }
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kc = 0; kc < k_slabs; ++kc) {
+          mbar_wait(&a_full[sa], pha);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smA + sa * hp.a_stage_bytes);
+          for (int tap = 0; tap < p.RS; ++tap) {
+            const int r = tap / p.S;
+            const int s = tap - r * p.S;
+            uint32_t b_addr;
+            if (B_RESIDENT) {
+              b_addr = smem_u32(smB + (kc * p.RS + tap) * B_BYTES);
+            } else {
+              mbar_wait(&b_full[sb], phb);
+              tc_fence_after();
+              b_addr = smem_u32(smB + sb * B_BYTES);
+            }
+            const uint32_t a_addr = a_base + static_cast<uint32_t>((r * hp.PW + s) * 128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t a_desc = make_smem_desc_sw128(a_addr + k * 32, 16, sbo_a);
+              const uint64_t b_desc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+              umma_bf16(d_tmem, a_desc, b_desc, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+            }
+            if (!B_RESIDENT) {
+              umma_commit(&b_empty[sb]);
+              if (++sb == SB) {
+                sb = 0;
+                phb ^= 1;
+              }
+            }
+          }
+          umma_commit(&a_empty[sa]);
+          if (++sa == SA) {
+            sa = 0;
+            pha ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int tw = m_tile % p.tiles_w;
+      const int th = (m_tile / p.tiles_w) % p.tiles_h;
+      const int tn = m_tile / (p.tiles_w * p.tiles_h);
+      const int pw = tw * kHaloTW + (row % kHaloTW);
+      const int ph = th * kHaloTH + (row / kHaloTW);
+      const bool valid = (pw < p.Wo) && (ph < p.Ho);
+      const size_t pix = (static_cast<size_t>(tn) * p.Ho + ph) * p.Wo + pw;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      conv_epilogue_tile<BLOCK_N>(p, tmem_base + acc * BLOCK_N, q, n_tile, valid, pix);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& hp, cudaStream_t stream) {
+  const int b_tiles = B_RESIDENT ? hp.c.RS * hp.c.kc_blocks : SB;
+  const int smem = SA * hp.a_stage_bytes + b_tiles * BLOCK_N * 128 + (2 * SA + 2 * SB + 4) * 8 + 16 + 1024;
+  JG_CHECK(smem <= 232448, JG_ERR_INVALID, "conv_halo: smem %d too large", smem);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    JG_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, SA, SB, B_RESIDENT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  const int grid = hp.c.total_tiles < num_sms() ? hp.c.total_tiles : num_sms();
+  conv_halo_kernel<BLOCK_N, SA, SB, B_RESIDENT><<<grid, kThreads, smem, stream>>>(tmA, tmB, hp);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
+int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                     const void* residual, void* y, cudaStream_t stream) {
+  // qualification: stride 1, a real spatial filter, "same"-style geometry handled generally via pad,
+  // tiles of 8 x 16 output pixels must tile the output exactly (ragged sizes go to the generic kernel)
+  if (d->stride != 1 || d->R * d->S == 1 || d->R > 5 || d->S > 5) return JG_ERR_UNSUPPORTED;
+  if (d->Wo % kHaloTW != 0 || d->Ho % kHaloTH != 0) return JG_ERR_UNSUPPORTED;
+  HaloParams hp{};
+  ConvFwdParams& p = hp.c;
+  p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;
+  p.RS = d->R * d->S; p.S = d->S; p.pad = d->pad; p.stride = 1;
+  p.TW = kHaloTW; p.TH = kHaloTH; p.TN = 1;
+  p.tiles_w = d->Wo / kHaloTW;
+  p.tiles_h = d->Ho / kHaloTH;
+  p.tiles_n = d->N;
+  const int block_n = d->Cout > 128 ? 256 : d->Cout > 64 ? 128 : d->Cout > 32 ? 64 : 32;
+  p.n_tiles = ceil_div(d->Cout, block_n);
+  p.kc_blocks = ceil_div(d->Cin, 64);
+  p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  p.ldy = d->ldy; p.ldres = d->ldres; p.act = d->act; p.res_scale = d->res_scale;
+  p.bias = bias;
+  p.res = static_cast<const __nv_bfloat16*>(residual);
+  p.y = static_cast<__nv_bfloat16*>(y);
+  hp.R = d->R;
+  hp.PW = kHaloTW + d->S - 1;
+  hp.PH = kHaloTH + d->R - 1;
+  hp.a_stage_bytes = (hp.PW * hp.PH * 128 + 1023) / 1024 * 1024;
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t strides[3] = {(uint64_t)d->ldx * 2, (uint64_t)d->W * d->ldx * 2, (uint64_t)d->H * d->W * d->ldx * 2};
+    uint32_t box[4] = {64, (uint32_t)hp.PW, (uint32_t)hp.PH, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    rc = make_tmap_bf16(&tmA, x, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  {
+    const int cin8 = (d->Cin + 7) / 8 * 8;
+    uint64_t dims[3] = {(uint64_t)cin8, (uint64_t)p.RS, (uint64_t)d->Cout};
+    uint64_t strides[2] = {(uint64_t)cin8 * 2, (uint64_t)p.RS * cin8 * 2};
+    uint32_t box[3] = {64, 1, (uint32_t)block_n};
+    uint32_t es[3] = {1, 1, 1};
+    rc = make_tmap_bf16(&tmB, w_packed, 3, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  // resident weights: one N tile and all (slab, tap) tiles within ~128 KB
+  const bool resident = p.n_tiles == 1 && (size_t)p.RS * p.kc_blocks * block_n * 128 <= 131072;
+  switch (block_n) {
+    case 256: return launch_halo<256, 3, 4, false>(tmA, tmB, hp, stream);
+    case 128: return launch_halo<128, 4, 6, false>(tmA, tmB, hp, stream);
+    case 64:
+      return resident ? launch_halo<64, 4, 1, true>(tmA, tmB, hp, stream)
+                      : launch_halo<64, 4, 8, false>(tmA, tmB, hp, stream);
+    default:
+      return resident ? launch_halo<32, 4, 1, true>(tmA, tmB, hp, stream)
+                      : launch_halo<32, 4, 8, false>(tmA, tmB, hp, stream);
+  }
+}
+
+}  // namespace jg

@@ -16,40 +16,11 @@
 //
 // Replaces the cuDNN calls behind nn.Conv2d in the reference:
 //   models/modules/unet_generator_attn/unet_generator_attn.py:186-190,208-220,481-483,639-643
-#include "common.cuh"
-#include "ptx.cuh"
+#include "conv_common.cuh"
+
+#include <stdlib.h>
 
 namespace jg {
-
-constexpr int kThreads = 192;
-constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
-
-struct ConvFwdParams {
-  int N, Ho, Wo;
-  int Cout;
-  int RS, S, pad, stride;
-  int TW, TH, TN;
-  int tiles_w, tiles_h, tiles_n;
-  int n_tiles;    // ceil(Cout / BLOCK_N)
-  int kc_blocks;  // ceil(Cin / 64)
-  int total_tiles;
-  int ldy, ldres;
-  int act;
-  float res_scale;
-  const float* bias;
-  const __nv_bfloat16* res;
-  __nv_bfloat16* y;
-};
-
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case JG_ACT_RELU: return v > 0.f ? v : 0.f;
-    case JG_ACT_LRELU02: return v > 0.f ? v : 0.2f * v;
-    case JG_ACT_TANH: return tanhf(v);
-    case JG_ACT_SILU: return v / (1.f + __expf(-v));
-    default: return v;
-  }
-}
 
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -183,51 +154,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c, v);
-        tmem_ld_wait();
-        const int co0 = n_tile * BLOCK_N + c;
-        if (valid && co0 < p.Cout) {
-          __nv_bfloat16* yp = p.y + pix * p.ldy + co0;
-          const __nv_bfloat16* rp = p.res ? p.res + pix * p.ldres + co0 : nullptr;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {  // 8 channels per 16-byte store
-            if (co0 + g * 8 < p.Cout) {
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-              if (p.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + g * 8));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + g * 8 + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              }
-              if (rp) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(rp + g * 8);
-                const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y);
-                const float2 r2 = unpack_bf16x2(rv.z), r3 = unpack_bf16x2(rv.w);
-                f[0] += p.res_scale * r0.x; f[1] += p.res_scale * r0.y;
-                f[2] += p.res_scale * r1.x; f[3] += p.res_scale * r1.y;
-                f[4] += p.res_scale * r2.x; f[5] += p.res_scale * r2.y;
-                f[6] += p.res_scale * r3.x; f[7] += p.res_scale * r3.y;
-              }
-              if (p.act != JG_ACT_NONE) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
-              }
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(yp + g * 8) = o;
-            }
-          }
-        }
-      }
+      conv_epilogue_tile<BLOCK_N>(p, tmem_base + acc * BLOCK_N, q, n_tile, valid, pix);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -522,6 +449,13 @@ extern "C" int jg_conv2d_fwd(const jg_conv_desc* d, const void* x, const void* w
            "conv_fwd: bad ldres %d", d->ldres);
   JG_CHECK(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, JG_ERR_INVALID,
            "conv_fwd: bias must be 16-byte aligned");
+
+  // stride-1 spatial filters on 8x16-tileable outputs: halo-reuse kernel (conv_halo.cu)
+  static const bool no_halo = getenv("JG_NO_HALO") != nullptr;
+  if (!no_halo) {
+    rc = launch_conv_halo(d, x, w_packed, bias, residual, y, stream);
+    if (rc != JG_ERR_UNSUPPORTED) return rc;
+  }
 
   ConvFwdParams p{};
   p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;

@@ -91,6 +91,7 @@ class PaletteTrainer:
         self._static = None
         self._eager_steps = 0
         self.step_dev = torch.zeros((), dtype=torch.int32, device=self.device)
+        self.launches_per_step = 0  # kernels of libjg_b200.so per step (counted on an eager step)
 
     # -- data -----------------------------------------------------------------------------------
     def set_input(self, data, non_blocking=True):
@@ -172,13 +173,18 @@ class PaletteTrainer:
                 dp.allreduce_sum_(self.flat.grad, self.pg)
                 self._graph_opt.replay()
                 self.step += 1
+                from . import lib as L
+                L.launch_count[0] += self.launches_per_step  # the replayed graphs hold the same kernels
                 self.loss_G_tot = self._static_loss
                 return self._static_loss
+        from . import lib as L
+        n0 = L.launch_count[0]
         loss = self._forward_backward(noise=noise, t=t, u=u)
         if self.niter % self.iter_size == 0:
             dp.allreduce_sum_(self.flat.grad, self.pg)
             self._optimizer_step()
         self._eager_steps += 1
+        self.launches_per_step = L.launch_count[0] - n0
         return loss
 
     # -- state ----------------------------------------------------------------------------------

@@ -29,6 +29,11 @@ CASES = [
     ("c3_64_64_256_b4", 4, 256, 256, 64, 64, 3, 1, 1, "bias,time"),
     ("c3_256_256_64_b8", 8, 64, 64, 256, 256, 3, 1, 1, "bias,time"),
     ("c3_512_512_32_b32", 32, 32, 32, 512, 512, 3, 1, 1, "bias,time"),
+    ("c3_128_128_128_b16", 16, 128, 128, 128, 128, 3, 1, 1, "bias,time"),
+    ("c3_64_64_256_b32", 32, 256, 256, 64, 64, 3, 1, 1, "bias,res,time"),
+    ("c3_8_64_256_b8", 8, 256, 256, 8, 64, 3, 1, 1, "bias,time"),
+    ("c3_192_64_256_b8", 8, 256, 256, 192, 64, 3, 1, 1, "bias,time"),
+    ("c3_64_128_64_b4_5x5", 4, 64, 64, 64, 128, 5, 1, 2, ""),
 ]
 
 
@@ -153,12 +158,13 @@ def main():
     sel = range(len(CASES))
     if "--only" in sys.argv:
         sel = [int(v) for v in sys.argv[sys.argv.index("--only") + 1].split(",")]
-    with open(os.path.join(out_dir, "conv_check.jsonl"), "w") as f:
+    tag = os.environ.get("JG_CHECK_TAG", "")
+    with open(os.path.join(out_dir, "conv_check%s.jsonl" % tag), "w") as f:
         for i in sel:
             t0 = time.time()
             try:
                 p = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", str(i)], capture_output=True,
-                                   text=True, timeout=180)
+                                   text=True, timeout=300)
                 lines = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
                 if lines:
                     r = json.loads(lines[-1][7:])
