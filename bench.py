@@ -231,6 +231,10 @@ def main():
             flops = 2.0 * d.N * d.Ho * d.Wo * d.Cout * d.Cin * d.R * d.S
             recs.append((name, flops, e0, e1))
             allrecs.append((name, (d.N, d.H, d.W, d.Cin, d.Cout, d.R, d.stride), flops, e0, e1))
+        elif name == "jg_groupnorm_fwd":
+            allrecs.append((name, tuple(int(v) for v in cargs[4:8]), 0.0, e0, e1))
+        elif name == "jg_groupnorm_bwd":
+            allrecs.append((name, tuple(int(v) for v in cargs[7:11]), 0.0, e0, e1))
         else:
             allrecs.append((name, None, 0.0, e0, e1))
 

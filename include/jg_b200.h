@@ -69,10 +69,11 @@ typedef struct {
 int jg_conv2d_fwd(const jg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                   const void* residual, void* y, jg_stream_t stream);
 
-/* dw[Cout][R*S][Cin] (fp32, OHWI) += sum over pixels dy (x) x.  The caller zeroes dw beforehand
- * (split-K partial sums are accumulated with fp32 atomics).  d describes the FORWARD conv. */
-int jg_conv2d_wgrad(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* dw_ohwi,
-                    jg_stream_t stream);
+/* dw_oihw[Cout][Cin][R][S] = beta*dw_oihw + sum over pixels dy (x) x  (fp32, the reference's weight layout).
+ * ws: fp32 workspace of R*S*Cin*Cout floats (zeroed by the call; split-K partial tiles are accumulated
+ * into it with fp32 atomics, then permuted to OIHW).  d describes the FORWARD conv. */
+int jg_conv2d_wgrad(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* ws, float* dw_oihw,
+                    float beta, jg_stream_t stream);
 
 /* fp32 OIHW master weight -> bf16 packed copies.
  *   w_fwd   [Cout][R*S][Cin8]   (B operand of the forward implicit GEMM)

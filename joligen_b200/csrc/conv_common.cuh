@@ -92,4 +92,8 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvFwdParams& p, uint3
 int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                      const void* residual, void* y, cudaStream_t stream);
 
+// wgrad with halo reuse (conv_halo.cu): zeroes ws, accumulates, writes OIHW; JG_ERR_UNSUPPORTED if not eligible.
+int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* ws, float* dw_oihw,
+                      float beta, cudaStream_t stream);
+
 }  // namespace jg

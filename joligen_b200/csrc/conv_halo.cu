@@ -293,4 +293,256 @@ int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// wgrad with halo reuse
+// ------------------------------------------------------------------------------------------------
+// dW[tap][ci][co] += sum_pixels X[pixel + tap][ci] * dY[pixel][co]
+// Work item = (64-channel ci block, 64-channel co block, pixel range).  Per 64-pixel k-block (an 8x8 patch)
+// ONE X halo patch ((8+S-1) x (8+R-1) pixels x 64 ci) and ONE dY tile (64 pixels x 64 co) are staged; the
+// R*S tap operands are windows of the halo (MN-major, SBO = PW*128).  Two taps share one M = 128 MMA: the
+// second 64 rows of A are the next tap's window (LBO = distance between the two window origins), so a 3x3
+// filter needs 5 MMA groups x N = 64 -> 320 TMEM columns; 9/10 of the issued MMA work is useful.
+// Accumulator layout: fp32 [R*S][Cin][Cout] (HWIO), split-K partials added with red.global.add.v4.f32.
+struct WgradHaloParams {
+  int Cin, Cout, RS, S, pad;
+  int PW, PH, x_stage_bytes;
+  int tiles_w, tiles_h, pix_blocks;
+  int cib, cob, npairs;
+  int ksplit, kb_per_split, total_items;
+  float* acc;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                  const WgradHaloParams p) {
+  constexpr uint32_t TMEM_COLS = 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = 8192 + p.x_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(STAGES) * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // item -> (ci block, co block, split): split fastest
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int split = item % p.ksplit;
+        const int cob = (item / p.ksplit) % p.cob;
+        const int cib = item / (p.ksplit * p.cob);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.pix_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int tw = kb % p.tiles_w;
+          const int th = (kb / p.tiles_w) % p.tiles_h;
+          const int tn = kb / (p.tiles_w * p.tiles_h);
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(8192 + p.PW * p.PH * 128));
+          uint8_t* st = smem + static_cast<size_t>(stage) * stage_bytes;
+          tma_load_4d(st, &tmDY, &full[stage], cob * 64, tw * 8, th * 8, tn);
+          tma_load_4d(st + 8192, &tmX, &full[stage], cib * 64, tw * 8 - p.pad, th * 8 - p.pad, tn);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t sbo_x = static_cast<uint32_t>(p.PW * 128);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int split = item % p.ksplit;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.pix_blocks);
+        mbar_wait(tempty, acc_phase ^ 1);
+        tc_fence_after();
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t dy_addr = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t x_addr = dy_addr + 8192;
+          for (int j = 0; j < p.npairs; ++j) {
+            const int t0 = 2 * j;
+            const int t1 = (t0 + 1 < p.RS) ? t0 + 1 : t0;
+            const int off0 = (t0 / p.S) * p.PW + (t0 % p.S);
+            const int off1 = (t1 / p.S) * p.PW + (t1 % p.S);
+            const uint32_t lbo = static_cast<uint32_t>((off1 - off0) * 128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // 16 pixels per MMA = two 8-pixel rows of the 8x8 patch = two PW-pixel rows of the halo
+              const uint64_t a_desc =
+                  make_smem_desc_sw128(x_addr + static_cast<uint32_t>(off0 * 128) + k * 2 * sbo_x, lbo, sbo_x);
+              const uint64_t b_desc = make_smem_desc_sw128(dy_addr + k * 2048, 8192, 1024);
+              umma_bf16(tmem_base + j * 64, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull);
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int split = item % p.ksplit;
+      const int cob = (item / p.ksplit) % p.cob;
+      const int cib = item / (p.ksplit * p.cob);
+      const bool has_work = split * p.kb_per_split < p.pix_blocks;
+      const int ci = cib * 64 + (row & 63);
+      const int co0 = cob * 64;
+      mbar_wait(tfull, acc_phase);
+      tc_fence_after();
+      for (int j = 0; j < p.npairs; ++j) {
+        const int tap = 2 * j + (row >> 6);
+        const bool ok = has_work && tap < p.RS && ci < p.Cin;
+        float* dst = p.acc + (static_cast<size_t>(tap) * p.Cin + ci) * p.Cout + co0;
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * 64 + c, v);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (co0 + c + g * 4 < p.Cout)
+                red_add_v4(dst + c + g * 4, __uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
+                           __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+      acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// acc [RS][Cin][Cout] (HWIO) -> OIHW
+__global__ void unpack_hwio_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin, int RS,
+                                   float beta) {
+  const long long total = (long long)Cout * Cin * RS;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int tap = (int)(i % RS);
+  const int ci = (int)((i / RS) % Cin);
+  const int co = (int)(i / ((long long)RS * Cin));
+  const float v = src[((long long)tap * Cin + ci) * Cout + co];
+  dst[i] = beta == 0.f ? v : beta * dst[i] + v;
+}
+
+int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* ws, float* dw_oihw,
+                      float beta, cudaStream_t stream) {
+  if (d->stride != 1 || d->R * d->S == 1 || d->R * d->S > 16 || d->R > 5 || d->S > 5) return JG_ERR_UNSUPPORTED;
+  if (d->Wo % 8 != 0 || d->Ho % 8 != 0) return JG_ERR_UNSUPPORTED;
+  WgradHaloParams p{};
+  p.Cin = d->Cin; p.Cout = d->Cout; p.RS = d->R * d->S; p.S = d->S; p.pad = d->pad;
+  p.PW = 8 + d->S - 1;
+  p.PH = 8 + d->R - 1;
+  p.x_stage_bytes = (p.PW * p.PH * 128 + 1023) / 1024 * 1024;
+  p.tiles_w = d->Wo / 8;
+  p.tiles_h = d->Ho / 8;
+  p.pix_blocks = p.tiles_w * p.tiles_h * d->N;
+  p.cib = ceil_div(d->Cin, 64);
+  p.cob = ceil_div(d->Cout, 64);
+  p.npairs = (p.RS + 1) / 2;
+  const int pairs = p.cib * p.cob;
+  int ksplit = num_sms() / pairs;
+  if (ksplit < 1) ksplit = 1;
+  const int max_split = p.pix_blocks / 8 > 0 ? p.pix_blocks / 8 : 1;
+  if (ksplit > max_split) ksplit = max_split;
+  p.kb_per_split = ceil_div(p.pix_blocks, ksplit);
+  p.ksplit = ceil_div(p.pix_blocks, p.kb_per_split);
+  p.total_items = pairs * p.ksplit;
+  p.acc = ws;
+  JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)p.RS * d->Cin * d->Cout, stream));
+
+  CUtensorMap tmDY, tmX;
+  int rc;
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
+    uint64_t strides[3] = {(uint64_t)lddy * 2, (uint64_t)d->Wo * lddy * 2, (uint64_t)d->Ho * d->Wo * lddy * 2};
+    uint32_t box[4] = {64, 8, 8, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    rc = make_tmap_bf16(&tmDY, dy, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t strides[3] = {(uint64_t)d->ldx * 2, (uint64_t)d->W * d->ldx * 2, (uint64_t)d->H * d->W * d->ldx * 2};
+    uint32_t box[4] = {64, (uint32_t)p.PW, (uint32_t)p.PH, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    rc = make_tmap_bf16(&tmX, x, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  constexpr int STAGES = 8;
+  const int smem = STAGES * (8192 + p.x_stage_bytes) + (2 * STAGES + 2) * 8 + 16 + 1024;
+  JG_CHECK(smem <= 232448, JG_ERR_INVALID, "wgrad_halo: smem %d too large", smem);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    JG_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  const int grid = p.total_items < num_sms() ? p.total_items : num_sms();
+  wgrad_halo_kernel<STAGES><<<grid, kThreads, smem, stream>>>(tmDY, tmX, p);
+  JG_LAUNCH_CHECK();
+  const long long total = (long long)d->Cout * d->Cin * p.RS;
+  unpack_hwio_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ws, dw_oihw, d->Cout, d->Cin, p.RS, beta);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
 }  // namespace jg

@@ -501,14 +501,21 @@ extern "C" int jg_conv2d_fwd(const jg_conv_desc* d, const void* x, const void* w
   }
 }
 
-extern "C" int jg_conv2d_wgrad(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* dw,
-                               jg_stream_t stream_) {
+extern "C" int jg_conv2d_wgrad(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* ws,
+                               float* dw_oihw, float beta, jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_desc(d);
   if (rc) return rc;
-  JG_CHECK(x && dy && dw, JG_ERR_INVALID, "conv_wgrad: null pointer");
+  JG_CHECK(x && dy && ws && dw_oihw, JG_ERR_INVALID, "conv_wgrad: null pointer");
   JG_CHECK(d->stride == 1, JG_ERR_INVALID, "conv_wgrad: stride %d not supported yet", d->stride);
   JG_CHECK(lddy % 8 == 0 && lddy >= d->Cout, JG_ERR_INVALID, "conv_wgrad: bad lddy %d", lddy);
+  static const bool no_halo = getenv("JG_NO_HALO") != nullptr;
+  if (!no_halo) {
+    rc = launch_wgrad_halo(d, x, dy, lddy, ws, dw_oihw, beta, stream);
+    if (rc != JG_ERR_UNSUPPORTED) return rc;
+  }
+  float* dw = ws;  // generic kernel: OHWI accumulator
+  JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)d->R * d->S * d->Cin * d->Cout, stream));
 
   ConvWgradParams p{};
   p.Cin = d->Cin; p.Cout = d->Cout; p.RS = d->R * d->S; p.S = d->S; p.pad = d->pad;
@@ -551,9 +558,11 @@ extern "C" int jg_conv2d_wgrad(const jg_conv_desc* d, const void* x, const void*
     if (rc) return rc;
   }
   switch (nb) {
-    case 4: return launch_wgrad<4, 4>(tmDY, tmX, p, stream);
-    case 3: return launch_wgrad<3, 5>(tmDY, tmX, p, stream);
-    case 2: return launch_wgrad<2, 6>(tmDY, tmX, p, stream);
-    default: return launch_wgrad<1, 8>(tmDY, tmX, p, stream);
+    case 4: rc = launch_wgrad<4, 4>(tmDY, tmX, p, stream); break;
+    case 3: rc = launch_wgrad<3, 5>(tmDY, tmX, p, stream); break;
+    case 2: rc = launch_wgrad<2, 6>(tmDY, tmX, p, stream); break;
+    default: rc = launch_wgrad<1, 8>(tmDY, tmX, p, stream); break;
   }
+  if (rc) return rc;
+  return jg_unpack_conv_wgrad(ws, dw_oihw, d->Cout, d->Cin, d->R, d->S, beta, stream_);
 }

@@ -69,10 +69,9 @@ def conv2d_wgrad(x, dy, cout, r, s, stride=1, pad=None):
     """Returns fp32 OIHW weight gradient [cout, Cin, r, s] (Cin = x channels)."""
     cin = x.shape[-1]
     d = make_conv_desc(x, cout, r, s, stride, pad)
-    acc = torch.zeros((cout, r * s, cin), dtype=torch.float32, device=x.device)
-    L.call("jg_conv2d_wgrad", ctypes.byref(d), L.ptr(x), L.ptr(dy), _ld(dy), L.ptr(acc), L.stream())
+    ws = torch.empty((cout * r * s * cin,), dtype=torch.float32, device=x.device)
     out = torch.empty((cout, cin, r, s), dtype=torch.float32, device=x.device)
-    L.call("jg_unpack_conv_wgrad", L.ptr(acc), L.ptr(out), cout, cin, r, s, 0.0, L.stream())
+    L.call("jg_conv2d_wgrad", ctypes.byref(d), L.ptr(x), L.ptr(dy), _ld(dy), L.ptr(ws), L.ptr(out), 0.0, L.stream())
     return out
 
 

@@ -39,7 +39,7 @@ _SIGNATURES = {
     "jg_version": [],
     "jg_check_device": [],
     "jg_conv2d_fwd": [ctypes.POINTER(ConvDesc), c_p, c_p, c_p, c_p, c_p, c_p],
-    "jg_conv2d_wgrad": [ctypes.POINTER(ConvDesc), c_p, c_p, c_int, c_p, c_p],
+    "jg_conv2d_wgrad": [ctypes.POINTER(ConvDesc), c_p, c_p, c_int, c_p, c_p, c_f, c_p],
     "jg_pack_conv_weight": [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],
     "jg_unpack_conv_wgrad": [c_p, c_p, c_int, c_int, c_int, c_int, c_f, c_p],
     "jg_bias_grad": [c_p, c_i64, c_int, c_int, c_p, c_p],
@@ -111,7 +111,7 @@ def ptr(t):
 
 # kernels launched per C-ABI call (memsets excluded) — bench.py's `gpu_launches` claim is counted from these
 KERNELS_PER_CALL = {
-    "jg_conv2d_fwd": 1, "jg_conv2d_wgrad": 1, "jg_pack_conv_weight": 1, "jg_unpack_conv_wgrad": 1, "jg_bias_grad": 1,
+    "jg_conv2d_fwd": 1, "jg_conv2d_wgrad": 2, "jg_pack_conv_weight": 1, "jg_unpack_conv_wgrad": 1, "jg_bias_grad": 1,
     "jg_nchw_f32_to_nhwc_bf16": 1, "jg_nhwc_bf16_to_nchw_f32": 1, "jg_copy_channels": 1, "jg_resample2x": 1,
     "jg_groupnorm_fwd": 3, "jg_groupnorm_bwd": 4, "jg_attn_fwd": 1, "jg_attn_bwd": 3, "jg_linear_fwd": 1,
     "jg_linear_bwd": 2, "jg_noise_pack_fwd": 1, "jg_palette_loss_fwd": 1, "jg_palette_loss_bwd": 1,
