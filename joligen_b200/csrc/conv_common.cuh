@@ -5,7 +5,8 @@
 
 namespace jg {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kWgradThreads = 192;
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 
 struct ConvFwdParams {
@@ -37,34 +38,71 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 
 // Epilogue of one 128 x BLOCK_N output tile held in TMEM: bias + res_scale*residual + activation -> bf16 ->
-// 16-byte global stores.  Called by the 4 epilogue warps (q = TMEM lane quarter of the calling warp).
+// 16-byte global stores.  Called by the 8 epilogue warps: q = TMEM lane quarter of the calling warp, half
+// = which of the two warps of that quarter (they interleave 32-column chunks).  The residual chunk (DRAM
+// latency) is prefetched one chunk ahead; call conv_epilogue_prefetch before waiting for the accumulator.
+struct EpiPrefetch {
+  uint4 r[4];
+};
+
+// All threads: copy bias[0, Cout) (fp32, Cout a multiple of 8) into shared memory (call before __syncthreads).
+__device__ __forceinline__ void conv_stage_bias(const ConvFwdParams& p, float* s_bias) {
+  if (p.bias)
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
+}
+
 template <int BLOCK_N>
-__device__ __forceinline__ void conv_epilogue_tile(const ConvFwdParams& p, uint32_t t_acc, int q, int n_tile,
-                                                   bool valid, size_t pix) {
+__device__ __forceinline__ void conv_epilogue_prefetch(const ConvFwdParams& p, EpiPrefetch& pf, int half, int n_tile,
+                                                       bool valid, size_t pix) {
+  const int c = half * 32;
+  const int co0 = n_tile * BLOCK_N + c;
+  if (p.res && valid && c < BLOCK_N) {
+    const __nv_bfloat16* rp = p.res + pix * p.ldres + co0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (co0 + g * 8 < p.Cout) pf.r[g] = *reinterpret_cast<const uint4*>(rp + g * 8);
+  }
+}
+
+// s_bias: the bias vector staged in shared memory by conv_stage_bias (nullptr when the conv has no bias).
+template <int BLOCK_N>
+__device__ __forceinline__ void conv_epilogue_tile(const ConvFwdParams& p, EpiPrefetch& pf, const float* s_bias,
+                                                   uint32_t t_acc, int q, int half, int n_tile, bool valid,
+                                                   size_t pix) {
   const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-  for (int c = 0; c < BLOCK_N; c += 32) {
+  for (int c = half * 32; c < BLOCK_N; c += 64) {
     uint32_t v[32];
     tmem_ld_32x32(t_row + c, v);
-    tmem_ld_wait();
     const int co0 = n_tile * BLOCK_N + c;
-    if (valid && co0 < p.Cout) {
+    const bool do_store = valid && co0 < p.Cout;
+    uint4 rcur[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) rcur[g] = pf.r[g];
+    // prefetch the next chunk's residual while this one is processed
+    if (p.res && valid && c + 64 < BLOCK_N) {
+      const __nv_bfloat16* rn = p.res + pix * p.ldres + co0 + 64;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (co0 + 64 + g * 8 < p.Cout) pf.r[g] = *reinterpret_cast<const uint4*>(rn + g * 8);
+    }
+    tmem_ld_wait();
+    if (do_store) {
       __nv_bfloat16* yp = p.y + pix * p.ldy + co0;
-      const __nv_bfloat16* rp = p.res ? p.res + pix * p.ldres + co0 : nullptr;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {  // 8 channels per 16-byte store
         if (co0 + g * 8 < p.Cout) {
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-          if (p.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + g * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + g * 8 + 4));
+          if (s_bias) {
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + co0 + g * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + co0 + g * 8 + 4);
             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
             f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
           }
-          if (rp) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(rp + g * 8);
+          if (p.res) {
+            const uint4 rv = rcur[g];
             const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y);
             const float2 r2 = unpack_bf16x2(rv.z), r3 = unpack_bf16x2(rv.w);
             f[0] += p.res_scale * r0.x; f[1] += p.res_scale * r0.y;

@@ -47,6 +47,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull = bars + 2 * SA + 2 * SB;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_bias = reinterpret_cast<float*>(tempty + 4);
+  conv_stage_bias(p, s_bias);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -64,7 +66,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_barrier_init();
   }
@@ -120,69 +122,77 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
-      const uint32_t sbo_a = static_cast<uint32_t>(hp.PW * 128);
-      int sa = 0, sb = 0;
-      uint32_t pha = 0, phb = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      if (B_RESIDENT) {
-        mbar_wait(&b_full[0], 0);
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    const uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+    const uint32_t sbo_a = static_cast<uint32_t>(hp.PW * 128);
+    const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smA), 16, sbo_a);
+    const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smB), 16, 1024);
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if (B_RESIDENT) {
+      mbar_wait(&b_full[0], 0);
+      tc_fence_after();
+    }
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kc = 0; kc < k_slabs; ++kc) {
+        mbar_wait(&a_full[sa], pha);
         tc_fence_after();
-      }
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kc = 0; kc < k_slabs; ++kc) {
-          mbar_wait(&a_full[sa], pha);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smA + sa * hp.a_stage_bytes);
-          for (int tap = 0; tap < p.RS; ++tap) {
-            const int r = tap / p.S;
-            const int s = tap - r * p.S;
-            uint32_t b_addr;
-            if (B_RESIDENT) {
-              b_addr = smem_u32(smB + (kc * p.RS + tap) * B_BYTES);
-            } else {
-              mbar_wait(&b_full[sb], phb);
-              tc_fence_after();
-              b_addr = smem_u32(smB + sb * B_BYTES);
-            }
-            const uint32_t a_addr = a_base + static_cast<uint32_t>((r * hp.PW + s) * 128);
+        const uint64_t a_stage = desc_advance(a_desc0, sa * hp.a_stage_bytes);
+        int r = 0, sx = 0;
+        for (int tap = 0; tap < p.RS; ++tap) {
+          uint64_t b_desc;
+          if (B_RESIDENT) {
+            b_desc = desc_advance(b_desc0, (kc * p.RS + tap) * B_BYTES);
+          } else {
+            mbar_wait(&b_full[sb], phb);
+            tc_fence_after();
+            b_desc = desc_advance(b_desc0, sb * B_BYTES);
+          }
+          const uint64_t a_desc = desc_advance(a_stage, (r * hp.PW + sx) * 128);
+          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t a_desc = make_smem_desc_sw128(a_addr + k * 32, 16, sbo_a);
-              const uint64_t b_desc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-              umma_bf16(d_tmem, a_desc, b_desc, idesc, (kc | tap | k) != 0 ? 1u : 0u);
-            }
-            if (!B_RESIDENT) {
-              umma_commit(&b_empty[sb]);
-              if (++sb == SB) {
-                sb = 0;
-                phb ^= 1;
-              }
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, desc_advance(a_desc, k * 32), desc_advance(b_desc, k * 32), idesc,
+                        (kc | tap | k) != 0 ? 1u : 0u);
+            if (!B_RESIDENT) umma_commit(&b_empty[sb]);
+          }
+          __syncwarp();
+          if (!B_RESIDENT) {
+            if (++sb == SB) {
+              sb = 0;
+              phb ^= 1;
             }
           }
-          umma_commit(&a_empty[sa]);
-          if (++sa == SA) {
-            sa = 0;
-            pha ^= 1;
+          if (++sx == p.S) {
+            sx = 0;
+            ++r;
           }
         }
-        umma_commit(&tfull[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        if (elect_one()) umma_commit(&a_empty[sa]);
+        __syncwarp();
+        if (++sa == SA) {
+          sa = 0;
+          pha ^= 1;
         }
+      }
+      if (elect_one()) umma_commit(&tfull[acc]);
+      __syncwarp();
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    EpiPrefetch pf;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -195,9 +205,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int ph = th * kHaloTH + (row / kHaloTW);
       const bool valid = (pw < p.Wo) && (ph < p.Ho);
       const size_t pix = (static_cast<size_t>(tn) * p.Ho + ph) * p.Wo + pw;
+      conv_epilogue_prefetch<BLOCK_N>(p, pf, half, n_tile, valid, pix);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      conv_epilogue_tile<BLOCK_N>(p, tmem_base + acc * BLOCK_N, q, n_tile, valid, pix);
+      conv_epilogue_tile<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile, valid,
+                                   pix);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -219,7 +231,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& hp, cudaStream_t stream) {
   const int b_tiles = B_RESIDENT ? hp.c.RS * hp.c.kc_blocks : SB;
-  const int smem = SA * hp.a_stage_bytes + b_tiles * BLOCK_N * 128 + (2 * SA + 2 * SB + 4) * 8 + 16 + 1024;
+  const int smem = SA * hp.a_stage_bytes + b_tiles * BLOCK_N * 128 + (2 * SA + 2 * SB + 6) * 8 + 4096 + 1024;
   JG_CHECK(smem <= 232448, JG_ERR_INVALID, "conv_halo: smem %d too large", smem);
   static int attr_smem = 0;
   if (smem > attr_smem) {
@@ -319,7 +331,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 template <int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                   const WgradHaloParams p) {
   constexpr uint32_t TMEM_COLS = 512;
@@ -383,46 +395,61 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
-      const uint32_t sbo_x = static_cast<uint32_t>(p.PW * 128);
-      int stage = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        const int split = item % p.ksplit;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.pix_blocks);
-        mbar_wait(tempty, acc_phase ^ 1);
+    const uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+    const uint32_t sbo_x = static_cast<uint32_t>(p.PW * 128);
+    const uint64_t dy_desc0 = make_smem_desc_sw128(smem_u32(smem), 8192, 1024);
+    const uint64_t x_hi = make_smem_desc_sw128(0, 0, sbo_x);  // start address and LBO are added per tap pair
+    int stage = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int split = item % p.ksplit;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.pix_blocks);
+      mbar_wait(tempty, acc_phase ^ 1);
+      tc_fence_after();
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t dy_addr = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t x_addr = dy_addr + 8192;
-          for (int j = 0; j < p.npairs; ++j) {
-            const int t0 = 2 * j;
-            const int t1 = (t0 + 1 < p.RS) ? t0 + 1 : t0;
-            const int off0 = (t0 / p.S) * p.PW + (t0 % p.S);
-            const int off1 = (t1 / p.S) * p.PW + (t1 % p.S);
-            const uint32_t lbo = static_cast<uint32_t>((off1 - off0) * 128);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // 16 pixels per MMA = two 8-pixel rows of the 8x8 patch = two PW-pixel rows of the halo
-              const uint64_t a_desc =
-                  make_smem_desc_sw128(x_addr + static_cast<uint32_t>(off0 * 128) + k * 2 * sbo_x, lbo, sbo_x);
-              const uint64_t b_desc = make_smem_desc_sw128(dy_addr + k * 2048, 8192, 1024);
-              umma_bf16(tmem_base + j * 64, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            }
+        const uint64_t dy_desc = desc_advance(dy_desc0, stage * stage_bytes);
+        const uint32_t x_addr = smem_u32(smem) + stage * stage_bytes + 8192;
+        const uint32_t first = kb > kb0 ? 1u : 0u;
+        int r0 = 0, s0 = 0;  // tap 2j
+        for (int j = 0; j < p.npairs; ++j) {
+          int r1 = r0, s1 = s0 + 1;  // tap 2j+1
+          if (s1 == p.S) {
+            s1 = 0;
+            ++r1;
           }
-          umma_commit(&empty[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+          const int off0 = r0 * p.PW + s0;
+          const int off1 = (2 * j + 1 < p.RS) ? r1 * p.PW + s1 : off0;
+          // LBO (bits 16..29) = distance between the two taps' window origins, in 16-byte units
+          const uint64_t a_desc = x_hi | static_cast<uint64_t>(((x_addr + off0 * 128) >> 4) & 0x3FFF) |
+                                  (static_cast<uint64_t>(((off1 - off0) * 8) & 0x3FFF) << 16);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              // 16 pixels per MMA = two 8-pixel rows of the 8x8 patch = two PW-pixel rows of the halo
+              umma_bf16(tmem_base + j * 64, desc_advance(a_desc, k * 2 * sbo_x), desc_advance(dy_desc, k * 2048),
+                        idesc, (first | k) != 0 ? 1u : 0u);
+          }
+          __syncwarp();
+          // advance (r0, s0) by two taps
+          s0 += 2;
+          while (s0 >= p.S) {
+            s0 -= p.S;
+            ++r0;
           }
         }
-        umma_commit(tfull);
-        acc_phase ^= 1;
+        if (elect_one()) umma_commit(&empty[stage]);
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one()) umma_commit(tfull);
+      __syncwarp();
+      acc_phase ^= 1;
     }
   } else {
     const int q = warp & 3;
@@ -537,7 +564,7 @@ int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int 
     attr_smem = smem;
   }
   const int grid = p.total_items < num_sms() ? p.total_items : num_sms();
-  wgrad_halo_kernel<STAGES><<<grid, kThreads, smem, stream>>>(tmDY, tmX, p);
+  wgrad_halo_kernel<STAGES><<<grid, kWgradThreads, smem, stream>>>(tmDY, tmX, p);
   JG_LAUNCH_CHECK();
   const long long total = (long long)d->Cout * d->Cin * p.RS;
   unpack_hwio_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ws, dw_oihw, d->Cout, d->Cin, p.RS, beta);

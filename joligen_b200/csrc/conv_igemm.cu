@@ -40,6 +40,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * STAGES + 6);
+  conv_stage_bias(p, s_bias);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -53,7 +55,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_barrier_init();
   }
@@ -100,44 +102,50 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers;
+    // one elected lane issues tcgen05.mma / tcgen05.commit.
+    const uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+    const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smA), 16, 1024);
+    const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smB), 16, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smA + stage * kABytes);
-          const uint32_t b_addr = smem_u32(smB + stage * B_BYTES);
+        const uint64_t a_desc = desc_advance(a_desc0, stage * kABytes);
+        const uint64_t b_desc = desc_advance(b_desc0, stage * B_BYTES);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t a_desc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t b_desc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, desc_advance(a_desc, k * 32), desc_advance(b_desc, k * 32), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tfull[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (elect_one()) umma_commit(&tfull[acc]);
+      __syncwarp();
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    EpiPrefetch pf;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -152,9 +160,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bool valid = (pw < p.Wo) && (ph < p.Ho) && (pn < p.N);
       const size_t pix = (static_cast<size_t>(pn) * p.Ho + ph) * p.Wo + pw;
 
+      conv_epilogue_prefetch<BLOCK_N>(p, pf, half, n_tile, valid, pix);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      conv_epilogue_tile<BLOCK_N>(p, tmem_base + acc * BLOCK_N, q, n_tile, valid, pix);
+      conv_epilogue_tile<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile, valid,
+                                   pix);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -192,7 +202,7 @@ struct ConvWgradParams {
 };
 
 template <int NB, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                   const ConvWgradParams p) {
   constexpr int BLOCK_N = 64 * NB;
@@ -275,43 +285,45 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        const int split = item % p.ksplit;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.pix_blocks);
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    const uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+    // MN-major: 16 K-rows (pixels) per MMA = 2048 B; LBO = next 64-channel block (8192 B), SBO = next
+    // 8-pixel group (1024 B).
+    const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smA), 8192, 1024);
+    const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smB), 8192, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int split = item % p.ksplit;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.pix_blocks);
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smA + stage * kABytes);
-          const uint32_t b_addr = smem_u32(smB + stage * B_BYTES);
+        const uint64_t a_desc = desc_advance(a_desc0, stage * kABytes);
+        const uint64_t b_desc = desc_advance(b_desc0, stage * B_BYTES);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // MN-major: 16 K-rows (pixels) per MMA = 2048 B; LBO = next 64-channel block (8192 B),
-            // SBO = next 8-pixel group (1024 B).
-            const uint64_t a_desc = make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024);
-            const uint64_t b_desc = make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024);
-            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, desc_advance(a_desc, k * 2048), desc_advance(b_desc, k * 2048), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tfull[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (elect_one()) umma_commit(&tfull[acc]);
+      __syncwarp();
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else {
@@ -386,7 +398,7 @@ static void pick_patch(int total, int Wo, int Ho, int* tw, int* th, int* tn) {
 template <int BLOCK_N, int STAGES>
 static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvFwdParams& p,
                       cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (2 * STAGES + 6) * 8 + 4096 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     JG_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -410,7 +422,7 @@ static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const C
     attr_done = true;
   }
   int grid = p.total_items < num_sms() ? p.total_items : num_sms();
-  conv_wgrad_kernel<NB, STAGES><<<grid, kThreads, smem, stream>>>(tmDY, tmX, p);
+  conv_wgrad_kernel<NB, STAGES><<<grid, kWgradThreads, smem, stream>>>(tmDY, tmX, p);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }
@@ -423,6 +435,7 @@ static int check_desc(const jg_conv_desc* d) {
   JG_CHECK(d->Cout > 0 && d->Cout % 8 == 0 && d->ldy % 8 == 0 && d->ldy >= d->Cout, JG_ERR_INVALID,
            "conv: Cout=%d ldy=%d must be multiples of 8 with ldy >= Cout", d->Cout, d->ldy);
   JG_CHECK(d->R > 0 && d->S > 0 && d->R * d->S <= 64, JG_ERR_INVALID, "conv: bad filter %dx%d", d->R, d->S);
+  JG_CHECK(d->Cout <= 1024, JG_ERR_INVALID, "conv: Cout %d > 1024 (bias staging buffer)", d->Cout);
   JG_CHECK(d->stride == 1 || d->stride == 2, JG_ERR_INVALID, "conv: stride %d unsupported", d->stride);
   JG_CHECK(d->up2x == 0, JG_ERR_INVALID, "conv: up2x is reserved");
   const int ho = (d->H + 2 * d->pad - d->R) / d->stride + 1;

@@ -30,16 +30,31 @@ __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __re
   y[idx] = acc;
 }
 // dx[b][i] = act'(x[b][i]) * sum_o dy[b][o] w[o][i]
-__global__ void linear_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                     const float* __restrict__ dy, float* __restrict__ dx, int B, int I, int O,
-                                     int act_in, int accumulate) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * I) return;
-  const int b = idx / I, i = idx % I;
-  float acc = 0.f;
-  for (int o = 0; o < O; ++o) acc += dy[(size_t)b * O + o] * w[(size_t)o * I + i];
-  if (act_in == JG_ACT_SILU) acc *= silu_g(x[idx]);
-  dx[idx] = accumulate ? dx[idx] + acc : acc;
+// one block per batch row; the O reduction is split over blockDim.x / 32 slices and combined in smem.
+__global__ void __launch_bounds__(256)
+linear_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ dy,
+                     float* __restrict__ dx, int B, int I, int O, int act_in, int accumulate) {
+  __shared__ float part[8][32];
+  const int b = blockIdx.x;
+  const int il = threadIdx.x & 31;
+  const int slice = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < I; i0 += 32) {
+    const int i = i0 + il;
+    float acc = 0.f;
+    if (i < I)
+      for (int o = slice; o < O; o += 8) acc += dy[(size_t)b * O + o] * w[(size_t)o * I + i];
+    part[slice][il] = acc;
+    __syncthreads();
+    if (slice == 0 && i < I) {
+      float tot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot += part[k][il];
+      const int idx = b * I + i;
+      if (act_in == JG_ACT_SILU) tot *= silu_g(x[idx]);
+      dx[idx] = accumulate ? dx[idx] + tot : tot;
+    }
+    __syncthreads();
+  }
 }
 // dw[o][i] = sum_b dy[b][o] act(x[b][i]);  db[o] = sum_b dy[b][o]
 __global__ void linear_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
@@ -207,7 +222,7 @@ extern "C" int jg_linear_bwd(const float* x, const float* w, const float* dy, fl
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   JG_CHECK(x && w && dy && B > 0 && I > 0 && O > 0, JG_ERR_INVALID, "linear_bwd: bad args");
   if (dx) {
-    linear_bwd_dx_kernel<<<(B * I + 127) / 128, 128, 0, stream>>>(x, w, dy, dx, B, I, O, act_in, dx_accumulate);
+    linear_bwd_dx_kernel<<<B, 256, 0, stream>>>(x, w, dy, dx, B, I, O, act_in, dx_accumulate);
     JG_LAUNCH_CHECK();
   }
   if (dw) {

@@ -49,6 +49,23 @@ __device__ __forceinline__ float silu_grad(float u) {
   const float s = 1.f / (1.f + __expf(-u));
   return s * (1.f + u * (1.f - s));
 }
+// activation applied after the affine: none / SiLU (UNet) / ReLU, LeakyReLU(0.2) (GAN generator / discriminator)
+__device__ __forceinline__ float act_f(float u, int act) {
+  switch (act) {
+    case JG_ACT_SILU: return silu_f(u);
+    case JG_ACT_RELU: return u > 0.f ? u : 0.f;
+    case JG_ACT_LRELU02: return u > 0.f ? u : 0.2f * u;
+    default: return u;
+  }
+}
+__device__ __forceinline__ float act_grad(float u, int act) {
+  switch (act) {
+    case JG_ACT_SILU: return silu_grad(u);
+    case JG_ACT_RELU: return u > 0.f ? 1.f : 0.f;
+    case JG_ACT_LRELU02: return u > 0.f ? 1.f : 0.2f;
+    default: return 1.f;
+  }
+}
 
 // ---- pass 1 (fwd): per-(n, group) sum and sum of squares --------------------------------------
 // grid (chunks, N); smem: 2*C floats.
@@ -182,7 +199,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __r
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float u = f[j] * a[j] + b[j];
-        f[j] = act == JG_ACT_SILU ? silu_f(u) : u;
+        f[j] = act_f(u, act);
       }
       store8(yb + (size_t)(r + k * rstep) * ldy, f);
     }
@@ -193,7 +210,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __r
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float u = f[j] * a[j] + b[j];
-      f[j] = act == JG_ACT_SILU ? silu_f(u) : u;
+      f[j] = act_f(u, act);
     }
     store8(yb + (size_t)r * ldy, f);
   }
@@ -241,7 +258,7 @@ gn_bwd_sums_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bflo
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float du = d[j];
-          if (act == JG_ACT_SILU) du *= silu_grad(f[j] * a[j] + b[j]);
+          if (act != JG_ACT_NONE) du *= act_grad(f[j] * a[j] + b[j], act);
           sa[j] += du;
           sb[j] += du * f[j];
         }
@@ -254,7 +271,7 @@ gn_bwd_sums_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bflo
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float du = d[j];
-        if (act == JG_ACT_SILU) du *= silu_grad(f[j] * a[j] + b[j]);
+        if (act != JG_ACT_NONE) du *= act_grad(f[j] * a[j] + b[j], act);
         sa[j] += du;
         sb[j] += du * f[j];
       }
@@ -378,7 +395,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfl
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float du = d[j];
-        if (act == JG_ACT_SILU) du *= silu_grad(f[j] * a[j] + b[j]);
+        if (act != JG_ACT_NONE) du *= act_grad(f[j] * a[j] + b[j], act);
         o[j] = c1[j] * du + c2[j] * f[j] + c3[j];
       }
       store8(ob + (size_t)(r + k * rstep) * lddx, o);
@@ -392,7 +409,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfl
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float du = d[j];
-      if (act == JG_ACT_SILU) du *= silu_grad(f[j] * a[j] + b[j]);
+      if (act != JG_ACT_NONE) du *= act_grad(f[j] * a[j] + b[j], act);
       const float val = c1[j] * du + c2[j] * f[j] + c3[j];
       o[j] = accumulate ? o[j] + val : val;
     }
@@ -435,7 +452,8 @@ extern "C" int jg_groupnorm_fwd(const void* x, int ldx, void* y, int ldy, int N,
   if (rc) return rc;
   JG_CHECK(x && y && stats && ab && ws, JG_ERR_INVALID, "groupnorm_fwd: null pointer");
   JG_CHECK(ldy % 8 == 0 && ldy >= C, JG_ERR_INVALID, "groupnorm_fwd: bad ldy");
-  JG_CHECK(act == JG_ACT_NONE || act == JG_ACT_SILU, JG_ERR_INVALID, "groupnorm_fwd: act %d unsupported", act);
+  JG_CHECK(act == JG_ACT_NONE || act == JG_ACT_SILU || act == JG_ACT_RELU || act == JG_ACT_LRELU02, JG_ERR_INVALID,
+           "groupnorm_fwd: act %d unsupported", act);
   JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)N * groups * 2, stream));
   const int rpb = rows_per_block_for(HW, N);
   dim3 grid((HW + rpb - 1) / rpb, N);

@@ -211,6 +211,10 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_
   return d;
 }
 
+// Descriptor whose start address is advanced by `bytes` (the start-address field is the low 14 bits, in
+// 16-byte units; smem addresses are < 256 KB so the add never carries out of the field).
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (bytes >> 4); }
+
 // ----------------------------------------------------------------------------------------------
 // bf16 packing
 // ----------------------------------------------------------------------------------------------
