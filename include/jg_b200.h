@@ -181,6 +181,31 @@ int jg_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, 
                       float beta2, float eps, float weight_decay, int adamw, int step, int* step_dev,
                       float grad_scale, float ema_beta, int ema_init, jg_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * GAN generator / discriminator helpers (NHWC bf16, HBM-bound).
+ *   jg_pad2d_*    nn.ReflectionPad2d / ReplicationPad2d (resnet_generator.py:52-55, 207, 326-331); mode 0 reflect,
+ *                 1 replicate (forward only)
+ *   jg_dilate2x   mode 0: zero insertion dst[2h][2w] = src[h][w] (dst is Hd x Wd = 2H x 2W) — prologue of
+ *                 nn.ConvTranspose2d(k=3, s=2, p=1, output_padding=1) (resnet_generator.py:306-318) and of the
+ *                 dgrad of stride-2 convolutions, both then run as stride-1 implicit GEMMs;
+ *                 mode 1: the adjoint gather dst[h][w] = src[2h][2w] (src is 2Hd x 2Wd)
+ *   jg_act_bwd    dx = dy * act'(x) from the OUTPUT y (tanh: 1 - y^2; (Leaky)ReLU: sign of y)
+ *   jg_gan_loss_* GANLoss (loss.py:11-85) on PatchGAN logits [rows][C]: mode 0 lsgan mean((p-target)^2),
+ *                 1 hinge mean(relu(1 - sign*p)), 2 linear mean(-sign*p)
+ * ------------------------------------------------------------------------------------------- */
+int jg_pad2d_fwd(const void* src, int lds, void* dst, int ldd, int N, int H, int W, int C, int pad, int mode,
+                 jg_stream_t stream);
+int jg_pad2d_bwd(const void* dpad, int ldp, void* dsrc, int lds, int N, int H, int W, int C, int pad, int mode,
+                 jg_stream_t stream);
+int jg_dilate2x(const void* src, int lds, void* dst, int ldd, int N, int Hd, int Wd, int C, int mode,
+                jg_stream_t stream);
+int jg_act_bwd(const void* y, int ldy, const void* dy, int lddy, void* dx, int lddx, int64_t rows, int C, int act,
+               jg_stream_t stream);
+int jg_gan_loss_fwd(const void* pred, int ld, int64_t rows, int C, int mode, float target, float sign, float* loss,
+                    jg_stream_t stream);
+int jg_gan_loss_bwd(const void* pred, int ld, int64_t rows, int C, int mode, float target, float sign,
+                    const float* grad_out, void* dpred, int ldd, jg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

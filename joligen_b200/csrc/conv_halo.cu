@@ -231,7 +231,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& hp, cudaStream_t stream) {
   const int b_tiles = B_RESIDENT ? hp.c.RS * hp.c.kc_blocks : SB;
-  const int smem = SA * hp.a_stage_bytes + b_tiles * BLOCK_N * 128 + (2 * SA + 2 * SB + 6) * 8 + 4096 + 1024;
+  const int smem = SA * hp.a_stage_bytes + b_tiles * BLOCK_N * 128 + (2 * SA + 2 * SB + 6) * 8 + ((hp.c.Cout * 4 + 127) / 128) * 128 + 1024;
   JG_CHECK(smem <= 232448, JG_ERR_INVALID, "conv_halo: smem %d too large", smem);
   static int attr_smem = 0;
   if (smem > attr_smem) {

@@ -188,7 +188,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 struct ConvWgradParams {
   int Cin, Cout;
-  int RS, S, pad;
+  int RS, S, pad, stride;
   int KW, KH, KN;  // 64-pixel k-block patch
   int tiles_w, tiles_h, tiles_n;
   int pix_blocks;  // tiles_w * tiles_h * tiles_n
@@ -275,7 +275,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
             const int ci0 = (bi - tap * p.cblocks) * 64;
             const int r = tap / p.S;
             const int s = tap - r * p.S;
-            tma_load_4d(b + j * 8192, &tmX, &full[stage], ci0, w0 + s - p.pad, h0 + r - p.pad, n0);
+            tma_load_4d(b + j * 8192, &tmX, &full[stage], ci0, w0 * p.stride + s - p.pad,
+                        h0 * p.stride + r - p.pad, n0);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -398,7 +399,7 @@ static void pick_patch(int total, int Wo, int Ho, int* tw, int* th, int* tn) {
 template <int BLOCK_N, int STAGES>
 static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvFwdParams& p,
                       cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (2 * STAGES + 6) * 8 + 4096 + 1024;
+  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (2 * STAGES + 6) * 8 + 8192 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     JG_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -435,13 +436,15 @@ static int check_desc(const jg_conv_desc* d) {
   JG_CHECK(d->Cout > 0 && d->Cout % 8 == 0 && d->ldy % 8 == 0 && d->ldy >= d->Cout, JG_ERR_INVALID,
            "conv: Cout=%d ldy=%d must be multiples of 8 with ldy >= Cout", d->Cout, d->ldy);
   JG_CHECK(d->R > 0 && d->S > 0 && d->R * d->S <= 64, JG_ERR_INVALID, "conv: bad filter %dx%d", d->R, d->S);
-  JG_CHECK(d->Cout <= 1024, JG_ERR_INVALID, "conv: Cout %d > 1024 (bias staging buffer)", d->Cout);
+  JG_CHECK(d->Cout <= 2048, JG_ERR_INVALID, "conv: Cout %d > 2048 (bias staging buffer)", d->Cout);
   JG_CHECK(d->stride == 1 || d->stride == 2, JG_ERR_INVALID, "conv: stride %d unsupported", d->stride);
   JG_CHECK(d->up2x == 0, JG_ERR_INVALID, "conv: up2x is reserved");
   const int ho = (d->H + 2 * d->pad - d->R) / d->stride + 1;
   const int wo = (d->W + 2 * d->pad - d->S) / d->stride + 1;
-  JG_CHECK(ho == d->Ho && wo == d->Wo, JG_ERR_INVALID, "conv: output dims %dx%d do not match %dx%d", d->Ho,
-           d->Wo, ho, wo);
+  // Ho/Wo may be SMALLER than the full correlation size: a cropped output (transposed convolutions with
+  // output_padding read one row/column less than the symmetric-padding formula yields)
+  JG_CHECK(d->Ho <= ho && d->Wo <= wo && d->Ho > 0 && d->Wo > 0, JG_ERR_INVALID,
+           "conv: output dims %dx%d exceed %dx%d", d->Ho, d->Wo, ho, wo);
   return JG_OK;
 }
 
@@ -520,7 +523,6 @@ extern "C" int jg_conv2d_wgrad(const jg_conv_desc* d, const void* x, const void*
   int rc = check_desc(d);
   if (rc) return rc;
   JG_CHECK(x && dy && ws && dw_oihw, JG_ERR_INVALID, "conv_wgrad: null pointer");
-  JG_CHECK(d->stride == 1, JG_ERR_INVALID, "conv_wgrad: stride %d not supported yet", d->stride);
   JG_CHECK(lddy % 8 == 0 && lddy >= d->Cout, JG_ERR_INVALID, "conv_wgrad: bad lddy %d", lddy);
   static const bool no_halo = getenv("JG_NO_HALO") != nullptr;
   if (!no_halo) {
@@ -531,7 +533,7 @@ extern "C" int jg_conv2d_wgrad(const jg_conv_desc* d, const void* x, const void*
   JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)d->R * d->S * d->Cin * d->Cout, stream));
 
   ConvWgradParams p{};
-  p.Cin = d->Cin; p.Cout = d->Cout; p.RS = d->R * d->S; p.S = d->S; p.pad = d->pad;
+  p.Cin = d->Cin; p.Cout = d->Cout; p.RS = d->R * d->S; p.S = d->S; p.pad = d->pad; p.stride = d->stride;
   pick_patch(64, d->Wo, d->Ho, &p.KW, &p.KH, &p.KN);
   p.tiles_w = ceil_div(d->Wo, p.KW);
   p.tiles_h = ceil_div(d->Ho, p.KH);
@@ -565,8 +567,9 @@ extern "C" int jg_conv2d_wgrad(const jg_conv_desc* d, const void* x, const void*
   {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
     uint64_t strides[3] = {(uint64_t)d->ldx * 2, (uint64_t)d->W * d->ldx * 2, (uint64_t)d->H * d->W * d->ldx * 2};
-    uint32_t box[4] = {64, (uint32_t)p.KW, (uint32_t)p.KH, (uint32_t)p.KN};
-    uint32_t es[4] = {1, 1, 1, 1};
+    const uint32_t st = (uint32_t)d->stride;  // stride 2: the box walks every other input pixel
+    uint32_t box[4] = {64, (uint32_t)p.KW * st, (uint32_t)p.KH * st, (uint32_t)p.KN};
+    uint32_t es[4] = {1, st, st, 1};
     rc = make_tmap_bf16(&tmX, x, 4, dims, strides, box, es);
     if (rc) return rc;
   }

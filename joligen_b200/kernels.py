@@ -65,6 +65,21 @@ def conv2d_fwd(x, w_packed, bias, cout, r, s, stride=1, pad=None, act=L.ACT_NONE
     return out
 
 
+def conv2d_cropped(x, w_packed, bias, cout, r, s, pad, out_hw, act=L.ACT_NONE):
+    """stride-1 conv whose output is cropped to out_hw (<= the full correlation size): the transposed
+    convolution / stride-2 dgrad after zero insertion."""
+    n, h, w, cin = x.shape
+    ho, wo = out_hw
+    out = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
+    d = L.ConvDesc()
+    d.N, d.H, d.W, d.Cin, d.ldx = n, h, w, cin, _ld(x)
+    d.Ho, d.Wo, d.Cout, d.ldy = ho, wo, cout, cout
+    d.R, d.S, d.stride, d.pad, d.up2x, d.act = r, s, 1, pad, 0, act
+    d.ldres, d.res_scale = 0, 1.0
+    L.call("jg_conv2d_fwd", ctypes.byref(d), L.ptr(x), L.ptr(w_packed), L.ptr(bias), 0, L.ptr(out), L.stream())
+    return out
+
+
 def conv2d_wgrad(x, dy, cout, r, s, stride=1, pad=None):
     """Returns fp32 OIHW weight gradient [cout, Cin, r, s] (Cin = x channels)."""
     cin = x.shape[-1]
@@ -241,3 +256,63 @@ def adamw_ema_step(p, g, m, v, ema, lr, beta1, beta2, eps, weight_decay, adamw, 
     L.call("jg_adamw_ema_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), L.ptr(ema), p.numel(), float(lr),
            float(beta1), float(beta2), float(eps), float(weight_decay), int(adamw), int(step), L.ptr(step_dev),
            float(grad_scale), float(ema_beta), int(ema_init), L.stream())
+
+
+# ---------------------------------------------------------------------------------------------
+# GAN generator / discriminator helpers
+# ---------------------------------------------------------------------------------------------
+def pad2d(x, pad, mode=0):
+    n, h, w, c = x.shape
+    out = torch.empty((n, h + 2 * pad, w + 2 * pad, c), dtype=torch.bfloat16, device=x.device)
+    L.call("jg_pad2d_fwd", L.ptr(x), _ld(x), L.ptr(out), c, n, h, w, c, pad, mode, L.stream())
+    return out
+
+
+def pad2d_bwd(dpad, pad, mode=0):
+    n, hp, wp, c = dpad.shape
+    h, w = hp - 2 * pad, wp - 2 * pad
+    out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dpad.device)
+    L.call("jg_pad2d_bwd", L.ptr(dpad), _ld(dpad), L.ptr(out), c, n, h, w, c, pad, mode, L.stream())
+    return out
+
+
+def dilate2x(x):
+    """zero insertion: [N,H,W,C] -> [N,2H,2W,C] with x at even positions"""
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+    L.call("jg_dilate2x", L.ptr(x), _ld(x), L.ptr(out), c, n, 2 * h, 2 * w, c, 0, L.stream())
+    return out
+
+
+def undilate2x(x):
+    """adjoint of dilate2x: [N,2H,2W,C] -> [N,H,W,C] taking even positions"""
+    n, h2, w2, c = x.shape
+    out = torch.empty((n, h2 // 2, w2 // 2, c), dtype=torch.bfloat16, device=x.device)
+    L.call("jg_dilate2x", L.ptr(x), _ld(x), L.ptr(out), c, n, h2 // 2, w2 // 2, c, 1, L.stream())
+    return out
+
+
+def act_bwd(y, dy, act):
+    n, h, w, c = y.shape
+    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=y.device)
+    L.call("jg_act_bwd", L.ptr(y), _ld(y), L.ptr(dy), _ld(dy), L.ptr(dx), c, n * h * w, c, act, L.stream())
+    return dx
+
+
+GAN_LSGAN, GAN_HINGE, GAN_LINEAR = 0, 1, 2
+
+
+def gan_loss_fwd(pred, c_real, mode, target, sign):
+    n, h, w, _ = pred.shape
+    loss = torch.empty((), dtype=torch.float32, device=pred.device)
+    L.call("jg_gan_loss_fwd", L.ptr(pred), _ld(pred), n * h * w, c_real, mode, float(target), float(sign), L.ptr(loss),
+           L.stream())
+    return loss
+
+
+def gan_loss_bwd(pred, c_real, mode, target, sign, grad_out):
+    n, h, w, c = pred.shape
+    d = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=pred.device)
+    L.call("jg_gan_loss_bwd", L.ptr(pred), _ld(pred), n * h * w, c_real, mode, float(target), float(sign),
+           L.ptr(grad_out), L.ptr(d), c, L.stream())
+    return d

@@ -60,6 +60,12 @@ _SIGNATURES = {
     "jg_palette_loss_bwd": [c_p, c_p, c_int, c_p, c_p, c_p, c_int, c_int, c_int, c_f, c_int, c_p, c_p, c_int, c_p],
     "jg_adamw_ema_step": [c_p, c_p, c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_f, c_int, c_int, c_p, c_f, c_f,
                           c_int, c_p],
+    "jg_pad2d_fwd": [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_pad2d_bwd": [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_dilate2x": [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_act_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_int, c_p],
+    "jg_gan_loss_fwd": [c_p, c_int, c_i64, c_int, c_int, c_f, c_f, c_p, c_p],
+    "jg_gan_loss_bwd": [c_p, c_int, c_i64, c_int, c_int, c_f, c_f, c_p, c_p, c_int, c_p],
 }
 _SIZE_T_FUNCS = {
     "jg_groupnorm_fwd_ws_floats": [c_int, c_int, c_int],
@@ -115,7 +121,8 @@ KERNELS_PER_CALL = {
     "jg_nchw_f32_to_nhwc_bf16": 1, "jg_nhwc_bf16_to_nchw_f32": 1, "jg_copy_channels": 1, "jg_resample2x": 1,
     "jg_groupnorm_fwd": 3, "jg_groupnorm_bwd": 4, "jg_attn_fwd": 1, "jg_attn_bwd": 3, "jg_linear_fwd": 1,
     "jg_linear_bwd": 2, "jg_noise_pack_fwd": 1, "jg_palette_loss_fwd": 1, "jg_palette_loss_bwd": 1,
-    "jg_adamw_ema_step": 2,
+    "jg_adamw_ema_step": 2, "jg_pad2d_fwd": 1, "jg_pad2d_bwd": 1, "jg_dilate2x": 1, "jg_act_bwd": 1,
+    "jg_gan_loss_fwd": 1, "jg_gan_loss_bwd": 1,
 }
 launch_count = [0]
 call_hook = [None]  # optional profiling hook: fn(name, args) -> context manager

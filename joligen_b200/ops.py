@@ -230,3 +230,146 @@ def to_nchw(x, c):
 
 def palette_loss(noise_hat, noise, mask, w_b=None, lambda_g=1.0, l1=False):
     return PaletteLossFn.apply(noise_hat, noise, mask, w_b, lambda_g, l1)
+
+
+# ---------------------------------------------------------------------------------------------
+# GAN generator / discriminator ops
+# ---------------------------------------------------------------------------------------------
+class ConvActFn(torch.autograd.Function):
+    """Generalised conv for the GAN nets: y = act(conv(x, W, stride) + b), act in {none, lrelu, tanh}.
+
+    stride 2: forward = the strided implicit GEMM; dgrad = zero-insertion of dy then a stride-1 implicit GEMM
+    with the flipped weights (cropped to the input size); wgrad = strided-X implicit GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, wf, wd, bias_p, stride, pad, act):
+        cout, cin, r, s = weight.shape
+        cout8 = (cout + 7) // 8 * 8
+        y = K.conv2d_fwd(x, wf, bias_p, cout8, r, s, stride=stride, pad=pad, act=act)
+        ctx.save_for_backward(x, wd, y if act != L.ACT_NONE else None)
+        ctx.geom = (cout, cin, r, s, stride, pad, act, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wd, y = ctx.saved_tensors
+        cout, cin, r, s, stride, pad, act, has_bias = ctx.geom
+        cout8 = (cout + 7) // 8 * 8
+        dy = dy.contiguous()
+        if act != L.ACT_NONE:
+            dy = K.act_bwd(y, dy, act)
+        dx = dw = db = None
+        n, h, w, cx = x.shape
+        if _needs(ctx, 0):
+            if stride == 1:
+                dx = K.conv2d_fwd(dy, wd, None, cx, r, s, stride=1, pad=r - 1 - pad)
+            else:
+                dyd = K.dilate2x(dy)
+                dx = K.conv2d_cropped(dyd, wd, None, cx, r, s, pad=r - 1 - pad, out_hw=(h, w))
+        if _needs(ctx, 1):
+            dw = K.conv2d_wgrad(x, dy, cout8, r, s, stride=stride, pad=pad)
+            if dw.shape[0] != cout or dw.shape[1] != cin:
+                dw = dw[:cout, :cin].contiguous()
+        if has_bias and _needs(ctx, 2):
+            db = K.bias_grad(dy)
+            if cout8 != cout:
+                db = db[:cout].contiguous()
+        return dx, dw, db, None, None, None, None, None, None
+
+
+class ConvTranspose2dFn(torch.autograd.Function):
+    """nn.ConvTranspose2d(k=3, stride=2, padding=1, output_padding=1) (resnet_generator.py:306-318):
+    y[2H,2W] = the dgrad of a stride-2 3x3 convolution whose OIHW weight is the transposed-conv weight
+    [Cin, Cout, 3, 3] read as O = Cin, I = Cout."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, wf, wd, bias_p, pad):
+        cin, cout, r, s = weight.shape
+        n, h, w, _ = x.shape
+        cout8 = (cout + 7) // 8 * 8
+        xd = K.dilate2x(x)
+        y = K.conv2d_cropped(xd, wd, bias_p, cout8, r, s, pad=r - 1 - pad, out_hw=(2 * h, 2 * w))
+        ctx.save_for_backward(x, wf)
+        ctx.geom = (cin, cout, r, s, pad, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wf = ctx.saved_tensors
+        cin, cout, r, s, pad, has_bias = ctx.geom
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if _needs(ctx, 0):
+            # adjoint of the transposed conv = the stride-2 conv with the same weight (O = Cin_ct, I = Cout_ct)
+            dx = K.conv2d_fwd(dy, wf, None, x.shape[-1], r, s, stride=2, pad=pad)
+        if _needs(ctx, 1):
+            # wgrad of that conv: its input is dy (2H x 2W, Cout_ct channels), its output gradient is x
+            dw = K.conv2d_wgrad(dy, x, x.shape[-1], r, s, stride=2, pad=pad)  # [Cin_ct8, Cout_ct8, r, s]
+            if dw.shape[0] != cin or dw.shape[1] != cout:
+                dw = dw[:cin, :cout].contiguous()
+        if has_bias and _needs(ctx, 2):
+            db = K.bias_grad(dy)
+            if db.shape[0] != cout:
+                db = db[:cout].contiguous()
+        return dx, dw, db, None, None, None, None
+
+
+class Pad2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pad):
+        ctx.pad = pad
+        return K.pad2d(x, pad, 0)
+
+    @staticmethod
+    def backward(ctx, d):
+        return K.pad2d_bwd(d.contiguous(), ctx.pad, 0), None
+
+
+class AddFn(torch.autograd.Function):
+    """a + b for NHWC bf16 tensors (ResnetBlock skip, resnet_generator.py:92-95)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        out = a.clone()
+        K.copy_channels(b, out, accumulate=True)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        return d, d
+
+
+class GanLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, c_real, mode, target, sign):
+        ctx.save_for_backward(pred)
+        ctx.cfg = (c_real, mode, target, sign)
+        return K.gan_loss_fwd(pred, c_real, mode, target, sign)
+
+    @staticmethod
+    def backward(ctx, g):
+        (pred,) = ctx.saved_tensors
+        c_real, mode, target, sign = ctx.cfg
+        return K.gan_loss_bwd(pred, c_real, mode, target, sign, g.contiguous().float()), None, None, None, None
+
+
+def conv_act(x, weight, bias, packed, stride=1, pad=0, act=L.ACT_NONE):
+    wf, wd, bias_p = packed
+    return ConvActFn.apply(x, weight, bias, wf, wd, bias_p, stride, pad, act)
+
+
+def conv_transpose2d(x, weight, bias, packed, pad=1):
+    wf, wd, bias_p = packed
+    return ConvTranspose2dFn.apply(x, weight, bias, wf, wd, bias_p, pad)
+
+
+def reflection_pad(x, pad):
+    return Pad2dFn.apply(x, pad)
+
+
+def add(a, b):
+    return AddFn.apply(a, b)
+
+
+def gan_loss(pred, c_real, mode, target=1.0, sign=1.0):
+    return GanLossFn.apply(pred, c_real, mode, target, sign)

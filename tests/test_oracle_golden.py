@@ -74,3 +74,31 @@ def test_param_count_of_headline_config():
     n = sum(int(torch.Size(s).numel()) for s in shapes.values())
     assert abs(n - 59.35e6) < 0.05e6
     assert len(shapes) + 14 == 338
+
+
+def test_gan_oracle_matches_reference(golden_dir):
+    """ResnetGenerator / NLayerDiscriminator / GANLoss restatements vs the unmodified reference."""
+    from oracle import gan_oracle as G
+    gold = torch.load(os.path.join(golden_dir, "gan_resnet.pt"))
+    shapes = G.resnet_param_shapes(3, 3, gold["ngf"], gold["n_blocks"])
+    leaves = {k: v.requires_grad_(True) for k, v in G.init_from_shapes(shapes, gold["wseed"]).items()}
+    feats = {}
+    y = G.resnet_decoder(leaves, G.resnet_encoder(leaves, gold["x"], gold["n_blocks"], feats=feats))
+    assert _rel(y.detach(), gold["y"]) < 1e-4
+    for lid, f in zip(gold["feat_ids"], gold["feats"]):
+        assert _rel(feats[lid].detach(), f) < 1e-4, lid
+    y.backward(gold["dy"])
+    for k, gref in gold["grads"].items():
+        assert _rel(leaves[k].grad, gref) < 2e-4, k
+    gold = torch.load(os.path.join(golden_dir, "gan_nlayerd.pt"))
+    shapes = G.nlayer_d_param_shapes(3, gold["ndf"], 3)
+    leaves = {k: v.requires_grad_(True) for k, v in G.init_from_shapes(shapes, gold["wseed"]).items()}
+    pred = G.nlayer_discriminator(leaves, gold["x"])
+    assert _rel(pred.detach(), gold["pred"]) < 1e-4
+    assert abs(float(G.gan_loss(pred, True)) - gold["loss_real"]) < 1e-5
+    assert abs(float(G.gan_loss(pred, False)) - gold["loss_fake"]) < 1e-5
+    assert abs(float(G.gan_loss(pred, True, "projected")) - gold["hinge_real"]) < 1e-5
+    assert abs(float(G.gan_loss(pred, False, "projected")) - gold["hinge_fake"]) < 1e-5
+    G.gan_loss(pred, True).backward()
+    for k, gref in gold["grads"].items():
+        assert _rel(leaves[k].grad, gref) < 2e-4, k
