@@ -1,0 +1,214 @@
+"""GPU parity of the GAN generator / discriminator operators:
+per-op checks against plain fp32 torch on the same bf16-rounded operands (1e-2 bf16 / 1e-3 fp32 paths /
+bit-exact index work), then ResnetGenerator and NLayerDiscriminator + GANLoss end to end against the
+golden vectors of the unmodified reference (tests/golden/gan_*.pt; bf16-storage floor as in
+tests/test_gpu_palette.py)."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from joligen_b200 import kernels
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return kernels
+
+
+def rel(a, b):
+    return float((a.float().cpu() - b.float().cpu()).abs().max()) / (float(b.abs().max()) + 1e-12)
+
+
+def rel_l2(a, b):
+    a, b = a.detach().float().cpu().double(), b.detach().float().cpu().double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def r16(x):
+    return x.to(torch.bfloat16).float()
+
+
+def test_reflection_pad_and_dilate_bit_exact(K):
+    g = torch.Generator().manual_seed(0)
+    x = r16(torch.randn(2, 16, 12, 20, generator=g))
+    for pad in (1, 3):
+        xr = x.clone().requires_grad_(True)
+        ref = F.pad(xr, (pad,) * 4, mode="reflect")
+        got = K.pad2d(K.nchw_to_nhwc(x.cuda()), pad, 0)
+        assert torch.equal(K.nhwc_to_nchw(got).cpu(), ref.detach())
+        dy = r16(torch.randn(ref.shape, generator=g))
+        ref.backward(dy)
+        dx = K.pad2d_bwd(K.nchw_to_nhwc(dy.cuda()), pad, 0)
+        assert rel(K.nhwc_to_nchw(dx), xr.grad) < 8e-3  # up to 4 bf16 values summed in fp32, one rounding
+    d = K.dilate2x(K.nchw_to_nhwc(x.cuda()))
+    ref = torch.zeros(2, 16, 24, 40)
+    ref[:, :, ::2, ::2] = x
+    assert torch.equal(K.nhwc_to_nchw(d).cpu(), ref)
+    assert torch.equal(K.nhwc_to_nchw(K.undilate2x(d)).cpu(), x)
+
+
+@pytest.mark.parametrize("case", [(2, 32, 32, 64, 128, 3, 1), (2, 64, 64, 8, 64, 4, 1), (2, 16, 16, 128, 256, 4, 1)])
+def test_stride2_conv_fwd_dgrad_wgrad(K, case):
+    from joligen_b200 import lib as L
+    from joligen_b200 import ops
+    n, h, w, cin, cout, k, pad = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = r16(torch.randn(n, cin, h, w, generator=g))
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    b = 0.1 * torch.randn(cout, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), r16(wt).requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.leaky_relu(F.conv2d(xr, wr, br, stride=2, padding=pad), 0.2)
+    dy = r16(torch.randn(ref.shape, generator=g))
+    ref.backward(dy)
+    xd = K.nchw_to_nhwc(x.cuda()).requires_grad_(True)
+    wd_ = wt.cuda().requires_grad_(True)
+    bd = b.cuda().requires_grad_(True)
+    wf, wdg = K.pack_conv_weight(wd_.detach())
+    y = ops.conv_act(xd, wd_, bd, (wf, wdg, bd.detach()), stride=2, pad=pad, act=L.ACT_LRELU02)
+    assert rel(K.nhwc_to_nchw(y), ref.detach()) < 1e-2
+    y.backward(K.nchw_to_nhwc(dy.cuda()))
+    assert rel(K.nhwc_to_nchw(xd.grad, cin), xr.grad) < 1e-2
+    assert rel(wd_.grad, wr.grad) < 2e-3
+    assert rel(bd.grad, br.grad) < 2e-3
+
+
+def test_conv_transpose_fwd_bwd(K):
+    from joligen_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = r16(torch.randn(2, 128, 16, 16, generator=g))
+    wt = torch.randn(128, 64, 3, 3, generator=g) / math.sqrt(128 * 9 / 4)
+    b = 0.1 * torch.randn(64, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), r16(wt).requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv_transpose2d(xr, wr, br, stride=2, padding=1, output_padding=1)
+    dy = r16(torch.randn(ref.shape, generator=g))
+    ref.backward(dy)
+    xd = K.nchw_to_nhwc(x.cuda()).requires_grad_(True)
+    wd_ = wt.cuda().requires_grad_(True)
+    bd = b.cuda().requires_grad_(True)
+    wf, wdg = K.pack_conv_weight(wd_.detach())
+    y = ops.conv_transpose2d(xd, wd_, bd, (wf, wdg, bd.detach()), pad=1)
+    assert tuple(y.shape) == (2, 32, 32, 64)
+    assert rel(K.nhwc_to_nchw(y), ref.detach()) < 1e-2
+    y.backward(K.nchw_to_nhwc(dy.cuda()))
+    assert rel(K.nhwc_to_nchw(xd.grad), xr.grad) < 1e-2
+    assert rel(wd_.grad, wr.grad) < 2e-3
+    assert rel(bd.grad, br.grad) < 2e-3
+
+
+@pytest.mark.parametrize("act", ["relu", "lrelu", "none"])
+def test_instance_norm_act_fwd_bwd(K, act):
+    from joligen_b200 import lib as L
+    g = torch.Generator().manual_seed(7)
+    x = r16(torch.randn(2, 64, 24, 24, generator=g) * 2 + 0.5)
+    xr = x.clone().requires_grad_(True)
+    h = F.instance_norm(xr, eps=1e-5)
+    ref = F.relu(h) if act == "relu" else (F.leaky_relu(h, 0.2) if act == "lrelu" else h)
+    dy = r16(torch.randn(ref.shape, generator=g))
+    ref.backward(dy)
+    code = {"relu": L.ACT_RELU, "lrelu": L.ACT_LRELU02, "none": L.ACT_NONE}[act]
+    xd = K.nchw_to_nhwc(x.cuda())
+    y, stats, ab = K.groupnorm_fwd(xd, None, None, 64, act=code)
+    assert rel(K.nhwc_to_nchw(y), ref.detach()) < 1e-2
+    dx, _, _, _ = K.groupnorm_bwd(xd, K.nchw_to_nhwc(dy.cuda()), None, None, 64, None, code, stats, ab,
+                                  need_param_grads=False)
+    assert rel(K.nhwc_to_nchw(dx), xr.grad) < 1e-2
+
+
+def test_tanh_epilogue_and_gan_losses(K):
+    from joligen_b200 import lib as L
+    from joligen_b200 import ops
+    from oracle import gan_oracle as G
+    g = torch.Generator().manual_seed(9)
+    x = r16(torch.randn(2, 64, 16, 16, generator=g))
+    wt = torch.randn(3, 64, 7, 7, generator=g) / math.sqrt(64 * 49)
+    b = 0.1 * torch.randn(3, generator=g)
+    xr, wr = x.clone().requires_grad_(True), r16(wt).requires_grad_(True)
+    ref = torch.tanh(F.conv2d(F.pad(xr, (3,) * 4, mode="reflect"), wr, b))
+    dy = r16(torch.randn(ref.shape, generator=g))
+    ref.backward(dy)
+    xd = K.nchw_to_nhwc(x.cuda()).requires_grad_(True)
+    wd_ = wt.cuda().requires_grad_(True)
+    wf, wdg = K.pack_conv_weight(wd_.detach())
+    bias_p = torch.zeros(8, device="cuda")
+    bias_p[:3] = b.cuda()
+    y = ops.conv_act(ops.reflection_pad(xd, 3), wd_, b.cuda(), (wf, wdg, bias_p), stride=1, pad=0, act=L.ACT_TANH)
+    assert rel(K.nhwc_to_nchw(y, 3), ref.detach()) < 1e-2
+    y.backward(K.nchw_to_nhwc(dy.cuda()))
+    assert rel(K.nhwc_to_nchw(xd.grad), xr.grad) < 1.5e-2
+    assert rel(wd_.grad, wr.grad) < 3e-3
+    # GANLoss on 1-channel logits (channel-padded to 8)
+    pred = r16(torch.randn(2, 1, 30, 30, generator=g))
+    for mode, real in (("lsgan", True), ("lsgan", False), ("projected", True), ("projected", False), ("wgangp", True)):
+        pr = pred.clone().requires_grad_(True)
+        ref_loss = G.gan_loss(pr, real, mode)
+        ref_loss.backward()
+        pd = K.nchw_to_nhwc(pred.cuda()).requires_grad_(True)
+        from joligen_b200.nets_gan import GANLoss
+        loss = GANLoss(mode).forward_nhwc(pd, real)
+        assert abs(float(loss) - float(ref_loss)) < 1e-5 * max(1.0, abs(float(ref_loss))), (mode, real)
+        loss.backward()
+        assert rel(K.nhwc_to_nchw(pd.grad, 1), pr.grad) < 8e-3, (mode, real)
+        assert float(pd.grad[..., 1:].float().abs().max()) == 0.0
+
+
+def test_resnet_generator_vs_reference_golden(K, golden_dir):
+    from joligen_b200 import nets_gan
+    from oracle import gan_oracle as G
+    gold = torch.load(os.path.join(golden_dir, "gan_resnet.pt"))
+    net = nets_gan.ResnetGenerator(3, 3, gold["ngf"], n_blocks=gold["n_blocks"])
+    shapes = G.resnet_param_shapes(3, 3, gold["ngf"], gold["n_blocks"])
+    assert [(k, tuple(v.shape)) for k, v in net.named_parameters()] == list(shapes.items())
+    net.load_state_dict(G.init_from_shapes(shapes, gold["wseed"]))
+    net = net.cuda()
+    y = net(gold["x"].cuda())
+    assert rel_l2(y, gold["y"]) < 3e-2
+    y.backward(gold["dy"].cuda())
+    floor = 1e-3 * max(float(v.double().norm()) for v in gold["grads"].values())
+    num = den = 0.0
+    for k, p in net.named_parameters():
+        gref = gold["grads"][k].double()
+        e = float((p.grad.cpu().double() - gref).norm())
+        assert e <= 6e-2 * float(gref.norm()) + floor, k
+        num += e * e
+        den += float(gref.norm()) ** 2
+    assert (num / den) ** 0.5 < 3e-2
+    feats = net.get_feats(gold["x"].cuda(), gold["feat_ids"])
+    assert len(feats) == len(gold["feats"])
+    for f, fref in zip(feats, gold["feats"]):
+        assert tuple(f.shape) == tuple(fref.shape)
+        assert rel_l2(f, fref) < 3e-2
+
+
+def test_nlayer_discriminator_lsgan_vs_reference_golden(K, golden_dir):
+    from joligen_b200 import nets_gan
+    from joligen_b200 import ops
+    from oracle import gan_oracle as G
+    gold = torch.load(os.path.join(golden_dir, "gan_nlayerd.pt"))
+    net = nets_gan.NLayerDiscriminator(3, gold["ndf"], n_layers=3)
+    shapes = G.nlayer_d_param_shapes(3, gold["ndf"], 3)
+    assert [(k, tuple(v.shape)) for k, v in net.named_parameters()] == list(shapes.items())
+    net.load_state_dict(G.init_from_shapes(shapes, gold["wseed"]))
+    net = net.cuda()
+    pred = net(gold["x"].cuda())
+    assert tuple(pred.shape) == tuple(gold["pred"].shape)
+    assert rel_l2(pred, gold["pred"]) < 3e-2
+    crit = nets_gan.GANLoss("lsgan")
+    logits = net.forward_nhwc(ops.to_nhwc(gold["x"].cuda()))
+    loss_real = crit.forward_nhwc(logits, True)
+    assert abs(float(loss_real) - gold["loss_real"]) < 2e-2 * gold["loss_real"]
+    assert abs(float(crit.forward_nhwc(logits, False)) - gold["loss_fake"]) < 2e-2 * gold["loss_fake"]
+    hinge = nets_gan.GANLoss("projected")
+    assert abs(float(hinge.forward_nhwc(logits, True)) - gold["hinge_real"]) < 2e-2 * gold["hinge_real"]
+    loss_real.backward()
+    floor = 1e-3 * max(float(v.double().norm()) for v in gold["grads"].values())
+    for k, p in net.named_parameters():
+        gref = gold["grads"][k].double()
+        assert float((p.grad.cpu().double() - gref).norm()) <= 8e-2 * float(gref.norm()) + floor, k
