@@ -69,7 +69,7 @@ __device__ __forceinline__ float act_grad(float u, int act) {
 
 // ---- pass 1 (fwd): per-(n, group) sum and sum of squares --------------------------------------
 // grid (chunks, N); smem: 2*C floats.
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, 4)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int groups, int rows_per_block,
                 float* __restrict__ sums /*[N][groups][2]*/) {
   extern __shared__ float sm[];
@@ -89,12 +89,12 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int
     const __nv_bfloat16* base = x + ((size_t)n * HW) * ldx + v * 8;
     // 4 independent 16-byte loads in flight per thread
     int r = r0 + rl;
-    for (; r + 3 * rstep < r1; r += 4 * rstep) {
-      uint4 u[4];
+    for (; r + 7 * rstep < r1; r += 8 * rstep) {
+      uint4 u[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = ldg_stream(base + (size_t)(r + k * rstep) * ldx);
+      for (int k = 0; k < 8; ++k) u[k] = ldg_stream(base + (size_t)(r + k * rstep) * ldx);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         float f[8];
         unpack8(u[k], f);
 #pragma unroll
@@ -168,7 +168,7 @@ __global__ void gn_finalize_fwd_kernel(const float* __restrict__ sums, int HW, i
 }
 
 // ---- pass 3 (fwd): y = act(x*a + b) -------------------------------------------------------------
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, 4)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy, int HW, int C,
                 int rows_per_block, const float* __restrict__ ab, int act) {
   const int n = blockIdx.y;
@@ -188,12 +188,12 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __r
   const __nv_bfloat16* xb = x + ((size_t)n * HW) * ldx + v * 8;
   __nv_bfloat16* yb = y + ((size_t)n * HW) * ldy + v * 8;
   int r = r0 + rl;
-  for (; r + 3 * rstep < r1; r += 4 * rstep) {
-    uint4 u4[4];
+  for (; r + 7 * rstep < r1; r += 8 * rstep) {
+    uint4 u4[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u4[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
+    for (int k = 0; k < 8; ++k) u4[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
       float f[8];
       unpack8(u4[k], f);
 #pragma unroll
@@ -218,7 +218,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __r
 
 // ---- bwd pass 1: A[n,c] = sum du, B[n,c] = sum du*x ------------------------------------------
 // grid (chunks, N); smem 2*C floats (block-level reduction before the global atomics).
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, 3)
 gn_bwd_sums_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy, int lddy,
                    int HW, int C, int rows_per_block, const float* __restrict__ ab, int act,
                    float* __restrict__ AB /*[N][C][2]*/) {
@@ -243,15 +243,15 @@ gn_bwd_sums_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bflo
     const __nv_bfloat16* xb = x + ((size_t)n * HW) * ldx + v * 8;
     const __nv_bfloat16* db = dy + ((size_t)n * HW) * lddy + v * 8;
     int r = r0 + rl;
-    for (; r + rstep < r1; r += 2 * rstep) {
-      uint4 ux[2], ud[2];
+    for (; r + 3 * rstep < r1; r += 4 * rstep) {
+      uint4 ux[4], ud[4];
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < 4; ++k) {
         ux[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
         ud[k] = ldg_stream(db + (size_t)(r + k * rstep) * lddy);
       }
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < 4; ++k) {
         float f[8], d[8];
         unpack8(ux[k], f);
         unpack8(ud[k], d);
@@ -351,7 +351,7 @@ __global__ void gn_param_grad_kernel(const float* __restrict__ gAB, int N, int C
 }
 
 // ---- bwd pass 3: dx = k1*du + k2*x + k3 ----------------------------------------------------------
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, 3)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy, int lddy,
                     __nv_bfloat16* __restrict__ dx, int lddx, int HW, int C, int groups, int rows_per_block,
                     const float* __restrict__ ab, int act, const float* __restrict__ k1,
@@ -380,15 +380,15 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfl
   const __nv_bfloat16* db = dy + ((size_t)n * HW) * lddy + v * 8;
   __nv_bfloat16* ob = dx + ((size_t)n * HW) * lddx + v * 8;
   int r = r0 + rl;
-  for (; r + rstep < r1 && !accumulate; r += 2 * rstep) {
-    uint4 ux[2], ud[2];
+  for (; r + 3 * rstep < r1 && !accumulate; r += 4 * rstep) {
+    uint4 ux[4], ud[4];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 4; ++k) {
       ux[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
       ud[k] = ldg_stream(db + (size_t)(r + k * rstep) * lddy);
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 4; ++k) {
       float f[8], d[8], o[8];
       unpack8(ux[k], f);
       unpack8(ud[k], d);
