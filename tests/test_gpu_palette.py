@@ -115,7 +115,10 @@ def test_every_block_matches_bf16_emulated_oracle_fwd_bwd(env):
         gscale = max(float(leaves[k].grad.double().norm()) for k in keys)
         for k in keys:
             ga, gb = local[k[len(name) + 1:]].grad.detach().cpu().double(), leaves[k].grad.double()
-            errs["d" + k[len(name) + 1:]] = float((ga - gb).norm()) / max(float(gb.norm()), 5e-3 * gscale)
+            short = k[len(name) + 1:]
+            # in_layers.2.bias feeds a GroupNorm with ONE channel per group here: its true gradient is exactly 0
+            floor = (5e-2 if short == "in_layers.2.bias" else 5e-3) * gscale
+            errs["d" + short] = float((ga - gb).norm()) / max(float(gb.norm()), floor)
         # activations / input gradients 3e-3; parameter gradients (sums over all pixels of bf16 products) 6e-3
         bad = {k: v for k, v in errs.items() if v > (3e-3 if k in ("out", "dx", "demb") else 6e-3)}
         assert not bad, (name, b.kind, bad)
