@@ -99,34 +99,67 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def usable_cpu_threads():
+    """Host threads this process can really run on: scheduler affinity capped by the cgroup CPU quota (a container
+    that sees 128 logical CPUs but is throttled to a few cores makes a 128-thread torch run pathologically slow)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // period))
+            break
+        except Exception:
+            continue
+    return n
+
+
 def make_cfg(O, size):
     return O.UNetCfg(image_size=size)
 
 
-def cpu_reference_throughput(size, steps, threads=None):
-    """Oracle port of the reference's CPU training step (fp32, torch CPU kernels, all host cores)."""
+def cpu_reference_throughput(size, steps, threads=None, budget_s=40.0):
+    """Oracle port of the reference's CPU training step (fp32, torch CPU kernels) on the host cores.
+    Bounded sample: thread pools are warmed on one 64x64 step, then up to `steps` steps of batch 1 at the
+    full resolution are timed, stopping once `budget_s` seconds are spent (at least one step)."""
     from oracle import palette_oracle as O
-    threads = threads or os.cpu_count()
+    if threads is None:
+        threads = int(os.environ.get("JG_CPU_THREADS", "0")) or min(usable_cpu_threads(), torch.get_num_threads())
     torch.set_num_threads(threads)
-    cfg = make_cfg(O, size)
-    state = O.TrainState(params=O.init_params(cfg, 1234))
     oc = O.OptimCfg(lr=1e-4)
     b = 1
-    times = []
-    for s in range(steps + 1):
-        data = O.synthetic_batch(b, size, 77 + s)
-        torch.manual_seed(s)
+
+    def one_step(state, cfg, sz, seed):
+        data = O.synthetic_batch(b, sz, 77 + seed)
+        torch.manual_seed(seed)
         t, u = O.sample_t_gamma(cfg, b)
         noise = torch.randn_like(data["gt"])
         t0 = time.perf_counter()
         O.train_step(state, cfg, oc, data["gt"], data["cond"], data["mask"], noise, t, u)
-        dt = time.perf_counter() - t0
-        if s > 0:  # first step = warm-up
-            times.append(dt)
+        return time.perf_counter() - t0
+
+    cfg = make_cfg(O, size)
+    state = O.TrainState(params=O.init_params(cfg, 1234))
+    one_step(state, make_cfg(O, 64), 64, 0)  # warm-up (same weights, small crop)
+    times = []
+    for s in range(steps):
+        times.append(one_step(state, cfg, size, 1 + s))
+        if sum(times) > budget_s:
+            break
     sec = sum(times) / len(times)
     return {"value": b / sec, "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": "%d step(s) of batch %d at %dx%d after 1 warm-up, fp32 torch-CPU oracle port, %.1f s/step" % (
-                len(times), b, size, size, sec)}
+            "sample": "%d step(s) of batch %d at %dx%d (fwd+loss+bwd+AdamW+EMA), fp32 torch-CPU oracle port, "
+                      "%d threads of %d logical CPUs, %.1f s/step" % (len(times), b, size, size, threads,
+                                                                      os.cpu_count() or 0, sec)}
 
 
 def run_reference(args):

@@ -44,9 +44,21 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   o.w = pack_bf16x2(f[6], f[7]);
   *reinterpret_cast<uint4*>(p) = o;
 }
-__device__ __forceinline__ float silu_f(float u) { return u / (1.f + __expf(-u)); }
+// sigmoid with ONE MUFU op per element (ex2); the reciprocal of 1 + e in [1, inf) is a bit-trick seed plus three
+// Newton steps on the FMA pipe (relative error < 1e-7).  At HBM speed these kernels need ~6 elements/cycle/SM:
+// two MUFU ops per element (ex2 + rcp) would put the 16/cycle/SM special-function unit on the critical path.
+__device__ __forceinline__ float fast_sigmoid(float u) {
+  const float e = exp2f(-1.4426950408889634f * fminf(fmaxf(u, -80.f), 80.f));
+  const float x = 1.f + e;
+  float r = __int_as_float(0x7EF311C7 - __float_as_int(x));
+  r = r * (2.f - x * r);
+  r = r * (2.f - x * r);
+  r = r * (2.f - x * r);
+  return r;
+}
+__device__ __forceinline__ float silu_f(float u) { return u * fast_sigmoid(u); }
 __device__ __forceinline__ float silu_grad(float u) {
-  const float s = 1.f / (1.f + __expf(-u));
+  const float s = fast_sigmoid(u);
   return s * (1.f + u * (1.f - s));
 }
 // activation applied after the affine: none / SiLU (UNet) / ReLU, LeakyReLU(0.2) (GAN generator / discriminator)

@@ -154,3 +154,23 @@ def gan_loss(pred, target_is_real, mode="lsgan", relu=True):
             return F.relu(1 - pred).mean() if target_is_real else F.relu(1 + pred).mean()
         return (-pred).mean()
     raise NotImplementedError(mode)
+
+
+def gan_train_step(state_G, state_D, oc_G, oc_D, real_A, real_B, n_blocks=9, n_layers=3, lambda_gan=1.0, mode="lsgan"):
+    """One optimize_parameters() of the (G), (D) groups restricted to the GAN terms
+    (cut_model.py:406-437, base_gan_model.py:382-419,457-503, loss.py:288-313).  Returns (loss_G, loss_D)."""
+    from .palette_oracle import adam_update
+    gl = {k: v.detach().clone().requires_grad_(True) for k, v in state_G.params.items()}
+    dl = {k: v.detach().clone() for k, v in state_D.params.items()}
+    fake = resnet_generator(gl, real_A, n_blocks)
+    loss_G = lambda_gan * gan_loss(nlayer_discriminator(dl, fake, n_layers), True, mode, relu=False)
+    loss_G.backward()
+    with torch.no_grad():
+        adam_update(state_G, {k: v.grad for k, v in gl.items()}, oc_G)
+    dl = {k: v.detach().clone().requires_grad_(True) for k, v in state_D.params.items()}
+    loss_D = 0.5 * (gan_loss(nlayer_discriminator(dl, real_B, n_layers), True, mode)
+                    + gan_loss(nlayer_discriminator(dl, fake.detach(), n_layers), False, mode))
+    loss_D.backward()
+    with torch.no_grad():
+        adam_update(state_D, {k: v.grad for k, v in dl.items()}, oc_D)
+    return loss_G.detach(), loss_D.detach()

@@ -223,3 +223,40 @@ def test_nlayer_discriminator_lsgan_vs_reference_golden(K, golden_dir):
     for k, p in net.named_parameters():
         gref = gold["grads"][k].double()
         assert float((p.grad.cpu().double() - gref).norm()) <= 8e-2 * float(gref.norm()) + floor, k
+
+
+def test_gan_train_step_matches_oracle(K):
+    """Two optimize_parameters() of the (G) and (D) groups (lsgan, Adam) vs the oracle's restatement."""
+    from joligen_b200 import nets_gan
+    from joligen_b200.trainer_gan import GanTrainer
+    from oracle import gan_oracle as G
+    from oracle import palette_oracle as O
+    ngf, nb, ndf = 16, 2, 16
+    gshapes, dshapes = G.resnet_param_shapes(3, 3, ngf, nb), G.nlayer_d_param_shapes(3, ndf, 3)
+    gp, dpar = G.init_from_shapes(gshapes, 41), G.init_from_shapes(dshapes, 42)
+    netG = nets_gan.ResnetGenerator(3, 3, ngf, n_blocks=nb)
+    netD = nets_gan.NLayerDiscriminator(3, ndf, n_layers=3)
+    netG.load_state_dict(gp)
+    netD.load_state_dict(dpar)
+    tr = GanTrainer(netG, netD, gan_mode="lsgan", G_lr=2e-4, D_lr=1e-4, optim="adam")
+    sG = O.TrainState(params={k: v.clone() for k, v in gp.items()})
+    sD = O.TrainState(params={k: v.clone() for k, v in dpar.items()})
+    ocG = O.OptimCfg(lr=2e-4, kind="adam", ema_beta=0.999)
+    ocD = O.OptimCfg(lr=1e-4, kind="adam", ema_beta=0.999)
+    g = torch.Generator().manual_seed(3)
+    for step in range(2):
+        a = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+        b = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+        tr.set_input({"A": a, "B": b})
+        lg, ld = tr.optimize_parameters()
+        rg, rd = G.gan_train_step(sG, sD, ocG, ocD, a, b, n_blocks=nb)
+        assert abs(float(lg) - float(rg)) < 3e-2 * abs(float(rg)), (step, float(lg), float(rg))
+        assert abs(float(ld) - float(rd)) < 3e-2 * abs(float(rd)), (step, float(ld), float(rd))
+    # weights moved like the oracle's (Adam: +-lr per element early on; compare update directions in aggregate)
+    num = den = 0.0
+    for k, p in netD.named_parameters():
+        if p.dim() > 1:
+            u, ur = p.detach().cpu().double() - dpar[k].double(), sD.params[k].double() - dpar[k].double()
+            num += float((u * ur).sum())
+            den += float(u.norm() * ur.norm())
+    assert num / den > 0.7
