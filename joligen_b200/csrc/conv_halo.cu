@@ -135,30 +135,31 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&b_full[0], 0);
       tc_fence_after();
     }
+    const uint32_t row_skip16 = static_cast<uint32_t>((hp.PW - p.S) * 128) >> 4;  // window origin step at a filter-row end
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      uint64_t b_res = b_desc0;  // resident weights: tiles are consecutive in (slab, tap) order
       for (int kc = 0; kc < k_slabs; ++kc) {
         mbar_wait(&a_full[sa], pha);
         tc_fence_after();
-        const uint64_t a_stage = desc_advance(a_desc0, sa * hp.a_stage_bytes);
-        int r = 0, sx = 0;
+        uint64_t a_desc = a_desc0 + (static_cast<uint32_t>(sa * hp.a_stage_bytes) >> 4);
+        int sx = 0;
         for (int tap = 0; tap < p.RS; ++tap) {
           uint64_t b_desc;
           if (B_RESIDENT) {
-            b_desc = desc_advance(b_desc0, (kc * p.RS + tap) * B_BYTES);
+            b_desc = b_res;
+            b_res += B_BYTES >> 4;
           } else {
             mbar_wait(&b_full[sb], phb);
             tc_fence_after();
-            b_desc = desc_advance(b_desc0, sb * B_BYTES);
+            b_desc = b_desc0 + (static_cast<uint32_t>(sb * B_BYTES) >> 4);
           }
-          const uint64_t a_desc = desc_advance(a_stage, (r * hp.PW + sx) * 128);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, desc_advance(a_desc, k * 32), desc_advance(b_desc, k * 32), idesc,
-                        (kc | tap | k) != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
             if (!B_RESIDENT) umma_commit(&b_empty[sb]);
           }
           __syncwarp();
@@ -168,9 +169,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               phb ^= 1;
             }
           }
+          // next tap: one pixel (128 B) to the right, or to the start of the next filter row
+          a_desc += 8;
           if (++sx == p.S) {
             sx = 0;
-            ++r;
+            a_desc += row_skip16;
           }
         }
         if (elect_one()) umma_commit(&a_empty[sa]);
@@ -398,7 +401,21 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     const uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
     const uint32_t sbo_x = static_cast<uint32_t>(p.PW * 128);
     const uint64_t dy_desc0 = make_smem_desc_sw128(smem_u32(smem), 8192, 1024);
-    const uint64_t x_hi = make_smem_desc_sw128(0, 0, sbo_x);  // start address and LBO are added per tap pair
+    // X-window descriptor of stage 0 / tap 0 with LBO = 0; per tap pair only the start address (low bits)
+    // and the LBO field (bits 16..29 = distance between the two taps' window origins) differ: precompute
+    // those deltas once so that the issue loop is a handful of 64-bit adds per MMA (with N = 64 an MMA
+    // retires every 48 cycles: a longer issue sequence makes the issuing lane the bottleneck).
+    const uint64_t x_desc0 = make_smem_desc_sw128(smem_u32(smem) + 8192, 0, sbo_x);
+    uint64_t pair_delta[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int t0 = 2 * j;
+      const int t1 = (t0 + 1 < p.RS) ? t0 + 1 : t0;
+      const int off0 = (t0 / p.S) * p.PW + (t0 % p.S);
+      const int off1 = (t1 / p.S) * p.PW + (t1 % p.S);
+      pair_delta[j] = static_cast<uint64_t>(off0 * 8) | (static_cast<uint64_t>(((off1 - off0) * 8) & 0x3FFF) << 16);
+    }
+    const uint32_t kstep_x = (2 * sbo_x) >> 4;  // 16 pixels = two PW-pixel rows of the halo, in 16-byte units
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -410,37 +427,22 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint64_t dy_desc = desc_advance(dy_desc0, stage * stage_bytes);
-        const uint32_t x_addr = smem_u32(smem) + stage * stage_bytes + 8192;
+        const uint32_t st16 = static_cast<uint32_t>(stage * stage_bytes) >> 4;
+        const uint64_t dy_desc = dy_desc0 + st16;
+        const uint64_t x_desc = x_desc0 + st16;
         const uint32_t first = kb > kb0 ? 1u : 0u;
-        int r0 = 0, s0 = 0;  // tap 2j
-        for (int j = 0; j < p.npairs; ++j) {
-          int r1 = r0, s1 = s0 + 1;  // tap 2j+1
-          if (s1 == p.S) {
-            s1 = 0;
-            ++r1;
-          }
-          const int off0 = r0 * p.PW + s0;
-          const int off1 = (2 * j + 1 < p.RS) ? r1 * p.PW + s1 : off0;
-          // LBO (bits 16..29) = distance between the two taps' window origins, in 16-byte units
-          const uint64_t a_desc = x_hi | static_cast<uint64_t>(((x_addr + off0 * 128) >> 4) & 0x3FFF) |
-                                  (static_cast<uint64_t>(((off1 - off0) * 8) & 0x3FFF) << 16);
-          if (elect_one()) {
+        if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              // 16 pixels per MMA = two 8-pixel rows of the 8x8 patch = two PW-pixel rows of the halo
-              umma_bf16(tmem_base + j * 64, desc_advance(a_desc, k * 2 * sbo_x), desc_advance(dy_desc, k * 2048),
-                        idesc, (first | k) != 0 ? 1u : 0u);
+          for (int j = 0; j < 8; ++j) {
+            if (j < p.npairs) {
+              const uint64_t a_desc = x_desc + pair_delta[j];
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + j * 64, a_desc + k * kstep_x, dy_desc + k * 128, idesc, (first | k) != 0 ? 1u : 0u);
+            }
           }
-          __syncwarp();
-          // advance (r0, s0) by two taps
-          s0 += 2;
-          while (s0 >= p.S) {
-            s0 -= p.S;
-            ++r0;
-          }
+          umma_commit(&empty[stage]);
         }
-        if (elect_one()) umma_commit(&empty[stage]);
         __syncwarp();
         if (++stage == STAGES) {
           stage = 0;

@@ -80,13 +80,16 @@ def conv2d_cropped(x, w_packed, bias, cout, r, s, pad, out_hw, act=L.ACT_NONE):
     return out
 
 
-def conv2d_wgrad(x, dy, cout, r, s, stride=1, pad=None):
-    """Returns fp32 OIHW weight gradient [cout, Cin, r, s] (Cin = x channels)."""
+def conv2d_wgrad(x, dy, cout, r, s, stride=1, pad=None, out=None, beta=0.0):
+    """fp32 OIHW weight gradient [cout, Cin, r, s] (Cin = x channels): out = beta*out + dW."""
     cin = x.shape[-1]
     d = make_conv_desc(x, cout, r, s, stride, pad)
     ws = torch.empty((cout * r * s * cin,), dtype=torch.float32, device=x.device)
-    out = torch.empty((cout, cin, r, s), dtype=torch.float32, device=x.device)
-    L.call("jg_conv2d_wgrad", ctypes.byref(d), L.ptr(x), L.ptr(dy), _ld(dy), L.ptr(ws), L.ptr(out), 0.0, L.stream())
+    if out is None:
+        out = torch.empty((cout, cin, r, s), dtype=torch.float32, device=x.device)
+        beta = 0.0
+    L.call("jg_conv2d_wgrad", ctypes.byref(d), L.ptr(x), L.ptr(dy), _ld(dy), L.ptr(ws), L.ptr(out), float(beta),
+           L.stream())
     return out
 
 

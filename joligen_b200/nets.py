@@ -66,7 +66,7 @@ def _conv(x, conv, pack, residual=None, res_scale=1.0):
     if w.dim() == 3:
         w = w.unsqueeze(-1)
     return ops.conv2d(x, w, conv.bias, pack.get(), stride=conv.stride[0], pad=conv.padding[0], residual=residual,
-                      res_scale=res_scale)
+                      res_scale=res_scale, grad_sink=conv.weight)
 
 
 class GroupNorm(nn.Module):

@@ -19,12 +19,13 @@ class Conv2dFn(torch.autograd.Function):
     round_up(Cout, 8) channels (padding channels are exactly zero)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, wf, wd, bias_p, stride, pad, res_scale):
+    def forward(ctx, x, weight, bias, residual, wf, wd, bias_p, stride, pad, res_scale, sink):
         cout, cin, r, s = weight.shape
         cout8 = (cout + 7) // 8 * 8
         y = K.conv2d_fwd(x, wf, bias_p, cout8, r, s, stride=stride, pad=pad, residual=residual, res_scale=res_scale)
         ctx.save_for_backward(x, wd)
         ctx.geom = (cout, cin, r, s, stride, pad, res_scale, bias is not None, residual is not None)
+        ctx.sink = sink  # (weight Parameter,) or None: accumulate dW straight into its .grad when possible
         return y
 
     @staticmethod
@@ -39,16 +40,26 @@ class Conv2dFn(torch.autograd.Function):
                 raise RuntimeError("Conv2dFn: dgrad for stride %d is not implemented" % stride)
             dx = K.conv2d_fwd(dy, wd, None, x.shape[-1], r, s, stride=1, pad=r - 1 - pad)
         if _needs(ctx, 1):
-            dw = K.conv2d_wgrad(x, dy, cout8, r, s, stride=stride, pad=pad)
-            if dw.shape[0] != cout or dw.shape[1] != cin:  # zero-padded channels (e.g. 6 -> 8, 3 -> 8)
-                dw = dw[:cout, :cin].contiguous()
+            g = None
+            if ctx.sink is not None and cout8 == cout and x.shape[-1] == cin:
+                g = ctx.sink[0].grad
+                if g is not None and not (g.is_contiguous() and g.dtype == torch.float32 and g.numel() == cout * cin * r * s):
+                    g = None
+            if g is not None:
+                # the unpack epilogue of the wgrad adds into the existing .grad (beta = 1): no separate
+                # gradient tensor, no autograd accumulation kernel
+                K.conv2d_wgrad(x, dy, cout8, r, s, stride=stride, pad=pad, out=g, beta=1.0)
+            else:
+                dw = K.conv2d_wgrad(x, dy, cout8, r, s, stride=stride, pad=pad)
+                if dw.shape[0] != cout or dw.shape[1] != cin:  # zero-padded channels (e.g. 6 -> 8, 3 -> 8)
+                    dw = dw[:cout, :cin].contiguous()
         if has_bias and _needs(ctx, 2):
             db = K.bias_grad(dy)
             if cout8 != cout:
                 db = db[:cout].contiguous()
         if has_res and _needs(ctx, 3):
             dres = dy if res_scale == 1.0 else (dy.float() * res_scale).to(torch.bfloat16)
-        return dx, dw, db, dres, None, None, None, None, None, None
+        return dx, dw, db, dres, None, None, None, None, None, None, None
 
 
 class GroupNormFn(torch.autograd.Function):
@@ -187,13 +198,15 @@ class PaletteLossFn(torch.autograd.Function):
         return K.palette_loss_bwd(noise, noise_hat, mask, w_b, g, lambda_g, l1), None, None, None, None, None
 
 
-def conv2d(x, weight, bias, packed, stride=1, pad=None, residual=None, res_scale=1.0):
-    """packed = (wf, wd, bias_padded) from nets.ConvPack.get()."""
+def conv2d(x, weight, bias, packed, stride=1, pad=None, residual=None, res_scale=1.0, grad_sink=None):
+    """packed = (wf, wd, bias_padded) from nets.ConvPack.get(); grad_sink = the weight nn.Parameter whose
+    (pre-existing, fp32, contiguous) .grad the weight gradient is accumulated into directly."""
     r = weight.shape[2]
     if pad is None:
         pad = (r - 1) // 2
     wf, wd, bias_p = packed
-    return Conv2dFn.apply(x, weight, bias, residual, wf, wd, bias_p, stride, pad, res_scale)
+    return Conv2dFn.apply(x, weight, bias, residual, wf, wd, bias_p, stride, pad, res_scale,
+                          None if grad_sink is None else (grad_sink,))
 
 
 def group_norm(x, gamma, beta, groups, film=None, act=L.ACT_NONE):
