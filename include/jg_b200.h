@@ -117,8 +117,11 @@ size_t jg_groupnorm_bwd_ws_floats(int N, int C, int groups);
 int jg_groupnorm_fwd(const void* x, int ldx, void* y, int ldy, int N, int HW, int C, int groups, float eps,
                      const float* gamma, const float* beta, const float* film, int act, float* stats, float* ab,
                      float* ws, jg_stream_t stream);
-/* dx (=|+=) d/dx; dgamma/dbeta [C] overwritten (may be NULL); dfilm [N][2C] overwritten (may be NULL). */
-int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int accumulate, int N,
+/* dx = d/dx (+ addend, an NHWC bf16 tensor like dx with stride ldadd, or NULL: the gradient of a second consumer
+ * of x — e.g. the ResBlock's skip path — summed in the same pass; addend may alias dx);
+ * dgamma/dbeta [C] overwritten (may be NULL); dfilm [N][2C] overwritten (may be NULL). */
+int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, const void* addend,
+                     int ldadd, int N,
                      int HW, int C, int groups, const float* gamma, const float* beta, const float* film, int act,
                      const float* stats, const float* ab, float* dgamma, float* dbeta, float* dfilm, float* ws,
                      jg_stream_t stream);

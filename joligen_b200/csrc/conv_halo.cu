@@ -15,6 +15,8 @@
 // Same warp roles / TMEM double buffering / epilogue as conv_igemm.cu.
 #include "conv_common.cuh"
 
+#include <stdlib.h>
+
 namespace jg {
 
 constexpr int kHaloTW = 8, kHaloTH = 16;
@@ -323,7 +325,8 @@ struct WgradHaloParams {
   int Cin, Cout, RS, S, pad;
   int PW, PH, x_stage_bytes;
   int tiles_w, tiles_h, pix_blocks;
-  int cib, cob, npairs;
+  int cib, cob;
+  int tap0, ntaps, npairs;  // this launch covers taps [tap0, tap0 + ntaps) as npairs = ceil(ntaps / 2) MMA groups
   int ksplit, kb_per_split, total_items;
   float* acc;
 };
@@ -333,14 +336,19 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-template <int STAGES>
+// NCO = output-channel block = N of the MMA (64 or 128).  tools/umma_bench.cu: an M128 x N64 MMA is shared-memory
+// bound (48 cycles instead of 32: 6 KB of operands per MMA), N = 128 runs at the full tensor rate — but 5 tap
+// pairs x 128 columns exceed the 512 TMEM columns, so with NCO = 128 a 3x3 filter is covered by two launches
+// (taps 0..7 as 4 pairs, then tap 8), while NCO = 64 covers all 9 taps in one.
+template <int STAGES, int NCO>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                   const WgradHaloParams p) {
   constexpr uint32_t TMEM_COLS = 512;
+  constexpr int DY_BYTES = 8192 * (NCO / 64);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = 8192 + p.x_stage_bytes;
+  const int stage_bytes = DY_BYTES + p.x_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(STAGES) * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
@@ -386,10 +394,12 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           const int th = (kb / p.tiles_w) % p.tiles_h;
           const int tn = kb / (p.tiles_w * p.tiles_h);
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(8192 + p.PW * p.PH * 128));
+          mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(DY_BYTES + p.PW * p.PH * 128));
           uint8_t* st = smem + static_cast<size_t>(stage) * stage_bytes;
-          tma_load_4d(st, &tmDY, &full[stage], cob * 64, tw * 8, th * 8, tn);
-          tma_load_4d(st + 8192, &tmX, &full[stage], cib * 64, tw * 8 - p.pad, th * 8 - p.pad, tn);
+#pragma unroll
+          for (int h = 0; h < NCO / 64; ++h)
+            tma_load_4d(st + h * 8192, &tmDY, &full[stage], cob * NCO + h * 64, tw * 8, th * 8, tn);
+          tma_load_4d(st + DY_BYTES, &tmX, &full[stage], cib * 64, tw * 8 - p.pad, th * 8 - p.pad, tn);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -398,19 +408,18 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+    const uint32_t idesc = make_idesc_bf16(128, NCO, 1, 1);
     const uint32_t sbo_x = static_cast<uint32_t>(p.PW * 128);
     const uint64_t dy_desc0 = make_smem_desc_sw128(smem_u32(smem), 8192, 1024);
-    // X-window descriptor of stage 0 / tap 0 with LBO = 0; per tap pair only the start address (low bits)
-    // and the LBO field (bits 16..29 = distance between the two taps' window origins) differ: precompute
-    // those deltas once so that the issue loop is a handful of 64-bit adds per MMA (with N = 64 an MMA
-    // retires every 48 cycles: a longer issue sequence makes the issuing lane the bottleneck).
-    const uint64_t x_desc0 = make_smem_desc_sw128(smem_u32(smem) + 8192, 0, sbo_x);
+    // X-window descriptor of stage 0 / window origin 0 with LBO = 0; per tap pair only the start address (low
+    // bits) and the LBO field (bits 16..29 = distance between the two taps' window origins) differ: those
+    // deltas are precomputed so that the issue loop is a handful of 64-bit adds per MMA.
+    const uint64_t x_desc0 = make_smem_desc_sw128(smem_u32(smem) + DY_BYTES, 0, sbo_x);
     uint64_t pair_delta[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int t0 = 2 * j;
-      const int t1 = (t0 + 1 < p.RS) ? t0 + 1 : t0;
+      const int t0 = p.tap0 + 2 * j;
+      const int t1 = (2 * j + 1 < p.ntaps) ? t0 + 1 : t0;
       const int off0 = (t0 / p.S) * p.PW + (t0 % p.S);
       const int off1 = (t1 / p.S) * p.PW + (t1 % p.S);
       pair_delta[j] = static_cast<uint64_t>(off0 * 8) | (static_cast<uint64_t>(((off1 - off0) * 8) & 0x3FFF) << 16);
@@ -438,7 +447,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
               const uint64_t a_desc = x_desc + pair_delta[j];
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_base + j * 64, a_desc + k * kstep_x, dy_desc + k * 128, idesc, (first | k) != 0 ? 1u : 0u);
+                umma_bf16(tmem_base + j * NCO, a_desc + k * kstep_x, dy_desc + k * 128, idesc,
+                          (first | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(&empty[stage]);
@@ -463,17 +473,18 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       const int cib = item / (p.ksplit * p.cob);
       const bool has_work = split * p.kb_per_split < p.pix_blocks;
       const int ci = cib * 64 + (row & 63);
-      const int co0 = cob * 64;
+      const int co0 = cob * NCO;
       mbar_wait(tfull, acc_phase);
       tc_fence_after();
       for (int j = 0; j < p.npairs; ++j) {
-        const int tap = 2 * j + (row >> 6);
-        const bool ok = has_work && tap < p.RS && ci < p.Cin;
+        const int tl = 2 * j + (row >> 6);  // tap index within this launch
+        const int tap = p.tap0 + tl;
+        const bool ok = has_work && tl < p.ntaps && ci < p.Cin;
         float* dst = p.acc + (static_cast<size_t>(tap) * p.Cin + ci) * p.Cout + co0;
 #pragma unroll 1
-        for (int c = 0; c < 64; c += 32) {
+        for (int c = 0; c < NCO; c += 32) {
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * 64 + c, v);
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * NCO + c, v);
           tmem_ld_wait();
           if (ok) {
 #pragma unroll
@@ -513,10 +524,29 @@ __global__ void unpack_hwio_kernel(const float* __restrict__ src, float* __restr
   dst[i] = beta == 0.f ? v : beta * dst[i] + v;
 }
 
+template <int STAGES, int NCO>
+static int launch_wgrad_halo_one(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradHaloParams& p,
+                                 cudaStream_t stream) {
+  const int smem = STAGES * (8192 * (NCO / 64) + p.x_stage_bytes) + (2 * STAGES + 2) * 8 + 16 + 1024;
+  JG_CHECK(smem <= 232448, JG_ERR_INVALID, "wgrad_halo: smem %d too large", smem);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    JG_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<STAGES, NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  const int grid = p.total_items < num_sms() ? p.total_items : num_sms();
+  wgrad_halo_kernel<STAGES, NCO><<<grid, kWgradThreads, smem, stream>>>(tmDY, tmX, p);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
 int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* ws, float* dw_oihw,
                       float beta, cudaStream_t stream) {
-  if (d->stride != 1 || d->R * d->S == 1 || d->R * d->S > 16 || d->R > 5 || d->S > 5) return JG_ERR_UNSUPPORTED;
+  if (d->stride != 1 || d->R * d->S == 1 || d->R * d->S > 32 || d->R > 5 || d->S > 5) return JG_ERR_UNSUPPORTED;
   if (d->Wo % 8 != 0 || d->Ho % 8 != 0) return JG_ERR_UNSUPPORTED;
+  static const bool force64 = getenv("JG_WGRAD_N64") != nullptr;
+  const int nco = (d->Cout >= 128 && !force64) ? 128 : 64;
+  const int taps_per_launch = nco == 128 ? 8 : 16;  // 512 TMEM columns / nco columns per pair * 2 taps per pair
   WgradHaloParams p{};
   p.Cin = d->Cin; p.Cout = d->Cout; p.RS = d->R * d->S; p.S = d->S; p.pad = d->pad;
   p.PW = 8 + d->S - 1;
@@ -526,8 +556,7 @@ int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int 
   p.tiles_h = d->Ho / 8;
   p.pix_blocks = p.tiles_w * p.tiles_h * d->N;
   p.cib = ceil_div(d->Cin, 64);
-  p.cob = ceil_div(d->Cout, 64);
-  p.npairs = (p.RS + 1) / 2;
+  p.cob = ceil_div(d->Cout, nco);
   const int pairs = p.cib * p.cob;
   int ksplit = num_sms() / pairs;
   if (ksplit < 1) ksplit = 1;
@@ -557,17 +586,14 @@ int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int 
     rc = make_tmap_bf16(&tmX, x, 4, dims, strides, box, es);
     if (rc) return rc;
   }
-  constexpr int STAGES = 8;
-  const int smem = STAGES * (8192 + p.x_stage_bytes) + (2 * STAGES + 2) * 8 + 16 + 1024;
-  JG_CHECK(smem <= 232448, JG_ERR_INVALID, "wgrad_halo: smem %d too large", smem);
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    JG_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
+  for (int t0 = 0; t0 < p.RS; t0 += taps_per_launch) {
+    p.tap0 = t0;
+    p.ntaps = p.RS - t0 < taps_per_launch ? p.RS - t0 : taps_per_launch;
+    p.npairs = (p.ntaps + 1) / 2;
+    rc = nco == 128 ? launch_wgrad_halo_one<7, 128>(tmDY, tmX, p, stream)
+                    : launch_wgrad_halo_one<8, 64>(tmDY, tmX, p, stream);
+    if (rc) return rc;
   }
-  const int grid = p.total_items < num_sms() ? p.total_items : num_sms();
-  wgrad_halo_kernel<STAGES><<<grid, kWgradThreads, smem, stream>>>(tmDY, tmX, p);
-  JG_LAUNCH_CHECK();
   const long long total = (long long)d->Cout * d->Cin * p.RS;
   unpack_hwio_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ws, dw_oihw, d->Cout, d->Cin, p.RS, beta);
   JG_LAUNCH_CHECK();

@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(kNormThreads, 3)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy, int lddy,
                     __nv_bfloat16* __restrict__ dx, int lddx, int HW, int C, int groups, int rows_per_block,
                     const float* __restrict__ ab, int act, const float* __restrict__ k1,
-                    const float* __restrict__ k23, int accumulate) {
+                    const float* __restrict__ k23, const __nv_bfloat16* __restrict__ addend, int ldadd) {
   const int n = blockIdx.y;
   const int vecs = C / 8;
   const int rstep = kNormThreads / vecs;
@@ -391,24 +391,28 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfl
   const __nv_bfloat16* xb = x + ((size_t)n * HW) * ldx + v * 8;
   const __nv_bfloat16* db = dy + ((size_t)n * HW) * lddy + v * 8;
   __nv_bfloat16* ob = dx + ((size_t)n * HW) * lddx + v * 8;
+  const __nv_bfloat16* ab_ = addend ? addend + ((size_t)n * HW) * ldadd + v * 8 : nullptr;
   int r = r0 + rl;
-  for (; r + 3 * rstep < r1 && !accumulate; r += 4 * rstep) {
-    uint4 ux[4], ud[4];
+  for (; r + 3 * rstep < r1; r += 4 * rstep) {
+    uint4 ux[4], ud[4], ua[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       ux[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
       ud[k] = ldg_stream(db + (size_t)(r + k * rstep) * lddy);
+      if (ab_) ua[k] = *reinterpret_cast<const uint4*>(ab_ + (size_t)(r + k * rstep) * ldadd);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float f[8], d[8], o[8];
+      float f[8], d[8], o[8], e[8];
       unpack8(ux[k], f);
       unpack8(ud[k], d);
+      if (ab_) unpack8(ua[k], e);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float du = d[j];
         if (act != JG_ACT_NONE) du *= act_grad(f[j] * a[j] + b[j], act);
         o[j] = c1[j] * du + c2[j] * f[j] + c3[j];
+        if (ab_) o[j] += e[j];
       }
       store8(ob + (size_t)(r + k * rstep) * lddx, o);
     }
@@ -417,13 +421,13 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfl
     float f[8], d[8], o[8];
     load8(xb + (size_t)r * ldx, f);
     load8(db + (size_t)r * lddy, d);
-    if (accumulate) load8(ob + (size_t)r * lddx, o);
+    if (ab_) load8(ab_ + (size_t)r * ldadd, o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float du = d[j];
       if (act != JG_ACT_NONE) du *= act_grad(f[j] * a[j] + b[j], act);
       const float val = c1[j] * du + c2[j] * f[j] + c3[j];
-      o[j] = accumulate ? o[j] + val : val;
+      o[j] = ab_ ? o[j] + val : val;
     }
     store8(ob + (size_t)r * lddx, o);
   }
@@ -480,7 +484,8 @@ extern "C" int jg_groupnorm_fwd(const void* x, int ldx, void* y, int ldy, int N,
   return JG_OK;
 }
 
-extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int accumulate,
+extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, const void* addend,
+                                int ldadd,
                                 int N, int HW, int C, int groups, const float* gamma, const float* beta,
                                 const float* film, int act, const float* stats, const float* ab, float* dgamma,
                                 float* dbeta, float* dfilm, float* ws, jg_stream_t stream_) {
@@ -489,6 +494,7 @@ extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy
   if (rc) return rc;
   JG_CHECK(x && dy && dx && stats && ab && ws, JG_ERR_INVALID, "groupnorm_bwd: null pointer");
   JG_CHECK(lddy % 8 == 0 && lddy >= C && lddx % 8 == 0 && lddx >= C, JG_ERR_INVALID, "groupnorm_bwd: bad ld");
+  JG_CHECK(addend == nullptr || (ldadd % 8 == 0 && ldadd >= C), JG_ERR_INVALID, "groupnorm_bwd: bad ldadd");
   float* AB = ws;
   float* k1 = AB + (size_t)N * C * 2;
   float* k23 = k1 + (size_t)N * C;
@@ -509,7 +515,8 @@ extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy
   }
   gn_bwd_apply_kernel<<<grid, kNormThreads, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(dy), lddy,
-      static_cast<__nv_bfloat16*>(dx), lddx, HW, C, groups, rpb, ab, act, k1, k23, accumulate);
+      static_cast<__nv_bfloat16*>(dx), lddx, HW, C, groups, rpb, ab, act, k1, k23,
+      static_cast<const __nv_bfloat16*>(addend), ldadd);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }

@@ -79,6 +79,10 @@ class GroupNorm(nn.Module):
     def forward_nhwc(self, x, film=None, act=L.ACT_NONE):
         return ops.group_norm(x, self.norm.weight, self.norm.bias, self.norm.num_groups, film=film, act=act)
 
+    def forward_tap_nhwc(self, x, act=L.ACT_NONE):
+        """-> (y, x_tap); every other consumer of x must read x_tap (gradient sum fused into the GN backward)."""
+        return ops.group_norm_tap(x, self.norm.weight, self.norm.bias, self.norm.num_groups, film=None, act=act)
+
 
 def normalization(channels, norm="groupnorm32"):
     if "groupnorm" in norm:
@@ -164,7 +168,7 @@ class ResBlock(EmbedBlock):
         self._pack_skip = ConvPack(self.skip_connection) if isinstance(self.skip_connection, nn.Conv2d) else None
 
     def forward_nhwc(self, x, emb):
-        h = self.in_layers[0].forward_nhwc(x, act=L.ACT_SILU)
+        h, x = self.in_layers[0].forward_tap_nhwc(x, act=L.ACT_SILU)
         if self.updown:
             h = self.h_upd.forward_nhwc(h)
             x = self.x_upd.forward_nhwc(x)
@@ -217,7 +221,7 @@ class AttentionBlock(nn.Module):
 
     def forward_nhwc(self, x):
         c = self.channels
-        xn = ops.group_norm(x, None, None, c, film=None, act=L.ACT_NONE)  # per-(n, c) statistics over T
+        xn, x = ops.group_norm_tap(x, None, None, c, film=None, act=L.ACT_NONE)  # per-(n, c) statistics over T
         qkv = _conv(xn, self.qkv, self._pack_qkv)
         a = ops.attention(qkv, self.num_heads, c // self.num_heads)
         return _conv(a, self.proj_out, self._pack_proj, residual=x, res_scale=1.0)

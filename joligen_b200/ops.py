@@ -84,6 +84,33 @@ class GroupNormFn(torch.autograd.Function):
         return dx, dgamma, dbeta, dfilm, None, None
 
 
+class GroupNormTapFn(torch.autograd.Function):
+    """GroupNorm(+FiLM)(+act) that also hands its input through: returns (y, x_tap).  x has two consumers in a
+    ResBlock / AttentionBlock (the norm and the skip path); routing the skip path through x_tap lets the backward
+    sum both gradients inside the GN-backward apply pass (dx = GN'(dy) + d_tap) instead of a separate add kernel."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, film, groups, act):
+        y, stats, ab = K.groupnorm_fwd(x, gamma, beta, groups, film=film, act=act)
+        ctx.save_for_backward(x, gamma, beta, film, stats, ab)
+        ctx.cfg = (groups, act)
+        return y, x.detach()
+
+    @staticmethod
+    def backward(ctx, dy, dtap):
+        x, gamma, beta, film, stats, ab = ctx.saved_tensors
+        groups, act = ctx.cfg
+        if dy is None:
+            return dtap, None, None, None, None, None
+        dy = dy.contiguous()
+        need_p = gamma is not None and (_needs(ctx, 1) or _needs(ctx, 2))
+        need_f = film is not None and _needs(ctx, 3)
+        dx, dgamma, dbeta, dfilm = K.groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab,
+                                                   need_param_grads=need_p, need_film_grad=need_f,
+                                                   addend=None if dtap is None else dtap.contiguous())
+        return dx, dgamma, dbeta, dfilm, None, None
+
+
 class AttentionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, heads, ch):
@@ -211,6 +238,11 @@ def conv2d(x, weight, bias, packed, stride=1, pad=None, residual=None, res_scale
 
 def group_norm(x, gamma, beta, groups, film=None, act=L.ACT_NONE):
     return GroupNormFn.apply(x, gamma, beta, film, groups, act)
+
+
+def group_norm_tap(x, gamma, beta, groups, film=None, act=L.ACT_NONE):
+    """-> (y, x_tap): use x_tap for every other consumer of x (see GroupNormTapFn)."""
+    return GroupNormTapFn.apply(x, gamma, beta, film, groups, act)
 
 
 def attention(qkv, heads, ch):
