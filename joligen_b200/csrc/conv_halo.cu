@@ -545,7 +545,9 @@ int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int 
   if (d->stride != 1 || d->R * d->S == 1 || d->R * d->S > 32 || d->R > 5 || d->S > 5) return JG_ERR_UNSUPPORTED;
   if (d->Wo % 8 != 0 || d->Ho % 8 != 0) return JG_ERR_UNSUPPORTED;
   static const bool force64 = getenv("JG_WGRAD_N64") != nullptr;
-  const int nco = (d->Cout >= 128 && !force64) ? 128 : 64;
+  // N = 128 runs the MMA at full rate (N = 64 is shared-memory bound at 2/3 rate) but holds only 8 taps in TMEM, so a 3x3
+  // filter takes two passes over the activations; past 9 taps the extra passes cost more than the MMA rate buys.
+  const int nco = (d->Cout >= 128 && d->R * d->S <= 9 && !force64) ? 128 : 64;
   const int taps_per_launch = nco == 128 ? 8 : 16;  // 512 TMEM columns / nco columns per pair * 2 taps per pair
   WgradHaloParams p{};
   p.Cin = d->Cin; p.Cout = d->Cout; p.RS = d->R * d->S; p.S = d->S; p.pad = d->pad;

@@ -180,7 +180,7 @@ __global__ void gn_finalize_fwd_kernel(const float* __restrict__ sums, int HW, i
 }
 
 // ---- pass 3 (fwd): y = act(x*a + b) -------------------------------------------------------------
-__global__ void __launch_bounds__(kNormThreads, 4)
+__global__ void __launch_bounds__(kNormThreads, 3)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy, int HW, int C,
                 int rows_per_block, const float* __restrict__ ab, int act) {
   const int n = blockIdx.y;
@@ -230,7 +230,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __r
 
 // ---- bwd pass 1: A[n,c] = sum du, B[n,c] = sum du*x ------------------------------------------
 // grid (chunks, N); smem 2*C floats (block-level reduction before the global atomics).
-__global__ void __launch_bounds__(kNormThreads, 3)
+__global__ void __launch_bounds__(kNormThreads, 2)
 gn_bwd_sums_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy, int lddy,
                    int HW, int C, int rows_per_block, const float* __restrict__ ab, int act,
                    float* __restrict__ AB /*[N][C][2]*/) {
@@ -362,8 +362,11 @@ __global__ void gn_param_grad_kernel(const float* __restrict__ gAB, int N, int C
   if (dgamma) dgamma[c] = sb;
 }
 
-// ---- bwd pass 3: dx = k1*du + k2*x + k3 ----------------------------------------------------------
-__global__ void __launch_bounds__(kNormThreads, 3)
+// ---- bwd pass 3: dx = k1*du + k2*x + k3 (+ addend) ----------------------------------------------
+// U rows are kept in flight per thread.  The per-channel constants take 40 registers, so the row unroll is what decides
+// whether the kernel spills: two blocks per SM (128 registers) with U = 3 (addend) or 4 keeps ~50 KB in flight per SM.
+template <bool HAS_ADD, int U>
+__global__ void __launch_bounds__(kNormThreads, 2)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy, int lddy,
                     __nv_bfloat16* __restrict__ dx, int lddx, int HW, int C, int groups, int rows_per_block,
                     const float* __restrict__ ab, int act, const float* __restrict__ k1,
@@ -391,43 +394,43 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfl
   const __nv_bfloat16* xb = x + ((size_t)n * HW) * ldx + v * 8;
   const __nv_bfloat16* db = dy + ((size_t)n * HW) * lddy + v * 8;
   __nv_bfloat16* ob = dx + ((size_t)n * HW) * lddx + v * 8;
-  const __nv_bfloat16* ab_ = addend ? addend + ((size_t)n * HW) * ldadd + v * 8 : nullptr;
+  const __nv_bfloat16* eb = HAS_ADD ? addend + ((size_t)n * HW) * ldadd + v * 8 : nullptr;
   int r = r0 + rl;
-  for (; r + 3 * rstep < r1; r += 4 * rstep) {
-    uint4 ux[4], ud[4], ua[4];
+  for (; r + (U - 1) * rstep < r1; r += U * rstep) {
+    uint4 ux[U], ud[U], ua[U];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < U; ++k) {
       ux[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
       ud[k] = ldg_stream(db + (size_t)(r + k * rstep) * lddy);
-      if (ab_) ua[k] = *reinterpret_cast<const uint4*>(ab_ + (size_t)(r + k * rstep) * ldadd);
+      if (HAS_ADD) ua[k] = ldg_stream(eb + (size_t)(r + k * rstep) * ldadd);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < U; ++k) {
       float f[8], d[8], o[8], e[8];
       unpack8(ux[k], f);
       unpack8(ud[k], d);
-      if (ab_) unpack8(ua[k], e);
+      if (HAS_ADD) unpack8(ua[k], e);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float du = d[j];
         if (act != JG_ACT_NONE) du *= act_grad(f[j] * a[j] + b[j], act);
         o[j] = c1[j] * du + c2[j] * f[j] + c3[j];
-        if (ab_) o[j] += e[j];
+        if (HAS_ADD) o[j] += e[j];
       }
       store8(ob + (size_t)(r + k * rstep) * lddx, o);
     }
   }
   for (; r < r1; r += rstep) {
-    float f[8], d[8], o[8];
+    float f[8], d[8], o[8], e[8];
     load8(xb + (size_t)r * ldx, f);
     load8(db + (size_t)r * lddy, d);
-    if (ab_) load8(ab_ + (size_t)r * ldadd, o);
+    if (HAS_ADD) load8(eb + (size_t)r * ldadd, e);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float du = d[j];
       if (act != JG_ACT_NONE) du *= act_grad(f[j] * a[j] + b[j], act);
-      const float val = c1[j] * du + c2[j] * f[j] + c3[j];
-      o[j] = ab_ ? o[j] + val : val;
+      o[j] = c1[j] * du + c2[j] * f[j] + c3[j];
+      if (HAS_ADD) o[j] += e[j];
     }
     store8(ob + (size_t)r * lddx, o);
   }
@@ -513,10 +516,15 @@ extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy
     gn_param_grad_kernel<<<(C + 127) / 128, 128, 0, stream>>>(gAB, N, C, dgamma, dbeta);
     JG_LAUNCH_CHECK();
   }
-  gn_bwd_apply_kernel<<<grid, kNormThreads, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(dy), lddy,
-      static_cast<__nv_bfloat16*>(dx), lddx, HW, C, groups, rpb, ab, act, k1, k23,
-      static_cast<const __nv_bfloat16*>(addend), ldadd);
+  if (addend)
+    gn_bwd_apply_kernel<true, 3><<<grid, kNormThreads, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(dy), lddy,
+        static_cast<__nv_bfloat16*>(dx), lddx, HW, C, groups, rpb, ab, act, k1, k23,
+        static_cast<const __nv_bfloat16*>(addend), ldadd);
+  else
+    gn_bwd_apply_kernel<false, 4><<<grid, kNormThreads, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(dy), lddy,
+        static_cast<__nv_bfloat16*>(dx), lddx, HW, C, groups, rpb, ab, act, k1, k23, nullptr, 0);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }
