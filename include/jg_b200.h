@@ -119,12 +119,14 @@ int jg_groupnorm_fwd(const void* x, int ldx, void* y, int ldy, int N, int HW, in
                      float* ws, jg_stream_t stream);
 /* dx = d/dx (+ addend, an NHWC bf16 tensor like dx with stride ldadd, or NULL: the gradient of a second consumer
  * of x — e.g. the ResBlock's skip path — summed in the same pass; addend may alias dx);
- * dgamma/dbeta [C] overwritten (may be NULL); dfilm [N][2C] overwritten (may be NULL). */
+ * dgamma/dbeta [C] overwritten (may be NULL); dfilm [N][2C] overwritten (may be NULL);
+ * dx_colsum [C] (may be NULL) receives sum over (n, pixel) of dx: x is the output of a conv, so this IS that conv's
+ * bias gradient (nn.Conv2d bias, unet_generator_attn.py:190,207) and saves the separate pass over dx. */
 int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, const void* addend,
                      int ldadd, int N,
                      int HW, int C, int groups, const float* gamma, const float* beta, const float* film, int act,
-                     const float* stats, const float* ab, float* dgamma, float* dbeta, float* dfilm, float* ws,
-                     jg_stream_t stream);
+                     const float* stats, const float* ab, float* dgamma, float* dbeta, float* dfilm,
+                     float* dx_colsum, float* ws, jg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Spatial self-attention (flash style, T x T never materialised), bf16, fp32 softmax.

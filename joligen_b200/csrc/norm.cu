@@ -44,100 +44,130 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   o.w = pack_bf16x2(f[6], f[7]);
   *reinterpret_cast<uint4*>(p) = o;
 }
-// sigmoid with ONE MUFU op per element (ex2); the reciprocal of 1 + e in [1, inf) is a bit-trick seed plus three
-// Newton steps on the FMA pipe (relative error < 1e-7).  At HBM speed these kernels need ~6 elements/cycle/SM:
-// two MUFU ops per element (ex2 + rcp) would put the 16/cycle/SM special-function unit on the critical path.
+// Packs eight floats to bf16 and returns the packed vector (the values that are actually stored).
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+// sigmoid with ONE MUFU op (ex2) and 7 FMA-pipe + 1 ALU-pipe instructions per element.  These kernels run at HBM speed
+// only if they stay near ~10 instructions per element (ncu: the first version, ~22 instructions/element, was issue-bound
+// at 76% issue utilisation and 50% DRAM utilisation), and two MUFU ops per element (ex2 + rcp) would load the 16-lane
+// special function unit to ~75%.  The reciprocal of x = 1 + e is an integer-subtract seed (5% error) refined by one
+// cubically convergent step r*(1 + eps + eps^2), eps = 1 - x*r: relative error < 1.3e-4, 30x below a bf16 ulp.
+// The saturating FMA (free modifier) keeps r in [0, 1] and flushes the NaN/inf that the seed produces for
+// e >= 2^126 (u < -87) to 0, which is the correct limit: no clamp instruction is needed.
 __device__ __forceinline__ float fast_sigmoid(float u) {
-  const float e = exp2f(-1.4426950408889634f * fminf(fmaxf(u, -80.f), 80.f));
+  float e;
+  const float t = -1.4426950408889634f * u;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
   const float x = 1.f + e;
-  float r = __int_as_float(0x7EF311C7 - __float_as_int(x));
-  r = r * (2.f - x * r);
-  r = r * (2.f - x * r);
-  r = r * (2.f - x * r);
-  return r;
+  const float r = __int_as_float(0x7EF311C7 - __float_as_int(x));
+  const float eps = fmaf(-x, r, 1.f);
+  const float w = fmaf(eps, eps, eps);
+  return __saturatef(fmaf(r, w, r));
 }
-__device__ __forceinline__ float silu_f(float u) { return u * fast_sigmoid(u); }
-__device__ __forceinline__ float silu_grad(float u) {
-  const float s = fast_sigmoid(u);
-  return s * (1.f + u * (1.f - s));
+// activation applied after the affine: none / SiLU (UNet) / ReLU, LeakyReLU(0.2) (GAN generator / discriminator);
+// a template parameter so that the per-element code has no activation dispatch in it
+template <int ACT>
+__device__ __forceinline__ float act_f(float u) {
+  if (ACT == JG_ACT_SILU) return u * fast_sigmoid(u);
+  if (ACT == JG_ACT_RELU) return fmaxf(u, 0.f);
+  if (ACT == JG_ACT_LRELU02) return u > 0.f ? u : 0.2f * u;
+  return u;
 }
-// activation applied after the affine: none / SiLU (UNet) / ReLU, LeakyReLU(0.2) (GAN generator / discriminator)
-__device__ __forceinline__ float act_f(float u, int act) {
-  switch (act) {
-    case JG_ACT_SILU: return silu_f(u);
-    case JG_ACT_RELU: return u > 0.f ? u : 0.f;
-    case JG_ACT_LRELU02: return u > 0.f ? u : 0.2f * u;
-    default: return u;
+template <int ACT>
+__device__ __forceinline__ float act_grad(float u) {
+  if (ACT == JG_ACT_SILU) {
+    const float s = fast_sigmoid(u);
+    return s * (1.f + fmaf(-u, s, u));  // s * (1 + u * (1 - s))
   }
+  if (ACT == JG_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+  if (ACT == JG_ACT_LRELU02) return u > 0.f ? 1.f : 0.2f;
+  return 1.f;
 }
-__device__ __forceinline__ float act_grad(float u, int act) {
-  switch (act) {
-    case JG_ACT_SILU: return silu_grad(u);
-    case JG_ACT_RELU: return u > 0.f ? 1.f : 0.f;
-    case JG_ACT_LRELU02: return u > 0.f ? 1.f : 0.2f;
-    default: return 1.f;
+#define JG_ACT_DISPATCH(act, ...)                                                    \
+  switch (act) {                                                                     \
+    case JG_ACT_SILU: { constexpr int ACT = JG_ACT_SILU; __VA_ARGS__; } break;       \
+    case JG_ACT_RELU: { constexpr int ACT = JG_ACT_RELU; __VA_ARGS__; } break;       \
+    case JG_ACT_LRELU02: { constexpr int ACT = JG_ACT_LRELU02; __VA_ARGS__; } break; \
+    default: { constexpr int ACT = JG_ACT_NONE; __VA_ARGS__; } break;                \
   }
+
+// Block-level sum over the row lanes of per-thread 8-channel partial sums, without shared-memory atomics (fp32
+// shared atomics are compare-and-swap loops: with 32 row lanes per channel they cost several microseconds per block).
+// part: [Q][rstep][C] scratch, out: [Q][C].  Every thread of the block must call it.
+constexpr int kPartFloats = kNormThreads * 8;  // rstep * C <= 256 * 8
+template <int Q>
+__device__ __forceinline__ void block_channel_sums(const float (&vals)[Q][8], bool active, int rl, int v, int rstep, int C,
+                                                   float* part, float* out) {
+  if (active) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      float* dst = part + ((size_t)q * rstep + rl) * C + v * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(vals[q][0], vals[q][1], vals[q][2], vals[q][3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(vals[q][4], vals[q][5], vals[q][6], vals[q][7]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Q * C; i += kNormThreads) {
+    const int q = i / C, c = i - q * C;
+    const float* src = part + (size_t)q * rstep * C + c;
+    float acc = 0.f;
+    for (int r = 0; r < rstep; ++r) acc += src[(size_t)r * C];
+    out[i] = acc;
+  }
+  __syncthreads();
 }
 
 // ---- pass 1 (fwd): per-(n, group) sum and sum of squares --------------------------------------
-// grid (chunks, N); smem: 2*C floats.
+// grid (chunks, N); smem: kPartFloats*2 + 2*C floats.  Eight rows (8 x 16 B) are in flight per thread.
 __global__ void __launch_bounds__(kNormThreads, 4)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int groups, int rows_per_block,
                 float* __restrict__ sums /*[N][groups][2]*/) {
   extern __shared__ float sm[];
-  float* csum = sm;
-  float* csq = sm + C;
+  float* part = sm;
+  float* csum = sm + 2 * kPartFloats;  // [2][C]: sum, sum of squares
   const int n = blockIdx.y;
   const int vecs = C / 8;
   const int rstep = kNormThreads / vecs;
   const int v = threadIdx.x % vecs;
   const int rl = threadIdx.x / vecs;
-  for (int i = threadIdx.x; i < 2 * C; i += kNormThreads) sm[i] = 0.f;
-  __syncthreads();
+  const bool active = rl < rstep;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(r0 + rows_per_block, HW);
-  if (rl < rstep) {
-    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float acc[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
+  if (active) {
     const __nv_bfloat16* base = x + ((size_t)n * HW) * ldx + v * 8;
-    // 4 independent 16-byte loads in flight per thread
+    auto reduce = [&](const uint4& u) {
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += f[j];
+        acc[1][j] = fmaf(f[j], f[j], acc[1][j]);
+      }
+    };
     int r = r0 + rl;
     for (; r + 7 * rstep < r1; r += 8 * rstep) {
       uint4 u[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) u[k] = ldg_stream(base + (size_t)(r + k * rstep) * ldx);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float f[8];
-        unpack8(u[k], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s[j] += f[j];
-          q[j] += f[j] * f[j];
-        }
-      }
+      for (int k = 0; k < 8; ++k) reduce(u[k]);
     }
-    for (; r < r1; r += rstep) {
-      float f[8];
-      load8(base + (size_t)r * ldx, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += f[j];
-        q[j] += f[j] * f[j];
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&csum[v * 8 + j], s[j]);
-      atomicAdd(&csq[v * 8 + j], q[j]);
-    }
+    for (; r < r1; r += rstep) reduce(ldg_stream(base + (size_t)r * ldx));
   }
-  __syncthreads();
+  block_channel_sums<2>(acc, active, rl, v, rstep, C, part, csum);
   const int cpg = C / groups;
   for (int g = threadIdx.x; g < groups; g += kNormThreads) {
     float s = 0.f, q = 0.f;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
       s += csum[c];
-      q += csq[c];
+      q += csum[C + c];
     }
     atomicAdd(&sums[((size_t)n * groups + g) * 2 + 0], s);
     atomicAdd(&sums[((size_t)n * groups + g) * 2 + 1], q);
@@ -180,9 +210,10 @@ __global__ void gn_finalize_fwd_kernel(const float* __restrict__ sums, int HW, i
 }
 
 // ---- pass 3 (fwd): y = act(x*a + b) -------------------------------------------------------------
+template <int ACT>
 __global__ void __launch_bounds__(kNormThreads, 3)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy, int HW, int C,
-                int rows_per_block, const float* __restrict__ ab, int act) {
+                int rows_per_block, const float* __restrict__ ab) {
   const int n = blockIdx.y;
   const int vecs = C / 8;
   const int rstep = kNormThreads / vecs;
@@ -201,38 +232,33 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __r
   __nv_bfloat16* yb = y + ((size_t)n * HW) * ldy + v * 8;
   int r = r0 + rl;
   for (; r + 7 * rstep < r1; r += 8 * rstep) {
-    uint4 u4[8];
+    uint4 u[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) u4[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
+    for (int k = 0; k < 8; ++k) u[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float f[8];
-      unpack8(u4[k], f);
+      unpack8(u[k], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float u = f[j] * a[j] + b[j];
-        f[j] = act_f(u, act);
-      }
-      store8(yb + (size_t)(r + k * rstep) * ldy, f);
+      for (int j = 0; j < 8; ++j) f[j] = act_f<ACT>(fmaf(f[j], a[j], b[j]));
+      *reinterpret_cast<uint4*>(yb + (size_t)(r + k * rstep) * ldy) = pack8(f);
     }
   }
   for (; r < r1; r += rstep) {
     float f[8];
-    load8(xb + (size_t)r * ldx, f);
+    unpack8(ldg_stream(xb + (size_t)r * ldx), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float u = f[j] * a[j] + b[j];
-      f[j] = act_f(u, act);
-    }
-    store8(yb + (size_t)r * ldy, f);
+    for (int j = 0; j < 8; ++j) f[j] = act_f<ACT>(fmaf(f[j], a[j], b[j]));
+    *reinterpret_cast<uint4*>(yb + (size_t)r * ldy) = pack8(f);
   }
 }
 
 // ---- bwd pass 1: A[n,c] = sum du, B[n,c] = sum du*x ------------------------------------------
-// grid (chunks, N); smem 2*C floats (block-level reduction before the global atomics).
+// grid (chunks, N); smem kPartFloats*2 + 2*C floats (block-level reduction before the global atomics).
+template <int ACT>
 __global__ void __launch_bounds__(kNormThreads, 2)
 gn_bwd_sums_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy, int lddy,
-                   int HW, int C, int rows_per_block, const float* __restrict__ ab, int act,
+                   int HW, int C, int rows_per_block, const float* __restrict__ ab,
                    float* __restrict__ AB /*[N][C][2]*/) {
   extern __shared__ float sm[];
   const int n = blockIdx.y;
@@ -240,16 +266,17 @@ gn_bwd_sums_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bflo
   const int rstep = kNormThreads / vecs;
   const int v = threadIdx.x % vecs;
   const int rl = threadIdx.x / vecs;
-  for (int i = threadIdx.x; i < 2 * C; i += kNormThreads) sm[i] = 0.f;
-  __syncthreads();
-  if (rl < rstep) {
+  float* part = sm;
+  float* tot = sm + 2 * kPartFloats;  // [2][C]: A, B
+  const bool active = rl < rstep;
+  float acc[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
+  if (active) {
     float a[8], b[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       a[j] = ab[((size_t)n * C + v * 8 + j) * 2 + 0];
       b[j] = ab[((size_t)n * C + v * 8 + j) * 2 + 1];
     }
-    float sa[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int r0 = blockIdx.x * rows_per_block;
     const int r1 = min(r0 + rows_per_block, HW);
     const __nv_bfloat16* xb = x + ((size_t)n * HW) * ldx + v * 8;
@@ -270,32 +297,30 @@ gn_bwd_sums_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bflo
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float du = d[j];
-          if (act != JG_ACT_NONE) du *= act_grad(f[j] * a[j] + b[j], act);
-          sa[j] += du;
-          sb[j] += du * f[j];
+          if (ACT != JG_ACT_NONE) du *= act_grad<ACT>(fmaf(f[j], a[j], b[j]));
+          acc[0][j] += du;
+          acc[1][j] = fmaf(du, f[j], acc[1][j]);
         }
       }
     }
     for (; r < r1; r += rstep) {
       float f[8], d[8];
-      load8(xb + (size_t)r * ldx, f);
-      load8(db + (size_t)r * lddy, d);
+      unpack8(ldg_stream(xb + (size_t)r * ldx), f);
+      unpack8(ldg_stream(db + (size_t)r * lddy), d);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float du = d[j];
-        if (act != JG_ACT_NONE) du *= act_grad(f[j] * a[j] + b[j], act);
-        sa[j] += du;
-        sb[j] += du * f[j];
+        if (ACT != JG_ACT_NONE) du *= act_grad<ACT>(fmaf(f[j], a[j], b[j]));
+        acc[0][j] += du;
+        acc[1][j] = fmaf(du, f[j], acc[1][j]);
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sm[(v * 8 + j) * 2 + 0], sa[j]);
-      atomicAdd(&sm[(v * 8 + j) * 2 + 1], sb[j]);
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += kNormThreads) atomicAdd(&AB[(size_t)n * C * 2 + i], sm[i]);
+  block_channel_sums<2>(acc, active, rl, v, rstep, C, part, tot);
+  for (int i = threadIdx.x; i < 2 * C; i += kNormThreads) {
+    const int q = i / C, c = i - q * C;
+    atomicAdd(&AB[((size_t)n * C + c) * 2 + q], tot[i]);
+  }
 }
 
 // ---- bwd pass 2: coefficients, dFiLM ---------------------------------------------------------------
@@ -362,83 +387,93 @@ __global__ void gn_param_grad_kernel(const float* __restrict__ gAB, int N, int C
   if (dgamma) dgamma[c] = sb;
 }
 
-// ---- bwd pass 3: dx = k1*du + k2*x + k3 (+ addend) ----------------------------------------------
-// U rows are kept in flight per thread.  The per-channel constants take 40 registers, so the row unroll is what decides
-// whether the kernel spills: two blocks per SM (128 registers) with U = 3 (addend) or 4 keeps ~50 KB in flight per SM.
-template <bool HAS_ADD, int U>
+// ---- bwd pass 3: dx = k1*du + k2*x + k3 (+ addend), optionally colsum[c] += sum over rows of dx ---------
+// U rows are in flight per thread.  The per-channel constants take 40 registers: two blocks per SM (128 registers)
+// with U = 3 (addend) or 4 keep ~50 KB in flight per SM without spilling.  smem: kPartFloats + C floats (column sums).
+template <bool HAS_ADD, int ACT, int U>
 __global__ void __launch_bounds__(kNormThreads, 2)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy, int lddy,
                     __nv_bfloat16* __restrict__ dx, int lddx, int HW, int C, int groups, int rows_per_block,
-                    const float* __restrict__ ab, int act, const float* __restrict__ k1,
-                    const float* __restrict__ k23, const __nv_bfloat16* __restrict__ addend, int ldadd) {
+                    const float* __restrict__ ab, const float* __restrict__ k1, const float* __restrict__ k23,
+                    const __nv_bfloat16* __restrict__ addend, int ldadd, float* __restrict__ colsum) {
+  extern __shared__ float sm[];
   const int n = blockIdx.y;
   const int vecs = C / 8;
   const int rstep = kNormThreads / vecs;
   const int v = threadIdx.x % vecs;
   const int rl = threadIdx.x / vecs;
-  if (rl >= rstep) return;
-  const int cpg = C / groups;
-  float a[8], b[8], c1[8], c2[8], c3[8];
+  const bool active = rl < rstep;
+  float cs[1][8] = {{0, 0, 0, 0, 0, 0, 0, 0}};
+  if (active) {
+    const int cpg = C / groups;
+    float a[8], b[8], c1[8], c2[8], c3[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = v * 8 + j;
-    const int g = c / cpg;
-    a[j] = ab[((size_t)n * C + c) * 2 + 0];
-    b[j] = ab[((size_t)n * C + c) * 2 + 1];
-    c1[j] = k1[(size_t)n * C + c];
-    c2[j] = k23[((size_t)n * groups + g) * 2 + 0];
-    c3[j] = k23[((size_t)n * groups + g) * 2 + 1];
-  }
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(r0 + rows_per_block, HW);
-  const __nv_bfloat16* xb = x + ((size_t)n * HW) * ldx + v * 8;
-  const __nv_bfloat16* db = dy + ((size_t)n * HW) * lddy + v * 8;
-  __nv_bfloat16* ob = dx + ((size_t)n * HW) * lddx + v * 8;
-  const __nv_bfloat16* eb = HAS_ADD ? addend + ((size_t)n * HW) * ldadd + v * 8 : nullptr;
-  int r = r0 + rl;
-  for (; r + (U - 1) * rstep < r1; r += U * rstep) {
-    uint4 ux[U], ud[U], ua[U];
-#pragma unroll
-    for (int k = 0; k < U; ++k) {
-      ux[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
-      ud[k] = ldg_stream(db + (size_t)(r + k * rstep) * lddy);
-      if (HAS_ADD) ua[k] = ldg_stream(eb + (size_t)(r + k * rstep) * ldadd);
+    for (int j = 0; j < 8; ++j) {
+      const int c = v * 8 + j;
+      const int g = c / cpg;
+      a[j] = ab[((size_t)n * C + c) * 2 + 0];
+      b[j] = ab[((size_t)n * C + c) * 2 + 1];
+      c1[j] = k1[(size_t)n * C + c];
+      c2[j] = k23[((size_t)n * groups + g) * 2 + 0];
+      c3[j] = k23[((size_t)n * groups + g) * 2 + 1];
     }
-#pragma unroll
-    for (int k = 0; k < U; ++k) {
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, HW);
+    const __nv_bfloat16* xb = x + ((size_t)n * HW) * ldx + v * 8;
+    const __nv_bfloat16* db = dy + ((size_t)n * HW) * lddy + v * 8;
+    __nv_bfloat16* ob = dx + ((size_t)n * HW) * lddx + v * 8;
+    const __nv_bfloat16* eb = HAS_ADD ? addend + ((size_t)n * HW) * ldadd + v * 8 : nullptr;
+    // one row: o = c1*du + c2*x + c3 (+ e), stored as bf16; the column sums are taken in fp32 before the rounding
+    auto row = [&](const uint4& ux, const uint4& ud, const uint4& ua, __nv_bfloat16* dst) {
       float f[8], d[8], o[8], e[8];
-      unpack8(ux[k], f);
-      unpack8(ud[k], d);
-      if (HAS_ADD) unpack8(ua[k], e);
+      unpack8(ux, f);
+      unpack8(ud, d);
+      if (HAS_ADD) unpack8(ua, e);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float du = d[j];
-        if (act != JG_ACT_NONE) du *= act_grad(f[j] * a[j] + b[j], act);
-        o[j] = c1[j] * du + c2[j] * f[j] + c3[j];
+        if (ACT != JG_ACT_NONE) du *= act_grad<ACT>(fmaf(f[j], a[j], b[j]));
+        o[j] = fmaf(c1[j], du, fmaf(c2[j], f[j], c3[j]));
         if (HAS_ADD) o[j] += e[j];
       }
-      store8(ob + (size_t)(r + k * rstep) * lddx, o);
+      *reinterpret_cast<uint4*>(dst) = pack8(o);
+      if (colsum) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[0][j] += o[j];
+      }
+    };
+    int r = r0 + rl;
+    for (; r + (U - 1) * rstep < r1; r += U * rstep) {
+      uint4 ux[U], ud[U], ua[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        ux[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
+        ud[k] = ldg_stream(db + (size_t)(r + k * rstep) * lddy);
+        if (HAS_ADD) ua[k] = ldg_stream(eb + (size_t)(r + k * rstep) * ldadd);
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) row(ux[k], ud[k], ua[k], ob + (size_t)(r + k * rstep) * lddx);
+    }
+    for (; r < r1; r += rstep) {
+      const uint4 ux = ldg_stream(xb + (size_t)r * ldx);
+      const uint4 ud = ldg_stream(db + (size_t)r * lddy);
+      uint4 ua = ux;
+      if (HAS_ADD) ua = ldg_stream(eb + (size_t)r * ldadd);
+      row(ux, ud, ua, ob + (size_t)r * lddx);
     }
   }
-  for (; r < r1; r += rstep) {
-    float f[8], d[8], o[8], e[8];
-    load8(xb + (size_t)r * ldx, f);
-    load8(db + (size_t)r * lddy, d);
-    if (HAS_ADD) load8(eb + (size_t)r * ldadd, e);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float du = d[j];
-      if (act != JG_ACT_NONE) du *= act_grad(f[j] * a[j] + b[j], act);
-      o[j] = c1[j] * du + c2[j] * f[j] + c3[j];
-      if (HAS_ADD) o[j] += e[j];
-    }
-    store8(ob + (size_t)r * lddx, o);
+  if (colsum) {  // block-uniform
+    float* tot = sm + kPartFloats;
+    block_channel_sums<1>(cs, active, rl, v, rstep, C, sm, tot);
+    for (int i = threadIdx.x; i < C; i += kNormThreads) atomicAdd(&colsum[i], tot[i]);
   }
 }
 
-static int rows_per_block_for(int HW, int N) {
-  // ~4 waves of blocks over the SMs, at least 32 rows per block
-  const int target_blocks = num_sms() * 8;
+// Rows per block for a grid of about per_sm blocks per SM (at least 32 rows per block).  The kernels that end in a
+// block-level reduction run as ONE wave of co-resident blocks: measured on B200, twice the blocks cost 25-70% more time.
+static int rows_per_block_for(int HW, int N, int per_sm) {
+  static const int scale = getenv("JG_GN_BLOCK_SCALE") ? atoi(getenv("JG_GN_BLOCK_SCALE")) : 1;  // experiments
+  const int target_blocks = num_sms() * per_sm * scale;
   int chunks = target_blocks / (N > 0 ? N : 1);
   if (chunks < 1) chunks = 1;
   int rpb = (HW + chunks - 1) / chunks;
@@ -474,24 +509,28 @@ extern "C" int jg_groupnorm_fwd(const void* x, int ldx, void* y, int ldy, int N,
   JG_CHECK(act == JG_ACT_NONE || act == JG_ACT_SILU || act == JG_ACT_RELU || act == JG_ACT_LRELU02, JG_ERR_INVALID,
            "groupnorm_fwd: act %d unsupported", act);
   JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)N * groups * 2, stream));
-  const int rpb = rows_per_block_for(HW, N);
-  dim3 grid((HW + rpb - 1) / rpb, N);
-  gn_stats_kernel<<<grid, kNormThreads, 2 * C * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,
-                                                                         HW, C, groups, rpb, ws);
-  JG_LAUNCH_CHECK();
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  {
+    const int rpb = rows_per_block_for(HW, N, 4);
+    dim3 grid((HW + rpb - 1) / rpb, N);
+    const size_t smem = (2 * kPartFloats + 2 * C) * sizeof(float);
+    gn_stats_kernel<<<grid, kNormThreads, smem, stream>>>(xb, ldx, HW, C, groups, rpb, ws);
+    JG_LAUNCH_CHECK();
+  }
   gn_finalize_fwd_kernel<<<N, 256, 0, stream>>>(ws, HW, C, groups, eps, gamma, beta, film, stats, ab);
   JG_LAUNCH_CHECK();
-  gn_apply_kernel<<<grid, kNormThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,
-                                                     static_cast<__nv_bfloat16*>(y), ldy, HW, C, rpb, ab, act);
+  const int rpb = rows_per_block_for(HW, N, 8);
+  dim3 grid((HW + rpb - 1) / rpb, N);
+  JG_ACT_DISPATCH(act, gn_apply_kernel<ACT><<<grid, kNormThreads, 0, stream>>>(
+                           xb, ldx, static_cast<__nv_bfloat16*>(y), ldy, HW, C, rpb, ab));
   JG_LAUNCH_CHECK();
   return JG_OK;
 }
 
 extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, const void* addend,
-                                int ldadd,
-                                int N, int HW, int C, int groups, const float* gamma, const float* beta,
+                                int ldadd, int N, int HW, int C, int groups, const float* gamma, const float* beta,
                                 const float* film, int act, const float* stats, const float* ab, float* dgamma,
-                                float* dbeta, float* dfilm, float* ws, jg_stream_t stream_) {
+                                float* dbeta, float* dfilm, float* dx_colsum, float* ws, jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_norm_args(N, HW, C, groups, ldx);
   if (rc) return rc;
@@ -503,11 +542,18 @@ extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy
   float* k23 = k1 + (size_t)N * C;
   float* gAB = k23 + (size_t)N * groups * 2;
   JG_CUDA(cudaMemsetAsync(AB, 0, sizeof(float) * (size_t)N * C * 2, stream));
-  const int rpb = rows_per_block_for(HW, N);
+  if (dx_colsum) JG_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, stream));
+  static const int apply_per_sm = getenv("JG_GN_BWD_APPLY_PER_SM") ? atoi(getenv("JG_GN_BWD_APPLY_PER_SM")) : 2;
+  const int rpb1 = rows_per_block_for(HW, N, 2);
+  const int rpb = rows_per_block_for(HW, N, apply_per_sm);
+  dim3 grid1((HW + rpb1 - 1) / rpb1, N);
   dim3 grid((HW + rpb - 1) / rpb, N);
-  gn_bwd_sums_kernel<<<grid, kNormThreads, 2 * C * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,
-                                                        static_cast<const __nv_bfloat16*>(dy), lddy, HW, C, rpb, ab,
-                                                        act, AB);
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* addb = static_cast<const __nv_bfloat16*>(addend);
+  __nv_bfloat16* dxb = static_cast<__nv_bfloat16*>(dx);
+  JG_ACT_DISPATCH(act, gn_bwd_sums_kernel<ACT><<<grid1, kNormThreads, (2 * kPartFloats + 2 * C) * sizeof(float), stream>>>(
+                           xb, ldx, dyb, lddy, HW, C, rpb1, ab, AB));
   JG_LAUNCH_CHECK();
   gn_finalize_bwd_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(AB, HW, C, groups, gamma, beta, film, stats, k1,
                                                                     k23, dfilm, gAB);
@@ -516,15 +562,14 @@ extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy
     gn_param_grad_kernel<<<(C + 127) / 128, 128, 0, stream>>>(gAB, N, C, dgamma, dbeta);
     JG_LAUNCH_CHECK();
   }
-  if (addend)
-    gn_bwd_apply_kernel<true, 3><<<grid, kNormThreads, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(dy), lddy,
-        static_cast<__nv_bfloat16*>(dx), lddx, HW, C, groups, rpb, ab, act, k1, k23,
-        static_cast<const __nv_bfloat16*>(addend), ldadd);
-  else
-    gn_bwd_apply_kernel<false, 4><<<grid, kNormThreads, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(dy), lddy,
-        static_cast<__nv_bfloat16*>(dx), lddx, HW, C, groups, rpb, ab, act, k1, k23, nullptr, 0);
+  const size_t smem = dx_colsum ? (kPartFloats + C) * sizeof(float) : 0;
+  if (addend) {
+    JG_ACT_DISPATCH(act, gn_bwd_apply_kernel<true, ACT, 3><<<grid, kNormThreads, smem, stream>>>(
+                             xb, ldx, dyb, lddy, dxb, lddx, HW, C, groups, rpb, ab, k1, k23, addb, ldadd, dx_colsum));
+  } else {
+    JG_ACT_DISPATCH(act, gn_bwd_apply_kernel<false, ACT, 4><<<grid, kNormThreads, smem, stream>>>(
+                             xb, ldx, dyb, lddy, dxb, lddx, HW, C, groups, rpb, ab, k1, k23, nullptr, 0, dx_colsum));
+  }
   JG_LAUNCH_CHECK();
   return JG_OK;
 }

@@ -148,27 +148,27 @@ def groupnorm_fwd(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5, o
         out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
     stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x.device)
     ab = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
-    ws = torch.empty((n * groups * 2,), dtype=torch.float32, device=x.device)
+    ws = torch.empty((L.load().jg_groupnorm_fwd_ws_floats(n, c, groups),), dtype=torch.float32, device=x.device)
     L.call("jg_groupnorm_fwd", L.ptr(x), _ld(x), L.ptr(out), _ld(out), n, h * w, c, groups, eps, L.ptr(gamma),
            L.ptr(beta), L.ptr(film), act, L.ptr(stats), L.ptr(ab), L.ptr(ws), L.stream())
     return out, stats, ab
 
 
 def groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab, need_param_grads=True, need_film_grad=False,
-                  dx=None, addend=None):
-    """addend: optional NHWC bf16 tensor summed into dx in the same pass (gradient of another consumer of x)."""
+                  dx=None, addend=None, colsum=None):
+    """addend: optional NHWC bf16 tensor summed into dx in the same pass (gradient of another consumer of x).
+    colsum: optional fp32 [C] output = per-channel sum of dx (the bias gradient of the conv that produced x)."""
     n, h, w, c = x.shape
     if dx is None:
         dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
     dgamma = torch.empty((c,), dtype=torch.float32, device=x.device) if need_param_grads else None
     dbeta = torch.empty((c,), dtype=torch.float32, device=x.device) if need_param_grads else None
     dfilm = torch.empty((n, 2 * c), dtype=torch.float32, device=x.device) if need_film_grad else None
-    nws = n * c * 2 + n * c + n * groups * 2 + n * c * 2
-    ws = torch.empty((nws,), dtype=torch.float32, device=x.device)
+    ws = torch.empty((L.load().jg_groupnorm_bwd_ws_floats(n, c, groups),), dtype=torch.float32, device=x.device)
     L.call("jg_groupnorm_bwd", L.ptr(x), _ld(x), L.ptr(dy), _ld(dy), L.ptr(dx), _ld(dx), L.ptr(addend),
            _ld(addend) if addend is not None else 0, n, h * w, c,
            groups, L.ptr(gamma), L.ptr(beta), L.ptr(film), act, L.ptr(stats), L.ptr(ab), L.ptr(dgamma), L.ptr(dbeta),
-           L.ptr(dfilm), L.ptr(ws), L.stream())
+           L.ptr(dfilm), L.ptr(colsum), L.ptr(ws), L.stream())
     return dx, dgamma, dbeta, dfilm
 
 

@@ -50,7 +50,7 @@ _SIGNATURES = {
     "jg_groupnorm_fwd": [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_f, c_p, c_p, c_p, c_int, c_p, c_p,
                          c_p, c_p],
     "jg_groupnorm_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p,
-                         c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+                         c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "jg_attn_fwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_p],
     "jg_attn_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_p],
     "jg_linear_fwd": [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],

@@ -9,6 +9,11 @@ from . import kernels as K
 from . import lib as L
 
 
+def _colsum_buffer(x):
+    """[C] fp32 buffer for the per-channel sums of dx that GroupNorm-backward produces on the side."""
+    return torch.empty((x.shape[-1],), dtype=torch.float32, device=x.device)
+
+
 def _needs(ctx, i):
     return ctx.needs_input_grad[i]
 
@@ -33,6 +38,8 @@ class Conv2dFn(torch.autograd.Function):
         x, wd = ctx.saved_tensors
         cout, cin, r, s, stride, pad, res_scale, has_bias, has_res = ctx.geom
         cout8 = (cout + 7) // 8 * 8
+        # a GroupNorm backward that produced this very tensor has already summed it over (n, pixel)
+        colsum = getattr(dy, "_jg_colsum", None) if dy.is_contiguous() else None
         dy = dy.contiguous()
         dx = dw = db = dres = None
         if _needs(ctx, 0):
@@ -54,7 +61,7 @@ class Conv2dFn(torch.autograd.Function):
                 if dw.shape[0] != cout or dw.shape[1] != cin:  # zero-padded channels (e.g. 6 -> 8, 3 -> 8)
                     dw = dw[:cout, :cin].contiguous()
         if has_bias and _needs(ctx, 2):
-            db = K.bias_grad(dy)
+            db = colsum if colsum is not None and colsum.numel() == cout8 else K.bias_grad(dy)
             if cout8 != cout:
                 db = db[:cout].contiguous()
         if has_res and _needs(ctx, 3):
@@ -79,8 +86,11 @@ class GroupNormFn(torch.autograd.Function):
         dy = dy.contiguous()
         need_p = gamma is not None and (_needs(ctx, 1) or _needs(ctx, 2))
         need_f = film is not None and _needs(ctx, 3)
+        colsum = _colsum_buffer(x)
         dx, dgamma, dbeta, dfilm = K.groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab,
-                                                   need_param_grads=need_p, need_film_grad=need_f)
+                                                   need_param_grads=need_p, need_film_grad=need_f, colsum=colsum)
+        if colsum is not None:
+            dx._jg_colsum = colsum  # picked up by Conv2dFn.backward when x is a conv output (its bias gradient)
         return dx, dgamma, dbeta, dfilm, None, None
 
 
@@ -105,9 +115,13 @@ class GroupNormTapFn(torch.autograd.Function):
         dy = dy.contiguous()
         need_p = gamma is not None and (_needs(ctx, 1) or _needs(ctx, 2))
         need_f = film is not None and _needs(ctx, 3)
+        colsum = _colsum_buffer(x)
         dx, dgamma, dbeta, dfilm = K.groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab,
                                                    need_param_grads=need_p, need_film_grad=need_f,
-                                                   addend=None if dtap is None else dtap.contiguous())
+                                                   addend=None if dtap is None else dtap.contiguous(),
+                                                   colsum=colsum)
+        if colsum is not None:
+            dx._jg_colsum = colsum
         return dx, dgamma, dbeta, dfilm, None, None
 
 

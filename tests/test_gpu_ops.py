@@ -102,6 +102,7 @@ GN_CASES = [
     (3, 8, 512, 32, True, True),
     (2, 16, 128, 128, False, False),  # attention InstanceNorm1d: one group per channel, no affine
     (1, 32, 1024, 32, True, True),
+    (3, 256, 64, 32, True, True),
 ]
 
 
@@ -140,6 +141,35 @@ def test_groupnorm_film_silu_fwd_bwd(K, case):
         assert rel(dbeta, br.grad) < 2e-3
     if use_film:
         assert rel(dfilm, fr.grad) < 2e-3
+
+
+def test_groupnorm_bwd_addend_colsum(K):
+    """dx = GN'(dy) + addend, plus the per-channel sums of dx produced on the side (the producer conv's bias
+    gradient); 96 channels: 12 vectors per row, so 4 threads of each block are idle."""
+    from joligen_b200 import lib as L
+    n, hw, c, groups = 5, 24, 96, 32
+    g = torch.Generator().manual_seed(11)
+    x = bf16_round(torch.randn(n, c, hw, hw, generator=g) * 1.2 - 0.2)
+    gamma = 1 + 0.2 * torch.randn(c, generator=g)
+    beta = 0.1 * torch.randn(c, generator=g)
+    film = 0.3 * torch.randn(n, 2 * c, generator=g)
+    xr = x.clone().requires_grad_(True)
+    h = F.group_norm(xr, groups, gamma, beta, eps=1e-5)
+    scale, shift = torch.chunk(film[:, :, None, None], 2, dim=1)
+    ref = F.silu(h * (1 + scale) + shift)
+    dy = bf16_round(torch.randn(ref.shape, generator=g))
+    add = bf16_round(torch.randn(ref.shape, generator=g))
+    ref.backward(dy)
+    want = xr.grad + add
+    x_d = to_dev_nhwc(K, x)
+    y, stats, ab = K.groupnorm_fwd(x_d, gamma.cuda(), beta.cuda(), groups, film=film.cuda(), act=L.ACT_SILU)
+    assert rel(K.nhwc_to_nchw(y), ref.detach()) < 1e-2
+    colsum = torch.full((c,), 123.0, device="cuda")
+    dx, dgamma, dbeta, dfilm = K.groupnorm_bwd(x_d, to_dev_nhwc(K, dy), gamma.cuda(), beta.cuda(), groups, film.cuda(),
+                                               L.ACT_SILU, stats, ab, need_film_grad=True,
+                                               addend=to_dev_nhwc(K, add), colsum=colsum)
+    assert rel(K.nhwc_to_nchw(dx), want) < 1e-2
+    assert rel(colsum.cpu(), want.sum(dim=(0, 2, 3))) < 5e-3
 
 
 @pytest.mark.parametrize("case", [(2, 256, 4, 16), (2, 64, 16, 32), (1, 1024, 2, 32), (1, 128, 2, 64)])

