@@ -126,6 +126,87 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvFwdParams& p, EpiPr
   }
 }
 
+// Epilogue through shared memory + TMA stores.  The direct epilogue above has every lane write 64 contiguous bytes of
+// its own pixel row: a warp-level 16-byte store touches 32 different 128-byte lines, and ncu showed the L1/LSU store
+// path 65% busy on the 64-channel 256^2 layers (the tile's MMAs were waiting for the epilogue).  Here the 8 epilogue
+// warps write each 64-channel slab of the tile (128 pixel rows x 128 bytes, 128B-swizzled exactly as TMA expects, which
+// also makes the 16-byte shared stores conflict-free) into one of two 16 KB staging buffers and one thread hands the
+// slab to the TMA engine.  One named barrier per slab: before it, the issuing thread has waited for the previous
+// slab's store to finish reading the other buffer.
+constexpr int kStageBytes = 128 * 128;
+constexpr int kEpiThreads = 256;
+
+template <int BLOCK_N>
+__device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, EpiPrefetch& pf, const float* s_bias,
+                                                       uint32_t t_acc, int q, int half, int n_tile, bool valid,
+                                                       size_t pix, uint8_t* stage, int& stage_idx,
+                                                       const CUtensorMap* tmY, int c1, int c2, int c3, bool issuer) {
+  static_assert(BLOCK_N % 64 == 0, "TMA-store epilogue works on 64-channel slabs");
+  const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16);
+  const int row = q * 32 + (threadIdx.x & 31);
+#pragma unroll 1
+  for (int c = half * 32; c < BLOCK_N; c += 64) {
+    const int co0 = n_tile * BLOCK_N + c;
+    const int slab_co = co0 - half * 32;         // first channel of this 64-channel slab
+    if (slab_co >= p.Cout) break;                // uniform over all 8 warps: the rest of the tile is channel padding
+    uint32_t v[32];
+    tmem_ld_32x32(t_row + c, v);
+    uint4 rcur[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) rcur[g] = pf.r[g];
+    if (p.res && valid && c + 64 < BLOCK_N) {
+      const __nv_bfloat16* rn = p.res + pix * p.ldres + co0 + 64;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (co0 + 64 + g * 8 < p.Cout) pf.r[g] = *reinterpret_cast<const uint4*>(rn + g * 8);
+    }
+    tmem_ld_wait();
+    uint8_t* buf = stage + stage_idx * kStageBytes + row * 128;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {  // 8 channels per 16-byte chunk
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+      if (co0 + g * 8 < p.Cout) {
+        if (s_bias) {
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + co0 + g * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + co0 + g * 8 + 4);
+          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+          f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+        }
+        if (p.res && valid) {
+          const uint4 rv = rcur[g];
+          const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y);
+          const float2 r2 = unpack_bf16x2(rv.z), r3 = unpack_bf16x2(rv.w);
+          f[0] += p.res_scale * r0.x; f[1] += p.res_scale * r0.y;
+          f[2] += p.res_scale * r1.x; f[3] += p.res_scale * r1.y;
+          f[4] += p.res_scale * r2.x; f[5] += p.res_scale * r2.y;
+          f[6] += p.res_scale * r3.x; f[7] += p.res_scale * r3.y;
+        }
+        if (p.act != JG_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
+        }
+      }
+      uint4 o;
+      o.x = pack_bf16x2(f[0], f[1]);
+      o.y = pack_bf16x2(f[2], f[3]);
+      o.z = pack_bf16x2(f[4], f[5]);
+      o.w = pack_bf16x2(f[6], f[7]);
+      const int chunk = (half * 4 + g) ^ (row & 7);  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+      *reinterpret_cast<uint4*>(buf + chunk * 16) = o;
+    }
+    fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA (async proxy)
+    if (issuer) bulk_wait_read<0>();     // the previous slab's store has released the other buffer
+    bar_sync(1, kEpiThreads);
+    if (issuer) {
+      tma_store_4d(tmY, stage + stage_idx * kStageBytes, slab_co, c1, c2, c3);
+      bulk_commit();
+    }
+    stage_idx ^= 1;
+  }
+}
+
 // Launch of the halo-reuse 3x3 kernel (conv_halo.cu); returns JG_ERR_UNSUPPORTED when the shape does not qualify.
 int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                      const void* residual, void* y, cudaStream_t stream);

@@ -30,10 +30,11 @@ struct HaloParams {
 template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const HaloParams hp) {
+                 const __grid_constant__ CUtensorMap tmY, const HaloParams hp) {
   const ConvFwdParams& p = hp.c;
   constexpr int B_BYTES = BLOCK_N * 128;
   constexpr uint32_t TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  constexpr bool TMA_STORE = BLOCK_N >= 64;  // output tiles leave through shared memory + TMA (conv_common.cuh)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -41,7 +42,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smB = smem + SA * hp.a_stage_bytes;
   const int k_slabs = p.kc_blocks;
   const int b_tiles = B_RESIDENT ? p.RS * k_slabs : SB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + static_cast<size_t>(b_tiles) * B_BYTES);
+  uint8_t* stage = smB + static_cast<size_t>(b_tiles) * B_BYTES;  // 2 x 16 KB output staging (1024-byte aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + (TMA_STORE ? 2 * kStageBytes : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + SA;
   uint64_t* b_full = bars + 2 * SA;           // SB entries (entry 0 only when resident)
@@ -58,6 +60,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (TMA_STORE) tma_prefetch_desc(&tmY);
     for (int i = 0; i < SA; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
@@ -197,8 +200,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    const bool issuer = threadIdx.x == 64;  // warp 2, lane 0
     EpiPrefetch pf;
     int acc = 0;
+    int stage_idx = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
@@ -213,8 +218,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       conv_epilogue_prefetch<BLOCK_N>(p, pf, half, n_tile, valid, pix);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      conv_epilogue_tile<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile, valid,
-                                   pix);
+      if constexpr (TMA_STORE)
+        conv_epilogue_tile_tma<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile,
+                                        valid, pix, stage, stage_idx, &tmY, tw * kHaloTW, th * kHaloTH, tn, issuer);
+      else
+        conv_epilogue_tile<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile,
+                                    valid, pix);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -223,6 +232,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         acc_phase ^= 1;
       }
     }
+    if (TMA_STORE && issuer) bulk_wait_read<0>();  // the staging buffers live until the last store has read them
   }
 
   tc_fence_before();
@@ -234,9 +244,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
-static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& hp, cudaStream_t stream) {
+static int halo_smem_bytes(const HaloParams& hp) {
   const int b_tiles = B_RESIDENT ? hp.c.RS * hp.c.kc_blocks : SB;
-  const int smem = SA * hp.a_stage_bytes + b_tiles * BLOCK_N * 128 + (2 * SA + 2 * SB + 6) * 8 + ((hp.c.Cout * 4 + 127) / 128) * 128 + 1024;
+  return SA * hp.a_stage_bytes + b_tiles * BLOCK_N * 128 + (BLOCK_N >= 64 ? 2 * kStageBytes : 0) +
+         (2 * SA + 2 * SB + 6) * 8 + ((hp.c.Cout * 4 + 127) / 128) * 128 + 1024;
+}
+
+template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const HaloParams& hp,
+                       cudaStream_t stream) {
+  const int smem = halo_smem_bytes<BLOCK_N, SA, SB, B_RESIDENT>(hp);
   JG_CHECK(smem <= 232448, JG_ERR_INVALID, "conv_halo: smem %d too large", smem);
   static int attr_smem = 0;
   if (smem > attr_smem) {
@@ -245,7 +262,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Hal
     attr_smem = smem;
   }
   const int grid = hp.c.total_tiles < num_sms() ? hp.c.total_tiles : num_sms();
-  conv_halo_kernel<BLOCK_N, SA, SB, B_RESIDENT><<<grid, kThreads, smem, stream>>>(tmA, tmB, hp);
+  conv_halo_kernel<BLOCK_N, SA, SB, B_RESIDENT><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmY, hp);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }
@@ -296,17 +313,27 @@ int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed,
     rc = make_tmap_bf16(&tmB, w_packed, 3, dims, strides, box, es);
     if (rc) return rc;
   }
-  // resident weights: one N tile and all (slab, tap) tiles within ~128 KB
-  const bool resident = p.n_tiles == 1 && (size_t)p.RS * p.kc_blocks * block_n * 128 <= 131072;
+  CUtensorMap tmY = tmA;  // only read by the kernels that store through TMA (block_n >= 64)
+  if (block_n >= 64) {
+    uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
+    uint64_t strides[3] = {(uint64_t)d->ldy * 2, (uint64_t)d->Wo * d->ldy * 2, (uint64_t)d->Ho * d->Wo * d->ldy * 2};
+    uint32_t box[4] = {64, (uint32_t)kHaloTW, (uint32_t)kHaloTH, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    rc = make_tmap_bf16(&tmY, y, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  // resident weights: one N tile and all (slab, tap) tiles fit next to the A ring and the output staging
+  const bool resident = p.n_tiles == 1 && (block_n == 64 ? halo_smem_bytes<64, 4, 1, true>(hp)
+                                                         : halo_smem_bytes<32, 4, 1, true>(hp)) <= 232448;
   switch (block_n) {
-    case 256: return launch_halo<256, 3, 4, false>(tmA, tmB, hp, stream);
-    case 128: return launch_halo<128, 4, 6, false>(tmA, tmB, hp, stream);
+    case 256: return launch_halo<256, 2, 4, false>(tmA, tmB, tmY, hp, stream);
+    case 128: return launch_halo<128, 3, 6, false>(tmA, tmB, tmY, hp, stream);
     case 64:
-      return resident ? launch_halo<64, 4, 1, true>(tmA, tmB, hp, stream)
-                      : launch_halo<64, 4, 8, false>(tmA, tmB, hp, stream);
+      return resident ? launch_halo<64, 4, 1, true>(tmA, tmB, tmY, hp, stream)
+                      : launch_halo<64, 4, 8, false>(tmA, tmB, tmY, hp, stream);
     default:
-      return resident ? launch_halo<32, 4, 1, true>(tmA, tmB, hp, stream)
-                      : launch_halo<32, 4, 8, false>(tmA, tmB, hp, stream);
+      return resident ? launch_halo<32, 4, 1, true>(tmA, tmB, tmY, hp, stream)
+                      : launch_halo<32, 4, 8, false>(tmA, tmB, tmY, hp, stream);
   }
 }
 
