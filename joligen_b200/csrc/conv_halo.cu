@@ -27,7 +27,8 @@ struct HaloParams {
   int a_stage_bytes;
 };
 
-template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
+// KS: compile-time filter size (3 = 3x3: the tap loop is unrolled, descriptor offsets become immediates); 0 = runtime R, S.
+template <int BLOCK_N, int SA, int SB, bool B_RESIDENT, int KS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmY, const HaloParams hp) {
@@ -149,40 +150,65 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kc = 0; kc < k_slabs; ++kc) {
         mbar_wait(&a_full[sa], pha);
         tc_fence_after();
-        uint64_t a_desc = a_desc0 + (static_cast<uint32_t>(sa * hp.a_stage_bytes) >> 4);
-        int sx = 0;
-        for (int tap = 0; tap < p.RS; ++tap) {
-          uint64_t b_desc;
-          if (B_RESIDENT) {
-            b_desc = b_res;
-            b_res += B_BYTES >> 4;
-          } else {
-            mbar_wait(&b_full[sb], phb);
-            tc_fence_after();
-            b_desc = b_desc0 + (static_cast<uint32_t>(sb * B_BYTES) >> 4);
-          }
-          if (elect_one()) {
+        // One elected lane issues the whole slab (R*S taps x 4 k-steps).  The tensor pipe accepts only a couple of MMAs
+        // ahead, so every instruction between two tcgen05.mma of the issuing thread is potential pipe idle time:
+        // the tap loop is unrolled for 3x3 and nothing but the weight-tile barrier wait sits between the MMAs.
+        if (elect_one()) {
+          uint64_t a_desc = a_desc0 + (static_cast<uint32_t>(sa * hp.a_stage_bytes) >> 4);
+          uint64_t b_desc = b_res;
+          int sbl = sb;
+          uint32_t phl = phb;
+          auto tap_mmas = [&](int tap) {
+            if (!B_RESIDENT) {
+              mbar_wait(&b_full[sbl], phl);
+              tc_fence_after();
+              b_desc = b_desc0 + (static_cast<uint32_t>(sbl * B_BYTES) >> 4);
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
-            if (!B_RESIDENT) umma_commit(&b_empty[sb]);
-          }
-          __syncwarp();
-          if (!B_RESIDENT) {
-            if (++sb == SB) {
-              sb = 0;
-              phb ^= 1;
+            if (B_RESIDENT) {
+              b_desc += B_BYTES >> 4;
+            } else {
+              umma_commit(&b_empty[sbl]);
+              if (++sbl == SB) {
+                sbl = 0;
+                phl ^= 1;
+              }
+            }
+          };
+          if (KS > 0) {
+#pragma unroll
+            for (int r = 0; r < KS; ++r) {
+#pragma unroll
+              for (int c = 0; c < KS; ++c) {
+                tap_mmas(r * KS + c);
+                a_desc += 8;  // one pixel (128 B) to the right
+              }
+              a_desc += row_skip16;  // start of the next filter row
+            }
+          } else {
+            int sx = 0;
+            for (int tap = 0; tap < p.RS; ++tap) {
+              tap_mmas(tap);
+              a_desc += 8;
+              if (++sx == p.S) {
+                sx = 0;
+                a_desc += row_skip16;
+              }
             }
           }
-          // next tap: one pixel (128 B) to the right, or to the start of the next filter row
-          a_desc += 8;
-          if (++sx == p.S) {
-            sx = 0;
-            a_desc += row_skip16;
-          }
+          umma_commit(&a_empty[sa]);
         }
-        if (elect_one()) umma_commit(&a_empty[sa]);
         __syncwarp();
+        // ring state, advanced identically by all lanes
+        if (B_RESIDENT) {
+          b_res += static_cast<uint64_t>(p.RS) * (B_BYTES >> 4);
+        } else {
+          const int adv = sb + p.RS;
+          phb ^= static_cast<uint32_t>(adv / SB) & 1u;
+          sb = adv % SB;
+        }
         if (++sa == SA) {
           sa = 0;
           pha ^= 1;
@@ -250,21 +276,28 @@ static int halo_smem_bytes(const HaloParams& hp) {
          (2 * SA + 2 * SB + 6) * 8 + ((hp.c.Cout * 4 + 127) / 128) * 128 + 1024;
 }
 
-template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
-static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const HaloParams& hp,
-                       cudaStream_t stream) {
+template <int BLOCK_N, int SA, int SB, bool B_RESIDENT, int KS>
+static int launch_halo_ks(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const HaloParams& hp,
+                          cudaStream_t stream) {
   const int smem = halo_smem_bytes<BLOCK_N, SA, SB, B_RESIDENT>(hp);
   JG_CHECK(smem <= 232448, JG_ERR_INVALID, "conv_halo: smem %d too large", smem);
   static int attr_smem = 0;
   if (smem > attr_smem) {
-    JG_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, SA, SB, B_RESIDENT>,
+    JG_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, SA, SB, B_RESIDENT, KS>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
   const int grid = hp.c.total_tiles < num_sms() ? hp.c.total_tiles : num_sms();
-  conv_halo_kernel<BLOCK_N, SA, SB, B_RESIDENT><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmY, hp);
+  conv_halo_kernel<BLOCK_N, SA, SB, B_RESIDENT, KS><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmY, hp);
   JG_LAUNCH_CHECK();
   return JG_OK;
+}
+
+template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const HaloParams& hp,
+                       cudaStream_t stream) {
+  if (hp.R == 3 && hp.c.S == 3) return launch_halo_ks<BLOCK_N, SA, SB, B_RESIDENT, 3>(tmA, tmB, tmY, hp, stream);
+  return launch_halo_ks<BLOCK_N, SA, SB, B_RESIDENT, 0>(tmA, tmB, tmY, hp, stream);
 }
 
 int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
