@@ -140,7 +140,8 @@ template <int BLOCK_N>
 __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, EpiPrefetch& pf, const float* s_bias,
                                                        uint32_t t_acc, int q, int half, int n_tile, bool valid,
                                                        size_t pix, uint8_t* stage, int& stage_idx,
-                                                       const CUtensorMap* tmY, int c1, int c2, int c3, bool issuer) {
+                                                       const CUtensorMap* tmY, int c1, int c2, int c3, bool issuer,
+                                                       const uint8_t* res_tile = nullptr) {
   static_assert(BLOCK_N % 64 == 0, "TMA-store epilogue works on 64-channel slabs");
   const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16);
   const int row = q * 32 + (threadIdx.x & 31);
@@ -152,13 +153,20 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
     uint32_t v[32];
     tmem_ld_32x32(t_row + c, v);
     uint4 rcur[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) rcur[g] = pf.r[g];
-    if (p.res && valid && c + 64 < BLOCK_N) {
-      const __nv_bfloat16* rn = p.res + pix * p.ldres + co0 + 64;
+    if (res_tile) {
+      // residual slab staged in shared memory by TMA (same 128B-swizzled layout as the output staging)
 #pragma unroll
       for (int g = 0; g < 4; ++g)
-        if (co0 + 64 + g * 8 < p.Cout) pf.r[g] = *reinterpret_cast<const uint4*>(rn + g * 8);
+        rcur[g] = *reinterpret_cast<const uint4*>(res_tile + row * 128 + (((half * 4 + g) ^ (row & 7)) << 4));
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) rcur[g] = pf.r[g];
+      if (p.res && valid && c + 64 < BLOCK_N) {
+        const __nv_bfloat16* rn = p.res + pix * p.ldres + co0 + 64;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (co0 + 64 + g * 8 < p.Cout) pf.r[g] = *reinterpret_cast<const uint4*>(rn + g * 8);
+      }
     }
     tmem_ld_wait();
     uint8_t* buf = stage + stage_idx * kStageBytes + row * 128;

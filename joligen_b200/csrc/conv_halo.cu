@@ -31,11 +31,15 @@ struct HaloParams {
 template <int BLOCK_N, int SA, int SB, bool B_RESIDENT, int KS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmY, const HaloParams hp) {
+                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                 const HaloParams hp) {
   const ConvFwdParams& p = hp.c;
   constexpr int B_BYTES = BLOCK_N * 128;
   constexpr uint32_t TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
   constexpr bool TMA_STORE = BLOCK_N >= 64;  // output tiles leave through shared memory + TMA (conv_common.cuh)
+  // Residual tiles arrive through TMA as well when the tile is one 64-channel slab: per-lane 64-byte residual loads
+  // made the 64-channel 256^2 conv2 layers 80% slower than the same conv without a residual (L1/LSU bound).
+  constexpr bool RES_TMA = BLOCK_N == 64;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -44,15 +48,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int k_slabs = p.kc_blocks;
   const int b_tiles = B_RESIDENT ? p.RS * k_slabs : SB;
   uint8_t* stage = smB + static_cast<size_t>(b_tiles) * B_BYTES;  // 2 x 16 KB output staging (1024-byte aligned)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + (TMA_STORE ? 2 * kStageBytes : 0));
+  uint8_t* res_stage = stage + (TMA_STORE ? 2 * kStageBytes : 0);  // 2 x 16 KB residual tiles (RES_TMA)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(res_stage + (RES_TMA ? 2 * kStageBytes : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + SA;
   uint64_t* b_full = bars + 2 * SA;           // SB entries (entry 0 only when resident)
   uint64_t* b_empty = bars + 2 * SA + SB;
   uint64_t* tfull = bars + 2 * SA + 2 * SB;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_bias = reinterpret_cast<float*>(tempty + 4);
+  uint64_t* rfull = tempty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rfull + 2);
+  float* s_bias = reinterpret_cast<float*>(rfull + 4);
   conv_stage_bias(p, s_bias);
 
   const int warp = threadIdx.x >> 5;
@@ -62,6 +68,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (TMA_STORE) tma_prefetch_desc(&tmY);
+    if (RES_TMA && p.res) tma_prefetch_desc(&tmR);
     for (int i = 0; i < SA; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
@@ -73,6 +80,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 8);
+      mbar_init(&rfull[i], 1);
     }
     fence_barrier_init();
   }
@@ -231,6 +239,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     int stage_idx = 0;
     uint32_t acc_phase = 0;
+    const bool res_tma = RES_TMA && p.res != nullptr;
+    // residual tile of this CTA's (i)th tile -> res_stage[i & 1]; issued two tiles ahead by the issuer thread
+    auto load_res_tile = [&](int tile, int buf) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int tw = m_tile % p.tiles_w;
+      const int th = (m_tile / p.tiles_w) % p.tiles_h;
+      const int tn = m_tile / (p.tiles_w * p.tiles_h);
+      mbar_arrive_expect_tx(&rfull[buf], kStageBytes);
+      tma_load_4d(res_stage + buf * kStageBytes, &tmR, &rfull[buf], n_tile * BLOCK_N, tw * kHaloTW, th * kHaloTH, tn);
+    };
+    if (res_tma && issuer) {
+      if (blockIdx.x < p.total_tiles) load_res_tile(blockIdx.x, 0);
+      if (blockIdx.x + gridDim.x < p.total_tiles) load_res_tile(blockIdx.x + gridDim.x, 1);
+    }
+    int rbuf = 0;
+    uint32_t rphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
@@ -241,13 +266,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int ph = th * kHaloTH + (row / kHaloTW);
       const bool valid = (pw < p.Wo) && (ph < p.Ho);
       const size_t pix = (static_cast<size_t>(tn) * p.Ho + ph) * p.Wo + pw;
-      conv_epilogue_prefetch<BLOCK_N>(p, pf, half, n_tile, valid, pix);
+      if (!res_tma) conv_epilogue_prefetch<BLOCK_N>(p, pf, half, n_tile, valid, pix);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      if constexpr (TMA_STORE)
+      if constexpr (TMA_STORE) {
+        if (res_tma) mbar_wait(&rfull[rbuf], rphase);
         conv_epilogue_tile_tma<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile,
-                                        valid, pix, stage, stage_idx, &tmY, tw * kHaloTW, th * kHaloTH, tn, issuer);
-      else
+                                        valid, pix, stage, stage_idx, &tmY, tw * kHaloTW, th * kHaloTH, tn, issuer,
+                                        res_tma ? res_stage + rbuf * kStageBytes : nullptr);
+        if (res_tma) {
+          // the slab barrier inside the epilogue ordered every thread's reads of this residual buffer before here
+          if (issuer && tile + 2 * static_cast<int>(gridDim.x) < p.total_tiles)
+            load_res_tile(tile + 2 * gridDim.x, rbuf);
+          if (++rbuf == 2) {
+            rbuf = 0;
+            rphase ^= 1;
+          }
+        }
+      } else
         conv_epilogue_tile<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile,
                                     valid, pix);
       tc_fence_before();
@@ -273,12 +309,12 @@ template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
 static int halo_smem_bytes(const HaloParams& hp) {
   const int b_tiles = B_RESIDENT ? hp.c.RS * hp.c.kc_blocks : SB;
   return SA * hp.a_stage_bytes + b_tiles * BLOCK_N * 128 + (BLOCK_N >= 64 ? 2 * kStageBytes : 0) +
-         (2 * SA + 2 * SB + 6) * 8 + ((hp.c.Cout * 4 + 127) / 128) * 128 + 1024;
+         (BLOCK_N == 64 ? 2 * kStageBytes : 0) + (2 * SA + 2 * SB + 8) * 8 + ((hp.c.Cout * 4 + 127) / 128) * 128 + 1024;
 }
 
 template <int BLOCK_N, int SA, int SB, bool B_RESIDENT, int KS>
-static int launch_halo_ks(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const HaloParams& hp,
-                          cudaStream_t stream) {
+static int launch_halo_ks(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
+                          const HaloParams& hp, cudaStream_t stream) {
   const int smem = halo_smem_bytes<BLOCK_N, SA, SB, B_RESIDENT>(hp);
   JG_CHECK(smem <= 232448, JG_ERR_INVALID, "conv_halo: smem %d too large", smem);
   static int attr_smem = 0;
@@ -288,16 +324,16 @@ static int launch_halo_ks(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     attr_smem = smem;
   }
   const int grid = hp.c.total_tiles < num_sms() ? hp.c.total_tiles : num_sms();
-  conv_halo_kernel<BLOCK_N, SA, SB, B_RESIDENT, KS><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmY, hp);
+  conv_halo_kernel<BLOCK_N, SA, SB, B_RESIDENT, KS><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmY, tmR, hp);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }
 
 template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
-static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const HaloParams& hp,
-                       cudaStream_t stream) {
-  if (hp.R == 3 && hp.c.S == 3) return launch_halo_ks<BLOCK_N, SA, SB, B_RESIDENT, 3>(tmA, tmB, tmY, hp, stream);
-  return launch_halo_ks<BLOCK_N, SA, SB, B_RESIDENT, 0>(tmA, tmB, tmY, hp, stream);
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
+                       const HaloParams& hp, cudaStream_t stream) {
+  if (hp.R == 3 && hp.c.S == 3) return launch_halo_ks<BLOCK_N, SA, SB, B_RESIDENT, 3>(tmA, tmB, tmY, tmR, hp, stream);
+  return launch_halo_ks<BLOCK_N, SA, SB, B_RESIDENT, 0>(tmA, tmB, tmY, tmR, hp, stream);
 }
 
 int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
@@ -355,18 +391,28 @@ int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed,
     rc = make_tmap_bf16(&tmY, y, 4, dims, strides, box, es);
     if (rc) return rc;
   }
-  // resident weights: one N tile and all (slab, tap) tiles fit next to the A ring and the output staging
-  const bool resident = p.n_tiles == 1 && (block_n == 64 ? halo_smem_bytes<64, 4, 1, true>(hp)
+  CUtensorMap tmR = tmA;  // residual tiles (64-channel kernels with a residual)
+  if (block_n == 64 && residual) {
+    uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
+    uint64_t strides[3] = {(uint64_t)d->ldres * 2, (uint64_t)d->Wo * d->ldres * 2,
+                           (uint64_t)d->Ho * d->Wo * d->ldres * 2};
+    uint32_t box[4] = {64, (uint32_t)kHaloTW, (uint32_t)kHaloTH, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    rc = make_tmap_bf16(&tmR, residual, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  // resident weights: one N tile and all (slab, tap) tiles fit next to the A ring and the staging buffers
+  const bool resident = p.n_tiles == 1 && (block_n == 64 ? halo_smem_bytes<64, 3, 1, true>(hp)
                                                          : halo_smem_bytes<32, 4, 1, true>(hp)) <= 232448;
   switch (block_n) {
-    case 256: return launch_halo<256, 2, 4, false>(tmA, tmB, tmY, hp, stream);
-    case 128: return launch_halo<128, 3, 6, false>(tmA, tmB, tmY, hp, stream);
+    case 256: return launch_halo<256, 2, 4, false>(tmA, tmB, tmY, tmR, hp, stream);
+    case 128: return launch_halo<128, 3, 6, false>(tmA, tmB, tmY, tmR, hp, stream);
     case 64:
-      return resident ? launch_halo<64, 4, 1, true>(tmA, tmB, tmY, hp, stream)
-                      : launch_halo<64, 4, 8, false>(tmA, tmB, tmY, hp, stream);
+      return resident ? launch_halo<64, 3, 1, true>(tmA, tmB, tmY, tmR, hp, stream)
+                      : launch_halo<64, 3, 7, false>(tmA, tmB, tmY, tmR, hp, stream);
     default:
-      return resident ? launch_halo<32, 4, 1, true>(tmA, tmB, tmY, hp, stream)
-                      : launch_halo<32, 4, 8, false>(tmA, tmB, tmY, hp, stream);
+      return resident ? launch_halo<32, 4, 1, true>(tmA, tmB, tmY, tmR, hp, stream)
+                      : launch_halo<32, 4, 8, false>(tmA, tmB, tmY, tmR, hp, stream);
   }
 }
 

@@ -1,5 +1,6 @@
 """Run one conv shape a few times (for ncu captures / quick timing).
-    python tools/gpu_conv_one.py N H W Cin Cout K [what=fwd|wgrad] [reps]"""
+    python tools/gpu_conv_one.py N H W Cin Cout K [what=fwd|fwdres|wgrad] [reps]
+fwdres = forward with the residual-add epilogue; inputs rotate over 3 buffers so that nothing is L2-resident."""
 import os
 import sys
 
@@ -18,7 +19,21 @@ wt = torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) **
 bias = torch.zeros(cout, device="cuda")
 wf, wd = K.pack_conv_weight(wt)
 dy = torch.randn(n, h, w, cout, device="cuda", generator=g).to(torch.bfloat16)
-fn = (lambda: K.conv2d_fwd(x, wf, bias, cout, k, k)) if what == "fwd" else (lambda: K.conv2d_wgrad(x, dy, cout, k, k))
+xs = [x, x.clone(), x.clone()]
+dys = [dy, dy.clone(), dy.clone()]
+it = [0]
+
+
+def fn():
+    it[0] += 1
+    xi, di = xs[it[0] % 3], dys[it[0] % 3]
+    if what == "fwd":
+        return K.conv2d_fwd(xi, wf, bias, cout, k, k)
+    if what == "fwdres":
+        return K.conv2d_fwd(xi, wf, bias, cout, k, k, residual=di)
+    return K.conv2d_wgrad(xi, di, cout, k, k)
+
+
 for _ in range(3):
     fn()
 torch.cuda.synchronize()
