@@ -45,10 +45,11 @@ struct EpiPrefetch {
   uint4 r[4];
 };
 
-// All threads: copy bias[0, Cout) (fp32, Cout a multiple of 8) into shared memory (call before __syncthreads).
+// All threads: copy bias[0, Cout) (fp32, Cout a multiple of 8) into shared memory, followed by 64 zeros (the TMA-store
+// epilogue processes whole 64-channel slabs without per-group bounds checks).  Call before __syncthreads.
 __device__ __forceinline__ void conv_stage_bias(const ConvFwdParams& p, float* s_bias) {
   if (p.bias)
-    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
+    for (int i = threadIdx.x; i < p.Cout + 64; i += blockDim.x) s_bias[i] = i < p.Cout ? p.bias[i] : 0.f;
 }
 
 template <int BLOCK_N>
@@ -145,6 +146,7 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
   static_assert(BLOCK_N % 64 == 0, "TMA-store epilogue works on 64-channel slabs");
   const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16);
   const int row = q * 32 + (threadIdx.x & 31);
+  const int swz = row & 7;
 #pragma unroll 1
   for (int c = half * 32; c < BLOCK_N; c += 64) {
     const int co0 = n_tile * BLOCK_N + c;
@@ -152,16 +154,25 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
     if (slab_co >= p.Cout) break;                // uniform over all 8 warps: the rest of the tile is channel padding
     uint32_t v[32];
     tmem_ld_32x32(t_row + c, v);
+    // While the TMEM load is in flight: bias (shared memory, zero-padded past Cout) and residual.  Straight-line code:
+    // the four 8-channel groups are independent, the two epilogue warps of an SM sub-partition have little else to
+    // hide latency with.  Channels >= Cout hold don't-care values that the TMA store clips.
+    float4 bias4[8];
+    if (s_bias) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) bias4[g] = *reinterpret_cast<const float4*>(s_bias + co0 + g * 4);
+    }
     uint4 rcur[4];
+    const bool has_res = p.res != nullptr;
     if (res_tile) {
       // residual slab staged in shared memory by TMA (same 128B-swizzled layout as the output staging)
 #pragma unroll
       for (int g = 0; g < 4; ++g)
-        rcur[g] = *reinterpret_cast<const uint4*>(res_tile + row * 128 + (((half * 4 + g) ^ (row & 7)) << 4));
-    } else {
+        rcur[g] = *reinterpret_cast<const uint4*>(res_tile + row * 128 + (((half * 4 + g) ^ swz) << 4));
+    } else if (has_res) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) rcur[g] = pf.r[g];
-      if (p.res && valid && c + 64 < BLOCK_N) {
+      if (valid && c + 64 < BLOCK_N) {
         const __nv_bfloat16* rn = p.res + pix * p.ldres + co0 + 64;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -169,40 +180,42 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
       }
     }
     tmem_ld_wait();
-    uint8_t* buf = stage + stage_idx * kStageBytes + row * 128;
+    float f[32];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {  // 8 channels per 16-byte chunk
-      float f[8];
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (s_bias) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-      if (co0 + g * 8 < p.Cout) {
-        if (s_bias) {
-          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + co0 + g * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + co0 + g * 8 + 4);
-          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-          f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-        }
-        if (p.res && valid) {
-          const uint4 rv = rcur[g];
-          const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y);
-          const float2 r2 = unpack_bf16x2(rv.z), r3 = unpack_bf16x2(rv.w);
-          f[0] += p.res_scale * r0.x; f[1] += p.res_scale * r0.y;
-          f[2] += p.res_scale * r1.x; f[3] += p.res_scale * r1.y;
-          f[4] += p.res_scale * r2.x; f[5] += p.res_scale * r2.y;
-          f[6] += p.res_scale * r3.x; f[7] += p.res_scale * r3.y;
-        }
-        if (p.act != JG_ACT_NONE) {
+      for (int g = 0; g < 8; ++g) {
+        f[g * 4 + 0] += bias4[g].x; f[g * 4 + 1] += bias4[g].y;
+        f[g * 4 + 2] += bias4[g].z; f[g * 4 + 3] += bias4[g].w;
+      }
+    }
+    if (has_res && (res_tile || valid)) {
+      const float rs = p.res_scale;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t w4[4] = {rcur[g].x, rcur[g].y, rcur[g].z, rcur[g].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 r = unpack_bf16x2(w4[k]);
+          f[g * 8 + 2 * k] = fmaf(rs, r.x, f[g * 8 + 2 * k]);
+          f[g * 8 + 2 * k + 1] = fmaf(rs, r.y, f[g * 8 + 2 * k + 1]);
         }
       }
+    }
+    if (p.act != JG_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+    }
+    uint8_t* buf = stage + stage_idx * kStageBytes + row * 128;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {  // 8 channels per 16-byte chunk; 128B swizzle: chunk index XOR (row mod 8)
       uint4 o;
-      o.x = pack_bf16x2(f[0], f[1]);
-      o.y = pack_bf16x2(f[2], f[3]);
-      o.z = pack_bf16x2(f[4], f[5]);
-      o.w = pack_bf16x2(f[6], f[7]);
-      const int chunk = (half * 4 + g) ^ (row & 7);  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
-      *reinterpret_cast<uint4*>(buf + chunk * 16) = o;
+      o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+      o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+      o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+      o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+      *reinterpret_cast<uint4*>(buf + (((half * 4 + g) ^ swz) << 4)) = o;
     }
     fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA (async proxy)
     if (issuer) bulk_wait_read<0>();     // the previous slab's store has released the other buffer

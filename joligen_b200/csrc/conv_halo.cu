@@ -309,7 +309,7 @@ template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
 static int halo_smem_bytes(const HaloParams& hp) {
   const int b_tiles = B_RESIDENT ? hp.c.RS * hp.c.kc_blocks : SB;
   return SA * hp.a_stage_bytes + b_tiles * BLOCK_N * 128 + (BLOCK_N >= 64 ? 2 * kStageBytes : 0) +
-         (BLOCK_N == 64 ? 2 * kStageBytes : 0) + (2 * SA + 2 * SB + 8) * 8 + ((hp.c.Cout * 4 + 127) / 128) * 128 + 1024;
+         (BLOCK_N == 64 ? 2 * kStageBytes : 0) + (2 * SA + 2 * SB + 8) * 8 + (((hp.c.Cout + 64) * 4 + 127) / 128) * 128 + 1024;
 }
 
 template <int BLOCK_N, int SA, int SB, bool B_RESIDENT, int KS>

@@ -25,8 +25,9 @@ namespace jg {
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const ConvFwdParams p) {
+                const __grid_constant__ CUtensorMap tmY, const ConvFwdParams p) {
   constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr bool TMA_STORE = BLOCK_N >= 64;  // output tiles leave through shared memory + TMA (conv_common.cuh)
   constexpr uint32_t TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of 2");
 
@@ -34,7 +35,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
   uint8_t* smB = smem + STAGES * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + STAGES * B_BYTES);
+  uint8_t* stage_out = smB + STAGES * B_BYTES;  // 2 x 16 KB output staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + (TMA_STORE ? 2 * kStageBytes : 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -49,6 +51,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (TMA_STORE) tma_prefetch_desc(&tmY);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -115,23 +118,31 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint64_t a_desc = desc_advance(a_desc0, stage * kABytes);
-        const uint64_t b_desc = desc_advance(b_desc0, stage * B_BYTES);
-        if (elect_one()) {
+      // one elected lane issues the whole tile (see conv_halo.cu: instructions between two MMAs are pipe idle time)
+      if (elect_one()) {
+        int st = stage;
+        uint32_t ph = phase;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint64_t a_desc = desc_advance(a_desc0, st * kABytes);
+          const uint64_t b_desc = desc_advance(b_desc0, st * B_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16(d_tmem, desc_advance(a_desc, k * 32), desc_advance(b_desc, k * 32), idesc,
                       (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);
+          umma_commit(&empty[st]);
+          if (++st == STAGES) {
+            st = 0;
+            ph ^= 1;
+          }
         }
-        __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+      }
+      __syncwarp();
+      {
+        const int adv = stage + k_blocks;
+        phase ^= static_cast<uint32_t>(adv / STAGES) & 1u;
+        stage = adv % STAGES;
       }
       if (elect_one()) umma_commit(&tfull[acc]);
       __syncwarp();
@@ -145,8 +156,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    const bool issuer = threadIdx.x == 64;  // warp 2, lane 0
     EpiPrefetch pf;
     int acc = 0;
+    int stage_idx = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
@@ -163,8 +176,13 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       conv_epilogue_prefetch<BLOCK_N>(p, pf, half, n_tile, valid, pix);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      conv_epilogue_tile<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile, valid,
-                                   pix);
+      if constexpr (TMA_STORE)
+        conv_epilogue_tile_tma<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile,
+                                        valid, pix, stage_out, stage_idx, &tmY, tw * p.TW, th * p.TH, tn * p.TN,
+                                        issuer);
+      else
+        conv_epilogue_tile<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile,
+                                    valid, pix);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -173,6 +191,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         acc_phase ^= 1;
       }
     }
+    if (TMA_STORE && issuer) bulk_wait_read<0>();  // the staging buffers live until the last store has read them
   }
 
   tc_fence_before();
@@ -397,9 +416,11 @@ static void pick_patch(int total, int Wo, int Ho, int* tw, int* th, int* tn) {
 }
 
 template <int BLOCK_N, int STAGES>
-static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvFwdParams& p,
+static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const ConvFwdParams& p,
                       cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (2 * STAGES + 6) * 8 + 8192 + 1024;
+  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (BLOCK_N >= 64 ? 2 * kStageBytes : 0) +
+                       (2 * STAGES + 6) * 8 + 8192 + 256 + 1024;
+  static_assert(smem <= 232448, "conv_fwd_kernel: shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
     JG_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -407,7 +428,7 @@ static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
     attr_done = true;
   }
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_fwd_kernel<BLOCK_N, STAGES><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  conv_fwd_kernel<BLOCK_N, STAGES><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmY, p);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }
@@ -509,11 +530,20 @@ extern "C" int jg_conv2d_fwd(const jg_conv_desc* d, const void* x, const void* w
     rc = make_tmap_bf16(&tmB, w_packed, 3, dims, strides, box, es);
     if (rc) return rc;
   }
+  CUtensorMap tmY = tmA;  // only read by the kernels that store through TMA (block_n >= 64)
+  if (block_n >= 64) {
+    uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
+    uint64_t strides[3] = {(uint64_t)d->ldy * 2, (uint64_t)d->Wo * d->ldy * 2, (uint64_t)d->Ho * d->Wo * d->ldy * 2};
+    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+    uint32_t es[4] = {1, 1, 1, 1};
+    rc = make_tmap_bf16(&tmY, y, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
   switch (block_n) {
-    case 256: return launch_fwd<256, 4>(tmA, tmB, p, stream);
-    case 128: return launch_fwd<128, 6>(tmA, tmB, p, stream);
-    case 64: return launch_fwd<64, 8>(tmA, tmB, p, stream);
-    default: return launch_fwd<32, 8>(tmA, tmB, p, stream);
+    case 256: return launch_fwd<256, 3>(tmA, tmB, tmY, p, stream);
+    case 128: return launch_fwd<128, 5>(tmA, tmB, tmY, p, stream);
+    case 64: return launch_fwd<64, 7>(tmA, tmB, tmY, p, stream);
+    default: return launch_fwd<32, 8>(tmA, tmB, tmY, p, stream);
   }
 }
 
