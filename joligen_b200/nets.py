@@ -61,12 +61,12 @@ class ConvPack:
         return self.packed
 
 
-def _conv(x, conv, pack, residual=None, res_scale=1.0):
+def _conv(x, conv, pack, residual=None, res_scale=1.0, out=None):
     w = conv.weight
     if w.dim() == 3:
         w = w.unsqueeze(-1)
     return ops.conv2d(x, w, conv.bias, pack.get(), stride=conv.stride[0], pad=conv.padding[0], residual=residual,
-                      res_scale=res_scale, grad_sink=conv.weight)
+                      res_scale=res_scale, grad_sink=conv.weight, out=out)
 
 
 class GroupNorm(nn.Module):
@@ -99,10 +99,27 @@ class EmbedBlock(nn.Module):
 
 
 class EmbedSequential(nn.Sequential, EmbedBlock):
-    def forward_nhwc(self, x, emb):
-        for layer in self:
-            x = layer.forward_nhwc(x, emb) if isinstance(layer, EmbedBlock) else layer.forward_nhwc(x)
+    def forward_nhwc(self, x, emb, out=None):
+        """out: optional destination view for the LAST layer's output (see UNet.forward_nhwc)."""
+        last = len(self) - 1
+        for i, layer in enumerate(self):
+            kw = {"out": out} if (i == last and out is not None) else {}
+            x = layer.forward_nhwc(x, emb, **kw) if isinstance(layer, EmbedBlock) else layer.forward_nhwc(x, **kw)
         return x
+
+    def out_geometry(self, h, w):
+        """(H, W, C) of the output for an (h, w) input, or None when the last layer cannot write into a view."""
+        c = None
+        for layer in self:
+            if isinstance(layer, ResBlock):
+                c = layer.out_channel
+                if layer.updown:
+                    h, w = (h * 2, w * 2) if layer.up else (h // 2, w // 2)
+            elif isinstance(layer, AttentionBlock):
+                c = layer.channels
+            else:
+                return None
+        return None if c is None else (h, w, (c + 7) // 8 * 8)
 
 
 class _Resample(nn.Module):
@@ -167,7 +184,7 @@ class ResBlock(EmbedBlock):
         self._pack_out = ConvPack(self.out_layers[3])
         self._pack_skip = ConvPack(self.skip_connection) if isinstance(self.skip_connection, nn.Conv2d) else None
 
-    def forward_nhwc(self, x, emb):
+    def forward_nhwc(self, x, emb, out=None):
         h, x = self.in_layers[0].forward_tap_nhwc(x, act=L.ACT_SILU)
         if self.updown:
             h = self.h_upd.forward_nhwc(h)
@@ -183,7 +200,7 @@ class ResBlock(EmbedBlock):
         skipw = 1.0 / math.sqrt(2) if self.efficient else 1.0
         if self._pack_skip is not None:
             x = _conv(x, self.skip_connection, self._pack_skip)
-        return _conv(h, self.out_layers[3], self._pack_out, residual=x, res_scale=skipw)
+        return _conv(h, self.out_layers[3], self._pack_out, residual=x, res_scale=skipw, out=out)
 
     def forward(self, x, emb):
         """Drop-in NCHW fp32 signature of the reference block."""
@@ -219,12 +236,12 @@ class AttentionBlock(nn.Module):
         self._pack_qkv = ConvPack(self.qkv)
         self._pack_proj = ConvPack(self.proj_out)
 
-    def forward_nhwc(self, x):
+    def forward_nhwc(self, x, out=None):
         c = self.channels
         xn, x = ops.group_norm_tap(x, None, None, c, film=None, act=L.ACT_NONE)  # per-(n, c) statistics over T
         qkv = _conv(xn, self.qkv, self._pack_qkv)
         a = ops.attention(qkv, self.num_heads, c // self.num_heads)
-        return _conv(a, self.proj_out, self._pack_proj, residual=x, res_scale=1.0)
+        return _conv(a, self.proj_out, self._pack_proj, residual=x, res_scale=1.0, out=out)
 
     def forward(self, x):
         y = self.forward_nhwc(ops.to_nhwc(x))
@@ -311,10 +328,23 @@ class UNet(nn.Module):
         for module in self.input_blocks:
             h = module.forward_nhwc(h, emb)
             hs.append(h)
-        h = self.middle_block.forward_nhwc(h, emb)
+        # torch.cat([h, hs.pop()], dim=1) (unet_generator_attn.py:687) without copying h: the block that produces h
+        # writes it straight into the first channels of the next block's concat buffer; only the skip is copied.
+        def concat_buffer(block, hin, win):
+            geo = block.out_geometry(hin, win) if hs else None
+            if geo is None or tuple(hs[-1].shape[1:3]) != geo[:2]:
+                return None, None
+            buf = torch.empty((h.shape[0], geo[0], geo[1], geo[2] + hs[-1].shape[-1]), dtype=torch.bfloat16,
+                              device=h.device)
+            return buf, buf[..., :geo[2]]
+
+        buf, dst = concat_buffer(self.middle_block, h.shape[1], h.shape[2])
+        h = self.middle_block.forward_nhwc(h, emb, out=dst)
         for module in self.output_blocks:
-            h = ops.cat_channels(h, hs.pop())
-            h = module.forward_nhwc(h, emb)
+            skip = hs.pop()
+            h = ops.cat_into(buf, h, skip) if buf is not None else ops.cat_channels(h, skip)
+            buf, dst = concat_buffer(module, h.shape[1], h.shape[2])
+            h = module.forward_nhwc(h, emb, out=dst)
         h = self.out[0].forward_nhwc(h, act=L.ACT_SILU)
         return _conv(h, self.out[2], self._pack_outconv)
 

@@ -18,16 +18,34 @@ def _needs(ctx, i):
     return ctx.needs_input_grad[i]
 
 
+def _rows(t):
+    """t as the kernels can address it: an NHWC tensor or a channel slice of one (unit channel stride, uniform row
+    stride that is a multiple of 8 elements, 16-byte aligned start).  Anything else is copied."""
+    if t.is_contiguous():
+        return t
+    if t.dim() == 4 and t.stride(3) == 1:
+        n, h, w, _ = t.shape
+        ld = t.stride(2)
+        if (ld % 8 == 0 and t.stride(1) == w * ld and (n == 1 or t.stride(0) == h * w * ld)
+                and t.storage_offset() % 8 == 0):
+            return t
+    return t.contiguous()
+
+
 class Conv2dFn(torch.autograd.Function):
     """y = conv(x, W) + b (+ res_scale*residual).  x NHWC bf16 with channels padded to a multiple of 8;
     W fp32 OIHW (its bf16 packed copies wf / wd and the 8-padded bias are passed in).  The output has
     round_up(Cout, 8) channels (padding channels are exactly zero)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, wf, wd, bias_p, stride, pad, res_scale, sink):
+    def forward(ctx, x, weight, bias, residual, wf, wd, bias_p, stride, pad, res_scale, sink, out):
         cout, cin, r, s = weight.shape
         cout8 = (cout + 7) // 8 * 8
-        y = K.conv2d_fwd(x, wf, bias_p, cout8, r, s, stride=stride, pad=pad, residual=residual, res_scale=res_scale)
+        # out: optional destination (a channel slice of a wider NHWC buffer, e.g. the next block's concat input)
+        y = K.conv2d_fwd(x, wf, bias_p, cout8, r, s, stride=stride, pad=pad, residual=residual, res_scale=res_scale,
+                         out=out)
+        if out is not None:
+            y = y.view(y.shape)  # a fresh tensor object: autograd must not see an input returned as an output
         ctx.save_for_backward(x, wd)
         ctx.geom = (cout, cin, r, s, stride, pad, res_scale, bias is not None, residual is not None)
         ctx.sink = sink  # (weight Parameter,) or None: accumulate dW straight into its .grad when possible
@@ -40,7 +58,7 @@ class Conv2dFn(torch.autograd.Function):
         cout8 = (cout + 7) // 8 * 8
         # a GroupNorm backward that produced this very tensor has already summed it over (n, pixel)
         colsum = getattr(dy, "_jg_colsum", None) if dy.is_contiguous() else None
-        dy = dy.contiguous()
+        dy = _rows(dy)
         dx = dw = db = dres = None
         if _needs(ctx, 0):
             if stride != 1:
@@ -66,7 +84,7 @@ class Conv2dFn(torch.autograd.Function):
                 db = db[:cout].contiguous()
         if has_res and _needs(ctx, 3):
             dres = dy if res_scale == 1.0 else (dy.float() * res_scale).to(torch.bfloat16)
-        return dx, dw, db, dres, None, None, None, None, None, None, None
+        return dx, dw, db, dres, None, None, None, None, None, None, None, None
 
 
 class GroupNormFn(torch.autograd.Function):
@@ -83,7 +101,7 @@ class GroupNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, gamma, beta, film, stats, ab = ctx.saved_tensors
         groups, act = ctx.cfg
-        dy = dy.contiguous()
+        dy = _rows(dy)
         need_p = gamma is not None and (_needs(ctx, 1) or _needs(ctx, 2))
         need_f = film is not None and _needs(ctx, 3)
         colsum = _colsum_buffer(x)
@@ -112,13 +130,13 @@ class GroupNormTapFn(torch.autograd.Function):
         groups, act = ctx.cfg
         if dy is None:
             return dtap, None, None, None, None, None
-        dy = dy.contiguous()
+        dy = _rows(dy)
         need_p = gamma is not None and (_needs(ctx, 1) or _needs(ctx, 2))
         need_f = film is not None and _needs(ctx, 3)
         colsum = _colsum_buffer(x)
         dx, dgamma, dbeta, dfilm = K.groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab,
                                                    need_param_grads=need_p, need_film_grad=need_f,
-                                                   addend=None if dtap is None else dtap.contiguous(),
+                                                   addend=None if dtap is None else _rows(dtap),
                                                    colsum=colsum)
         if colsum is not None:
             dx._jg_colsum = colsum
@@ -186,13 +204,27 @@ class CatChannelsFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d):
+        # channel-slice views: every backward kernel addresses its incoming gradient with a row stride
         ca, cb = ctx.split
-        n, h, w, _ = d.shape
-        da = torch.empty((n, h, w, ca), dtype=torch.bfloat16, device=d.device)
-        db = torch.empty((n, h, w, cb), dtype=torch.bfloat16, device=d.device)
-        K.copy_channels(d[..., :ca], da)
-        K.copy_channels(d[..., ca:], db)
-        return da, db
+        return d[..., :ca], d[..., ca:]
+
+
+class CatIntoFn(torch.autograd.Function):
+    """torch.cat([a, b], dim=channel) where `a` already IS buf[..., :Ca] (its producer wrote it there through
+    conv2d(out=...)): only b is copied.  Returns buf."""
+
+    @staticmethod
+    def forward(ctx, a, b, buf):
+        ca, cb = a.shape[-1], b.shape[-1]
+        assert buf.shape[-1] == ca + cb and a.data_ptr() == buf.data_ptr() and a.stride(2) == buf.stride(2)
+        K.copy_channels(b, buf[..., ca:])
+        ctx.split = (ca, cb)
+        return buf.view(buf.shape)
+
+    @staticmethod
+    def backward(ctx, d):
+        ca, cb = ctx.split
+        return d[..., :ca], d[..., ca:], None
 
 
 class ToNHWCFn(torch.autograd.Function):
@@ -239,15 +271,16 @@ class PaletteLossFn(torch.autograd.Function):
         return K.palette_loss_bwd(noise, noise_hat, mask, w_b, g, lambda_g, l1), None, None, None, None, None
 
 
-def conv2d(x, weight, bias, packed, stride=1, pad=None, residual=None, res_scale=1.0, grad_sink=None):
+def conv2d(x, weight, bias, packed, stride=1, pad=None, residual=None, res_scale=1.0, grad_sink=None, out=None):
     """packed = (wf, wd, bias_padded) from nets.ConvPack.get(); grad_sink = the weight nn.Parameter whose
-    (pre-existing, fp32, contiguous) .grad the weight gradient is accumulated into directly."""
+    (pre-existing, fp32, contiguous) .grad the weight gradient is accumulated into directly; out = optional
+    destination view (a channel slice of a wider NHWC buffer)."""
     r = weight.shape[2]
     if pad is None:
         pad = (r - 1) // 2
     wf, wd, bias_p = packed
     return Conv2dFn.apply(x, weight, bias, residual, wf, wd, bias_p, stride, pad, res_scale,
-                          None if grad_sink is None else (grad_sink,))
+                          None if grad_sink is None else (grad_sink,), out)
 
 
 def group_norm(x, gamma, beta, groups, film=None, act=L.ACT_NONE):
@@ -277,6 +310,11 @@ def avgpool2x(x):
 
 def cat_channels(a, b):
     return CatChannelsFn.apply(a, b)
+
+
+def cat_into(buf, a, b):
+    """a = buf[..., :Ca] already in place; copy b behind it and return the full buffer."""
+    return CatIntoFn.apply(a, b, buf)
 
 
 def to_nhwc(x):
