@@ -472,8 +472,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfl
 // Rows per block for a grid of about per_sm blocks per SM (at least 32 rows per block).  The kernels that end in a
 // block-level reduction run as ONE wave of co-resident blocks: measured on B200, twice the blocks cost 25-70% more time.
 static int rows_per_block_for(int HW, int N, int per_sm) {
-  static const int scale = getenv("JG_GN_BLOCK_SCALE") ? atoi(getenv("JG_GN_BLOCK_SCALE")) : 1;  // experiments
-  const int target_blocks = num_sms() * per_sm * scale;
+  const int target_blocks = num_sms() * per_sm;
   int chunks = target_blocks / (N > 0 ? N : 1);
   if (chunks < 1) chunks = 1;
   int rpb = (HW + chunks - 1) / chunks;
@@ -543,9 +542,8 @@ extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy
   float* gAB = k23 + (size_t)N * groups * 2;
   JG_CUDA(cudaMemsetAsync(AB, 0, sizeof(float) * (size_t)N * C * 2, stream));
   if (dx_colsum) JG_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, stream));
-  static const int apply_per_sm = getenv("JG_GN_BWD_APPLY_PER_SM") ? atoi(getenv("JG_GN_BWD_APPLY_PER_SM")) : 2;
   const int rpb1 = rows_per_block_for(HW, N, 2);
-  const int rpb = rows_per_block_for(HW, N, apply_per_sm);
+  const int rpb = rows_per_block_for(HW, N, 2);
   dim3 grid1((HW + rpb1 - 1) / rpb1, N);
   dim3 grid((HW + rpb - 1) / rpb, N);
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
