@@ -654,7 +654,11 @@ int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int 
   // N = 128 runs the MMA at full rate (N = 64 is shared-memory bound at 2/3 rate) but holds only 8 taps in TMEM, so a 3x3
   // filter takes two passes over the activations; past 9 taps the extra passes cost more than the MMA rate buys.
   const int nco = (d->Cout >= 128 && d->R * d->S <= 9 && !force64) ? 128 : 64;
-  const int taps_per_launch = nco == 128 ? 8 : 16;  // 512 TMEM columns / nco columns per pair * 2 taps per pair
+  // 512 TMEM columns / nco columns per pair * 2 taps per pair.  With NCO = 128 a 3x3 filter needs two passes over the
+  // activations; 6 + 3 taps (3 + 2 MMA pairs) instead of 8 + 1 keeps the second pass from being a pure L2 stream
+  // (28.8 KB of operands per 256 MMA cycles per SM is twice what the L2 sustains chip-wide).
+  // Measured (profiles/r01_wgrad_taps.log): 6 + 3 is 4-10 % faster than 8 + 1 on every 3x3 layer with Cout >= 128.
+  const int taps_per_launch = nco == 128 ? (d->R * d->S == 9 ? 6 : 8) : 16;
   WgradHaloParams p{};
   p.Cin = d->Cin; p.Cout = d->Cout; p.RS = d->R * d->S; p.S = d->S; p.pad = d->pad;
   p.PW = 8 + d->S - 1;
