@@ -134,11 +134,39 @@ int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx,
  *   scale ch^-1/4 on q and k, softmax in fp32).  qkv NHWC [N][T][3*heads*ch]; out [N][T][heads*ch];
  *   lse fp32 [N*heads][T] (log2 domain) is saved for the backward.  T % 64 == 0, ch in {16,32,64}.
  * ------------------------------------------------------------------------------------------- */
+/* layout 0: per-head (q|k|v) channel interleave (QKVAttentionLegacy, unet_generator_attn.py:331-347);
+ * layout 1: (q | k | v), each heads*ch wide (QKVAttention, unet_generator_attn_vid.py:334-363: the video UNet's
+ * default, use_new_attention_order=True). */
 int jg_attn_fwd(const void* qkv, int ldqkv, void* out, int ldo, float* lse, int N, int T, int heads, int ch,
-                jg_stream_t stream);
+                int layout, jg_stream_t stream);
 /* ws: N*heads*T floats.  dqkv has the layout of qkv. */
 int jg_attn_bwd(const void* qkv, int ldqkv, const void* out, int ldo, const void* d_out, int lddo, const float* lse,
-                void* dqkv, int lddqkv, float* ws, int N, int T, int heads, int ch, jg_stream_t stream);
+                void* dqkv, int lddqkv, float* ws, int N, int T, int heads, int ch, int layout, jg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MotionModule of the video UNet (unet_generator_attn_vid.py:374-590), tokens = NHWC pixels of N = B*F frames
+ * (frame index = n % F).  The Linear layers of the module are 1x1 convolutions (jg_conv2d_*).
+ *   jg_layernorm_*      nn.LayerNorm(C) of TemporalTransformerBlock.norms / ff_norm (:555-563, :574-588), eps 1e-5;
+ *                       pe fp32 [F][C] or NULL = PositionalEncoding.pe[0, :F] (:932-947) added after the affine,
+ *                       i.e. VersatileAttention's pos_encoder on the "(b d) f c" view (:993-999);
+ *                       stats fp32 [rows][2] = (mean, rstd) saved for the backward.
+ *   jg_temporal_attn_*  VersatileAttention over the F <= 8 frames of each pixel (:978-1054, _attention :758-793):
+ *                       qkv [B*F][HW][(q|k|v)] from to_q/to_k/to_v packed as one GEMM, scale dim_head^-1/2,
+ *                       fp32 softmax; out [B*F][HW][heads*ch]; the backward recomputes the F x F probabilities.
+ *   jg_geglu_*          GEGLU (:908-929): x = (a | gate) [rows][2*Cout] -> a * gelu(gate) (erf GELU).
+ * ------------------------------------------------------------------------------------------- */
+int jg_layernorm_fwd(const void* x, int ldx, void* y, int ldy, int64_t rows, int C, float eps, const float* gamma,
+                     const float* beta, const float* pe, int HW, int F, float* stats, jg_stream_t stream);
+/* dgamma / dbeta [C] overwritten. */
+int jg_layernorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int64_t rows, int C,
+                     const float* gamma, const float* stats, float* dgamma, float* dbeta, jg_stream_t stream);
+int jg_temporal_attn_fwd(const void* qkv, int ldqkv, void* out, int ldo, int B, int F, int HW, int heads, int ch,
+                         jg_stream_t stream);
+int jg_temporal_attn_bwd(const void* qkv, int ldqkv, const void* d_out, int lddo, void* dqkv, int lddqkv, int B, int F,
+                         int HW, int heads, int ch, jg_stream_t stream);
+int jg_geglu_fwd(const void* x, int ldx, void* y, int ldy, int64_t rows, int Cout, jg_stream_t stream);
+int jg_geglu_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int64_t rows, int Cout,
+                 jg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Small fp32 Linear on [B, I] embeddings with optional SiLU on the input / output:

@@ -87,14 +87,14 @@ __device__ __forceinline__ float quad_sum(float v) {
 template <int HD>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ldqkv, __nv_bfloat16* __restrict__ out, int ldo,
-                float* __restrict__ lse, int T, int heads, float scale_log2) {
+                float* __restrict__ lse, int T, int heads, float scale_log2, int hstride, int koff, int voff) {
   __shared__ __align__(16) Tile<HD> sQ, sK, sV;
   const int bh = blockIdx.y;
   const int n = bh / heads, h = bh % heads;
   const int q0 = blockIdx.x * kBM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const __nv_bfloat16* base = qkv + (size_t)n * T * ldqkv + h * 3 * HD;
+  const __nv_bfloat16* base = qkv + (size_t)n * T * ldqkv + h * hstride;
 
   sQ.load(base + (size_t)q0 * ldqkv, ldqkv);
   __syncthreads();
@@ -109,8 +109,8 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ldqkv, __nv_bfloat16*
 
   for (int k0 = 0; k0 < T; k0 += kBN) {
     __syncthreads();
-    sK.load(base + HD + (size_t)k0 * ldqkv, ldqkv);
-    sV.load(base + 2 * HD + (size_t)k0 * ldqkv, ldqkv);
+    sK.load(base + koff + (size_t)k0 * ldqkv, ldqkv);
+    sV.load(base + voff + (size_t)k0 * ldqkv, ldqkv);
     __syncthreads();
     float s[8][4];
 #pragma unroll
@@ -214,14 +214,14 @@ template <int HD>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, int ldqkv, const __nv_bfloat16* __restrict__ d_o, int lddo,
                    const float* __restrict__ lse, const float* __restrict__ D, __nv_bfloat16* __restrict__ dqkv,
-                   int lddqkv, int T, int heads, float scale_log2, float scale) {
+                   int lddqkv, int T, int heads, float scale_log2, float scale, int hstride, int koff, int voff) {
   __shared__ __align__(16) Tile<HD> sQ, sK, sV;  // sQ is reused for dO
   const int bh = blockIdx.y;
   const int n = bh / heads, h = bh % heads;
   const int q0 = blockIdx.x * kBM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const __nv_bfloat16* base = qkv + (size_t)n * T * ldqkv + h * 3 * HD;
+  const __nv_bfloat16* base = qkv + (size_t)n * T * ldqkv + h * hstride;
   const __nv_bfloat16* dob = d_o + (size_t)n * T * lddo + h * HD;
 
   uint32_t qa[HD / 16][4], da[HD / 16][4];
@@ -245,8 +245,8 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, int ldqkv, const __nv_
 
   for (int k0 = 0; k0 < T; k0 += kBN) {
     __syncthreads();
-    sK.load(base + HD + (size_t)k0 * ldqkv, ldqkv);
-    sV.load(base + 2 * HD + (size_t)k0 * ldqkv, ldqkv);
+    sK.load(base + koff + (size_t)k0 * ldqkv, ldqkv);
+    sV.load(base + voff + (size_t)k0 * ldqkv, ldqkv);
     __syncthreads();
     float s[8][4], dp[8][4];
 #pragma unroll
@@ -286,7 +286,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, int ldqkv, const __nv_
       }
     }
   }
-  __nv_bfloat16* ob = dqkv + (size_t)n * T * lddqkv + h * 3 * HD;
+  __nv_bfloat16* ob = dqkv + (size_t)n * T * lddqkv + h * hstride;
 #pragma unroll
   for (int i = 0; i < HD / 8; ++i) {
     *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * lddqkv + i * 8 + t4 * 2) =
@@ -303,7 +303,7 @@ template <int HD>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, int ldqkv, const __nv_bfloat16* __restrict__ d_o, int lddo,
                     const float* __restrict__ lse, const float* __restrict__ D, __nv_bfloat16* __restrict__ dqkv,
-                    int lddqkv, int T, int heads, float scale_log2, float scale) {
+                    int lddqkv, int T, int heads, float scale_log2, float scale, int hstride, int koff, int voff) {
   __shared__ __align__(16) Tile<HD> sK, sQ, sDO;  // sK is reused for V while building fragments
   __shared__ float sL[kBN], sD[kBN];
   const int bh = blockIdx.y;
@@ -311,16 +311,16 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, int ldqkv, const __nv
   const int k0 = blockIdx.x * kBM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const __nv_bfloat16* base = qkv + (size_t)n * T * ldqkv + h * 3 * HD;
+  const __nv_bfloat16* base = qkv + (size_t)n * T * ldqkv + h * hstride;
   const __nv_bfloat16* dob = d_o + (size_t)n * T * lddo + h * HD;
 
   uint32_t ka[HD / 16][4], va[HD / 16][4];
-  sK.load(base + HD + (size_t)k0 * ldqkv, ldqkv);
+  sK.load(base + koff + (size_t)k0 * ldqkv, ldqkv);
   __syncthreads();
 #pragma unroll
   for (int kk = 0; kk < HD / 16; ++kk) sK.a_frag(ka[kk], warp * 16, kk * 16);
   __syncthreads();
-  sK.load(base + 2 * HD + (size_t)k0 * ldqkv, ldqkv);
+  sK.load(base + voff + (size_t)k0 * ldqkv, ldqkv);
   __syncthreads();
 #pragma unroll
   for (int kk = 0; kk < HD / 16; ++kk) sK.a_frag(va[kk], warp * 16, kk * 16);
@@ -391,15 +391,15 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, int ldqkv, const __nv
     }
   }
   const int r0 = k0 + warp * 16 + g, r1 = r0 + 8;
-  __nv_bfloat16* ob = dqkv + (size_t)n * T * lddqkv + h * 3 * HD;
+  __nv_bfloat16* ob = dqkv + (size_t)n * T * lddqkv + h * hstride;
 #pragma unroll
   for (int i = 0; i < HD / 8; ++i) {
-    *reinterpret_cast<uint32_t*>(ob + HD + (size_t)r0 * lddqkv + i * 8 + t4 * 2) =
+    *reinterpret_cast<uint32_t*>(ob + koff + (size_t)r0 * lddqkv + i * 8 + t4 * 2) =
         pack_bf16x2(dk[i][0] * scale, dk[i][1] * scale);
-    *reinterpret_cast<uint32_t*>(ob + HD + (size_t)r1 * lddqkv + i * 8 + t4 * 2) =
+    *reinterpret_cast<uint32_t*>(ob + koff + (size_t)r1 * lddqkv + i * 8 + t4 * 2) =
         pack_bf16x2(dk[i][2] * scale, dk[i][3] * scale);
-    *reinterpret_cast<uint32_t*>(ob + 2 * HD + (size_t)r0 * lddqkv + i * 8 + t4 * 2) = pack_bf16x2(dv[i][0], dv[i][1]);
-    *reinterpret_cast<uint32_t*>(ob + 2 * HD + (size_t)r1 * lddqkv + i * 8 + t4 * 2) = pack_bf16x2(dv[i][2], dv[i][3]);
+    *reinterpret_cast<uint32_t*>(ob + voff + (size_t)r0 * lddqkv + i * 8 + t4 * 2) = pack_bf16x2(dv[i][0], dv[i][1]);
+    *reinterpret_cast<uint32_t*>(ob + voff + (size_t)r1 * lddqkv + i * 8 + t4 * 2) = pack_bf16x2(dv[i][2], dv[i][3]);
   }
 }
 
@@ -415,31 +415,41 @@ static int check_attn(int N, int T, int heads, int ch, int ldqkv) {
 
 using namespace jg;
 
+// layout 0: per-head (q|k|v) interleave = QKVAttentionLegacy; layout 1: (q | k | v), each heads*ch wide = QKVAttention
+#define JG_ATTN_LAYOUT(layout, heads, ch)                         \
+  const int hstride = (layout) == 0 ? 3 * (ch) : (ch);            \
+  const int koff = (layout) == 0 ? (ch) : (heads) * (ch);         \
+  const int voff = (layout) == 0 ? 2 * (ch) : 2 * (heads) * (ch);
+
 extern "C" int jg_attn_fwd(const void* qkv, int ldqkv, void* out, int ldo, float* lse, int N, int T, int heads, int ch,
-                           jg_stream_t stream_) {
+                           int layout, jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_attn(N, T, heads, ch, ldqkv);
   if (rc) return rc;
   JG_CHECK(qkv && out && lse && ldo % 8 == 0 && ldo >= heads * ch, JG_ERR_INVALID, "attn_fwd: bad args");
+  JG_CHECK(layout == 0 || layout == 1, JG_ERR_INVALID, "attn_fwd: layout %d", layout);
+  JG_ATTN_LAYOUT(layout, heads, ch)
   const float scale = 1.f / sqrtf((float)ch);  // (ch^-1/4)^2
   const float scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(T / kBM, N * heads);
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
-  if (ch == 16) attn_fwd_kernel<16><<<grid, kAttnThreads, 0, stream>>>(q, ldqkv, o, ldo, lse, T, heads, scale_log2);
-  else if (ch == 32) attn_fwd_kernel<32><<<grid, kAttnThreads, 0, stream>>>(q, ldqkv, o, ldo, lse, T, heads, scale_log2);
-  else attn_fwd_kernel<64><<<grid, kAttnThreads, 0, stream>>>(q, ldqkv, o, ldo, lse, T, heads, scale_log2);
+  if (ch == 16) attn_fwd_kernel<16><<<grid, kAttnThreads, 0, stream>>>(q, ldqkv, o, ldo, lse, T, heads, scale_log2, hstride, koff, voff);
+  else if (ch == 32) attn_fwd_kernel<32><<<grid, kAttnThreads, 0, stream>>>(q, ldqkv, o, ldo, lse, T, heads, scale_log2, hstride, koff, voff);
+  else attn_fwd_kernel<64><<<grid, kAttnThreads, 0, stream>>>(q, ldqkv, o, ldo, lse, T, heads, scale_log2, hstride, koff, voff);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }
 
 extern "C" int jg_attn_bwd(const void* qkv, int ldqkv, const void* out, int ldo, const void* d_out, int lddo,
                            const float* lse, void* dqkv, int lddqkv, float* ws /* N*heads*T floats */, int N, int T,
-                           int heads, int ch, jg_stream_t stream_) {
+                           int heads, int ch, int layout, jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_attn(N, T, heads, ch, ldqkv);
   if (rc) return rc;
   JG_CHECK(qkv && out && d_out && lse && dqkv && ws, JG_ERR_INVALID, "attn_bwd: null pointer");
+  JG_CHECK(layout == 0 || layout == 1, JG_ERR_INVALID, "attn_bwd: layout %d", layout);
+  JG_ATTN_LAYOUT(layout, heads, ch)
   JG_CHECK(ldo % 8 == 0 && lddo % 8 == 0 && lddqkv % 8 == 0 && lddqkv >= 3 * heads * ch, JG_ERR_INVALID,
            "attn_bwd: bad ld");
   const float scale = 1.f / sqrtf((float)ch);
@@ -455,9 +465,9 @@ extern "C" int jg_attn_bwd(const void* qkv, int ldqkv, const void* out, int ldo,
   __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(dqkv);
 #define JG_ATTN_BWD(HD)                                                                                         \
   attn_bwd_dq_kernel<HD><<<grid, kAttnThreads, 0, stream>>>(q, ldqkv, d, lddo, lse, ws, dq, lddqkv, T, heads,    \
-                                                            scale_log2, scale);                                  \
+                                                            scale_log2, scale, hstride, koff, voff);             \
   attn_bwd_dkv_kernel<HD><<<grid, kAttnThreads, 0, stream>>>(q, ldqkv, d, lddo, lse, ws, dq, lddqkv, T, heads,   \
-                                                             scale_log2, scale);
+                                                             scale_log2, scale, hstride, koff, voff);
   if (ch == 16) { JG_ATTN_BWD(16) } else if (ch == 32) { JG_ATTN_BWD(32) } else { JG_ATTN_BWD(64) }
 #undef JG_ATTN_BWD
   JG_LAUNCH_CHECK();

@@ -175,24 +175,83 @@ def groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab, need_param_g
 # ---------------------------------------------------------------------------------------------
 # attention
 # ---------------------------------------------------------------------------------------------
-def attn_fwd(qkv, heads, ch):
-    """qkv NHWC [N,H,W,3*heads*ch] (legacy per-head q|k|v interleave). Returns (out [N,H,W,heads*ch], lse)."""
+def attn_fwd(qkv, heads, ch, layout=0):
+    """qkv NHWC [N,H,W,3*heads*ch]; layout 0 = legacy per-head q|k|v interleave, 1 = (q | k | v) chunks.
+    Returns (out [N,H,W,heads*ch], lse)."""
     n, h, w, _ = qkv.shape
     t = h * w
     out = torch.empty((n, h, w, heads * ch), dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty((n * heads, t), dtype=torch.float32, device=qkv.device)
-    L.call("jg_attn_fwd", L.ptr(qkv), _ld(qkv), L.ptr(out), _ld(out), L.ptr(lse), n, t, heads, ch, L.stream())
+    L.call("jg_attn_fwd", L.ptr(qkv), _ld(qkv), L.ptr(out), _ld(out), L.ptr(lse), n, t, heads, ch, layout, L.stream())
     return out, lse
 
 
-def attn_bwd(qkv, out, d_out, lse, heads, ch):
+def attn_bwd(qkv, out, d_out, lse, heads, ch, layout=0):
     n, h, w, c3 = qkv.shape
     t = h * w
     dqkv = torch.empty((n, h, w, c3), dtype=torch.bfloat16, device=qkv.device)
     ws = torch.empty((n * heads * t,), dtype=torch.float32, device=qkv.device)
     L.call("jg_attn_bwd", L.ptr(qkv), _ld(qkv), L.ptr(out), _ld(out), L.ptr(d_out), _ld(d_out), L.ptr(lse),
-           L.ptr(dqkv), _ld(dqkv), L.ptr(ws), n, t, heads, ch, L.stream())
+           L.ptr(dqkv), _ld(dqkv), L.ptr(ws), n, t, heads, ch, layout, L.stream())
     return dqkv
+
+
+# ---------------------------------------------------------------------------------------------
+# MotionModule kernels (video UNet): LayerNorm(+PE), temporal attention, GEGLU
+# ---------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps=1e-5, pe=None, frames=1):
+    """x NHWC bf16 [N,H,W,C] (N = B*frames).  pe: fp32 [frames, C] added after the affine.  Returns (y, stats)."""
+    n, h, w, c = x.shape
+    rows = n * h * w
+    y = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+    L.call("jg_layernorm_fwd", L.ptr(x), _ld(x), L.ptr(y), _ld(y), rows, c, eps, L.ptr(gamma), L.ptr(beta), L.ptr(pe),
+           h * w, frames, L.ptr(stats), L.stream())
+    return y, stats
+
+
+def layernorm_bwd(x, dy, gamma, stats):
+    n, h, w, c = x.shape
+    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+    dgamma = torch.empty((c,), dtype=torch.float32, device=x.device)
+    dbeta = torch.empty((c,), dtype=torch.float32, device=x.device)
+    L.call("jg_layernorm_bwd", L.ptr(x), _ld(x), L.ptr(dy), _ld(dy), L.ptr(dx), _ld(dx), n * h * w, c, L.ptr(gamma),
+           L.ptr(stats), L.ptr(dgamma), L.ptr(dbeta), L.stream())
+    return dx, dgamma, dbeta
+
+
+def temporal_attn_fwd(qkv, frames, heads):
+    """qkv NHWC [B*frames,H,W,3*C] = (q | k | v).  Returns out [B*frames,H,W,C]."""
+    n, h, w, c3 = qkv.shape
+    c = c3 // 3
+    out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=qkv.device)
+    L.call("jg_temporal_attn_fwd", L.ptr(qkv), _ld(qkv), L.ptr(out), _ld(out), n // frames, frames, h * w, heads,
+           c // heads, L.stream())
+    return out
+
+
+def temporal_attn_bwd(qkv, d_out, frames, heads):
+    n, h, w, c3 = qkv.shape
+    c = c3 // 3
+    dqkv = torch.empty((n, h, w, c3), dtype=torch.bfloat16, device=qkv.device)
+    L.call("jg_temporal_attn_bwd", L.ptr(qkv), _ld(qkv), L.ptr(d_out), _ld(d_out), L.ptr(dqkv), _ld(dqkv),
+           n // frames, frames, h * w, heads, c // heads, L.stream())
+    return dqkv
+
+
+def geglu_fwd(x):
+    """x NHWC [N,H,W,2*Cout] = (a | gate) -> a * gelu(gate)."""
+    n, h, w, c2 = x.shape
+    y = torch.empty((n, h, w, c2 // 2), dtype=torch.bfloat16, device=x.device)
+    L.call("jg_geglu_fwd", L.ptr(x), _ld(x), L.ptr(y), _ld(y), n * h * w, c2 // 2, L.stream())
+    return y
+
+
+def geglu_bwd(x, dy):
+    n, h, w, c2 = x.shape
+    dx = torch.empty((n, h, w, c2), dtype=torch.bfloat16, device=x.device)
+    L.call("jg_geglu_bwd", L.ptr(x), _ld(x), L.ptr(dy), _ld(dy), L.ptr(dx), _ld(dx), n * h * w, c2 // 2, L.stream())
+    return dx
 
 
 # ---------------------------------------------------------------------------------------------

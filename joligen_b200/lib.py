@@ -51,8 +51,14 @@ _SIGNATURES = {
                          c_p, c_p],
     "jg_groupnorm_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p,
                          c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
-    "jg_attn_fwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_p],
-    "jg_attn_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_p],
+    "jg_attn_fwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_attn_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_layernorm_fwd": [c_p, c_int, c_p, c_int, c_i64, c_int, c_f, c_p, c_p, c_p, c_int, c_int, c_p, c_p],
+    "jg_layernorm_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_p, c_p, c_p, c_p, c_p],
+    "jg_temporal_attn_fwd": [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_temporal_attn_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_geglu_fwd": [c_p, c_int, c_p, c_int, c_i64, c_int, c_p],
+    "jg_geglu_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_p],
     "jg_linear_fwd": [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
     "jg_linear_bwd": [c_p, c_p, c_p, c_p, c_int, c_p, c_p, c_int, c_int, c_int, c_int, c_p],
     "jg_noise_pack_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
@@ -122,7 +128,8 @@ KERNELS_PER_CALL = {
     "jg_groupnorm_fwd": 3, "jg_groupnorm_bwd": 4, "jg_attn_fwd": 1, "jg_attn_bwd": 3, "jg_linear_fwd": 1,
     "jg_linear_bwd": 2, "jg_noise_pack_fwd": 1, "jg_palette_loss_fwd": 1, "jg_palette_loss_bwd": 1,
     "jg_adamw_ema_step": 2, "jg_pad2d_fwd": 1, "jg_pad2d_bwd": 1, "jg_dilate2x": 1, "jg_act_bwd": 1,
-    "jg_gan_loss_fwd": 1, "jg_gan_loss_bwd": 1,
+    "jg_gan_loss_fwd": 1, "jg_gan_loss_bwd": 1, "jg_layernorm_fwd": 1, "jg_layernorm_bwd": 1,
+    "jg_temporal_attn_fwd": 1, "jg_temporal_attn_bwd": 1, "jg_geglu_fwd": 1, "jg_geglu_bwd": 1,
 }
 launch_count = [0]
 call_hook = [None]  # optional profiling hook: fn(name, args) -> context manager

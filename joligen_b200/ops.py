@@ -145,17 +145,59 @@ class GroupNormTapFn(torch.autograd.Function):
 
 class AttentionFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, heads, ch):
-        out, lse = K.attn_fwd(qkv, heads, ch)
+    def forward(ctx, qkv, heads, ch, layout):
+        out, lse = K.attn_fwd(qkv, heads, ch, layout)
         ctx.save_for_backward(qkv, out, lse)
-        ctx.cfg = (heads, ch)
+        ctx.cfg = (heads, ch, layout)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         qkv, out, lse = ctx.saved_tensors
-        heads, ch = ctx.cfg
-        return K.attn_bwd(qkv, out, d_out.contiguous(), lse, heads, ch), None, None
+        heads, ch, layout = ctx.cfg
+        return K.attn_bwd(qkv, out, _rows(d_out), lse, heads, ch, layout), None, None, None
+
+
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over channels of NHWC tokens (+ the frame positional encoding of VersatileAttention)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, pe, frames, eps):
+        y, stats = K.layernorm_fwd(x, gamma, beta, eps=eps, pe=pe, frames=frames)
+        ctx.save_for_backward(x, gamma, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, stats = ctx.saved_tensors
+        dx, dgamma, dbeta = K.layernorm_bwd(x, _rows(dy), gamma, stats)
+        return dx, dgamma, dbeta, None, None, None
+
+
+class TemporalAttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, frames, heads):
+        ctx.save_for_backward(qkv)
+        ctx.cfg = (frames, heads)
+        return K.temporal_attn_fwd(qkv, frames, heads)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (qkv,) = ctx.saved_tensors
+        frames, heads = ctx.cfg
+        return K.temporal_attn_bwd(qkv, _rows(d_out), frames, heads), None, None
+
+
+class GegluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return K.geglu_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return K.geglu_bwd(x, _rows(dy))
 
 
 class LinearFn(torch.autograd.Function):
@@ -292,8 +334,21 @@ def group_norm_tap(x, gamma, beta, groups, film=None, act=L.ACT_NONE):
     return GroupNormTapFn.apply(x, gamma, beta, film, groups, act)
 
 
-def attention(qkv, heads, ch):
-    return AttentionFn.apply(qkv, heads, ch)
+def attention(qkv, heads, ch, layout=0):
+    """layout 0: QKVAttentionLegacy channel order, 1: QKVAttention (q | k | v)."""
+    return AttentionFn.apply(qkv, heads, ch, layout)
+
+
+def layer_norm(x, gamma, beta, pe=None, frames=1, eps=1e-5):
+    return LayerNormFn.apply(x, gamma, beta, pe, frames, eps)
+
+
+def temporal_attention(qkv, frames, heads):
+    return TemporalAttentionFn.apply(qkv, frames, heads)
+
+
+def geglu(x):
+    return GegluFn.apply(x)
 
 
 def linear(x, weight, bias, act_in=L.ACT_NONE):

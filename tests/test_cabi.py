@@ -38,7 +38,7 @@ def test_bad_arguments_fail_loudly_without_gpu():
     d.R, d.S, d.stride, d.pad = 3, 3, 1, 1
     rc = l.jg_conv2d_fwd(ctypes.byref(d), 16, 16, 0, 0, 16, 0)
     assert rc == -1 and b"multiples of 8" in l.jg_last_error()
-    rc = l.jg_attn_fwd(16, 96, 16, 32, 16, 1, 100, 2, 16, 0)
+    rc = l.jg_attn_fwd(16, 96, 16, 32, 16, 1, 100, 2, 16, 0, 0)
     assert rc == -1 and b"multiple of 64" in l.jg_last_error()
 
 
