@@ -44,7 +44,7 @@ class ConvPack:
         key = (w._version, _PACK_EPOCH[0], w.data_ptr(), None if b is None else (b._version, b.data_ptr()))
         if key != self.key:
             w4 = w.detach()
-            if w4.dim() == 3:  # Conv1d k=1
+            while w4.dim() < 4:  # Conv1d k=1 / nn.Linear
                 w4 = w4.unsqueeze(-1)
             wf, wd = K.pack_conv_weight(w4, want_dgrad=True)
             bias_p = None
@@ -117,6 +117,8 @@ class EmbedSequential(nn.Sequential, EmbedBlock):
                     h, w = (h * 2, w * 2) if layer.up else (h // 2, w // 2)
             elif isinstance(layer, AttentionBlock):
                 c = layer.channels
+            elif hasattr(layer, "temporal_transformer"):  # MotionModule (video UNet): shape-preserving
+                pass
             else:
                 return None
         return None if c is None else (h, w, (c + 7) // 8 * 8)
@@ -147,6 +149,8 @@ class ConvIn(nn.Conv2d):
 class ResBlock(EmbedBlock):
     """unet_generator_attn.ResBlock (lines 143-266): GN->SiLU->[up/down]->conv3x3, FiLM GN->SiLU->conv3x3,
     skip 1x1 conv, residual add fused into the second conv's epilogue."""
+
+    apply_skipw = True  # the video ResBlock computes skipw but never applies it (..._vid.py:272-275)
 
     def __init__(self, channels, emb_channels, dropout, norm, out_channel=None, use_conv=False,
                  use_scale_shift_norm=False, use_checkpoint=False, up=False, down=False, efficient=False,
@@ -192,12 +196,15 @@ class ResBlock(EmbedBlock):
         h = _conv(h, self.in_layers[2], self._pack_in)
         lin = self.emb_layers[1]
         emb_out = ops.linear(emb, lin.weight, lin.bias, act_in=L.ACT_SILU)  # [N, 2C] = (scale | shift)
+        if emb_out.shape[0] != h.shape[0]:
+            # video UNet: one embedding per clip, N = B*F frames (emb_out.repeat_interleave(f), ..._vid.py:260)
+            emb_out = emb_out.repeat_interleave(h.shape[0] // emb_out.shape[0], dim=0)
         if self.use_scale_shift_norm:
             h = self.out_layers[0].forward_nhwc(h, film=emb_out, act=L.ACT_SILU)
         else:
             # h + emb_out then GN -> SiLU: express the add as FiLM-free shift before the norm
             raise NotImplementedError("B200 ResBlock: use_scale_shift_norm=False is not supported yet")
-        skipw = 1.0 / math.sqrt(2) if self.efficient else 1.0
+        skipw = 1.0 / math.sqrt(2) if (self.efficient and self.apply_skipw) else 1.0
         if self._pack_skip is not None:
             x = _conv(x, self.skip_connection, self._pack_skip)
         return _conv(h, self.out_layers[3], self._pack_out, residual=x, res_scale=skipw, out=out)
@@ -222,8 +229,10 @@ class AttentionBlock(nn.Module):
     def __init__(self, channels, num_heads=1, num_head_channels=-1, use_checkpoint=False,
                  use_new_attention_order=False, use_transformer=False):
         super().__init__()
-        if use_new_attention_order or use_transformer or use_checkpoint:
-            raise NotImplementedError("B200 AttentionBlock: only the legacy attention order is supported")
+        if use_transformer or use_checkpoint:
+            raise NotImplementedError("B200 AttentionBlock: use_transformer / use_checkpoint are not supported")
+        # QKVAttentionLegacy splits heads before q|k|v (layout 0); QKVAttention splits q|k|v first (layout 1)
+        self.attention_layout = 1 if use_new_attention_order else 0
         self.channels = channels
         if num_head_channels == -1:
             self.num_heads = num_heads
@@ -240,7 +249,7 @@ class AttentionBlock(nn.Module):
         c = self.channels
         xn, x = ops.group_norm_tap(x, None, None, c, film=None, act=L.ACT_NONE)  # per-(n, c) statistics over T
         qkv = _conv(xn, self.qkv, self._pack_qkv)
-        a = ops.attention(qkv, self.num_heads, c // self.num_heads)
+        a = ops.attention(qkv, self.num_heads, c // self.num_heads, self.attention_layout)
         return _conv(a, self.proj_out, self._pack_proj, residual=x, res_scale=1.0, out=out)
 
     def forward(self, x):

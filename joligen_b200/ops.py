@@ -57,7 +57,9 @@ class Conv2dFn(torch.autograd.Function):
         cout, cin, r, s, stride, pad, res_scale, has_bias, has_res = ctx.geom
         cout8 = (cout + 7) // 8 * 8
         # a GroupNorm backward that produced this very tensor has already summed it over (n, pixel)
-        colsum = getattr(dy, "_jg_colsum", None) if dy.is_contiguous() else None
+        # (autograd may accumulate a second gradient INTO that tensor in place: the stamp carries its version)
+        stamp = getattr(dy, "_jg_colsum", None) if dy.is_contiguous() else None
+        colsum = stamp[0] if stamp is not None and stamp[1] == dy._version else None
         dy = _rows(dy)
         dx = dw = db = dres = None
         if _needs(ctx, 0):
@@ -91,8 +93,8 @@ class GroupNormFn(torch.autograd.Function):
     """y = act(GN(x; gamma, beta) * (1 + scale) + shift), film = [N, 2C] fp32 (scale | shift) or None."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, film, groups, act):
-        y, stats, ab = K.groupnorm_fwd(x, gamma, beta, groups, film=film, act=act)
+    def forward(ctx, x, gamma, beta, film, groups, act, eps=1e-5):
+        y, stats, ab = K.groupnorm_fwd(x, gamma, beta, groups, film=film, act=act, eps=eps)
         ctx.save_for_backward(x, gamma, beta, film, stats, ab)
         ctx.cfg = (groups, act)
         return y
@@ -108,8 +110,9 @@ class GroupNormFn(torch.autograd.Function):
         dx, dgamma, dbeta, dfilm = K.groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab,
                                                    need_param_grads=need_p, need_film_grad=need_f, colsum=colsum)
         if colsum is not None:
-            dx._jg_colsum = colsum  # picked up by Conv2dFn.backward when x is a conv output (its bias gradient)
-        return dx, dgamma, dbeta, dfilm, None, None
+            # picked up by Conv2dFn.backward when x is a conv output (its bias gradient)
+            dx._jg_colsum = (colsum, dx._version)
+        return dx, dgamma, dbeta, dfilm, None, None, None
 
 
 class GroupNormTapFn(torch.autograd.Function):
@@ -118,8 +121,8 @@ class GroupNormTapFn(torch.autograd.Function):
     sum both gradients inside the GN-backward apply pass (dx = GN'(dy) + d_tap) instead of a separate add kernel."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, film, groups, act):
-        y, stats, ab = K.groupnorm_fwd(x, gamma, beta, groups, film=film, act=act)
+    def forward(ctx, x, gamma, beta, film, groups, act, eps=1e-5):
+        y, stats, ab = K.groupnorm_fwd(x, gamma, beta, groups, film=film, act=act, eps=eps)
         ctx.save_for_backward(x, gamma, beta, film, stats, ab)
         ctx.cfg = (groups, act)
         return y, x.detach()
@@ -129,7 +132,7 @@ class GroupNormTapFn(torch.autograd.Function):
         x, gamma, beta, film, stats, ab = ctx.saved_tensors
         groups, act = ctx.cfg
         if dy is None:
-            return dtap, None, None, None, None, None
+            return dtap, None, None, None, None, None, None
         dy = _rows(dy)
         need_p = gamma is not None and (_needs(ctx, 1) or _needs(ctx, 2))
         need_f = film is not None and _needs(ctx, 3)
@@ -139,8 +142,8 @@ class GroupNormTapFn(torch.autograd.Function):
                                                    addend=None if dtap is None else _rows(dtap),
                                                    colsum=colsum)
         if colsum is not None:
-            dx._jg_colsum = colsum
-        return dx, dgamma, dbeta, dfilm, None, None
+            dx._jg_colsum = (colsum, dx._version)
+        return dx, dgamma, dbeta, dfilm, None, None, None
 
 
 class AttentionFn(torch.autograd.Function):
@@ -325,13 +328,13 @@ def conv2d(x, weight, bias, packed, stride=1, pad=None, residual=None, res_scale
                           None if grad_sink is None else (grad_sink,), out)
 
 
-def group_norm(x, gamma, beta, groups, film=None, act=L.ACT_NONE):
-    return GroupNormFn.apply(x, gamma, beta, film, groups, act)
+def group_norm(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5):
+    return GroupNormFn.apply(x, gamma, beta, film, groups, act, eps)
 
 
-def group_norm_tap(x, gamma, beta, groups, film=None, act=L.ACT_NONE):
+def group_norm_tap(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5):
     """-> (y, x_tap): use x_tap for every other consumer of x (see GroupNormTapFn)."""
-    return GroupNormTapFn.apply(x, gamma, beta, film, groups, act)
+    return GroupNormTapFn.apply(x, gamma, beta, film, groups, act, eps)
 
 
 def attention(qkv, heads, ch, layout=0):
@@ -365,6 +368,29 @@ def avgpool2x(x):
 
 def cat_channels(a, b):
     return CatChannelsFn.apply(a, b)
+
+
+class JoinSlicesFn(torch.autograd.Function):
+    """parts[i] already ARE consecutive channel slices of buf (written there through conv2d(out=...)): returns buf as
+    a function of the parts; the backward hands out the matching channel-slice views."""
+
+    @staticmethod
+    def forward(ctx, buf, *parts):
+        ctx.widths = [p.shape[-1] for p in parts]
+        assert sum(ctx.widths) == buf.shape[-1] and parts[0].data_ptr() == buf.data_ptr()
+        return buf.view(buf.shape)
+
+    @staticmethod
+    def backward(ctx, d):
+        outs, c0 = [None], 0
+        for w in ctx.widths:
+            outs.append(d[..., c0:c0 + w])
+            c0 += w
+        return tuple(outs)
+
+
+def join_slices(buf, *parts):
+    return JoinSlicesFn.apply(buf, *parts)
 
 
 def cat_into(buf, a, b):
