@@ -175,12 +175,13 @@ def groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab, need_param_g
 # ---------------------------------------------------------------------------------------------
 # attention
 # ---------------------------------------------------------------------------------------------
-def attn_fwd(qkv, heads, ch, layout=0):
+def attn_fwd(qkv, heads, ch, layout=0, out=None):
     """qkv NHWC [N,H,W,3*heads*ch]; layout 0 = legacy per-head q|k|v interleave, 1 = (q | k | v) chunks.
-    Returns (out [N,H,W,heads*ch], lse)."""
+    Returns (out [N,H,W,heads*ch], lse); `out` may be a channel slice of a wider buffer."""
     n, h, w, _ = qkv.shape
     t = h * w
-    out = torch.empty((n, h, w, heads * ch), dtype=torch.bfloat16, device=qkv.device)
+    if out is None:
+        out = torch.empty((n, h, w, heads * ch), dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty((n * heads, t), dtype=torch.float32, device=qkv.device)
     L.call("jg_attn_fwd", L.ptr(qkv), _ld(qkv), L.ptr(out), _ld(out), L.ptr(lse), n, t, heads, ch, layout, L.stream())
     return out, lse

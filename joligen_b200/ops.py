@@ -148,17 +148,44 @@ class GroupNormTapFn(torch.autograd.Function):
 
 class AttentionFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, heads, ch, layout):
-        out, lse = K.attn_fwd(qkv, heads, ch, layout)
-        ctx.save_for_backward(qkv, out, lse)
+    def forward(ctx, qkv, heads, ch, layout, out):
+        o, lse = K.attn_fwd(qkv, heads, ch, layout, out=out)
+        if out is not None:
+            o = o.view(o.shape)  # a fresh tensor object (see Conv2dFn.forward)
+        ctx.save_for_backward(qkv, o, lse)
         ctx.cfg = (heads, ch, layout)
-        return out
+        return o
 
     @staticmethod
     def backward(ctx, d_out):
         qkv, out, lse = ctx.saved_tensors
         heads, ch, layout = ctx.cfg
-        return K.attn_bwd(qkv, out, _rows(d_out), lse, heads, ch, layout), None, None, None
+        return K.attn_bwd(qkv, out, _rows(d_out), lse, heads, ch, layout), None, None, None, None
+
+
+class MixQkvFn(torch.autograd.Function):
+    """AttentionBlockRef._forward (unet_generator_attn.py:1111-1118): chunk(3) of the block's own qkv and of the
+    reference UNet's qkv along channels, then cat([q, k_ref, v_ref]): the first third of the channels comes from
+    `qkv`, the rest from `qkv_ref` (whatever the attention order does with those channels afterwards)."""
+
+    @staticmethod
+    def forward(ctx, qkv, qkv_ref):
+        c = qkv.shape[-1] // 3
+        out = torch.empty_like(qkv_ref, memory_format=torch.contiguous_format)
+        K.copy_channels(qkv[..., :c], out[..., :c])
+        K.copy_channels(qkv_ref[..., c:], out[..., c:])
+        ctx.c = c
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        c = ctx.c
+        d = _rows(d)
+        dq = torch.zeros(d.shape, dtype=d.dtype, device=d.device)
+        dr = torch.zeros(d.shape, dtype=d.dtype, device=d.device)
+        K.copy_channels(d[..., :c], dq[..., :c])
+        K.copy_channels(d[..., c:], dr[..., c:])
+        return dq, dr
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -337,9 +364,13 @@ def group_norm_tap(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5):
     return GroupNormTapFn.apply(x, gamma, beta, film, groups, act, eps)
 
 
-def attention(qkv, heads, ch, layout=0):
-    """layout 0: QKVAttentionLegacy channel order, 1: QKVAttention (q | k | v)."""
-    return AttentionFn.apply(qkv, heads, ch, layout)
+def attention(qkv, heads, ch, layout=0, out=None):
+    """layout 0: QKVAttentionLegacy channel order, 1: QKVAttention (q | k | v); out = optional destination slice."""
+    return AttentionFn.apply(qkv, heads, ch, layout, out)
+
+
+def mix_qkv(qkv, qkv_ref):
+    return MixQkvFn.apply(qkv, qkv_ref)
 
 
 def layer_norm(x, gamma, beta, pe=None, frames=1, eps=1e-5):

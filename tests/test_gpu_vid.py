@@ -162,3 +162,43 @@ def test_unetvid_forward_backward_vs_reference_golden(golden_dir):
         worst = max(worst, err)
         assert err < max(8e-2, 3 * emu), (k, err, emu)
     assert worst < 0.2
+
+
+def test_refattn_unet_forward_backward_vs_reference_golden(golden_dir):
+    """Row a-16: UNetGeneratorRefAttn (two UNets, attention on own and reference keys/values) end to end against the
+    unmodified reference's fp32 vectors and the oracle in bf16-storage emulation."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import palette_oracle as O
+    from oracle import ref_oracle as R
+    from oracle.gen_golden_ref import inputs
+    from oracle.vid_oracle import init_params_from_shapes
+    from test_ref_oracle import build_b200  # tests/ is on sys.path (pytest prepend import mode)
+    gold = torch.load(os.path.join(golden_dir, "refattn_small.pt"))
+    cfg = O.UNetCfg(**gold["cfg"])
+    params = init_params_from_shapes(gold["shapes"], gold["wseed"])
+    x, ref, emb, gy = inputs(cfg, gold["batch"], gold["dseed"])
+    net = build_b200(cfg)
+    missing, unexpected = net.load_state_dict(params, strict=False)
+    assert not missing and not unexpected
+    net = net.cuda()
+    y = net(x.cuda(), emb.cuda(), ref.cuda())
+    (y * gy.cuda()).sum().backward()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    O.EMULATE_BF16[0] = True
+    try:
+        yo = R.unet_ref_forward(leaves, x, emb, ref, cfg)
+        (yo * gy).sum().backward()
+    finally:
+        O.EMULATE_BF16[0] = False
+    emul_floor = rel(yo, gold["y"])
+    assert rel(y, gold["y"]) < max(3e-2, 2 * emul_floor), (rel(y, gold["y"]), emul_floor)
+    assert rel(y, yo) < max(3e-2, 2 * emul_floor), (rel(y, yo), emul_floor)
+    named = dict(net.named_parameters())
+    scale = max(g["l2"] for g in gold["grads"].values())
+    for k, g in gold["grads"].items():
+        mine = named[k].grad.detach().cpu().double()
+        refg = leaves[k].grad.double()
+        err = float((mine - refg).norm()) / max(float(refg.norm()), 2e-2 * scale)
+        emu = abs(float(refg.norm()) - g["l2"]) / max(g["l2"], 2e-2 * scale)
+        assert err < max(8e-2, 3 * emu), (k, err, emu)
