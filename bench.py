@@ -179,6 +179,21 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def conv_traffic(n_launches):
+    """DRAM bytes (read + write) per implicit-GEMM launch, averaged over the launches of one step, from the committed
+    ncu pass over one training step (tools/gpu_step_once.py + tools/ncu_traffic.py); None if the capture is missing or
+    was taken on a different number of launches."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+    except (OSError, ValueError):
+        return None
+    if abs(d.get("launches", 0) - n_launches) > 0.1 * n_launches:
+        return None
+    return d["dram_bytes_per_launch"]
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -319,7 +334,7 @@ def main():
             "clocks": clocks,
             "step_tflops_algorithmic": alg_flops_step / (ms / 1000.0) / 1e12,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": conv_traffic(len(recs)),
                          "kernel": "conv_fwd_kernel + conv_wgrad_kernel (all %d implicit-GEMM launches of one step)"
                                    % len(recs),
                          "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms,

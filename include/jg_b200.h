@@ -40,6 +40,9 @@ const char* jg_last_error(void);
 int jg_version(void);
 /* 0 if the current device can run the library (compute capability 10.x), JG_ERR_UNSUPPORTED otherwise */
 int jg_check_device(void);
+/* Number of CUDA kernels this library has launched so far in the process (every launch site counts itself);
+ * bench.py's `gpu_launches` is the difference over one step. */
+unsigned long long jg_kernel_launches(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Convolution as implicit GEMM on tcgen05 tensor cores (TMA-staged NHWC tiles, fp32 accumulation

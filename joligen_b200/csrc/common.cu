@@ -1,6 +1,8 @@
 // Error reporting, device query and TMA tensor-map construction for libjg_b200.so.
 #include "common.cuh"
 
+#include <atomic>
+
 #include <mutex>
 #include <string.h>
 
@@ -62,6 +64,9 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return JG_OK;
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -91,3 +96,5 @@ extern "C" int jg_check_device(void) {
   }
   return JG_OK;
 }
+
+extern "C" unsigned long long jg_kernel_launches(void) { return jg::g_launches.load(std::memory_order_relaxed); }

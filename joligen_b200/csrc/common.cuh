@@ -32,8 +32,10 @@ const char* get_error();
     }                                                                                          \
   } while (0)
 
+// Every kernel launch of the library is followed by this check; it also counts the launch (jg_kernel_launches()).
 #define JG_LAUNCH_CHECK()                                                                        \
   do {                                                                                           \
+    ::jg::count_launch();                                                                        \
     cudaError_t e__ = cudaGetLastError();                                                        \
     if (e__ != cudaSuccess) {                                                                    \
       ::jg::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
@@ -47,6 +49,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
 
 int num_sms();
+void count_launch();
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -73,6 +73,7 @@ _SIGNATURES = {
     "jg_gan_loss_fwd": [c_p, c_int, c_i64, c_int, c_int, c_f, c_f, c_p, c_p],
     "jg_gan_loss_bwd": [c_p, c_int, c_i64, c_int, c_int, c_f, c_f, c_p, c_p, c_int, c_p],
 }
+_U64_FUNCS = {"jg_kernel_launches": []}
 _SIZE_T_FUNCS = {
     "jg_groupnorm_fwd_ws_floats": [c_int, c_int, c_int],
     "jg_groupnorm_bwd_ws_floats": [c_int, c_int, c_int],
@@ -81,7 +82,7 @@ _SIZE_T_FUNCS = {
 
 def exported_symbols():
     """Every symbol include/jg_b200.h declares (used by the CPU test that checks the .so exports)."""
-    return sorted(list(_SIGNATURES.keys()) + list(_SIZE_T_FUNCS.keys()) + ["jg_last_error"])
+    return sorted(list(_SIGNATURES.keys()) + list(_SIZE_T_FUNCS.keys()) + list(_U64_FUNCS.keys()) + ["jg_last_error"])
 
 
 def load():
@@ -103,6 +104,10 @@ def load():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_size_t
         fn.argtypes = argtypes
+    for name, argtypes in _U64_FUNCS.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_ulonglong
+        fn.argtypes = argtypes
     _lib = lib
     return lib
 
@@ -121,26 +126,18 @@ def ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-# kernels launched per C-ABI call (memsets excluded) — bench.py's `gpu_launches` claim is counted from these
-KERNELS_PER_CALL = {
-    "jg_conv2d_fwd": 1, "jg_conv2d_wgrad": 2, "jg_pack_conv_weight": 1, "jg_unpack_conv_wgrad": 1, "jg_bias_grad": 1,
-    "jg_nchw_f32_to_nhwc_bf16": 1, "jg_nhwc_bf16_to_nchw_f32": 1, "jg_copy_channels": 1, "jg_resample2x": 1,
-    "jg_groupnorm_fwd": 3, "jg_groupnorm_bwd": 4, "jg_attn_fwd": 1, "jg_attn_bwd": 3, "jg_linear_fwd": 1,
-    "jg_linear_bwd": 2, "jg_noise_pack_fwd": 1, "jg_palette_loss_fwd": 1, "jg_palette_loss_bwd": 1,
-    "jg_adamw_ema_step": 2, "jg_pad2d_fwd": 1, "jg_pad2d_bwd": 1, "jg_dilate2x": 1, "jg_act_bwd": 1,
-    "jg_gan_loss_fwd": 1, "jg_gan_loss_bwd": 1, "jg_layernorm_fwd": 1, "jg_layernorm_bwd": 1,
-    "jg_temporal_attn_fwd": 1, "jg_temporal_attn_bwd": 1, "jg_geglu_fwd": 1, "jg_geglu_bwd": 1,
-}
+# kernels launched through the library since import (exact: see jg_kernel_launches in include/jg_b200.h)
 launch_count = [0]
 call_hook = [None]  # optional profiling hook: fn(name, args) -> context manager
 
 
 def call(name, *args):
     lib = load()
-    launch_count[0] += KERNELS_PER_CALL.get(name, 1)
+    before = lib.jg_kernel_launches()
     hook = call_hook[0]
     if hook is None:
         _check(getattr(lib, name)(*args), name)
     else:
         with hook(name, args):
             _check(getattr(lib, name)(*args), name)
+    launch_count[0] += lib.jg_kernel_launches() - before  # exact: every launch site of the library counts itself
