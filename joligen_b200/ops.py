@@ -258,7 +258,7 @@ class Resample2xFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        return K.resample2x(dy.contiguous(), 2 if ctx.mode == 0 else 3), None
+        return K.resample2x(_rows(dy), 2 if ctx.mode == 0 else 3), None
 
 
 class CatChannelsFn(torch.autograd.Function):
