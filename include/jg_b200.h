@@ -192,6 +192,16 @@ int jg_noise_pack_fwd(const float* y0, const float* ycond, const float* noise, c
                       const int64_t* mask_i64, const float* gammas, void* out, int B, int C, int H, int W, int ld,
                       jg_stream_t stream);
 
+/* One reverse-diffusion step of the DDPM sampler: DiffusionGenerator.p_sample
+ * (diffusion_generator.py:248-283) = predict_start_from_noise + clamp + q_posterior (diffusion_utils.py:122-137)
+ * + noise, the mask blend of restoration_ddpm (:168-170), and the next step's cat([y_cond, y_t]) NHWC bf16 pack.
+ * eps: UNet output NHWC bf16 (stride lde); y_t, y_cond, y_0, noise, y_next: fp32 NCHW [B,C,H,W]; noise NULL at t = 0;
+ * coef fp32 [B][5] = (sqrt_recip_gammas, sqrt_recipm1_gammas, posterior_mean_coef1, posterior_mean_coef2,
+ * exp(0.5 * posterior_log_variance_clipped)) gathered at t; x_next (may be NULL) NHWC bf16 [B,H,W,ld]. */
+int jg_ddpm_step(const void* eps, int lde, const float* y_t, const float* y_cond, const float* y_0,
+                 const float* mask_f32, const int64_t* mask_i64, const float* noise, const float* coef, float* y_next,
+                 void* x_next, int B, int C, int H, int W, int ld, jg_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * PaletteModel.compute_palette_loss (palette_model.py:596-620):
  *   loss = lambda_G * mean_{b,c,h,w} (w_b * clamp(mask,0,1) * (noise - noise_hat))^2   (l1: |.|)

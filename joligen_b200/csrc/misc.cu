@@ -109,6 +109,54 @@ __global__ void noise_pack_kernel(const float* __restrict__ y0, const float* __r
   for (int c = 2 * C; c < ld; ++c) o[c] = __float2bfloat16(0.f);
 }
 
+// One reverse-diffusion step (DiffusionGenerator.p_sample + the mask blend of restoration_ddpm,
+// diffusion_generator.py:122-177, 192-283; predict_start_from_noise / q_posterior, diffusion_utils.py:122-137):
+//   y0_hat = clamp(c1*y_t - c2*eps, -1, 1);  mean = pm1*y0_hat + pm2*y_t;  y = mean + sigma*noise
+//   y = y_0*(1-m) + m*y  (m = clamp(mask, 0, 1))
+// and, in the same pass, the NEXT step's UNet input cat([y_cond, y]) as NHWC bf16 (x_next, zero-padded to ld).
+// eps: the UNet output, NHWC bf16 with channel stride lde; y_t / y_cond / y_0 / noise / y_next fp32 NCHW;
+// coef fp32 [B][5] = (c1, c2, pm1, pm2, sigma) gathered at t; noise NULL = 0 (the t == 0 step).
+__global__ void ddpm_step_kernel(const __nv_bfloat16* __restrict__ eps, int lde, const float* __restrict__ yt,
+                                 const float* __restrict__ ycond, const float* __restrict__ y0,
+                                 const float* __restrict__ maskf, const long long* __restrict__ maski,
+                                 const float* __restrict__ noise, const float* __restrict__ coef,
+                                 float* __restrict__ ynext, __nv_bfloat16* __restrict__ xnext, int B, int C, int HW,
+                                 int ld) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * HW) return;
+  const int b = (int)(idx / HW);
+  const int p = (int)(idx % HW);
+  const float c1 = coef[b * 5 + 0], c2 = coef[b * 5 + 1], pm1 = coef[b * 5 + 2], pm2 = coef[b * 5 + 3];
+  const float sigma = coef[b * 5 + 4];
+  float m = 1.f;
+  bool has_mask = false;
+  if (maskf) {
+    m = fminf(fmaxf(maskf[idx], 0.f), 1.f);
+    has_mask = true;
+  } else if (maski) {
+    const long long mv = maski[idx];
+    m = mv < 0 ? 0.f : (mv > 1 ? 1.f : (float)mv);
+    has_mask = true;
+  }
+  __nv_bfloat16* o = xnext ? xnext + idx * ld : nullptr;
+  for (int c = 0; c < C; ++c) {
+    const size_t src = ((size_t)b * C + c) * HW + p;
+    const float y = yt[src];
+    const float e = __bfloat162float(eps[idx * lde + c]);
+    const float y0h = fminf(fmaxf(c1 * y - c2 * e, -1.f), 1.f);
+    float out = pm1 * y0h + pm2 * y;
+    if (noise) out += sigma * noise[src];
+    if (has_mask) out = y0[src] * (1.f - m) + m * out;
+    ynext[src] = out;
+    if (o) {
+      o[c] = __float2bfloat16(ycond[src]);
+      o[C + c] = __float2bfloat16(out);
+    }
+  }
+  if (o)
+    for (int c = 2 * C; c < ld; ++c) o[c] = __float2bfloat16(0.f);
+}
+
 // Palette loss (palette_model.py:596-620): loss = lambda * mean_{b,c,p} (w_b*m*(noise - noise_hat))^2  (MSE)
 //                                      or   lambda * mean |w_b*m*(noise - noise_hat)|              (L1)
 // noise fp32 NCHW, noise_hat NHWC bf16 (channel stride ld).  One pass: block partial sums -> atomicAdd(loss).
@@ -291,6 +339,23 @@ extern "C" int jg_adamw_ema_step(float* p, const float* g, float* m, float* v, f
   if (blocks > cap) blocks = cap;
   adamw_ema_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay,
                                                          adamw, step, step_dev, grad_scale, ema_beta, ema_init);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
+extern "C" int jg_ddpm_step(const void* eps, int lde, const float* y_t, const float* y_cond, const float* y_0,
+                            const float* mask_f32, const int64_t* mask_i64, const float* noise, const float* coef,
+                            float* y_next, void* x_next, int B, int C, int H, int W, int ld, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  JG_CHECK(eps && y_t && y_cond && coef && y_next && B > 0 && C > 0 && lde >= C, JG_ERR_INVALID,
+           "ddpm_step: null pointer / bad dims");
+  JG_CHECK(!(mask_f32 || mask_i64) || y_0, JG_ERR_INVALID, "ddpm_step: a mask needs y_0");
+  JG_CHECK(x_next == nullptr || (ld >= 2 * C && ld % 8 == 0), JG_ERR_INVALID, "ddpm_step: bad ld %d", ld);
+  const long long total = (long long)B * H * W;
+  ddpm_step_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(eps), lde, y_t, y_cond, y_0, mask_f32,
+      reinterpret_cast<const long long*>(mask_i64), noise, coef, y_next, static_cast<__nv_bfloat16*>(x_next), B, C,
+      H * W, ld);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }

@@ -474,6 +474,48 @@ class DiffusionGenerator(nn.Module):
         noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u)
         return noise, ops.to_nchw(noise_hat, y_0.shape[1]), w.view(-1, 1, 1, 1)
 
+    @torch.no_grad()
+    def restoration_ddpm(self, y_cond, y_t=None, y_0=None, mask=None, sample_num=2, cls=None, guidance_scale=0.0,
+                         ref=None, noise_fn=None):
+        """diffusion_generator.restoration_ddpm (:122-177) for conditioning "" (no class / ref, no guidance):
+        num_timesteps_test UNet forwards; per step ONE fused kernel does predict_start_from_noise, the clamp, the
+        posterior mean, the noise injection, the mask blend and the next step's NHWC bf16 input pack.
+        noise_fn(i, shape) -> fp32 NCHW noise for step i (default torch.randn on the device; the tests replay the
+        reference's CPU draws).  Returns (y_t, ret_arr) like the reference."""
+        if cls is not None or ref is not None or guidance_scale:
+            raise NotImplementedError("B200 restoration_ddpm: class / reference conditioning and guidance")
+        model = self.denoise_fn.model
+        T = model.num_timesteps_test
+        assert T > sample_num, "num_timesteps must greater than sample_num"
+        sample_inter = T // sample_num
+        b, c = y_cond.shape[0], model.out_channel
+        dev = y_cond.device
+        y_cond = y_cond.contiguous().float()
+        if noise_fn is None:
+            noise_fn = lambda i, shape: torch.randn(shape, device=dev)  # noqa: E731
+        if y_t is None:
+            y_t = noise_fn(T, (b, c) + tuple(y_cond.shape[2:]))
+        y_t = y_t.contiguous().float()
+        if mask is not None:
+            y_0 = y_0.contiguous().float()
+            mask = mask.contiguous()
+        ld = (y_cond.shape[1] + c + 7) // 8 * 8
+        sigma = torch.exp(0.5 * model.posterior_log_variance_clipped_test)
+        table = torch.stack([model.sqrt_recip_gammas_test, model.sqrt_recipm1_gammas_test,
+                             model.posterior_mean_coef1_test, model.posterior_mean_coef2_test, sigma], dim=1)
+        # first input: cat([y_cond, y_t]) (every later one comes out of the step kernel)
+        x = ops.to_nhwc(torch.cat([y_cond, y_t], dim=1))
+        ret_arr = y_t
+        for i in reversed(range(T)):
+            gam = model.gammas_test[i].reshape(1, 1).expand(b, 1)
+            eps = model.forward_nhwc(x, self.compute_gammas(gam))
+            noise = noise_fn(i, tuple(y_t.shape)).contiguous().float() if i > 0 else None
+            coef = table[i].reshape(1, 5).expand(b, 5).contiguous()
+            y_t, x = K.ddpm_step(eps, y_t, y_cond, y_0, mask, noise, coef, ld=ld, want_next_input=i > 0)
+            if i % sample_inter == 0:
+                ret_arr = torch.cat([ret_arr, y_t], dim=0)
+        return y_t, ret_arr
+
     def forward_loss(self, y_0, y_cond, mask, noise=None, lambda_G=1.0, use_minsnr=False, l1=False, t=None, u=None):
         """compute_palette_loss fused: the UNet output stays NHWC bf16 and feeds the eps-loss kernel directly."""
         noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u)

@@ -157,6 +157,30 @@ def plumbing_golden(name):
     print(name, "losses", losses)
 
 
+def sampling_golden(name, cfgd, batch, wseed, dseed, rseed, sample_num):
+    """DiffusionGenerator.restoration (DDPM, n_timestep_test steps) of the unmodified reference on CPU; the random
+    draws (initial y_t, one randn_like per step with t > 0) are recorded by replaying the seed."""
+    cfg = O.UNetCfg(**cfgd)
+    net = build_reference_generator(cfg)
+    params = O.init_params(cfg, wseed)
+    net.load_state_dict(params, strict=False)
+    data = O.synthetic_batch(batch, cfg.image_size, dseed)
+    torch.manual_seed(rseed)
+    with torch.no_grad():
+        y, ret = net.restoration(data["cond"], y_t=None, y_0=data["gt"], mask=data["mask"], sample_num=sample_num)
+    # the same draws, in the reference's order
+    torch.manual_seed(rseed)
+    y_t0 = torch.randn_like(data["gt"])
+    noises = {i: torch.randn_like(data["gt"]) for i in reversed(range(1, cfg.n_timestep_test))}
+    with torch.no_grad():
+        yo, reto = O.restoration_ddpm(params, data["cond"], y_t0, data["gt"], data["mask"], noises, cfg, sample_num)
+    print(name, "oracle vs reference: y rel max err %.2e, ret_arr %.2e" % (
+        float((yo - y).abs().max() / y.abs().max()), float((reto - ret).abs().max() / ret.abs().max())))
+    torch.save({"cfg": cfgd, "batch": batch, "wseed": wseed, "dseed": dseed, "rseed": rseed, "sample_num": sample_num,
+                "torch_version": str(torch.__version__), "y": y.clone(), "ret_arr": ret.clone()},
+               os.path.join(GOLDEN, name))
+
+
 def main():
     ref_stubs.install()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -164,6 +188,8 @@ def main():
     module_golden("palette_small.pt", SMALL, batch=2, wseed=7, dseed=11, rseed=123, full_grads=True)
     module_golden("palette_mid.pt", MID, batch=2, wseed=8, dseed=12, rseed=124, full_grads=False)
     plumbing_golden("palette_plumbing.pt")
+    sampling_golden("palette_sampling.pt", dict(SMALL, n_timestep_test=12), batch=2, wseed=7, dseed=11, rseed=321,
+                    sample_num=3)
 
 
 if __name__ == "__main__":

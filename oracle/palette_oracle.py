@@ -196,11 +196,16 @@ def schedule_buffers(cfg: UNetCfg, phase="train") -> Dict[str, torch.Tensor]:
     betas = np.linspace(lo, hi, n, dtype=np.float64)
     alphas = 1.0 - betas
     gammas = np.cumprod(alphas, axis=0)
+    gammas_prev = np.append(1.0, gammas[:-1])
+    posterior_variance = betas * (1.0 - gammas_prev) / (1.0 - gammas)
     f32 = lambda a: torch.tensor(a, dtype=torch.float32)
-    return {
+    return {  # diffusion_utils.set_new_noise_schedule, :79-119
         "gammas_" + phase: f32(gammas),
         "sqrt_recip_gammas_" + phase: f32(np.sqrt(1.0 / gammas)),
         "sqrt_recipm1_gammas_" + phase: f32(np.sqrt(1.0 / gammas - 1)),
+        "posterior_log_variance_clipped_" + phase: f32(np.log(np.maximum(posterior_variance, 1e-20))),
+        "posterior_mean_coef1_" + phase: f32(betas * np.sqrt(gammas_prev) / (1.0 - gammas)),
+        "posterior_mean_coef2_" + phase: f32((1.0 - gammas_prev) * np.sqrt(alphas) / (1.0 - gammas)),
     }
 
 
@@ -374,6 +379,39 @@ def diffusion_forward(sd, y_0, y_cond, mask, noise, t, u, cfg: UNetCfg):
     snr = torch.pow(snr1 / snr2, 2)
     w = torch.stack([snr, ksnr * torch.ones_like(t)], dim=1).min(dim=1)[0] / snr
     return noise, noise_hat, w.view(-1, 1, 1, 1)
+
+
+def restoration_ddpm(sd, y_cond, y_t, y_0, mask, noises, cfg: UNetCfg, sample_num=2):
+    """DiffusionGenerator.restoration_ddpm (diffusion_generator.py:122-177) with p_sample / p_mean_variance
+    (:192-283), predict_start_from_noise and q_posterior (diffusion_utils.py:122-137), conditioning "" and no
+    guidance.  `noises[i]` is the randn_like draw of step i (i > 0), in the reference's order.
+    Returns (y_t, ret_arr)."""
+    sched = schedule_buffers(cfg, "test")
+    T = int(sched["gammas_test"].shape[0])
+    sample_inter = T // sample_num
+    b = y_cond.shape[0]
+    ret_arr = y_t
+    for i in reversed(range(T)):
+        t = torch.full((b,), i, dtype=torch.long)
+        noise_level = sched["gammas_test"].gather(-1, t).reshape(b, 1)
+        emb = gamma_embedding(noise_level, cfg.cond_embed_dim)
+        emb = F.linear(emb, sd["cond_embed.0.weight"], sd["cond_embed.0.bias"])
+        emb = F.linear(F.silu(emb), sd["cond_embed.2.weight"], sd["cond_embed.2.bias"])
+        eps = unet_forward(sd, torch.cat([y_cond, y_t], dim=1), emb, cfg)
+
+        def ex(name):
+            return sched[name + "_test"].gather(-1, t).reshape(b, 1, 1, 1)
+
+        y0_hat = (ex("sqrt_recip_gammas") * y_t - ex("sqrt_recipm1_gammas") * eps).clamp(-1.0, 1.0)
+        mean = ex("posterior_mean_coef1") * y0_hat + ex("posterior_mean_coef2") * y_t
+        noise = noises[i] if i > 0 else torch.zeros_like(y_t)
+        y_t = mean + noise * (0.5 * ex("posterior_log_variance_clipped")).exp()
+        if mask is not None:
+            m = torch.clamp(mask, min=0.0, max=1.0)
+            y_t = y_0 * (1.0 - m) + m * y_t
+        if i % sample_inter == 0:
+            ret_arr = torch.cat([ret_arr, y_t], dim=0)
+    return y_t, ret_arr
 
 
 def palette_loss(noise, noise_hat, mask, min_snr_w=None, lambda_G=1.0, use_minsnr=False, kind="MSE"):

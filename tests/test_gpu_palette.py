@@ -239,3 +239,38 @@ def test_state_dict_roundtrip_and_modulewise_dropin(env):
     ref = O.attention_block(params, name, x2, mid[1])
     got = net.denoise_fn.model.middle_block[1](x2.cuda())
     assert rel_l2(got, ref) < 1e-2
+
+
+def test_ddpm_sampler_vs_reference_golden(env, golden_dir):
+    """restoration_ddpm (12 reverse steps, mask blend, fused step kernel) against the
+    unmodified reference's sampler with the same random draws.  Unmasked pixels are copied from y_0 (exact); inside
+    the mask the bf16 UNet error is fed back 12 times: held against the bf16-emulating oracle's own distance to fp32."""
+    nets, O = env
+    gold = torch.load(os.path.join(golden_dir, "palette_sampling.pt"))
+    cfg = O.UNetCfg(**gold["cfg"])
+    params = O.init_params(cfg, gold["wseed"])
+    data = O.synthetic_batch(gold["batch"], cfg.image_size, gold["dseed"])
+    torch.manual_seed(gold["rseed"])
+    y_t0 = torch.randn_like(data["gt"])
+    noises = {i: torch.randn_like(data["gt"]) for i in reversed(range(1, cfg.n_timestep_test))}
+    g = nets.build_palette_generator(image_size=cfg.image_size, inner_channel=cfg.inner_channel,
+                                     res_blocks=cfg.res_blocks, attn_res=cfg.attn_res,
+                                     channel_mults=cfg.channel_mults, num_head_channels=cfg.num_head_channels,
+                                     n_timestep_test=cfg.n_timestep_test)
+    g.load_state_dict(params, strict=False)
+    g = g.cuda()
+    y, ret = g.restoration_ddpm(data["cond"].cuda(), y_t=y_t0.cuda(), y_0=data["gt"].cuda(), mask=data["mask"].cuda(),
+                                sample_num=gold["sample_num"], noise_fn=lambda i, shape: noises[i].cuda())
+    assert ret.shape == gold["ret_arr"].shape
+    m = data["mask"].clamp(0, 1).bool().expand_as(data["gt"])
+    assert torch.equal(y.cpu()[~m], data["gt"][~m])  # outside the mask: y_0 exactly
+    O.EMULATE_BF16[0] = True
+    try:
+        with torch.no_grad():
+            yo, reto = O.restoration_ddpm(params, data["cond"], y_t0, data["gt"], data["mask"], noises, cfg,
+                                          gold["sample_num"])
+    finally:
+        O.EMULATE_BF16[0] = False
+    floor = rel_l2(yo, gold["y"])
+    assert rel_l2(y, gold["y"]) < max(3e-2, 2.5 * floor), (rel_l2(y, gold["y"]), floor)
+    assert rel_l2(ret, gold["ret_arr"]) < max(3e-2, 2.5 * rel_l2(reto, gold["ret_arr"]))

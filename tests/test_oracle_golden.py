@@ -102,3 +102,24 @@ def test_gan_oracle_matches_reference(golden_dir):
     G.gan_loss(pred, True).backward()
     for k, gref in gold["grads"].items():
         assert _rel(leaves[k].grad, gref) < 2e-4, k
+
+
+def _sampling_draws(gold, cfg):
+    data = O.synthetic_batch(gold["batch"], cfg.image_size, gold["dseed"])
+    torch.manual_seed(gold["rseed"])
+    y_t0 = torch.randn_like(data["gt"])
+    noises = {i: torch.randn_like(data["gt"]) for i in reversed(range(1, cfg.n_timestep_test))}
+    return data, y_t0, noises
+
+
+def test_oracle_ddpm_sampler_matches_reference(golden_dir):
+    """DiffusionGenerator.restoration (DDPM) of the unmodified reference."""
+    gold = torch.load(os.path.join(golden_dir, "palette_sampling.pt"))
+    cfg = O.UNetCfg(**gold["cfg"])
+    params = O.init_params(cfg, gold["wseed"])
+    data, y_t0, noises = _sampling_draws(gold, cfg)
+    with torch.no_grad():
+        y, ret = O.restoration_ddpm(params, data["cond"], y_t0, data["gt"], data["mask"], noises, cfg,
+                                    gold["sample_num"])
+    assert ret.shape == gold["ret_arr"].shape
+    assert _rel(y, gold["y"]) < 1e-4 and _rel(ret, gold["ret_arr"]) < 1e-4
