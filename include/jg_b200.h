@@ -197,10 +197,12 @@ int jg_noise_pack_fwd(const float* y0, const float* ycond, const float* noise, c
  * + noise, the mask blend of restoration_ddpm (:168-170), and the next step's cat([y_cond, y_t]) NHWC bf16 pack.
  * eps: UNet output NHWC bf16 (stride lde); y_t, y_cond, y_0, noise, y_next: fp32 NCHW [B,C,H,W]; noise NULL at t = 0;
  * coef fp32 [B][5] = (sqrt_recip_gammas, sqrt_recipm1_gammas, posterior_mean_coef1, posterior_mean_coef2,
- * exp(0.5 * posterior_log_variance_clipped)) gathered at t; x_next (may be NULL) NHWC bf16 [B,H,W,ld]. */
+ * exp(0.5 * posterior_log_variance_clipped)) gathered at t; x_next (may be NULL) NHWC bf16 [B,H,W,ld].
+ * ddim != 0: the DDIM update of ddim_p_sample / ddim_p_mean_variance (:349-456) instead:
+ * y = clamp(c1*y_t + c2*clamp(eps,-1,1), -1, 1) with coef = (sqrt(g_prev/g_t), coef_eps - sqrt(g_prev*(1-g_t)/g_t), ..). */
 int jg_ddpm_step(const void* eps, int lde, const float* y_t, const float* y_cond, const float* y_0,
                  const float* mask_f32, const int64_t* mask_i64, const float* noise, const float* coef, float* y_next,
-                 void* x_next, int B, int C, int H, int W, int ld, jg_stream_t stream);
+                 void* x_next, int B, int C, int H, int W, int ld, int ddim, jg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * PaletteModel.compute_palette_loss (palette_model.py:596-620):

@@ -116,12 +116,14 @@ __global__ void noise_pack_kernel(const float* __restrict__ y0, const float* __r
 // and, in the same pass, the NEXT step's UNet input cat([y_cond, y]) as NHWC bf16 (x_next, zero-padded to ld).
 // eps: the UNet output, NHWC bf16 with channel stride lde; y_t / y_cond / y_0 / noise / y_next fp32 NCHW;
 // coef fp32 [B][5] = (c1, c2, pm1, pm2, sigma) gathered at t; noise NULL = 0 (the t == 0 step).
+// ddim != 0: the deterministic DDIM update of ddim_p_sample / ddim_p_mean_variance (:349-456),
+//   y = clamp(c1*y_t + c2*clamp(eps, -1, 1), -1, 1),  c1 = sqrt(g_prev/g_t), c2 = coef_eps - sqrt(g_prev*(1-g_t)/g_t).
 __global__ void ddpm_step_kernel(const __nv_bfloat16* __restrict__ eps, int lde, const float* __restrict__ yt,
                                  const float* __restrict__ ycond, const float* __restrict__ y0,
                                  const float* __restrict__ maskf, const long long* __restrict__ maski,
                                  const float* __restrict__ noise, const float* __restrict__ coef,
                                  float* __restrict__ ynext, __nv_bfloat16* __restrict__ xnext, int B, int C, int HW,
-                                 int ld) {
+                                 int ld, int ddim) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= (long long)B * HW) return;
   const int b = (int)(idx / HW);
@@ -143,9 +145,16 @@ __global__ void ddpm_step_kernel(const __nv_bfloat16* __restrict__ eps, int lde,
     const size_t src = ((size_t)b * C + c) * HW + p;
     const float y = yt[src];
     const float e = __bfloat162float(eps[idx * lde + c]);
-    const float y0h = fminf(fmaxf(c1 * y - c2 * e, -1.f), 1.f);
-    float out = pm1 * y0h + pm2 * y;
-    if (noise) out += sigma * noise[src];
+    float out;
+    if (ddim) {
+      // ddim_p_mean_variance (:389-456): the network output is clamped, then the mean
+      const float ec = fminf(fmaxf(e, -1.f), 1.f);
+      out = fminf(fmaxf(c1 * y + c2 * ec, -1.f), 1.f);
+    } else {
+      const float y0h = fminf(fmaxf(c1 * y - c2 * e, -1.f), 1.f);
+      out = pm1 * y0h + pm2 * y;
+      if (noise) out += sigma * noise[src];
+    }
     if (has_mask) out = y0[src] * (1.f - m) + m * out;
     ynext[src] = out;
     if (o) {
@@ -345,7 +354,8 @@ extern "C" int jg_adamw_ema_step(float* p, const float* g, float* m, float* v, f
 
 extern "C" int jg_ddpm_step(const void* eps, int lde, const float* y_t, const float* y_cond, const float* y_0,
                             const float* mask_f32, const int64_t* mask_i64, const float* noise, const float* coef,
-                            float* y_next, void* x_next, int B, int C, int H, int W, int ld, jg_stream_t stream_) {
+                            float* y_next, void* x_next, int B, int C, int H, int W, int ld, int ddim,
+                            jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   JG_CHECK(eps && y_t && y_cond && coef && y_next && B > 0 && C > 0 && lde >= C, JG_ERR_INVALID,
            "ddpm_step: null pointer / bad dims");
@@ -355,7 +365,7 @@ extern "C" int jg_ddpm_step(const void* eps, int lde, const float* y_t, const fl
   ddpm_step_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(eps), lde, y_t, y_cond, y_0, mask_f32,
       reinterpret_cast<const long long*>(mask_i64), noise, coef, y_next, static_cast<__nv_bfloat16*>(x_next), B, C,
-      H * W, ld);
+      H * W, ld, ddim);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }

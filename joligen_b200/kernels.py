@@ -296,14 +296,14 @@ def noise_pack(y0, ycond, noise, mask, gammas, ld=8):
     return out
 
 
-def ddpm_step(eps, y_t, y_cond, y_0, mask, noise, coef, ld=8, want_next_input=True):
+def ddpm_step(eps, y_t, y_cond, y_0, mask, noise, coef, ld=8, want_next_input=True, ddim=False):
     """One reverse-diffusion step + mask blend + next-input pack (jg_ddpm_step).  Returns (y_next, x_next or None)."""
     b, c, h, w = y_t.shape
     y_next = torch.empty_like(y_t)
     x_next = torch.empty((b, h, w, ld), dtype=torch.bfloat16, device=y_t.device) if want_next_input else None
     mf, mi = _mask_ptrs(mask)
     L.call("jg_ddpm_step", L.ptr(eps), _ld(eps), L.ptr(y_t), L.ptr(y_cond), L.ptr(y_0), mf, mi, L.ptr(noise),
-           L.ptr(coef), L.ptr(y_next), L.ptr(x_next), b, c, h, w, ld, L.stream())
+           L.ptr(coef), L.ptr(y_next), L.ptr(x_next), b, c, h, w, ld, int(ddim), L.stream())
     return y_next, x_next
 
 

@@ -57,7 +57,8 @@ _SIGNATURES = {
     "jg_layernorm_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_p, c_p, c_p, c_p, c_p],
     "jg_temporal_attn_fwd": [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
     "jg_temporal_attn_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
-    "jg_ddpm_step": [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_ddpm_step": [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                     c_p],
     "jg_geglu_fwd": [c_p, c_int, c_p, c_int, c_i64, c_int, c_p],
     "jg_geglu_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_p],
     "jg_linear_fwd": [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],

@@ -516,6 +516,55 @@ class DiffusionGenerator(nn.Module):
                 ret_arr = torch.cat([ret_arr, y_t], dim=0)
         return y_t, ret_arr
 
+    @torch.no_grad()
+    def restoration_ddim(self, y_cond, y_t=None, y_0=None, mask=None, sample_num=8, cls=None, guidance_scale=0.0,
+                         num_steps=10, eta=0.5, ref=None):
+        """diffusion_generator.restoration_ddim (:286-347) with ddim_p_sample / ddim_p_mean_variance (:349-456):
+        num_steps UNet forwards on the linear t sequence; the update is deterministic (the reference draws a noise
+        tensor and does not use it), one fused kernel per step."""
+        if cls is not None or ref is not None or guidance_scale:
+            raise NotImplementedError("B200 restoration_ddim: class / reference conditioning and guidance")
+        model = self.denoise_fn.model
+        T = model.num_timesteps_test
+        assert T > sample_num, "num_timesteps must greater than sample_num"
+        sample_inter = T // sample_num
+        b = y_cond.shape[0]
+        y_cond = y_cond.contiguous().float()
+        y_t = (torch.randn_like(y_cond) if y_t is None else y_t).contiguous().float()
+        c = y_t.shape[1]
+        if mask is not None:
+            y_0 = y_0.contiguous().float()
+            mask = mask.contiguous()
+        ld = (y_cond.shape[1] + c + 7) // 8 * 8
+        tseq = list(np.linspace(0, T - 1, num_steps).astype(int))
+        x = ops.to_nhwc(torch.cat([y_cond, y_t], dim=1))
+        ret_arr = y_t
+        for i in range(num_steps):
+            t = int(tseq[-1 - i])
+            prevt = int(tseq[-2 - i]) if i != num_steps - 1 else -1
+            g_t = model.gammas_test[t]
+            g_p = model.gammas_prev_test[prevt + 1]
+            sigma = eta * torch.sqrt((1 - g_p) / (1 - g_t) * (1 - g_t / g_p))
+            coef_eps = torch.sqrt(torch.clamp(1 - g_p - sigma ** 2, min=0))
+            c1 = torch.sqrt(g_p) / torch.sqrt(g_t)
+            c2 = coef_eps - torch.sqrt(g_p) * torch.sqrt(1.0 - g_t) / torch.sqrt(g_t)
+            coef = torch.stack([c1, c2, c1 * 0, c1 * 0, c1 * 0]).reshape(1, 5).expand(b, 5).contiguous().float()
+            eps = model.forward_nhwc(x, self.compute_gammas(g_t.reshape(1, 1).expand(b, 1)))
+            y_t, x = K.ddpm_step(eps, y_t, y_cond, y_0, mask, None, coef, ld=ld, want_next_input=i != num_steps - 1,
+                                 ddim=True)
+            if i % sample_inter == 0:
+                ret_arr = torch.cat([ret_arr, y_t], dim=0)
+        return y_t, ret_arr
+
+    def restoration(self, y_cond, y_t=None, y_0=None, mask=None, sample_num=8, cls=None, ref=None,
+                    guidance_scale=0.0, ddim_num_steps=10, ddim_eta=0.5):
+        """diffusion_generator.restoration (:83-118)."""
+        if self.sampling_method == "ddpm":
+            return self.restoration_ddpm(y_cond, y_t=y_t, y_0=y_0, mask=mask, sample_num=sample_num, cls=cls,
+                                         guidance_scale=guidance_scale, ref=ref)
+        return self.restoration_ddim(y_cond, y_t=y_t, y_0=y_0, mask=mask, sample_num=sample_num, cls=cls,
+                                     guidance_scale=guidance_scale, num_steps=ddim_num_steps, eta=ddim_eta, ref=ref)
+
     def forward_loss(self, y_0, y_cond, mask, noise=None, lambda_G=1.0, use_minsnr=False, l1=False, t=None, u=None):
         """compute_palette_loss fused: the UNet output stays NHWC bf16 and feeds the eps-loss kernel directly."""
         noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u)

@@ -176,8 +176,19 @@ def sampling_golden(name, cfgd, batch, wseed, dseed, rseed, sample_num):
         yo, reto = O.restoration_ddpm(params, data["cond"], y_t0, data["gt"], data["mask"], noises, cfg, sample_num)
     print(name, "oracle vs reference: y rel max err %.2e, ret_arr %.2e" % (
         float((yo - y).abs().max() / y.abs().max()), float((reto - ret).abs().max() / ret.abs().max())))
+    # DDIM: 5 steps, eta 0.5, from the same initial y_t (the reference's y_t default has y_cond's shape)
+    net.sampling_method = "ddim"
+    torch.manual_seed(rseed + 1)
+    with torch.no_grad():
+        yd, retd = net.restoration(data["cond"], y_t=y_t0.clone(), y_0=data["gt"], mask=data["mask"],
+                                   sample_num=sample_num, ddim_num_steps=5, ddim_eta=0.5)
+        ydo, retdo = O.restoration_ddim(params, data["cond"], y_t0.clone(), data["gt"], data["mask"], cfg, sample_num,
+                                        num_steps=5, eta=0.5)
+    print(name, "DDIM oracle vs reference: y rel max err %.2e, ret_arr %.2e" % (
+        float((ydo - yd).abs().max() / yd.abs().max()), float((retdo - retd).abs().max() / retd.abs().max())))
     torch.save({"cfg": cfgd, "batch": batch, "wseed": wseed, "dseed": dseed, "rseed": rseed, "sample_num": sample_num,
-                "torch_version": str(torch.__version__), "y": y.clone(), "ret_arr": ret.clone()},
+                "torch_version": str(torch.__version__), "y": y.clone(), "ret_arr": ret.clone(),
+                "ddim_steps": 5, "ddim_eta": 0.5, "y_ddim": yd.clone(), "ret_arr_ddim": retd.clone()},
                os.path.join(GOLDEN, name))
 
 

@@ -414,6 +414,39 @@ def restoration_ddpm(sd, y_cond, y_t, y_0, mask, noises, cfg: UNetCfg, sample_nu
     return y_t, ret_arr
 
 
+def restoration_ddim(sd, y_cond, y_t, y_0, mask, cfg: UNetCfg, sample_num=8, num_steps=10, eta=0.5):
+    """DiffusionGenerator.restoration_ddim / ddim_p_sample / ddim_p_mean_variance (diffusion_generator.py:286-456),
+    conditioning "" and no guidance.  Deterministic given y_t (the reference's per-step noise draw is unused)."""
+    sched = schedule_buffers(cfg, "test")
+    T = int(sched["gammas_test"].shape[0])
+    sample_inter = T // sample_num
+    b = y_cond.shape[0]
+    ret_arr = y_t
+    tseq = list(np.linspace(0, T - 1, num_steps).astype(int))
+    gammas_prev = torch.cat([torch.ones(1), sched["gammas_test"][:-1]])
+    for i in range(num_steps):
+        t = torch.full((b,), int(tseq[-1 - i]), dtype=torch.long)
+        prevt = torch.full((b,), int(tseq[-2 - i]) if i != num_steps - 1 else -1, dtype=torch.long)
+        noise_level = sched["gammas_test"].gather(-1, t).reshape(b, 1)
+        emb = gamma_embedding(noise_level, cfg.cond_embed_dim)
+        emb = F.linear(emb, sd["cond_embed.0.weight"], sd["cond_embed.0.bias"])
+        emb = F.linear(F.silu(emb), sd["cond_embed.2.weight"], sd["cond_embed.2.bias"])
+        e = unet_forward(sd, torch.cat([y_cond, y_t], dim=1), emb, cfg).clamp(-1.0, 1.0)
+        g_t = sched["gammas_test"].gather(-1, t).reshape(b, 1, 1, 1)
+        g_p = gammas_prev.gather(-1, prevt + 1).reshape(b, 1, 1, 1)
+        sigma = eta * torch.sqrt((1 - g_p) / (1 - g_t) * (1 - g_t / g_p))
+        coef_eps = 1 - g_p - sigma ** 2
+        coef_eps[coef_eps < 0] = 0
+        coef_eps = torch.sqrt(coef_eps)
+        y_t = (torch.sqrt(g_p) * (y_t - torch.sqrt(1.0 - g_t) * e) / torch.sqrt(g_t) + coef_eps * e).clamp(-1.0, 1.0)
+        if mask is not None:
+            m = torch.clamp(mask, min=0.0, max=1.0)
+            y_t = y_0 * (1.0 - m) + m * y_t
+        if i % sample_inter == 0:
+            ret_arr = torch.cat([ret_arr, y_t], dim=0)
+    return y_t, ret_arr
+
+
 def palette_loss(noise, noise_hat, mask, min_snr_w=None, lambda_G=1.0, use_minsnr=False, kind="MSE"):
     """PaletteModel.compute_palette_loss, palette_model.py:596-620."""
     w = min_snr_w if use_minsnr else 1.0

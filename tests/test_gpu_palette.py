@@ -241,7 +241,7 @@ def test_state_dict_roundtrip_and_modulewise_dropin(env):
     assert rel_l2(got, ref) < 1e-2
 
 
-def test_ddpm_sampler_vs_reference_golden(env, golden_dir):
+def test_ddpm_and_ddim_samplers_vs_reference_golden(env, golden_dir):
     """restoration_ddpm (12 reverse steps, mask blend, fused step kernel) against the
     unmodified reference's sampler with the same random draws.  Unmasked pixels are copied from y_0 (exact); inside
     the mask the bf16 UNet error is fed back 12 times: held against the bf16-emulating oracle's own distance to fp32."""
@@ -274,3 +274,19 @@ def test_ddpm_sampler_vs_reference_golden(env, golden_dir):
     floor = rel_l2(yo, gold["y"])
     assert rel_l2(y, gold["y"]) < max(3e-2, 2.5 * floor), (rel_l2(y, gold["y"]), floor)
     assert rel_l2(ret, gold["ret_arr"]) < max(3e-2, 2.5 * rel_l2(reto, gold["ret_arr"]))
+    # DDIM (deterministic, 5 steps) through the reference's dispatcher signature
+    g.sampling_method = "ddim"
+    yd, retd = g.restoration(data["cond"].cuda(), y_t=y_t0.cuda(), y_0=data["gt"].cuda(), mask=data["mask"].cuda(),
+                             sample_num=gold["sample_num"], ddim_num_steps=gold["ddim_steps"],
+                             ddim_eta=gold["ddim_eta"])
+    assert retd.shape == gold["ret_arr_ddim"].shape
+    assert torch.equal(yd.cpu()[~m], data["gt"][~m])
+    O.EMULATE_BF16[0] = True
+    try:
+        with torch.no_grad():
+            ydo, _ = O.restoration_ddim(params, data["cond"], y_t0, data["gt"], data["mask"], cfg, gold["sample_num"],
+                                        num_steps=gold["ddim_steps"], eta=gold["ddim_eta"])
+    finally:
+        O.EMULATE_BF16[0] = False
+    floor = rel_l2(ydo, gold["y_ddim"])
+    assert rel_l2(yd, gold["y_ddim"]) < max(3e-2, 2.5 * floor), (rel_l2(yd, gold["y_ddim"]), floor)

@@ -123,3 +123,14 @@ def test_oracle_ddpm_sampler_matches_reference(golden_dir):
                                     gold["sample_num"])
     assert ret.shape == gold["ret_arr"].shape
     assert _rel(y, gold["y"]) < 1e-4 and _rel(ret, gold["ret_arr"]) < 1e-4
+
+
+def test_oracle_ddim_sampler_matches_reference(golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "palette_sampling.pt"))
+    cfg = O.UNetCfg(**gold["cfg"])
+    params = O.init_params(cfg, gold["wseed"])
+    data, y_t0, _ = _sampling_draws(gold, cfg)
+    with torch.no_grad():
+        y, ret = O.restoration_ddim(params, data["cond"], y_t0, data["gt"], data["mask"], cfg, gold["sample_num"],
+                                    num_steps=gold["ddim_steps"], eta=gold["ddim_eta"])
+    assert _rel(y, gold["y_ddim"]) < 1e-4 and _rel(ret, gold["ret_arr_ddim"]) < 1e-4
