@@ -62,11 +62,55 @@ def _unet_from_reference(ref):
         freq_space=getattr(ref, "freq_space", False))
 
 
+def _common_unet_kwargs(ref):
+    first_res = ref.input_blocks[1][0]
+    return dict(
+        image_size=ref.image_size, in_channel=ref.in_channel, inner_channel=ref.inner_channel,
+        out_channel=ref.out_channel, res_blocks=list(ref.res_blocks), attn_res=list(ref.attn_res), tanh=False,
+        n_timestep_train=ref.beta_schedule["train"]["n_timestep"],
+        n_timestep_test=ref.beta_schedule["test"]["n_timestep"], norm=_norm_spec(first_res.in_layers[0]),
+        group_norm_size=32, cond_embed_dim=ref.cond_embed_dim, channel_mults=tuple(ref.channel_mults),
+        use_scale_shift_norm=first_res.use_scale_shift_norm, efficient=first_res.efficient,
+        freq_space=getattr(ref, "freq_space", False))
+
+
+def _first_attention(ref):
+    for m in ref.modules():
+        if type(m).__name__ in ("AttentionBlock", "AttentionBlockRef"):
+            return m
+    return None
+
+
+def _unetvid_from_reference(ref):
+    from . import nets_vid
+    att = _first_attention(ref)
+    new_order = att is not None and type(att.attention).__name__ == "QKVAttention"
+    return nets_vid.UNetVid(num_heads=ref.num_heads, num_head_channels=ref.num_head_channels,
+                            num_heads_upsample=ref.num_heads_upsample, use_new_attention_order=new_order,
+                            max_sequence_length=ref.max_sequence_length, cross_attention_dim=ref.cross_attention_dim,
+                            num_attention_heads=ref.num_attention_heads,
+                            num_transformer_blocks=ref.num_transformer_blocks, **_common_unet_kwargs(ref))
+
+
+def _unetref_from_reference(ref):
+    from . import nets_ref
+    att = _first_attention(ref)
+    new_order = att is not None and type(att.attention).__name__ == "QKVAttention"
+    heads = att.num_heads if att is not None else 1
+    head_ch = att.channels // heads if att is not None else -1
+    # the reference class does not keep num_heads / num_head_channels: recover them from its attention blocks
+    # (all blocks share num_head_channels when it was given; otherwise num_heads)
+    per_block = {m.channels // m.num_heads for m in ref.modules() if type(m).__name__ == "AttentionBlockRef"}
+    kw = dict(num_head_channels=head_ch) if len(per_block) == 1 else dict(num_heads=heads)
+    return nets_ref.UNetGeneratorRefAttn(use_new_attention_order=new_order, **kw, **_common_unet_kwargs(ref))
+
+
 def accelerate(module: nn.Module) -> nn.Module:
     """Returns the accelerated module (the same object with children swapped, or a new root when the
     root itself is a hot-path class)."""
     cls = type(module).__name__
-    if isinstance(module, (nets.UNet, nets.DiffusionGenerator, nets.ResBlock, nets.AttentionBlock)):
+    if isinstance(module, (nets.UNet, nets.DiffusionGenerator, nets.ResBlock, nets.AttentionBlock)) or \
+            type(module).__module__.startswith("joligen_b200."):
         return module
     if cls == "DiffusionGenerator":
         ref_unet = module.denoise_fn.model
@@ -85,6 +129,16 @@ def accelerate(module: nn.Module) -> nn.Module:
         return new
     if cls == "UNet" and hasattr(module, "input_blocks") and hasattr(module, "middle_block"):
         new = _unet_from_reference(module)
+        _adopt(new, module)
+        new.train(module.training)
+        return new
+    if cls == "UNetVid" and hasattr(module, "input_blocks"):
+        new = _unetvid_from_reference(module)
+        _adopt(new, module)
+        new.train(module.training)
+        return new
+    if cls == "UNetGeneratorRefAttn" and hasattr(module, "input_blocks_ref"):
+        new = _unetref_from_reference(module)
         _adopt(new, module)
         new.train(module.training)
         return new

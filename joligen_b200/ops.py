@@ -58,7 +58,7 @@ class Conv2dFn(torch.autograd.Function):
         cout8 = (cout + 7) // 8 * 8
         # a GroupNorm backward that produced this very tensor has already summed it over (n, pixel)
         # (autograd may accumulate a second gradient INTO that tensor in place: the stamp carries its version)
-        stamp = getattr(dy, "_jg_colsum", None) if dy.is_contiguous() else None
+        stamp = getattr(dy, "_jg_colsum", None)
         colsum = stamp[0] if stamp is not None and stamp[1] == dy._version else None
         dy = _rows(dy)
         dx = dw = db = dres = None
@@ -278,7 +278,17 @@ class CatChannelsFn(torch.autograd.Function):
     def backward(ctx, d):
         # channel-slice views: every backward kernel addresses its incoming gradient with a row stride
         ca, cb = ctx.split
-        return d[..., :ca], d[..., ca:]
+        return _slice_with_stamp(d, 0, ca), _slice_with_stamp(d, ca, ca + cb)
+
+
+def _slice_with_stamp(d, c0, c1):
+    """d[..., c0:c1] as a view; the per-channel sums that a GroupNorm backward attached to d (see Conv2dFn.backward)
+    are sliced along with it, so the conv that produced this part of a concat input gets its bias gradient for free."""
+    v = d[..., c0:c1]
+    stamp = getattr(d, "_jg_colsum", None)
+    if stamp is not None and stamp[1] == d._version:
+        v._jg_colsum = (stamp[0][c0:c1], v._version)
+    return v
 
 
 class CatIntoFn(torch.autograd.Function):
@@ -296,7 +306,7 @@ class CatIntoFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d):
         ca, cb = ctx.split
-        return d[..., :ca], d[..., ca:], None
+        return _slice_with_stamp(d, 0, ca), _slice_with_stamp(d, ca, ca + cb), None
 
 
 class ToNHWCFn(torch.autograd.Function):

@@ -30,3 +30,25 @@ def test_accelerate_adopts_reference_parameters():
     holder.netG = gen_golden.build_reference_generator(cfg).denoise_fn.model
     accelerate(holder)
     assert isinstance(holder.netG, nets.UNet)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_accelerate_video_and_reference_attention_unets():
+    """Rows a-16..a-18: the reference's UNetVid / UNetGeneratorRefAttn objects are swapped for the B200 mirrors,
+    which adopt the reference's Parameter objects (incl. the MotionModule's positional-encoding buffers)."""
+    from oracle import ref_stubs
+    ref_stubs.install()
+    from oracle import gen_golden_ref, gen_golden_vid
+    from oracle import palette_oracle as O
+    from oracle import vid_oracle as V
+    from joligen_b200 import accelerate, nets_ref, nets_vid
+    ref_vid = gen_golden_vid.build_reference(V.VidCfg(**gen_golden_vid.CFG))
+    params, keys = dict(ref_vid.named_parameters()), list(ref_vid.state_dict().keys())
+    fast = accelerate(ref_vid)
+    assert isinstance(fast, nets_vid.UNetVid) and list(fast.state_dict().keys()) == keys
+    assert all(p is params[k] for k, p in fast.named_parameters())
+    ref_ra = gen_golden_ref.build_reference(O.UNetCfg(**gen_golden_ref.CFG))
+    params, keys = dict(ref_ra.named_parameters()), list(ref_ra.state_dict().keys())
+    fast = accelerate(ref_ra)
+    assert isinstance(fast, nets_ref.UNetGeneratorRefAttn) and list(fast.state_dict().keys()) == keys
+    assert all(p is params[k] for k, p in fast.named_parameters())
