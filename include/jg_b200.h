@@ -120,13 +120,14 @@ size_t jg_groupnorm_bwd_ws_floats(int N, int C, int groups);
 int jg_groupnorm_fwd(const void* x, int ldx, void* y, int ldy, int N, int HW, int C, int groups, float eps,
                      const float* gamma, const float* beta, const float* film, int act, float* stats, float* ab,
                      float* ws, jg_stream_t stream);
-/* dx = d/dx (+ addend, an NHWC bf16 tensor like dx with stride ldadd, or NULL: the gradient of a second consumer
- * of x — e.g. the ResBlock's skip path — summed in the same pass; addend may alias dx);
+/* dx = d/dx (+ addend (+ addend2), NHWC bf16 tensors like dx with strides ldadd / ldadd2, or NULL: the gradients of
+ * other consumers of x — the ResBlock's skip path, the decoder's concat (unet_generator_attn.py:687) — summed in the
+ * same pass; addend may alias dx; addend2 requires addend);
  * dgamma/dbeta [C] overwritten (may be NULL); dfilm [N][2C] overwritten (may be NULL);
  * dx_colsum [C] (may be NULL) receives sum over (n, pixel) of dx: x is the output of a conv, so this IS that conv's
  * bias gradient (nn.Conv2d bias, unet_generator_attn.py:190,207) and saves the separate pass over dx. */
 int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, const void* addend,
-                     int ldadd, int N,
+                     int ldadd, const void* addend2, int ldadd2, int N,
                      int HW, int C, int groups, const float* gamma, const float* beta, const float* film, int act,
                      const float* stats, const float* ab, float* dgamma, float* dbeta, float* dfilm,
                      float* dx_colsum, float* ws, jg_stream_t stream);

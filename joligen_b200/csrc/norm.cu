@@ -387,15 +387,19 @@ __global__ void gn_param_grad_kernel(const float* __restrict__ gAB, int N, int C
   if (dgamma) dgamma[c] = sb;
 }
 
-// ---- bwd pass 3: dx = k1*du + k2*x + k3 (+ addend), optionally colsum[c] += sum over rows of dx ---------
+// ---- bwd pass 3: dx = k1*du + k2*x + k3 (+ addend (+ addend2)), optionally colsum[c] += sum over rows of dx ---------
 // U rows are in flight per thread.  The per-channel constants take 40 registers: two blocks per SM (128 registers)
-// with U = 3 (addend) or 4 keep ~50 KB in flight per SM without spilling.  smem: kPartFloats + C floats (column sums).
-template <bool HAS_ADD, int ACT, int U>
+// with U = 4 / 3 / 2 (0 / 1 / 2 addends) keep ~50 KB in flight per SM without spilling.
+// smem: kPartFloats + C floats (column sums).  NADD = number of extra gradients of x summed in (other consumers of x).
+template <int NADD, int ACT, int U>
 __global__ void __launch_bounds__(kNormThreads, 2)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy, int lddy,
                     __nv_bfloat16* __restrict__ dx, int lddx, int HW, int C, int groups, int rows_per_block,
                     const float* __restrict__ ab, const float* __restrict__ k1, const float* __restrict__ k23,
-                    const __nv_bfloat16* __restrict__ addend, int ldadd, float* __restrict__ colsum) {
+                    const __nv_bfloat16* __restrict__ addend, int ldadd, const __nv_bfloat16* __restrict__ addend2,
+                    int ldadd2, float* __restrict__ colsum) {
+  constexpr bool HAS_ADD = NADD >= 1;
+  constexpr bool HAS_ADD2 = NADD >= 2;
   extern __shared__ float sm[];
   const int n = blockIdx.y;
   const int vecs = C / 8;
@@ -423,18 +427,21 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfl
     const __nv_bfloat16* db = dy + ((size_t)n * HW) * lddy + v * 8;
     __nv_bfloat16* ob = dx + ((size_t)n * HW) * lddx + v * 8;
     const __nv_bfloat16* eb = HAS_ADD ? addend + ((size_t)n * HW) * ldadd + v * 8 : nullptr;
-    // one row: o = c1*du + c2*x + c3 (+ e), stored as bf16; the column sums are taken in fp32 before the rounding
-    auto row = [&](const uint4& ux, const uint4& ud, const uint4& ua, __nv_bfloat16* dst) {
-      float f[8], d[8], o[8], e[8];
+    const __nv_bfloat16* eb2 = HAS_ADD2 ? addend2 + ((size_t)n * HW) * ldadd2 + v * 8 : nullptr;
+    // one row: o = c1*du + c2*x + c3 (+ e (+ e2)), stored as bf16; the column sums are taken in fp32 before the rounding
+    auto row = [&](const uint4& ux, const uint4& ud, const uint4& ua, const uint4& ua2, __nv_bfloat16* dst) {
+      float f[8], d[8], o[8], e[8], e2[8];
       unpack8(ux, f);
       unpack8(ud, d);
       if (HAS_ADD) unpack8(ua, e);
+      if (HAS_ADD2) unpack8(ua2, e2);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float du = d[j];
         if (ACT != JG_ACT_NONE) du *= act_grad<ACT>(fmaf(f[j], a[j], b[j]));
         o[j] = fmaf(c1[j], du, fmaf(c2[j], f[j], c3[j]));
         if (HAS_ADD) o[j] += e[j];
+        if (HAS_ADD2) o[j] += e2[j];
       }
       *reinterpret_cast<uint4*>(dst) = pack8(o);
       if (colsum) {
@@ -444,22 +451,24 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfl
     };
     int r = r0 + rl;
     for (; r + (U - 1) * rstep < r1; r += U * rstep) {
-      uint4 ux[U], ud[U], ua[U];
+      uint4 ux[U], ud[U], ua[U], ua2[U];
 #pragma unroll
       for (int k = 0; k < U; ++k) {
         ux[k] = ldg_stream(xb + (size_t)(r + k * rstep) * ldx);
         ud[k] = ldg_stream(db + (size_t)(r + k * rstep) * lddy);
         if (HAS_ADD) ua[k] = ldg_stream(eb + (size_t)(r + k * rstep) * ldadd);
+        if (HAS_ADD2) ua2[k] = ldg_stream(eb2 + (size_t)(r + k * rstep) * ldadd2);
       }
 #pragma unroll
-      for (int k = 0; k < U; ++k) row(ux[k], ud[k], ua[k], ob + (size_t)(r + k * rstep) * lddx);
+      for (int k = 0; k < U; ++k) row(ux[k], ud[k], ua[k], ua2[k], ob + (size_t)(r + k * rstep) * lddx);
     }
     for (; r < r1; r += rstep) {
       const uint4 ux = ldg_stream(xb + (size_t)r * ldx);
       const uint4 ud = ldg_stream(db + (size_t)r * lddy);
-      uint4 ua = ux;
+      uint4 ua = ux, ua2 = ux;
       if (HAS_ADD) ua = ldg_stream(eb + (size_t)r * ldadd);
-      row(ux, ud, ua, ob + (size_t)r * lddx);
+      if (HAS_ADD2) ua2 = ldg_stream(eb2 + (size_t)r * ldadd2);
+      row(ux, ud, ua, ua2, ob + (size_t)r * lddx);
     }
   }
   if (colsum) {  // block-uniform
@@ -527,7 +536,8 @@ extern "C" int jg_groupnorm_fwd(const void* x, int ldx, void* y, int ldy, int N,
 }
 
 extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, const void* addend,
-                                int ldadd, int N, int HW, int C, int groups, const float* gamma, const float* beta,
+                                int ldadd, const void* addend2, int ldadd2, int N, int HW, int C, int groups,
+                                const float* gamma, const float* beta,
                                 const float* film, int act, const float* stats, const float* ab, float* dgamma,
                                 float* dbeta, float* dfilm, float* dx_colsum, float* ws, jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -536,6 +546,8 @@ extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy
   JG_CHECK(x && dy && dx && stats && ab && ws, JG_ERR_INVALID, "groupnorm_bwd: null pointer");
   JG_CHECK(lddy % 8 == 0 && lddy >= C && lddx % 8 == 0 && lddx >= C, JG_ERR_INVALID, "groupnorm_bwd: bad ld");
   JG_CHECK(addend == nullptr || (ldadd % 8 == 0 && ldadd >= C), JG_ERR_INVALID, "groupnorm_bwd: bad ldadd");
+  JG_CHECK(addend2 == nullptr || (addend != nullptr && ldadd2 % 8 == 0 && ldadd2 >= C), JG_ERR_INVALID,
+           "groupnorm_bwd: addend2 needs addend and a valid ldadd2");
   float* AB = ws;
   float* k1 = AB + (size_t)N * C * 2;
   float* k23 = k1 + (size_t)N * C;
@@ -549,6 +561,7 @@ extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(dy);
   const __nv_bfloat16* addb = static_cast<const __nv_bfloat16*>(addend);
+  const __nv_bfloat16* addb2 = static_cast<const __nv_bfloat16*>(addend2);
   __nv_bfloat16* dxb = static_cast<__nv_bfloat16*>(dx);
   JG_ACT_DISPATCH(act, gn_bwd_sums_kernel<ACT><<<grid1, kNormThreads, (2 * kPartFloats + 2 * C) * sizeof(float), stream>>>(
                            xb, ldx, dyb, lddy, HW, C, rpb1, ab, AB));
@@ -561,12 +574,18 @@ extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy
     JG_LAUNCH_CHECK();
   }
   const size_t smem = dx_colsum ? (kPartFloats + C) * sizeof(float) : 0;
-  if (addend) {
-    JG_ACT_DISPATCH(act, gn_bwd_apply_kernel<true, ACT, 3><<<grid, kNormThreads, smem, stream>>>(
-                             xb, ldx, dyb, lddy, dxb, lddx, HW, C, groups, rpb, ab, k1, k23, addb, ldadd, dx_colsum));
+  if (addend2) {
+    JG_ACT_DISPATCH(act, gn_bwd_apply_kernel<2, ACT, 2><<<grid, kNormThreads, smem, stream>>>(
+                             xb, ldx, dyb, lddy, dxb, lddx, HW, C, groups, rpb, ab, k1, k23, addb, ldadd, addb2, ldadd2,
+                             dx_colsum));
+  } else if (addend) {
+    JG_ACT_DISPATCH(act, gn_bwd_apply_kernel<1, ACT, 3><<<grid, kNormThreads, smem, stream>>>(
+                             xb, ldx, dyb, lddy, dxb, lddx, HW, C, groups, rpb, ab, k1, k23, addb, ldadd, nullptr, 0,
+                             dx_colsum));
   } else {
-    JG_ACT_DISPATCH(act, gn_bwd_apply_kernel<false, ACT, 4><<<grid, kNormThreads, smem, stream>>>(
-                             xb, ldx, dyb, lddy, dxb, lddx, HW, C, groups, rpb, ab, k1, k23, nullptr, 0, dx_colsum));
+    JG_ACT_DISPATCH(act, gn_bwd_apply_kernel<0, ACT, 4><<<grid, kNormThreads, smem, stream>>>(
+                             xb, ldx, dyb, lddy, dxb, lddx, HW, C, groups, rpb, ab, k1, k23, nullptr, 0, nullptr, 0,
+                             dx_colsum));
   }
   JG_LAUNCH_CHECK();
   return JG_OK;

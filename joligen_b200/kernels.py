@@ -155,7 +155,7 @@ def groupnorm_fwd(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5, o
 
 
 def groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab, need_param_grads=True, need_film_grad=False,
-                  dx=None, addend=None, colsum=None):
+                  dx=None, addend=None, colsum=None, addend2=None):
     """addend: optional NHWC bf16 tensor summed into dx in the same pass (gradient of another consumer of x).
     colsum: optional fp32 [C] output = per-channel sum of dx (the bias gradient of the conv that produced x)."""
     n, h, w, c = x.shape
@@ -166,7 +166,8 @@ def groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab, need_param_g
     dfilm = torch.empty((n, 2 * c), dtype=torch.float32, device=x.device) if need_film_grad else None
     ws = torch.empty((L.load().jg_groupnorm_bwd_ws_floats(n, c, groups),), dtype=torch.float32, device=x.device)
     L.call("jg_groupnorm_bwd", L.ptr(x), _ld(x), L.ptr(dy), _ld(dy), L.ptr(dx), _ld(dx), L.ptr(addend),
-           _ld(addend) if addend is not None else 0, n, h * w, c,
+           _ld(addend) if addend is not None else 0, L.ptr(addend2), _ld(addend2) if addend2 is not None else 0,
+           n, h * w, c,
            groups, L.ptr(gamma), L.ptr(beta), L.ptr(film), act, L.ptr(stats), L.ptr(ab), L.ptr(dgamma), L.ptr(dbeta),
            L.ptr(dfilm), L.ptr(colsum), L.ptr(ws), L.stream())
     return dx, dgamma, dbeta, dfilm

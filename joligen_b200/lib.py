@@ -49,7 +49,7 @@ _SIGNATURES = {
     "jg_resample2x": [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
     "jg_groupnorm_fwd": [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_f, c_p, c_p, c_p, c_int, c_p, c_p,
                          c_p, c_p],
-    "jg_groupnorm_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p,
+    "jg_groupnorm_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p,
                          c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "jg_attn_fwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
     "jg_attn_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p],

@@ -83,6 +83,10 @@ class GroupNorm(nn.Module):
         """-> (y, x_tap); every other consumer of x must read x_tap (gradient sum fused into the GN backward)."""
         return ops.group_norm_tap(x, self.norm.weight, self.norm.bias, self.norm.num_groups, film=None, act=act)
 
+    def forward_tap2_nhwc(self, x, act=L.ACT_NONE):
+        """-> (y, x_tap, x_tap2): a second hand-through for a consumer outside the block (the decoder's concat)."""
+        return ops.group_norm_tap2(x, self.norm.weight, self.norm.bias, self.norm.num_groups, film=None, act=act)
+
 
 def normalization(channels, norm="groupnorm32"):
     if "groupnorm" in norm:
@@ -99,13 +103,20 @@ class EmbedBlock(nn.Module):
 
 
 class EmbedSequential(nn.Sequential, EmbedBlock):
-    def forward_nhwc(self, x, emb, out=None):
-        """out: optional destination view for the LAST layer's output (see UNet.forward_nhwc)."""
+    def forward_nhwc(self, x, emb, out=None, want_tap=False):
+        """out: optional destination view for the LAST layer's output (see UNet.forward_nhwc).
+        want_tap: also return a hand-through of the block INPUT made by the first layer's GroupNorm (a ResBlock):
+        the encoder keeps it as the skip tensor, so that the concat's gradient is summed inside that GroupNorm's
+        backward (-> (y, tap); tap is None when the first layer cannot provide one)."""
         last = len(self) - 1
+        tap = None
         for i, layer in enumerate(self):
             kw = {"out": out} if (i == last and out is not None) else {}
-            x = layer.forward_nhwc(x, emb, **kw) if isinstance(layer, EmbedBlock) else layer.forward_nhwc(x, **kw)
-        return x
+            if i == 0 and want_tap and isinstance(layer, ResBlock):
+                x, tap = layer.forward_nhwc(x, emb, want_tap=True, **kw)
+            else:
+                x = layer.forward_nhwc(x, emb, **kw) if isinstance(layer, EmbedBlock) else layer.forward_nhwc(x, **kw)
+        return (x, tap) if want_tap else x
 
     def out_geometry(self, h, w):
         """(H, W, C) of the output for an (h, w) input, or None when the last layer cannot write into a view."""
@@ -188,8 +199,12 @@ class ResBlock(EmbedBlock):
         self._pack_out = ConvPack(self.out_layers[3])
         self._pack_skip = ConvPack(self.skip_connection) if isinstance(self.skip_connection, nn.Conv2d) else None
 
-    def forward_nhwc(self, x, emb, out=None):
-        h, x = self.in_layers[0].forward_tap_nhwc(x, act=L.ACT_SILU)
+    def forward_nhwc(self, x, emb, out=None, want_tap=False):
+        tap2 = None
+        if want_tap:
+            h, x, tap2 = self.in_layers[0].forward_tap2_nhwc(x, act=L.ACT_SILU)
+        else:
+            h, x = self.in_layers[0].forward_tap_nhwc(x, act=L.ACT_SILU)
         if self.updown:
             h = self.h_upd.forward_nhwc(h)
             x = self.x_upd.forward_nhwc(x)
@@ -207,7 +222,8 @@ class ResBlock(EmbedBlock):
         skipw = 1.0 / math.sqrt(2) if (self.efficient and self.apply_skipw) else 1.0
         if self._pack_skip is not None:
             x = _conv(x, self.skip_connection, self._pack_skip)
-        return _conv(h, self.out_layers[3], self._pack_out, residual=x, res_scale=skipw, out=out)
+        y = _conv(h, self.out_layers[3], self._pack_out, residual=x, res_scale=skipw, out=out)
+        return (y, tap2) if want_tap else y
 
     def forward(self, x, emb):
         """Drop-in NCHW fp32 signature of the reference block."""
@@ -332,10 +348,15 @@ class UNet(nn.Module):
     # -- NHWC bf16 fast path -------------------------------------------------------------------
     def forward_nhwc(self, x, emb):
         """x: NHWC bf16 [N,H,W,round_up(in_channel,8)] -> NHWC bf16 [N,H,W,round_up(out_channel,8)]."""
+        # Skip tensors: every encoder output h_k is consumed by the next block AND by the decoder's concat.  The
+        # decoder reads a hand-through ("tap") of h_k made by the next block's first GroupNorm, so the two gradients
+        # meet inside that GroupNorm's backward pass instead of in a separate (strided) add kernel.
         hs = []
         h = x
         for module in self.input_blocks:
-            h = module.forward_nhwc(h, emb)
+            h, tap = module.forward_nhwc(h, emb, want_tap=True)
+            if tap is not None and hs:
+                hs[-1] = tap
             hs.append(h)
         # torch.cat([h, hs.pop()], dim=1) (unet_generator_attn.py:687) without copying h: the block that produces h
         # writes it straight into the first channels of the next block's concat buffer; only the skip is copied.
@@ -348,7 +369,9 @@ class UNet(nn.Module):
             return buf, buf[..., :geo[2]]
 
         buf, dst = concat_buffer(self.middle_block, h.shape[1], h.shape[2])
-        h = self.middle_block.forward_nhwc(h, emb, out=dst)
+        h, tap = self.middle_block.forward_nhwc(h, emb, out=dst, want_tap=True)
+        if tap is not None:
+            hs[-1] = tap
         for module in self.output_blocks:
             skip = hs.pop()
             h = ops.cat_into(buf, h, skip) if buf is not None else ops.cat_channels(h, skip)

@@ -116,22 +116,28 @@ class GroupNormFn(torch.autograd.Function):
 
 
 class GroupNormTapFn(torch.autograd.Function):
-    """GroupNorm(+FiLM)(+act) that also hands its input through: returns (y, x_tap).  x has two consumers in a
-    ResBlock / AttentionBlock (the norm and the skip path); routing the skip path through x_tap lets the backward
-    sum both gradients inside the GN-backward apply pass (dx = GN'(dy) + d_tap) instead of a separate add kernel."""
+    """GroupNorm(+FiLM)(+act) that also hands its input through: returns (y, x_tap, x_tap2).  x has several consumers
+    in the UNet (the norm, the ResBlock / AttentionBlock skip path, the decoder's concat of the same tensor);
+    routing the other consumers through the taps lets the backward sum all gradients inside the GN-backward apply
+    pass (dx = GN'(dy) + d_tap + d_tap2) instead of separate add kernels."""
 
     @staticmethod
     def forward(ctx, x, gamma, beta, film, groups, act, eps=1e-5):
         y, stats, ab = K.groupnorm_fwd(x, gamma, beta, groups, film=film, act=act, eps=eps)
         ctx.save_for_backward(x, gamma, beta, film, stats, ab)
         ctx.cfg = (groups, act)
-        return y, x.detach()
+        ctx.set_materialize_grads(False)  # an unused tap must arrive as None, not as a zero-filled tensor
+        return y, x.detach(), x.detach()
 
     @staticmethod
-    def backward(ctx, dy, dtap):
+    def backward(ctx, dy, dtap, dtap2):
         x, gamma, beta, film, stats, ab = ctx.saved_tensors
         groups, act = ctx.cfg
+        if dtap is None:
+            dtap, dtap2 = dtap2, None
         if dy is None:
+            if dtap2 is not None:
+                dtap = dtap + dtap2
             return dtap, None, None, None, None, None, None
         dy = _rows(dy)
         need_p = gamma is not None and (_needs(ctx, 1) or _needs(ctx, 2))
@@ -140,6 +146,7 @@ class GroupNormTapFn(torch.autograd.Function):
         dx, dgamma, dbeta, dfilm = K.groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab,
                                                    need_param_grads=need_p, need_film_grad=need_f,
                                                    addend=None if dtap is None else _rows(dtap),
+                                                   addend2=None if dtap2 is None else _rows(dtap2),
                                                    colsum=colsum)
         if colsum is not None:
             dx._jg_colsum = (colsum, dx._version)
@@ -371,6 +378,12 @@ def group_norm(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5):
 
 def group_norm_tap(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5):
     """-> (y, x_tap): use x_tap for every other consumer of x (see GroupNormTapFn)."""
+    y, tap, _ = GroupNormTapFn.apply(x, gamma, beta, film, groups, act, eps)
+    return y, tap
+
+
+def group_norm_tap2(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5):
+    """-> (y, x_tap, x_tap2): two independent hand-throughs of x (block skip path + decoder concat)."""
     return GroupNormTapFn.apply(x, gamma, beta, film, groups, act, eps)
 
 
