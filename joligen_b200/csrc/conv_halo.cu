@@ -668,15 +668,19 @@ int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int 
   p.tiles_h = d->Ho / 8;
   p.pix_blocks = p.tiles_w * p.tiles_h * d->N;
   p.cib = ceil_div(d->Cin, 64);
-  p.cob = ceil_div(d->Cout, nco);
-  const int pairs = p.cib * p.cob;
-  int ksplit = num_sms() / pairs;
-  if (ksplit < 1) ksplit = 1;
-  const int max_split = p.pix_blocks / 8 > 0 ? p.pix_blocks / 8 : 1;
-  if (ksplit > max_split) ksplit = max_split;
-  p.kb_per_split = ceil_div(p.pix_blocks, ksplit);
-  p.ksplit = ceil_div(p.pix_blocks, p.kb_per_split);
-  p.total_items = pairs * p.ksplit;
+  // work items of one pass: (ci block, co block of `n` channels, pixel range); split-K over the pixel blocks so that
+  // every SM gets an item where possible
+  auto plan = [&](int n) {
+    p.cob = ceil_div(d->Cout, n);
+    const int pairs = p.cib * p.cob;
+    int ksplit = num_sms() / pairs;
+    if (ksplit < 1) ksplit = 1;
+    const int max_split = p.pix_blocks / 8 > 0 ? p.pix_blocks / 8 : 1;
+    if (ksplit > max_split) ksplit = max_split;
+    p.kb_per_split = ceil_div(p.pix_blocks, ksplit);
+    p.ksplit = ceil_div(p.pix_blocks, p.kb_per_split);
+    p.total_items = pairs * p.ksplit;
+  };
   p.acc = ws;
   JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)p.RS * d->Cin * d->Cout, stream));
 
@@ -702,8 +706,20 @@ int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int 
     p.tap0 = t0;
     p.ntaps = p.RS - t0 < taps_per_launch ? p.RS - t0 : taps_per_launch;
     p.npairs = (p.ntaps + 1) / 2;
-    rc = nco == 128 ? launch_wgrad_halo_one<7, 128>(tmDY, tmX, p, stream)
-                    : launch_wgrad_halo_one<8, 64>(tmDY, tmX, p, stream);
+    // The short second pass of a 3x3 filter (3 taps = 2 MMA pairs) is L2-bound: 28.8 KB of operands per 512 MMA cycles
+    // per SM.  With 256 output channels per item the same X patch serves twice the MMA work (44.8 KB per 1 024 cycles,
+    // 2 pairs x 256 TMEM columns), i.e. 22 % less L2 traffic for that pass: +2..8 % on the Cout >= 256 layers
+    // (profiles/r01_wgrad_n256.log).
+    if (nco == 128 && p.npairs <= 2 && d->Cout >= 256) {
+      plan(256);
+      rc = launch_wgrad_halo_one<4, 256>(tmDY, tmX, p, stream);
+    } else if (nco == 128) {
+      plan(128);
+      rc = launch_wgrad_halo_one<7, 128>(tmDY, tmX, p, stream);
+    } else {
+      plan(64);
+      rc = launch_wgrad_halo_one<8, 64>(tmDY, tmX, p, stream);
+    }
     if (rc) return rc;
   }
   const long long total = (long long)d->Cout * d->Cin * p.RS;
