@@ -83,6 +83,33 @@ int jg_conv2d_wgrad(const jg_conv_desc* d, const void* x, const void* dy, int ld
  *   w_dgrad [Cin][R*S][Cout8]   taps flipped (B operand of the stride-1 dgrad), may be NULL */
 int jg_pack_conv_weight(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int R, int S,
                         jg_stream_t stream);
+/* Raw split-K accumulation for a trainer that keeps one persistent fp32 accumulator per convolution: adds this
+ * call's partial sums into acc (R*S*Cin*Cout floats; NOT zeroed, NOT permuted) and reports the accumulator layout in
+ * *layout (0: [R*S][Cin][Cout], 1: [Cout][R*S][Cin]; fixed for a given descriptor). */
+int jg_conv2d_wgrad_acc(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* acc, int* layout,
+                        jg_stream_t stream);
+
+/* Batched weight kernels: ONE launch for all convolutions of a model.  items_dev / tile_start_dev are DEVICE arrays;
+ * tile_start_dev[i] = first tile of item i, with jg_weight_tiles(Cout, Cin, R*S) tiles per item.
+ *   jg_pack_conv_weights_batched: jg_pack_conv_weight for n convolutions (w_dgrad may be NULL per item).
+ *   jg_wgrad_unpack_batched: dw_oihw += acc (permuted from its layout), then acc = 0 — the end of the backward pass
+ *   for accumulators filled by jg_conv2d_wgrad_acc. */
+typedef struct {
+  const float* w;  /* fp32 OIHW */
+  void* wf;        /* bf16 [Cout8][R*S][Cin8] */
+  void* wd;        /* bf16 [Cin8][R*S][Cout8], taps flipped, or NULL */
+  int Cout, Cin, RS, Cin8, Cout8, pad_;
+} jg_pack_item;
+typedef struct {
+  float* acc;  /* raw accumulator */
+  float* dw;   /* fp32 OIHW gradient, accumulated into */
+  int Cout, Cin, RS, layout;
+} jg_unpack_item;
+int jg_weight_tiles(int Cout, int Cin, int RS);
+int jg_pack_conv_weights_batched(const jg_pack_item* items_dev, const int* tile_start_dev, int n, int total_tiles,
+                                 jg_stream_t stream);
+int jg_wgrad_unpack_batched(const jg_unpack_item* items_dev, const int* tile_start_dev, int n, int total_tiles,
+                            jg_stream_t stream);
 /* fp32 OHWI wgrad accumulator -> fp32 OIHW gradient (dst = beta*dst + src). */
 int jg_unpack_conv_wgrad(const float* dw_ohwi, float* dw_oihw, int Cout, int Cin, int R, int S, float beta,
                          jg_stream_t stream);

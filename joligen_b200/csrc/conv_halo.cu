@@ -682,7 +682,9 @@ int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int 
     p.total_items = pairs * p.ksplit;
   };
   p.acc = ws;
-  JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)p.RS * d->Cin * d->Cout, stream));
+  // dw_oihw == nullptr: raw mode (jg_conv2d_wgrad_acc): the caller owns a persistent [R*S][Cin][Cout] accumulator that
+  // is neither zeroed nor unpacked here
+  if (dw_oihw) JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)p.RS * d->Cin * d->Cout, stream));
 
   CUtensorMap tmDY, tmX;
   int rc;
@@ -722,9 +724,11 @@ int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int 
     }
     if (rc) return rc;
   }
-  const long long total = (long long)d->Cout * d->Cin * p.RS;
-  unpack_hwio_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ws, dw_oihw, d->Cout, d->Cin, p.RS, beta);
-  JG_LAUNCH_CHECK();
+  if (dw_oihw) {
+    const long long total = (long long)d->Cout * d->Cin * p.RS;
+    unpack_hwio_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ws, dw_oihw, d->Cout, d->Cin, p.RS, beta);
+    JG_LAUNCH_CHECK();
+  }
   return JG_OK;
 }
 

@@ -547,20 +547,26 @@ extern "C" int jg_conv2d_fwd(const jg_conv_desc* d, const void* x, const void* w
   }
 }
 
-extern "C" int jg_conv2d_wgrad(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* ws,
-                               float* dw_oihw, float beta, jg_stream_t stream_) {
+// Shared by jg_conv2d_wgrad (zero + accumulate + unpack into dw_oihw) and jg_conv2d_wgrad_acc (dw_oihw == nullptr:
+// accumulate into the caller's persistent raw accumulator; *layout = 0: [R*S][Cin][Cout], 1: [Cout][R*S][Cin]).
+static int conv2d_wgrad_impl(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* ws, float* dw_oihw,
+                             float beta, int* layout, jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_desc(d);
   if (rc) return rc;
-  JG_CHECK(x && dy && ws && dw_oihw, JG_ERR_INVALID, "conv_wgrad: null pointer");
+  JG_CHECK(x && dy && ws, JG_ERR_INVALID, "conv_wgrad: null pointer");
   JG_CHECK(lddy % 8 == 0 && lddy >= d->Cout, JG_ERR_INVALID, "conv_wgrad: bad lddy %d", lddy);
   static const bool no_halo = getenv("JG_NO_HALO") != nullptr;
   if (!no_halo) {
     rc = launch_wgrad_halo(d, x, dy, lddy, ws, dw_oihw, beta, stream);
-    if (rc != JG_ERR_UNSUPPORTED) return rc;
+    if (rc != JG_ERR_UNSUPPORTED) {
+      if (layout) *layout = 0;
+      return rc;
+    }
   }
+  if (layout) *layout = 1;
   float* dw = ws;  // generic kernel: OHWI accumulator
-  JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)d->R * d->S * d->Cin * d->Cout, stream));
+  if (dw_oihw) JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)d->R * d->S * d->Cin * d->Cout, stream));
 
   ConvWgradParams p{};
   p.Cin = d->Cin; p.Cout = d->Cout; p.RS = d->R * d->S; p.S = d->S; p.pad = d->pad; p.stride = d->stride;
@@ -610,5 +616,18 @@ extern "C" int jg_conv2d_wgrad(const jg_conv_desc* d, const void* x, const void*
     default: rc = launch_wgrad<1, 8>(tmDY, tmX, p, stream); break;
   }
   if (rc) return rc;
+  if (!dw_oihw) return JG_OK;
   return jg_unpack_conv_wgrad(ws, dw_oihw, d->Cout, d->Cin, d->R, d->S, beta, stream_);
+}
+
+extern "C" int jg_conv2d_wgrad(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* ws,
+                               float* dw_oihw, float beta, jg_stream_t stream_) {
+  JG_CHECK(dw_oihw, JG_ERR_INVALID, "conv_wgrad: null pointer");
+  return conv2d_wgrad_impl(d, x, dy, lddy, ws, dw_oihw, beta, nullptr, stream_);
+}
+
+extern "C" int jg_conv2d_wgrad_acc(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* acc,
+                                   int* layout, jg_stream_t stream_) {
+  JG_CHECK(layout, JG_ERR_INVALID, "conv_wgrad_acc: null layout pointer");
+  return conv2d_wgrad_impl(d, x, dy, lddy, acc, nullptr, 0.f, layout, stream_);
 }

@@ -35,16 +35,19 @@ def make_conv_desc(x, cout, r, s, stride=1, pad=None, ldy=None, act=L.ACT_NONE, 
     return d
 
 
-def pack_conv_weight(w_oihw, want_dgrad=True):
-    """fp32 OIHW -> (bf16 [Cout8][RS][Cin8], bf16 [Cin8][RS][Cout8] or None)."""
+def pack_conv_weight(w_oihw, want_dgrad=True, out=None):
+    """fp32 OIHW -> (bf16 [Cout8][RS][Cin8], bf16 [Cin8][RS][Cout8] or None); out = (wf, wd) buffers to refill."""
     cout, cin, r, s = w_oihw.shape
     w = w_oihw.detach().contiguous().float()
     cin8, cout8 = (cin + 7) // 8 * 8, (cout + 7) // 8 * 8
-    # rows cout..cout8-1 of wf stay zero (the kernels see round_up(Cout, 8) output channels)
-    alloc = torch.zeros if cout8 != cout else torch.empty
-    wf = alloc((cout8, r * s, cin8), dtype=torch.bfloat16, device=w.device)
-    alloc_d = torch.zeros if cin8 != cin else torch.empty
-    wd = alloc_d((cin8, r * s, cout8), dtype=torch.bfloat16, device=w.device) if want_dgrad else None
+    if out is not None:
+        wf, wd = out
+    else:
+        # rows cout..cout8-1 of wf stay zero (the kernels see round_up(Cout, 8) output channels)
+        alloc = torch.zeros if cout8 != cout else torch.empty
+        wf = alloc((cout8, r * s, cin8), dtype=torch.bfloat16, device=w.device)
+        alloc_d = torch.zeros if cin8 != cin else torch.empty
+        wd = alloc_d((cin8, r * s, cout8), dtype=torch.bfloat16, device=w.device) if want_dgrad else None
     L.call("jg_pack_conv_weight", L.ptr(w), L.ptr(wf), L.ptr(wd), cout, cin, r, s, L.stream())
     return wf, wd
 
@@ -91,6 +94,50 @@ def conv2d_wgrad(x, dy, cout, r, s, stride=1, pad=None, out=None, beta=0.0):
     L.call("jg_conv2d_wgrad", ctypes.byref(d), L.ptr(x), L.ptr(dy), _ld(dy), L.ptr(ws), L.ptr(out), float(beta),
            L.stream())
     return out
+
+
+def conv2d_wgrad_acc(x, dy, cout, r, s, acc, stride=1, pad=None):
+    """Raw split-K accumulation into the persistent fp32 accumulator `acc` (flat, R*S*Cin*Cout).  Returns the layout
+    code of the accumulator (0: [RS][Cin][Cout], 1: [Cout][RS][Cin])."""
+    if pad is None:
+        pad = (r - 1) // 2
+    d = make_conv_desc(x, cout, r, s, stride, pad)
+    layout = ctypes.c_int(-1)
+    L.call("jg_conv2d_wgrad_acc", ctypes.byref(d), L.ptr(x), L.ptr(dy), _ld(dy), L.ptr(acc), ctypes.byref(layout),
+           L.stream())
+    return layout.value
+
+
+def _device_table(structs, device):
+    """ctypes struct array -> uint8 device tensor (kept alive by the caller)."""
+    arr = (type(structs[0]) * len(structs))(*structs)
+    raw = bytes(arr)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+
+class WeightTable:
+    """Device-side item table + tile prefix sums for the batched pack / unpack launches."""
+
+    def __init__(self, items, dims, device):
+        lib = L.load()
+        starts, tot = [], 0
+        for (cout, cin, rs) in dims:
+            starts.append(tot)
+            tot += lib.jg_weight_tiles(cout, cin, rs)
+        self.n = len(items)
+        self.total_tiles = tot
+        self.items = _device_table(items, device)
+        self.tile_start = torch.tensor(starts, dtype=torch.int32, device=device)
+
+
+def pack_conv_weights_batched(table):
+    L.call("jg_pack_conv_weights_batched", L.ptr(table.items), L.ptr(table.tile_start), table.n, table.total_tiles,
+           L.stream())
+
+
+def wgrad_unpack_batched(table):
+    L.call("jg_wgrad_unpack_batched", L.ptr(table.items), L.ptr(table.tile_start), table.n, table.total_tiles,
+           L.stream())
 
 
 def bias_grad(dy):

@@ -32,6 +32,15 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class PackItem(ctypes.Structure):  # jg_pack_item
+    _fields_ = [("w", c_p), ("wf", c_p), ("wd", c_p), ("Cout", c_int), ("Cin", c_int), ("RS", c_int),
+                ("Cin8", c_int), ("Cout8", c_int), ("pad_", c_int)]
+
+
+class UnpackItem(ctypes.Structure):  # jg_unpack_item
+    _fields_ = [("acc", c_p), ("dw", c_p), ("Cout", c_int), ("Cin", c_int), ("RS", c_int), ("layout", c_int)]
+
+
 ACT_NONE, ACT_RELU, ACT_LRELU02, ACT_TANH, ACT_SILU = 0, 1, 2, 3, 4
 
 # name -> argtypes (restype is always int unless listed in _RESTYPES)
@@ -41,6 +50,10 @@ _SIGNATURES = {
     "jg_conv2d_fwd": [ctypes.POINTER(ConvDesc), c_p, c_p, c_p, c_p, c_p, c_p],
     "jg_conv2d_wgrad": [ctypes.POINTER(ConvDesc), c_p, c_p, c_int, c_p, c_p, c_f, c_p],
     "jg_pack_conv_weight": [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],
+    "jg_conv2d_wgrad_acc": [ctypes.POINTER(ConvDesc), c_p, c_p, c_int, c_p, ctypes.POINTER(c_int), c_p],
+    "jg_pack_conv_weights_batched": [c_p, c_p, c_int, c_int, c_p],
+    "jg_wgrad_unpack_batched": [c_p, c_p, c_int, c_int, c_p],
+    "jg_weight_tiles": [c_int, c_int, c_int],
     "jg_unpack_conv_wgrad": [c_p, c_p, c_int, c_int, c_int, c_int, c_f, c_p],
     "jg_bias_grad": [c_p, c_i64, c_int, c_int, c_p, c_p],
     "jg_nchw_f32_to_nhwc_bf16": [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],

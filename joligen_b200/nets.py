@@ -31,34 +31,93 @@ def invalidate_packed_weights():
 
 
 class ConvPack:
-    """bf16 implicit-GEMM copies of one conv's fp32 master weight, refreshed when the weight changes."""
+    """bf16 implicit-GEMM copies of one conv's fp32 master weight, refreshed when the weight changes.
+    A trainer may take over (`managed`): it owns persistent packed buffers and refreshes ALL convolutions of the
+    model with one batched launch after every optimizer step (WeightPackSet); get() then only hands them out."""
 
     def __init__(self, conv):
         self.conv = conv
         self.key = None
         self.packed = None
+        self.managed_epoch = None  # _PACK_EPOCH value at which a trainer's batched pack last refreshed this entry
+
+    def _weight4(self):
+        w4 = self.conv.weight.detach()
+        while w4.dim() < 4:  # Conv1d k=1 / nn.Linear
+            w4 = w4.unsqueeze(-1)
+        return w4
+
+    def _bias_padded(self):
+        b = self.conv.bias
+        if b is None:
+            return None
+        cout = b.shape[0]
+        cout8 = (cout + 7) // 8 * 8
+        if cout8 != cout:
+            bias_p = torch.zeros(cout8, dtype=torch.float32, device=b.device)
+            bias_p[:cout] = b.detach()
+            return bias_p
+        return b.detach()  # aliases the parameter storage: always current
 
     def get(self):
+        if self.managed_epoch is not None and self.managed_epoch == _PACK_EPOCH[0]:
+            return self.packed
         w = self.conv.weight
         b = self.conv.bias
         key = (w._version, _PACK_EPOCH[0], w.data_ptr(), None if b is None else (b._version, b.data_ptr()))
         if key != self.key:
-            w4 = w.detach()
-            while w4.dim() < 4:  # Conv1d k=1 / nn.Linear
-                w4 = w4.unsqueeze(-1)
-            wf, wd = K.pack_conv_weight(w4, want_dgrad=True)
-            bias_p = None
-            if b is not None:
-                cout = b.shape[0]
-                cout8 = (cout + 7) // 8 * 8
-                if cout8 != cout:
-                    bias_p = torch.zeros(cout8, dtype=torch.float32, device=b.device)
-                    bias_p[:cout] = b.detach()
-                else:
-                    bias_p = b.detach()  # aliases the parameter storage: always current
-            self.packed = (wf, wd, bias_p)
+            # a managed entry keeps its persistent buffers (the trainer's batched table points at them)
+            out = (self.packed[0], self.packed[1]) if (self.managed_epoch is not None and self.packed) else None
+            wf, wd = K.pack_conv_weight(self._weight4(), want_dgrad=True, out=out)
+            self.packed = (wf, wd, self._bias_padded())
             self.key = key
         return self.packed
+
+
+def conv_packs(module):
+    """Every ConvPack reachable from `module`'s sub-modules (attributes holding a ConvPack or a list of them)."""
+    out, seen = [], set()
+    for m in module.modules():
+        for v in vars(m).values():
+            for c in (v if isinstance(v, (list, tuple)) else (v,)):
+                if isinstance(c, ConvPack) and id(c) not in seen:
+                    seen.add(id(c))
+                    out.append(c)
+    return out
+
+
+class WeightPackSet:
+    """All convolutions of a model packed by ONE launch (jg_pack_conv_weights_batched).  The packed buffers are
+    persistent; call refresh() after the master weights changed (the trainer does, after every optimizer step)."""
+
+    def __init__(self, module):
+        self.packs = [p for p in conv_packs(module) if p.conv.weight.is_cuda]
+        items, dims = [], []
+        for p in self.packs:
+            w4 = p._weight4()
+            cout, cin, r, s = w4.shape
+            if not w4.is_contiguous() or w4.dtype != torch.float32:
+                raise RuntimeError("WeightPackSet: master weights must be contiguous fp32")
+            wf, wd = K.pack_conv_weight(w4, want_dgrad=True)  # allocates (zero-padded) and fills once
+            p.packed = (wf, wd, p._bias_padded())
+            cin8, cout8 = (cin + 7) // 8 * 8, (cout + 7) // 8 * 8
+            items.append(L.PackItem(w4.data_ptr(), wf.data_ptr(), wd.data_ptr(), cout, cin, r * s, cin8, cout8, 0))
+            dims.append((cout, cin, r * s))
+        self.table = K.WeightTable(items, dims, self.packs[0].conv.weight.device) if self.packs else None
+        self._mark()
+
+    def _mark(self):
+        for p in self.packs:
+            p.managed_epoch = _PACK_EPOCH[0]
+
+    def refresh(self):
+        if self.table is not None:
+            K.pack_conv_weights_batched(self.table)
+            for p in self.packs:  # padded biases are copies
+                b = p.conv.bias
+                if b is not None and p.packed[2] is not None and p.packed[2].data_ptr() != b.data_ptr():
+                    p.packed[2][:b.shape[0]].copy_(b.detach())
+        self._mark()
 
 
 def _conv(x, conv, pack, residual=None, res_scale=1.0, out=None):

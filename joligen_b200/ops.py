@@ -72,7 +72,12 @@ class Conv2dFn(torch.autograd.Function):
                 g = ctx.sink[0].grad
                 if g is not None and not (g.is_contiguous() and g.dtype == torch.float32 and g.numel() == cout * cin * r * s):
                     g = None
-            if g is not None:
+            stage = getattr(ctx.sink[0], "_jg_wstage", None) if (g is not None) else None
+            if stage is not None and stage.enabled:
+                # trainer-owned persistent split-K accumulator: raw accumulation now, ONE batched unpack into .grad
+                # for all convolutions at the end of the backward pass (WgradStage.flush)
+                stage.layout = K.conv2d_wgrad_acc(x, dy, cout8, r, s, stage.acc, stride=stride, pad=pad)
+            elif g is not None:
                 # the unpack epilogue of the wgrad adds into the existing .grad (beta = 1): no separate
                 # gradient tensor, no autograd accumulation kernel
                 K.conv2d_wgrad(x, dy, cout8, r, s, stride=stride, pad=pad, out=g, beta=1.0)

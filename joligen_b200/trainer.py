@@ -17,6 +17,7 @@ import torch
 
 from . import dp
 from . import kernels as K
+from . import lib as L
 from . import nets
 
 
@@ -52,6 +53,59 @@ class FlatParams:
         return {n: flat[o:o + p.numel()].view(p.shape) for n, p, o in zip(self.names, self.params, self.offsets)}
 
 
+class _WgradSlot:
+    __slots__ = ("acc", "layout", "param", "dims", "owner")
+
+    def __init__(self, acc, param, dims, owner):
+        self.acc, self.layout, self.param, self.dims, self.owner = acc, None, param, dims, owner
+
+    @property
+    def enabled(self):  # only between WgradStage.begin() and flush(): plain autograd use of the model stays immediate
+        return self.owner.active
+
+
+class WgradStage:
+    """Persistent fp32 split-K accumulators for every convolution weight of a model (one flat buffer).  The wgrad
+    kernels add their partial tiles into a slot (no per-call memset, no per-call permutation); flush() — ONE launch at
+    the end of the backward pass — permutes every slot into the parameter's OIHW .grad (+=) and zeroes it again."""
+
+    def __init__(self, module):
+        slots, total = [], 0
+        for pack in nets.conv_packs(module):
+            w = pack.conv.weight
+            w4 = pack._weight4()
+            cout, cin, r, s = w4.shape
+            if cout % 8 or cin % 8 or not w.is_cuda:
+                continue  # padded channels: Conv2dFn uses its immediate path for these
+            slots.append((w, (cout, cin, r * s), total))
+            total += (w.numel() + 63) // 64 * 64
+        self.buf = torch.zeros(max(total, 1), dtype=torch.float32, device=slots[0][0].device) if slots else None
+        self.slots = []
+        for w, dims, off in slots:
+            slot = _WgradSlot(self.buf[off:off + w.numel()], w, dims, self)
+            w._jg_wstage = slot
+            self.slots.append(slot)
+        self._table = None
+        self._table_key = None
+        self.active = False
+
+    def begin(self):
+        self.active = True
+
+    def flush(self):
+        self.active = False
+        active = [sl for sl in self.slots if sl.layout is not None and sl.param.grad is not None]
+        if not active:
+            return
+        key = tuple((id(sl), sl.layout, sl.param.grad.data_ptr()) for sl in active)
+        if key != self._table_key:
+            items = [L.UnpackItem(sl.acc.data_ptr(), sl.param.grad.data_ptr(), sl.dims[0], sl.dims[1], sl.dims[2],
+                                  sl.layout) for sl in active]
+            self._table = K.WeightTable(items, [sl.dims for sl in active], self.buf.device)
+            self._table_key = key
+        K.wgrad_unpack_batched(self._table)
+
+
 class PaletteTrainer:
     def __init__(self, netG_A, lr=2e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, optim="adamw",
                  ema=True, ema_beta=0.999, iter_size=1, lambda_G=1.0, use_minsnr=False, loss="MSE",
@@ -61,6 +115,9 @@ class PaletteTrainer:
         self.device = torch.device(device if device is not None else "cuda")
         self.netG_A = netG_A.to(self.device)
         self.flat = FlatParams(self.netG_A)
+        # all conv weights: one batched bf16 re-pack after each optimizer step, one batched wgrad unpack per backward
+        self.packset = nets.WeightPackSet(self.netG_A)
+        self.wstage = WgradStage(self.netG_A)
         self.exp_avg = torch.zeros_like(self.flat.data)
         self.exp_avg_sq = torch.zeros_like(self.flat.data)
         self.ema = torch.zeros_like(self.flat.data) if ema else None
@@ -114,7 +171,7 @@ class PaletteTrainer:
 
     def broadcast_parameters(self):
         dp.broadcast_(self.flat.data, self.pg)
-        nets.invalidate_packed_weights()
+        self.packset.refresh()
 
     # -- step -----------------------------------------------------------------------------------
     def compute_palette_loss(self, noise=None, t=None, u=None):
@@ -126,7 +183,9 @@ class PaletteTrainer:
     def _forward_backward(self, noise=None, t=None, u=None):
         self.flat.rebind_grads()
         loss = self.compute_palette_loss(noise=noise, t=t, u=u)
+        self.wstage.begin()
         (loss / self.iter_size).backward()
+        self.wstage.flush()
         # hand out a graph-free scalar: a retained autograd graph would keep this iteration's
         # AccumulateGrad nodes (and their stream binding) alive across iterations / graph capture
         self.loss_G_tot = loss.detach()
@@ -140,7 +199,7 @@ class PaletteTrainer:
                          ema_init=not self.ema_started, **self.hp)
         self.ema_started = True
         self.flat.grad.zero_()
-        nets.invalidate_packed_weights()
+        self.packset.refresh()
 
     def _capture(self):
         """Capture the step into CUDA graphs (called once, after `graph_warmup` eager steps)."""
