@@ -118,6 +118,8 @@ class PaletteTrainer:
         # all conv weights: one batched bf16 re-pack after each optimizer step, one batched wgrad unpack per backward
         self.packset = nets.WeightPackSet(self.netG_A)
         self.wstage = WgradStage(self.netG_A)
+        self._loose = [(p, self.flat.grad[o:o + p.numel()].view(p.shape))
+                       for p, o in zip(self.flat.params, self.flat.offsets) if not hasattr(p, "_jg_wstage")]
         self.exp_avg = torch.zeros_like(self.flat.data)
         self.exp_avg_sq = torch.zeros_like(self.flat.data)
         self.ema = torch.zeros_like(self.flat.data) if ema else None
@@ -183,9 +185,19 @@ class PaletteTrainer:
     def _forward_backward(self, noise=None, t=None, u=None):
         self.flat.rebind_grads()
         loss = self.compute_palette_loss(noise=noise, t=t, u=u)
+        # Parameters whose gradient arrives as a tensor (norm gains, biases, linears, padded convs: ~250 of them)
+        # start the backward WITHOUT a .grad: autograd then just keeps the incoming tensor instead of launching one
+        # tiny add kernel per parameter, and a single multi-tensor add folds them into the flat gradient buffer.
+        for p, _ in self._loose:
+            p.grad = None
         self.wstage.begin()
         (loss / self.iter_size).backward()
         self.wstage.flush()
+        pairs = [(v, p.grad) for p, v in self._loose if p.grad is not None]
+        if pairs:
+            torch._foreach_add_([v for v, _ in pairs], [g.reshape(v.shape) for v, g in pairs])
+        for p, v in self._loose:
+            p.grad = v
         # hand out a graph-free scalar: a retained autograd graph would keep this iteration's
         # AccumulateGrad nodes (and their stream binding) alive across iterations / graph capture
         self.loss_G_tot = loss.detach()
