@@ -275,7 +275,7 @@ def main():
         e0.record()
         yield
         e1.record()
-        if name in ("jg_conv2d_fwd", "jg_conv2d_wgrad"):
+        if name in ("jg_conv2d_fwd", "jg_conv2d_wgrad", "jg_conv2d_wgrad_acc"):
             d = cargs[0]._obj
             flops = 2.0 * d.N * d.Ho * d.Wo * d.Cout * d.Cin * d.R * d.S
             recs.append((name, flops, e0, e1))
