@@ -49,7 +49,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int b_tiles = B_RESIDENT ? p.RS * k_slabs : SB;
   uint8_t* stage = smB + static_cast<size_t>(b_tiles) * B_BYTES;  // 2 x 16 KB output staging (1024-byte aligned)
   uint8_t* res_stage = stage + (TMA_STORE ? 2 * kStageBytes : 0);  // 2 x 16 KB residual tiles (RES_TMA)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(res_stage + (RES_TMA ? 2 * kStageBytes : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(res_stage + ((RES_TMA && p.res) ? 2 * kStageBytes : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + SA;
   uint64_t* b_full = bars + 2 * SA;           // SB entries (entry 0 only when resident)
@@ -309,7 +309,7 @@ template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
 static int halo_smem_bytes(const HaloParams& hp) {
   const int b_tiles = B_RESIDENT ? hp.c.RS * hp.c.kc_blocks : SB;
   return SA * hp.a_stage_bytes + b_tiles * BLOCK_N * 128 + (BLOCK_N >= 64 ? 2 * kStageBytes : 0) +
-         (BLOCK_N == 64 ? 2 * kStageBytes : 0) + (2 * SA + 2 * SB + 8) * 8 + (((hp.c.Cout + 64) * 4 + 127) / 128) * 128 + 1024;
+         ((BLOCK_N == 64 && hp.c.res) ? 2 * kStageBytes : 0) + (2 * SA + 2 * SB + 8) * 8 + (((hp.c.Cout + 64) * 4 + 127) / 128) * 128 + 1024;
 }
 
 template <int BLOCK_N, int SA, int SB, bool B_RESIDENT, int KS>
@@ -401,15 +401,19 @@ int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed,
     rc = make_tmap_bf16(&tmR, residual, 4, dims, strides, box, es);
     if (rc) return rc;
   }
-  // resident weights: one N tile and all (slab, tap) tiles fit next to the A ring and the staging buffers
+  // resident weights: one N tile and all (slab, tap) tiles fit next to the A ring and the staging buffers (the
+  // residual staging exists only when there is a residual; two A stages are enough when a slab's 36 MMAs cover the
+  // load latency, which lets the 128 -> 64 layers at 256^2 keep their 147 KB of weights resident too)
   const bool resident = p.n_tiles == 1 && (block_n == 64 ? halo_smem_bytes<64, 3, 1, true>(hp)
                                                          : halo_smem_bytes<32, 4, 1, true>(hp)) <= 232448;
+  const bool resident2 = p.n_tiles == 1 && block_n == 64 && halo_smem_bytes<64, 2, 1, true>(hp) <= 232448;
   switch (block_n) {
     case 256: return launch_halo<256, 2, 4, false>(tmA, tmB, tmY, tmR, hp, stream);
     case 128: return launch_halo<128, 3, 6, false>(tmA, tmB, tmY, tmR, hp, stream);
     case 64:
-      return resident ? launch_halo<64, 3, 1, true>(tmA, tmB, tmY, tmR, hp, stream)
-                      : launch_halo<64, 3, 7, false>(tmA, tmB, tmY, tmR, hp, stream);
+      if (resident) return launch_halo<64, 3, 1, true>(tmA, tmB, tmY, tmR, hp, stream);
+      if (resident2) return launch_halo<64, 2, 1, true>(tmA, tmB, tmY, tmR, hp, stream);
+      return launch_halo<64, 3, 7, false>(tmA, tmB, tmY, tmR, hp, stream);
     default:
       return resident ? launch_halo<32, 4, 1, true>(tmA, tmB, tmY, tmR, hp, stream)
                       : launch_halo<32, 4, 8, false>(tmA, tmB, tmY, tmR, hp, stream);

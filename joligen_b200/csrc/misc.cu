@@ -41,8 +41,17 @@ linear_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ w, c
   for (int i0 = 0; i0 < I; i0 += 32) {
     const int i = i0 + il;
     float acc = 0.f;
-    if (i < I)
-      for (int o = slice; o < O; o += 8) acc += dy[(size_t)b * O + o] * w[(size_t)o * I + i];
+    if (i < I) {
+      // 8 independent partial sums: the loads of 8 consecutive iterations are in flight together
+      float a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      int o = slice;
+      for (; o + 56 < O; o += 64) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a8[k] = fmaf(dy[(size_t)b * O + o + 8 * k], w[(size_t)(o + 8 * k) * I + i], a8[k]);
+      }
+      for (; o < O; o += 8) a8[0] = fmaf(dy[(size_t)b * O + o], w[(size_t)o * I + i], a8[0]);
+      acc = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+    }
     part[slice][il] = acc;
     __syncthreads();
     if (slice == 0 && i < I) {
@@ -63,11 +72,12 @@ __global__ void linear_bwd_dw_kernel(const float* __restrict__ x, const float* _
   if (idx >= O * I) return;
   const int o = idx / I, i = idx % I;
   float acc = 0.f, accb = 0.f;
+#pragma unroll 8
   for (int b = 0; b < B; ++b) {
     float xv = x[b * I + i];
     if (act_in == JG_ACT_SILU) xv = silu_f(xv);
     const float d = dy[(size_t)b * O + o];
-    acc += d * xv;
+    acc = fmaf(d, xv, acc);
     accb += d;
   }
   dw[idx] = acc;
