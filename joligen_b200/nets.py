@@ -538,23 +538,50 @@ class DiffusionGenerator(nn.Module):
         return t, sample_gammas, w
 
     def forward_nhwc(self, y_0, y_cond, mask, noise, t=None, u=None):
-        """Returns (noise, noise_hat NHWC bf16 [B,H,W,8], min_snr_w [B])."""
+        """Returns (noise, noise_hat NHWC bf16 [N,H,W,8], min_snr_w [B]).  Video clips [B,F,C,H,W] (UNetVid,
+        diffusion_generator.py:460-463, 497-500) are folded to N = B*F frames: one (t, gamma) draw per clip, the
+        per-frame work is identical to the image path; noise is returned in the folded [N,C,H,W] layout."""
         b = y_0.shape[0]
+        frames = 0
+        if y_0.dim() == 5:
+            frames = y_0.shape[1]
+            if noise is None:
+                noise = torch.randn_like(y_0)
+            fold = lambda v: None if v is None else v.reshape((b * frames,) + tuple(v.shape[2:]))  # noqa: E731
+            y_0, y_cond, mask, noise = fold(y_0), fold(y_cond), fold(mask), fold(noise)
+            self.denoise_fn.model._clip["frames"] = frames
         if noise is None:
             noise = torch.randn_like(y_0)
         _, sample_gammas, w = self.sample_noise_level(b, y_0.device, t, u)
         emb = self.compute_gammas(sample_gammas)
+        g_per_image = sample_gammas.reshape(b)
+        if frames:
+            g_per_image = g_per_image.repeat_interleave(frames)
         x = K.noise_pack(y_0.contiguous().float(), y_cond.contiguous().float(), noise.contiguous().float(),
-                         None if mask is None else mask.contiguous(), sample_gammas.reshape(b).contiguous(),
+                         None if mask is None else mask.contiguous(), g_per_image.contiguous(),
                          ld=(2 * y_0.shape[1] + 7) // 8 * 8)
         noise_hat = self.denoise_fn.model.forward_nhwc(x, emb)
         return noise, noise_hat, w
 
     def forward(self, y_0, y_cond, mask, noise, cls=None, ref=None, dropout_prob=0.0, t=None, u=None):
-        if y_0.dim() != 4:
-            raise NotImplementedError("B200 DiffusionGenerator: video (5-D) inputs are not supported yet")
+        shape5 = tuple(y_0.shape) if y_0.dim() == 5 else None
+        c = y_0.shape[2] if shape5 else y_0.shape[1]
         noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u)
-        return noise, ops.to_nchw(noise_hat, y_0.shape[1]), w.view(-1, 1, 1, 1)
+        noise_hat = ops.to_nchw(noise_hat, c)
+        if shape5:
+            noise, noise_hat = noise.reshape(shape5), noise_hat.reshape(shape5)
+        return noise, noise_hat, w.view(-1, 1, 1, 1)
+
+    def forward_loss(self, y_0, y_cond, mask, noise=None, lambda_G=1.0, use_minsnr=False, l1=False, t=None, u=None):
+        """compute_palette_loss fused: the UNet output stays NHWC bf16 and feeds the eps-loss kernel directly."""
+        if y_0.dim() == 5 and use_minsnr:
+            raise NotImplementedError("B200 DiffusionGenerator: min-SNR weighting with video clips")
+        b5 = y_0.shape[0] * y_0.shape[1] if y_0.dim() == 5 else None
+        noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u)
+        if b5 is not None and mask is not None:
+            mask = mask.reshape((b5,) + tuple(mask.shape[2:]))
+        return ops.palette_loss(noise_hat, noise.contiguous().float(), None if mask is None else mask.contiguous(),
+                                w.contiguous() if use_minsnr else None, lambda_G, l1)
 
     @torch.no_grad()
     def restoration_ddpm(self, y_cond, y_t=None, y_0=None, mask=None, sample_num=2, cls=None, guidance_scale=0.0,
@@ -646,12 +673,6 @@ class DiffusionGenerator(nn.Module):
                                          guidance_scale=guidance_scale, ref=ref)
         return self.restoration_ddim(y_cond, y_t=y_t, y_0=y_0, mask=mask, sample_num=sample_num, cls=cls,
                                      guidance_scale=guidance_scale, num_steps=ddim_num_steps, eta=ddim_eta, ref=ref)
-
-    def forward_loss(self, y_0, y_cond, mask, noise=None, lambda_G=1.0, use_minsnr=False, l1=False, t=None, u=None):
-        """compute_palette_loss fused: the UNet output stays NHWC bf16 and feeds the eps-loss kernel directly."""
-        noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u)
-        return ops.palette_loss(noise_hat, noise.contiguous().float(), None if mask is None else mask.contiguous(),
-                                w.contiguous() if use_minsnr else None, lambda_G, l1)
 
 
 def build_palette_generator(image_size=256, in_channel=6, inner_channel=64, out_channel=3, res_blocks=(2, 2, 2, 2),

@@ -82,5 +82,59 @@ def main():
     print("oracle vs reference: y rel max err %.2e, worst grad rel L2 err %.2e" % (err, gerr))
 
 
+def generator_inputs(cfg, batch, frames, seed):
+    g = torch.Generator().manual_seed(seed)
+    shp = (batch, frames, 3, cfg.image_size, cfg.image_size)
+    gt = (0.5 * torch.randn(shp, generator=g)).clamp(-1, 1)
+    mask = (torch.rand((batch, frames, 1, cfg.image_size, cfg.image_size), generator=g) > 0.6).long()
+    cond = gt * (1 - mask) + torch.randn(shp, generator=g) * mask
+    noise = torch.randn(shp, generator=g)
+    return gt, cond, mask, noise
+
+
+def generator_golden():
+    """cfg 5 end to end: DiffusionGenerator(PaletteDenoiseFn(UNetVid)) forward on a clip + the Palette loss + backward."""
+    from einops import rearrange
+    from models.modules.diffusion_generator import DiffusionGenerator
+    from models.modules.palette_denoise_fn import PaletteDenoiseFn
+    from oracle import palette_oracle as O
+    cfg = V.VidCfg(**CFG)
+    dn = PaletteDenoiseFn(model=build_reference(cfg), cond_embed_dim=cfg.cond_embed_dim, ref_embed_net="",
+                          conditioning="", nclasses=2)
+    net = DiffusionGenerator(denoise_fn=dn, sampling_method="ddpm", image_size=cfg.image_size, G_ngf=cfg.inner_channel,
+                             loading_backward_compatibility=False)
+    shapes = [(k, tuple(v.shape)) for k, v in net.named_parameters()]
+    params = V.init_params_from_shapes(shapes, seed=6)
+    missing, unexpected = net.load_state_dict(params, strict=False)
+    assert not unexpected and all(("gammas" in m or "posterior" in m or m.endswith("pos_encoder.pe")) for m in missing), \
+        (missing, unexpected)
+    batch, frames, rseed = 2, 4, 77
+    gt, cond, mask, noise = generator_inputs(cfg, batch, frames, seed=10)
+    torch.manual_seed(rseed)
+    noise_fh = rearrange(noise, "b f c h w -> b c (f h) w")
+    n_out, noise_hat, _ = net(y_0=gt, y_cond=cond, mask=mask, noise=noise_fh, cls=None, ref=None)
+    assert torch.equal(n_out, noise)
+    mb = torch.clamp(mask, min=0, max=1)
+    loss = torch.nn.MSELoss()(mb * n_out, mb * noise_hat)
+    loss.backward()
+    torch.manual_seed(rseed)
+    t, u = O.sample_t_gamma(cfg, batch)
+    grads = {k: {"sum": float(p.grad.double().sum()), "l2": float(p.grad.double().norm()),
+                 "head": p.grad.flatten()[:16].clone()} for k, p in net.named_parameters()}
+    torch.save({"cfg": CFG, "batch": batch, "frames": frames, "wseed": 6, "dseed": 10, "rseed": rseed, "t": t, "u": u,
+                "torch_version": str(torch.__version__), "shapes": shapes, "noise_hat": noise_hat.detach().clone(),
+                "loss": float(loss.detach()), "grads": grads}, os.path.join(GOLDEN, "vid_generator.pt"))
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    sd = V.add_buffers(leaves, cfg)
+    _, nh = V.diffusion_forward_vid(sd, gt, cond, mask, noise, t, u, cfg)
+    lo = torch.nn.MSELoss()(mb * noise, mb * nh)
+    lo.backward()
+    gerr = max(float((leaves[k].grad - p.grad).norm() / (p.grad.norm() + 1e-12)) for k, p in net.named_parameters())
+    print("vid_generator.pt: loss %.6f (oracle %.6f), noise_hat rel max err %.2e, worst grad rel L2 err %.2e" % (
+        float(loss), float(lo), float((nh - noise_hat).abs().max() / noise_hat.abs().max()), gerr))
+
+
 if __name__ == "__main__":
+    ref_stubs.install()
     main()
+    generator_golden()

@@ -95,6 +95,47 @@ def test_conv_residual_epilogue_and_stride2(K):
     assert rel(K.nhwc_to_nchw(y2), F.conv2d(x, bf16_round(wt), stride=2, padding=1)) < 1e-2
 
 
+STAGED_CASES = [
+    # n, h, w, cin, cout, k, stride  (both accumulator layouts, the N=128/256 second pass, 1x1 and strided generics)
+    (8, 16, 16, 64, 64, 3, 1), (8, 16, 16, 64, 128, 3, 1), (8, 8, 8, 128, 64, 1, 1), (8, 16, 16, 64, 64, 3, 2),
+    (2, 32, 32, 256, 256, 3, 1), (8, 16, 16, 192, 64, 3, 1), (2, 16, 16, 512, 1024, 1, 1),
+]
+
+
+def test_staged_wgrad_and_batched_pack_match_immediate(K):
+    """The trainer's path — raw split-K accumulation into persistent slots (jg_conv2d_wgrad_acc), ONE batched unpack
+    that adds into the OIHW gradients and re-zeroes the slots, ONE batched bf16 weight pack — against the immediate
+    per-convolution entry points, two accumulation rounds (the second checks the slots were left at zero)."""
+    from joligen_b200 import lib as L
+    g = torch.Generator().manual_seed(11)
+    work, unpack_items, pack_items, dims = [], [], [], []
+    for (n, h, w, cin, cout, k, stride) in STAGED_CASES:
+        pad = (k - 1) // 2
+        ho = (h + 2 * pad - k) // stride + 1
+        x = torch.randn(n, h, w, cin, generator=g).bfloat16().cuda()
+        dy = torch.randn(n, ho, ho, cout, generator=g).bfloat16().cuda()
+        wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).cuda()
+        ref = K.conv2d_wgrad(x, dy, cout, k, k, stride=stride, pad=pad)
+        acc = torch.zeros(cout * cin * k * k, device="cuda")
+        grad = torch.zeros(cout, cin, k, k, device="cuda")
+        wf_ref, wd_ref = K.pack_conv_weight(wt)
+        wf, wd = torch.zeros_like(wf_ref), torch.zeros_like(wd_ref)
+        work.append((x, dy, wt, ref, acc, grad, wf_ref, wd_ref, wf, wd, (cout, k, stride, pad)))
+        pack_items.append(L.PackItem(wt.data_ptr(), wf.data_ptr(), wd.data_ptr(), cout, cin, k * k, cin, cout, 0))
+        dims.append((cout, cin, k * k))
+    K.pack_conv_weights_batched(K.WeightTable(pack_items, dims, torch.device("cuda")))
+    for rnd in range(2):
+        unpack_items = []
+        for (x, dy, wt, ref, acc, grad, _, _, _, _, (cout, k, stride, pad)) in work:
+            lay = K.conv2d_wgrad_acc(x, dy, cout, k, k, acc, stride=stride, pad=pad)
+            unpack_items.append(L.UnpackItem(acc.data_ptr(), grad.data_ptr(), cout, x.shape[-1], k * k, lay))
+        K.wgrad_unpack_batched(K.WeightTable(unpack_items, dims, torch.device("cuda")))
+    for (x, dy, wt, ref, acc, grad, wf_ref, wd_ref, wf, wd, _) in work:
+        assert rel(grad / 2, ref) < 1e-5
+        assert float(acc.abs().max()) == 0.0
+        assert torch.equal(wf, wf_ref) and torch.equal(wd, wd_ref)
+
+
 GN_CASES = [
     # n, hw, c, groups, film, silu
     (2, 16, 64, 32, False, True),

@@ -202,3 +202,78 @@ def test_refattn_unet_forward_backward_vs_reference_golden(golden_dir):
         err = float((mine - refg).norm()) / max(float(refg.norm()), 2e-2 * scale)
         emu = abs(float(refg.norm()) - g["l2"]) / max(g["l2"], 2e-2 * scale)
         assert err < max(8e-2, 3 * emu), (k, err, emu)
+
+
+def test_video_generator_and_trainer_vs_reference_golden(golden_dir):
+    """cfg 5 end to end: DiffusionGenerator(PaletteDenoiseFn(UNetVid)) on a clip — loss and all gradients against the
+    unmodified reference's vectors / the bf16-emulating oracle; then the same clip through PaletteTrainer (flat
+    buffers, batched pack / unpack, fused AdamW+EMA): the first step's loss is the generator's and every parameter
+    moves by the first Adam step -lr * g / (|g| + eps) computed from the gradients checked above."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from joligen_b200 import nets
+    from joligen_b200.trainer import PaletteTrainer
+    from oracle import palette_oracle as O
+    from oracle import vid_oracle as V
+    from oracle.gen_golden_vid import generator_inputs
+    gold = torch.load(os.path.join(golden_dir, "vid_generator.pt"))
+    cfg = V.VidCfg(**gold["cfg"])
+    params = V.init_params_from_shapes(gold["shapes"], gold["wseed"])
+    gt, cond, mask, noise = generator_inputs(cfg, gold["batch"], gold["frames"], gold["dseed"])
+
+    def build():
+        unet = _build(cfg, {k[len("denoise_fn.model."):]: v for k, v in params.items()
+                            if k.startswith("denoise_fn.model.")}).cpu()
+        g = nets.DiffusionGenerator(nets.PaletteDenoiseFn(unet, cfg.cond_embed_dim), image_size=cfg.image_size,
+                                    G_ngf=cfg.inner_channel)
+        missing, unexpected = g.load_state_dict(params, strict=False)
+        assert not unexpected
+        return g.cuda()
+
+    g = build()
+    t, u = gold["t"].cuda(), gold["u"].cuda()
+    loss = g.forward_loss(gt.cuda(), cond.cuda(), mask.cuda(), noise=noise.cuda(), t=t, u=u)
+    loss.backward()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    O.EMULATE_BF16[0] = True
+    try:
+        _, nh = V.diffusion_forward_vid(V.add_buffers(leaves, cfg), gt, cond, mask, noise, gold["t"], gold["u"], cfg)
+        mb = torch.clamp(mask, min=0, max=1)
+        lo = torch.nn.MSELoss()(mb * noise, mb * nh)
+        lo.backward()
+    finally:
+        O.EMULATE_BF16[0] = False
+    assert abs(float(loss) - gold["loss"]) < 2e-2 * gold["loss"], (float(loss), gold["loss"])
+    assert abs(float(loss) - float(lo)) < 2e-2 * gold["loss"]
+    named = dict(g.named_parameters())
+    scale = max(x["l2"] for x in gold["grads"].values())
+    for k, x in gold["grads"].items():
+        mine = named[k].grad.detach().cpu().double()
+        refg = leaves[k].grad.double()
+        err = float((mine - refg).norm()) / max(float(refg.norm()), 2e-2 * scale)
+        emu = abs(float(refg.norm()) - x["l2"]) / max(x["l2"], 2e-2 * scale)
+        assert err < max(8e-2, 3 * emu), (k, err, emu)
+    # trainer on the clip
+    lr = 1e-3
+    net2 = build()
+    before = {k: v.detach().clone() for k, v in net2.named_parameters()}
+    tr = PaletteTrainer(net2, lr=lr, optim="adam", ema=True, ema_beta=0.9, device="cuda")
+    tr.set_input({"A": cond, "B": gt, "B_label_mask": mask})
+    l1 = float(tr.optimize_parameters(noise=noise.cuda(), t=t, u=u))
+    assert abs(l1 - float(loss)) < 1e-3 * abs(float(loss)), (l1, float(loss))
+    moved = 0
+    for k, pnew in net2.named_parameters():
+        gk = named[k].grad
+        step = pnew.detach() - before[k]
+        if gk is None:
+            assert float(step.abs().max()) == 0.0, k
+            continue
+        # away from zero the first Adam step is -lr * sign(g); small elements take the sign of the bf16 / summation
+        # order noise (two runs of the same backward differ by ~1.5% of each tensor's norm)
+        big = (gk.abs() > 0.25 * gk.abs().max()) & (gk.abs() > 1e-5)
+        if not bool(big.any()):
+            continue
+        err = float((step[big] + lr * torch.sign(gk[big])).abs().max()) / lr
+        assert err < 0.05, (k, err)
+        moved += 1
+    assert moved > 100, moved

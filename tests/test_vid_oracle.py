@@ -54,3 +54,22 @@ def test_b200_unetvid_has_reference_parameter_list(golden_dir):
     assert pes and all(torch.equal(sd[k], ref[k]) for k in pes)
     # zero-initialised proj_out, like zero_module() in the reference MotionModule
     assert all(float(p.abs().sum()) == 0.0 for k, p in net.named_parameters() if ".temporal_transformer.proj_out." in k)
+
+
+def test_vid_generator_oracle_matches_reference(golden_dir):
+    """cfg 5 end to end on CPU: DiffusionGenerator(PaletteDenoiseFn(UNetVid)) + Palette loss + backward."""
+    from oracle.gen_golden_vid import generator_inputs
+    gold = torch.load(os.path.join(golden_dir, "vid_generator.pt"))
+    cfg = V.VidCfg(**gold["cfg"])
+    params = V.init_params_from_shapes(gold["shapes"], gold["wseed"])
+    gt, cond, mask, noise = generator_inputs(cfg, gold["batch"], gold["frames"], gold["dseed"])
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    _, nh = V.diffusion_forward_vid(V.add_buffers(leaves, cfg), gt, cond, mask, noise, gold["t"], gold["u"], cfg)
+    assert float((nh - gold["noise_hat"]).abs().max()) < 1e-4 * float(gold["noise_hat"].abs().max())
+    mb = torch.clamp(mask, min=0, max=1)
+    loss = torch.nn.MSELoss()(mb * noise, mb * nh)
+    assert abs(float(loss) - gold["loss"]) < 1e-5 * gold["loss"]
+    loss.backward()
+    scale = max(g["l2"] for g in gold["grads"].values())
+    for k, g in gold["grads"].items():
+        assert abs(float(leaves[k].grad.double().norm()) - g["l2"]) < 1e-4 * max(g["l2"], 1e-3 * scale), k
