@@ -114,13 +114,15 @@ def accelerate(module: nn.Module) -> nn.Module:
         return module
     if cls == "DiffusionGenerator":
         ref_unet = module.denoise_fn.model
-        if type(ref_unet).__name__ != "UNet":
+        builders = {"UNet": _unet_from_reference, "UNetVid": _unetvid_from_reference,
+                    "UNetGeneratorRefAttn": _unetref_from_reference}
+        if type(ref_unet).__name__ not in builders:
             raise NotImplementedError("accelerate: DiffusionGenerator backbone %s is not on the B200 path yet"
                                       % type(ref_unet).__name__)
         if getattr(module.denoise_fn, "conditioning", ""):
             raise NotImplementedError("accelerate: conditioning %r is not supported yet"
                                       % module.denoise_fn.conditioning)
-        unet = _unet_from_reference(ref_unet)
+        unet = builders[type(ref_unet).__name__](ref_unet)
         dn = nets.PaletteDenoiseFn(model=unet, cond_embed_dim=module.denoise_fn.cond_embed_dim, conditioning="")
         new = nets.DiffusionGenerator(denoise_fn=dn, sampling_method=module.sampling_method,
                                       image_size=module.image_size)

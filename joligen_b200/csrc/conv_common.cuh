@@ -47,6 +47,9 @@ struct EpiPrefetch {
 
 // All threads: copy bias[0, Cout) (fp32, Cout a multiple of 8) into shared memory, followed by 64 zeros (the TMA-store
 // epilogue processes whole 64-channel slabs without per-group bounds checks).  Call before __syncthreads.
+// widest layer on the path: the video UNet's GEGLU projection at the bottleneck (512 * 4 * 2 output features)
+constexpr int kMaxCout = 4096;
+
 __device__ __forceinline__ void conv_stage_bias(const ConvFwdParams& p, float* s_bias) {
   if (p.bias)
     for (int i = threadIdx.x; i < p.Cout + 64; i += blockDim.x) s_bias[i] = i < p.Cout ? p.bias[i] : 0.f;

@@ -419,7 +419,7 @@ template <int BLOCK_N, int STAGES>
 static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const ConvFwdParams& p,
                       cudaStream_t stream) {
   constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (BLOCK_N >= 64 ? 2 * kStageBytes : 0) +
-                       (2 * STAGES + 6) * 8 + 8192 + 256 + 1024;
+                       (2 * STAGES + 6) * 8 + kMaxCout * 4 + 256 + 1024;
   static_assert(smem <= 232448, "conv_fwd_kernel: shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
@@ -457,7 +457,7 @@ static int check_desc(const jg_conv_desc* d) {
   JG_CHECK(d->Cout > 0 && d->Cout % 8 == 0 && d->ldy % 8 == 0 && d->ldy >= d->Cout, JG_ERR_INVALID,
            "conv: Cout=%d ldy=%d must be multiples of 8 with ldy >= Cout", d->Cout, d->ldy);
   JG_CHECK(d->R > 0 && d->S > 0 && d->R * d->S <= 64, JG_ERR_INVALID, "conv: bad filter %dx%d", d->R, d->S);
-  JG_CHECK(d->Cout <= 2048, JG_ERR_INVALID, "conv: Cout %d > 2048 (bias staging buffer)", d->Cout);
+  JG_CHECK(d->Cout <= kMaxCout, JG_ERR_INVALID, "conv: Cout %d > %d (bias staging buffer)", d->Cout, kMaxCout);
   JG_CHECK(d->stride == 1 || d->stride == 2, JG_ERR_INVALID, "conv: stride %d unsupported", d->stride);
   JG_CHECK(d->up2x == 0, JG_ERR_INVALID, "conv: up2x is reserved");
   const int ho = (d->H + 2 * d->pad - d->R) / d->stride + 1;

@@ -395,16 +395,20 @@ extern "C" int jg_unpack_conv_wgrad(const float* src, float* dst, int Cout, int 
 
 extern "C" int jg_bias_grad(const void* dy, int64_t rows, int C, int ld, float* db, jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  JG_CHECK(dy && db && rows > 0 && C > 0 && C % 8 == 0 && ld % 8 == 0 && C / 8 <= 256, JG_ERR_INVALID,
+  JG_CHECK(dy && db && rows > 0 && C > 0 && C % 8 == 0 && ld % 8 == 0 && ld >= C, JG_ERR_INVALID,
            "bias_grad: bad args (C=%d ld=%d)", C, ld);
   JG_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, stream));
   long long blocks = (long long)num_sms() * 8;
   long long rows_per_block = (rows + blocks - 1) / blocks;
   if (rows_per_block < 64) rows_per_block = 64;
   const int grid = (int)((rows + rows_per_block - 1) / rows_per_block);
-  bias_grad_kernel<<<grid, 256, C * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(dy), rows, C, ld, db,
-                                                             rows_per_block);
-  JG_LAUNCH_CHECK();
+  // one thread column per 8 channels, 256 columns per block: wider tensors go in 2048-channel slabs
+  for (int c0 = 0; c0 < C; c0 += 2048) {
+    const int cs = C - c0 < 2048 ? C - c0 : 2048;
+    bias_grad_kernel<<<grid, 256, cs * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(dy) + c0, rows, cs,
+                                                                ld, db + c0, rows_per_block);
+    JG_LAUNCH_CHECK();
+  }
   return JG_OK;
 }
 

@@ -12,6 +12,7 @@ their `forward` is never used: the blocks call the sm_100a kernels through jolig
 bf16 activations.  `accelerate.accelerate()` swaps a reference-built tree for these classes while
 SHARING the nn.Parameter objects.  There is no CPU path: calling forward without CUDA raises.
 """
+import inspect
 import math
 
 import numpy as np
@@ -445,6 +446,24 @@ class UNet(nn.Module):
         y = self.forward_nhwc(ops.to_nhwc(input), embed_gammas)
         return ops.to_nchw(y, self.out_channel)
 
+    def compute_feats(self, input, embed_gammas):
+        """UNet.compute_feats (:660-681): (bottleneck, [encoder block outputs], emb), NCHW fp32 like the reference;
+        embed_gammas None = the GAN use (all-ones embedding)."""
+        if embed_gammas is None:
+            embed_gammas = torch.ones((input.shape[0], self.cond_embed_dim), device=input.device)
+        hs = []
+        h = ops.to_nhwc(input)
+        for module in self.input_blocks:
+            h = module.forward_nhwc(h, embed_gammas)
+            hs.append(h)
+        h = self.middle_block.forward_nhwc(h, embed_gammas)
+        return ops.to_nchw(h, h.shape[-1]), [ops.to_nchw(f, f.shape[-1]) for f in hs], embed_gammas
+
+    def get_feats(self, input, extract_layer_ids):
+        """UNet.get_feats (:697-705): the encoder features CUT's PatchNCE samples from."""
+        _, hs, _ = self.compute_feats(input, embed_gammas=None)
+        return [feat for i, feat in enumerate(hs) if i in extract_layer_ids]
+
 
 def set_new_noise_schedule(model, phase):
     """diffusion_utils.set_new_noise_schedule (lines 79-119), linear schedule only: registers the same 7
@@ -482,18 +501,36 @@ def gamma_embedding(gammas, dim, max_period=10000):
 
 
 class PaletteDenoiseFn(nn.Module):
-    """palette_denoise_fn.PaletteDenoiseFn restricted to conditioning == "" (no class / mask / ref embedding)."""
+    """palette_denoise_fn.PaletteDenoiseFn restricted to conditioning == "" (no class / mask / ref embedding).  A
+    UNet whose forward takes three arguments (UNetGeneratorRefAttn) receives the dataloader's reference image
+    (palette_denoise_fn.py:40-41, 111-114)."""
 
     def __init__(self, model, cond_embed_dim, ref_embed_net="", conditioning="", nclasses=2):
         super().__init__()
         if conditioning:
             raise NotImplementedError("B200 PaletteDenoiseFn: conditioning %r is not supported yet" % conditioning)
         self.model = model
+        self.model_nargs = len(inspect.signature(model.forward).parameters)
         self.cond_embed_dim = cond_embed_dim
         self.conditioning = conditioning
 
     def forward(self, input, embed_noise_level, cls=None, mask=None, ref=None):
+        if self.model_nargs == 3:
+            return self.model(input, embed_noise_level, ref)
         return self.model(input, embed_noise_level)
+
+    def pack_ref(self, ref):
+        """ref NCHW fp32 -> what the UNet's NHWC path consumes (None for two-argument UNets)."""
+        if self.model_nargs != 3:
+            return None
+        if ref is None:
+            raise RuntimeError("B200 PaletteDenoiseFn: this UNet needs the reference image (ref)")
+        return self.model.pack_ref(ref)
+
+    def forward_nhwc(self, x, emb, ref_nhwc=None):
+        if self.model_nargs == 3:
+            return self.model.forward_nhwc(x, emb, ref_nhwc)
+        return self.model.forward_nhwc(x, emb)
 
 
 class DiffusionGenerator(nn.Module):
@@ -537,7 +574,7 @@ class DiffusionGenerator(nn.Module):
         w = torch.stack([snr, 5.0 * torch.ones_like(t)], dim=1).min(dim=1)[0] / snr
         return t, sample_gammas, w
 
-    def forward_nhwc(self, y_0, y_cond, mask, noise, t=None, u=None):
+    def forward_nhwc(self, y_0, y_cond, mask, noise, t=None, u=None, ref=None):
         """Returns (noise, noise_hat NHWC bf16 [N,H,W,8], min_snr_w [B]).  Video clips [B,F,C,H,W] (UNetVid,
         diffusion_generator.py:460-463, 497-500) are folded to N = B*F frames: one (t, gamma) draw per clip, the
         per-frame work is identical to the image path; noise is returned in the folded [N,C,H,W] layout."""
@@ -560,24 +597,27 @@ class DiffusionGenerator(nn.Module):
         x = K.noise_pack(y_0.contiguous().float(), y_cond.contiguous().float(), noise.contiguous().float(),
                          None if mask is None else mask.contiguous(), g_per_image.contiguous(),
                          ld=(2 * y_0.shape[1] + 7) // 8 * 8)
-        noise_hat = self.denoise_fn.model.forward_nhwc(x, emb)
+        noise_hat = self.denoise_fn.forward_nhwc(x, emb, self.denoise_fn.pack_ref(ref))
         return noise, noise_hat, w
 
     def forward(self, y_0, y_cond, mask, noise, cls=None, ref=None, dropout_prob=0.0, t=None, u=None):
+        if cls is not None or dropout_prob:
+            raise NotImplementedError("B200 DiffusionGenerator: class conditioning / conditioning dropout")
         shape5 = tuple(y_0.shape) if y_0.dim() == 5 else None
         c = y_0.shape[2] if shape5 else y_0.shape[1]
-        noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u)
+        noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u, ref=ref)
         noise_hat = ops.to_nchw(noise_hat, c)
         if shape5:
             noise, noise_hat = noise.reshape(shape5), noise_hat.reshape(shape5)
         return noise, noise_hat, w.view(-1, 1, 1, 1)
 
-    def forward_loss(self, y_0, y_cond, mask, noise=None, lambda_G=1.0, use_minsnr=False, l1=False, t=None, u=None):
+    def forward_loss(self, y_0, y_cond, mask, noise=None, lambda_G=1.0, use_minsnr=False, l1=False, t=None, u=None,
+                     ref=None):
         """compute_palette_loss fused: the UNet output stays NHWC bf16 and feeds the eps-loss kernel directly."""
         if y_0.dim() == 5 and use_minsnr:
             raise NotImplementedError("B200 DiffusionGenerator: min-SNR weighting with video clips")
         b5 = y_0.shape[0] * y_0.shape[1] if y_0.dim() == 5 else None
-        noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u)
+        noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u, ref=ref)
         if b5 is not None and mask is not None:
             mask = mask.reshape((b5,) + tuple(mask.shape[2:]))
         return ops.palette_loss(noise_hat, noise.contiguous().float(), None if mask is None else mask.contiguous(),
@@ -586,14 +626,16 @@ class DiffusionGenerator(nn.Module):
     @torch.no_grad()
     def restoration_ddpm(self, y_cond, y_t=None, y_0=None, mask=None, sample_num=2, cls=None, guidance_scale=0.0,
                          ref=None, noise_fn=None):
-        """diffusion_generator.restoration_ddpm (:122-177) for conditioning "" (no class / ref, no guidance):
+        """diffusion_generator.restoration_ddpm (:122-177) for conditioning "" (no class, no guidance; `ref` is the
+        reference image of a UNetGeneratorRefAttn denoiser):
         num_timesteps_test UNet forwards; per step ONE fused kernel does predict_start_from_noise, the clamp, the
         posterior mean, the noise injection, the mask blend and the next step's NHWC bf16 input pack.
         noise_fn(i, shape) -> fp32 NCHW noise for step i (default torch.randn on the device; the tests replay the
         reference's CPU draws).  Returns (y_t, ret_arr) like the reference."""
-        if cls is not None or ref is not None or guidance_scale:
-            raise NotImplementedError("B200 restoration_ddpm: class / reference conditioning and guidance")
+        if cls is not None or guidance_scale:
+            raise NotImplementedError("B200 restoration_ddpm: class conditioning and guidance")
         model = self.denoise_fn.model
+        ref_p = self.denoise_fn.pack_ref(ref)
         T = model.num_timesteps_test
         assert T > sample_num, "num_timesteps must greater than sample_num"
         sample_inter = T // sample_num
@@ -617,7 +659,7 @@ class DiffusionGenerator(nn.Module):
         ret_arr = y_t
         for i in reversed(range(T)):
             gam = model.gammas_test[i].reshape(1, 1).expand(b, 1)
-            eps = model.forward_nhwc(x, self.compute_gammas(gam))
+            eps = self.denoise_fn.forward_nhwc(x, self.compute_gammas(gam), ref_p)
             noise = noise_fn(i, tuple(y_t.shape)).contiguous().float() if i > 0 else None
             coef = table[i].reshape(1, 5).expand(b, 5).contiguous()
             y_t, x = K.ddpm_step(eps, y_t, y_cond, y_0, mask, noise, coef, ld=ld, want_next_input=i > 0)
@@ -631,9 +673,10 @@ class DiffusionGenerator(nn.Module):
         """diffusion_generator.restoration_ddim (:286-347) with ddim_p_sample / ddim_p_mean_variance (:349-456):
         num_steps UNet forwards on the linear t sequence; the update is deterministic (the reference draws a noise
         tensor and does not use it), one fused kernel per step."""
-        if cls is not None or ref is not None or guidance_scale:
-            raise NotImplementedError("B200 restoration_ddim: class / reference conditioning and guidance")
+        if cls is not None or guidance_scale:
+            raise NotImplementedError("B200 restoration_ddim: class conditioning and guidance")
         model = self.denoise_fn.model
+        ref_p = self.denoise_fn.pack_ref(ref)
         T = model.num_timesteps_test
         assert T > sample_num, "num_timesteps must greater than sample_num"
         sample_inter = T // sample_num
@@ -658,7 +701,7 @@ class DiffusionGenerator(nn.Module):
             c1 = torch.sqrt(g_p) / torch.sqrt(g_t)
             c2 = coef_eps - torch.sqrt(g_p) * torch.sqrt(1.0 - g_t) / torch.sqrt(g_t)
             coef = torch.stack([c1, c2, c1 * 0, c1 * 0, c1 * 0]).reshape(1, 5).expand(b, 5).contiguous().float()
-            eps = model.forward_nhwc(x, self.compute_gammas(g_t.reshape(1, 1).expand(b, 1)))
+            eps = self.denoise_fn.forward_nhwc(x, self.compute_gammas(g_t.reshape(1, 1).expand(b, 1)), ref_p)
             y_t, x = K.ddpm_step(eps, y_t, y_cond, y_0, mask, None, coef, ld=ld, want_next_input=i != num_steps - 1,
                                  ddim=True)
             if i % sample_inter == 0:

@@ -197,11 +197,15 @@ class UNetGeneratorRefAttn(nn.Module):
         h = self.out[0].forward_nhwc(h, act=L.ACT_SILU)
         return _conv(h, self.out[2], self._pack_outconv)
 
+    @staticmethod
+    def pack_ref(ref):
+        """ref NCHW fp32 [N,3,H,W] -> NHWC bf16 of cat([ref, ref], dim=1) (:1577)."""
+        return ops.to_nhwc(torch.cat([ref, ref], dim=1))
+
     def forward(self, input, embed_gammas=None, ref=None):
         if ref is None:
             raise NotImplementedError("B200 UNetGeneratorRefAttn: the reference image is required")
         if embed_gammas is None:
             embed_gammas = torch.ones((input.shape[0], self.cond_embed_dim), device=input.device)
-        ref2 = torch.cat([ref, ref], dim=1)
-        y = self.forward_nhwc(ops.to_nhwc(input), embed_gammas, ops.to_nhwc(ref2))
+        y = self.forward_nhwc(ops.to_nhwc(input), embed_gammas, self.pack_ref(ref))
         return ops.to_nchw(y, self.out_channel)

@@ -134,6 +134,8 @@ class PaletteTrainer:
         self.l1 = (loss == "L1")
         if loss not in ("MSE", "L1"):
             raise NotImplementedError("alg_palette_loss %r" % loss)
+        self.use_ref = getattr(getattr(self.netG_A, "denoise_fn", None), "model_nargs", 2) == 3
+        self.ref_A = None
         self.pg = process_group
         self.world = dp.world_size(process_group)
         self.niter = 0
@@ -154,8 +156,12 @@ class PaletteTrainer:
 
     # -- data -----------------------------------------------------------------------------------
     def set_input(self, data, non_blocking=True):
-        """data: {"A": cond image y_t, "B": ground truth, "B_label_mask": int64/float mask [B,1,H,W]}"""
+        """data: {"A": cond image y_t, "B": ground truth, "B_label_mask": int64/float mask [B,1,H,W]} (+ "ref_A": the
+        reference image when the denoiser is a UNetGeneratorRefAttn, palette_model.py:373-374, 586-588)"""
         m = data.get("B_label_mask")
+        if self.use_ref and "ref_A" not in data:
+            raise RuntimeError('PaletteTrainer: this generator needs data["ref_A"]')
+        r = data["ref_A"] if self.use_ref else None
         if self._static is not None:
             # graph mode: refill the captured input buffers in place
             st = self._static
@@ -165,10 +171,13 @@ class PaletteTrainer:
             st["B"].copy_(data["B"], non_blocking=non_blocking)
             if m is not None:
                 st["M"].copy_(m, non_blocking=non_blocking)
+            if r is not None:
+                st["R"].copy_(r, non_blocking=non_blocking)
             return
         self.y_t = data["A"].to(self.device, non_blocking=non_blocking)
         self.gt_image = data["B"].to(self.device, non_blocking=non_blocking)
         self.mask = None if m is None else m.to(self.device, non_blocking=non_blocking)
+        self.ref_A = None if r is None else r.to(self.device, non_blocking=non_blocking)
         self.cond_image = self.y_t
 
     def broadcast_parameters(self):
@@ -179,7 +188,7 @@ class PaletteTrainer:
     def compute_palette_loss(self, noise=None, t=None, u=None):
         self.loss_G_tot = self.netG_A.forward_loss(self.gt_image, self.cond_image, self.mask, noise=noise,
                                                    lambda_G=self.lambda_G, use_minsnr=self.use_minsnr, l1=self.l1,
-                                                   t=t, u=u)
+                                                   t=t, u=u, ref=self.ref_A)
         return self.loss_G_tot
 
     def _forward_backward(self, noise=None, t=None, u=None):
@@ -216,10 +225,12 @@ class PaletteTrainer:
     def _capture(self):
         """Capture the step into CUDA graphs (called once, after `graph_warmup` eager steps)."""
         self._static = {"A": self.y_t.clone(), "B": self.gt_image.clone(),
-                        "M": None if self.mask is None else self.mask.clone()}
+                        "M": None if self.mask is None else self.mask.clone(),
+                        "R": None if self.ref_A is None else self.ref_A.clone()}
         self.y_t = self.cond_image = self._static["A"]
         self.gt_image = self._static["B"]
         self.mask = self._static["M"]
+        self.ref_A = self._static["R"]
         self.loss_G_tot = None
         import gc
         gc.collect()

@@ -353,9 +353,12 @@ def sample_t_gamma(cfg: UNetCfg, batch: int, generator: Optional[torch.Generator
     return t, u
 
 
-def diffusion_forward(sd, y_0, y_cond, mask, noise, t, u, cfg: UNetCfg):
+def diffusion_forward(sd, y_0, y_cond, mask, noise, t, u, cfg: UNetCfg, unet=None):
     """DiffusionGenerator.forward for 4-D inputs with explicit randomness (t, u, noise).
-    Returns (noise, noise_hat, min_snr_loss_weight) like diffusion_generator.py:521."""
+    Returns (noise, noise_hat, min_snr_loss_weight) like diffusion_generator.py:521.
+    unet(sd, input, emb, cfg): the denoiser (default: the plain UNet; oracle.ref_oracle.denoiser(ref) for the
+    reference-attention UNet, whose extra `ref` argument PaletteDenoiseFn forwards, palette_denoise_fn.py:111-112)."""
+    unet = unet or unet_forward
     sched = schedule_buffers(cfg, "train")
     gammas = sched["gammas_train"]
     b = y_0.shape[0]
@@ -372,7 +375,7 @@ def diffusion_forward(sd, y_0, y_cond, mask, noise, t, u, cfg: UNetCfg):
         temp_mask = torch.clamp(mask, min=0.0, max=1.0)
         y_noisy = y_noisy * temp_mask + (1.0 - temp_mask) * y_0
     inp = torch.cat([y_cond, y_noisy], dim=1)
-    noise_hat = unet_forward(sd, inp, emb, cfg)
+    noise_hat = unet(sd, inp, emb, cfg)
     ksnr = 5.0
     snr1 = sched["sqrt_recip_gammas_train"].gather(-1, t)
     snr2 = sched["sqrt_recipm1_gammas_train"].gather(-1, t)
@@ -381,11 +384,12 @@ def diffusion_forward(sd, y_0, y_cond, mask, noise, t, u, cfg: UNetCfg):
     return noise, noise_hat, w.view(-1, 1, 1, 1)
 
 
-def restoration_ddpm(sd, y_cond, y_t, y_0, mask, noises, cfg: UNetCfg, sample_num=2):
+def restoration_ddpm(sd, y_cond, y_t, y_0, mask, noises, cfg: UNetCfg, sample_num=2, unet=None):
     """DiffusionGenerator.restoration_ddpm (diffusion_generator.py:122-177) with p_sample / p_mean_variance
     (:192-283), predict_start_from_noise and q_posterior (diffusion_utils.py:122-137), conditioning "" and no
     guidance.  `noises[i]` is the randn_like draw of step i (i > 0), in the reference's order.
     Returns (y_t, ret_arr)."""
+    unet = unet or unet_forward
     sched = schedule_buffers(cfg, "test")
     T = int(sched["gammas_test"].shape[0])
     sample_inter = T // sample_num
@@ -397,7 +401,7 @@ def restoration_ddpm(sd, y_cond, y_t, y_0, mask, noises, cfg: UNetCfg, sample_nu
         emb = gamma_embedding(noise_level, cfg.cond_embed_dim)
         emb = F.linear(emb, sd["cond_embed.0.weight"], sd["cond_embed.0.bias"])
         emb = F.linear(F.silu(emb), sd["cond_embed.2.weight"], sd["cond_embed.2.bias"])
-        eps = unet_forward(sd, torch.cat([y_cond, y_t], dim=1), emb, cfg)
+        eps = unet(sd, torch.cat([y_cond, y_t], dim=1), emb, cfg)
 
         def ex(name):
             return sched[name + "_test"].gather(-1, t).reshape(b, 1, 1, 1)
@@ -414,9 +418,10 @@ def restoration_ddpm(sd, y_cond, y_t, y_0, mask, noises, cfg: UNetCfg, sample_nu
     return y_t, ret_arr
 
 
-def restoration_ddim(sd, y_cond, y_t, y_0, mask, cfg: UNetCfg, sample_num=8, num_steps=10, eta=0.5):
+def restoration_ddim(sd, y_cond, y_t, y_0, mask, cfg: UNetCfg, sample_num=8, num_steps=10, eta=0.5, unet=None):
     """DiffusionGenerator.restoration_ddim / ddim_p_sample / ddim_p_mean_variance (diffusion_generator.py:286-456),
     conditioning "" and no guidance.  Deterministic given y_t (the reference's per-step noise draw is unused)."""
+    unet = unet or unet_forward
     sched = schedule_buffers(cfg, "test")
     T = int(sched["gammas_test"].shape[0])
     sample_inter = T // sample_num
@@ -431,7 +436,7 @@ def restoration_ddim(sd, y_cond, y_t, y_0, mask, cfg: UNetCfg, sample_num=8, num
         emb = gamma_embedding(noise_level, cfg.cond_embed_dim)
         emb = F.linear(emb, sd["cond_embed.0.weight"], sd["cond_embed.0.bias"])
         emb = F.linear(F.silu(emb), sd["cond_embed.2.weight"], sd["cond_embed.2.bias"])
-        e = unet_forward(sd, torch.cat([y_cond, y_t], dim=1), emb, cfg).clamp(-1.0, 1.0)
+        e = unet(sd, torch.cat([y_cond, y_t], dim=1), emb, cfg).clamp(-1.0, 1.0)
         g_t = sched["gammas_test"].gather(-1, t).reshape(b, 1, 1, 1)
         g_p = gammas_prev.gather(-1, prevt + 1).reshape(b, 1, 1, 1)
         sigma = eta * torch.sqrt((1 - g_p) / (1 - g_t) * (1 - g_t / g_p))

@@ -157,3 +157,9 @@ def unet_ref_forward(sd, x, emb, ref, cfg: O.UNetCfg, prefix=""):
     h = _r(F.silu(O.group_norm(h, sd[prefix + "out.0.norm.weight"], sd[prefix + "out.0.norm.bias"],
                                cfg.group_norm_size)))
     return _r(O._conv2d(h, sd[prefix + "out.2.weight"], sd[prefix + "out.2.bias"], padding=1))
+
+
+def denoiser(ref, prefix="denoise_fn.model."):
+    """The `unet` callable of oracle.palette_oracle.diffusion_forward / restoration_* for cfg 4: PaletteDenoiseFn hands
+    the dataloader's reference image to the three-argument UNet (palette_denoise_fn.py:40-41, 111-112)."""
+    return lambda sd, x, emb, cfg: unet_ref_forward(sd, x, emb, ref, cfg, prefix=prefix)

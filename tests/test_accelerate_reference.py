@@ -52,3 +52,19 @@ def test_accelerate_video_and_reference_attention_unets():
     fast = accelerate(ref_ra)
     assert isinstance(fast, nets_ref.UNetGeneratorRefAttn) and list(fast.state_dict().keys()) == keys
     assert all(p is params[k] for k, p in fast.named_parameters())
+    # whole generators (cfg 4 / cfg 5): DiffusionGenerator(PaletteDenoiseFn(<those UNets>))
+    from models.modules.diffusion_generator import DiffusionGenerator
+    from models.modules.palette_denoise_fn import PaletteDenoiseFn
+    from joligen_b200 import nets
+    for unet, kind, nargs in ((gen_golden_vid.build_reference(V.VidCfg(**gen_golden_vid.CFG)), nets_vid.UNetVid, 2),
+                              (gen_golden_ref.build_reference(O.UNetCfg(**gen_golden_ref.CFG)),
+                               nets_ref.UNetGeneratorRefAttn, 3)):
+        dn = PaletteDenoiseFn(model=unet, cond_embed_dim=32, ref_embed_net="", conditioning="", nclasses=2)
+        gen = DiffusionGenerator(denoise_fn=dn, sampling_method="ddpm", image_size=32, G_ngf=64,
+                                 loading_backward_compatibility=False)
+        params, keys = dict(gen.named_parameters()), list(gen.state_dict().keys())
+        fast = accelerate(gen)
+        assert isinstance(fast, nets.DiffusionGenerator) and isinstance(fast.denoise_fn.model, kind)
+        assert fast.denoise_fn.model_nargs == nargs == dn.model_nargs
+        assert list(fast.state_dict().keys()) == keys
+        assert all(p is params[k] for k, p in fast.named_parameters())

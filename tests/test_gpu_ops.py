@@ -45,6 +45,7 @@ CONV_CASES = [
     (2, 32, 32, 64, 3, 3, 1),     # last UNet conv: 3 output channels, padded to 8
     (3, 8, 8, 512, 512, 3, 1),    # several images per M tile
     (1, 30, 30, 64, 128, 4, 1),   # ragged tiles (NLayerDiscriminator stride-1 layers)
+    (2, 8, 8, 512, 4096, 1, 0),   # widest layer: the video UNet's GEGLU projection (Linear as a 1x1 conv)
 ]
 
 

@@ -290,3 +290,32 @@ def test_ddpm_and_ddim_samplers_vs_reference_golden(env, golden_dir):
         O.EMULATE_BF16[0] = False
     floor = rel_l2(ydo, gold["y_ddim"])
     assert rel_l2(yd, gold["y_ddim"]) < max(3e-2, 2.5 * floor), (rel_l2(yd, gold["y_ddim"]), floor)
+
+
+def test_unet_compute_feats_and_get_feats(env):
+    """UNet.compute_feats / get_feats (unet_generator_attn.py:660-705; CUT's PatchNCE feature taps) against the
+    oracle's encoder outputs, all-ones embedding like the reference's GAN use."""
+    nets, O = env
+    cfg = O.UNetCfg(image_size=32, inner_channel=32, channel_mults=(1, 2), res_blocks=(1, 1), attn_res=(2,),
+                    num_head_channels=16)
+    params = O.init_params(cfg, 5)
+    net = build(nets, O, cfg, params)
+    unet = net.denoise_fn.model
+    x = torch.randn(2, cfg.in_channel, 32, 32, generator=torch.Generator().manual_seed(1))
+    emb = torch.ones(2, cfg.cond_embed_dim)
+    O.EMULATE_BF16[0] = True
+    try:
+        with torch.no_grad():
+            _, feats = O.unet_forward(params, x, emb, cfg, return_feats=True)
+    finally:
+        O.EMULATE_BF16[0] = False
+    with torch.no_grad():
+        mid, hs, e = unet.compute_feats(x.cuda(), None)
+        picked = unet.get_feats(x.cuda(), [0, 2])
+    assert len(hs) == len(feats) and torch.equal(e.cpu(), emb)
+    for mine, ref in zip(hs, feats):
+        assert mine.shape == ref.shape and mine.dtype == torch.float32
+        assert rel_l2(mine, ref) < 2e-2
+    assert mid.shape[1] == cfg.inner_channel * cfg.channel_mults[-1]
+    # two forward passes: GroupNorm statistics are summed with atomics, so a bf16 ulp may differ between runs
+    assert len(picked) == 2 and rel_l2(picked[0], hs[0]) < 1e-3 and rel_l2(picked[1], hs[2]) < 1e-3

@@ -204,6 +204,96 @@ def test_refattn_unet_forward_backward_vs_reference_golden(golden_dir):
         assert err < max(8e-2, 3 * emu), (k, err, emu)
 
 
+def test_refattn_generator_trainer_and_samplers_vs_reference_golden(golden_dir):
+    """cfg 4 end to end: DiffusionGenerator(PaletteDenoiseFn(UNetGeneratorRefAttn)) with the dataloader's reference
+    image — loss and gradients against the unmodified reference / the bf16-emulating oracle, the same batch through
+    PaletteTrainer (data["ref_A"]), and the DDPM / DDIM samplers with the reference image."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from joligen_b200 import nets
+    from joligen_b200.trainer import PaletteTrainer
+    from oracle import palette_oracle as O
+    from oracle import ref_oracle as R
+    from oracle.gen_golden_ref import generator_inputs
+    from oracle.vid_oracle import init_params_from_shapes
+    from test_ref_oracle import build_b200
+    gold = torch.load(os.path.join(golden_dir, "refattn_generator.pt"))
+    cfg = O.UNetCfg(**gold["cfg"])
+    params = init_params_from_shapes(gold["shapes"], gold["wseed"])
+    gt, cond, mask, noise, ref = generator_inputs(cfg, gold["batch"], gold["dseed"])
+
+    def build():
+        g = nets.DiffusionGenerator(nets.PaletteDenoiseFn(build_b200(cfg), cfg.cond_embed_dim),
+                                    image_size=cfg.image_size, G_ngf=cfg.inner_channel)
+        missing, unexpected = g.load_state_dict(params, strict=False)
+        assert not unexpected and not [m for m in missing if "gammas" not in m and "posterior" not in m]
+        return g.cuda()
+
+    g = build()
+    assert g.denoise_fn.model_nargs == 3
+    t, u = gold["t"].cuda(), gold["u"].cuda()
+    n_out, nh, _ = g(gt.cuda(), cond.cuda(), mask.cuda(), noise.cuda(), cls=None, ref=ref.cuda(), t=t, u=u)
+    assert torch.equal(n_out.cpu(), noise)
+    loss = g.forward_loss(gt.cuda(), cond.cuda(), mask.cuda(), noise=noise.cuda(), t=t, u=u, ref=ref.cuda())
+    loss.backward()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    mb = torch.clamp(mask, min=0, max=1)
+    O.EMULATE_BF16[0] = True
+    try:
+        _, nho, _ = O.diffusion_forward(leaves, gt, cond, mask, noise, gold["t"], gold["u"], cfg, unet=R.denoiser(ref))
+        lo = torch.nn.MSELoss()(mb * noise, mb * nho)
+        lo.backward()
+    finally:
+        O.EMULATE_BF16[0] = False
+    floor = rel(nho, gold["noise_hat"])
+    assert rel(nh, gold["noise_hat"]) < max(3e-2, 2 * floor), (rel(nh, gold["noise_hat"]), floor)
+    assert abs(float(loss) - gold["loss"]) < 2e-2 * gold["loss"], (float(loss), gold["loss"])
+    assert abs(float(loss) - float(lo)) < 2e-2 * gold["loss"]
+    named = dict(g.named_parameters())
+    scale = max(x["l2"] for x in gold["grads"].values())
+    for k, x in gold["grads"].items():
+        mine = named[k].grad.detach().cpu().double()
+        refg = leaves[k].grad.double()
+        err = float((mine - refg).norm()) / max(float(refg.norm()), 2e-2 * scale)
+        emu = abs(float(refg.norm()) - x["l2"]) / max(x["l2"], 2e-2 * scale)
+        assert err < max(8e-2, 3 * emu), (k, err, emu)
+    # trainer: first loss = the generator's; a batch without ref_A is refused
+    net2 = build()
+    tr = PaletteTrainer(net2, lr=1e-4, optim="adamw", ema=True, ema_beta=0.9, device="cuda")
+    with pytest.raises(RuntimeError):
+        tr.set_input({"A": cond, "B": gt, "B_label_mask": mask})
+    tr.set_input({"A": cond, "B": gt, "B_label_mask": mask, "ref_A": ref})
+    l1 = float(tr.optimize_parameters(noise=noise.cuda(), t=t, u=u))
+    assert abs(l1 - float(loss)) < 1e-3 * abs(float(loss)), (l1, float(loss))
+    changed = sum(1 for k, p in net2.named_parameters() if not torch.equal(p.detach().cpu(), params[k]))
+    assert changed == len(gold["shapes"]), (changed, len(gold["shapes"]))
+    # samplers with the reference image
+    torch.manual_seed(gold["rseed"] + 1)
+    y_t0 = torch.randn_like(gt)
+    noises = {i: torch.randn_like(gt) for i in reversed(range(1, cfg.n_timestep_test))}
+    y, ret = g.restoration_ddpm(cond.cuda(), y_t=y_t0.cuda(), y_0=gt.cuda(), mask=mask.cuda(), ref=ref.cuda(),
+                                sample_num=gold["sample_num"], noise_fn=lambda i, shape: noises[i].cuda())
+    g.sampling_method = "ddim"
+    yd, retd = g.restoration(cond.cuda(), y_t=y_t0.cuda(), y_0=gt.cuda(), mask=mask.cuda(), ref=ref.cuda(),
+                             sample_num=gold["sample_num"], ddim_num_steps=gold["ddim_steps"], ddim_eta=gold["ddim_eta"])
+    O.EMULATE_BF16[0] = True
+    try:
+        with torch.no_grad():
+            yo, reto = O.restoration_ddpm(params, cond, y_t0, gt, mask, noises, cfg, gold["sample_num"],
+                                          unet=R.denoiser(ref))
+            ydo, retdo = O.restoration_ddim(params, cond, y_t0.clone(), gt, mask, cfg, gold["sample_num"],
+                                            num_steps=gold["ddim_steps"], eta=gold["ddim_eta"], unet=R.denoiser(ref))
+    finally:
+        O.EMULATE_BF16[0] = False
+    m = mask.clamp(0, 1).bool().expand_as(gt)
+    assert torch.equal(y.cpu()[~m], gt[~m]) and torch.equal(yd.cpu()[~m], gt[~m])
+    l2 = lambda a, b: float((a.float().cpu() - b.float().cpu()).norm() / b.float().norm())  # noqa: E731
+    assert ret.shape == gold["ret_arr"].shape and retd.shape == gold["ret_arr_ddim"].shape
+    assert l2(y, gold["y"]) < max(3e-2, 2.5 * l2(yo, gold["y"])), (l2(y, gold["y"]), l2(yo, gold["y"]))
+    assert l2(yd, gold["y_ddim"]) < max(3e-2, 2.5 * l2(ydo, gold["y_ddim"])), (l2(yd, gold["y_ddim"]),
+                                                                                l2(ydo, gold["y_ddim"]))
+
+
 def test_video_generator_and_trainer_vs_reference_golden(golden_dir):
     """cfg 5 end to end: DiffusionGenerator(PaletteDenoiseFn(UNetVid)) on a clip — loss and all gradients against the
     unmodified reference's vectors / the bf16-emulating oracle; then the same clip through PaletteTrainer (flat
