@@ -223,38 +223,62 @@ __device__ __forceinline__ int find_item(const int* __restrict__ tile_start, int
 // read or written, `wrow` = warp index picks one of 8 rows per pass (4 passes cover the 32-wide tile).  All loops have
 // compile-time bounds (taps are predicated against nt), so the 36 loads of a phase are independent and in flight together.
 
-// OIHW side of a tile: for a fixed co the (ci, tap) elements [ci0, ci0+32) x [t0, t0+nt) — one contiguous run of
-// 32*nt floats when the chunk covers all taps.  pos enumerates that run with tap fastest.
+// Tile geometry.  R*S > 1: 32 co x 32 ci x up to 9 taps (slot = tap).  1x1 convolutions (every Linear of the video
+// UNet's MotionModule) have a single tap, so their tiles take 9 consecutive 32-channel ci blocks instead (slot = ci
+// block): the same 9216-element work unit instead of a ninth of it.
+struct WTile {
+  int co0, ci0, t0, nt, RS, Cout, Cin;
+  bool wide;
+  __device__ __forceinline__ int ci_of(int slot, int x) const { return wide ? ci0 + slot * kWT + x : ci0 + x; }
+  __device__ __forceinline__ int tap_of(int slot) const { return wide ? 0 : t0 + slot; }
+};
+__device__ __forceinline__ WTile make_tile(int tile, int Cout, int Cin, int RS) {
+  WTile g;
+  g.RS = RS; g.Cout = Cout; g.Cin = Cin;
+  g.wide = RS == 1;
+  const int ci_span = g.wide ? kWT * kWTaps : kWT;
+  const int tchunks = g.wide ? 1 : (RS + kWTaps - 1) / kWTaps;
+  const int ci_tiles = (Cin + ci_span - 1) / ci_span;
+  const int tc = tile % tchunks; tile /= tchunks;
+  const int cit = tile % ci_tiles;
+  g.co0 = (tile / ci_tiles) * kWT;
+  g.ci0 = cit * ci_span;
+  g.t0 = tc * kWTaps;
+  g.nt = g.wide ? min(kWTaps, (Cin - g.ci0 + kWT - 1) / kWT) : min(kWTaps, RS - g.t0);
+  return g;
+}
+
+// OIHW side of a tile: for a fixed co the (ci, tap) elements of the tile are one contiguous run of 32*nt floats (when
+// the chunk covers all taps); pos enumerates that run (tap fastest, as in memory).
 struct OihwIter {
-  int ci, tl;
+  int ci, tl;   // channel within the slot's 32-wide block, slot
   bool ok;
   size_t off;
 };
-__device__ __forceinline__ OihwIter oihw_pos(int pos, int nt, int co, int co0, int ci0, int t0, int Cout, int Cin,
-                                             int RS) {
+__device__ __forceinline__ OihwIter oihw_pos(const WTile& g, int pos, int co) {
   OihwIter r;
-  r.ci = pos / nt;
-  r.tl = pos - r.ci * nt;
-  r.ok = (co0 + co < Cout) && (ci0 + r.ci < Cin) && r.ci < kWT;
-  r.off = ((size_t)(co0 + co) * Cin + ci0 + r.ci) * RS + t0 + r.tl;
+  if (g.wide) {
+    r.tl = pos >> 5;
+    r.ci = pos & 31;
+    r.ok = (g.co0 + co < g.Cout) && (g.ci0 + pos < g.Cin);
+    r.off = (size_t)(g.co0 + co) * g.Cin + g.ci0 + pos;
+  } else {
+    r.ci = pos / g.nt;
+    r.tl = pos - r.ci * g.nt;
+    r.ok = (g.co0 + co < g.Cout) && (g.ci0 + r.ci < g.Cin) && r.ci < kWT;
+    r.off = ((size_t)(g.co0 + co) * g.Cin + g.ci0 + r.ci) * g.RS + g.t0 + r.tl;
+  }
   return r;
 }
 
 // fp32 OIHW master -> bf16 wf [Cout8][RS][Cin8] and wd [Cin8][RS][Cout8] (taps flipped)
 __global__ void __launch_bounds__(256)
 pack_weights_batched_kernel(const jg_pack_item* __restrict__ items, const int* __restrict__ tile_start, int n) {
-  __shared__ float sm[kWTaps][kWT][kWT + 1];  // [tap][co][ci]
+  __shared__ float sm[kWTaps][kWT][kWT + 1];  // [slot][co][ci]
   const int it = find_item(tile_start, n, blockIdx.x);
   const jg_pack_item p = items[it];
-  const int RS = p.RS;
-  const int tchunks = (RS + kWTaps - 1) / kWTaps;
-  const int ci_tiles = (p.Cin + kWT - 1) / kWT;
-  int t = blockIdx.x - tile_start[it];
-  const int tc = t % tchunks; t /= tchunks;
-  const int cit = t % ci_tiles;
-  const int cot = t / ci_tiles;
-  const int co0 = cot * kWT, ci0 = cit * kWT, t0 = tc * kWTaps;
-  const int nt = min(kWTaps, RS - t0);
+  const WTile g = make_tile(blockIdx.x - tile_start[it], p.Cout, p.Cin, p.RS);
+  const int RS = p.RS, nt = g.nt;
   const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
   // phase 1: OIHW runs -> smem
 #pragma unroll
@@ -263,12 +287,12 @@ pack_weights_batched_kernel(const jg_pack_item* __restrict__ items, const int* _
     float v[kWTaps];
 #pragma unroll
     for (int c = 0; c < kWTaps; ++c) {
-      const OihwIter q = oihw_pos(lane + 32 * c, nt, co, co0, ci0, t0, p.Cout, p.Cin, RS);
+      const OihwIter q = oihw_pos(g, lane + 32 * c, co);
       v[c] = (c < nt && q.ok) ? p.w[q.off] : 0.f;
     }
 #pragma unroll
     for (int c = 0; c < kWTaps; ++c) {
-      const OihwIter q = oihw_pos(lane + 32 * c, nt, co, co0, ci0, t0, p.Cout, p.Cin, RS);
+      const OihwIter q = oihw_pos(g, lane + 32 * c, co);
       if (c < nt && q.ci < kWT) sm[q.tl][co][q.ci] = v[c];
     }
   }
@@ -279,10 +303,12 @@ pack_weights_batched_kernel(const jg_pack_item* __restrict__ items, const int* _
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int co = wrow + 8 * k;
-    if (co0 + co < p.Cout && ci0 + lane < p.Cin) {
+    if (g.co0 + co < p.Cout) {
 #pragma unroll
       for (int tl = 0; tl < kWTaps; ++tl)
-        if (tl < nt) wf[((size_t)(co0 + co) * RS + t0 + tl) * p.Cin8 + ci0 + lane] = __float2bfloat16(sm[tl][co][lane]);
+        if (tl < nt && g.ci_of(tl, lane) < p.Cin)
+          wf[((size_t)(g.co0 + co) * RS + g.tap_of(tl)) * p.Cin8 + g.ci_of(tl, lane)] =
+              __float2bfloat16(sm[tl][co][lane]);
     }
   }
   // phase 2b: wd[ci][RS-1-tap][co], lane = co
@@ -290,11 +316,11 @@ pack_weights_batched_kernel(const jg_pack_item* __restrict__ items, const int* _
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int ci = wrow + 8 * k;
-      if (ci0 + ci < p.Cin && co0 + lane < p.Cout) {
+      if (g.co0 + lane < p.Cout) {
 #pragma unroll
         for (int tl = 0; tl < kWTaps; ++tl)
-          if (tl < nt)
-            wd[((size_t)(ci0 + ci) * RS + (RS - 1 - (t0 + tl))) * p.Cout8 + co0 + lane] =
+          if (tl < nt && g.ci_of(tl, ci) < p.Cin)
+            wd[((size_t)g.ci_of(tl, ci) * RS + (RS - 1 - g.tap_of(tl))) * p.Cout8 + g.co0 + lane] =
                 __float2bfloat16(sm[tl][lane][ci]);
       }
     }
@@ -304,18 +330,11 @@ pack_weights_batched_kernel(const jg_pack_item* __restrict__ items, const int* _
 // dw_oihw += acc (layout 0: [RS][Cin][Cout], 1: [Cout][RS][Cin]);  acc = 0 (ready for the next step's split-K sums)
 __global__ void __launch_bounds__(256)
 wgrad_unpack_batched_kernel(const jg_unpack_item* __restrict__ items, const int* __restrict__ tile_start, int n) {
-  __shared__ float sm[kWTaps][kWT][kWT + 1];  // [tap][co][ci]
+  __shared__ float sm[kWTaps][kWT][kWT + 1];  // [slot][co][ci]
   const int it = find_item(tile_start, n, blockIdx.x);
   const jg_unpack_item p = items[it];
-  const int RS = p.RS;
-  const int tchunks = (RS + kWTaps - 1) / kWTaps;
-  const int ci_tiles = (p.Cin + kWT - 1) / kWT;
-  int t = blockIdx.x - tile_start[it];
-  const int tc = t % tchunks; t /= tchunks;
-  const int cit = t % ci_tiles;
-  const int cot = t / ci_tiles;
-  const int co0 = cot * kWT, ci0 = cit * kWT, t0 = tc * kWTaps;
-  const int nt = min(kWTaps, RS - t0);
+  const WTile g = make_tile(blockIdx.x - tile_start[it], p.Cout, p.Cin, p.RS);
+  const int RS = p.RS, nt = g.nt;
   const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
   // phase 1: raw accumulator -> smem (and zero it)
 #pragma unroll
@@ -323,22 +342,23 @@ wgrad_unpack_batched_kernel(const jg_unpack_item* __restrict__ items, const int*
     const int row = wrow + 8 * k;
     float v[kWTaps];
     size_t off[kWTaps];
-    bool ok;
-    if (p.layout == 0) {  // [tap][ci][co]: lane = co, row = ci
-      ok = (ci0 + row < p.Cin) && (co0 + lane < p.Cout);
+    bool ok[kWTaps];
 #pragma unroll
-      for (int tl = 0; tl < kWTaps; ++tl) off[tl] = ((size_t)(t0 + tl) * p.Cin + ci0 + row) * p.Cout + co0 + lane;
-    } else {              // [co][tap][ci]: lane = ci, row = co
-      ok = (co0 + row < p.Cout) && (ci0 + lane < p.Cin);
-#pragma unroll
-      for (int tl = 0; tl < kWTaps; ++tl) off[tl] = ((size_t)(co0 + row) * RS + t0 + tl) * p.Cin + ci0 + lane;
+    for (int tl = 0; tl < kWTaps; ++tl) {
+      if (p.layout == 0) {  // [tap][ci][co]: lane = co, row = ci
+        ok[tl] = tl < nt && (g.ci_of(tl, row) < p.Cin) && (g.co0 + lane < p.Cout);
+        off[tl] = ((size_t)g.tap_of(tl) * p.Cin + g.ci_of(tl, row)) * p.Cout + g.co0 + lane;
+      } else {              // [co][tap][ci]: lane = ci, row = co
+        ok[tl] = tl < nt && (g.co0 + row < p.Cout) && (g.ci_of(tl, lane) < p.Cin);
+        off[tl] = ((size_t)(g.co0 + row) * RS + g.tap_of(tl)) * p.Cin + g.ci_of(tl, lane);
+      }
     }
 #pragma unroll
-    for (int tl = 0; tl < kWTaps; ++tl) v[tl] = (ok && tl < nt) ? p.acc[off[tl]] : 0.f;
+    for (int tl = 0; tl < kWTaps; ++tl) v[tl] = ok[tl] ? p.acc[off[tl]] : 0.f;
 #pragma unroll
     for (int tl = 0; tl < kWTaps; ++tl) {
       if (tl < nt) {
-        if (ok) p.acc[off[tl]] = 0.f;
+        if (ok[tl]) p.acc[off[tl]] = 0.f;
         if (p.layout == 0) sm[tl][lane][row] = v[tl]; else sm[tl][row][lane] = v[tl];
       }
     }
@@ -351,12 +371,12 @@ wgrad_unpack_batched_kernel(const jg_unpack_item* __restrict__ items, const int*
     float v[kWTaps];
 #pragma unroll
     for (int c = 0; c < kWTaps; ++c) {
-      const OihwIter q = oihw_pos(lane + 32 * c, nt, co, co0, ci0, t0, p.Cout, p.Cin, RS);
+      const OihwIter q = oihw_pos(g, lane + 32 * c, co);
       v[c] = (c < nt && q.ok) ? p.dw[q.off] : 0.f;
     }
 #pragma unroll
     for (int c = 0; c < kWTaps; ++c) {
-      const OihwIter q = oihw_pos(lane + 32 * c, nt, co, co0, ci0, t0, p.Cout, p.Cin, RS);
+      const OihwIter q = oihw_pos(g, lane + 32 * c, co);
       if (c < nt && q.ok) p.dw[q.off] = v[c] + sm[q.tl][co][q.ci];
     }
   }
@@ -481,5 +501,6 @@ extern "C" int jg_wgrad_unpack_batched(const jg_unpack_item* items_dev, const in
 }
 
 extern "C" int jg_weight_tiles(int Cout, int Cin, int RS) {
+  if (RS == 1) return ((Cout + 31) / 32) * ((Cin + 32 * 9 - 1) / (32 * 9));  // 1x1: 9 ci blocks per tile (make_tile)
   return ((Cout + 31) / 32) * ((Cin + 31) / 32) * ((RS + 8) / 9);
 }

@@ -31,33 +31,47 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 constexpr int kLnMaxVec = 4;  // 8-channel vectors per lane: C <= 32 * 4 * 8 = 1024
 
-// ---- LayerNorm forward: one warp per token --------------------------------------------------------------------------
+// sum over the G-lane group of the calling lane (G a power of two; groups are aligned)
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- LayerNorm forward: G lanes per token, 32 / G tokens per warp ----------------------------------------------------
 // y = (x - mean) * rstd * gamma + beta (+ pe[frame][c]),  frame = (row / HW) % F;  stats[row] = (mean, rstd)
+// (the MotionModule's widths are 64 ... 512: a full warp per 64-channel token would leave 24 lanes idle)
+template <int G, int KV>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,
                      long long rows, int C, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ pe, int HW, int F, float* __restrict__ stats) {
+  constexpr int R = 32 / G;
   const int lane = threadIdx.x & 31;
+  const int sub = lane % G;
   const int vecs = C / 8;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * (long long)blockDim.x) >> 5;
-  for (long long row = warp0; row < rows; row += nwarps) {
-    float f[kLnMaxVec][8];
+  for (long long base = warp0 * R; base < rows; base += nwarps * R) {
+    const long long row = base + lane / G;
+    const bool live = row < rows;
+    float f[KV][8];
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
-      const int v = lane + 32 * k;
-      if (v < vecs) {
+    for (int k = 0; k < KV; ++k) {
+      const int v = sub + G * k;
+      if (live && v < vecs) {
         unpack8v(*reinterpret_cast<const uint4*>(x + row * ldx + v * 8), f[k]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += f[k][j];
       }
     }
-    const float mean = warp_sum(s) / (float)C;
+    const float mean = group_sum<G>(s) / (float)C;
     float q = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
-      if (lane + 32 * k < vecs) {
+    for (int k = 0; k < KV; ++k) {
+      if (live && sub + G * k < vecs) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float d = f[k][j] - mean;
@@ -65,23 +79,27 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16
         }
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
-    if (lane == 0) {
-      stats[row * 2 + 0] = mean;
-      stats[row * 2 + 1] = rstd;
-    }
+    const float rstd = rsqrtf(group_sum<G>(q) / (float)C + eps);
+    if (!live) continue;
+    if (sub == 0) *reinterpret_cast<float2*>(stats + row * 2) = make_float2(mean, rstd);
     const float* per = pe ? pe + (size_t)((row / HW) % F) * C : nullptr;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
-      const int v = lane + 32 * k;
+    for (int k = 0; k < KV; ++k) {
+      const int v = sub + G * k;
       if (v < vecs) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = v * 8 + j;
-          o[j] = (f[k][j] - mean) * rstd * gamma[c] + beta[c];
-          if (per) o[j] += per[c];
+        float gm[8], bt[8], o[8];
+        *reinterpret_cast<float4*>(gm) = *reinterpret_cast<const float4*>(gamma + v * 8);
+        *reinterpret_cast<float4*>(gm + 4) = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+        *reinterpret_cast<float4*>(bt) = *reinterpret_cast<const float4*>(beta + v * 8);
+        *reinterpret_cast<float4*>(bt + 4) = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+        if (per) {
+          const float4 p0 = *reinterpret_cast<const float4*>(per + v * 8);
+          const float4 p1 = *reinterpret_cast<const float4*>(per + v * 8 + 4);
+          bt[0] += p0.x; bt[1] += p0.y; bt[2] += p0.z; bt[3] += p0.w;
+          bt[4] += p1.x; bt[5] += p1.y; bt[6] += p1.z; bt[7] += p1.w;
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf((f[k][j] - mean) * rstd, gm[j], bt[j]);
         *reinterpret_cast<uint4*>(y + row * ldy + v * 8) = pack8v(o);
       }
     }
@@ -90,38 +108,53 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16
 
 // ---- LayerNorm backward ----------------------------------------------------------------------------------------------
 // dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)),  g = dy * gamma;  dgamma += dy * xhat, dbeta += dy
-// (per-warp register accumulators over the warp's rows, block reduction in shared memory, one atomic per channel)
+// (per-lane register accumulators over the lane's rows, block reduction in shared memory, one atomic per channel)
+template <int G, int KV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy, int lddy,
                      __nv_bfloat16* __restrict__ dx, int lddx, long long rows, int C, const float* __restrict__ gamma,
                      const float* __restrict__ stats, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float sm[];  // 2 * C floats
+  constexpr int R = 32 / G;
   const int lane = threadIdx.x & 31;
+  const int sub = lane % G;
   const int vecs = C / 8;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
-  float ag[kLnMaxVec][8], ab[kLnMaxVec][8];
+  float ag[KV][8], ab[KV][8], gm[KV][8];
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k)
+  for (int k = 0; k < KV; ++k) {
+    const int v = sub + G * k;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ag[k][j] = ab[k][j] = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      ag[k][j] = ab[k][j] = 0.f;
+      gm[k][j] = v < vecs ? gamma[v * 8 + j] : 0.f;
+    }
+  }
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * (long long)blockDim.x) >> 5;
-  for (long long row = warp0; row < rows; row += nwarps) {
-    const float mean = stats[row * 2 + 0], rstd = stats[row * 2 + 1];
-    float xh[kLnMaxVec][8], g[kLnMaxVec][8];
+  for (long long base = warp0 * R; base < rows; base += nwarps * R) {
+    const long long row = base + lane / G;
+    const bool live = row < rows;
+    float mean = 0.f, rstd = 0.f;
+    if (live) {
+      const float2 st = *reinterpret_cast<const float2*>(stats + row * 2);
+      mean = st.x;
+      rstd = st.y;
+    }
+    float xh[KV][8], g[KV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
-      const int v = lane + 32 * k;
-      if (v < vecs) {
+    for (int k = 0; k < KV; ++k) {
+      const int v = sub + G * k;
+      if (live && v < vecs) {
         float fx[8], fd[8];
         unpack8v(*reinterpret_cast<const uint4*>(x + row * ldx + v * 8), fx);
         unpack8v(*reinterpret_cast<const uint4*>(dy + row * lddy + v * 8), fd);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[k][j] = (fx[j] - mean) * rstd;
-          g[k][j] = fd[j] * gamma[v * 8 + j];
+          g[k][j] = fd[j] * gm[k][j];
           s1 += g[k][j];
           s2 = fmaf(g[k][j], xh[k][j], s2);
           ag[k][j] = fmaf(fd[j], xh[k][j], ag[k][j]);
@@ -129,11 +162,11 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bf
         }
       }
     }
-    const float m1 = warp_sum(s1) / (float)C, m2 = warp_sum(s2) / (float)C;
+    const float m1 = group_sum<G>(s1) / (float)C, m2 = group_sum<G>(s2) / (float)C;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
-      const int v = lane + 32 * k;
-      if (v < vecs) {
+    for (int k = 0; k < KV; ++k) {
+      const int v = sub + G * k;
+      if (live && v < vecs) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rstd * (g[k][j] - m1 - xh[k][j] * m2);
@@ -141,10 +174,19 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bf
       }
     }
   }
+  // the R row groups of a warp hold the same channels: fold them with shuffles before touching shared memory
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k) {
-    const int v = lane + 32 * k;
-    if (v < vecs) {
+  for (int k = 0; k < KV; ++k) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int o = G; o < 32; o <<= 1) {
+        ag[k][j] += __shfl_xor_sync(0xffffffffu, ag[k][j], o);
+        ab[k][j] += __shfl_xor_sync(0xffffffffu, ab[k][j], o);
+      }
+    }
+    const int v = sub + G * k;
+    if (lane < G && v < vecs) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         atomicAdd(&sm[v * 8 + j], ag[k][j]);
@@ -158,6 +200,18 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bf
     atomicAdd(&dbeta[i], sm[C + i]);
   }
 }
+
+// (G, KV) for a width: the smallest power-of-two lane group that covers C / 8 vectors, then 2 / 4 vectors per lane
+#define JG_LN_DISPATCH(vecs, CALL)            \
+  do {                                        \
+    if ((vecs) <= 8) { CALL(8, 1); }          \
+    else if ((vecs) <= 16) { CALL(16, 1); }   \
+    else if ((vecs) <= 32) { CALL(32, 1); }   \
+    else if ((vecs) <= 64) { CALL(32, 2); }   \
+    else { CALL(32, 4); }                     \
+  } while (0)
+
+static inline int ln_rows_per_warp(int vecs) { return vecs <= 8 ? 4 : vecs <= 16 ? 2 : 1; }
 
 // ---- temporal self-attention over F <= 8 frames ----------------------------------------------------------------------
 // qkv: [B*F][HW][ldqkv] with channels (q | k | v), each heads*ch wide (the three Linear layers packed as one GEMM);
@@ -384,9 +438,14 @@ extern "C" int jg_layernorm_fwd(const void* x, int ldx, void* y, int ldy, int64_
   JG_CHECK(C % 8 == 0 && C > 0 && C <= 32 * kLnMaxVec * 8 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C,
            JG_ERR_INVALID, "layernorm_fwd: bad dims C=%d ldx=%d ldy=%d", C, ldx, ldy);
   JG_CHECK(pe == nullptr || (HW > 0 && F > 0), JG_ERR_INVALID, "layernorm_fwd: positional encoding needs HW, F");
-  layernorm_fwd_kernel<<<grid_for(rows, 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,
-                                                             static_cast<__nv_bfloat16*>(y), ldy, rows, C, eps, gamma,
-                                                             beta, pe, HW > 0 ? HW : 1, F > 0 ? F : 1, stats);
+  // two tokens per lane group: enough loads in flight per SM without a long serial loop
+  const int grid = grid_for(rows, 8 * ln_rows_per_warp(C / 8) * 2);
+#define JG_LN_FWD(G, KV)                                                                                           \
+  layernorm_fwd_kernel<G, KV><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,                 \
+                                                        static_cast<__nv_bfloat16*>(y), ldy, rows, C, eps, gamma,  \
+                                                        beta, pe, HW > 0 ? HW : 1, F > 0 ? F : 1, stats)
+  JG_LN_DISPATCH(C / 8, JG_LN_FWD);
+#undef JG_LN_FWD
   JG_LAUNCH_CHECK();
   return JG_OK;
 }
@@ -401,11 +460,14 @@ extern "C" int jg_layernorm_bwd(const void* x, int ldx, const void* dy, int lddy
            JG_ERR_INVALID, "layernorm_bwd: bad dims C=%d", C);
   JG_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, stream));
   JG_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, stream));
-  int grid = grid_for(rows, 8 * 16);  // ~16 rows per warp: few blocks, few atomics
+  int grid = grid_for(rows, 8 * ln_rows_per_warp(C / 8) * 8);  // >= 8 rows per lane group: few blocks, few atomics
   if (grid > num_sms() * 4) grid = num_sms() * 4;
-  layernorm_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(dy), lddy,
-      static_cast<__nv_bfloat16*>(dx), lddx, rows, C, gamma, stats, dgamma, dbeta);
+#define JG_LN_BWD(G, KV)                                                            \
+  layernorm_bwd_kernel<G, KV><<<grid, 256, 2 * C * sizeof(float), stream>>>(        \
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(dy), lddy, \
+      static_cast<__nv_bfloat16*>(dx), lddx, rows, C, gamma, stats, dgamma, dbeta)
+  JG_LN_DISPATCH(C / 8, JG_LN_BWD);
+#undef JG_LN_BWD
   JG_LAUNCH_CHECK();
   return JG_OK;
 }

@@ -31,7 +31,8 @@ def nhwc(K, t):  # [N, C, H, W] fp32 cpu -> NHWC bf16 cuda
     return K.nchw_to_nhwc(t.cuda())
 
 
-@pytest.mark.parametrize("case", [(6, 5, 64, 3, True), (4, 8, 512, 2, True), (3, 7, 1024, 1, False), (8, 4, 96, 4, True)])
+@pytest.mark.parametrize("case", [(6, 5, 64, 3, True), (4, 8, 512, 2, True), (3, 7, 1024, 1, False), (8, 4, 96, 4, True),
+                                  (5, 3, 128, 5, True), (2, 4, 256, 2, False), (8, 32, 64, 8, True)])
 def test_layernorm_pe_fwd_bwd(K, case):
     n, hw, c, frames, use_pe = case
     g = torch.Generator().manual_seed(c + n)
