@@ -188,9 +188,12 @@ int jg_attn_bwd(const void* qkv, int ldqkv, const void* out, int ldo, const void
  * ------------------------------------------------------------------------------------------- */
 int jg_layernorm_fwd(const void* x, int ldx, void* y, int ldy, int64_t rows, int C, float eps, const float* gamma,
                      const float* beta, const float* pe, int HW, int F, float* stats, jg_stream_t stream);
-/* dgamma / dbeta [C] overwritten. */
-int jg_layernorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int64_t rows, int C,
-                     const float* gamma, const float* stats, float* dgamma, float* dbeta, jg_stream_t stream);
+/* dgamma / dbeta [C] overwritten.  addend (optional, bf16 rows of stride ldadd): added to dx — the gradient of the
+ * residual branch x also feeds (BasicTransformerBlock: norm(x) -> attn/ff -> + x, unet_generator_attn_vid.py:565-590).
+ * dx_colsum (optional, [C], overwritten): sum over rows of dx = the bias gradient of the Linear that produced x. */
+int jg_layernorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, const void* addend,
+                     int ldadd, int64_t rows, int C, const float* gamma, const float* stats, float* dgamma,
+                     float* dbeta, float* dx_colsum, jg_stream_t stream);
 int jg_temporal_attn_fwd(const void* qkv, int ldqkv, void* out, int ldo, int B, int F, int HW, int heads, int ch,
                          jg_stream_t stream);
 int jg_temporal_attn_bwd(const void* qkv, int ldqkv, const void* d_out, int lddo, void* dqkv, int lddqkv, int B, int F,

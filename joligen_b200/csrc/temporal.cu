@@ -107,27 +107,33 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16
 }
 
 // ---- LayerNorm backward ----------------------------------------------------------------------------------------------
-// dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)),  g = dy * gamma;  dgamma += dy * xhat, dbeta += dy
+// dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)) (+ addend),  g = dy * gamma;  dgamma += dy * xhat, dbeta += dy
 // (per-lane register accumulators over the lane's rows, block reduction in shared memory, one atomic per channel)
-template <int G, int KV>
+// addend: the gradient of the transformer's residual branch (x feeds the norm AND the residual add: both gradients meet
+// here instead of in an add kernel).  CS: dx_colsum[c] += sum over rows of dx — the bias gradient of the Linear that
+// produced x, for free.
+template <int G, int KV, bool CS>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy, int lddy,
-                     __nv_bfloat16* __restrict__ dx, int lddx, long long rows, int C, const float* __restrict__ gamma,
-                     const float* __restrict__ stats, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  extern __shared__ float sm[];  // 2 * C floats
+                     __nv_bfloat16* __restrict__ dx, int lddx, const __nv_bfloat16* __restrict__ addend, int ldadd,
+                     long long rows, int C, const float* __restrict__ gamma, const float* __restrict__ stats,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx_colsum) {
+  extern __shared__ float sm[];  // (2 + CS) * C floats
+  constexpr int NCS = CS ? KV : 1;
   constexpr int R = 32 / G;
   const int lane = threadIdx.x & 31;
   const int sub = lane % G;
   const int vecs = C / 8;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  for (int i = threadIdx.x; i < (CS ? 3 : 2) * C; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
-  float ag[KV][8], ab[KV][8], gm[KV][8];
+  float ag[KV][8], ab[KV][8], gm[KV][8], ac[NCS][8];
 #pragma unroll
   for (int k = 0; k < KV; ++k) {
     const int v = sub + G * k;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       ag[k][j] = ab[k][j] = 0.f;
+      if (CS) ac[k][j] = 0.f;
       gm[k][j] = v < vecs ? gamma[v * 8 + j] : 0.f;
     }
   }
@@ -170,6 +176,16 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bf
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rstd * (g[k][j] - m1 - xh[k][j] * m2);
+        if (addend) {
+          float e[8];
+          unpack8v(*reinterpret_cast<const uint4*>(addend + row * ldadd + v * 8), e);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += e[j];
+        }
+        if (CS) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ac[k][j] += o[j];
+        }
         *reinterpret_cast<uint4*>(dx + row * lddx + v * 8) = pack8v(o);
       }
     }
@@ -183,6 +199,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bf
       for (int o = G; o < 32; o <<= 1) {
         ag[k][j] += __shfl_xor_sync(0xffffffffu, ag[k][j], o);
         ab[k][j] += __shfl_xor_sync(0xffffffffu, ab[k][j], o);
+        if (CS) ac[k][j] += __shfl_xor_sync(0xffffffffu, ac[k][j], o);
       }
     }
     const int v = sub + G * k;
@@ -191,6 +208,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bf
       for (int j = 0; j < 8; ++j) {
         atomicAdd(&sm[v * 8 + j], ag[k][j]);
         atomicAdd(&sm[C + v * 8 + j], ab[k][j]);
+        if (CS) atomicAdd(&sm[2 * C + v * 8 + j], ac[k][j]);
       }
     }
   }
@@ -198,6 +216,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bf
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     atomicAdd(&dgamma[i], sm[i]);
     atomicAdd(&dbeta[i], sm[C + i]);
+    if (CS) atomicAdd(&dx_colsum[i], sm[2 * C + i]);
   }
 }
 
@@ -450,24 +469,35 @@ extern "C" int jg_layernorm_fwd(const void* x, int ldx, void* y, int ldy, int64_
   return JG_OK;
 }
 
-extern "C" int jg_layernorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int64_t rows,
-                                int C, const float* gamma, const float* stats, float* dgamma, float* dbeta,
+extern "C" int jg_layernorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx,
+                                const void* addend, int ldadd, int64_t rows, int C, const float* gamma,
+                                const float* stats, float* dgamma, float* dbeta, float* dx_colsum,
                                 jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   JG_CHECK(x && dy && dx && gamma && stats && dgamma && dbeta && rows > 0, JG_ERR_INVALID,
            "layernorm_bwd: null pointer / no rows");
   JG_CHECK(C % 8 == 0 && C > 0 && C <= 32 * kLnMaxVec * 8 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0,
            JG_ERR_INVALID, "layernorm_bwd: bad dims C=%d", C);
+  JG_CHECK(addend == nullptr || (ldadd % 8 == 0 && ldadd >= C), JG_ERR_INVALID, "layernorm_bwd: bad addend stride %d",
+           ldadd);
+  if (dx_colsum) JG_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, stream));
   JG_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, stream));
   JG_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, stream));
   int grid = grid_for(rows, 8 * ln_rows_per_warp(C / 8) * 8);  // >= 8 rows per lane group: few blocks, few atomics
   if (grid > num_sms() * 4) grid = num_sms() * 4;
-#define JG_LN_BWD(G, KV)                                                            \
-  layernorm_bwd_kernel<G, KV><<<grid, 256, 2 * C * sizeof(float), stream>>>(        \
-      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(dy), lddy, \
-      static_cast<__nv_bfloat16*>(dx), lddx, rows, C, gamma, stats, dgamma, dbeta)
+#define JG_LN_BWD_CS(G, KV, CS)                                                                            \
+  layernorm_bwd_kernel<G, KV, CS><<<grid, 256, (CS ? 3 : 2) * C * sizeof(float), stream>>>(                 \
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(dy), lddy,               \
+      static_cast<__nv_bfloat16*>(dx), lddx, static_cast<const __nv_bfloat16*>(addend), ldadd, rows, C, gamma, \
+      stats, dgamma, dbeta, dx_colsum)
+#define JG_LN_BWD(G, KV)                                 \
+  do {                                                   \
+    if (dx_colsum) JG_LN_BWD_CS(G, KV, true);            \
+    else JG_LN_BWD_CS(G, KV, false);                     \
+  } while (0)
   JG_LN_DISPATCH(C / 8, JG_LN_BWD);
 #undef JG_LN_BWD
+#undef JG_LN_BWD_CS
   JG_LAUNCH_CHECK();
   return JG_OK;
 }

@@ -259,13 +259,15 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5, pe=None, frames=1):
     return y, stats
 
 
-def layernorm_bwd(x, dy, gamma, stats):
+def layernorm_bwd(x, dy, gamma, stats, addend=None, colsum=None):
+    """-> (dx, dgamma, dbeta); dx += addend (bf16 rows); colsum ([C] fp32 buffer, optional) = column sums of dx."""
     n, h, w, c = x.shape
     dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
     dgamma = torch.empty((c,), dtype=torch.float32, device=x.device)
     dbeta = torch.empty((c,), dtype=torch.float32, device=x.device)
-    L.call("jg_layernorm_bwd", L.ptr(x), _ld(x), L.ptr(dy), _ld(dy), L.ptr(dx), _ld(dx), n * h * w, c, L.ptr(gamma),
-           L.ptr(stats), L.ptr(dgamma), L.ptr(dbeta), L.stream())
+    L.call("jg_layernorm_bwd", L.ptr(x), _ld(x), L.ptr(dy), _ld(dy), L.ptr(dx), _ld(dx), L.ptr(addend),
+           0 if addend is None else _ld(addend), n * h * w, c, L.ptr(gamma), L.ptr(stats), L.ptr(dgamma),
+           L.ptr(dbeta), L.ptr(colsum), L.stream())
     return dx, dgamma, dbeta
 
 

@@ -67,7 +67,7 @@ _SIGNATURES = {
     "jg_attn_fwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
     "jg_attn_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
     "jg_layernorm_fwd": [c_p, c_int, c_p, c_int, c_i64, c_int, c_f, c_p, c_p, c_p, c_int, c_int, c_p, c_p],
-    "jg_layernorm_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_p, c_p, c_p, c_p, c_p],
+    "jg_layernorm_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_p, c_p, c_p, c_p, c_p, c_p],
     "jg_temporal_attn_fwd": [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
     "jg_temporal_attn_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
     "jg_ddpm_step": [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -116,9 +116,11 @@ class TemporalTransformerBlock(nn.Module):
     def forward_nhwc(self, h, frames):
         for attn, norm in zip(self.attention_blocks, self.norms):
             pe = attn.pos_encoder.pe[0, :frames].contiguous() if attn.pos_encoder is not None else None
-            h = attn.forward_nhwc(ops.layer_norm(h, norm.weight, norm.bias, pe=pe, frames=frames, eps=norm.eps), h,
-                                  frames)
-        return self.ff.forward_nhwc(ops.layer_norm(h, self.ff_norm.weight, self.ff_norm.bias, eps=self.ff_norm.eps), h)
+            # h feeds the norm and the residual add: the tap sums both gradients inside the LayerNorm backward
+            normed, h = ops.layer_norm_tap(h, norm.weight, norm.bias, pe=pe, frames=frames, eps=norm.eps)
+            h = attn.forward_nhwc(normed, h, frames)
+        normed, h = ops.layer_norm_tap(h, self.ff_norm.weight, self.ff_norm.bias, eps=self.ff_norm.eps)
+        return self.ff.forward_nhwc(normed, h)
 
 
 class TemporalTransformer3DModel(nn.Module):

@@ -216,6 +216,31 @@ class LayerNormFn(torch.autograd.Function):
         return dx, dgamma, dbeta, None, None, None
 
 
+class LayerNormTapFn(torch.autograd.Function):
+    """LayerNorm that also hands its input through: returns (y, x_tap).  In the temporal transformer x feeds the norm
+    AND the residual add after the attention / feed-forward branch; the residual reads x_tap, so both gradients meet
+    inside the LayerNorm backward (dx = LN'(dy) + d_tap) and its column sums come out on the side — the bias gradient
+    of the Linear that produced x."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, pe, frames, eps):
+        y, stats = K.layernorm_fwd(x, gamma, beta, eps=eps, pe=pe, frames=frames)
+        ctx.save_for_backward(x, gamma, stats)
+        ctx.set_materialize_grads(False)
+        return y, x.detach()
+
+    @staticmethod
+    def backward(ctx, dy, dtap):
+        x, gamma, stats = ctx.saved_tensors
+        if dy is None:
+            return dtap, None, None, None, None, None
+        colsum = _colsum_buffer(x)
+        dx, dgamma, dbeta = K.layernorm_bwd(x, _rows(dy), gamma, stats, addend=None if dtap is None else _rows(dtap),
+                                            colsum=colsum)
+        dx._jg_colsum = (colsum, dx._version)
+        return dx, dgamma, dbeta, None, None, None
+
+
 class TemporalAttentionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, frames, heads):
@@ -403,6 +428,11 @@ def mix_qkv(qkv, qkv_ref):
 
 def layer_norm(x, gamma, beta, pe=None, frames=1, eps=1e-5):
     return LayerNormFn.apply(x, gamma, beta, pe, frames, eps)
+
+
+def layer_norm_tap(x, gamma, beta, pe=None, frames=1, eps=1e-5):
+    """-> (y, x_tap): the residual add that follows the normed branch must read x_tap (see LayerNormTapFn)."""
+    return LayerNormTapFn.apply(x, gamma, beta, pe, frames, eps)
 
 
 def temporal_attention(qkv, frames, heads):

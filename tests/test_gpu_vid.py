@@ -53,6 +53,14 @@ def test_layernorm_pe_fwd_bwd(K, case):
     dx, dg, db = K.layernorm_bwd(xd, nhwc(K, dy), gamma.cuda(), stats)
     assert rel(dx.float().cpu(), xr.grad.permute(0, 2, 3, 1)) < 1e-2
     assert rel(dg, gr.grad) < 3e-3 and rel(db, br.grad) < 3e-3
+    # residual hand-through: dx + addend in the same pass, column sums of the result on the side
+    add = bf16_round(torch.randn(n, c, hw, hw, generator=g))
+    cs = torch.empty(c, device="cuda")
+    dx2, dg2, db2 = K.layernorm_bwd(xd, nhwc(K, dy), gamma.cuda(), stats, addend=nhwc(K, add), colsum=cs)
+    want = dx.float() + nhwc(K, add).float()
+    assert rel(dx2.float().cpu(), want.cpu()) < 6e-3
+    assert rel(cs, want.reshape(-1, c).sum(0)) < 3e-3
+    assert rel(dg2, gr.grad) < 3e-3 and rel(db2, br.grad) < 3e-3
 
 
 @pytest.mark.parametrize("case", [(2, 8, 6, 64, 8), (1, 4, 5, 128, 8), (3, 3, 4, 512, 8), (2, 1, 3, 64, 4)])

@@ -1,7 +1,7 @@
 """Informative timings of the other SURVEY.md section 8(d) configurations through PaletteTrainer (not bench lines):
 cfg 4 = UNetGeneratorRefAttn (example_ddpm_unetref_viton.json: res_blocks [2,4,4,2], attention at ds 4 and 8, 128^2,
 batch 16), cfg 5 = UNetVid (example_ddpm_vid_mario.json: 8 frames; 64^2 native and 128^2, one clip per GPU).
-    python tools/gpu_time_configs.py [steps]
+    python tools/gpu_time_configs.py [steps] [all|ref|vid] [graph]
 """
 import os
 import sys
@@ -50,7 +50,8 @@ def clip_batch(frames, size, seed):
 
 if __name__ == "__main__":
     which = sys.argv[2] if len(sys.argv) > 2 else "all"
-    for graph in (False, True):
+    modes = (True,) if (len(sys.argv) > 3 and sys.argv[3] == "graph") else (False, True)
+    for graph in modes:
         if which in ("all", "ref"):
             unet = nets_ref.UNetGeneratorRefAttn(image_size=128, res_blocks=[2, 4, 4, 2], attn_res=[4, 8], **COMMON)
             d = synthetic.synthetic_batch(16, 128, 1)
