@@ -1,0 +1,50 @@
+"""CUT contrastive path, CPU side: the oracle restatement of PatchSampleF +
+PatchNCELoss + calculate_NCE_loss against the golden vectors of the unmodified reference (oracle/gen_golden_cut.py)."""
+import os
+
+import torch
+
+from oracle import cut_oracle as C
+from oracle.vid_oracle import init_params_from_shapes
+
+
+def test_cut_nce_oracle_matches_reference(golden_dir):
+    from oracle.gen_golden_cut import feature_maps
+    gold = torch.load(os.path.join(golden_dir, "cut_nce.pt"))
+    params = init_params_from_shapes(gold["shapes"], gold["wseed"])
+    assert {k: tuple(v.shape) for k, v in params.items()} == C.mlp_param_shapes([c for c, _, _ in gold["feats"]],
+                                                                                 gold["nc"])
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    feat_k = feature_maps(gold["kseed"])
+    feat_q = [f.requires_grad_(True) for f in feature_maps(gold["qseed"])]
+    k_pool = C.patch_sample(leaves, feat_k, gold["num_patches"], gold["ids"])
+    q_pool = C.patch_sample(leaves, feat_q, gold["num_patches"], gold["ids"])
+    for mine, ref in zip(k_pool + q_pool, gold["k_pool"] + gold["q_pool"]):
+        assert mine.shape == ref.shape and float((mine - ref).abs().max()) < 1e-6
+        assert float((mine.norm(dim=1) - 1).abs().max()) < 1e-5   # rows are L2-normalised
+    for i, ref in enumerate(gold["per_layer"]):
+        mine = C.patch_nce_loss(q_pool[i], k_pool[i], gold["batch"], gold["T"]) * gold["lambda_NCE"]
+        assert float((mine - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+    total = C.nce_loss_total(q_pool, k_pool, gold["batch"], gold["T"], gold["lambda_NCE"])
+    assert abs(float(total) - gold["loss"]) < 1e-6 * abs(gold["loss"])
+    total.backward()
+    for mine, ref in zip(feat_q, gold["dfeat_q"]):
+        assert float((mine.grad - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+    for k, ref in gold["grads"].items():
+        # the keys' MLP pass receives gradient through the (undetached) negatives, like the reference
+        assert float((leaves[k].grad - ref).abs().max()) < 1e-5 * float(ref.abs().max()), k
+
+
+def test_cut_nce_all_negatives_and_small_maps():
+    """Edge cases the reference handles: fewer positions than num_patches (the id list is clamped), negatives from the
+    whole minibatch (one bmm group); with identical q and k the positive logit is 1 and the loss is small, and more
+    negatives can only raise it."""
+    g = torch.Generator().manual_seed(0)
+    feats = [torch.randn(2, 8, 2, 2, generator=g)]
+    ids = [torch.randperm(4, generator=g)]
+    pooled = C.patch_sample(None, feats, 16, ids, use_mlp=False)
+    assert pooled[0].shape == (2 * 4, 8)
+    same = C.patch_nce_loss(pooled[0], pooled[0], 2, T=0.07)
+    assert same.shape == (8,) and float(same.max()) < 5e-2
+    allneg = C.patch_nce_loss(pooled[0], pooled[0], 2, T=0.07, all_negatives_from_minibatch=True)
+    assert allneg.shape == (8,) and bool((allneg >= same - 1e-7).all()) and float(allneg.max()) < 5e-2
