@@ -285,6 +285,26 @@ int jg_gan_loss_fwd(const void* pred, int ld, int64_t rows, int C, int mode, flo
 int jg_gan_loss_bwd(const void* pred, int ld, int64_t rows, int C, int mode, float target, float sign,
                     const float* grad_out, void* dpred, int ldd, jg_stream_t stream);
 
+/* ---- CUT contrastive path (written in round 1, NOT yet verified on hardware) ----
+ * PatchSampleF.forward (models/modules/cut_networks.py:38-73): dst[b*P + p] = src[b*HW + ids[p]] (bf16 rows, the same
+ * ids for every image); the backward zeroes dsrc [B*HW rows] and scatters.  ids: int64 on the device, distinct. */
+int jg_gather_rows(const void* src, int lds, const int64_t* ids, void* dst, int ldd, int B, int HW, int P, int C,
+                   jg_stream_t stream);
+int jg_gather_rows_bwd(const void* ddst, int ldd, const int64_t* ids, void* dsrc, int lds, int B, int HW, int P, int C,
+                       jg_stream_t stream);
+/* torch.nn.functional.normalize(x, eps) over D features (cut_networks.py:66): bf16 rows in, fp32 [rows][D] out,
+ * norms [rows] kept for the backward (dx bf16). */
+int jg_l2norm_fwd(const void* x, int ldx, float* y, float* norms, int64_t rows, int D, float eps, jg_stream_t stream);
+int jg_l2norm_bwd(const float* y, const float* dy, const float* norms, void* dx, int lddx, int64_t rows, int D,
+                  float eps, jg_stream_t stream);
+/* PatchNCELoss (models/modules/NCE/base_NCE.py:17-77): q, k fp32 [G*P][D]; G groups of P patches (G = batch, or 1 with
+ * P = batch * patches for --alg_cut_nce_includes_all_negatives_from_minibatch); loss / lse [G*P].  Backward:
+ * grad_loss [G*P]; dq and/or dk [G*P][D] (k receives gradient through the negatives only, like the reference). */
+int jg_patch_nce_fwd(const float* q, const float* k, int G, int P, int D, float T, float* loss, float* lse,
+                     jg_stream_t stream);
+int jg_patch_nce_bwd(const float* q, const float* k, const float* lse, const float* grad_loss, int G, int P, int D,
+                     float T, float* dq, float* dk, jg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

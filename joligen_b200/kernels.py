@@ -441,3 +441,58 @@ def gan_loss_bwd(pred, c_real, mode, target, sign, grad_out):
     L.call("jg_gan_loss_bwd", L.ptr(pred), _ld(pred), n * h * w, c_real, mode, float(target), float(sign),
            L.ptr(grad_out), L.ptr(d), c, L.stream())
     return d
+
+
+# ---- CUT contrastive path (csrc/nce.cu; not yet verified on hardware, see tests/test_gpu_cut.py) ---------------------
+def gather_rows(feat, ids):
+    """feat NHWC bf16 [B,H,W,C]; ids int64 [P] on the device (distinct positions in [0, H*W)).
+    -> [B*P, C] bf16: the same positions of every image (PatchSampleF.forward, cut_networks.py:44-56)."""
+    b, h, w, c = feat.shape
+    p = ids.numel()
+    out = torch.empty((b * p, c), dtype=torch.bfloat16, device=feat.device)
+    L.call("jg_gather_rows", L.ptr(feat), _ld(feat), L.ptr(ids), L.ptr(out), c, b, h * w, p, c, L.stream())
+    return out
+
+
+def gather_rows_bwd(d_out, ids, shape):
+    b, h, w, c = shape
+    p = ids.numel()
+    d_feat = torch.empty((b, h, w, c), dtype=torch.bfloat16, device=d_out.device)
+    L.call("jg_gather_rows_bwd", L.ptr(d_out), d_out.stride(0), L.ptr(ids), L.ptr(d_feat), c, b, h * w, p, c,
+           L.stream())
+    return d_feat
+
+
+def l2norm_fwd(x, eps=1e-7):
+    """x bf16 [rows, D] -> (y fp32 [rows, D], norms fp32 [rows]) = F.normalize(x, dim=1, eps)."""
+    rows, d = x.shape
+    y = torch.empty((rows, d), dtype=torch.float32, device=x.device)
+    norms = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    L.call("jg_l2norm_fwd", L.ptr(x), x.stride(0), L.ptr(y), L.ptr(norms), rows, d, float(eps), L.stream())
+    return y, norms
+
+
+def l2norm_bwd(y, dy, norms, eps=1e-7):
+    rows, d = y.shape
+    dx = torch.empty((rows, d), dtype=torch.bfloat16, device=y.device)
+    L.call("jg_l2norm_bwd", L.ptr(y), L.ptr(dy), L.ptr(norms), L.ptr(dx), d, rows, d, float(eps), L.stream())
+    return dx
+
+
+def patch_nce_fwd(q, k, groups, temperature):
+    """q, k fp32 [groups*P, D] -> (loss [groups*P], lse [groups*P])."""
+    rows, d = q.shape
+    loss = torch.empty((rows,), dtype=torch.float32, device=q.device)
+    lse = torch.empty((rows,), dtype=torch.float32, device=q.device)
+    L.call("jg_patch_nce_fwd", L.ptr(q), L.ptr(k), groups, rows // groups, d, float(temperature), L.ptr(loss),
+           L.ptr(lse), L.stream())
+    return loss, lse
+
+
+def patch_nce_bwd(q, k, lse, grad_loss, groups, temperature, need_dq=True, need_dk=True):
+    rows, d = q.shape
+    dq = torch.empty_like(q) if need_dq else None
+    dk = torch.empty_like(k) if need_dk else None
+    L.call("jg_patch_nce_bwd", L.ptr(q), L.ptr(k), L.ptr(lse), L.ptr(grad_loss), groups, rows // groups, d,
+           float(temperature), L.ptr(dq), L.ptr(dk), L.stream())
+    return dq, dk

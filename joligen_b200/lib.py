@@ -87,6 +87,12 @@ _SIGNATURES = {
     "jg_act_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_int, c_p],
     "jg_gan_loss_fwd": [c_p, c_int, c_i64, c_int, c_int, c_f, c_f, c_p, c_p],
     "jg_gan_loss_bwd": [c_p, c_int, c_i64, c_int, c_int, c_f, c_f, c_p, c_p, c_int, c_p],
+    "jg_gather_rows": [c_p, c_int, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_gather_rows_bwd": [c_p, c_int, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_l2norm_fwd": [c_p, c_int, c_p, c_p, c_i64, c_int, c_f, c_p],
+    "jg_l2norm_bwd": [c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_f, c_p],
+    "jg_patch_nce_fwd": [c_p, c_p, c_int, c_int, c_int, c_f, c_p, c_p, c_p],
+    "jg_patch_nce_bwd": [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_f, c_p, c_p, c_p],
 }
 _U64_FUNCS = {"jg_kernel_launches": []}
 _SIZE_T_FUNCS = {

@@ -640,3 +640,62 @@ def add(a, b):
 
 def gan_loss(pred, c_real, mode, target=1.0, sign=1.0):
     return GanLossFn.apply(pred, c_real, mode, target, sign)
+
+
+# ---- CUT contrastive path (not yet verified on hardware, see tests/test_gpu_cut.py) ----------------------------------
+class GatherRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, ids):
+        ctx.save_for_backward(ids)
+        ctx.shape = tuple(feat.shape)
+        return K.gather_rows(feat.contiguous(), ids)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (ids,) = ctx.saved_tensors
+        return K.gather_rows_bwd(d_out.contiguous(), ids, ctx.shape), None
+
+
+class L2NormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps):
+        y, norms = K.l2norm_fwd(x.contiguous(), eps)
+        ctx.save_for_backward(y, norms)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, norms = ctx.saved_tensors
+        return K.l2norm_bwd(y, dy.contiguous().float(), norms, ctx.eps), None
+
+
+class PatchNceFn(torch.autograd.Function):
+    """loss per patch of PatchNCELoss; q and k both receive gradient (k through the negatives only)."""
+
+    @staticmethod
+    def forward(ctx, q, k, groups, temperature):
+        q, k = q.contiguous().float(), k.contiguous().float()
+        loss, lse = K.patch_nce_fwd(q, k, groups, temperature)
+        ctx.save_for_backward(q, k, lse)
+        ctx.cfg = (groups, temperature)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        q, k, lse = ctx.saved_tensors
+        groups, temperature = ctx.cfg
+        dq, dk = K.patch_nce_bwd(q, k, lse, g.contiguous().float(), groups, temperature, _needs(ctx, 0), _needs(ctx, 1))
+        return dq, dk, None, None
+
+
+def gather_rows(feat, ids):
+    return GatherRowsFn.apply(feat, ids)
+
+
+def l2_normalize(x, eps=1e-7):
+    return L2NormFn.apply(x, eps)
+
+
+def patch_nce(q, k, groups, temperature):
+    return PatchNceFn.apply(q, k, groups, temperature)

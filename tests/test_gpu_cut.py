@@ -1,0 +1,110 @@
+"""CUT contrastive path on the GPU: csrc/nce.cu + joligen_b200/nets_cut.py against
+oracle/cut_oracle.py and the reference's golden vectors (tests/golden/cut_nce.pt).
+
+SKIPPED: the kernels were written after round 1's GPU minutes were spent.  They compile for sm_100a but have never run
+on hardware — first task of the next round: remove the skip, run, fix.  (The oracle side is pinned: test_cut_oracle.py.)
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skip(reason="csrc/nce.cu is not yet verified on hardware (written without GPU time left)")]
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from joligen_b200 import kernels
+    return kernels
+
+
+def rel(a, b):
+    return float((a.float().cpu() - b.float().cpu()).abs().max()) / (float(b.float().abs().max()) + 1e-12)
+
+
+def test_gather_rows_bit_exact(K):
+    g = torch.Generator().manual_seed(0)
+    feat = torch.randn(3, 6, 5, 16, generator=g).bfloat16().cuda()
+    ids = torch.randperm(30, generator=g)[:7].cuda()
+    out = K.gather_rows(feat, ids)
+    ref = feat.reshape(3, 30, 16)[:, ids, :].reshape(21, 16)
+    assert torch.equal(out, ref)
+    d_out = torch.randn(21, 16, generator=g).bfloat16().cuda()
+    d_feat = K.gather_rows_bwd(d_out, ids, tuple(feat.shape))
+    want = torch.zeros(3, 30, 16, dtype=torch.bfloat16, device="cuda")
+    want[:, ids, :] = d_out.reshape(3, 7, 16)
+    assert torch.equal(d_feat.reshape(3, 30, 16), want)
+
+
+@pytest.mark.parametrize("d", [32, 256, 512])
+def test_l2norm_fwd_bwd(K, d):
+    g = torch.Generator().manual_seed(d)
+    x = torch.randn(37, d, generator=g).bfloat16().float()
+    x[3] = 0.0  # the eps clamp
+    dy = torch.randn(37, d, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = F.normalize(xr, eps=1e-7)
+    ref.backward(dy)
+    y, norms = K.l2norm_fwd(x.bfloat16().cuda(), 1e-7)
+    assert rel(y, ref.detach()) < 1e-6
+    dx = K.l2norm_bwd(y, dy.cuda(), norms, 1e-7)
+    keep = torch.arange(37) != 3
+    assert rel(dx[keep], xr.grad[keep]) < 6e-3  # bf16 output
+
+
+@pytest.mark.parametrize("groups", [2, 1])
+def test_patch_nce_fwd_bwd_vs_oracle(K, groups):
+    from oracle import cut_oracle as C
+    g = torch.Generator().manual_seed(5)
+    batch, p, d = 2, 48, 256
+    q = F.normalize(torch.randn(batch * p, d, generator=g)).requires_grad_(True)
+    k = F.normalize(torch.randn(batch * p, d, generator=g)).requires_grad_(True)
+    gout = torch.rand(batch * p, generator=g)
+    ref = C.patch_nce_loss(q, k, batch, T=0.07, all_negatives_from_minibatch=(groups == 1))
+    ref.backward(gout)
+    loss, lse = K.patch_nce_fwd(q.detach().cuda(), k.detach().cuda(), groups, 0.07)
+    assert rel(loss, ref.detach()) < 1e-4
+    dq, dk = K.patch_nce_bwd(q.detach().cuda(), k.detach().cuda(), lse, gout.cuda(), groups, 0.07)
+    assert rel(dq, q.grad) < 1e-4 and rel(dk, k.grad) < 1e-4
+
+
+def test_patch_sample_and_nce_vs_reference_golden(golden_dir):
+    """PatchSampleF (gather -> MLP as 1x1 convolutions -> L2 norm) + PatchNCELoss + calculate_NCE_loss against the
+    unmodified reference: loss, d loss / d query features, MLP gradients (incl. the part through the keys)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from types import SimpleNamespace
+    from joligen_b200 import nets_cut
+    from oracle.gen_golden_cut import feature_maps
+    from oracle.vid_oracle import init_params_from_shapes
+    gold = torch.load(os.path.join(golden_dir, "cut_nce.pt"))
+    params = init_params_from_shapes(gold["shapes"], gold["wseed"])
+    netF = nets_cut.PatchSampleF(use_mlp=True, nc=gold["nc"])
+    netF.set_device(torch.device("cuda"))
+    feat_k = [f.cuda() for f in feature_maps(gold["kseed"])]
+    feat_q = [f.cuda().requires_grad_(True) for f in feature_maps(gold["qseed"])]
+    netF.data_dependent_initialize(feat_k)
+    assert [(k, tuple(v.shape)) for k, v in netF.named_parameters()] == [(k, tuple(s)) for k, s in gold["shapes"]]
+    netF.load_state_dict(params)
+    netF = netF.cuda()
+    opt = SimpleNamespace(alg_cut_nce_T=gold["T"], alg_cut_nce_includes_all_negatives_from_minibatch=False,
+                          alg_cut_num_patches=gold["num_patches"])
+    crit = nets_cut.PatchNCELoss(opt)
+    ids = [i.cuda() for i in gold["ids"]]
+    k_pool, ids_out = netF(feat_k, gold["num_patches"], ids)
+    q_pool, _ = netF(feat_q, gold["num_patches"], ids_out)
+    for mine, ref in zip(k_pool + q_pool, gold["k_pool"] + gold["q_pool"]):
+        assert rel(mine, ref) < 2e-2
+    total = sum((crit(feat_q=fq, feat_k=fk, current_batch=gold["batch"]) * gold["lambda_NCE"]).mean()
+                for fq, fk in zip(q_pool, k_pool)) / len(q_pool)
+    assert abs(float(total) - gold["loss"]) < 2e-2 * abs(gold["loss"])
+    total.backward()
+    for mine, ref in zip(feat_q, gold["dfeat_q"]):
+        assert rel(mine.grad, ref) < 5e-2
+    named = dict(netF.named_parameters())
+    for k, ref in gold["grads"].items():
+        assert float((named[k].grad.cpu() - ref).norm()) < 5e-2 * float(ref.norm()) + 1e-6, k
