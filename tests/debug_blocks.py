@@ -1,5 +1,6 @@
-"""Per-block error localisation: every UNet block is fed the SAME (bf16-rounded) input on the CPU
-oracle (bf16-storage emulation and fp32) and on the CUDA path; prints rel-L2 of the block outputs."""
+"""Debug aid (test infrastructure: it lives under tests/ because it calls the oracle).  Per-block error localisation:
+every UNet block is fed the SAME (bf16-rounded) input on the CPU oracle (bf16-storage emulation and fp32) and on the
+CUDA path; prints rel-L2 of the block outputs.        python tests/debug_blocks.py"""
 import os
 import sys
 

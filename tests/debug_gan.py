@@ -1,4 +1,5 @@
-"""Per-parameter gradient errors of the B200 ResnetGenerator vs the reference golden (debug aid)."""
+"""Debug aid (test infrastructure: it lives under tests/ because it calls the oracle): per-parameter gradient errors
+of the B200 ResnetGenerator vs the reference golden.        python tests/debug_gan.py"""
 import os
 import sys
 
