@@ -6,7 +6,8 @@ in the build container (TEST INFRASTRUCTURE — see oracle/__init__.py).
 Fixture: PatchSampleF(use_mlp=True, nc=256) + PatchNCELoss (T 0.07, negatives from the same image) on five seeded
 feature maps shaped like ResnetGenerator.get_feats(nce_layers 0,4,8,12,16) at reduced resolution, batch 2, 16
 patches per layer; seeded MLP weights; the reference's own randperm draws are stored.  Values: pooled features,
-per-layer per-patch losses, total loss, gradients w.r.t. the query features and the MLP parameters.
+per-layer per-patch losses, total loss, gradients w.r.t. the query features (full) and the MLP parameters (sum, L2,
+first 16 values).
 """
 import os
 import sys
@@ -60,7 +61,8 @@ def main():
            "k_pool": [k.detach().clone() for k in k_pool], "q_pool": [q.detach().clone() for q in q_pool],
            "per_layer": [p.detach().clone() for p in per_layer], "loss": float(total.detach()),
            "dfeat_q": [f.grad.clone() for f in feat_q],
-           "grads": {k: p.grad.clone() for k, p in netF.named_parameters()}}
+           "grads": {k: {"sum": float(p.grad.double().sum()), "l2": float(p.grad.double().norm()),
+                         "head": p.grad.flatten()[:16].clone()} for k, p in netF.named_parameters()}}
     torch.save(out, os.path.join(GOLDEN, "cut_nce.pt"))
     # the restatement against the reference, right here
     leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}

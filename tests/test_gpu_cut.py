@@ -107,4 +107,5 @@ def test_patch_sample_and_nce_vs_reference_golden(golden_dir):
         assert rel(mine.grad, ref) < 5e-2
     named = dict(netF.named_parameters())
     for k, ref in gold["grads"].items():
-        assert float((named[k].grad.cpu() - ref).norm()) < 5e-2 * float(ref.norm()) + 1e-6, k
+        assert abs(float(named[k].grad.double().norm()) - ref["l2"]) < 5e-2 * ref["l2"] + 1e-6, k
+        assert float((named[k].grad.flatten()[:16].cpu() - ref["head"]).norm()) < 5e-2 * ref["l2"] + 1e-6, k
