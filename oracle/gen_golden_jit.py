@@ -83,7 +83,13 @@ def main():
         g = p.grad if p.grad is not None else torch.zeros_like(p)
         grads[k] = {"sum": float(g.double().sum()), "l2": float(g.double().norm()), "head": g.flatten()[:16].clone(),
                     "none": p.grad is None}
-    torch.save({"cfg": CFG, "batch": batch, "frames": frames, "wseed": 12, "dseed": 14, "rseed": rseed,
+    # sampling: 3 denoising steps (2 Heun + the final Euler step), guidance neutral
+    net.eval()
+    torch.manual_seed(rseed + 1)
+    init_noise = torch.randn_like(gt)
+    restored = net.restoration(gt, cond, denoise_timesteps=3, mask=mask, labels=label, init_noise=init_noise)
+    net.train()
+    torch.save({"cfg": CFG, "restored": restored.clone(), "denoise_timesteps": 3, "batch": batch, "frames": frames, "wseed": 12, "dseed": 14, "rseed": rseed,
                 "t_base": t_base, "torch_version": str(torch.__version__), "shapes": shapes, "frozen": frozen,
                 "x_pred": x_pred.detach().clone(), "loss": float(loss.detach()), "grads": grads},
                os.path.join(GOLDEN, "jit_small.pt"))
@@ -93,6 +99,9 @@ def main():
     vp2, v2, xp2 = J.b2b_forward(sd, gt, mask, cond, label, t_base, e, cfg)
     lo = J.masked_region_loss(vp2, v2, mb)
     lo.backward()
+    rest2 = J.restoration(J.add_buffers({**params, **frozen}, cfg), gt, cond, mask, label, init_noise, cfg, steps=3)
+    print("restoration: oracle vs reference rel max err %.2e" % float((rest2 - restored).abs().max() /
+                                                                        restored.abs().max()))
     zero = lambda g, p: g if g is not None else torch.zeros_like(p)  # noqa: E731
     named = dict(net.named_parameters())
     gerr = max(float((zero(leaves[k].grad, leaves[k]) - zero(named[k].grad, named[k])).norm() /

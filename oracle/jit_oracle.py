@@ -233,3 +233,49 @@ def b2b_loss(sd, x, mask, x_cond, label, t_base, e, cfg: JitCfg, kind="pseudo_hu
         raise NotImplementedError(kind)
     c = 0.00054 * math.sqrt(math.prod(v_pred.shape[1:]))
     return lambda_G * torch.mean(torch.sqrt((mb * v_pred - mb * v) ** 2 + c ** 2) - c)
+
+
+def restoration(sd, y, y_cond, mask, labels, init_noise, cfg: JitCfg, steps: int, clip_denoised=False,
+                disable_inference_clipping=True, prefix="b2b_model."):
+    """B2BGenerator.restoration (b2b_generator.py:406-500) with cfg_scale 1 (guidance neutral): Heun steps on the
+    linspace(0, 1, steps + 1) grid, a final Euler step, known pixels re-projected after every step, final clamp.
+    y / y_cond [B, F, C, H, W]; init_noise = the randn_like(y) draw."""
+    b, f = y.shape[:2]
+    if mask is not None:
+        mask = torch.clamp(mask, 0.0, 1.0)
+        y_background = y * (1.0 - mask)
+    else:
+        y_background = y
+    if labels is None:
+        labels = torch.zeros(b, dtype=torch.long)
+    x = y_background + init_noise * cfg.noise_scale
+    if mask is not None:
+        x = x * mask + y * (1.0 - mask)
+    ts = torch.linspace(0.0, 1.0, steps + 1)
+
+    def project(v):
+        return v if mask is None else v * mask + y * (1.0 - mask)
+
+    def velocity(xc, t):
+        x_in = project(xc)
+        inp = x_in if y_cond is None else torch.cat([y_cond, x_in], dim=2)
+        xp = jit_vid_forward(sd, inp, torch.full((b * f,), float(t)), labels, cfg, prefix=prefix)
+        xp = project(xp[:, :, -x_in.shape[2]:])
+        den = 1.0 - t
+        if not disable_inference_clipping:
+            den = den.clamp_min(cfg.t_eps)
+        return (xp - x_in) / den
+
+    with torch.no_grad():
+        for i in range(steps - 1):
+            t, tn = ts[i], ts[i + 1]
+            v_t = velocity(x, t)
+            v_n = velocity(x + (tn - t) * v_t, tn)
+            x = x + (tn - t) * 0.5 * (v_t + v_n)
+            if clip_denoised:
+                x = x.clamp(-1.0, 1.0)
+            x = project(x)
+        x = x + (ts[-1] - ts[-2]) * velocity(x, ts[-2])
+        if clip_denoised:
+            x = x.clamp(-1.0, 1.0)
+        return project(x).clamp(-1.0, 1.0)

@@ -35,6 +35,22 @@ def test_jit_b2b_oracle_matches_reference(golden_dir):
         assert float((mine.flatten()[:16] - g["head"]).abs().max()) < 1e-4 * max(g["l2"], 1e-3 * scale), k
 
 
+def test_b2b_restoration_oracle_matches_reference(golden_dir):
+    """B2BGenerator.restoration: Heun steps + the final Euler step on the flow ODE, known pixels re-projected."""
+    from oracle.gen_golden_jit import inputs
+    gold = torch.load(os.path.join(golden_dir, "jit_small.pt"))
+    cfg = J.JitCfg(**gold["cfg"])
+    params = init_params_from_shapes(gold["shapes"], gold["wseed"])
+    gt, cond, mask, label = inputs(cfg, gold["batch"], gold["frames"], gold["dseed"])
+    torch.manual_seed(gold["rseed"] + 1)
+    init_noise = torch.randn_like(gt)
+    sd = J.add_buffers({**params, **gold["frozen"]}, cfg)
+    out = J.restoration(sd, gt, cond, mask, label, init_noise, cfg, steps=gold["denoise_timesteps"])
+    assert float((out - gold["restored"]).abs().max()) < 1e-4 * float(gold["restored"].abs().max())
+    m = mask.bool().expand_as(gt)
+    assert torch.equal(out[~m], gt[~m].clamp(-1, 1))
+
+
 def test_rope_tables_and_unpatchify():
     cfg = J.JitCfg(input_size=32, patch_size=8, hidden_size=96, num_heads=6, in_context_len=4)
     cos, sin = J.rope_tables(cfg, 4)
