@@ -336,7 +336,7 @@ def main():
             "step_tflops_algorithmic": alg_flops_step / (ms / 1000.0) / 1e12,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_tflops"], "traffic": conv_traffic(len(recs)),
-                         "kernel": "conv_fwd_kernel + conv_wgrad_kernel (all %d implicit-GEMM launches of one step)"
+                         "kernel": "conv_halo / conv_fwd / wgrad_halo / conv_wgrad kernels (all %d implicit-GEMM calls of one step)"
                                    % len(recs),
                          "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms,
                          "padded_flops_over_algorithmic": conv_flops_padded / alg_flops_step,
