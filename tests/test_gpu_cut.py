@@ -109,3 +109,34 @@ def test_patch_sample_and_nce_vs_reference_golden(golden_dir):
     for k, ref in gold["grads"].items():
         assert abs(float(named[k].grad.double().norm()) - ref["l2"]) < 5e-2 * ref["l2"] + 1e-6, k
         assert float((named[k].grad.flatten()[:16].cpu() - ref["head"]).norm()) < 5e-2 * ref["l2"] + 1e-6, k
+
+
+def test_multi_scale_d_vs_reference_golden(golden_dir):
+    """nets_projd.MultiScaleD (spectral-norm 4x4 stride-2 convs, GroupNorm(c/2) + LeakyReLU, 4x4 valid conv) on feature
+    maps against the unmodified reference: logits, hinge loss, parameter / feature gradients, power-iteration state."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from joligen_b200 import nets_projd
+    from oracle.gen_golden_projd import features, seeded_state
+    gold = torch.load(os.path.join(golden_dir, "projd_small.pt"))
+    net = nets_projd.MultiScaleD(channels=gold["channels"], resolutions=gold["resolutions"], conv=True, feats=None,
+                                 num_discs=len(gold["channels"]))
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(s)) for k, s in gold["shapes"]]
+    net.load_state_dict(seeded_state(gold["shapes"], gold["wseed"]))
+    net = net.cuda().train()
+    feats = {k: v.cuda().requires_grad_(True) for k, v in features(gold["fseed"]).items()}
+    logits = net(feats)
+    assert logits.shape == gold["logits"].shape
+    assert rel(logits, gold["logits"]) < 2e-2
+    loss = F.relu(torch.ones_like(logits) - logits).mean()
+    assert abs(float(loss) - gold["loss"]) < 2e-2 * abs(gold["loss"])
+    loss.backward()
+    named = dict(net.named_parameters())
+    scale = max(g["l2"] for g in gold["grads"].values())
+    for k, g in gold["grads"].items():
+        assert abs(float(named[k].grad.double().norm()) - g["l2"]) < 5e-2 * max(g["l2"], 1e-2 * scale), k
+    for k, ref in gold["dfeats"].items():
+        assert rel(feats[k].grad, ref) < 5e-2
+    sd = net.state_dict()
+    for k, ref in gold["uv_after"].items():     # the power iteration is fp32 torch arithmetic: tight
+        assert float((sd[k].cpu() - ref).abs().max()) < 1e-5, k
