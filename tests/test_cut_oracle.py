@@ -49,3 +49,35 @@ def test_cut_nce_all_negatives_and_small_maps():
     assert same.shape == (8,) and float(same.max()) < 5e-2
     allneg = C.patch_nce_loss(pooled[0], pooled[0], 2, T=0.07, all_negatives_from_minibatch=True)
     assert allneg.shape == (8,) and bool((allneg >= same - 1e-7).all()) and float(allneg.max()) < 5e-2
+
+
+def test_cut_train_steps_match_reference_plumbing(golden_dir):
+    """BASELINE.json config 3 through the reference's own control path (options -> create_model -> two
+    optimize_parameters(): G_A + F group, then D group; MoNCE with Sinkhorn weights, the example's default): the oracle's
+    cut_train_step reproduces every loss of both steps and the parameters afterwards."""
+    from oracle import palette_oracle as O
+    from oracle.gen_golden_cut_plumbing import batch, patch_ids
+    gold = torch.load(os.path.join(golden_dir, "cut_plumbing.pt"))
+    opt, cut = gold["optim"], gold["cut"]
+    assert cut["nce_loss"] == "monce" and cut["iter_size"] == 1 and not cut["G_ema"]
+    sG, sF, sD = (O.TrainState(params=init_params_from_shapes(gold[k], seed))
+                  for k, seed in zip(("shapes_G", "shapes_F", "shapes_D"), gold["seeds"]))
+    mk = lambda lr: O.OptimCfg(lr=lr, beta1=opt["beta1"], beta2=opt["beta2"], eps=opt["eps"],  # noqa: E731
+                               weight_decay=opt["weight_decay"], kind=opt["kind"], ema_beta=0.0)
+    for step in range(2):
+        a, b = batch(gold["data_seeds"][step])
+        ids_a, ids_b = patch_ids(gold["rng_seeds"][step], cut["hw"])
+        lo = C.cut_train_step(sG, sF, sD, mk(opt["G_lr"]), mk(opt["G_lr"]), mk(opt["D_lr"]), a, b, ids_a, ids_b,
+                              cut["nce_layers"], n_blocks=gold["n_blocks"], n_layers=3, lambda_gan=cut["lambda_GAN"],
+                              lambda_nce=cut["lambda_NCE"], T=cut["T"], num_patches=cut["num_patches"],
+                              mode=cut["gan_mode"], nce_idt=cut["nce_idt"], nce_kind=cut["nce_loss"])
+        ref = gold["losses"][step]
+        for mine, key in ((lo["G_tot"], "G_tot"), (lo["G_GAN"], "G_GAN_D_B_basic"), (lo["G_NCE"], "G_NCE"),
+                          (lo["G_NCE_Y"], "G_NCE_Y"), (lo["D_tot"], "D_tot")):
+            assert abs(mine - ref[key]) < 1e-5 * abs(ref[key]), (step, key, mine, ref[key])
+    for state, stats in ((sG, gold["stats_G"]), (sF, gold["stats_F"]), (sD, gold["stats_D"])):
+        for k, (s, n) in stats.items():
+            # a bias in front of an InstanceNorm has a zero gradient in exact arithmetic: Adam turns its rounding noise
+            # into +-lr steps that no two implementations share
+            tol = 5e-2 if k.endswith(".bias") else 1e-4
+            assert abs(float(state.params[k].double().norm()) - n) <= tol * n + 1e-9, k
