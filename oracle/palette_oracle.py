@@ -515,11 +515,16 @@ def adam_update(state: TrainState, grads: Dict[str, torch.Tensor], oc: OptimCfg)
 
 
 def train_step(state: TrainState, cfg: UNetCfg, oc: OptimCfg, y_0, y_cond, mask, noise, t, u,
-               lambda_G=1.0, use_minsnr=False):
+               lambda_G=1.0, use_minsnr=False, forward=None):
     """One optimize_parameters() of the palette group: forward + loss + backward + Adam(W) + EMA.
-    Returns (loss, noise_hat, grads)."""
+    Returns (loss, noise_hat, grads).  forward(leaves) -> (noise, noise_hat, w): the generator forward for the other
+    denoisers (reference-attention UNet: diffusion_forward(..., unet=ref_oracle.denoiser(ref)); video UNet:
+    vid_oracle.diffusion_forward_vid); default = the plain UNet."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in state.params.items()}
-    _, noise_hat, w = diffusion_forward(leaves, y_0, y_cond, mask, noise, t, u, cfg)
+    if forward is None:
+        _, noise_hat, w = diffusion_forward(leaves, y_0, y_cond, mask, noise, t, u, cfg)
+    else:
+        _, noise_hat, w = forward(leaves)
     loss = palette_loss(noise, noise_hat, mask, w, lambda_G, use_minsnr)
     (loss / oc.iter_size).backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
