@@ -71,7 +71,7 @@ def main():
     e = torch.randn_like(gt)
     import math
     c = 0.00054 * math.sqrt(math.prod(v_pred.shape[1:]))
-    mb = torch.clamp(mask, 0, 1).expand_as(v_pred)
+    mb = torch.clamp(mask, 0, 1)     # one channel: broadcast in the numerator only, like B2BModel._masked_region_loss
     le = torch.sqrt((v_pred - v) ** 2 + c ** 2) - c
     dims = tuple(range(1, le.ndim))
     loss = ((le * mb).sum(dim=dims) / mb.sum(dim=dims).clamp_min(1e-8)).mean()     # _masked_region_loss

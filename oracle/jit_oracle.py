@@ -206,7 +206,9 @@ def b2b_forward(sd, x, mask, x_cond, label, t_base, e, cfg: JitCfg, prefix="b2b_
 
 
 def masked_region_loss(pred, target, mask, kind="pseudo_huber", eps=1e-8):
-    """B2BModel._masked_region_loss: the mean over the batch of (sum of the masked per-element loss / mask area)."""
+    """B2BModel._masked_region_loss: the mean over the batch of (sum of the masked per-element loss / mask sum).  The
+    mask is passed as the model holds it — ONE channel, broadcast over the image channels in the numerator but not in
+    the denominator — so the value is `channels` times a per-element mean (pinned by b2b_plumbing.pt)."""
     if kind == "MSE":
         le = (pred - target) ** 2
     elif kind == "L1":
@@ -226,7 +228,6 @@ def b2b_loss(sd, x, mask, x_cond, label, t_base, e, cfg: JitCfg, kind="pseudo_hu
     frozen networks, out of scope) and without min-SNR weighting."""
     v_pred, v, _ = b2b_forward(sd, x, mask, x_cond, label, t_base, e, cfg, prefix=prefix)
     mb = torch.clamp(mask, min=0, max=1)
-    mb = mb.expand_as(v_pred) if mb.shape != v_pred.shape else mb
     if masked_region_only:
         return lambda_G * masked_region_loss(v_pred, v, mb, kind)
     if kind != "pseudo_huber":

@@ -25,7 +25,7 @@ def test_jit_b2b_oracle_matches_reference(golden_dir):
     assert float((x_pred - gold["x_pred"]).abs().max()) < 1e-5 * float(gold["x_pred"].abs().max())
     m = mask.bool().expand_as(gt)
     assert torch.equal(x_pred[~m], gt[~m])              # known pixels are kept exactly
-    loss = J.masked_region_loss(v_pred, v, torch.clamp(mask, 0, 1).expand_as(v_pred))
+    loss = J.masked_region_loss(v_pred, v, torch.clamp(mask, 0, 1))
     assert abs(float(loss) - gold["loss"]) < 1e-5 * gold["loss"]
     loss.backward()
     scale = max(g["l2"] for g in gold["grads"].values())
@@ -62,3 +62,34 @@ def test_rope_tables_and_unpatchify():
     img = torch.arange(2 * 3 * 16 * 16, dtype=torch.float32).reshape(2, 3, 16, 16)
     patches = img.reshape(2, 3, 2, 8, 2, 8).permute(0, 2, 4, 3, 5, 1).reshape(2, 4, 8 * 8 * 3)
     assert torch.equal(J.unpatchify(patches, 8, 3), img)
+
+
+def test_b2b_train_steps_match_reference_plumbing(golden_dir):
+    """BASELINE.json config 5 as written (b2b_model + vit_vid, JiTVid-B/16, 156 M parameters) through the reference's
+    own control path: two optimize_parameters() with AdamW(0.9, 0.95) + EMA.  The oracle reproduces both losses and the
+    parameters / EMA afterwards — including the reference's quirks that the one-channel mask is broadcast only in the
+    numerator of the masked loss and that the "fixed" pos_embed is trained (set_requires_grad turns it on)."""
+    from oracle import palette_oracle as O
+    from oracle.gen_golden_b2b_plumbing import batch, draws
+    gold = torch.load(os.path.join(golden_dir, "b2b_plumbing.pt"))
+    gen = gold["gen"]
+    cfg = J.JitCfg(**gold["cfg"], t_eps=gen["t_eps"], noise_scale=gen["noise_scale"])
+    params = init_params_from_shapes(gold["shapes"], gold["wseed"])
+    state = O.TrainState(params={**params, **{k: v.clone() for k, v in gold["frozen"].items()}})
+    label = torch.zeros(gold["batch"], dtype=torch.long)
+    for step in range(2):
+        data = batch(gold["data_seeds"][step])
+        t_base, e = draws(gold["rng_seeds"][step], gen["P_mean"], gen["P_std"], gen["mix"])
+        leaves = {k: v.detach().clone().requires_grad_(True) for k, v in state.params.items()}
+        loss = J.b2b_loss(J.add_buffers(leaves, cfg), data["B"], data["B_label_mask"].float(), None, label, t_base, e,
+                          cfg, kind=gold["loss_kind"], lambda_G=gold["lambda_G"],
+                          masked_region_only=gold["masked_region_only"])
+        assert abs(float(loss) - gold["losses"][step]) < 2e-5 * gold["losses"][step], (step, float(loss))
+        loss.backward()
+        with torch.no_grad():
+            O.adam_update(state, {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()},
+                          O.OptimCfg(**gold["optim"]))
+    for k, (s, n) in gold["param_stats"].items():
+        assert abs(float(state.params[k].double().norm()) - n) <= 2e-4 * n + 1e-9, k
+    for k, (s, n) in gold["ema_stats"].items():
+        assert abs(float(state.ema[k].double().norm()) - n) <= 2e-4 * n + 1e-9, k
