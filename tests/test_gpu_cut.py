@@ -10,8 +10,9 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skip(reason="csrc/nce.cu is not yet verified on hardware (written without GPU time left)")]
+# JG_RUN_UNVERIFIED=1 python -m pytest tests/test_gpu_cut.py -m gpu      runs them anyway
+pytestmark = [pytest.mark.gpu] + ([] if os.environ.get("JG_RUN_UNVERIFIED") == "1" else [
+    pytest.mark.skip(reason="csrc/nce.cu is not yet verified on hardware (written without GPU time left)")])
 
 
 @pytest.fixture(scope="module")
