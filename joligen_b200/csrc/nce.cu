@@ -4,8 +4,9 @@
 // (conv_igemm.cu) on the gathered rows; everything here is small fp32 / bf16 row work:
 //   rows = B * P (P = 256 patches), feature width D = 256  ->  4096 x 256 per NCE layer at batch 16.
 //
-// STATUS: written at the end of round 1 without GPU time left — compiled for sm_100a, NOT yet run on hardware.  The
-// GPU tests that hold it to oracle/cut_oracle.py are in tests/test_gpu_cut.py (skipped until verified).
+// STATUS: written at the end of round 1; one run on a B200 (profiles/r01_cut_tests_first_run.log): gather / scatter bit
+// exact, L2 normalisation and PatchNCE forward / backward within 1e-4 of oracle/cut_oracle.py
+// (tests/test_gpu_widen_cut.py).  Not tuned: one warp per row, keys re-read from L2.
 #include "common.cuh"
 
 namespace jg {

@@ -443,7 +443,7 @@ def gan_loss_bwd(pred, c_real, mode, target, sign, grad_out):
     return d
 
 
-# ---- CUT contrastive path (csrc/nce.cu; not yet verified on hardware, see tests/test_gpu_cut.py) ---------------------
+# ---- CUT contrastive path (csrc/nce.cu; tests/test_gpu_widen_cut.py) -------------------------------------------------
 def gather_rows(feat, ids):
     """feat NHWC bf16 [B,H,W,C]; ids int64 [P] on the device (distinct positions in [0, H*W)).
     -> [B*P, C] bf16: the same positions of every image (PatchSampleF.forward, cut_networks.py:44-56)."""

@@ -6,8 +6,10 @@
 same constructor arguments, sub-module names (mlp_<i>.0 / .2) and call signatures, so that
 `cut_model.calculate_feats` / `calculate_NCE_loss` (models/cut_model.py:848-909) run unchanged.
 
-STATUS: written at the end of round 1 without GPU time left.  The CPU oracle (oracle/cut_oracle.py) is pinned to the
-reference; these modules and csrc/nce.cu are NOT yet verified on hardware (tests/test_gpu_cut.py is skipped).
+STATUS: written at the end of round 1; one run on a B200 (profiles/r01_cut_tests_first_run.log): the kernels match
+the oracle (1e-4) and the pooled features / total NCE loss match the reference's golden vectors; the gradient checks
+of the end-to-end test are not calibrated yet (tests/test_gpu_widen_cut.py, `unverified` marker).  MoNCE (the example's
+default --alg_cut_nce_loss, Sinkhorn weights) has an oracle but no CUDA side.
 """
 import torch
 import torch.nn as nn

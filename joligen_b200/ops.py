@@ -642,7 +642,7 @@ def gan_loss(pred, c_real, mode, target=1.0, sign=1.0):
     return GanLossFn.apply(pred, c_real, mode, target, sign)
 
 
-# ---- CUT contrastive path (not yet verified on hardware, see tests/test_gpu_cut.py) ----------------------------------
+# ---- CUT contrastive path (tests/test_gpu_widen_cut.py) --------------------------------------------------------------
 class GatherRowsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, ids):
