@@ -108,8 +108,18 @@ def _patch_sample_and_nce(golden_dir, with_gradients):
     if not with_gradients:
         return
     total.backward()
-    for mine, ref in zip(feat_q, gold["dfeat_q"]):
-        assert rel(mine.grad, ref) < 5e-2
+    # bf16 storage floor: the same computation on the CPU oracle under bf16 autocast, against its own fp32 result
+    from oracle import cut_oracle as C
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    fk = [f.bfloat16().float() for f in feature_maps(gold["kseed"])]
+    fq = [f.bfloat16().float().requires_grad_(True) for f in feature_maps(gold["qseed"])]
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        kp = C.patch_sample(leaves, fk, gold["num_patches"], gold["ids"])
+        qp = C.patch_sample(leaves, fq, gold["num_patches"], gold["ids"])
+    C.nce_loss_total([q.float() for q in qp], [k.float() for k in kp], gold["batch"], gold["T"],
+                     gold["lambda_NCE"]).backward()
+    for mine, emu, ref in zip(feat_q, fq, gold["dfeat_q"]):
+        assert rel(mine.grad, ref) < max(5e-2, 2.5 * rel(emu.grad, ref)), (rel(mine.grad, ref), rel(emu.grad, ref))
     named = dict(netF.named_parameters())
     for k, ref in gold["grads"].items():
         assert abs(float(named[k].grad.double().norm()) - ref["l2"]) < 5e-2 * ref["l2"] + 1e-6, k
@@ -152,8 +162,17 @@ def _multi_scale_d(golden_dir, with_feature_gradients):
         assert abs(float(named[k].grad.double().norm()) - g["l2"]) < 5e-2 * max(g["l2"], 1e-2 * scale), k
     if not with_feature_gradients:
         return
+    # bf16 storage floor (GroupNorm over 2-channel groups amplifies rounding: ~13 % max-abs on the first scale): the
+    # CPU oracle under bf16 autocast against its own fp32 result
+    from oracle import projd_oracle as P
+    sd0 = seeded_state(gold["shapes"], gold["wseed"])
+    emu_feats = {k: v.requires_grad_(True) for k, v in features(gold["fseed"]).items()}
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        lg = P.multi_scale_d(sd0, emu_feats, gold["channels"], gold["resolutions"], training=True)
+    F.relu(1 - lg.float()).mean().backward()
     for k, ref in gold["dfeats"].items():
-        assert rel(feats[k].grad, ref) < 5e-2
+        floor = rel(emu_feats[k].grad, ref)
+        assert rel(feats[k].grad, ref) < max(5e-2, 2.5 * floor), (k, rel(feats[k].grad, ref), floor)
     sd = net.state_dict()
     for k, ref in gold["uv_after"].items():     # the power iteration is fp32 torch arithmetic: tight
         assert float((sd[k].cpu() - ref).abs().max()) < 1e-5, k
