@@ -1,7 +1,8 @@
 """CUT (BASELINE.json config 3) through the reference's OWN control path, on CPU in the build container (TEST
 INFRASTRUCTURE — see oracle/__init__.py):
 
-    python -m oracle.gen_golden_cut_plumbing        # writes tests/golden/cut_plumbing.pt
+    python -m oracle.gen_golden_cut_plumbing            # writes tests/golden/cut_plumbing.pt (MoNCE, the example's loss)
+    python -m oracle.gen_golden_cut_plumbing patchnce   # writes tests/golden/cut_plumbing_patchnce.pt
 
 options (example_gan_horse2zebra.json, reduced: resnet 2 blocks ngf 16, D_netDs ["basic"] ndf 16, 32x32, batch 2, 16
 patches) -> create_model -> data_dependent_initialize -> setup -> two optimize_parameters().  Stored: the losses of
@@ -46,7 +47,9 @@ def seeded(net, seed):
     return shapes, init_params_from_shapes(shapes, seed)
 
 
-def main():
+def main(nce_loss=None):
+    """nce_loss None: the example's own --alg_cut_nce_loss (monce) -> cut_plumbing.pt;
+    "patchnce" -> cut_plumbing_patchnce.pt (the variant the CUDA path implements)."""
     ref_stubs.install()
     import train as ref_train
     from models import create_model
@@ -70,6 +73,8 @@ def main():
                  "dataroot": tmp, "checkpoints_dir": tmp, "name": "golden", "G_netG": "resnet", "G_nblocks": NB,
                  "G_ngf": NGF, "D_netDs": ["basic"], "D_ndf": NDF, "output_no_html": True, "alg_cut_num_patches": P,
                  "train_G_lr": 1e-3, "train_D_lr": 5e-4, "train_iter_size": 1})  # the example accumulates 8 iterations
+    if nce_loss is not None:
+        flat["alg_cut_nce_loss"] = nce_loss
     opt = TrainOptions().parse_json(flat, save_config=False)
     opt.use_cuda = False
     opt.optim = ref_train.optim
@@ -111,8 +116,9 @@ def main():
            "data_seeds": [100, 101], "rng_seeds": [1000, 1001], "shapes_G": shapes_G, "shapes_F": shapes_F,
            "shapes_D": shapes_D, "optim": optim, "cut": cutopt, "losses": losses, "torch_version": str(torch.__version__),
            "stats_G": stat(model.netG_A), "stats_F": stat(model.netF), "stats_D": stat(model.netD_B_basic)}
-    torch.save(out, os.path.join(GOLDEN, "cut_plumbing.pt"))
-    print("cut_plumbing.pt", json.dumps(cutopt), json.dumps(optim))
+    name = "cut_plumbing.pt" if nce_loss is None else "cut_plumbing_%s.pt" % nce_loss
+    torch.save(out, os.path.join(GOLDEN, name))
+    print(name, json.dumps(cutopt), json.dumps(optim))
     print("reference losses", losses)
     # the restatement against the reference, right here
     mk = lambda lr: O.OptimCfg(lr=lr, beta1=optim["beta1"], beta2=optim["beta2"], eps=optim["eps"],  # noqa: E731
@@ -138,4 +144,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

@@ -51,15 +51,21 @@ def test_cut_nce_all_negatives_and_small_maps():
     assert allneg.shape == (8,) and bool((allneg >= same - 1e-7).all()) and float(allneg.max()) < 5e-2
 
 
-def test_cut_train_steps_match_reference_plumbing(golden_dir):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["cut_plumbing.pt", "cut_plumbing_patchnce.pt"])
+def test_cut_train_steps_match_reference_plumbing(golden_dir, name):
     """BASELINE.json config 3 through the reference's own control path (options -> create_model -> two
-    optimize_parameters(): G_A + F group, then D group; MoNCE with Sinkhorn weights, the example's default): the oracle's
-    cut_train_step reproduces every loss of both steps and the parameters afterwards."""
+    optimize_parameters(): G_A + F group, then D group) with MoNCE (Sinkhorn weights, the example's default) and with
+    plain PatchNCE (what the CUDA path implements): the oracle's cut_train_step reproduces every loss of both steps and
+    the parameters afterwards."""
     from oracle import palette_oracle as O
     from oracle.gen_golden_cut_plumbing import batch, patch_ids
-    gold = torch.load(os.path.join(golden_dir, "cut_plumbing.pt"))
+    gold = torch.load(os.path.join(golden_dir, name))
     opt, cut = gold["optim"], gold["cut"]
-    assert cut["nce_loss"] == "monce" and cut["iter_size"] == 1 and not cut["G_ema"]
+    assert cut["nce_loss"] == ("patchnce" if "patchnce" in name else "monce") and cut["iter_size"] == 1
+    assert not cut["G_ema"]
     sG, sF, sD = (O.TrainState(params=init_params_from_shapes(gold[k], seed))
                   for k, seed in zip(("shapes_G", "shapes_F", "shapes_D"), gold["seeds"]))
     mk = lambda lr: O.OptimCfg(lr=lr, beta1=opt["beta1"], beta2=opt["beta2"], eps=opt["eps"],  # noqa: E731

@@ -188,3 +188,66 @@ def test_multi_scale_d_vs_reference_golden(golden_dir):
 def test_multi_scale_d_feature_gradients_vs_reference_golden(golden_dir):
     """... and d loss / d features, the power-iteration state after the step."""
     _multi_scale_d(golden_dir, with_feature_gradients=True)
+
+
+@unverified
+def test_cut_trainer_vs_reference_plumbing(golden_dir):
+    """CutTrainer (G on cat(real_A, real_B), GAN + 0.5 (NCE + identity NCE), F and D updates) against the reference's
+    own control path with --alg_cut_nce_loss patchnce (cut_plumbing_patchnce.pt) and the bf16-emulating oracle step."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from joligen_b200 import nets_cut, nets_gan
+    from joligen_b200.trainer_cut import CutTrainer
+    from oracle import cut_oracle as C
+    from oracle import palette_oracle as O
+    from oracle.gen_golden_cut_plumbing import batch, patch_ids
+    from oracle.vid_oracle import init_params_from_shapes
+    gold = torch.load(os.path.join(golden_dir, "cut_plumbing_patchnce.pt"))
+    opt, cut = gold["optim"], gold["cut"]
+    pG, pF, pD = (init_params_from_shapes(gold[k], seed)
+                  for k, seed in zip(("shapes_G", "shapes_F", "shapes_D"), gold["seeds"]))
+    netG = nets_gan.ResnetGenerator(3, 3, gold["ngf"], n_blocks=gold["n_blocks"])
+    netD = nets_gan.NLayerDiscriminator(3, gold["ndf"], n_layers=3)
+    netG.load_state_dict(pG)
+    netD.load_state_dict(pD)
+    netG, netD = netG.cuda(), netD.cuda()
+    netF = nets_cut.PatchSampleF(use_mlp=True, nc=256)
+    netF.set_device(torch.device("cuda"))
+    a0, _ = batch(40)
+    netF.data_dependent_initialize(netG.get_feats(a0.cuda(), cut["nce_layers"]))
+    assert [(k, tuple(v.shape)) for k, v in netF.named_parameters()] == [(k, tuple(s)) for k, s in gold["shapes_F"]]
+    netF.load_state_dict(pF)
+    tr = CutTrainer(netG, netF, netD, nce_layers=cut["nce_layers"], num_patches=cut["num_patches"], nce_T=cut["T"],
+                    lambda_NCE=cut["lambda_NCE"], nce_idt=cut["nce_idt"], nce_loss=cut["nce_loss"],
+                    gan_mode=cut["gan_mode"], lambda_gan=cut["lambda_GAN"], G_lr=opt["G_lr"], D_lr=opt["D_lr"],
+                    beta1=opt["beta1"], beta2=opt["beta2"], eps=opt["eps"], weight_decay=opt["weight_decay"],
+                    optim=opt["kind"])
+    mk = lambda lr: O.OptimCfg(lr=lr, beta1=opt["beta1"], beta2=opt["beta2"], eps=opt["eps"],  # noqa: E731
+                               weight_decay=opt["weight_decay"], kind=opt["kind"], ema_beta=0.0)
+    sG, sF, sD = (O.TrainState(params={k: v.clone() for k, v in p.items()}) for p in (pG, pF, pD))
+    for step in range(2):
+        a, b = batch(gold["data_seeds"][step])
+        ids_a, ids_b = patch_ids(gold["rng_seeds"][step], cut["hw"])
+        tr.set_input({"A": a, "B": b})
+        tr.optimize_parameters(patch_ids_A=[i.cuda() for i in ids_a], patch_ids_B=[i.cuda() for i in ids_b])
+        O.EMULATE_BF16[0] = True
+        try:
+            lo = C.cut_train_step(sG, sF, sD, mk(opt["G_lr"]), mk(opt["G_lr"]), mk(opt["D_lr"]), a, b, ids_a, ids_b,
+                                  cut["nce_layers"], n_blocks=gold["n_blocks"], n_layers=3,
+                                  lambda_gan=cut["lambda_GAN"], lambda_nce=cut["lambda_NCE"], T=cut["T"],
+                                  num_patches=cut["num_patches"], mode=cut["gan_mode"], nce_idt=cut["nce_idt"],
+                                  nce_kind=cut["nce_loss"])
+        finally:
+            O.EMULATE_BF16[0] = False
+        ref = gold["losses"][step]
+        for mine, key, emu in ((tr.loss_G_tot, "G_tot", lo["G_tot"]), (tr.loss_G_GAN, "G_GAN_D_B_basic", lo["G_GAN"]),
+                               (tr.loss_G_NCE, "G_NCE", lo["G_NCE"]), (tr.loss_G_NCE_Y, "G_NCE_Y", lo["G_NCE_Y"]),
+                               (tr.loss_D_tot, "D_tot", lo["D_tot"])):
+            floor = abs(emu - ref[key]) / abs(ref[key])
+            assert abs(float(mine) - ref[key]) < max(3e-2, 3 * floor) * abs(ref[key]), (step, key, float(mine), ref[key])
+    # weights after two Adam steps (biases in front of an InstanceNorm take noise-signed steps: norms only, loosely)
+    for net, stats in ((netG, gold["stats_G"]), (netF, gold["stats_F"]), (netD, gold["stats_D"])):
+        sd = net.state_dict()
+        for k, (s, n) in stats.items():
+            tol = 5e-2 if k.endswith(".bias") else 1e-2
+            assert abs(float(sd[k].double().norm()) - n) <= tol * n + 1e-6, k
