@@ -21,6 +21,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 import torch.nn.functional as F
 
+from .palette_oracle import _r, _rw
+
 
 def mlp_param_shapes(feat_channels: Sequence[int], nc: int = 256) -> Dict[str, Tuple[int, ...]]:
     """state_dict of PatchSampleF after create_mlp (cut_networks.py:23-36): mlp_<i>.{0,2}.{weight,bias}."""
@@ -39,12 +41,13 @@ def patch_sample(sd: Optional[Dict[str, torch.Tensor]], feats: List[torch.Tensor
     num_patches == 0 branch reshapes whole maps and is not used by cut_model)."""
     out = []
     for i, feat in enumerate(feats):
-        flat = feat.permute(0, 2, 3, 1).flatten(1, 2)                    # [B, H*W, C]
+        flat = _r(feat).permute(0, 2, 3, 1).flatten(1, 2)                # [B, H*W, C]  (bf16 NHWC map on the CUDA path)
         pid = patch_ids[i].reshape(-1)[: int(min(num_patches, flat.shape[1]))]
         x = flat[:, pid, :].flatten(0, 1)                                # [B*P, C]
         if use_mlp:
-            x = F.linear(x, sd["mlp_%d.0.weight" % i], sd["mlp_%d.0.bias" % i])
-            x = F.linear(F.relu(x), sd["mlp_%d.2.weight" % i], sd["mlp_%d.2.bias" % i])
+            # with palette_oracle.EMULATE_BF16 set, tensors the CUDA path stores as bf16 are rounded at the same places
+            x = _r(F.relu(F.linear(x, _rw(sd["mlp_%d.0.weight" % i]), sd["mlp_%d.0.bias" % i])))
+            x = _r(F.linear(x, _rw(sd["mlp_%d.2.weight" % i]), sd["mlp_%d.2.bias" % i]))
         out.append(F.normalize(x, eps=1e-7))
     return out
 

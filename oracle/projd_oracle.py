@@ -18,6 +18,8 @@ from typing import Dict, List, Tuple
 import torch
 import torch.nn.functional as F
 
+from .palette_oracle import _r, _rw
+
 CHANNEL_DICT = {4: 512, 8: 512, 16: 256, 32: 128, 64: 64, 128: 64, 256: 32, 512: 16, 1024: 8}
 
 
@@ -54,14 +56,14 @@ def single_disc(sd, name, x, nc, start_sz, training=True, new_state=None):
         w, u, v = spectral_normalize(sd, n + ".0", training)
         if new_state is not None:
             new_state[n + ".0.weight_u"], new_state[n + ".0.weight_v"] = u, v
-        x = F.conv2d(x, w, sd[n + ".0.bias"], stride=2, padding=1)
-        x = F.group_norm(x, cout // 2, sd[n + ".1.weight"], sd[n + ".1.bias"], eps=1e-5)
-        x = F.leaky_relu(x, 0.2)
+        # with palette_oracle.EMULATE_BF16 set, tensors the CUDA path stores as bf16 are rounded at the same places
+        x = _r(F.conv2d(x, _rw(w), sd[n + ".0.bias"], stride=2, padding=1))
+        x = _r(F.leaky_relu(F.group_norm(x, cout // 2, sd[n + ".1.weight"], sd[n + ".1.bias"], eps=1e-5), 0.2))
     n = "%s.main.%d" % (name, len(plan))
     w, u, v = spectral_normalize(sd, n, training)
     if new_state is not None:
         new_state[n + ".weight_u"], new_state[n + ".weight_v"] = u, v
-    return F.conv2d(x, w, None, stride=1, padding=0)
+    return _r(F.conv2d(x, _rw(w), None, stride=1, padding=0))
 
 
 def multi_scale_d(sd, feats: Dict[str, torch.Tensor], channels, resolutions, training=True, new_state=None,
@@ -69,7 +71,7 @@ def multi_scale_d(sd, feats: Dict[str, torch.Tensor], channels, resolutions, tra
     """MultiScaleD.forward (conv mini-discriminators): logits of every scale flattened and concatenated."""
     outs = []
     for i, (c, r) in enumerate(zip(channels, resolutions)):
-        x = feats[str(i)]
+        x = _r(feats[str(i)])
         outs.append(single_disc(sd, "%smini_discs.%d" % (prefix, i), x, c, r, training, new_state)
                     .reshape(x.shape[0], -1))
     return torch.cat(outs, dim=1)
