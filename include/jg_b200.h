@@ -305,6 +305,17 @@ int jg_patch_nce_fwd(const float* q, const float* k, int G, int P, int D, float 
 int jg_patch_nce_bwd(const float* q, const float* k, const float* lse, const float* grad_loss, int G, int P, int D,
                      float T, float* dq, float* dk, jg_stream_t stream);
 
+/* MoNCELoss (models/modules/NCE/monce.py:12-33 + sinkhorn.py; --alg_cut_nce_loss monce): PatchNCE whose negative logits
+ * get T * log of the Sinkhorn optimal-transport weights (cost "hard", eps 1, `iters` scalings), differentiated through
+ * the iterations w.r.t. q.  ws: jg_monce_ws_floats(G, P, iters, backward) floats, the SAME buffer for the forward and
+ * the backward of one step (the forward leaves C, K and the scaling history in it).  P <= 1024 (one CTA per group).
+ * Compiled, not yet run on hardware. */
+size_t jg_monce_ws_floats(int G, int P, int iters, int backward);
+int jg_monce_fwd(const float* q, const float* k, int G, int P, int D, float T, int num_patches_opt, int iters, float* ws,
+                 float* loss, float* lse, jg_stream_t stream);
+int jg_monce_bwd(const float* q, const float* k, const float* lse, const float* grad_loss, int G, int P, int D, float T,
+                 int num_patches_opt, int iters, float* ws, float* dq, float* dk, jg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

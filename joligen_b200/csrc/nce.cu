@@ -233,6 +233,244 @@ patch_nce_bwd_k_kernel(const float* __restrict__ q, const float* __restrict__ k,
     if (e < per) dk[row * D + lane + 32 * e] = acc[e] * invT;
 }
 
+
+// ---- MoNCE: PatchNCE whose negatives are re-weighted by Sinkhorn optimal-transport weights ---------------------------
+// models/modules/NCE/monce.py:12-33 + sinkhorn.py (cost "hard", eps 1, 50 iterations):
+//   C_ij = <q_i, k_j>, diagonal -10;  K = exp(C);  u = v = 1;  repeat: u_i = 1 / sum_j K_ij v_j,  v_j = 1 / sum_i u_i K_ij
+//   f_ij = u_i K_ij v_j (popt - 1) + 1e-8;   out_i = [ <q_i, k_i> / T,  C_ij / T + log f_ij (diagonal: -10 / T) ]
+//   loss_i = logsumexp(out_i) - out_i[0]
+// The reference differentiates through the iterations w.r.t. q (k is detached inside the OT): the backward kernel runs
+// the reverse sweep over the stored u^t, v^t.  One CTA per group (image); C, K (and, backward, the adjoint of K and the
+// direct softmax weights) live in an L2-resident workspace of P x P floats each.  STATUS: compiled, NOT yet run on
+// hardware; the algorithm (forward + reverse sweep) was checked against autograd on the CPU in fp64.
+constexpr int kMonceThreads = 256;
+
+__device__ __forceinline__ float row_dot_K(const float* __restrict__ row, const float* __restrict__ vec, int P, int lane) {
+  float s = 0.f;
+  for (int j = lane; j < P; j += 32) s = fmaf(row[j], vec[j], s);
+  return warp_sum_nce(s);
+}
+
+__global__ void __launch_bounds__(kMonceThreads)
+monce_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, int P, int D, float invT, float popt1,
+                 int iters, float* __restrict__ Cmat, float* __restrict__ Kmat, float* __restrict__ U,
+                 float* __restrict__ V, float* __restrict__ loss, float* __restrict__ lse) {
+  extern __shared__ float sm[];  // u [P], v [P]
+  float* su = sm;
+  float* sv = sm + P;
+  const int g = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kMonceThreads / 32;
+  const int per = D / 32;
+  const float* qg = q + (size_t)g * P * D;
+  const float* kg = k + (size_t)g * P * D;
+  float* Cg = Cmat + (size_t)g * P * P;
+  float* Kg = Kmat + (size_t)g * P * P;
+  float* Ug = U + (size_t)g * iters * P;
+  float* Vg = V + (size_t)g * (iters + 1) * P;
+  // C and K
+  for (int i = warp; i < P; i += nwarps) {
+    float qr[kNceMaxPerLane], kr[kNceMaxPerLane];
+#pragma unroll
+    for (int e = 0; e < kNceMaxPerLane; ++e)
+      if (e < per) qr[e] = qg[(size_t)i * D + lane + 32 * e];
+    for (int j = 0; j < P; ++j) {
+      const float c = nce_dot(qr, kg + (size_t)j * D, kr, per, lane);
+      if (lane == 0) {
+        Cg[(size_t)i * P + j] = c;
+        Kg[(size_t)i * P + j] = __expf(j == i ? -10.f : c);
+      }
+    }
+  }
+  for (int j = threadIdx.x; j < P; j += kMonceThreads) {
+    su[j] = 1.f;
+    sv[j] = 1.f;
+    Vg[j] = 1.f;
+  }
+  __syncthreads();
+  // Sinkhorn scalings
+  for (int t = 0; t < iters; ++t) {
+    for (int i = warp; i < P; i += nwarps) {
+      const float r = row_dot_K(Kg + (size_t)i * P, sv, P, lane);
+      if (lane == 0) {
+        su[i] = 1.f / r;
+        Ug[(size_t)t * P + i] = 1.f / r;
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < P; j += kMonceThreads) {
+      float s = 0.f;
+      for (int i = 0; i < P; ++i) s = fmaf(su[i], Kg[(size_t)i * P + j], s);
+      sv[j] = 1.f / s;
+      Vg[(size_t)(t + 1) * P + j] = 1.f / s;
+    }
+    __syncthreads();
+  }
+  // loss
+  for (int i = warp; i < P; i += nwarps) {
+    float qr[kNceMaxPerLane], kr[kNceMaxPerLane];
+#pragma unroll
+    for (int e = 0; e < kNceMaxPerLane; ++e)
+      if (e < per) qr[e] = qg[(size_t)i * D + lane + 32 * e];
+    const float pos = nce_dot(qr, kg + (size_t)i * D, kr, per, lane) * invT;
+    const float ui = su[i];
+    float m = pos;
+    for (int j = lane; j < P; j += 32) {
+      const float f = ui * Kg[(size_t)i * P + j] * sv[j] * popt1 + 1e-8f;
+      const float l = (j == i) ? -10.f * invT : Cg[(size_t)i * P + j] * invT + __logf(f);
+      m = fmaxf(m, l);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int j = lane; j < P; j += 32) {
+      const float f = ui * Kg[(size_t)i * P + j] * sv[j] * popt1 + 1e-8f;
+      const float l = (j == i) ? -10.f * invT : Cg[(size_t)i * P + j] * invT + __logf(f);
+      s += __expf(l - m);
+    }
+    s = warp_sum_nce(s) + __expf(pos - m);
+    const float lz = m + __logf(s);
+    if (lane == 0) {
+      lse[(size_t)g * P + i] = lz;
+      loss[(size_t)g * P + i] = lz - pos;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kMonceThreads)
+monce_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ lse,
+                 const float* __restrict__ gout, int P, int D, float invT, float popt1, int iters,
+                 const float* __restrict__ Cmat, const float* __restrict__ Kmat, const float* __restrict__ U,
+                 const float* __restrict__ V, float* __restrict__ Kbar, float* __restrict__ Wmat,
+                 float* __restrict__ dq, float* __restrict__ dk) {
+  extern __shared__ float sm[];  // ubar, vbar, sbar, rbar, p0 : 5 * P
+  float* ubar = sm;
+  float* vbar = sm + P;
+  float* sbar = sm + 2 * P;
+  float* rbar = sm + 3 * P;
+  float* p0s = sm + 4 * P;
+  const int g = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kMonceThreads / 32;
+  const int per = D / 32;
+  const float* qg = q + (size_t)g * P * D;
+  const float* kg = k + (size_t)g * P * D;
+  const float* Cg = Cmat + (size_t)g * P * P;
+  const float* Kg = Kmat + (size_t)g * P * P;
+  const float* Ug = U + (size_t)g * iters * P;
+  const float* Vg = V + (size_t)g * (iters + 1) * P;
+  float* Kb = Kbar + (size_t)g * P * P;
+  float* Wg = Wmat + (size_t)g * P * P;
+  const float* lz = lse + (size_t)g * P;
+  const float* go = gout + (size_t)g * P;
+  const float* uF = Ug + (size_t)(iters - 1) * P;  // final u, v
+  const float* vF = Vg + (size_t)iters * P;
+  for (int j = threadIdx.x; j < P; j += kMonceThreads) vbar[j] = 0.f;
+  __syncthreads();
+  // softmax weights: W_ij = g_i p_ij / T (direct term), Fbar_ij = g_i p_ij (popt-1) / f_ij; ubar, Kbar initialised
+  for (int i = warp; i < P; i += nwarps) {
+    float qr[kNceMaxPerLane], kr[kNceMaxPerLane];
+#pragma unroll
+    for (int e = 0; e < kNceMaxPerLane; ++e)
+      if (e < per) qr[e] = qg[(size_t)i * D + lane + 32 * e];
+    const float pos = nce_dot(qr, kg + (size_t)i * D, kr, per, lane) * invT;
+    const float ui = uF[i], gi = go[i], lzi = lz[i];
+    float ub = 0.f;
+    for (int j = lane; j < P; j += 32) {
+      const float kij = Kg[(size_t)i * P + j];
+      const float f = ui * kij * vF[j] * popt1 + 1e-8f;
+      float w = 0.f, fb = 0.f;
+      if (j != i) {
+        const float pij = __expf(Cg[(size_t)i * P + j] * invT + __logf(f) - lzi);
+        w = gi * pij * invT;
+        fb = gi * pij * popt1 / f;
+      }
+      Wg[(size_t)i * P + j] = w;
+      Kb[(size_t)i * P + j] = fb * ui * vF[j];
+      ub = fmaf(fb * kij, vF[j], ub);
+      atomicAdd(&vbar[j], fb * ui * kij);
+    }
+    ub = warp_sum_nce(ub);
+    if (lane == 0) {
+      ubar[i] = ub;
+      p0s[i] = __expf(pos - lzi);
+    }
+  }
+  __syncthreads();
+  // reverse sweep over the Sinkhorn iterations
+  for (int t = iters - 1; t >= 0; --t) {
+    const float* ut = Ug + (size_t)t * P;
+    const float* vt = Vg + (size_t)(t + 1) * P;
+    const float* vp = Vg + (size_t)t * P;
+    for (int j = threadIdx.x; j < P; j += kMonceThreads) sbar[j] = -vbar[j] * vt[j] * vt[j];
+    __syncthreads();
+    for (int i = warp; i < P; i += nwarps) {
+      const float ui = ut[i];
+      float acc = 0.f;
+      for (int j = lane; j < P; j += 32) {
+        const float sb = sbar[j];
+        acc = fmaf(Kg[(size_t)i * P + j], sb, acc);
+        Kb[(size_t)i * P + j] += ui * sb;
+      }
+      acc = warp_sum_nce(acc);
+      if (lane == 0) {
+        const float ubt = ubar[i] + acc;
+        rbar[i] = -ubt * ui * ui;
+        ubar[i] = 0.f;
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < P; j += kMonceThreads) {
+      const float vpj = vp[j];
+      float acc = 0.f;
+      for (int i = 0; i < P; ++i) {
+        const float rb = rbar[i];
+        acc = fmaf(Kg[(size_t)i * P + j], rb, acc);
+        Kb[(size_t)i * P + j] += rb * vpj;
+      }
+      vbar[j] = acc;
+    }
+    __syncthreads();
+  }
+  // dq_i = g_i (p0 - 1) / T k_i + sum_j (W_ij + Kbar_ij K_ij) k_j   (the Sinkhorn branch reaches q only)
+  for (int i = warp; i < P; i += nwarps) {
+    float kr[kNceMaxPerLane], acc[kNceMaxPerLane];
+    const float c0 = go[i] * (p0s[i] - 1.f) * invT;
+#pragma unroll
+    for (int e = 0; e < kNceMaxPerLane; ++e)
+      if (e < per) acc[e] = c0 * kg[(size_t)i * D + lane + 32 * e];
+    for (int j = 0; j < P; ++j) {
+      if (j == i) continue;
+      const float c = Wg[(size_t)i * P + j] + Kb[(size_t)i * P + j] * Kg[(size_t)i * P + j];
+#pragma unroll
+      for (int e = 0; e < kNceMaxPerLane; ++e) {
+        if (e < per) {
+          kr[e] = kg[(size_t)j * D + lane + 32 * e];
+          acc[e] = fmaf(c, kr[e], acc[e]);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < kNceMaxPerLane; ++e)
+      if (e < per) dq[((size_t)g * P + i) * D + lane + 32 * e] = acc[e];
+  }
+  // dk_j = sum_i W_ij q_i
+  if (dk) {
+    for (int j = warp; j < P; j += nwarps) {
+      float acc[kNceMaxPerLane];
+#pragma unroll
+      for (int e = 0; e < kNceMaxPerLane; ++e) acc[e] = 0.f;
+      for (int i = 0; i < P; ++i) {
+        const float w = Wg[(size_t)i * P + j];
+#pragma unroll
+        for (int e = 0; e < kNceMaxPerLane; ++e)
+          if (e < per) acc[e] = fmaf(w, qg[(size_t)i * D + lane + 32 * e], acc[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < kNceMaxPerLane; ++e)
+        if (e < per) dk[((size_t)g * P + j) * D + lane + 32 * e] = acc[e];
+    }
+  }
+}
+
 }  // namespace
 }  // namespace jg
 
@@ -322,5 +560,56 @@ extern "C" int jg_patch_nce_bwd(const float* q, const float* k, const float* lse
     patch_nce_bwd_k_kernel<<<grid, 128, 0, stream>>>(q, k, lse, grad_loss, G, P, D, 1.f / T, dk);
     JG_LAUNCH_CHECK();
   }
+  return JG_OK;
+}
+
+
+static int monce_check(const float* q, const float* k, int G, int P, int D, float T, int iters, const char* what) {
+  if (int rc = nce_check(q, k, G, P, D, T, what)) return rc;
+  JG_CHECK(P <= 1024 && iters > 0 && iters <= 1000, JG_ERR_UNSUPPORTED,
+           "%s: P=%d (one CTA per group: at most 1024 patches) iters=%d", what, P, iters);
+  return JG_OK;
+}
+
+extern "C" size_t jg_monce_ws_floats(int G, int P, int iters, int backward) {
+  const size_t pp = (size_t)G * P * P;
+  return (backward ? 4 : 2) * pp + (size_t)G * (2 * iters + 1) * P;
+}
+
+// ws layout: C [G,P,P] | K [G,P,P] | U [G,iters,P] | V [G,iters+1,P] | (backward only) Kbar [G,P,P] | W [G,P,P]
+extern "C" int jg_monce_fwd(const float* q, const float* k, int G, int P, int D, float T, int num_patches_opt, int iters,
+                            float* ws, float* loss, float* lse, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = monce_check(q, k, G, P, D, T, iters, "monce_fwd")) return rc;
+  JG_CHECK(ws && loss && lse, JG_ERR_INVALID, "monce_fwd: null pointer");
+  const size_t pp = (size_t)G * P * P;
+  float* Cm = ws;
+  float* Km = ws + pp;
+  float* U = ws + 2 * pp;
+  float* V = U + (size_t)G * iters * P;
+  monce_fwd_kernel<<<G, kMonceThreads, 2 * P * sizeof(float), stream>>>(q, k, P, D, 1.f / T,
+                                                                        (float)(num_patches_opt - 1), iters, Cm, Km, U,
+                                                                        V, loss, lse);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
+extern "C" int jg_monce_bwd(const float* q, const float* k, const float* lse, const float* grad_loss, int G, int P, int D,
+                            float T, int num_patches_opt, int iters, float* ws, float* dq, float* dk,
+                            jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = monce_check(q, k, G, P, D, T, iters, "monce_bwd")) return rc;
+  JG_CHECK(ws && lse && grad_loss && dq, JG_ERR_INVALID, "monce_bwd: null pointer");
+  const size_t pp = (size_t)G * P * P;
+  float* Cm = ws;
+  float* Km = ws + pp;
+  float* U = ws + 2 * pp;
+  float* V = U + (size_t)G * iters * P;
+  float* Kb = V + (size_t)G * (iters + 1) * P;
+  float* Wm = Kb + pp;
+  monce_bwd_kernel<<<G, kMonceThreads, 5 * P * sizeof(float), stream>>>(q, k, lse, grad_loss, P, D, 1.f / T,
+                                                                        (float)(num_patches_opt - 1), iters, Cm, Km, U,
+                                                                        V, Kb, Wm, dq, dk);
+  JG_LAUNCH_CHECK();
   return JG_OK;
 }

@@ -496,3 +496,25 @@ def patch_nce_bwd(q, k, lse, grad_loss, groups, temperature, need_dq=True, need_
     L.call("jg_patch_nce_bwd", L.ptr(q), L.ptr(k), L.ptr(lse), L.ptr(grad_loss), groups, rows // groups, d,
            float(temperature), L.ptr(dq), L.ptr(dk), L.stream())
     return dq, dk
+
+
+def monce_fwd(q, k, groups, temperature, num_patches_opt, iters=50):
+    """MoNCE loss per patch; returns (loss, lse, ws) — ws keeps C, K and the Sinkhorn scaling history for the backward."""
+    rows, d = q.shape
+    p = rows // groups
+    lib = L.load()
+    ws = torch.empty((lib.jg_monce_ws_floats(groups, p, iters, 1),), dtype=torch.float32, device=q.device)
+    loss = torch.empty((rows,), dtype=torch.float32, device=q.device)
+    lse = torch.empty((rows,), dtype=torch.float32, device=q.device)
+    L.call("jg_monce_fwd", L.ptr(q), L.ptr(k), groups, p, d, float(temperature), int(num_patches_opt), int(iters),
+           L.ptr(ws), L.ptr(loss), L.ptr(lse), L.stream())
+    return loss, lse, ws
+
+
+def monce_bwd(q, k, lse, grad_loss, ws, groups, temperature, num_patches_opt, iters=50, need_dk=True):
+    rows, d = q.shape
+    dq = torch.empty_like(q)
+    dk = torch.empty_like(k) if need_dk else None
+    L.call("jg_monce_bwd", L.ptr(q), L.ptr(k), L.ptr(lse), L.ptr(grad_loss), groups, rows // groups, d,
+           float(temperature), int(num_patches_opt), int(iters), L.ptr(ws), L.ptr(dq), L.ptr(dk), L.stream())
+    return dq, dk

@@ -93,11 +93,14 @@ _SIGNATURES = {
     "jg_l2norm_bwd": [c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_f, c_p],
     "jg_patch_nce_fwd": [c_p, c_p, c_int, c_int, c_int, c_f, c_p, c_p, c_p],
     "jg_patch_nce_bwd": [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_f, c_p, c_p, c_p],
+    "jg_monce_fwd": [c_p, c_p, c_int, c_int, c_int, c_f, c_int, c_int, c_p, c_p, c_p, c_p],
+    "jg_monce_bwd": [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_f, c_int, c_int, c_p, c_p, c_p, c_p],
 }
 _U64_FUNCS = {"jg_kernel_launches": []}
 _SIZE_T_FUNCS = {
     "jg_groupnorm_fwd_ws_floats": [c_int, c_int, c_int],
     "jg_groupnorm_bwd_ws_floats": [c_int, c_int, c_int],
+    "jg_monce_ws_floats": [c_int, c_int, c_int, c_int],
 }
 
 

@@ -8,8 +8,8 @@ same constructor arguments, sub-module names (mlp_<i>.0 / .2) and call signature
 
 STATUS: written at the end of round 1; one run on a B200 (profiles/r01_cut_tests_first_run.log): the kernels match
 the oracle (1e-4) and the pooled features / total NCE loss match the reference's golden vectors; the gradient checks
-of the end-to-end test are not calibrated yet (tests/test_gpu_widen_cut.py, `unverified` marker).  MoNCE (the example's
-default --alg_cut_nce_loss, Sinkhorn weights) has an oracle but no CUDA side.
+of the end-to-end test are re-bounded but not re-run yet (tests/test_gpu_widen_cut.py, `unverified` marker).  MoNCELoss
+(the example's default --alg_cut_nce_loss) is compiled but has not run on hardware.
 """
 import torch
 import torch.nn as nn
@@ -118,3 +118,18 @@ class PatchNCELoss(nn.Module):
         if d % 32 or d > 512:
             raise NotImplementedError("B200 PatchNCELoss: feature width %d (multiples of 32 up to 512)" % d)
         return ops.patch_nce(feat_q, feat_k, groups, self.opt.alg_cut_nce_T)
+
+
+class MoNCELoss(PatchNCELoss):
+    """models/modules/NCE/monce.py: the negatives are re-weighted by Sinkhorn optimal-transport weights (csrc/nce.cu:
+    monce_fwd / monce_bwd kernels — compiled, NOT yet run on hardware; checked against autograd on the CPU only)."""
+
+    def forward(self, feat_q, feat_k, current_batch, **unused_args):
+        if unused_args.get("weight") is not None:
+            raise NotImplementedError("B200 MoNCELoss: per-patch weights (SRC loss)")
+        if self.opt.alg_cut_nce_includes_all_negatives_from_minibatch:
+            raise NotImplementedError("B200 MoNCELoss: negatives from the whole minibatch (one CTA per group, P <= 1024)")
+        d = feat_q.shape[1]
+        if d % 32 or d > 512:
+            raise NotImplementedError("B200 MoNCELoss: feature width %d (multiples of 32 up to 512)" % d)
+        return ops.monce(feat_q, feat_k, current_batch, self.opt.alg_cut_nce_T, self.opt.alg_cut_num_patches)

@@ -689,6 +689,26 @@ class PatchNceFn(torch.autograd.Function):
         return dq, dk, None, None
 
 
+class MonceFn(torch.autograd.Function):
+    """loss per patch of MoNCELoss (Sinkhorn-weighted negatives); q gets the gradient through the OT iterations too."""
+
+    @staticmethod
+    def forward(ctx, q, k, groups, temperature, num_patches_opt):
+        q, k = q.contiguous().float(), k.contiguous().float()
+        loss, lse, ws = K.monce_fwd(q, k, groups, temperature, num_patches_opt)
+        ctx.save_for_backward(q, k, lse, ws)
+        ctx.cfg = (groups, temperature, num_patches_opt)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        q, k, lse, ws = ctx.saved_tensors
+        groups, temperature, num_patches_opt = ctx.cfg
+        dq, dk = K.monce_bwd(q, k, lse, g.contiguous().float(), ws, groups, temperature, num_patches_opt,
+                             need_dk=_needs(ctx, 1))
+        return dq, dk, None, None, None
+
+
 def gather_rows(feat, ids):
     return GatherRowsFn.apply(feat, ids)
 
@@ -699,3 +719,7 @@ def l2_normalize(x, eps=1e-7):
 
 def patch_nce(q, k, groups, temperature):
     return PatchNceFn.apply(q, k, groups, temperature)
+
+
+def monce(q, k, groups, temperature, num_patches_opt):
+    return MonceFn.apply(q, k, groups, temperature, num_patches_opt)

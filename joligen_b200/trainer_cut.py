@@ -9,7 +9,7 @@
                                    the layer sum is divided by the number of REQUESTED layers (:892, 909)
     compute_D_loss                 0.5 * (GANLoss(D(real_B), True) + GANLoss(D(fake_B.detach()), False))
 
---alg_cut_nce_loss patchnce only: MoNCE's Sinkhorn weights (the example's default) have an oracle but no kernels yet.
+--alg_cut_nce_loss patchnce (kernels ran on hardware) or monce (the example's default; kernels compiled, not yet run).
 Parameters / gradients / Adam moments are flat fp32 buffers per network (G, F, D), one SUM all-reduce per group.
 
 STATUS: composition of kernels that each passed on hardware (generator / discriminator / GAN loss: test_gpu_gan.py;
@@ -30,8 +30,8 @@ class CutTrainer:
                  device=None, process_group=None):
         if not torch.cuda.is_available():
             raise RuntimeError("joligen_b200.CutTrainer needs a CUDA device (there is no CPU path)")
-        if nce_loss != "patchnce":
-            raise NotImplementedError("B200 CutTrainer: --alg_cut_nce_loss %r (patchnce is implemented)" % nce_loss)
+        if nce_loss not in ("patchnce", "monce"):
+            raise NotImplementedError("B200 CutTrainer: --alg_cut_nce_loss %r (patchnce / monce)" % nce_loss)
         if not netF.mlp_init:
             raise RuntimeError("CutTrainer: call netF.data_dependent_initialize(netG_A.get_feats(x, nce_layers)) first "
                                "(cut_model.data_dependent_initialize, :504-538)")
@@ -42,7 +42,7 @@ class CutTrainer:
         self.netF = netF.to(self.device)
         self.netD_B = netD_B.to(self.device)
         self.crit = GANLoss(gan_mode)
-        self.crit_nce = nets_cut.PatchNCELoss(SimpleNamespace(
+        self.crit_nce = (nets_cut.MoNCELoss if nce_loss == "monce" else nets_cut.PatchNCELoss)(SimpleNamespace(
             alg_cut_nce_T=nce_T, alg_cut_num_patches=num_patches,
             alg_cut_nce_includes_all_negatives_from_minibatch=nce_includes_all_negatives_from_minibatch))
         self.nce_layers = list(nce_layers)

@@ -80,6 +80,24 @@ def test_patch_nce_fwd_bwd_vs_oracle(K, groups):
     assert rel(dq, q.grad) < 1e-4 and rel(dk, k.grad) < 1e-4
 
 
+@unverified
+@pytest.mark.parametrize("shape", [(2, 48, 256, 16), (3, 256, 256, 256), (1, 20, 32, 256)])
+def test_monce_fwd_bwd_vs_oracle(K, shape):
+    """MoNCE (Sinkhorn-weighted negatives, differentiated through the 50 scalings) against the oracle's autograd."""
+    from oracle import cut_oracle as C
+    groups, p, d, popt = shape
+    g = torch.Generator().manual_seed(p + d)
+    q = F.normalize(torch.randn(groups * p, d, generator=g)).requires_grad_(True)
+    k = F.normalize(torch.randn(groups * p, d, generator=g)).requires_grad_(True)
+    gout = torch.rand(groups * p, generator=g)
+    ref = C.patch_nce_loss(q, k, groups, T=0.07, kind="monce", num_patches_opt=popt)
+    ref.backward(gout)
+    loss, lse, ws = K.monce_fwd(q.detach().cuda(), k.detach().cuda(), groups, 0.07, popt)
+    assert rel(loss, ref.detach()) < 1e-3
+    dq, dk = K.monce_bwd(q.detach().cuda(), k.detach().cuda(), lse, gout.cuda(), ws, groups, 0.07, popt)
+    assert rel(dq, q.grad) < 2e-3 and rel(dk, k.grad) < 2e-3
+
+
 def _patch_sample_and_nce(golden_dir, with_gradients):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
