@@ -158,3 +158,49 @@ def cut_train_step(state_G, state_F, state_D, oc_G, oc_F, oc_D, real_A, real_B, 
         adam_update(state_D, {k: v.grad for k, v in dl.items()}, oc_D)
     return {"G_tot": float(loss_G), "G_GAN": float(loss_gan), "G_NCE": float(loss_nce), "G_NCE_Y": float(loss_nce_y),
             "D_tot": float(loss_D)}
+
+
+def monce_explicit(q, k, gout, groups, T=0.07, num_patches_opt=256, iters=50):
+    """The MoNCE forward and its HAND-DERIVED backward exactly as csrc/nce.cu computes them (monce_fwd_kernel /
+    monce_bwd_kernel): scalings stored per iteration, softmax weights, then the reverse sweep over the iterations —
+    in fp64 on the CPU, to be held against autograd through patch_nce_loss(kind="monce").  Returns (loss, dq, dk)."""
+    rows, d = q.shape
+    p = rows // groups
+    q = q.detach().double().view(groups, p, d)
+    k = k.detach().double().view(groups, p, d)
+    g = gout.double().view(groups, p)
+    eye = torch.eye(p, dtype=torch.bool)
+    cm = torch.einsum("gid,gjd->gij", q, k)
+    kk = torch.exp(cm.masked_fill(eye, -10.0))
+    us, vs = [], [torch.ones(groups, p, dtype=torch.double)]
+    u, v = None, vs[0]
+    for _ in range(iters):
+        u = 1.0 / torch.einsum("gij,gj->gi", kk, v)
+        us.append(u)
+        v = 1.0 / torch.einsum("gij,gi->gj", kk, u)
+        vs.append(v)
+    f = u[:, :, None] * kk * v[:, None, :] * (num_patches_opt - 1) + 1e-8
+    pos = (q * k).sum(-1) / T
+    neg = (cm / T + torch.log(f)).masked_fill(eye, -10.0 / T)
+    m = torch.maximum(pos, neg.max(-1).values)
+    lse = m + torch.log(torch.exp(pos - m) + torch.exp(neg - m[..., None]).sum(-1))
+    p0 = torch.exp(pos - lse)
+    pij = torch.exp(neg - lse[..., None]).masked_fill(eye, 0.0)
+    w = g[..., None] * pij / T                                           # direct softmax term
+    dq = (g * (p0 - 1))[..., None] * k / T + torch.einsum("gij,gjd->gid", w, k)
+    dk = torch.einsum("gij,gid->gjd", w, q)
+    fbar = g[..., None] * pij * (num_patches_opt - 1) / f                # through T log f
+    ubar = (fbar * kk * v[:, None, :]).sum(-1)
+    vbar = (fbar * u[:, :, None] * kk).sum(-2)
+    kbar = fbar * u[:, :, None] * v[:, None, :]
+    for t in reversed(range(iters)):
+        u_t, v_t, v_prev = us[t], vs[t + 1], vs[t]
+        sbar = -vbar * v_t * v_t                                          # v_t = 1 / (K^T u_t)
+        ubar = ubar + torch.einsum("gij,gj->gi", kk, sbar)
+        kbar = kbar + u_t[:, :, None] * sbar[:, None, :]
+        rbar = -ubar * u_t * u_t                                          # u_t = 1 / (K v_prev)
+        vbar = torch.einsum("gij,gi->gj", kk, rbar)
+        kbar = kbar + rbar[:, :, None] * v_prev[:, None, :]
+        ubar = torch.zeros_like(ubar)
+    dq = dq + torch.einsum("gij,gjd->gid", (kbar * kk).masked_fill(eye, 0.0), k)   # the OT branch reaches q only
+    return (lse - pos).reshape(-1), dq.reshape(rows, d), dk.reshape(rows, d)

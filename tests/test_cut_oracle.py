@@ -87,3 +87,20 @@ def test_cut_train_steps_match_reference_plumbing(golden_dir, name):
             # into +-lr steps that no two implementations share
             tol = 5e-2 if k.endswith(".bias") else 1e-4
             assert abs(float(state.params[k].double().norm()) - n) <= tol * n + 1e-9, k
+
+
+def test_monce_hand_derived_backward_equals_autograd():
+    """The reverse sweep over the Sinkhorn scalings that csrc/nce.cu implements (restated in fp64 by
+    cut_oracle.monce_explicit) against autograd through the reference-pinned patch_nce_loss(kind="monce")."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    groups, p, d, popt = 2, 24, 32, 16
+    q = F.normalize(torch.randn(groups * p, d, generator=g)).requires_grad_(True)
+    k = F.normalize(torch.randn(groups * p, d, generator=g)).requires_grad_(True)
+    gout = torch.rand(groups * p, generator=g)
+    ref = C.patch_nce_loss(q, k, groups, T=0.07, kind="monce", num_patches_opt=popt)
+    ref.backward(gout)
+    loss, dq, dk = C.monce_explicit(q, k, gout, groups, T=0.07, num_patches_opt=popt)
+    assert float((loss.float() - ref.detach()).abs().max()) < 1e-4
+    assert float((dq.float() - q.grad).abs().max()) < 1e-5 * float(q.grad.abs().max())
+    assert float((dk.float() - k.grad).abs().max()) < 1e-5 * float(k.grad.abs().max())
