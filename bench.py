@@ -210,7 +210,6 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from joligen_b200 import kernels as K
     from joligen_b200 import lib as L
     from joligen_b200 import nets
     from joligen_b200 import synthetic

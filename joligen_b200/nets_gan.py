@@ -18,7 +18,6 @@ state_dict keys (`encoder.model.1.weight`, `encoder.model.10.conv_block.5.bias`,
 """
 import functools
 
-import torch
 import torch.nn as nn
 
 from . import kernels as K

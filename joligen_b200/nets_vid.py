@@ -15,8 +15,7 @@ import torch.nn as nn
 
 from . import lib as L
 from . import ops
-from .nets import (AttentionBlock, ConvIn, ConvPack, EmbedBlock, EmbedSequential, ResBlock, UNet, _OutHead,
-                   normalization)
+from .nets import AttentionBlock, ConvIn, ConvPack, EmbedSequential, ResBlock, UNet, _OutHead, normalization
 
 
 class VidResBlock(ResBlock):

@@ -28,7 +28,7 @@ Randomness (t, e) is an input.  Pinned against the real reference by oracle/gen_
 import math
 from dataclasses import dataclass
 from types import SimpleNamespace
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 import torch.nn.functional as F

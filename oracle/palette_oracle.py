@@ -21,7 +21,7 @@ without renaming.  Pinned against the real reference by oracle/gen_golden.py + t
 """
 import math
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch

@@ -7,7 +7,6 @@ nothing on the GPU box reads /root/reference.
 import importlib.abc
 import importlib.machinery
 import sys
-import types
 from unittest import mock
 
 REFERENCE_ROOT = "/root/reference"
