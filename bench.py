@@ -171,7 +171,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Palette UNet 256x256 train step (BASELINE config 2), CPU sample: " + cb["sample"]},
+        "config": {"workload": "palette_model Palette UNet %dx%d bf16 batch=%d/GPU, synthetic self-supervised masks"
+                               % (args.size, args.size, args.batch),
+                   "sample": "reference arithmetic (fp32 torch-CPU oracle port) on the host cores: " + cb["sample"]},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
