@@ -29,6 +29,7 @@ def _adopt(dst: nn.Module, src: nn.Module):
         if mod._parameters[leaf].shape != src_params[name].shape:
             raise RuntimeError("accelerate: shape mismatch for %s" % name)
         mod._parameters[leaf] = src_params[name]
+    _check_structure(dst, src)
     for name, buf in src_bufs.items():
         mod, leaf = _resolve(dst, name, create=True)
         mod._buffers[leaf] = buf
@@ -48,14 +49,39 @@ def _norm_spec(gn_wrapper):
     return "groupnorm%d" % g.num_groups
 
 
+def _has_tanh(ref):
+    """UNet(tanh=True) ends in (norm, conv, Tanh) instead of (norm, SiLU, conv) (unet_generator_attn.py:634-645)."""
+    return any(isinstance(m, nn.Tanh) for m in ref.out)
+
+
+def _check_structure(dst: nn.Module, src: nn.Module):
+    """Beyond parameter names: the two trees must hold the same number of blocks of each hot-path kind and the same
+    resampling / dropout configuration, otherwise an option this mirror does not implement would be dropped silently."""
+    kinds = ("ResBlock", "AttentionBlock", "AttentionBlockRef", "MotionModule")
+    is_kind = lambda m, k: any(c.__name__ == k for c in type(m).__mro__)  # noqa: E731  (VidResBlock is a ResBlock)
+    count = lambda root: {k: sum(is_kind(m, k) for m in root.modules()) for k in kinds}  # noqa: E731
+    if count(dst) != count(src):
+        raise RuntimeError("accelerate: block structure differs: reference %s vs B200 %s" % (count(src), count(dst)))
+    drops = sorted({float(m.p) for m in src.modules() if isinstance(m, nn.Dropout) and m.p > 0})
+    if drops:
+        raise NotImplementedError("accelerate: the reference net uses dropout %s (not supported on the B200 path)" % drops)
+    for a, b in zip((m for m in src.modules() if is_kind(m, "ResBlock")),
+                    (m for m in dst.modules() if is_kind(m, "ResBlock"))):
+        if (bool(a.updown), bool(a.use_scale_shift_norm), bool(getattr(a, "efficient", False))) != \
+                (bool(b.updown), bool(b.use_scale_shift_norm), bool(b.efficient)):
+            raise RuntimeError("accelerate: ResBlock configuration differs between reference and B200 module")
+
+
 def _unet_from_reference(ref):
     first_res = ref.input_blocks[1][0]
     norm = _norm_spec(first_res.in_layers[0])
     return nets.UNet(
         image_size=ref.image_size, in_channel=ref.in_channel, inner_channel=ref.inner_channel,
-        out_channel=ref.out_channel, res_blocks=list(ref.res_blocks), attn_res=list(ref.attn_res), tanh=False,
+        out_channel=ref.out_channel, res_blocks=list(ref.res_blocks), attn_res=list(ref.attn_res),
+        tanh=_has_tanh(ref), dropout=getattr(ref, "dropout", 0),
         n_timestep_train=ref.beta_schedule["train"]["n_timestep"],
-        n_timestep_test=ref.beta_schedule["test"]["n_timestep"], norm=norm, group_norm_size=32,
+        n_timestep_test=ref.beta_schedule["test"]["n_timestep"], norm=norm,
+        group_norm_size=first_res.in_layers[0].norm.num_groups,
         cond_embed_dim=ref.cond_embed_dim, channel_mults=tuple(ref.channel_mults), num_heads=ref.num_heads,
         num_head_channels=ref.num_head_channels, num_heads_upsample=ref.num_heads_upsample,
         use_scale_shift_norm=first_res.use_scale_shift_norm, efficient=first_res.efficient,
@@ -66,10 +92,12 @@ def _common_unet_kwargs(ref):
     first_res = ref.input_blocks[1][0]
     return dict(
         image_size=ref.image_size, in_channel=ref.in_channel, inner_channel=ref.inner_channel,
-        out_channel=ref.out_channel, res_blocks=list(ref.res_blocks), attn_res=list(ref.attn_res), tanh=False,
+        out_channel=ref.out_channel, res_blocks=list(ref.res_blocks), attn_res=list(ref.attn_res),
+        tanh=_has_tanh(ref), dropout=getattr(ref, "dropout", 0),
         n_timestep_train=ref.beta_schedule["train"]["n_timestep"],
         n_timestep_test=ref.beta_schedule["test"]["n_timestep"], norm=_norm_spec(first_res.in_layers[0]),
-        group_norm_size=32, cond_embed_dim=ref.cond_embed_dim, channel_mults=tuple(ref.channel_mults),
+        group_norm_size=first_res.in_layers[0].norm.num_groups, cond_embed_dim=ref.cond_embed_dim,
+        channel_mults=tuple(ref.channel_mults),
         use_scale_shift_norm=first_res.use_scale_shift_norm, efficient=first_res.efficient,
         freq_space=getattr(ref, "freq_space", False))
 

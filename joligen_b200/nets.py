@@ -41,6 +41,7 @@ class ConvPack:
         self.key = None
         self.packed = None
         self.managed_epoch = None  # _PACK_EPOCH value at which a trainer's batched pack last refreshed this entry
+        self.managed_key = None    # (weight._version, data_ptr, bias._version) seen by that refresh
 
     def _weight4(self):
         w4 = self.conv.weight.detach()
@@ -60,8 +61,16 @@ class ConvPack:
             return bias_p
         return b.detach()  # aliases the parameter storage: always current
 
+    def _torch_key(self):
+        w, b = self.conv.weight, self.conv.bias
+        return (w._version, w.data_ptr(), None if b is None else b._version)
+
     def get(self):
-        if self.managed_epoch is not None and self.managed_epoch == _PACK_EPOCH[0]:
+        # Managed entries are current as long as nothing wrote the master weights THROUGH torch since the trainer's
+        # last batched pack: the fused optimizer writes them through raw pointers (no version bump) and re-packs right
+        # after, whereas load_state_dict / copy_ / manual init bump `_version` and must trigger a re-pack here.
+        if (self.managed_epoch is not None and self.managed_epoch == _PACK_EPOCH[0]
+                and self.managed_key == self._torch_key()):
             return self.packed
         w = self.conv.weight
         b = self.conv.bias
@@ -70,8 +79,15 @@ class ConvPack:
             # a managed entry keeps its persistent buffers (the trainer's batched table points at them)
             out = (self.packed[0], self.packed[1]) if (self.managed_epoch is not None and self.packed) else None
             wf, wd = K.pack_conv_weight(self._weight4(), want_dgrad=True, out=out)
-            self.packed = (wf, wd, self._bias_padded())
+            bias_p = self._bias_padded()
+            if out is not None and self.packed[2] is not None and bias_p is not None \
+                    and self.packed[2].data_ptr() != bias_p.data_ptr():
+                self.packed[2].copy_(bias_p)  # managed padded-bias copy: keep the buffer captured graphs point at
+                bias_p = self.packed[2]
+            self.packed = (wf, wd, bias_p)
             self.key = key
+            if self.managed_epoch is not None:
+                self.managed_epoch, self.managed_key = _PACK_EPOCH[0], self._torch_key()
         return self.packed
 
 
@@ -110,6 +126,7 @@ class WeightPackSet:
     def _mark(self):
         for p in self.packs:
             p.managed_epoch = _PACK_EPOCH[0]
+            p.managed_key = p._torch_key()
 
     def refresh(self):
         if self.table is not None:

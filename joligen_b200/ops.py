@@ -67,20 +67,20 @@ class Conv2dFn(torch.autograd.Function):
                 raise RuntimeError("Conv2dFn: dgrad for stride %d is not implemented" % stride)
             dx = K.conv2d_fwd(dy, wd, None, x.shape[-1], r, s, stride=1, pad=r - 1 - pad)
         if _needs(ctx, 1):
+            # Writing dW behind autograd's back (no AccumulateGrad: DDP reducer hooks, register_hook and
+            # post-accumulate-grad hooks never fire for that parameter) is strictly opt-in: only a trainer that owns
+            # the parameter's flat .grad and its own all-reduce installs a `_jg_wstage` slot (trainer.WgradStage) and
+            # enables it for the duration of ITS backward pass.  Plain / accelerate() / DDP use always gets dw returned.
             g = None
-            if ctx.sink is not None and cout8 == cout and x.shape[-1] == cin:
+            stage = getattr(ctx.sink[0], "_jg_wstage", None) if ctx.sink is not None else None
+            if stage is not None and stage.enabled and cout8 == cout and x.shape[-1] == cin:
                 g = ctx.sink[0].grad
                 if g is not None and not (g.is_contiguous() and g.dtype == torch.float32 and g.numel() == cout * cin * r * s):
                     g = None
-            stage = getattr(ctx.sink[0], "_jg_wstage", None) if (g is not None) else None
-            if stage is not None and stage.enabled:
+            if g is not None:
                 # trainer-owned persistent split-K accumulator: raw accumulation now, ONE batched unpack into .grad
                 # for all convolutions at the end of the backward pass (WgradStage.flush)
                 stage.layout = K.conv2d_wgrad_acc(x, dy, cout8, r, s, stage.acc, stride=stride, pad=pad)
-            elif g is not None:
-                # the unpack epilogue of the wgrad adds into the existing .grad (beta = 1): no separate
-                # gradient tensor, no autograd accumulation kernel
-                K.conv2d_wgrad(x, dy, cout8, r, s, stride=stride, pad=pad, out=g, beta=1.0)
             else:
                 dw = K.conv2d_wgrad(x, dy, cout8, r, s, stride=stride, pad=pad)
                 if dw.shape[0] != cout or dw.shape[1] != cin:  # zero-padded channels (e.g. 6 -> 8, 3 -> 8)

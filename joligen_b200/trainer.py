@@ -153,6 +153,9 @@ class PaletteTrainer:
         self._eager_steps = 0
         self.step_dev = torch.zeros((), dtype=torch.int32, device=self.device)
         self.launches_per_step = 0  # kernels of libjg_b200.so per step (counted on an eager step)
+        # weights written through torch after construction (load_state_dict of a checkpoint, base_model.load_networks
+        # :957-1103): re-pack the bf16 copies at once — captured graphs never pass through ConvPack.get()
+        self.netG_A.register_load_state_dict_post_hook(lambda module, incompatible: self.packset.refresh())
 
     # -- data -----------------------------------------------------------------------------------
     def set_input(self, data, non_blocking=True):
@@ -212,6 +215,16 @@ class PaletteTrainer:
         self.loss_G_tot = loss.detach()
         return self.loss_G_tot
 
+    def reduced_gradient(self, noise=None, t=None, u=None):
+        """Forward + backward + the gradient exchange, without the optimizer: returns a copy of the flat fp32 gradient
+        SUMMED over the ranks (divide by the world size for DDP's mean) and leaves the gradient buffer zeroed.
+        Diagnostic / test entry point (tests/test_gpu_multi.py)."""
+        self._forward_backward(noise=noise, t=t, u=u)
+        dp.allreduce_sum_(self.flat.grad, self.pg)
+        g = self.flat.grad.clone()
+        self.flat.grad.zero_()
+        return g
+
     def _optimizer_step(self):
         grad_scale = 1.0 / self.world
         self.step += 1
@@ -270,6 +283,34 @@ class PaletteTrainer:
         return loss
 
     # -- state ----------------------------------------------------------------------------------
+    def state_dict(self):
+        """Everything a resumed run needs beyond netG_A.state_dict() (base_model.save_networks :824-868 stores the
+        nets and the optimizers): Adam moments, step counters and the EMA copy, keyed by parameter name."""
+        sd = {"step": self.step, "niter": self.niter, "ema_started": self.ema_started,
+              "exp_avg": {k: v.clone() for k, v in self.flat.unflatten(self.exp_avg).items()},
+              "exp_avg_sq": {k: v.clone() for k, v in self.flat.unflatten(self.exp_avg_sq).items()}}
+        if self.ema is not None:
+            sd["ema"] = {k: v.clone() for k, v in self.flat.unflatten(self.ema).items()}
+        return sd
+
+    def load_state_dict(self, sd):
+        """Inverse of state_dict(); the live weights are restored separately by netG_A.load_state_dict (which
+        re-packs the bf16 copies through the hook installed in __init__)."""
+        for name, flat in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq), ("ema", self.ema)):
+            if flat is None or name not in sd:
+                continue
+            views = self.flat.unflatten(flat)
+            missing = set(views) - set(sd[name])
+            if missing:
+                raise KeyError("PaletteTrainer.load_state_dict: %s lacks %s" % (name, sorted(missing)[:3]))
+            for k, v in views.items():
+                v.copy_(sd[name][k])
+        self.step = int(sd["step"])
+        self.niter = int(sd.get("niter", self.step * self.iter_size))
+        self.ema_started = bool(sd.get("ema_started", self.step > 0))
+        self.step_dev.fill_(self.step)  # the device-side counter the captured optimizer graph increments
+        self.packset.refresh()
+
     def ema_state_dict(self):
         """state_dict of netG_A_ema (base_model.py:1284-1297) — parameters from the flat EMA buffer,
         buffers copied from the live net."""

@@ -9,12 +9,10 @@
                                    the layer sum is divided by the number of REQUESTED layers (:892, 909)
     compute_D_loss                 0.5 * (GANLoss(D(real_B), True) + GANLoss(D(fake_B.detach()), False))
 
---alg_cut_nce_loss patchnce (kernels ran on hardware) or monce (the example's default; kernels compiled, not yet run).
+--alg_cut_nce_loss patchnce or monce (the example's default: Sinkhorn-weighted negatives, csrc/nce.cu).
 Parameters / gradients / Adam moments are flat fp32 buffers per network (G, F, D), one SUM all-reduce per group.
-
-STATUS: composition of kernels that each passed on hardware (generator / discriminator / GAN loss: test_gpu_gan.py;
-gather, L2 normalisation, PatchNCE: test_gpu_widen_cut.py); the step as a whole has NOT run on hardware yet — its test
-(tests/test_gpu_widen_cut.py::test_cut_trainer_vs_reference_plumbing) is behind the `unverified` marker.
+Checked on a B200 against the reference's own control path for both losses
+(tests/test_gpu_widen_cut.py::test_cut_trainer_vs_reference_plumbing, cut_plumbing*.pt).
 """
 import torch
 

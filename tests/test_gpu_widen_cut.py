@@ -2,14 +2,10 @@
 joligen_b200/nets_cut.py and nets_projd.py against oracle/cut_oracle.py, oracle/projd_oracle.py and the reference's
 golden vectors (tests/golden/cut_nce.pt, projd_small.pt).
 
-These were written after round 1's GPU minutes were nearly spent and got ONE run on a B200 with the last 80 seconds
-(profiles/r01_cut_tests_first_run.log): the kernel-level tests and every forward / loss / parameter-gradient check of
-the two end-to-end tests passed.  What did not pass were the feature-gradient checks: 6.81 % (NCE, second layer) and
-13.44 % (MultiScaleD, first scale) max-abs error against a 5 % bound chosen without measurements.  Both are the bf16
-storage floor — the oracle with the CUDA path's rounding points (palette_oracle.EMULATE_BF16) deviates from the fp32
-reference by 6.81 % and 13.44 % at exactly those places — so the bound is now max(5 %, 2.5 x that floor).  The
-re-bounded checks and the few that come after them have not run yet and stay behind the `unverified` marker
-(JG_RUN_UNVERIFIED=1 runs them).
+Feature-gradient bounds: the bf16 storage floor decides them — the oracle with the CUDA path's rounding points
+(palette_oracle.EMULATE_BF16) deviates from the fp32 reference by 6.81 % (NCE, second layer) and 13.44 % (MultiScaleD,
+first scale), so those checks are bounded by max(5 %, 2.5 x that floor).  Every test of this file, MoNCE and CutTrainer
+included, ran green on a B200 (profiles/r02_unverified_tests_first_run.log).
 """
 import os
 
@@ -18,8 +14,6 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
-unverified = pytest.mark.skipif(os.environ.get("JG_RUN_UNVERIFIED") != "1",
-                                reason="bound not yet calibrated on hardware (JG_RUN_UNVERIFIED=1 runs it)")
 
 
 @pytest.fixture(scope="module")
@@ -80,7 +74,6 @@ def test_patch_nce_fwd_bwd_vs_oracle(K, groups):
     assert rel(dq, q.grad) < 1e-4 and rel(dk, k.grad) < 1e-4
 
 
-@unverified
 @pytest.mark.parametrize("shape", [(2, 48, 256, 16), (3, 256, 256, 256), (1, 20, 32, 256)])
 def test_monce_fwd_bwd_vs_oracle(K, shape):
     """MoNCE (Sinkhorn-weighted negatives, differentiated through the 50 scalings) against the oracle's autograd."""
@@ -156,7 +149,6 @@ def test_patch_sample_and_nce_vs_reference_golden(golden_dir):
     _patch_sample_and_nce(golden_dir, with_gradients=False)
 
 
-@unverified
 def test_patch_sample_and_nce_gradients_vs_reference_golden(golden_dir):
     """... and d loss / d query features, MLP gradients (incl. the part through the keys)."""
     _patch_sample_and_nce(golden_dir, with_gradients=True)
@@ -212,16 +204,16 @@ def test_multi_scale_d_vs_reference_golden(golden_dir):
     _multi_scale_d(golden_dir, with_feature_gradients=False)
 
 
-@unverified
 def test_multi_scale_d_feature_gradients_vs_reference_golden(golden_dir):
     """... and d loss / d features, the power-iteration state after the step."""
     _multi_scale_d(golden_dir, with_feature_gradients=True)
 
 
-@unverified
-def test_cut_trainer_vs_reference_plumbing(golden_dir):
+@pytest.mark.parametrize("golden_name", ["cut_plumbing_patchnce.pt", "cut_plumbing.pt"])
+def test_cut_trainer_vs_reference_plumbing(golden_dir, golden_name):
     """CutTrainer (G on cat(real_A, real_B), GAN + 0.5 (NCE + identity NCE), F and D updates) against the reference's
-    own control path with --alg_cut_nce_loss patchnce (cut_plumbing_patchnce.pt) and the bf16-emulating oracle step."""
+    own control path with --alg_cut_nce_loss patchnce (cut_plumbing_patchnce.pt) and with the example's default, monce
+    (cut_plumbing.pt), and the bf16-emulating oracle step."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from joligen_b200 import nets_cut, nets_gan
@@ -230,7 +222,7 @@ def test_cut_trainer_vs_reference_plumbing(golden_dir):
     from oracle import palette_oracle as O
     from oracle.gen_golden_cut_plumbing import batch, patch_ids
     from oracle.vid_oracle import init_params_from_shapes
-    gold = torch.load(os.path.join(golden_dir, "cut_plumbing_patchnce.pt"))
+    gold = torch.load(os.path.join(golden_dir, golden_name))
     opt, cut = gold["optim"], gold["cut"]
     pG, pF, pD = (init_params_from_shapes(gold[k], seed)
                   for k, seed in zip(("shapes_G", "shapes_F", "shapes_D"), gold["seeds"]))

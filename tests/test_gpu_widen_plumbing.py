@@ -2,17 +2,14 @@
 vid_plumbing.pt: options -> create_model -> two optimize_parameters(), oracle/gen_golden_plumbing45.py) — the analogue
 of test_gpu_palette.py::test_train_steps_match_reference_plumbing for the other denoisers.
 
-Written after round 1's GPU minutes were spent: the trainer paths it exercises are covered by test_gpu_vid.py, but these
-two-step comparisons have not run on hardware yet and sit behind the `unverified` marker (JG_RUN_UNVERIFIED=1 runs them).
+Ran green on a B200 (profiles/r02_unverified_tests_first_run.log).
 """
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("JG_RUN_UNVERIFIED") != "1",
-                                 reason="not yet run on hardware (JG_RUN_UNVERIFIED=1 runs it)")]
+pytestmark = pytest.mark.gpu
 
 
 def _build(which, gold, params):
