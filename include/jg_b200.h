@@ -72,6 +72,30 @@ typedef struct {
 int jg_conv2d_fwd(const jg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                   const void* residual, void* y, jg_stream_t stream);
 
+/* GroupNorm work fused into the convolution's epilogue ("emit partial sum x, sum x^2 from the
+ * producing conv's epilogue so GN becomes a single read-modify-write pass"), all optional (NULL = off):
+ *   stats   fp32 [N][Cout][2], ACCUMULATED into (zero it first): per-(image, channel) sum and sum of squares of the
+ *           stored (bf16-rounded) output y — the statistics pass of the GroupNorm that reads y next
+ *           (unet_attn_utils.py:42-48 computes them in a separate pass over y).
+ *   gn_sums fp32 [N][Cout][2], ACCUMULATED into: this call is the DGRAD of the convolution that follows
+ *           act(a*x + b), a / b = the fused per-(n,c) GroupNorm(+FiLM) coefficients (jg_groupnorm_fwd's `ab`), so its
+ *           output y IS dL/d(act output); A[n,c] += sum_pixels du, B[n,c] += sum_pixels du*x with
+ *           du = y * act'(a*x + b): the reduction pass of jg_groupnorm_bwd (pass the result as `sums_pre`).
+ *           gn_x = the GroupNorm's input x (bf16 NHWC, channel stride ldgx), gn_ab = [N][Cout][2], gn_act = JG_ACT_*.
+ *           Not combinable with a residual operand.
+ * Kernels whose epilogue cannot fuse the work (tiles spanning several images, Cout <= 32) run the equivalent
+ * stand-alone reduction right after the convolution: the outputs are always filled. */
+typedef struct {
+  float* stats;
+  float* gn_sums;
+  const void* gn_x;
+  int ldgx;
+  const float* gn_ab;
+  int gn_act;
+} jg_conv_epilogue;
+int jg_conv2d_fwd_ex(const jg_conv_desc* d, const jg_conv_epilogue* e, const void* x, const void* w_packed,
+                     const float* bias, const void* residual, void* y, jg_stream_t stream);
+
 /* dw_oihw[Cout][Cin][R][S] = beta*dw_oihw + sum over pixels dy (x) x  (fp32, the reference's weight layout).
  * ws: fp32 workspace of R*S*Cin*Cout floats (zeroed by the call; split-K partial tiles are accumulated
  * into it with fp32 atomics, then permuted to OIHW).  d describes the FORWARD conv. */
@@ -146,7 +170,11 @@ size_t jg_groupnorm_fwd_ws_floats(int N, int C, int groups);
 size_t jg_groupnorm_bwd_ws_floats(int N, int C, int groups);
 int jg_groupnorm_fwd(const void* x, int ldx, void* y, int ldy, int N, int HW, int C, int groups, float eps,
                      const float* gamma, const float* beta, const float* film, int act, float* stats, float* ab,
-                     float* ws, jg_stream_t stream);
+                     float* ws, const float* chan_stats, jg_stream_t stream);
+/* chan_stats (above; may be NULL): per-(n, channel) sum / sum of squares of x, fp32 [N][C][2], already accumulated by
+ * the producer of x (jg_conv_epilogue.stats) or by jg_chan_stats: the statistics pass over x is skipped. */
+int jg_chan_stats(const void* x, int ldx, int N, int HW, int C, float* stats /* accumulated into */,
+                  jg_stream_t stream);
 /* dx = d/dx (+ addend (+ addend2), NHWC bf16 tensors like dx with strides ldadd / ldadd2, or NULL: the gradients of
  * other consumers of x — the ResBlock's skip path, the decoder's concat (unet_generator_attn.py:687) — summed in the
  * same pass; addend may alias dx; addend2 requires addend);
@@ -157,7 +185,9 @@ int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx,
                      int ldadd, const void* addend2, int ldadd2, int N,
                      int HW, int C, int groups, const float* gamma, const float* beta, const float* film, int act,
                      const float* stats, const float* ab, float* dgamma, float* dbeta, float* dfilm,
-                     float* dx_colsum, float* ws, jg_stream_t stream);
+                     float* dx_colsum, float* ws, const float* sums_pre, jg_stream_t stream);
+/* sums_pre (may be NULL): fp32 [N][C][2] = (sum du, sum du*x) per (n, channel), already accumulated by the dgrad that
+ * produced dy (jg_conv_epilogue.gn_sums): the reduction pass over (x, dy) is skipped. */
 
 /* ---------------------------------------------------------------------------------------------
  * Spatial self-attention (flash style, T x T never materialised), bf16, fp32 softmax.

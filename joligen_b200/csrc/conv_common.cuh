@@ -1,5 +1,6 @@
 // Shared pieces of the implicit-GEMM convolution kernels (conv_igemm.cu, conv_halo.cu).
 #pragma once
+#include "act.cuh"
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -24,7 +25,49 @@ struct ConvFwdParams {
   const float* bias;
   const __nv_bfloat16* res;
   __nv_bfloat16* y;
+  // ---- fused GroupNorm work (jg_conv_epilogue; TMA-store epilogue with one image per tile only) ----
+  // stats: per-(image, channel) sum and sum of squares of the STORED (bf16-rounded) output, [N][Cout][2] fp32,
+  //        accumulated with red.global.add: the statistics pass of the GroupNorm that consumes y.
+  float* stats;
+  // gn_sums: this launch is the dgrad of the conv that follows act(a*x+b) (a, b = the GroupNorm's fused per-(n,c)
+  //        coefficients): its output is dy.  A[n,c] += sum du, B[n,c] += sum du*x with du = dy*act'(a*x+b),
+  //        [N][Cout][2] fp32.  x travels as the `res` operand (res_mode = 1: it is NOT added to the output).
+  float* gn_sums;
+  const float* gn_ab;  // [N][Cout][2]
+  int gn_act;
+  int res_mode;        // 0: y += res_scale * res;  1: res is the GroupNorm input x of the gn_sums mode
 };
+
+// Column sums over the 32 lanes of a warp of 32 per-lane values each: on return lane l holds sum_lanes v[l].
+// Transposing butterfly: at every step a lane keeps one half of its values and hands the other half to its
+// partner (31 shuffles for 32 columns instead of 32 x 5).
+__device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+__device__ __forceinline__ float act_grad_rt(float u, int act) {
+  switch (act) {
+    case JG_ACT_SILU: return act_grad<JG_ACT_SILU>(u);
+    case JG_ACT_RELU: return act_grad<JG_ACT_RELU>(u);
+    case JG_ACT_LRELU02: return act_grad<JG_ACT_LRELU02>(u);
+    default: return 1.f;
+  }
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -145,7 +188,8 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
                                                        uint32_t t_acc, int q, int half, int n_tile, bool valid,
                                                        size_t pix, uint8_t* stage, int& stage_idx,
                                                        const CUtensorMap* tmY, int c1, int c2, int c3, bool issuer,
-                                                       const uint8_t* res_tile = nullptr) {
+                                                       const uint8_t* res_tile = nullptr, int img = 0,
+                                                       const float* s_ab = nullptr) {
   static_assert(BLOCK_N % 64 == 0, "TMA-store epilogue works on 64-channel slabs");
   const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16);
   const int row = q * 32 + (threadIdx.x & 31);
@@ -193,7 +237,7 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
         f[g * 4 + 2] += bias4[g].z; f[g * 4 + 3] += bias4[g].w;
       }
     }
-    if (has_res && (res_tile || valid)) {
+    if (has_res && p.res_mode == 0 && (res_tile || valid)) {
       const float rs = p.res_scale;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -219,6 +263,54 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
       o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
       o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
       *reinterpret_cast<uint4*>(buf + (((half * 4 + g) ^ swz) << 4)) = o;
+      if (p.stats || p.gn_sums) {  // keep the values that were actually stored (bf16-rounded)
+        const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 r = unpack_bf16x2(w4[k]);
+          f[g * 8 + 2 * k] = r.x;
+          f[g * 8 + 2 * k + 1] = r.y;
+        }
+      }
+    }
+    if (p.stats) {
+      // statistics of the stored tile for the GroupNorm that reads y next: per-channel sum / sum of squares over the
+      // warp's 32 pixel rows, one 8-byte red per lane (lane l <-> channel co0 + l)
+      float sq[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float r = valid ? f[j] : 0.f;  // rows outside a ragged output contribute nothing
+        sq[j] = r * r;
+        f[j] = r;
+      }
+      const float S = warp_colsum32(f);
+      const float Q = warp_colsum32(sq);
+      const int co = co0 + (threadIdx.x & 31);
+      if (co < p.Cout) red_add_v2(p.stats + (static_cast<size_t>(img) * p.Cout + co) * 2, S, Q);
+    } else if (p.gn_sums) {  // (never together with stats: f is consumed by the column sums)
+      // GroupNorm-backward sums: du = dy * act'(a*x + b), A = sum du, B = sum du*x over the warp's 32 pixel rows
+      float dux[32];
+      const bool live = res_tile != nullptr || valid;  // x of rows outside a ragged output was never loaded
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t w4[4] = {rcur[g].x, rcur[g].y, rcur[g].z, rcur[g].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 xv = unpack_bf16x2(w4[k]);
+          const int j = g * 8 + 2 * k;
+          const float4 ab = *reinterpret_cast<const float4*>(s_ab + 2 * (c + j));  // a_j, b_j, a_j+1, b_j+1
+          const float du0 = live ? f[j] * act_grad_rt(fmaf(xv.x, ab.x, ab.y), p.gn_act) : 0.f;
+          const float du1 = live ? f[j + 1] * act_grad_rt(fmaf(xv.y, ab.z, ab.w), p.gn_act) : 0.f;
+          f[j] = du0;
+          f[j + 1] = du1;
+          dux[j] = live ? du0 * xv.x : 0.f;
+          dux[j + 1] = live ? du1 * xv.y : 0.f;
+        }
+      }
+      const float A = warp_colsum32(f);
+      const float B = warp_colsum32(dux);
+      const int co = co0 + (threadIdx.x & 31);
+      if (co < p.Cout) red_add_v2(p.gn_sums + (static_cast<size_t>(img) * p.Cout + co) * 2, A, B);
     }
     fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA (async proxy)
     if (issuer) bulk_wait_read<0>();     // the previous slab's store has released the other buffer
@@ -232,8 +324,40 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
 }
 
 // Launch of the halo-reuse 3x3 kernel (conv_halo.cu); returns JG_ERR_UNSUPPORTED when the shape does not qualify.
-int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
-                     const void* residual, void* y, cudaStream_t stream);
+// e (may be NULL): fused GroupNorm work; *fused is set when the launched kernel's epilogue did it.
+int launch_conv_halo(const jg_conv_desc* d, const jg_conv_epilogue* e, const void* x, const void* w_packed,
+                     const float* bias, const void* residual, void* y, cudaStream_t stream, bool* fused);
+
+// Fills the fused-GroupNorm fields of the kernel parameters from the C-ABI structs; returns the operand that travels
+// through the residual plumbing (the residual itself, or the GroupNorm input x of the gn_sums mode).
+inline const void* conv_apply_epilogue(ConvFwdParams& p, const jg_conv_desc* d, const jg_conv_epilogue* e,
+                                       const void* residual) {
+  p.stats = nullptr; p.gn_sums = nullptr; p.gn_ab = nullptr; p.gn_act = 0; p.res_mode = 0;
+  if (!e) return residual;
+  p.stats = e->stats;
+  if (e->gn_sums) {
+    p.gn_sums = e->gn_sums; p.gn_ab = e->gn_ab; p.gn_act = e->gn_act; p.res_mode = 1;
+    p.ldres = e->ldgx;
+    return e->gn_x;
+  }
+  return residual;
+}
+
+// Stand-alone forms of the fused reductions (norm.cu).
+int launch_chan_stats(const void* x, int ldx, int N, int HW, int C, float* stats, cudaStream_t stream);
+int launch_gn_bwd_sums(const void* x, int ldx, const void* dy, int lddy, int N, int HW, int C, const float* ab, int act,
+                       float* AB, cudaStream_t stream);
+
+// The (a, b) coefficients of one tile's image and channel block, staged in shared memory for the gn_sums epilogue by
+// the 256 epilogue threads (double-buffered by the caller; named barrier 2).
+template <int BLOCK_N>
+__device__ __forceinline__ void conv_stage_gn_ab(const ConvFwdParams& p, float* dst, int img, int n_tile) {
+  const int e = threadIdx.x - 64;
+  const int c0 = n_tile * BLOCK_N;
+  for (int i = e; i < 2 * BLOCK_N; i += kEpiThreads)
+    dst[i] = (c0 + (i >> 1) < p.Cout) ? p.gn_ab[(static_cast<size_t>(img) * p.Cout + c0) * 2 + i] : 0.f;
+  bar_sync(2, kEpiThreads);
+}
 
 // wgrad with halo reuse (conv_halo.cu): zeroes ws, accumulates, writes OIHW; JG_ERR_UNSUPPORTED if not eligible.
 int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* ws, float* dw_oihw,

@@ -59,6 +59,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* rfull = tempty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rfull + 2);
   float* s_bias = reinterpret_cast<float*>(rfull + 4);
+  float* s_ab = s_bias + ((p.Cout + 64 + 31) / 32) * 32;  // 2 x [BLOCK_N][2] (gn_sums mode)
   conv_stage_bias(p, s_bias);
 
   const int warp = threadIdx.x >> 5;
@@ -256,6 +257,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     int rbuf = 0;
     uint32_t rphase = 0;
+    int ab_buf = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
@@ -267,13 +269,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool valid = (pw < p.Wo) && (ph < p.Ho);
       const size_t pix = (static_cast<size_t>(tn) * p.Ho + ph) * p.Wo + pw;
       if (!res_tma) conv_epilogue_prefetch<BLOCK_N>(p, pf, half, n_tile, valid, pix);
+      const float* ab_tile = nullptr;
+      if constexpr (TMA_STORE) {
+        if (p.gn_sums) {
+          conv_stage_gn_ab<BLOCK_N>(p, s_ab + ab_buf * 2 * BLOCK_N, tn, n_tile);
+          ab_tile = s_ab + ab_buf * 2 * BLOCK_N;
+          ab_buf ^= 1;
+        }
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if constexpr (TMA_STORE) {
         if (res_tma) mbar_wait(&rfull[rbuf], rphase);
         conv_epilogue_tile_tma<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile,
                                         valid, pix, stage, stage_idx, &tmY, tw * kHaloTW, th * kHaloTH, tn, issuer,
-                                        res_tma ? res_stage + rbuf * kStageBytes : nullptr);
+                                        res_tma ? res_stage + rbuf * kStageBytes : nullptr, tn, ab_tile);
         if (res_tma) {
           // the slab barrier inside the epilogue ordered every thread's reads of this residual buffer before here
           if (issuer && tile + 2 * static_cast<int>(gridDim.x) < p.total_tiles)
@@ -309,7 +319,8 @@ template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
 static int halo_smem_bytes(const HaloParams& hp) {
   const int b_tiles = B_RESIDENT ? hp.c.RS * hp.c.kc_blocks : SB;
   return SA * hp.a_stage_bytes + b_tiles * BLOCK_N * 128 + (BLOCK_N >= 64 ? 2 * kStageBytes : 0) +
-         ((BLOCK_N == 64 && hp.c.res) ? 2 * kStageBytes : 0) + (2 * SA + 2 * SB + 8) * 8 + (((hp.c.Cout + 64) * 4 + 127) / 128) * 128 + 1024;
+         ((BLOCK_N == 64 && hp.c.res) ? 2 * kStageBytes : 0) + (2 * SA + 2 * SB + 8) * 8 +
+         (((hp.c.Cout + 64) * 4 + 127) / 128) * 128 + (hp.c.gn_sums ? 2 * 2 * BLOCK_N * 4 : 0) + 1024;
 }
 
 template <int BLOCK_N, int SA, int SB, bool B_RESIDENT, int KS>
@@ -336,8 +347,8 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return launch_halo_ks<BLOCK_N, SA, SB, B_RESIDENT, 0>(tmA, tmB, tmY, tmR, hp, stream);
 }
 
-int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
-                     const void* residual, void* y, cudaStream_t stream) {
+int launch_conv_halo(const jg_conv_desc* d, const jg_conv_epilogue* e, const void* x, const void* w_packed,
+                     const float* bias, const void* residual_in, void* y, cudaStream_t stream, bool* fused) {
   // qualification: stride 1, a real spatial filter, "same"-style geometry handled generally via pad,
   // tiles of 8 x 16 output pixels must tile the output exactly (ragged sizes go to the generic kernel)
   if (d->stride != 1 || d->R * d->S == 1 || d->R > 5 || d->S > 5) return JG_ERR_UNSUPPORTED;
@@ -356,6 +367,10 @@ int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed,
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   p.ldy = d->ldy; p.ldres = d->ldres; p.act = d->act; p.res_scale = d->res_scale;
   p.bias = bias;
+  // fused GroupNorm work needs the TMA-store epilogue (Cout > 32); otherwise the caller runs the stand-alone reduction
+  const bool fuse = e != nullptr && block_n >= 64;
+  const void* residual = conv_apply_epilogue(p, d, fuse ? e : nullptr, residual_in);
+  if (fused) *fused = fuse;
   p.res = static_cast<const __nv_bfloat16*>(residual);
   p.y = static_cast<__nv_bfloat16*>(y);
   hp.R = d->R;
@@ -394,8 +409,8 @@ int launch_conv_halo(const jg_conv_desc* d, const void* x, const void* w_packed,
   CUtensorMap tmR = tmA;  // residual tiles (64-channel kernels with a residual)
   if (block_n == 64 && residual) {
     uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
-    uint64_t strides[3] = {(uint64_t)d->ldres * 2, (uint64_t)d->Wo * d->ldres * 2,
-                           (uint64_t)d->Ho * d->Wo * d->ldres * 2};
+    uint64_t strides[3] = {(uint64_t)p.ldres * 2, (uint64_t)d->Wo * p.ldres * 2,
+                           (uint64_t)d->Ho * d->Wo * p.ldres * 2};
     uint32_t box[4] = {64, (uint32_t)kHaloTW, (uint32_t)kHaloTH, 1};
     uint32_t es[4] = {1, 1, 1, 1};
     rc = make_tmap_bf16(&tmR, residual, 4, dims, strides, box, es);

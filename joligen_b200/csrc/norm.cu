@@ -12,6 +12,7 @@
 // forward:   y = act(x*a[n,c] + b[n,c]),   a = rstd*gamma*(1+scale),  b = (beta - mean*rstd*gamma)*(1+scale) + shift
 // backward:  du = dy*act'(u);  A[n,c] = sum du, B[n,c] = sum du*x;  everything else (dgamma, dbeta, dscale,
 //            dshift, the two group means) is a function of A,B;  dx = k1[n,c]*du + k2[n,g]*x + k3[n,g].
+#include "act.cuh"
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -53,42 +54,6 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   o.w = pack_bf16x2(f[6], f[7]);
   return o;
 }
-// sigmoid with ONE MUFU op (ex2) and 7 FMA-pipe + 1 ALU-pipe instructions per element.  These kernels run at HBM speed
-// only if they stay near ~10 instructions per element (ncu: the first version, ~22 instructions/element, was issue-bound
-// at 76% issue utilisation and 50% DRAM utilisation), and two MUFU ops per element (ex2 + rcp) would load the 16-lane
-// special function unit to ~75%.  The reciprocal of x = 1 + e is an integer-subtract seed (5% error) refined by one
-// cubically convergent step r*(1 + eps + eps^2), eps = 1 - x*r: relative error < 1.3e-4, 30x below a bf16 ulp.
-// The saturating FMA (free modifier) keeps r in [0, 1] and flushes the NaN/inf that the seed produces for
-// e >= 2^126 (u < -87) to 0, which is the correct limit: no clamp instruction is needed.
-__device__ __forceinline__ float fast_sigmoid(float u) {
-  float e;
-  const float t = -1.4426950408889634f * u;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
-  const float x = 1.f + e;
-  const float r = __int_as_float(0x7EF311C7 - __float_as_int(x));
-  const float eps = fmaf(-x, r, 1.f);
-  const float w = fmaf(eps, eps, eps);
-  return __saturatef(fmaf(r, w, r));
-}
-// activation applied after the affine: none / SiLU (UNet) / ReLU, LeakyReLU(0.2) (GAN generator / discriminator);
-// a template parameter so that the per-element code has no activation dispatch in it
-template <int ACT>
-__device__ __forceinline__ float act_f(float u) {
-  if (ACT == JG_ACT_SILU) return u * fast_sigmoid(u);
-  if (ACT == JG_ACT_RELU) return fmaxf(u, 0.f);
-  if (ACT == JG_ACT_LRELU02) return u > 0.f ? u : 0.2f * u;
-  return u;
-}
-template <int ACT>
-__device__ __forceinline__ float act_grad(float u) {
-  if (ACT == JG_ACT_SILU) {
-    const float s = fast_sigmoid(u);
-    return s * (1.f + fmaf(-u, s, u));  // s * (1 + u * (1 - s))
-  }
-  if (ACT == JG_ACT_RELU) return u > 0.f ? 1.f : 0.f;
-  if (ACT == JG_ACT_LRELU02) return u > 0.f ? 1.f : 0.2f;
-  return 1.f;
-}
 #define JG_ACT_DISPATCH(act, ...)                                                    \
   switch (act) {                                                                     \
     case JG_ACT_SILU: { constexpr int ACT = JG_ACT_SILU; __VA_ARGS__; } break;       \
@@ -127,7 +92,7 @@ __device__ __forceinline__ void block_channel_sums(const float (&vals)[Q][8], bo
 // grid (chunks, N); smem: kPartFloats*2 + 2*C floats.  Eight rows (8 x 16 B) are in flight per thread.
 __global__ void __launch_bounds__(kNormThreads, 4)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int groups, int rows_per_block,
-                float* __restrict__ sums /*[N][groups][2]*/) {
+                float* __restrict__ sums /*[N][groups][2], or [N][C][2] when groups == 0 (per-channel sums)*/) {
   extern __shared__ float sm[];
   float* part = sm;
   float* csum = sm + 2 * kPartFloats;  // [2][C]: sum, sum of squares
@@ -162,6 +127,13 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int
     for (; r < r1; r += rstep) reduce(ldg_stream(base + (size_t)r * ldx));
   }
   block_channel_sums<2>(acc, active, rl, v, rstep, C, part, csum);
+  if (groups == 0) {  // per-channel sums (the layout the convolution epilogues accumulate into)
+    for (int c = threadIdx.x; c < C; c += kNormThreads) {
+      atomicAdd(&sums[((size_t)n * C + c) * 2 + 0], csum[c]);
+      atomicAdd(&sums[((size_t)n * C + c) * 2 + 1], csum[C + c]);
+    }
+    return;
+  }
   const int cpg = C / groups;
   for (int g = threadIdx.x; g < groups; g += kNormThreads) {
     float s = 0.f, q = 0.f;
@@ -176,7 +148,9 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int
 
 // ---- pass 2 (fwd): mean/rstd and the per-(n,c) affine coefficients -----------------------------
 // grid N, threads over C.
-__global__ void gn_finalize_fwd_kernel(const float* __restrict__ sums, int HW, int C, int groups, float eps,
+// chan_sums != 0: `sums` holds per-(n, channel) sums [N][C][2] (produced by a convolution epilogue or by
+// gn_stats_kernel in per-channel mode) instead of per-group sums.
+__global__ void gn_finalize_fwd_kernel(const float* __restrict__ sums, int chan_sums, int HW, int C, int groups, float eps,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        const float* __restrict__ film /*[N][2C]*/, float* __restrict__ stats,
                                        float* __restrict__ ab /*[N][C][2]*/) {
@@ -185,8 +159,17 @@ __global__ void gn_finalize_fwd_kernel(const float* __restrict__ sums, int HW, i
   const float cnt = (float)cpg * (float)HW;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const float s = sums[((size_t)n * groups + g) * 2 + 0];
-    const float q = sums[((size_t)n * groups + g) * 2 + 1];
+    float s, q;
+    if (chan_sums) {
+      s = q = 0.f;
+      for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
+        s += sums[((size_t)n * C + k) * 2 + 0];
+        q += sums[((size_t)n * C + k) * 2 + 1];
+      }
+    } else {
+      s = sums[((size_t)n * groups + g) * 2 + 0];
+      q = sums[((size_t)n * groups + g) * 2 + 1];
+    }
     const float mean = s / cnt;
     const float var = fmaxf(q / cnt - mean * mean, 0.f);
     const float rstd = rsqrtf(var + eps);
@@ -506,9 +489,41 @@ extern "C" size_t jg_groupnorm_bwd_ws_floats(int N, int C, int groups) {
   return (size_t)N * C * 2 /*AB*/ + (size_t)N * C /*k1*/ + (size_t)N * groups * 2 /*k23*/ + (size_t)N * C * 2 /*gAB*/;
 }
 
+namespace jg {
+// Stand-alone forms of the two reductions that the convolution epilogues fuse (conv_common.cuh): used by the conv
+// launchers for kernels whose epilogue cannot do it, and exported for tests.
+int launch_chan_stats(const void* x, int ldx, int N, int HW, int C, float* stats, cudaStream_t stream) {
+  int rc = check_norm_args(N, HW, C, 1, ldx);
+  if (rc) return rc;
+  const int rpb = rows_per_block_for(HW, N, 4);
+  dim3 grid((HW + rpb - 1) / rpb, N);
+  const size_t smem = (2 * kPartFloats + 2 * C) * sizeof(float);
+  gn_stats_kernel<<<grid, kNormThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, HW, C, 0, rpb, stats);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+int launch_gn_bwd_sums(const void* x, int ldx, const void* dy, int lddy, int N, int HW, int C, const float* ab, int act,
+                       float* AB, cudaStream_t stream) {
+  int rc = check_norm_args(N, HW, C, 1, ldx);
+  if (rc) return rc;
+  const int rpb = rows_per_block_for(HW, N, 2);
+  dim3 grid((HW + rpb - 1) / rpb, N);
+  JG_ACT_DISPATCH(act, gn_bwd_sums_kernel<ACT><<<grid, kNormThreads, (2 * kPartFloats + 2 * C) * sizeof(float), stream>>>(
+                           static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(dy), lddy, HW, C,
+                           rpb, ab, AB));
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+}  // namespace jg
+
+extern "C" int jg_chan_stats(const void* x, int ldx, int N, int HW, int C, float* stats, jg_stream_t stream_) {
+  JG_CHECK(x && stats, JG_ERR_INVALID, "chan_stats: null pointer");
+  return launch_chan_stats(x, ldx, N, HW, C, stats, static_cast<cudaStream_t>(stream_));
+}
+
 extern "C" int jg_groupnorm_fwd(const void* x, int ldx, void* y, int ldy, int N, int HW, int C, int groups, float eps,
                                 const float* gamma, const float* beta, const float* film, int act, float* stats,
-                                float* ab, float* ws, jg_stream_t stream_) {
+                                float* ab, float* ws, const float* chan_stats, jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_norm_args(N, HW, C, groups, ldx);
   if (rc) return rc;
@@ -516,16 +531,18 @@ extern "C" int jg_groupnorm_fwd(const void* x, int ldx, void* y, int ldy, int N,
   JG_CHECK(ldy % 8 == 0 && ldy >= C, JG_ERR_INVALID, "groupnorm_fwd: bad ldy");
   JG_CHECK(act == JG_ACT_NONE || act == JG_ACT_SILU || act == JG_ACT_RELU || act == JG_ACT_LRELU02, JG_ERR_INVALID,
            "groupnorm_fwd: act %d unsupported", act);
-  JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)N * groups * 2, stream));
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
-  {
+  if (!chan_stats) {
+    JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)N * groups * 2, stream));
     const int rpb = rows_per_block_for(HW, N, 4);
     dim3 grid((HW + rpb - 1) / rpb, N);
     const size_t smem = (2 * kPartFloats + 2 * C) * sizeof(float);
     gn_stats_kernel<<<grid, kNormThreads, smem, stream>>>(xb, ldx, HW, C, groups, rpb, ws);
     JG_LAUNCH_CHECK();
   }
-  gn_finalize_fwd_kernel<<<N, 256, 0, stream>>>(ws, HW, C, groups, eps, gamma, beta, film, stats, ab);
+  // chan_stats: the producer of x (a convolution epilogue, jg_conv_epilogue.stats) already summed it per channel
+  gn_finalize_fwd_kernel<<<N, 256, 0, stream>>>(chan_stats ? chan_stats : ws, chan_stats != nullptr, HW, C, groups, eps,
+                                                gamma, beta, film, stats, ab);
   JG_LAUNCH_CHECK();
   const int rpb = rows_per_block_for(HW, N, 8);
   dim3 grid((HW + rpb - 1) / rpb, N);
@@ -539,7 +556,8 @@ extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy
                                 int ldadd, const void* addend2, int ldadd2, int N, int HW, int C, int groups,
                                 const float* gamma, const float* beta,
                                 const float* film, int act, const float* stats, const float* ab, float* dgamma,
-                                float* dbeta, float* dfilm, float* dx_colsum, float* ws, jg_stream_t stream_) {
+                                float* dbeta, float* dfilm, float* dx_colsum, float* ws, const float* sums_pre,
+                                jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_norm_args(N, HW, C, groups, ldx);
   if (rc) return rc;
@@ -552,7 +570,9 @@ extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy
   float* k1 = AB + (size_t)N * C * 2;
   float* k23 = k1 + (size_t)N * C;
   float* gAB = k23 + (size_t)N * groups * 2;
-  JG_CUDA(cudaMemsetAsync(AB, 0, sizeof(float) * (size_t)N * C * 2, stream));
+  // sums_pre: A / B were accumulated by the dgrad that produced dy (jg_conv_epilogue.gn_sums): no reduction pass
+  if (sums_pre) AB = const_cast<float*>(sums_pre);
+  else JG_CUDA(cudaMemsetAsync(AB, 0, sizeof(float) * (size_t)N * C * 2, stream));
   if (dx_colsum) JG_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, stream));
   const int rpb1 = rows_per_block_for(HW, N, 2);
   const int rpb = rows_per_block_for(HW, N, 2);
@@ -563,9 +583,11 @@ extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy
   const __nv_bfloat16* addb = static_cast<const __nv_bfloat16*>(addend);
   const __nv_bfloat16* addb2 = static_cast<const __nv_bfloat16*>(addend2);
   __nv_bfloat16* dxb = static_cast<__nv_bfloat16*>(dx);
-  JG_ACT_DISPATCH(act, gn_bwd_sums_kernel<ACT><<<grid1, kNormThreads, (2 * kPartFloats + 2 * C) * sizeof(float), stream>>>(
-                           xb, ldx, dyb, lddy, HW, C, rpb1, ab, AB));
-  JG_LAUNCH_CHECK();
+  if (!sums_pre) {
+    JG_ACT_DISPATCH(act, gn_bwd_sums_kernel<ACT><<<grid1, kNormThreads, (2 * kPartFloats + 2 * C) * sizeof(float), stream>>>(
+                             xb, ldx, dyb, lddy, HW, C, rpb1, ab, AB));
+    JG_LAUNCH_CHECK();
+  }
   gn_finalize_bwd_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(AB, HW, C, groups, gamma, beta, film, stats, k1,
                                                                     k23, dfilm, gAB);
   JG_LAUNCH_CHECK();

@@ -29,6 +29,21 @@ def synthetic_batch(batch, size, seed):
     return {"A": cond, "B": gt, "B_label_mask": mask}
 
 
+def synthetic_rect_batch(batch, h, w, seed):
+    """The same inputs for non-square crops (config 4's 512 x 384 VITON frames): boxes cover 10-40 % of the area."""
+    g = torch.Generator().manual_seed(seed)
+    gt = (0.5 * torch.randn(batch, 3, h, w, generator=g)).clamp(-1, 1)
+    mask = torch.zeros(batch, 1, h, w, dtype=torch.int64)
+    for i in range(batch):
+        frac = math.sqrt(0.1 + 0.3 * float(torch.rand((), generator=g)))
+        bh, bw = max(1, int(round(h * frac))), max(1, int(round(w * frac)))
+        y0 = int(torch.randint(0, h - bh + 1, (), generator=g))
+        x0 = int(torch.randint(0, w - bw + 1, (), generator=g))
+        mask[i, 0, y0:y0 + bh, x0:x0 + bw] = 1
+    rnd = torch.randn(batch, 3, h, w, generator=g)
+    return {"A": gt * (1 - mask) + rnd * mask, "B": gt, "B_label_mask": mask}
+
+
 @torch.no_grad()
 def dezero_init_(module, seed, scale=1.0):
     """In-place seeded init of every parameter, in named_parameters() order: fan-in scaled normal

@@ -215,6 +215,13 @@ class PaletteTrainer:
         self.loss_G_tot = loss.detach()
         return self.loss_G_tot
 
+    def eager_step(self):
+        """One full step launched kernel by kernel (no graph replay), on the current inputs: profiling entry point."""
+        loss = self._forward_backward()
+        dp.allreduce_sum_(self.flat.grad, self.pg)
+        self._optimizer_step()
+        return loss
+
     def reduced_gradient(self, noise=None, t=None, u=None):
         """Forward + backward + the gradient exchange, without the optimizer: returns a copy of the flat fp32 gradient
         SUMMED over the ranks (divide by the world size for DDP's mean) and leaves the gradient buffer zeroed.

@@ -9,9 +9,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_the_contract_line():
+    # as torchrun launches it: OMP_NUM_THREADS=1 in the environment must not throttle the CPU arm to one thread
+    env = dict(os.environ, OMP_NUM_THREADS="1", JG_CPU_THREADS="2")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                         "--warmup", "0", "--size", "64", "--batch", "1"], capture_output=True, text=True, timeout=600,
-                       cwd=ROOT)
+                       cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1, r.stdout
@@ -23,3 +25,7 @@ def test_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+    assert d["cpu_baseline"]["cores"] == 2                       # the explicit thread count, not torchrun's 1
+    assert d["steps"] == d["cpu_baseline"]["steps_timed"] == 1   # the line reports what was really timed
+    if os.path.exists(os.path.join(ROOT, "baseline", "_ref", "models", "base_model.py")):
+        assert d["cpu_baseline"]["kind"] == "reference"
