@@ -415,11 +415,15 @@ def main():
         e0.record()
         yield
         e1.record()
-        if name in ("jg_conv2d_fwd", "jg_conv2d_wgrad", "jg_conv2d_wgrad_acc"):
+        if name in ("jg_conv2d_fwd", "jg_conv2d_fwd_ex", "jg_conv2d_wgrad", "jg_conv2d_wgrad_acc"):
             d = cargs[0]._obj
             flops = 2.0 * d.N * d.Ho * d.Wo * d.Cout * d.Cin * d.R * d.S
             recs.append((name, flops, e0, e1))
-            allrecs.append((name, (d.N, d.H, d.W, d.Cin, d.Cout, d.R, d.stride), flops, e0, e1))
+            tag = name
+            if name == "jg_conv2d_fwd_ex":  # which GroupNorm reduction rides in the epilogue
+                e = cargs[1]._obj
+                tag = "jg_conv2d_fwd+" + ("stats" if e.stats else "") + ("gnsums" if e.gn_sums else "")
+            allrecs.append((tag, (d.N, d.H, d.W, d.Cin, d.Cout, d.R, d.stride), flops, e0, e1))
         elif name == "jg_groupnorm_fwd":
             allrecs.append((name, tuple(int(v) for v in cargs[4:8]), 0.0, e0, e1))
         elif name == "jg_groupnorm_bwd":

@@ -141,6 +141,30 @@ int jg_unpack_conv_wgrad(const float* dw_ohwi, float* dw_oihw, int Cout, int Cin
 int jg_bias_grad(const void* dy, int64_t rows, int C, int ld, float* db, jg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Gradient exchange: a communicator owned by the library, one per process / GPU,
+ * bound to NCCL at run time.  Replaces DistributedDataParallel's bucketed, backward-overlapped all-reduce
+ * (models/base_model.py:725-737) for the trainers of this package.
+ *   jg_comm_unique_id   rank 0 creates the 128-byte id; the caller ships it to the other ranks (torch.distributed
+ *                       broadcast, MPI, a file ...).  HOST pointer.
+ *   jg_comm_init        collective over all ranks; uses the calling thread's current device.
+ *   jg_comm_allreduce_async  in-place SUM of buf[count] (dtype 0 = fp32, 1 = bf16) on the communicator's own stream,
+ *                       ordered after everything `compute_stream` has been given so far; returns at once, so the
+ *                       caller keeps launching backward kernels while the bucket is in flight.
+ *   jg_comm_wait        `compute_stream` waits for every collective issued so far (no host synchronisation).
+ *   Both work inside a CUDA-graph capture of `compute_stream` (the collective becomes a forked branch of the graph).
+ *   jg_comm_broadcast   in-place byte broadcast from `root`, complete on `compute_stream` order.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct jg_comm* jg_comm_t;
+int jg_comm_unique_id(void* id128_host);
+int jg_comm_init(const void* id128_host, int rank, int world, jg_comm_t* out);
+int jg_comm_allreduce_async(jg_comm_t c, void* buf, size_t count, int dtype, jg_stream_t compute_stream);
+int jg_comm_broadcast(jg_comm_t c, void* buf, size_t bytes, int root, jg_stream_t compute_stream);
+int jg_comm_wait(jg_comm_t c, jg_stream_t compute_stream);
+int jg_comm_info(jg_comm_t c, int* rank, int* world, unsigned long long* collectives, unsigned long long* bytes,
+                 int* nccl_version);
+int jg_comm_destroy(jg_comm_t c);
+
+/* ---------------------------------------------------------------------------------------------
  * Boundary / layout kernels (HBM-bound).
  * ------------------------------------------------------------------------------------------- */
 /* NCHW fp32 (reference layout, e.g. UNet.compute_feats input `h = input.type(torch.float32)`,
@@ -157,6 +181,30 @@ int jg_copy_channels(const void* src, int lds, void* dst, int ldd, int64_t rows,
  * mode 1: nn.AvgPool2d(2,2) (Downsample, :125-140); mode 2 / 3: their backward passes. */
 int jg_resample2x(const void* src, int lds, void* dst, int ldd, int N, int Hs, int Ws, int C, int mode,
                   jg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * On-GPU input preparation and Haar wavelets, fp32 NCHW images.  HBM-bound.
+ *   jg_fill_mask_random      data/online_creation.py:1366-1376 fill_mask_with_random(img, mask, cls):
+ *                            out = img*(1-m) + noise*m, m = (mask != 0) if cls == -1 else (mask == cls); the mask
+ *                            ([N][1][H][W], fp32 or int64 — pass exactly one) is compared exactly.
+ *   jg_u8_to_f32_normalized  transforms.ToTensor + transforms.Normalize(mean, std) (data/base_dataset.py
+ *                            get_transform): uint8 [N][H][W][C] -> fp32 [N][C][H][W], (x/255 - mean)/std.
+ *   jg_mask_class_dropout    models/palette_model.py:565-584: mask <- fill (= num_classes - 1) for the samples with
+ *                            drop_u[n] < prob, unchanged elsewhere (per_image = elements of one sample's mask).
+ *   jg_haar                  models/modules/freq_utils.py:22-59 on upfirdn2d (models/modules/op/upfirdn2d.py:167-208,
+ *                            upfirdn2d_kernel.cu:49-200).  (h, w) is the LOW-resolution size.
+ *                            mode 0 HaarTransform: x [N][C][2h][2w] -> [N][4C][h][w] = cat(ll, lh, hl, hh)
+ *                            mode 1 its backward;  mode 2 InverseHaarTransform: [N][4C][h][w] -> [N][C][2h][2w]
+ *                            mode 3 its backward.
+ * ------------------------------------------------------------------------------------------- */
+int jg_fill_mask_random(const float* img, const float* mask_f32, const int64_t* mask_i64, const float* noise,
+                        float* out, int N, int C, int HW, int cls, jg_stream_t stream);
+int jg_u8_to_f32_normalized(const uint8_t* src_nhwc, float* dst_nchw, int N, int C, int H, int W, float mean,
+                            float stdv, jg_stream_t stream);
+int jg_mask_class_dropout(const float* mask_f32, const int64_t* mask_i64, const float* drop_u, float prob,
+                          int64_t fill, float* out_f32, int64_t* out_i64, int N, int64_t per_image,
+                          jg_stream_t stream);
+int jg_haar(const float* src, float* dst, int N, int C, int h, int w, int mode, jg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GroupNorm (+ FiLM scale/shift) (+ SiLU), NHWC bf16, fp32 statistics.  HBM-bound.
@@ -232,6 +280,23 @@ int jg_geglu_fwd(const void* x, int ldx, void* y, int ldy, int64_t rows, int Cou
 int jg_geglu_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int64_t rows, int Cout,
                  jg_stream_t stream);
 
+/* All emb_layers Linears of a UNet in ONE launch (unet_generator_attn.py:201-207, 247-258): n items
+ * y_i[B][O_i] = act_in(x[B][I]) @ W_i^T + b_i on the same x.  Item i owns the contiguous [B][O_i] block of Y (and of
+ * dY in the backward) at float offset B * off, off = the item's first output in the concatenation of all items.
+ * Tiles: jg_linear_batched_tiles(O_i) per item, tile_start_dev = exclusive prefix sum.  Backward: dW [sum O][I] and
+ * dB [sum O] (item i at rows off .. off + O_i) are overwritten; dx [B][I] (may be NULL) = the sum over items.
+ * B <= 64, I <= 128. */
+typedef struct {
+  const float* w;  /* [O][I] */
+  const float* b;  /* [O] or NULL */
+  int O, off;
+} jg_linear_item;
+int jg_linear_batched_tiles(int O);
+int jg_linear_batched_fwd(const float* x, const jg_linear_item* items_dev, const int* tile_start_dev, int n,
+                          int total_tiles, float* Y, int B, int I, int act_in, jg_stream_t stream);
+int jg_linear_batched_bwd(const float* x, const jg_linear_item* items_dev, const int* tile_start_dev, int n,
+                          int total_tiles, const float* dY, float* dW, float* dB, float* dx, int B, int I, int act_in,
+                          jg_stream_t stream);
 /* ---------------------------------------------------------------------------------------------
  * Small fp32 Linear on [B, I] embeddings with optional SiLU on the input / output:
  *   ResBlock.emb_layers = SiLU -> Linear (unet_generator_attn.py:201-207),

@@ -65,7 +65,7 @@ def build(force=False, verbose=False):
     rebuilt = any(r for _, r in results)
     if rebuilt or not os.path.exists(LIB):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                      "-lcudart"]
+                                                      "-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

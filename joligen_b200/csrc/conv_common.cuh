@@ -1,5 +1,7 @@
 // Shared pieces of the implicit-GEMM convolution kernels (conv_igemm.cu, conv_halo.cu).
 #pragma once
+#include <stdlib.h>
+
 #include "act.cuh"
 #include "common.cuh"
 #include "ptx.cuh"
@@ -9,6 +11,9 @@ namespace jg {
 constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int kWgradThreads = 192;
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kStageBytes = 128 * 128;  // one 64-channel slab of an output tile (TMA-store epilogue)
+constexpr int kEpiThreads = 256;
+constexpr int kMaxFusedCout = 1024;     // widest output whose GroupNorm sums fit the shared-memory accumulators
 
 struct ConvFwdParams {
   int N, Ho, Wo;
@@ -36,28 +41,43 @@ struct ConvFwdParams {
   const float* gn_ab;  // [N][Cout][2]
   int gn_act;
   int res_mode;        // 0: y += res_scale * res;  1: res is the GroupNorm input x of the gn_sums mode
+  int dbg;             // JG_DBG_EPI bits (timing experiments only): 1 = plain stores instead of red.global.add
 };
 
-// Column sums over the 32 lanes of a warp of 32 per-lane values each: on return lane l holds sum_lanes v[l].
-// Transposing butterfly: at every step a lane keeps one half of its values and hands the other half to its
-// partner (31 shuffles for 32 columns instead of 32 x 5).
-__device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
-  const uint32_t lane = threadIdx.x & 31;
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = up ? v[i] : v[i + off];
-      const float keep = up ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
+__device__ __forceinline__ void red_add_v4f(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
 }
 
-__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
-  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+// Tile schedule of the persistent forward kernels.  Default: static round robin (tile = cta, cta + grid, ...): CTAs
+// that run together work on neighbouring tiles.  With fused GroupNorm reductions every CTA takes ONE CONTIGUOUS chunk of
+// tiles instead: its tiles then stay inside one or two images, so the per-(image, channel) sums can be accumulated in
+// shared memory and reach global memory once per image.  (Measured on B200: with round robin, the 148 CTAs of a wave all
+// hit the same image's 2*Cout addresses with red.global.add at the same time and the conv slows down by up to 50 %.)
+struct TileRange {
+  int begin, end, step;
+};
+__device__ __forceinline__ TileRange conv_tile_range(const ConvFwdParams& p) {
+  if ((p.stats || p.gn_sums) && !(p.dbg & 2)) {
+    const int per = (p.total_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int b = static_cast<int>(blockIdx.x) * per;
+    return TileRange{b, min(p.total_tiles, b + per), 1};
+  }
+  return TileRange{static_cast<int>(blockIdx.x), p.total_tiles, static_cast<int>(gridDim.x)};
+}
+
+// Epilogue threads (256): add the CTA's shared-memory sums of image `img` into the global [N][Cout][2] array and clear
+// them.  Named barrier 2 on both sides (every epilogue thread must call it at the same point of its tile loop).
+__device__ __forceinline__ void conv_flush_sums(const ConvFwdParams& p, float* s_acc, int img) {
+  bar_sync(2, kEpiThreads);
+  float* dst = (p.stats ? p.stats : p.gn_sums) + static_cast<size_t>(img) * p.Cout * 2;
+  for (int i = (static_cast<int>(threadIdx.x) - 64) * 4; i < 2 * p.Cout; i += kEpiThreads * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(s_acc + i);
+    *reinterpret_cast<float4*>(s_acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.dbg & 1) *reinterpret_cast<float4*>(dst + i) = v;  // (wrong sums: timing experiments only)
+    else red_add_v4f(dst + i, v.x, v.y, v.z, v.w);
+  }
+  bar_sync(2, kEpiThreads);
 }
 
 __device__ __forceinline__ float act_grad_rt(float u, int act) {
@@ -103,7 +123,7 @@ __device__ __forceinline__ void conv_epilogue_prefetch(const ConvFwdParams& p, E
                                                        bool valid, size_t pix) {
   const int c = half * 32;
   const int co0 = n_tile * BLOCK_N + c;
-  if (p.res && valid && c < BLOCK_N) {
+  if (p.res && p.res_mode == 0 && valid && c < BLOCK_N) {
     const __nv_bfloat16* rp = p.res + pix * p.ldres + co0;
 #pragma unroll
     for (int g = 0; g < 4; ++g)
@@ -180,16 +200,13 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvFwdParams& p, EpiPr
 // also makes the 16-byte shared stores conflict-free) into one of two 16 KB staging buffers and one thread hands the
 // slab to the TMA engine.  One named barrier per slab: before it, the issuing thread has waited for the previous
 // slab's store to finish reading the other buffer.
-constexpr int kStageBytes = 128 * 128;
-constexpr int kEpiThreads = 256;
-
 template <int BLOCK_N>
 __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, EpiPrefetch& pf, const float* s_bias,
                                                        uint32_t t_acc, int q, int half, int n_tile, bool valid,
                                                        size_t pix, uint8_t* stage, int& stage_idx,
                                                        const CUtensorMap* tmY, int c1, int c2, int c3, bool issuer,
-                                                       const uint8_t* res_tile = nullptr, int img = 0,
-                                                       const float* s_ab = nullptr) {
+                                                       const uint8_t* res_tile = nullptr, int tile_w = 8,
+                                                       float* s_acc = nullptr) {
   static_assert(BLOCK_N % 64 == 0, "TMA-store epilogue works on 64-channel slabs");
   const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16);
   const int row = q * 32 + (threadIdx.x & 31);
@@ -216,7 +233,7 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
 #pragma unroll
       for (int g = 0; g < 4; ++g)
         rcur[g] = *reinterpret_cast<const uint4*>(res_tile + row * 128 + (((half * 4 + g) ^ swz) << 4));
-    } else if (has_res) {
+    } else if (has_res && p.res_mode == 0) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) rcur[g] = pf.r[g];
       if (valid && c + 64 < BLOCK_N) {
@@ -226,6 +243,14 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
           if (co0 + 64 + g * 8 < p.Cout) pf.r[g] = *reinterpret_cast<const uint4*>(rn + g * 8);
       }
     }
+    // Fused GroupNorm reductions run as a COLUMN pass over the staged slab after the slab barrier.  Epilogue warp w8
+    // owns the channel pairs 4*w8 .. 4*w8+3 of the slab; lane = (row lane rl, pair pp) reads rows rl, rl+8, ..: the 32
+    // lanes of a load hit 32 different banks (the 128B swizzle XORs the 16-byte chunk index w8 with row mod 8 = rl).
+    // The 8 row lanes are combined with 3 shuffle steps; lane (0, pp) then adds into the CTA's shared-memory sums —
+    // it is the only thread that ever touches that address, so no atomics (fp32 shared atomics are CAS loops).
+    const int w8 = (static_cast<int>(threadIdx.x) - 64) >> 5;
+    const int pp = threadIdx.x & 3, rl = (threadIdx.x & 31) >> 2;
+    const int colco = slab_co + 2 * (4 * w8 + pp);
     tmem_ld_wait();
     float f[32];
 #pragma unroll
@@ -263,54 +288,26 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
       o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
       o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
       *reinterpret_cast<uint4*>(buf + (((half * 4 + g) ^ swz) << 4)) = o;
-      if (p.stats || p.gn_sums) {  // keep the values that were actually stored (bf16-rounded)
-        const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 r = unpack_bf16x2(w4[k]);
-          f[g * 8 + 2 * k] = r.x;
-          f[g * 8 + 2 * k + 1] = r.y;
-        }
-      }
     }
-    if (p.stats) {
-      // statistics of the stored tile for the GroupNorm that reads y next: per-channel sum / sum of squares over the
-      // warp's 32 pixel rows, one 8-byte red per lane (lane l <-> channel co0 + l)
-      float sq[32];
+    // x words of the first XB rows, issued here (the accumulator registers are dead by now) so that the loads fly
+    // during the fence / slab barrier / store issue below.  XB = 16 rows at once where registers allow (BLOCK_N = 64,
+    // the kernels with the least time per tile), two batches of 8 otherwise.
+    constexpr int XB = BLOCK_N == 64 ? 16 : 8;
+    uint32_t xw[XB];
+    float4 ab4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_x = [&](int k0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float r = valid ? f[j] : 0.f;  // rows outside a ragged output contribute nothing
-        sq[j] = r * r;
-        f[j] = r;
+      for (int k = 0; k < XB; ++k) {
+        const int rr = rl + 8 * (k0 + k);
+        const int pw = c1 + rr % tile_w, ph = c2 + rr / tile_w;
+        xw[k] = (pw < p.Wo && ph < p.Ho)
+                    ? *reinterpret_cast<const uint32_t*>(p.res + ((static_cast<size_t>(c3) * p.Ho + ph) * p.Wo + pw) * p.ldres + colco)
+                    : 0u;
       }
-      const float S = warp_colsum32(f);
-      const float Q = warp_colsum32(sq);
-      const int co = co0 + (threadIdx.x & 31);
-      if (co < p.Cout) red_add_v2(p.stats + (static_cast<size_t>(img) * p.Cout + co) * 2, S, Q);
-    } else if (p.gn_sums) {  // (never together with stats: f is consumed by the column sums)
-      // GroupNorm-backward sums: du = dy * act'(a*x + b), A = sum du, B = sum du*x over the warp's 32 pixel rows
-      float dux[32];
-      const bool live = res_tile != nullptr || valid;  // x of rows outside a ragged output was never loaded
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint32_t w4[4] = {rcur[g].x, rcur[g].y, rcur[g].z, rcur[g].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 xv = unpack_bf16x2(w4[k]);
-          const int j = g * 8 + 2 * k;
-          const float4 ab = *reinterpret_cast<const float4*>(s_ab + 2 * (c + j));  // a_j, b_j, a_j+1, b_j+1
-          const float du0 = live ? f[j] * act_grad_rt(fmaf(xv.x, ab.x, ab.y), p.gn_act) : 0.f;
-          const float du1 = live ? f[j + 1] * act_grad_rt(fmaf(xv.y, ab.z, ab.w), p.gn_act) : 0.f;
-          f[j] = du0;
-          f[j + 1] = du1;
-          dux[j] = live ? du0 * xv.x : 0.f;
-          dux[j + 1] = live ? du1 * xv.y : 0.f;
-        }
-      }
-      const float A = warp_colsum32(f);
-      const float B = warp_colsum32(dux);
-      const int co = co0 + (threadIdx.x & 31);
-      if (co < p.Cout) red_add_v2(p.gn_sums + (static_cast<size_t>(img) * p.Cout + co) * 2, A, B);
+    };
+    if (p.gn_sums && colco < p.Cout) {
+      ab4 = *reinterpret_cast<const float4*>(p.gn_ab + (static_cast<size_t>(c3) * p.Cout + colco) * 2);
+      load_x(0);
     }
     fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA (async proxy)
     if (issuer) bulk_wait_read<0>();     // the previous slab's store has released the other buffer
@@ -318,6 +315,51 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
     if (issuer) {
       tma_store_4d(tmY, stage + stage_idx * kStageBytes, slab_co, c1, c2, c3);
       bulk_commit();
+    }
+    if ((p.stats || p.gn_sums) && colco < p.Cout) {
+      // (this buffer is rewritten two slabs from now, behind the next slab's barrier: every thread has left by then)
+      const uint8_t* slab = stage + stage_idx * kStageBytes;
+      float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int k0 = 0; k0 < 16; k0 += XB) {
+        if (k0 > 0 && p.gn_sums) load_x(k0);
+#pragma unroll
+        for (int k = 0; k < XB; ++k) {
+          const int rr = rl + 8 * (k0 + k);
+          const float2 yv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
+              slab + rr * 128 + (((w8 ^ rl) << 4) | (pp << 2))));
+          const bool live = (c1 + rr % tile_w < p.Wo) && (c2 + rr / tile_w < p.Ho);  // ragged output tiles
+          if (p.stats) {
+            // statistics of the STORED values for the GroupNorm that reads y next: sum, sum of squares
+            if (live) {
+              s0 += yv.x; t0 = fmaf(yv.x, yv.x, t0);
+              s1 += yv.y; t1 = fmaf(yv.y, yv.y, t1);
+            }
+          } else {
+            // GroupNorm-backward sums: y is dL/d(act output); du = y * act'(a*x + b); A = sum du, B = sum du * x
+            const float2 xv = unpack_bf16x2(xw[k]);
+            if (live) {
+              const float du0 = yv.x * act_grad_rt(fmaf(xv.x, ab4.x, ab4.y), p.gn_act);
+              const float du1 = yv.y * act_grad_rt(fmaf(xv.y, ab4.z, ab4.w), p.gn_act);
+              s0 += du0; t0 = fmaf(du0, xv.x, t0);
+              s1 += du1; t1 = fmaf(du1, xv.y, t1);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int off = 4; off <= 16; off <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+        t0 += __shfl_xor_sync(0xffffffffu, t0, off);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, off);
+      }
+      if (rl == 0) {  // CTA-local sums of the current image; conv_flush_sums ships them once per image
+        float4* acc = reinterpret_cast<float4*>(s_acc + 2 * colco);
+        float4 a = *acc;
+        a.x += s0; a.y += t0; a.z += s1; a.w += t1;
+        *acc = a;
+      }
     }
     stage_idx ^= 1;
   }
@@ -333,6 +375,8 @@ int launch_conv_halo(const jg_conv_desc* d, const jg_conv_epilogue* e, const voi
 inline const void* conv_apply_epilogue(ConvFwdParams& p, const jg_conv_desc* d, const jg_conv_epilogue* e,
                                        const void* residual) {
   p.stats = nullptr; p.gn_sums = nullptr; p.gn_ab = nullptr; p.gn_act = 0; p.res_mode = 0;
+  static const int dbg = getenv("JG_DBG_EPI") ? atoi(getenv("JG_DBG_EPI")) : 0;
+  p.dbg = dbg;
   if (!e) return residual;
   p.stats = e->stats;
   if (e->gn_sums) {
@@ -348,16 +392,6 @@ int launch_chan_stats(const void* x, int ldx, int N, int HW, int C, float* stats
 int launch_gn_bwd_sums(const void* x, int ldx, const void* dy, int lddy, int N, int HW, int C, const float* ab, int act,
                        float* AB, cudaStream_t stream);
 
-// The (a, b) coefficients of one tile's image and channel block, staged in shared memory for the gn_sums epilogue by
-// the 256 epilogue threads (double-buffered by the caller; named barrier 2).
-template <int BLOCK_N>
-__device__ __forceinline__ void conv_stage_gn_ab(const ConvFwdParams& p, float* dst, int img, int n_tile) {
-  const int e = threadIdx.x - 64;
-  const int c0 = n_tile * BLOCK_N;
-  for (int i = e; i < 2 * BLOCK_N; i += kEpiThreads)
-    dst[i] = (c0 + (i >> 1) < p.Cout) ? p.gn_ab[(static_cast<size_t>(img) * p.Cout + c0) * 2 + i] : 0.f;
-  bar_sync(2, kEpiThreads);
-}
 
 // wgrad with halo reuse (conv_halo.cu): zeroes ws, accumulates, writes OIHW; JG_ERR_UNSUPPORTED if not eligible.
 int launch_wgrad_halo(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* ws, float* dw_oihw,

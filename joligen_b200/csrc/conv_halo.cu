@@ -49,7 +49,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int b_tiles = B_RESIDENT ? p.RS * k_slabs : SB;
   uint8_t* stage = smB + static_cast<size_t>(b_tiles) * B_BYTES;  // 2 x 16 KB output staging (1024-byte aligned)
   uint8_t* res_stage = stage + (TMA_STORE ? 2 * kStageBytes : 0);  // 2 x 16 KB residual tiles (RES_TMA)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(res_stage + ((RES_TMA && p.res) ? 2 * kStageBytes : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(res_stage + ((RES_TMA && p.res && p.res_mode == 0) ? 2 * kStageBytes : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + SA;
   uint64_t* b_full = bars + 2 * SA;           // SB entries (entry 0 only when resident)
@@ -59,8 +59,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* rfull = tempty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rfull + 2);
   float* s_bias = reinterpret_cast<float*>(rfull + 4);
-  float* s_ab = s_bias + ((p.Cout + 64 + 31) / 32) * 32;  // 2 x [BLOCK_N][2] (gn_sums mode)
+  float* s_acc = s_bias + ((p.Cout + 64 + 31) / 32) * 32;  // [Cout][2] GroupNorm sums of the current image (fused modes)
   conv_stage_bias(p, s_bias);
+  if (p.stats || p.gn_sums)
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) s_acc[i] = 0.f;
+  const TileRange tr = conv_tile_range(p);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -69,7 +72,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (TMA_STORE) tma_prefetch_desc(&tmY);
-    if (RES_TMA && p.res) tma_prefetch_desc(&tmR);
+    if (RES_TMA && p.res && p.res_mode == 0) tma_prefetch_desc(&tmR);
     for (int i = 0; i < SA; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
@@ -106,7 +109,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int tap = 0; tap < p.RS; ++tap)
             tma_load_3d(smB + (kc * p.RS + tap) * B_BYTES, &tmB, &b_full[0], kc * 64, tap, 0);
       }
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tr.begin; tile < tr.end; tile += tr.step) {
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
         const int tw = m_tile % p.tiles_w;
@@ -151,7 +154,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
     }
     const uint32_t row_skip16 = static_cast<uint32_t>((hp.PW - p.S) * 128) >> 4;  // window origin step at a filter-row end
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = tr.begin; tile < tr.end; tile += tr.step) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -240,7 +243,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     int stage_idx = 0;
     uint32_t acc_phase = 0;
-    const bool res_tma = RES_TMA && p.res != nullptr;
+    const bool res_tma = RES_TMA && p.res != nullptr && p.res_mode == 0;
     // residual tile of this CTA's (i)th tile -> res_stage[i & 1]; issued two tiles ahead by the issuer thread
     auto load_res_tile = [&](int tile, int buf) {
       const int n_tile = tile % p.n_tiles;
@@ -252,13 +255,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tma_load_4d(res_stage + buf * kStageBytes, &tmR, &rfull[buf], n_tile * BLOCK_N, tw * kHaloTW, th * kHaloTH, tn);
     };
     if (res_tma && issuer) {
-      if (blockIdx.x < p.total_tiles) load_res_tile(blockIdx.x, 0);
-      if (blockIdx.x + gridDim.x < p.total_tiles) load_res_tile(blockIdx.x + gridDim.x, 1);
+      if (tr.begin < tr.end) load_res_tile(tr.begin, 0);
+      if (tr.begin + tr.step < tr.end) load_res_tile(tr.begin + tr.step, 1);
     }
     int rbuf = 0;
     uint32_t rphase = 0;
-    int ab_buf = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const bool fused = TMA_STORE && (p.stats || p.gn_sums);
+    int cur_img = -1;
+    for (int tile = tr.begin; tile < tr.end; tile += tr.step) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int tw = m_tile % p.tiles_w;
@@ -269,25 +273,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool valid = (pw < p.Wo) && (ph < p.Ho);
       const size_t pix = (static_cast<size_t>(tn) * p.Ho + ph) * p.Wo + pw;
       if (!res_tma) conv_epilogue_prefetch<BLOCK_N>(p, pf, half, n_tile, valid, pix);
-      const float* ab_tile = nullptr;
-      if constexpr (TMA_STORE) {
-        if (p.gn_sums) {
-          conv_stage_gn_ab<BLOCK_N>(p, s_ab + ab_buf * 2 * BLOCK_N, tn, n_tile);
-          ab_tile = s_ab + ab_buf * 2 * BLOCK_N;
-          ab_buf ^= 1;
-        }
+      if (fused && tn != cur_img) {  // the chunk of tiles moved on to the next image: ship the finished one's sums
+        if (cur_img >= 0) conv_flush_sums(p, s_acc, cur_img);
+        cur_img = tn;
       }
+
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if constexpr (TMA_STORE) {
         if (res_tma) mbar_wait(&rfull[rbuf], rphase);
         conv_epilogue_tile_tma<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile,
                                         valid, pix, stage, stage_idx, &tmY, tw * kHaloTW, th * kHaloTH, tn, issuer,
-                                        res_tma ? res_stage + rbuf * kStageBytes : nullptr, tn, ab_tile);
+                                        res_tma ? res_stage + rbuf * kStageBytes : nullptr, kHaloTW, s_acc);
         if (res_tma) {
           // the slab barrier inside the epilogue ordered every thread's reads of this residual buffer before here
-          if (issuer && tile + 2 * static_cast<int>(gridDim.x) < p.total_tiles)
-            load_res_tile(tile + 2 * gridDim.x, rbuf);
+          if (issuer && tile + 2 * tr.step < tr.end) load_res_tile(tile + 2 * tr.step, rbuf);
           if (++rbuf == 2) {
             rbuf = 0;
             rphase ^= 1;
@@ -304,6 +304,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         acc_phase ^= 1;
       }
     }
+    if (fused && cur_img >= 0) conv_flush_sums(p, s_acc, cur_img);
     if (TMA_STORE && issuer) bulk_wait_read<0>();  // the staging buffers live until the last store has read them
   }
 
@@ -319,8 +320,8 @@ template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
 static int halo_smem_bytes(const HaloParams& hp) {
   const int b_tiles = B_RESIDENT ? hp.c.RS * hp.c.kc_blocks : SB;
   return SA * hp.a_stage_bytes + b_tiles * BLOCK_N * 128 + (BLOCK_N >= 64 ? 2 * kStageBytes : 0) +
-         ((BLOCK_N == 64 && hp.c.res) ? 2 * kStageBytes : 0) + (2 * SA + 2 * SB + 8) * 8 +
-         (((hp.c.Cout + 64) * 4 + 127) / 128) * 128 + (hp.c.gn_sums ? 2 * 2 * BLOCK_N * 4 : 0) + 1024;
+         ((BLOCK_N == 64 && hp.c.res && hp.c.res_mode == 0) ? 2 * kStageBytes : 0) + (2 * SA + 2 * SB + 8) * 8 +
+         (((hp.c.Cout + 64) * 4 + 127) / 128) * 128 + ((hp.c.stats || hp.c.gn_sums) ? 2 * hp.c.Cout * 4 : 0) + 1024;
 }
 
 template <int BLOCK_N, int SA, int SB, bool B_RESIDENT, int KS>
@@ -368,7 +369,7 @@ int launch_conv_halo(const jg_conv_desc* d, const jg_conv_epilogue* e, const voi
   p.ldy = d->ldy; p.ldres = d->ldres; p.act = d->act; p.res_scale = d->res_scale;
   p.bias = bias;
   // fused GroupNorm work needs the TMA-store epilogue (Cout > 32); otherwise the caller runs the stand-alone reduction
-  const bool fuse = e != nullptr && block_n >= 64;
+  const bool fuse = e != nullptr && block_n >= 64 && d->Cout <= kMaxFusedCout;
   const void* residual = conv_apply_epilogue(p, d, fuse ? e : nullptr, residual_in);
   if (fused) *fused = fuse;
   p.res = static_cast<const __nv_bfloat16*>(residual);
@@ -407,7 +408,7 @@ int launch_conv_halo(const jg_conv_desc* d, const jg_conv_epilogue* e, const voi
     if (rc) return rc;
   }
   CUtensorMap tmR = tmA;  // residual tiles (64-channel kernels with a residual)
-  if (block_n == 64 && residual) {
+  if (block_n == 64 && residual && p.res_mode == 0) {
     uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
     uint64_t strides[3] = {(uint64_t)p.ldres * 2, (uint64_t)d->Wo * p.ldres * 2,
                            (uint64_t)d->Ho * d->Wo * p.ldres * 2};

@@ -43,7 +43,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* s_bias = reinterpret_cast<float*>(bars + 2 * STAGES + 6);
+  float* s_acc = s_bias + kMaxCout + 64;  // [Cout <= kMaxFusedCout][2] GroupNorm sums of the current image
   conv_stage_bias(p, s_bias);
+  if (p.stats || p.gn_sums)
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) s_acc[i] = 0.f;
+  const TileRange tr = conv_tile_range(p);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -78,7 +82,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tr.begin; tile < tr.end; tile += tr.step) {
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
         const int tw = m_tile % p.tiles_w;
@@ -114,7 +118,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = tr.begin; tile < tr.end; tile += tr.step) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -161,12 +165,18 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int acc = 0;
     int stage_idx = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const bool fused = TMA_STORE && (p.stats || p.gn_sums);
+    int cur_img = -1;
+    for (int tile = tr.begin; tile < tr.end; tile += tr.step) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int tw = m_tile % p.tiles_w;
       const int th = (m_tile / p.tiles_w) % p.tiles_h;
       const int tn = m_tile / (p.tiles_w * p.tiles_h);
+      if (fused && tn != cur_img) {  // (TN == 1 in the fused modes: tn is the image)
+        if (cur_img >= 0) conv_flush_sums(p, s_acc, cur_img);
+        cur_img = tn;
+      }
       const int pw = tw * p.TW + (row % p.TW);
       const int ph = th * p.TH + ((row / p.TW) % p.TH);
       const int pn = tn * p.TN + row / (p.TW * p.TH);
@@ -179,7 +189,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if constexpr (TMA_STORE)
         conv_epilogue_tile_tma<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile,
                                         valid, pix, stage_out, stage_idx, &tmY, tw * p.TW, th * p.TH, tn * p.TN,
-                                        issuer);
+                                        issuer, nullptr, p.TW, s_acc);  // (fused GroupNorm sums: TN == 1)
       else
         conv_epilogue_tile<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile,
                                     valid, pix);
@@ -191,6 +201,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         acc_phase ^= 1;
       }
     }
+    if (fused && cur_img >= 0) conv_flush_sums(p, s_acc, cur_img);
     if (TMA_STORE && issuer) bulk_wait_read<0>();  // the staging buffers live until the last store has read them
   }
 
@@ -419,7 +430,7 @@ template <int BLOCK_N, int STAGES>
 static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const ConvFwdParams& p,
                       cudaStream_t stream) {
   constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (BLOCK_N >= 64 ? 2 * kStageBytes : 0) +
-                       (2 * STAGES + 6) * 8 + kMaxCout * 4 + 256 + 1024;
+                       (2 * STAGES + 6) * 8 + kMaxCout * 4 + 256 + 2 * kMaxFusedCout * 4 + 1024;
   static_assert(smem <= 232448, "conv_fwd_kernel: shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
@@ -475,9 +486,33 @@ using namespace jg;
 
 extern "C" int jg_conv2d_fwd(const jg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                              const void* residual, void* y, jg_stream_t stream_) {
+  return jg_conv2d_fwd_ex(d, nullptr, x, w_packed, bias, residual, y, stream_);
+}
+
+// The fused-GroupNorm outputs that the launched kernel's epilogue did not produce, as stand-alone reductions over y.
+static int conv_epilogue_fallback(const jg_conv_desc* d, const jg_conv_epilogue* e, const void* y, cudaStream_t stream) {
+  int rc = JG_OK;
+  if (e->stats) rc = launch_chan_stats(y, d->ldy, d->N, d->Ho * d->Wo, d->Cout, e->stats, stream);
+  if (rc == JG_OK && e->gn_sums)
+    rc = launch_gn_bwd_sums(e->gn_x, e->ldgx, y, d->ldy, d->N, d->Ho * d->Wo, d->Cout, e->gn_ab, e->gn_act, e->gn_sums,
+                            stream);
+  return rc;
+}
+
+extern "C" int jg_conv2d_fwd_ex(const jg_conv_desc* d, const jg_conv_epilogue* e, const void* x, const void* w_packed,
+                                const float* bias, const void* residual_in, void* y, jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_desc(d);
   if (rc) return rc;
+  const void* residual = residual_in;
+  if (e && !e->stats && !e->gn_sums) e = nullptr;
+  if (e && e->gn_sums) {
+    JG_CHECK(residual == nullptr, JG_ERR_INVALID, "conv_fwd_ex: gn_sums cannot be combined with a residual");
+    JG_CHECK(e->gn_x && e->gn_ab && e->ldgx % 8 == 0 && e->ldgx >= d->Cout &&
+                 (reinterpret_cast<uintptr_t>(e->gn_x) & 15) == 0,
+             JG_ERR_INVALID, "conv_fwd_ex: gn_sums needs gn_x (16-byte aligned, ldgx >= Cout) and gn_ab");
+    JG_CHECK(d->act == JG_ACT_NONE, JG_ERR_INVALID, "conv_fwd_ex: gn_sums expects a linear epilogue (a dgrad)");
+  }
   JG_CHECK(x && w_packed && y, JG_ERR_INVALID, "conv_fwd: null pointer");
   JG_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
@@ -490,8 +525,12 @@ extern "C" int jg_conv2d_fwd(const jg_conv_desc* d, const void* x, const void* w
   // stride-1 spatial filters on 8x16-tileable outputs: halo-reuse kernel (conv_halo.cu)
   static const bool no_halo = getenv("JG_NO_HALO") != nullptr;
   if (!no_halo) {
-    rc = launch_conv_halo(d, x, w_packed, bias, residual, y, stream);
-    if (rc != JG_ERR_UNSUPPORTED) return rc;
+    bool fused = false;
+    rc = launch_conv_halo(d, e, x, w_packed, bias, residual, y, stream, &fused);
+    if (rc != JG_ERR_UNSUPPORTED) {
+      if (rc == JG_OK && e && !fused) rc = conv_epilogue_fallback(d, e, y, stream);
+      return rc;
+    }
   }
 
   ConvFwdParams p{};
@@ -507,6 +546,9 @@ extern "C" int jg_conv2d_fwd(const jg_conv_desc* d, const void* x, const void* w
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   p.ldy = d->ldy; p.ldres = d->ldres; p.act = d->act; p.res_scale = d->res_scale;
   p.bias = bias;
+  // fused GroupNorm work: TMA-store epilogue and one image per tile (per-(image, channel) sums)
+  const bool fuse = e != nullptr && block_n >= 64 && p.TN == 1 && d->Cout <= kMaxFusedCout;
+  residual = conv_apply_epilogue(p, d, fuse ? e : nullptr, residual);
   p.res = static_cast<const __nv_bfloat16*>(residual);
   p.y = static_cast<__nv_bfloat16*>(y);
 
@@ -540,11 +582,13 @@ extern "C" int jg_conv2d_fwd(const jg_conv_desc* d, const void* x, const void* w
     if (rc) return rc;
   }
   switch (block_n) {
-    case 256: return launch_fwd<256, 3>(tmA, tmB, tmY, p, stream);
-    case 128: return launch_fwd<128, 5>(tmA, tmB, tmY, p, stream);
-    case 64: return launch_fwd<64, 7>(tmA, tmB, tmY, p, stream);
-    default: return launch_fwd<32, 8>(tmA, tmB, tmY, p, stream);
+    case 256: rc = launch_fwd<256, 3>(tmA, tmB, tmY, p, stream); break;
+    case 128: rc = launch_fwd<128, 5>(tmA, tmB, tmY, p, stream); break;
+    case 64: rc = launch_fwd<64, 7>(tmA, tmB, tmY, p, stream); break;
+    default: rc = launch_fwd<32, 8>(tmA, tmB, tmY, p, stream); break;
   }
+  if (rc == JG_OK && e && !fuse) rc = conv_epilogue_fallback(d, e, y, stream);
+  return rc;
 }
 
 // Shared by jg_conv2d_wgrad (zero + accumulate + unpack into dw_oihw) and jg_conv2d_wgrad_acc (dw_oihw == nullptr:

@@ -84,6 +84,91 @@ __global__ void linear_bwd_dw_kernel(const float* __restrict__ x, const float* _
   if (db && i == 0) db[o] = accb;
 }
 
+// ---- all emb_layers Linears of a UNet in ONE launch ("the 28 tiny Linears -> one batched GEMM") -------
+// Every ResBlock owns Linear(emb_channels -> 2*Cout) applied to the SAME SiLU(emb) [B][I] (unet_generator_attn.py:
+// 201-207, 247-258).  Item i writes its own contiguous [B][O_i] block of Y at float offset B * off_i.
+// One tile = (item, 64 outputs); grid = total tiles; 256 threads = 64 outputs x 4 batch slices.
+struct LinearItem {  // mirror of jg_linear_item
+  const float* w;    // [O][I]
+  const float* b;    // [O] or null
+  int O, off;        // outputs; first output in the concatenation of all items
+};
+
+__device__ __forceinline__ int find_item(const int* __restrict__ tile_start, int n, int tile) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_start[mid] <= tile) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+constexpr int kLinMaxI = 128, kLinMaxB = 64;
+
+__global__ void __launch_bounds__(256)
+linear_batched_fwd_kernel(const float* __restrict__ x, const LinearItem* __restrict__ items,
+                          const int* __restrict__ tile_start, int n, float* __restrict__ Y, int B, int I, int act_in) {
+  __shared__ float sx[kLinMaxB * kLinMaxI];
+  for (int i = threadIdx.x; i < B * I; i += 256) sx[i] = act_in == JG_ACT_SILU ? silu_f(x[i]) : x[i];
+  __syncthreads();
+  const int it = find_item(tile_start, n, blockIdx.x);
+  const LinearItem item = items[it];
+  const int o = (blockIdx.x - tile_start[it]) * 64 + (threadIdx.x & 63);
+  if (o >= item.O) return;
+  const float* wr = item.w + (size_t)o * I;
+  const float bias = item.b ? item.b[o] : 0.f;
+  float* y = Y + (size_t)B * item.off;
+  for (int b = threadIdx.x >> 6; b < B; b += 4) {
+    float acc = bias;
+    for (int i = 0; i < I; ++i) acc = fmaf(sx[b * I + i], wr[i], acc);
+    y[(size_t)b * item.O + o] = acc;
+  }
+}
+
+// dW_i[o][k] = sum_b dY_i[b][o] act(x[b][k]);  db_i[o] = sum_b dY_i[b][o];
+// dx[b][k] += act'(x[b][k]) * sum_o dY_i[b][o] W_i[o][k]   (summed over ALL items: fp32 atomics into a zeroed dx)
+__global__ void __launch_bounds__(256)
+linear_batched_bwd_kernel(const float* __restrict__ x, const LinearItem* __restrict__ items,
+                          const int* __restrict__ tile_start, int n, const float* __restrict__ dY,
+                          float* __restrict__ dW, float* __restrict__ dB, float* __restrict__ dx, int B, int I,
+                          int act_in) {
+  __shared__ float sx[kLinMaxB * kLinMaxI];   // act(x)
+  __shared__ float sdy[kLinMaxB * 64];        // dY tile [B][64]
+  for (int i = threadIdx.x; i < B * I; i += 256) sx[i] = act_in == JG_ACT_SILU ? silu_f(x[i]) : x[i];
+  const int it = find_item(tile_start, n, blockIdx.x);
+  const LinearItem item = items[it];
+  const int o0 = (blockIdx.x - tile_start[it]) * 64;
+  const float* dy = dY + (size_t)B * item.off;
+  for (int i = threadIdx.x; i < B * 64; i += 256) {
+    const int b = i >> 6, oo = i & 63;
+    sdy[i] = (o0 + oo < item.O) ? dy[(size_t)b * item.O + o0 + oo] : 0.f;
+  }
+  __syncthreads();
+  // weight / bias gradients: thread -> (output oo, input slice)
+  for (int idx = threadIdx.x; idx < 64 * I; idx += 256) {
+    const int oo = idx / I, k = idx - oo * I;
+    if (o0 + oo >= item.O) continue;
+    float acc = 0.f, accb = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float d = sdy[b * 64 + oo];
+      acc = fmaf(d, sx[b * I + k], acc);
+      accb += d;
+    }
+    dW[(size_t)(item.off + o0 + oo) * I + k] = acc;
+    if (k == 0) dB[item.off + o0 + oo] = accb;
+  }
+  // input gradient: thread -> (b, k), reduce over the tile's 64 outputs
+  if (dx) {
+    for (int idx = threadIdx.x; idx < B * I; idx += 256) {
+      const int b = idx / I, k = idx - b * I;
+      float acc = 0.f;
+      for (int oo = 0; oo < 64 && o0 + oo < item.O; ++oo) acc = fmaf(sdy[b * 64 + oo], item.w[(size_t)(o0 + oo) * I + k], acc);
+      if (act_in == JG_ACT_SILU) acc *= silu_g(x[idx]);
+      atomicAdd(&dx[idx], acc);
+    }
+  }
+}
+
 // DiffusionGenerator.forward prologue (diffusion_generator.py:480-491):
 //   y_noisy = sqrt(g)*y0 + sqrt(1-g)*noise;  y_noisy = y_noisy*m + (1-m)*y0, m = clamp(mask,0,1);
 //   input = cat([y_cond, y_noisy], dim=1)  ->  NHWC bf16 with channel stride ld (zero padded).
@@ -280,6 +365,36 @@ extern "C" int jg_linear_fwd(const float* x, const float* w, const float* bias, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   JG_CHECK(x && w && y && B > 0 && I > 0 && O > 0, JG_ERR_INVALID, "linear_fwd: bad args");
   linear_fwd_kernel<<<(B * O + 127) / 128, 128, 0, stream>>>(x, w, bias, y, B, I, O, act_in, act_out);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
+extern "C" int jg_linear_batched_tiles(int O) { return (O + 63) / 64; }
+
+extern "C" int jg_linear_batched_fwd(const float* x, const jg_linear_item* items_dev, const int* tile_start_dev, int n,
+                                     int total_tiles, float* Y, int B, int I, int act_in, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  JG_CHECK(x && items_dev && tile_start_dev && Y && n > 0 && total_tiles > 0, JG_ERR_INVALID,
+           "linear_batched_fwd: bad args");
+  JG_CHECK(B > 0 && B <= kLinMaxB && I > 0 && I <= kLinMaxI, JG_ERR_INVALID,
+           "linear_batched_fwd: B=%d (<= %d), I=%d (<= %d)", B, kLinMaxB, I, kLinMaxI);
+  linear_batched_fwd_kernel<<<total_tiles, 256, 0, stream>>>(x, reinterpret_cast<const LinearItem*>(items_dev),
+                                                             tile_start_dev, n, Y, B, I, act_in);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
+extern "C" int jg_linear_batched_bwd(const float* x, const jg_linear_item* items_dev, const int* tile_start_dev, int n,
+                                     int total_tiles, const float* dY, float* dW, float* dB, float* dx, int B, int I,
+                                     int act_in, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  JG_CHECK(x && items_dev && tile_start_dev && dY && dW && dB && n > 0 && total_tiles > 0, JG_ERR_INVALID,
+           "linear_batched_bwd: bad args");
+  JG_CHECK(B > 0 && B <= kLinMaxB && I > 0 && I <= kLinMaxI, JG_ERR_INVALID,
+           "linear_batched_bwd: B=%d (<= %d), I=%d (<= %d)", B, kLinMaxB, I, kLinMaxI);
+  if (dx) JG_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * I, stream));
+  linear_batched_bwd_kernel<<<total_tiles, 256, 0, stream>>>(x, reinterpret_cast<const LinearItem*>(items_dev),
+                                                             tile_start_dev, n, dY, dW, dB, dx, B, I, act_in);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }

@@ -53,8 +53,12 @@ def pack_conv_weight(w_oihw, want_dgrad=True, out=None):
 
 
 def conv2d_fwd(x, w_packed, bias, cout, r, s, stride=1, pad=None, act=L.ACT_NONE, residual=None, res_scale=1.0,
-               out=None):
-    """x: NHWC bf16 (C multiple of 8). Returns NHWC bf16 [N,Ho,Wo,cout]; `out` may be a channel slice."""
+               out=None, stats=None, gn=None):
+    """x: NHWC bf16 (C multiple of 8). Returns NHWC bf16 [N,Ho,Wo,cout]; `out` may be a channel slice.
+    GroupNorm work fused into the epilogue (jg_conv_epilogue):
+      stats: fp32 [N, cout, 2] ZEROED buffer that receives the per-(image, channel) sum / sum of squares of the output;
+      gn = (x_gn, ab, act, sums): this call is the dgrad of the conv that follows act(GN(x_gn)): sums (fp32 [N, cout, 2],
+           zeroed) receives (sum du, sum du * x_gn) with du = out * act'(a * x_gn + b)."""
     n, h, w, _ = x.shape
     if pad is None:
         pad = (r - 1) // 2
@@ -63,9 +67,29 @@ def conv2d_fwd(x, w_packed, bias, cout, r, s, stride=1, pad=None, act=L.ACT_NONE
         out = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
     d = make_conv_desc(x, cout, r, s, stride, pad, ldy=_ld(out), act=act,
                        ldres=(_ld(residual) if residual is not None else 0), res_scale=res_scale)
-    L.call("jg_conv2d_fwd", ctypes.byref(d), L.ptr(x), L.ptr(w_packed), L.ptr(bias), L.ptr(residual), L.ptr(out),
-           L.stream())
+    if stats is None and gn is None:
+        L.call("jg_conv2d_fwd", ctypes.byref(d), L.ptr(x), L.ptr(w_packed), L.ptr(bias), L.ptr(residual), L.ptr(out),
+               L.stream())
+        return out
+    e = L.ConvEpilogue()
+    if stats is not None:
+        assert stats.is_contiguous() and stats.dtype == torch.float32 and stats.numel() == n * cout * 2
+        e.stats = stats.data_ptr()
+    if gn is not None:
+        x_gn, ab, gn_act, sums = gn
+        assert tuple(x_gn.shape) == (n, ho, wo, cout) and ab.numel() == n * cout * 2 and sums.numel() == n * cout * 2
+        e.gn_sums, e.gn_x, e.ldgx, e.gn_ab, e.gn_act = sums.data_ptr(), x_gn.data_ptr(), _ld(x_gn), ab.data_ptr(), gn_act
+    L.call("jg_conv2d_fwd_ex", ctypes.byref(d), ctypes.byref(e), L.ptr(x), L.ptr(w_packed), L.ptr(bias),
+           L.ptr(residual), L.ptr(out), L.stream())
     return out
+
+
+def chan_stats(x):
+    """fp32 [N, C, 2]: per-(image, channel) sum and sum of squares of an NHWC bf16 tensor (stand-alone pass)."""
+    n, h, w, c = x.shape
+    stats = torch.zeros((n, c, 2), dtype=torch.float32, device=x.device)
+    L.call("jg_chan_stats", L.ptr(x), _ld(x), n, h * w, c, L.ptr(stats), L.stream())
+    return stats
 
 
 def conv2d_cropped(x, w_packed, bias, cout, r, s, pad, out_hw, act=L.ACT_NONE):
@@ -188,35 +212,43 @@ def resample2x(x, mode):
 # ---------------------------------------------------------------------------------------------
 # GroupNorm (+FiLM)(+SiLU)
 # ---------------------------------------------------------------------------------------------
-def groupnorm_fwd(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5, out=None):
-    """x NHWC bf16.  Returns (y, stats[N,G,2], ab[N,C,2])."""
+def groupnorm_fwd(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5, out=None, chan_stats=None):
+    """x NHWC bf16.  Returns (y, stats[N,G,2], ab[N,C,2]).  chan_stats: fp32 [N,C,2] per-channel sums of x that its
+    producer already accumulated (conv2d_fwd(stats=...)): the statistics pass is skipped."""
     n, h, w, c = x.shape
     if out is None:
         out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
     stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x.device)
     ab = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
     ws = torch.empty((L.load().jg_groupnorm_fwd_ws_floats(n, c, groups),), dtype=torch.float32, device=x.device)
+    if chan_stats is not None:
+        assert chan_stats.is_contiguous() and chan_stats.numel() == n * c * 2 and chan_stats.dtype == torch.float32
     L.call("jg_groupnorm_fwd", L.ptr(x), _ld(x), L.ptr(out), _ld(out), n, h * w, c, groups, eps, L.ptr(gamma),
-           L.ptr(beta), L.ptr(film), act, L.ptr(stats), L.ptr(ab), L.ptr(ws), L.stream())
+           L.ptr(beta), L.ptr(film), act, L.ptr(stats), L.ptr(ab), L.ptr(ws), L.ptr(chan_stats), L.stream())
     return out, stats, ab
 
 
 def groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab, need_param_grads=True, need_film_grad=False,
-                  dx=None, addend=None, colsum=None, addend2=None):
+                  dx=None, addend=None, colsum=None, addend2=None, sums_pre=None, dfilm_out=None):
     """addend: optional NHWC bf16 tensor summed into dx in the same pass (gradient of another consumer of x).
-    colsum: optional fp32 [C] output = per-channel sum of dx (the bias gradient of the conv that produced x)."""
+    colsum: optional fp32 [C] output = per-channel sum of dx (the bias gradient of the conv that produced x).
+    sums_pre: fp32 [N,C,2] = (sum du, sum du*x) already accumulated by the dgrad that produced dy
+    (conv2d_fwd(gn=...)): the reduction pass over (x, dy) is skipped."""
     n, h, w, c = x.shape
     if dx is None:
         dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
     dgamma = torch.empty((c,), dtype=torch.float32, device=x.device) if need_param_grads else None
     dbeta = torch.empty((c,), dtype=torch.float32, device=x.device) if need_param_grads else None
-    dfilm = torch.empty((n, 2 * c), dtype=torch.float32, device=x.device) if need_film_grad else None
+    dfilm = None
+    if need_film_grad:
+        ok = dfilm_out is not None and dfilm_out.is_contiguous() and tuple(dfilm_out.shape) == (n, 2 * c)
+        dfilm = dfilm_out if ok else torch.empty((n, 2 * c), dtype=torch.float32, device=x.device)
     ws = torch.empty((L.load().jg_groupnorm_bwd_ws_floats(n, c, groups),), dtype=torch.float32, device=x.device)
     L.call("jg_groupnorm_bwd", L.ptr(x), _ld(x), L.ptr(dy), _ld(dy), L.ptr(dx), _ld(dx), L.ptr(addend),
            _ld(addend) if addend is not None else 0, L.ptr(addend2), _ld(addend2) if addend2 is not None else 0,
            n, h * w, c,
            groups, L.ptr(gamma), L.ptr(beta), L.ptr(film), act, L.ptr(stats), L.ptr(ab), L.ptr(dgamma), L.ptr(dbeta),
-           L.ptr(dfilm), L.ptr(colsum), L.ptr(ws), L.stream())
+           L.ptr(dfilm), L.ptr(colsum), L.ptr(ws), L.ptr(sums_pre), L.stream())
     return dx, dgamma, dbeta, dfilm
 
 
@@ -324,6 +356,48 @@ def linear_bwd(x, w, dy, act_in=L.ACT_NONE, need_dx=True):
     db = torch.empty((o,), dtype=torch.float32, device=x.device)
     L.call("jg_linear_bwd", L.ptr(x), L.ptr(w), L.ptr(dy), L.ptr(dx), 0, L.ptr(dw), L.ptr(db), bsz, i, o, act_in,
            L.stream())
+    return dx, dw, db
+
+
+class LinearBank:
+    """Device table for the batched Linear launches: n Linears with the same input width applied to the same input."""
+
+    def __init__(self, linears, device):
+        lib = L.load()
+        self.widths = [lin.weight.shape[0] for lin in linears]
+        self.in_features = linears[0].weight.shape[1]
+        items, starts, off, tiles = [], [], 0, 0
+        for lin in linears:
+            w = lin.weight
+            assert w.dtype == torch.float32 and w.is_contiguous() and w.shape[1] == self.in_features
+            items.append(L.LinearItem(w.data_ptr(), 0 if lin.bias is None else lin.bias.data_ptr(), w.shape[0], off))
+            starts.append(tiles)
+            tiles += lib.jg_linear_batched_tiles(w.shape[0])
+            off += w.shape[0]
+        self.offsets = [it.off for it in items]
+        self.total_out, self.total_tiles, self.n = off, tiles, len(items)
+        self.key = tuple((it.w, it.b) for it in items)
+        self.items = _device_table(items, device)
+        self.tile_start = torch.tensor(starts, dtype=torch.int32, device=device)
+
+
+def linear_batched_fwd(x, bank, act_in=L.ACT_NONE):
+    """-> Y flat fp32 [B * sum O]; item i is Y[B*off_i : B*(off_i+O_i)].view(B, O_i)."""
+    bsz, i = x.shape
+    y = torch.empty((bsz * bank.total_out,), dtype=torch.float32, device=x.device)
+    L.call("jg_linear_batched_fwd", L.ptr(x), L.ptr(bank.items), L.ptr(bank.tile_start), bank.n, bank.total_tiles,
+           L.ptr(y), bsz, i, act_in, L.stream())
+    return y
+
+
+def linear_batched_bwd(x, bank, dy, act_in=L.ACT_NONE, need_dx=True):
+    """dy: flat like the forward's Y.  -> (dx [B,I] or None, dW [sum O, I], dB [sum O])"""
+    bsz, i = x.shape
+    dw = torch.empty((bank.total_out, i), dtype=torch.float32, device=x.device)
+    db = torch.empty((bank.total_out,), dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x) if need_dx else None
+    L.call("jg_linear_batched_bwd", L.ptr(x), L.ptr(bank.items), L.ptr(bank.tile_start), bank.n, bank.total_tiles,
+           L.ptr(dy), L.ptr(dw), L.ptr(db), L.ptr(dx), bsz, i, act_in, L.stream())
     return dx, dw, db
 
 
@@ -518,3 +592,49 @@ def monce_bwd(q, k, lse, grad_loss, ws, groups, temperature, num_patches_opt, it
     L.call("jg_monce_bwd", L.ptr(q), L.ptr(k), L.ptr(lse), L.ptr(grad_loss), groups, rows // groups, d,
            float(temperature), int(num_patches_opt), int(iters), L.ptr(ws), L.ptr(dq), L.ptr(dk), L.stream())
     return dq, dk
+
+
+# ---- on-GPU input preparation and Haar wavelets (csrc/prep.cu) -------------------------
+def fill_mask_random(img, mask, noise, cls=-1):
+    """data/online_creation.fill_mask_with_random on the device: img, noise fp32 [N,C,H,W]; mask [N,1,H,W] int64/fp32."""
+    n, c, h, w = img.shape
+    img, noise = img.contiguous().float(), noise.contiguous().float()
+    out = torch.empty_like(img)
+    mf, mi = _mask_ptrs(mask.contiguous())
+    L.call("jg_fill_mask_random", L.ptr(img), mf, mi, L.ptr(noise), L.ptr(out), n, c, h * w, int(cls), L.stream())
+    return out
+
+
+def u8_to_f32_normalized(x_nhwc_u8, mean=0.5, std=0.5):
+    """ToTensor + Normalize: uint8 [N,H,W,C] -> fp32 [N,C,H,W]."""
+    n, h, w, c = x_nhwc_u8.shape
+    assert x_nhwc_u8.dtype == torch.uint8 and x_nhwc_u8.is_contiguous()
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x_nhwc_u8.device)
+    L.call("jg_u8_to_f32_normalized", L.ptr(x_nhwc_u8), L.ptr(out), n, c, h, w, float(mean), float(std), L.stream())
+    return out
+
+
+def mask_class_dropout(mask, drop_u, prob, fill):
+    """palette_model.py:565-584: samples with drop_u[n] < prob get the unconditioned class `fill` everywhere."""
+    mask = mask.contiguous()
+    n = mask.shape[0]
+    out = torch.empty_like(mask)
+    mf, mi = _mask_ptrs(mask)
+    of, oi = _mask_ptrs(out)
+    L.call("jg_mask_class_dropout", mf, mi, L.ptr(drop_u.contiguous().float()), float(prob), int(fill), of, oi, n,
+           mask.numel() // n, L.stream())
+    return out
+
+
+def haar(x, mode):
+    """mode 0: DWT fwd, 1: DWT bwd, 2: IWT fwd, 3: IWT bwd (freq_utils.HaarTransform / InverseHaarTransform)."""
+    x = x.contiguous().float()
+    n, c, hh, ww = x.shape
+    if mode in (0, 3):   # full resolution in, bands out
+        c_img, h, w = c, hh // 2, ww // 2
+        out = torch.empty((n, 4 * c, h, w), dtype=torch.float32, device=x.device)
+    else:                # bands in, full resolution out
+        c_img, h, w = c // 4, hh, ww
+        out = torch.empty((n, c_img, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
+    L.call("jg_haar", L.ptr(x), L.ptr(out), n, c_img, h, w, mode, L.stream())
+    return out

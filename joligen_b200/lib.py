@@ -32,6 +32,15 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class ConvEpilogue(ctypes.Structure):
+    """Mirror of jg_conv_epilogue (GroupNorm work fused into the convolution epilogue)."""
+    _fields_ = [("stats", c_p), ("gn_sums", c_p), ("gn_x", c_p), ("ldgx", c_int), ("gn_ab", c_p), ("gn_act", c_int)]
+
+
+class LinearItem(ctypes.Structure):  # jg_linear_item
+    _fields_ = [("w", c_p), ("b", c_p), ("O", c_int), ("off", c_int)]
+
+
 class PackItem(ctypes.Structure):  # jg_pack_item
     _fields_ = [("w", c_p), ("wf", c_p), ("wd", c_p), ("Cout", c_int), ("Cin", c_int), ("RS", c_int),
                 ("Cin8", c_int), ("Cout8", c_int), ("pad_", c_int)]
@@ -48,6 +57,23 @@ _SIGNATURES = {
     "jg_version": [],
     "jg_check_device": [],
     "jg_conv2d_fwd": [ctypes.POINTER(ConvDesc), c_p, c_p, c_p, c_p, c_p, c_p],
+    "jg_conv2d_fwd_ex": [ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvEpilogue), c_p, c_p, c_p, c_p, c_p, c_p],
+    "jg_chan_stats": [c_p, c_int, c_int, c_int, c_int, c_p, c_p],
+    "jg_fill_mask_random": [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],
+    "jg_u8_to_f32_normalized": [c_p, c_p, c_int, c_int, c_int, c_int, c_f, c_f, c_p],
+    "jg_mask_class_dropout": [c_p, c_p, c_p, c_f, c_i64, c_p, c_p, c_int, c_i64, c_p],
+    "jg_haar": [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_linear_batched_tiles": [c_int],
+    "jg_linear_batched_fwd": [c_p, c_p, c_p, c_int, c_int, c_p, c_int, c_int, c_int, c_p],
+    "jg_linear_batched_bwd": [c_p, c_p, c_p, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p],
+    "jg_comm_unique_id": [c_p],
+    "jg_comm_init": [c_p, c_int, c_int, ctypes.POINTER(c_p)],
+    "jg_comm_allreduce_async": [c_p, c_p, ctypes.c_size_t, c_int, c_p],
+    "jg_comm_broadcast": [c_p, c_p, ctypes.c_size_t, c_int, c_p],
+    "jg_comm_wait": [c_p, c_p],
+    "jg_comm_info": [c_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_ulonglong),
+                     ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(c_int)],
+    "jg_comm_destroy": [c_p],
     "jg_conv2d_wgrad": [ctypes.POINTER(ConvDesc), c_p, c_p, c_int, c_p, c_p, c_f, c_p],
     "jg_pack_conv_weight": [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],
     "jg_conv2d_wgrad_acc": [ctypes.POINTER(ConvDesc), c_p, c_p, c_int, c_p, ctypes.POINTER(c_int), c_p],
@@ -61,9 +87,9 @@ _SIGNATURES = {
     "jg_copy_channels": [c_p, c_int, c_p, c_int, c_i64, c_int, c_int, c_p],
     "jg_resample2x": [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
     "jg_groupnorm_fwd": [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_f, c_p, c_p, c_p, c_int, c_p, c_p,
-                         c_p, c_p],
+                         c_p, c_p, c_p],
     "jg_groupnorm_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p,
-                         c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+                         c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "jg_attn_fwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
     "jg_attn_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
     "jg_layernorm_fwd": [c_p, c_int, c_p, c_int, c_i64, c_int, c_f, c_p, c_p, c_p, c_int, c_int, c_p, c_p],

@@ -138,12 +138,13 @@ class WeightPackSet:
         self._mark()
 
 
-def _conv(x, conv, pack, residual=None, res_scale=1.0, out=None):
+def _conv(x, conv, pack, residual=None, res_scale=1.0, out=None, want_stats=False):
+    """want_stats: the output is read by a GroupNorm next (see ops.conv2d)."""
     w = conv.weight
     if w.dim() == 3:
         w = w.unsqueeze(-1)
     return ops.conv2d(x, w, conv.bias, pack.get(), stride=conv.stride[0], pad=conv.padding[0], residual=residual,
-                      res_scale=res_scale, grad_sink=conv.weight, out=out)
+                      res_scale=res_scale, grad_sink=conv.weight, out=out, want_stats=want_stats)
 
 
 class GroupNorm(nn.Module):
@@ -231,7 +232,7 @@ class ConvIn(nn.Conv2d):
         self._pack = ConvPack(self)
 
     def forward_nhwc(self, x):
-        return _conv(x, self, self._pack)
+        return _conv(x, self, self._pack, want_stats=True)
 
 
 class ResBlock(EmbedBlock):
@@ -275,6 +276,7 @@ class ResBlock(EmbedBlock):
         self._pack_in = ConvPack(self.in_layers[2])
         self._pack_out = ConvPack(self.out_layers[3])
         self._pack_skip = ConvPack(self.skip_connection) if isinstance(self.skip_connection, nn.Conv2d) else None
+        self._film_pre = None
 
     def forward_nhwc(self, x, emb, out=None, want_tap=False):
         tap2 = None
@@ -285,9 +287,11 @@ class ResBlock(EmbedBlock):
         if self.updown:
             h = self.h_upd.forward_nhwc(h)
             x = self.x_upd.forward_nhwc(x)
-        h = _conv(h, self.in_layers[2], self._pack_in)
+        h = _conv(h, self.in_layers[2], self._pack_in, want_stats=True)
         lin = self.emb_layers[1]
-        emb_out = ops.linear(emb, lin.weight, lin.bias, act_in=L.ACT_SILU)  # [N, 2C] = (scale | shift)
+        emb_out, self._film_pre = self._film_pre, None  # computed for all blocks at once by the UNet (EmbBank)
+        if emb_out is None:
+            emb_out = ops.linear(emb, lin.weight, lin.bias, act_in=L.ACT_SILU)  # [N, 2C] = (scale | shift)
         if emb_out.shape[0] != h.shape[0]:
             # video UNet: one embedding per clip, N = B*F frames (emb_out.repeat_interleave(f), ..._vid.py:260)
             emb_out = emb_out.repeat_interleave(h.shape[0] // emb_out.shape[0], dim=0)
@@ -299,13 +303,34 @@ class ResBlock(EmbedBlock):
         skipw = 1.0 / math.sqrt(2) if (self.efficient and self.apply_skipw) else 1.0
         if self._pack_skip is not None:
             x = _conv(x, self.skip_connection, self._pack_skip)
-        y = _conv(h, self.out_layers[3], self._pack_out, residual=x, res_scale=skipw, out=out)
+        # the block output is normalised next (the following block's in_layers / attention norm / the UNet's out head)
+        y = _conv(h, self.out_layers[3], self._pack_out, residual=x, res_scale=skipw, out=out, want_stats=True)
         return (y, tap2) if want_tap else y
 
     def forward(self, x, emb):
         """Drop-in NCHW fp32 signature of the reference block."""
         y = self.forward_nhwc(ops.to_nhwc(x), emb)
         return ops.to_nchw(y, self.out_channel)
+
+
+class EmbBank:
+    """emb_layers of every ResBlock of a UNet evaluated in ONE launch: each ResBlock finds its
+    (scale | shift) in `_film_pre` instead of running its own tiny Linear (and two tiny backward kernels)."""
+
+    def __init__(self, root):
+        self.blocks = [m for m in root.modules() if isinstance(m, ResBlock)]
+        self.bank = None
+
+    def distribute(self, emb):
+        if not self.blocks:
+            return
+        lins = [b.emb_layers[1] for b in self.blocks]
+        key = tuple((l.weight.data_ptr(), None if l.bias is None else l.bias.data_ptr()) for l in lins)
+        if self.bank is None or self.bank.key != key:  # (parameters are re-pointed when a trainer flattens them)
+            self.bank = K.LinearBank(lins, emb.device)
+        outs = ops.linear_bank(emb, self.bank, lins, act_in=L.ACT_SILU)
+        for blk, y in zip(self.blocks, outs):
+            blk._film_pre = y
 
 
 class _NoAffineInstanceNorm1d(nn.Module):
@@ -343,7 +368,7 @@ class AttentionBlock(nn.Module):
         xn, x = ops.group_norm_tap(x, None, None, c, film=None, act=L.ACT_NONE)  # per-(n, c) statistics over T
         qkv = _conv(xn, self.qkv, self._pack_qkv)
         a = ops.attention(qkv, self.num_heads, c // self.num_heads, self.attention_layout)
-        return _conv(a, self.proj_out, self._pack_proj, residual=x, res_scale=1.0, out=out)
+        return _conv(a, self.proj_out, self._pack_proj, residual=x, res_scale=1.0, out=out, want_stats=True)
 
     def forward(self, x):
         y = self.forward_nhwc(ops.to_nhwc(x))
@@ -416,6 +441,7 @@ class UNet(nn.Module):
                 self.output_blocks.append(EmbedSequential(*layers))
         self.out = _OutHead(normalization(ch, norm), nn.SiLU(), nn.Conv2d(input_ch, out_channel, 3, padding=1))
         self._pack_outconv = ConvPack(self.out[2])
+        self._emb_bank = None
         self.beta_schedule = {
             "train": {"schedule": "linear", "n_timestep": n_timestep_train, "linear_start": 1e-6,
                       "linear_end": 0.01},
@@ -428,6 +454,10 @@ class UNet(nn.Module):
         # Skip tensors: every encoder output h_k is consumed by the next block AND by the decoder's concat.  The
         # decoder reads a hand-through ("tap") of h_k made by the next block's first GroupNorm, so the two gradients
         # meet inside that GroupNorm's backward pass instead of in a separate (strided) add kernel.
+        if emb.shape[0] <= 64 and emb.shape[1] <= 128:
+            if getattr(self, "_emb_bank", None) is None:  # (subclasses build themselves without UNet.__init__)
+                self._emb_bank = EmbBank(self)
+            self._emb_bank.distribute(emb)
         hs = []
         h = x
         for module in self.input_blocks:

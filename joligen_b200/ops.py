@@ -18,6 +18,42 @@ def _needs(ctx, i):
     return ctx.needs_input_grad[i]
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# GroupNorm work that travels with tensors (python attributes on the tensor OBJECT, validated by its version counter):
+#   t._jg_stats  = (fp32 [N,C,2] per-(image, channel) sum / sum of squares of t, version)   set by the conv that wrote t
+#                  -> the GroupNorm reading t skips its statistics pass (jg_conv_epilogue.stats)
+#   y._jg_gn     = (x, ab, act, version)   set by the GroupNorm that produced y = act(a*x + b)
+#                  -> the conv reading y hands (x, ab, act) to its dgrad, which accumulates the GroupNorm-backward sums
+#   dy._jg_gnsums = (fp32 [N,C,2] (sum du, sum du*x), version)   set by that dgrad on its output
+#                  -> the GroupNorm backward receiving dy skips its reduction pass (jg_conv_epilogue.gn_sums)
+# A missing or stale stamp only means the stand-alone pass runs.  JG_FUSE_GN=0 turns the fusion off.
+# ---------------------------------------------------------------------------------------------------------------------
+import os as _os
+
+# JG_FUSE_GN: "1" (default) both reductions, "stats" / "sums" one of them, "0" none (diagnostics)
+_FUSE_MODE = _os.environ.get("JG_FUSE_GN", "1")
+FUSE_GN = [_FUSE_MODE != "0"]
+FUSE_STATS = [_FUSE_MODE in ("1", "stats")]
+FUSE_SUMS = [_FUSE_MODE in ("1", "sums")]
+# the dgrad epilogue takes the GroupNorm-backward sums only for GroupNorms with at least this many channels
+FUSE_SUMS_MIN_C = [int(_os.environ.get("JG_FUSE_SUMS_MIN_C", "0"))]
+
+
+def _stamp(t, name):
+    st = getattr(t, name, None)
+    if st is not None and st[-1] == t._version:
+        return st
+    return None
+
+
+def _carry_stats(src, *dst):
+    st = _stamp(src, "_jg_stats")
+    if st is not None:
+        for d in dst:
+            if d is not None:
+                d._jg_stats = (st[0], d._version)
+
+
 def _rows(t):
     """t as the kernels can address it: an NHWC tensor or a channel slice of one (unit channel stride, uniform row
     stride that is a multiple of 8 elements, 16-byte aligned start).  Anything else is copied."""
@@ -38,22 +74,34 @@ class Conv2dFn(torch.autograd.Function):
     round_up(Cout, 8) channels (padding channels are exactly zero)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, wf, wd, bias_p, stride, pad, res_scale, sink, out):
+    def forward(ctx, x, weight, bias, residual, wf, wd, bias_p, stride, pad, res_scale, sink, out, aux):
         cout, cin, r, s = weight.shape
         cout8 = (cout + 7) // 8 * 8
+        # aux (dict or None): {"want_stats": bool, "gn": (x_gn, ab, act) of the GroupNorm that produced x}; receives
+        # "stats" = the per-(image, channel) sums of y accumulated by the conv epilogue
+        stats = None
+        if aux is not None and aux.get("want_stats"):
+            stats = torch.zeros((x.shape[0], cout8, 2), dtype=torch.float32, device=x.device)
+            aux["stats"] = stats
         # out: optional destination (a channel slice of a wider NHWC buffer, e.g. the next block's concat input)
         y = K.conv2d_fwd(x, wf, bias_p, cout8, r, s, stride=stride, pad=pad, residual=residual, res_scale=res_scale,
-                         out=out)
+                         out=out, stats=stats)
         if out is not None:
             y = y.view(y.shape)  # a fresh tensor object: autograd must not see an input returned as an output
-        ctx.save_for_backward(x, wd)
+        gn = aux.get("gn") if aux is not None else None
+        if gn is not None and stride == 1:
+            ctx.save_for_backward(x, wd, gn[0], gn[1])
+            ctx.gn_act = gn[2]
+        else:
+            ctx.save_for_backward(x, wd)
+            ctx.gn_act = None
         ctx.geom = (cout, cin, r, s, stride, pad, res_scale, bias is not None, residual is not None)
         ctx.sink = sink  # (weight Parameter,) or None: accumulate dW straight into its .grad when possible
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, wd = ctx.saved_tensors
+        x, wd = ctx.saved_tensors[:2]
         cout, cin, r, s, stride, pad, res_scale, has_bias, has_res = ctx.geom
         cout8 = (cout + 7) // 8 * 8
         # a GroupNorm backward that produced this very tensor has already summed it over (n, pixel)
@@ -65,7 +113,16 @@ class Conv2dFn(torch.autograd.Function):
         if _needs(ctx, 0):
             if stride != 1:
                 raise RuntimeError("Conv2dFn: dgrad for stride %d is not implemented" % stride)
-            dx = K.conv2d_fwd(dy, wd, None, x.shape[-1], r, s, stride=1, pad=r - 1 - pad)
+            if ctx.gn_act is not None:
+                # x = act(a * x_gn + b): dx is that GroupNorm's incoming gradient; its reduction pass (sum du,
+                # sum du * x_gn per (image, channel)) runs in this dgrad's epilogue
+                x_gn, ab = ctx.saved_tensors[2:4]
+                sums = torch.zeros((x.shape[0], x.shape[-1], 2), dtype=torch.float32, device=x.device)
+                dx = K.conv2d_fwd(dy, wd, None, x.shape[-1], r, s, stride=1, pad=r - 1 - pad,
+                                  gn=(x_gn, ab, ctx.gn_act, sums))
+                dx._jg_gnsums = (sums, dx._version)
+            else:
+                dx = K.conv2d_fwd(dy, wd, None, x.shape[-1], r, s, stride=1, pad=r - 1 - pad)
         if _needs(ctx, 1):
             # Writing dW behind autograd's back (no AccumulateGrad: DDP reducer hooks, register_hook and
             # post-accumulate-grad hooks never fire for that parameter) is strictly opt-in: only a trainer that owns
@@ -81,6 +138,7 @@ class Conv2dFn(torch.autograd.Function):
                 # trainer-owned persistent split-K accumulator: raw accumulation now, ONE batched unpack into .grad
                 # for all convolutions at the end of the backward pass (WgradStage.flush)
                 stage.layout = K.conv2d_wgrad_acc(x, dy, cout8, r, s, stage.acc, stride=stride, pad=pad)
+                stage.notify()  # gradient final: the trainer may ship its bucket (overlapped all-reduce)
             else:
                 dw = K.conv2d_wgrad(x, dy, cout8, r, s, stride=stride, pad=pad)
                 if dw.shape[0] != cout or dw.shape[1] != cin:  # zero-padded channels (e.g. 6 -> 8, 3 -> 8)
@@ -91,33 +149,39 @@ class Conv2dFn(torch.autograd.Function):
                 db = db[:cout].contiguous()
         if has_res and _needs(ctx, 3):
             dres = dy if res_scale == 1.0 else (dy.float() * res_scale).to(torch.bfloat16)
-        return dx, dw, db, dres, None, None, None, None, None, None, None, None
+        return dx, dw, db, dres, None, None, None, None, None, None, None, None, None
 
 
 class GroupNormFn(torch.autograd.Function):
     """y = act(GN(x; gamma, beta) * (1 + scale) + shift), film = [N, 2C] fp32 (scale | shift) or None."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, film, groups, act, eps=1e-5):
-        y, stats, ab = K.groupnorm_fwd(x, gamma, beta, groups, film=film, act=act, eps=eps)
+    def forward(ctx, x, gamma, beta, film, groups, act, eps=1e-5, chan_stats=None, aux=None):
+        y, stats, ab = K.groupnorm_fwd(x, gamma, beta, groups, film=film, act=act, eps=eps, chan_stats=chan_stats)
         ctx.save_for_backward(x, gamma, beta, film, stats, ab)
         ctx.cfg = (groups, act)
+        ctx.film_slot = getattr(film, "_jg_grad_slot", None) if film is not None else None
+        if aux is not None:
+            aux["ab"] = ab
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, gamma, beta, film, stats, ab = ctx.saved_tensors
         groups, act = ctx.cfg
+        pre = _stamp(dy, "_jg_gnsums")
         dy = _rows(dy)
         need_p = gamma is not None and (_needs(ctx, 1) or _needs(ctx, 2))
         need_f = film is not None and _needs(ctx, 3)
         colsum = _colsum_buffer(x)
         dx, dgamma, dbeta, dfilm = K.groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab,
-                                                   need_param_grads=need_p, need_film_grad=need_f, colsum=colsum)
+                                                   need_param_grads=need_p, need_film_grad=need_f, colsum=colsum,
+                                                   sums_pre=None if pre is None else pre[0],
+                                                   dfilm_out=ctx.film_slot)
         if colsum is not None:
             # picked up by Conv2dFn.backward when x is a conv output (its bias gradient)
             dx._jg_colsum = (colsum, dx._version)
-        return dx, dgamma, dbeta, dfilm, None, None, None
+        return dx, dgamma, dbeta, dfilm, None, None, None, None, None
 
 
 class GroupNormTapFn(torch.autograd.Function):
@@ -127,11 +191,14 @@ class GroupNormTapFn(torch.autograd.Function):
     pass (dx = GN'(dy) + d_tap + d_tap2) instead of separate add kernels."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, film, groups, act, eps=1e-5):
-        y, stats, ab = K.groupnorm_fwd(x, gamma, beta, groups, film=film, act=act, eps=eps)
+    def forward(ctx, x, gamma, beta, film, groups, act, eps=1e-5, chan_stats=None, aux=None):
+        y, stats, ab = K.groupnorm_fwd(x, gamma, beta, groups, film=film, act=act, eps=eps, chan_stats=chan_stats)
         ctx.save_for_backward(x, gamma, beta, film, stats, ab)
         ctx.cfg = (groups, act)
+        ctx.film_slot = getattr(film, "_jg_grad_slot", None) if film is not None else None
         ctx.set_materialize_grads(False)  # an unused tap must arrive as None, not as a zero-filled tensor
+        if aux is not None:
+            aux["ab"] = ab
         return y, x.detach(), x.detach()
 
     @staticmethod
@@ -143,7 +210,8 @@ class GroupNormTapFn(torch.autograd.Function):
         if dy is None:
             if dtap2 is not None:
                 dtap = dtap + dtap2
-            return dtap, None, None, None, None, None, None
+            return dtap, None, None, None, None, None, None, None, None
+        pre = _stamp(dy, "_jg_gnsums")
         dy = _rows(dy)
         need_p = gamma is not None and (_needs(ctx, 1) or _needs(ctx, 2))
         need_f = film is not None and _needs(ctx, 3)
@@ -152,10 +220,11 @@ class GroupNormTapFn(torch.autograd.Function):
                                                    need_param_grads=need_p, need_film_grad=need_f,
                                                    addend=None if dtap is None else _rows(dtap),
                                                    addend2=None if dtap2 is None else _rows(dtap2),
-                                                   colsum=colsum)
+                                                   colsum=colsum, sums_pre=None if pre is None else pre[0],
+                                                   dfilm_out=ctx.film_slot)
         if colsum is not None:
             dx._jg_colsum = (colsum, dx._version)
-        return dx, dgamma, dbeta, dfilm, None, None, None
+        return dx, dgamma, dbeta, dfilm, None, None, None, None, None
 
 
 class AttentionFn(torch.autograd.Function):
@@ -285,6 +354,54 @@ class LinearFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class LinearBankFn(torch.autograd.Function):
+    """All emb_layers Linears of a UNet on the same SiLU(emb) in ONE launch each way (kernels.LinearBank).  Returns one
+    [B, O_i] tensor per Linear (views of one buffer).  Every output carries `_jg_grad_slot`: the matching view of the
+    backward's dY buffer — a GroupNorm whose FiLM input is that output writes its d(film) straight into the slot, so
+    the backward needs no gather."""
+
+    @staticmethod
+    def forward(ctx, x, bank, act_in, holder, *params):
+        x = x.contiguous().float()
+        y = K.linear_batched_fwd(x, bank, act_in)
+        bsz = x.shape[0]
+        ctx.save_for_backward(x)
+        ctx.bank, ctx.act_in = bank, act_in
+        ctx.dy = torch.empty_like(y)
+        ctx.set_materialize_grads(False)
+        holder["slots"] = [ctx.dy[bsz * off:bsz * (off + o)].view(bsz, o) for off, o in zip(bank.offsets, bank.widths)]
+        return tuple(y[bsz * off:bsz * (off + o)].view(bsz, o) for off, o in zip(bank.offsets, bank.widths))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        (x,) = ctx.saved_tensors
+        bank, bsz = ctx.bank, x.shape[0]
+        for g, off, o in zip(grads, bank.offsets, bank.widths):
+            slot = ctx.dy[bsz * off:bsz * (off + o)].view(bsz, o)
+            if g is None:
+                slot.zero_()
+            elif g.data_ptr() != slot.data_ptr():
+                slot.copy_(g)
+        dx, dw, db = K.linear_batched_bwd(x, bank, ctx.dy, ctx.act_in, need_dx=_needs(ctx, 0))
+        out = [dx, None, None, None]
+        for off, o in zip(bank.offsets, bank.widths):
+            out.append(dw[off:off + o])
+            out.append(db[off:off + o])
+        return tuple(out)
+
+
+def linear_bank(x, bank, linears, act_in=L.ACT_NONE):
+    """[lin(act_in(x)) for lin in linears] in one launch; see LinearBankFn."""
+    holder = {}
+    params = []
+    for lin in linears:
+        params += [lin.weight, lin.bias]
+    outs = LinearBankFn.apply(x, bank, act_in, holder, *params)
+    for y, slot in zip(outs, holder["slots"]):
+        y._jg_grad_slot = slot
+    return outs
+
+
 class Resample2xFn(torch.autograd.Function):
     """mode 0: nearest 2x upsample; mode 1: 2x2 average pool."""
 
@@ -316,6 +433,13 @@ class CatChannelsFn(torch.autograd.Function):
         # channel-slice views: every backward kernel addresses its incoming gradient with a row stride
         ca, cb = ctx.split
         return _slice_with_stamp(d, 0, ca), _slice_with_stamp(d, ca, ca + cb)
+
+
+def _cat_stats(out, a, b):
+    """per-channel statistics of a channel concatenation = the concatenation of the parts' statistics"""
+    sa, sb = _stamp(a, "_jg_stats"), _stamp(b, "_jg_stats")
+    if sa is not None and sb is not None:
+        out._jg_stats = (torch.cat([sa[0], sb[0]], dim=1), out._version)
 
 
 def _slice_with_stamp(d, c0, c1):
@@ -390,31 +514,57 @@ class PaletteLossFn(torch.autograd.Function):
         return K.palette_loss_bwd(noise, noise_hat, mask, w_b, g, lambda_g, l1), None, None, None, None, None
 
 
-def conv2d(x, weight, bias, packed, stride=1, pad=None, residual=None, res_scale=1.0, grad_sink=None, out=None):
+def conv2d(x, weight, bias, packed, stride=1, pad=None, residual=None, res_scale=1.0, grad_sink=None, out=None,
+           want_stats=False):
     """packed = (wf, wd, bias_padded) from nets.ConvPack.get(); grad_sink = the weight nn.Parameter whose
     (pre-existing, fp32, contiguous) .grad the weight gradient is accumulated into directly; out = optional
-    destination view (a channel slice of a wider NHWC buffer)."""
+    destination view (a channel slice of a wider NHWC buffer); want_stats: the output feeds a GroupNorm — accumulate
+    its per-(image, channel) statistics in the epilogue and attach them to the returned tensor."""
     r = weight.shape[2]
     if pad is None:
         pad = (r - 1) // 2
     wf, wd, bias_p = packed
-    return Conv2dFn.apply(x, weight, bias, residual, wf, wd, bias_p, stride, pad, res_scale,
-                          None if grad_sink is None else (grad_sink,), out)
+    aux = None
+    if FUSE_GN[0]:
+        # the GroupNorm that produced x rides along for the dgrad; a 3x3 conv feeding a GroupNorm emits its statistics
+        gn = _stamp(x, "_jg_gn") if (FUSE_SUMS[0] and stride == 1 and x.requires_grad
+                                     and x.shape[-1] >= FUSE_SUMS_MIN_C[0]) else None
+        want_stats = bool(want_stats) and FUSE_STATS[0]
+        if gn is not None or want_stats:
+            aux = {"want_stats": want_stats, "gn": None if gn is None else gn[:3]}
+    y = Conv2dFn.apply(x, weight, bias, residual, wf, wd, bias_p, stride, pad, res_scale,
+                       None if grad_sink is None else (grad_sink,), out, aux)
+    if aux is not None and "stats" in aux:
+        y._jg_stats = (aux["stats"], y._version)
+    return y
+
+
+def _gn_apply(fn, x, gamma, beta, film, groups, act, eps):
+    st = _stamp(x, "_jg_stats") if FUSE_GN[0] else None
+    aux = {} if FUSE_GN[0] else None
+    out = fn.apply(x, gamma, beta, film, groups, act, eps, None if st is None else st[0], aux)
+    y = out[0] if isinstance(out, tuple) else out
+    if aux is not None and "ab" in aux:
+        y._jg_gn = (x.detach(), aux["ab"], act, y._version)
+    return out
 
 
 def group_norm(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5):
-    return GroupNormFn.apply(x, gamma, beta, film, groups, act, eps)
+    return _gn_apply(GroupNormFn, x, gamma, beta, film, groups, act, eps)
 
 
 def group_norm_tap(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5):
     """-> (y, x_tap): use x_tap for every other consumer of x (see GroupNormTapFn)."""
-    y, tap, _ = GroupNormTapFn.apply(x, gamma, beta, film, groups, act, eps)
+    y, tap, _ = _gn_apply(GroupNormTapFn, x, gamma, beta, film, groups, act, eps)
+    _carry_stats(x, tap)
     return y, tap
 
 
 def group_norm_tap2(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5):
     """-> (y, x_tap, x_tap2): two independent hand-throughs of x (block skip path + decoder concat)."""
-    return GroupNormTapFn.apply(x, gamma, beta, film, groups, act, eps)
+    y, tap, tap2 = _gn_apply(GroupNormTapFn, x, gamma, beta, film, groups, act, eps)
+    _carry_stats(x, tap, tap2)
+    return y, tap, tap2
 
 
 def attention(qkv, heads, ch, layout=0, out=None):
@@ -456,7 +606,9 @@ def avgpool2x(x):
 
 
 def cat_channels(a, b):
-    return CatChannelsFn.apply(a, b)
+    out = CatChannelsFn.apply(a, b)
+    _cat_stats(out, a, b)
+    return out
 
 
 class JoinSlicesFn(torch.autograd.Function):
@@ -484,7 +636,9 @@ def join_slices(buf, *parts):
 
 def cat_into(buf, a, b):
     """a = buf[..., :Ca] already in place; copy b behind it and return the full buffer."""
-    return CatIntoFn.apply(a, b, buf)
+    out = CatIntoFn.apply(a, b, buf)
+    _cat_stats(out, a, b)
+    return out
 
 
 def to_nhwc(x):
@@ -723,3 +877,25 @@ def patch_nce(q, k, groups, temperature):
 
 def monce(q, k, groups, temperature, num_patches_opt):
     return MonceFn.apply(q, k, groups, temperature, num_patches_opt)
+
+
+# ---- Haar wavelets (freq_utils.HaarTransform / InverseHaarTransform) -------------------------------------------------
+class HaarFn(torch.autograd.Function):
+    """inverse=False: x [N,C,H,W] -> [N,4C,H/2,W/2] = cat(ll, lh, hl, hh); inverse=True: the synthesis transform."""
+
+    @staticmethod
+    def forward(ctx, x, inverse):
+        ctx.inverse = inverse
+        return K.haar(x, 2 if inverse else 0)
+
+    @staticmethod
+    def backward(ctx, d):
+        return K.haar(d, 3 if ctx.inverse else 1), None
+
+
+def haar_dwt(x):
+    return HaarFn.apply(x, False)
+
+
+def haar_iwt(x):
+    return HaarFn.apply(x, True)

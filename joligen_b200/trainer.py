@@ -54,14 +54,21 @@ class FlatParams:
 
 
 class _WgradSlot:
-    __slots__ = ("acc", "layout", "param", "dims", "owner")
+    __slots__ = ("acc", "layout", "param", "dims", "owner", "index")
 
     def __init__(self, acc, param, dims, owner):
         self.acc, self.layout, self.param, self.dims, self.owner = acc, None, param, dims, owner
+        self.index = None  # position of the parameter in the trainer's flat buffers (set by the trainer)
 
     @property
     def enabled(self):  # only between WgradStage.begin() and flush(): plain autograd use of the model stays immediate
         return self.owner.active
+
+    def notify(self):
+        """called by Conv2dFn.backward right after this slot's wgrad was launched: the gradient is final"""
+        cb = self.owner.on_ready
+        if cb is not None and self.index is not None:
+            cb(self.index)
 
 
 class WgradStage:
@@ -85,31 +92,40 @@ class WgradStage:
             slot = _WgradSlot(self.buf[off:off + w.numel()], w, dims, self)
             w._jg_wstage = slot
             self.slots.append(slot)
-        self._table = None
-        self._table_key = None
+        self._tables = {}  # subset key -> (table key, WeightTable)
         self.active = False
+        self.on_ready = None  # fn(flat parameter index): the trainer's bucket bookkeeping (overlapped all-reduce)
 
     def begin(self):
         self.active = True
 
-    def flush(self):
+    def end(self):
         self.active = False
-        active = [sl for sl in self.slots if sl.layout is not None and sl.param.grad is not None]
+
+    def flush(self, slots=None, tag="all"):
+        """Permute-add the accumulators of `slots` (default: all) into their parameters' .grad and zero them: ONE
+        launch.  `tag` names the subset for the cached device table (one per gradient bucket)."""
+        if slots is None:
+            self.active = False
+            slots = self.slots
+        active = [sl for sl in slots if sl.layout is not None and sl.param.grad is not None]
         if not active:
             return
         key = tuple((id(sl), sl.layout, sl.param.grad.data_ptr()) for sl in active)
-        if key != self._table_key:
+        cached = self._tables.get(tag)
+        if cached is None or cached[0] != key:
             items = [L.UnpackItem(sl.acc.data_ptr(), sl.param.grad.data_ptr(), sl.dims[0], sl.dims[1], sl.dims[2],
                                   sl.layout) for sl in active]
-            self._table = K.WeightTable(items, [sl.dims for sl in active], self.buf.device)
-            self._table_key = key
-        K.wgrad_unpack_batched(self._table)
+            cached = (key, K.WeightTable(items, [sl.dims for sl in active], self.buf.device))
+            self._tables[tag] = cached
+        K.wgrad_unpack_batched(cached[1])
 
 
 class PaletteTrainer:
     def __init__(self, netG_A, lr=2e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, optim="adamw",
                  ema=True, ema_beta=0.999, iter_size=1, lambda_G=1.0, use_minsnr=False, loss="MSE",
-                 device=None, process_group=None, cuda_graph=False, graph_warmup=3):
+                 device=None, process_group=None, cuda_graph=False, graph_warmup=3, overlap_comm=True,
+                 comm_buckets=8):
         if not torch.cuda.is_available():
             raise RuntimeError("joligen_b200.PaletteTrainer needs a CUDA device (there is no CPU path)")
         self.device = torch.device(device if device is not None else "cuda")
@@ -138,6 +154,24 @@ class PaletteTrainer:
         self.ref_A = None
         self.pg = process_group
         self.world = dp.world_size(process_group)
+        # gradient exchange: the library's own NCCL communicator; buckets of the flat gradient leave as soon as the
+        # backward pass has produced them (DDP's overlap, base_model.py:725-737)
+        self.comm = dp.Comm(process_group, self.device)
+        self.overlap = bool(overlap_comm) and self.world > 1
+        self._index = {id(p): i for i, p in enumerate(self.flat.params)}
+        for sl in self.wstage.slots:
+            sl.index = self._index[id(sl.param)]
+        self._sizes = [(p.numel() + 63) // 64 * 64 for p in self.flat.params]
+        self.buckets = dp.GradBuckets(self.flat.offsets, self._sizes, self.flat.total, self._reduce_bucket,
+                                      n_buckets=comm_buckets)
+        self._bucket_slots = [[sl for sl in self.wstage.slots if self.buckets.bucket_of[sl.index] == b]
+                              for b in range(len(self.buckets.buckets))]
+        self._bucket_loose = [[(p, v) for p, v in self._loose if self.buckets.bucket_of[self._index[id(p)]] == b]
+                              for b in range(len(self.buckets.buckets))]
+        if self.overlap:
+            self.wstage.on_ready = self.buckets.ready
+            for p, _ in self._loose:
+                p.register_post_accumulate_grad_hook(lambda q, i=self._index[id(p)]: self.buckets.ready(i))
         self.niter = 0
         self.step = 0
         self.loss_G_tot = None
@@ -184,8 +218,19 @@ class PaletteTrainer:
         self.cond_image = self.y_t
 
     def broadcast_parameters(self):
-        dp.broadcast_(self.flat.data, self.pg)
+        self.comm.broadcast(self.flat.data, root=0)
         self.packset.refresh()
+
+    def comm_stats(self):
+        st = self.comm.stats()
+        if st is None:
+            return None
+        st.update(buckets=len(self.buckets.buckets), overlapped=self.overlap,
+                  bucket_mb=[round(4e-6 * (hi - lo), 1) for lo, hi, _ in self.buckets.buckets],
+                  payload_mb_per_step=round(4e-6 * self.flat.total, 1), dtype="f32",
+                  what="library-owned NCCL communicator (jg_comm_*), one all-reduce per gradient bucket on a "
+                       "communication stream forked from the backward pass (captured inside the step's CUDA graph)")
+        return st
 
     # -- step -----------------------------------------------------------------------------------
     def compute_palette_loss(self, noise=None, t=None, u=None):
@@ -194,20 +239,46 @@ class PaletteTrainer:
                                                    t=t, u=u, ref=self.ref_A)
         return self.loss_G_tot
 
-    def _forward_backward(self, noise=None, t=None, u=None):
+    @staticmethod
+    def _fold(pairs):
+        """one multi-tensor add of the gradients autograd returned as tensors into their flat-buffer slices"""
+        pairs = [(v, p.grad) for p, v in pairs if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+        if pairs:
+            torch._foreach_add_([v for v, _ in pairs], [g.reshape(v.shape) for v, g in pairs])
+
+    def _reduce_bucket(self, b):
+        """Bucket b of the flat gradient is final on this rank: unpack its convolution accumulators, fold its small
+        gradients, and start its all-reduce on the communication stream (the backward pass keeps running)."""
+        self.wstage.flush(self._bucket_slots[b], tag=b)
+        self._fold(self._bucket_loose[b])
+        lo, hi, _ = self.buckets.buckets[b]
+        self.comm.allreduce_async(self.flat.grad[lo:hi])
+
+    def _forward_backward(self, noise=None, t=None, u=None, reduce=True):
+        """Forward + loss + backward (+ the gradient exchange across ranks unless reduce=False: an accumulation
+        micro-step, base_model.py:1313-1315 no_sync)."""
         self.flat.rebind_grads()
         loss = self.compute_palette_loss(noise=noise, t=t, u=u)
         # Parameters whose gradient arrives as a tensor (norm gains, biases, linears, padded convs: ~250 of them)
         # start the backward WITHOUT a .grad: autograd then just keeps the incoming tensor instead of launching one
-        # tiny add kernel per parameter, and a single multi-tensor add folds them into the flat gradient buffer.
+        # tiny add kernel per parameter, and a multi-tensor add folds them into the flat gradient buffer.
         for p, _ in self._loose:
             p.grad = None
+        overlap = self.overlap and reduce
         self.wstage.begin()
+        if overlap:
+            self.buckets.begin()
         (loss / self.iter_size).backward()
-        self.wstage.flush()
-        pairs = [(v, p.grad) for p, v in self._loose if p.grad is not None]
-        if pairs:
-            torch._foreach_add_([v for v, _ in pairs], [g.reshape(v.shape) for v, g in pairs])
+        self.wstage.end()
+        if overlap:
+            self.buckets.finish()  # whatever did not complete during the backward pass, in launch order
+            self.comm.wait()
+        else:
+            self.wstage.flush()
+            self._fold(self._loose)
+            if reduce and self.world > 1:
+                self.comm.allreduce_async(self.flat.grad)
+                self.comm.wait()
         for p, v in self._loose:
             p.grad = v
         # hand out a graph-free scalar: a retained autograd graph would keep this iteration's
@@ -218,7 +289,6 @@ class PaletteTrainer:
     def eager_step(self):
         """One full step launched kernel by kernel (no graph replay), on the current inputs: profiling entry point."""
         loss = self._forward_backward()
-        dp.allreduce_sum_(self.flat.grad, self.pg)
         self._optimizer_step()
         return loss
 
@@ -227,7 +297,6 @@ class PaletteTrainer:
         SUMMED over the ranks (divide by the world size for DDP's mean) and leaves the gradient buffer zeroed.
         Diagnostic / test entry point (tests/test_gpu_multi.py)."""
         self._forward_backward(noise=noise, t=t, u=u)
-        dp.allreduce_sum_(self.flat.grad, self.pg)
         g = self.flat.grad.clone()
         self.flat.grad.zero_()
         return g
@@ -271,8 +340,7 @@ class PaletteTrainer:
             if self._graph_fb is None and self._eager_steps >= self.graph_warmup:
                 self._capture()
             if self._graph_fb is not None:
-                self._graph_fb.replay()
-                dp.allreduce_sum_(self.flat.grad, self.pg)
+                self._graph_fb.replay()  # forward + backward + the bucketed all-reduce (a forked branch of the graph)
                 self._graph_opt.replay()
                 self.step += 1
                 from . import lib as L
@@ -281,9 +349,9 @@ class PaletteTrainer:
                 return self._static_loss
         from . import lib as L
         n0 = L.launch_count[0]
-        loss = self._forward_backward(noise=noise, t=t, u=u)
-        if self.niter % self.iter_size == 0:
-            dp.allreduce_sum_(self.flat.grad, self.pg)
+        last = self.niter % self.iter_size == 0
+        loss = self._forward_backward(noise=noise, t=t, u=u, reduce=last)
+        if last:
             self._optimizer_step()
         self._eager_steps += 1
         self.launches_per_step = L.launch_count[0] - n0

@@ -108,6 +108,27 @@ def test_conv_production_shape(K, case):
     dw = K.conv2d_wgrad(x_d, dy_d, cout8, k, k, pad=pad)[:cout, :cin]
     assert rel(dw, wr.grad) < 1e-3
     assert rel(K.bias_grad(dy_d)[:cout], br.grad) < 1e-3
+    # GroupNorm work fused into the epilogues (jg_conv_epilogue): the statistics of the stored output ...
+    stats = torch.zeros(n, cout8, 2, device="cuda")
+    y3 = K.conv2d_fwd(x_d, wf, bias_p, cout8, k, k, pad=pad, residual=resbuf[..., 8:8 + cout8],
+                      res_scale=1.0 / math.sqrt(2), stats=stats)
+    assert torch.equal(y3, y2)  # the fused reduction does not disturb the output
+    yf = y3.float()
+    want = torch.stack([yf.sum(dim=(1, 2)), (yf * yf).sum(dim=(1, 2))], dim=-1)
+    assert rel(stats, want) < 1e-4
+    assert rel(K.chan_stats(y3), want) < 1e-4  # the stand-alone pass computes the same thing
+    # ... and the GroupNorm-backward sums in the dgrad epilogue: du = dx * silu'(a * x_gn + b), (sum du, sum du * x_gn)
+    from joligen_b200 import lib as L
+    x_gn = _pad_channels(_nhwc((rnd(n, cin, size, size) * 1.5).bfloat16().float()), cin8)
+    ab = torch.stack([1 + 0.3 * rnd(n, cin8), 0.2 * rnd(n, cin8)], dim=-1).contiguous()
+    sums = torch.zeros(n, cin8, 2, device="cuda")
+    dx2 = K.conv2d_fwd(dy_d, wd, None, cin8, k, k, pad=k - 1 - pad, gn=(x_gn, ab, L.ACT_SILU, sums))
+    assert torch.equal(dx2, dx)
+    u = x_gn.float() * ab[:, None, None, :, 0] + ab[:, None, None, :, 1]
+    sg = torch.sigmoid(u)
+    du = dx.float() * (sg * (1 + u * (1 - sg)))
+    want = torch.stack([du.sum(dim=(1, 2)), (du * x_gn.float()).sum(dim=(1, 2))], dim=-1)
+    assert rel(sums, want) < 2e-3
     # the trainer's path: raw accumulation into a persistent slot + batched unpack
     if cin8 == cin and cout8 == cout:
         from joligen_b200 import lib as L
