@@ -205,6 +205,15 @@ int jg_mask_class_dropout(const float* mask_f32, const int64_t* mask_i64, const 
                           int64_t fill, float* out_f32, int64_t* out_i64, int N, int64_t per_image,
                           jg_stream_t stream);
 int jg_haar(const float* src, float* dst, int N, int C, int h, int w, int mode, jg_stream_t stream);
+/* Per-pixel label embedding of PaletteDenoiseFn ("mask" conditioning, palette_denoise_fn.py:118-136):
+ * out[row][col0 .. col0+E) = bf16(table[idx[row]][:]) written into an NHWC bf16 tensor of channel stride ld (the
+ * embedding channels the reference concatenates to the UNet input); idx = the semantic mask, int64 or fp32 (exactly
+ * one).  Backward: dtable [K][E] and counts [K] (both overwritten) = the row-wise scatter-sum of d and the label
+ * frequencies (nn.Embedding(scale_grad_by_freq=True) divides by them). */
+int jg_embed_rows(const float* table, const float* idx_f32, const int64_t* idx_i64, void* out, int ld, int col0,
+                  int64_t rows, int E, int K, jg_stream_t stream);
+int jg_embed_rows_bwd(const void* d, int ld, int col0, const float* idx_f32, const int64_t* idx_i64, int64_t rows,
+                      int E, int K, float* dtable, float* counts, jg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GroupNorm (+ FiLM scale/shift) (+ SiLU), NHWC bf16, fp32 statistics.  HBM-bound.

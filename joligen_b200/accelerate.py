@@ -147,11 +147,14 @@ def accelerate(module: nn.Module) -> nn.Module:
         if type(ref_unet).__name__ not in builders:
             raise NotImplementedError("accelerate: DiffusionGenerator backbone %s is not on the B200 path yet"
                                       % type(ref_unet).__name__)
-        if getattr(module.denoise_fn, "conditioning", ""):
-            raise NotImplementedError("accelerate: conditioning %r is not supported yet"
-                                      % module.denoise_fn.conditioning)
+        cond = getattr(module.denoise_fn, "conditioning", "")
+        nclasses = 2
+        for name in ("netl_embedder_class", "netl_embedder_mask"):
+            if hasattr(module.denoise_fn, name):
+                nclasses = getattr(module.denoise_fn, name).num_classes
         unet = builders[type(ref_unet).__name__](ref_unet)
-        dn = nets.PaletteDenoiseFn(model=unet, cond_embed_dim=module.denoise_fn.cond_embed_dim, conditioning="")
+        dn = nets.PaletteDenoiseFn(model=unet, cond_embed_dim=module.denoise_fn.cond_embed_dim, conditioning=cond,
+                                   nclasses=nclasses)  # ("ref" conditioning raises: frozen third-party backbone)
         new = nets.DiffusionGenerator(denoise_fn=dn, sampling_method=module.sampling_method,
                                       image_size=module.image_size)
         _adopt(new, module)

@@ -200,7 +200,8 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvFwdParams& p, EpiPr
 // also makes the 16-byte shared stores conflict-free) into one of two 16 KB staging buffers and one thread hands the
 // slab to the TMA engine.  One named barrier per slab: before it, the issuing thread has waited for the previous
 // slab's store to finish reading the other buffer.
-template <int BLOCK_N>
+// RAGGED: output tiles may hang over the image border (generic kernel); the halo kernel tiles its output exactly.
+template <int BLOCK_N, bool RAGGED = true>
 __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, EpiPrefetch& pf, const float* s_bias,
                                                        uint32_t t_acc, int q, int half, int n_tile, bool valid,
                                                        size_t pix, uint8_t* stage, int& stage_idx,
@@ -318,32 +319,35 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
     }
     if ((p.stats || p.gn_sums) && colco < p.Cout) {
       // (this buffer is rewritten two slabs from now, behind the next slab's barrier: every thread has left by then)
-      const uint8_t* slab = stage + stage_idx * kStageBytes;
+      // The two modes are separate loops (the mode test is NOT inside the row loop): only the code of the active mode
+      // is ever fetched — with both interleaved, ncu showed the kernel stalling on instruction-cache misses.
+      const uint8_t* colbase = stage + stage_idx * kStageBytes + rl * 128 + (((w8 ^ rl) << 4) | (pp << 2));
       float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+      if (p.stats) {
+        // statistics of the STORED values for the GroupNorm that reads y next: sum, sum of squares
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+          const int rr = rl + 8 * k;
+          float2 yv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(colbase + k * 1024));
+          if (RAGGED && !((c1 + rr % tile_w < p.Wo) && (c2 + rr / tile_w < p.Ho))) yv = make_float2(0.f, 0.f);
+          s0 += yv.x; t0 = fmaf(yv.x, yv.x, t0);
+          s1 += yv.y; t1 = fmaf(yv.y, yv.y, t1);
+        }
+      } else {
+        // GroupNorm-backward sums: y is dL/d(act output); du = y * act'(a*x + b); A = sum du, B = sum du * x
 #pragma unroll
-      for (int k0 = 0; k0 < 16; k0 += XB) {
-        if (k0 > 0 && p.gn_sums) load_x(k0);
+        for (int k0 = 0; k0 < 16; k0 += XB) {
+          if (k0 > 0) load_x(k0);
 #pragma unroll
-        for (int k = 0; k < XB; ++k) {
-          const int rr = rl + 8 * (k0 + k);
-          const float2 yv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
-              slab + rr * 128 + (((w8 ^ rl) << 4) | (pp << 2))));
-          const bool live = (c1 + rr % tile_w < p.Wo) && (c2 + rr / tile_w < p.Ho);  // ragged output tiles
-          if (p.stats) {
-            // statistics of the STORED values for the GroupNorm that reads y next: sum, sum of squares
-            if (live) {
-              s0 += yv.x; t0 = fmaf(yv.x, yv.x, t0);
-              s1 += yv.y; t1 = fmaf(yv.y, yv.y, t1);
-            }
-          } else {
-            // GroupNorm-backward sums: y is dL/d(act output); du = y * act'(a*x + b); A = sum du, B = sum du * x
+          for (int k = 0; k < XB; ++k) {
+            const int rr = rl + 8 * (k0 + k);
+            const float2 yv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(colbase + (k0 + k) * 1024));
             const float2 xv = unpack_bf16x2(xw[k]);
-            if (live) {
-              const float du0 = yv.x * act_grad_rt(fmaf(xv.x, ab4.x, ab4.y), p.gn_act);
-              const float du1 = yv.y * act_grad_rt(fmaf(xv.y, ab4.z, ab4.w), p.gn_act);
-              s0 += du0; t0 = fmaf(du0, xv.x, t0);
-              s1 += du1; t1 = fmaf(du1, xv.y, t1);
-            }
+            const bool live = !RAGGED || ((c1 + rr % tile_w < p.Wo) && (c2 + rr / tile_w < p.Ho));
+            const float du0 = live ? yv.x * act_grad_rt(fmaf(xv.x, ab4.x, ab4.y), p.gn_act) : 0.f;
+            const float du1 = live ? yv.y * act_grad_rt(fmaf(xv.y, ab4.z, ab4.w), p.gn_act) : 0.f;
+            s0 += du0; t0 = fmaf(du0, xv.x, t0);
+            s1 += du1; t1 = fmaf(du1, xv.y, t1);
           }
         }
       }

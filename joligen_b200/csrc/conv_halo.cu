@@ -282,8 +282,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       if constexpr (TMA_STORE) {
         if (res_tma) mbar_wait(&rfull[rbuf], rphase);
-        conv_epilogue_tile_tma<BLOCK_N>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half, n_tile,
-                                        valid, pix, stage, stage_idx, &tmY, tw * kHaloTW, th * kHaloTH, tn, issuer,
+        conv_epilogue_tile_tma<BLOCK_N, false>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half,
+                                               n_tile, valid, pix, stage, stage_idx, &tmY, tw * kHaloTW, th * kHaloTH, tn, issuer,
                                         res_tma ? res_stage + rbuf * kStageBytes : nullptr, kHaloTW, s_acc);
         if (res_tma) {
           // the slab barrier inside the epilogue ordered every thread's reads of this residual buffer before here

@@ -58,14 +58,16 @@ __global__ void mask_dropout_kernel(const float* __restrict__ maskf, const long 
   else outf[i] = drop ? (float)fill : maskf[i];
 }
 
-// Haar analysis / synthesis.  k_band[a][b] (a = row, b = column), all entries +-0.5:
+// Haar analysis / synthesis.  k_band[a][b] (a = row, b = column), all entries +-(1/sqrt2)^2:
 //   ll = +,+,+,+   lh = -,-,+,+   hl = -,+,-,+   hh = +,-,-,+        (freq_utils.get_haar_wavelet)
 // upfirdn2d(down=2) correlates with the FLIPPED kernel: out[i][j] = sum_ab x[2i+a][2j+b] * k[1-a][1-b];
 // upfirdn2d(up=2, pad=(1,0,1,0)): out[2i+a][2j+b] = x[i][j] * k[a][b].
 __device__ __forceinline__ float haar_k(int band, int a, int b) {
   // sign tables, row-major [a][b]
   const int s = band == 0 ? 0x0 : band == 1 ? 0x3 : band == 2 ? 0x5 : 0x6;  // bit (a*2+b) set = negative
-  return ((s >> (a * 2 + b)) & 1) ? -0.5f : 0.5f;
+  // the reference builds the taps as fp32 products of 1/sqrt(2): 0.70710677f * 0.70710677f = 0.49999997f, not 0.5f
+  const float kk = __fmul_rn(0.70710677f, 0.70710677f);
+  return ((s >> (a * 2 + b)) & 1) ? -kk : kk;
 }
 
 // mode 0: DWT forward   x [N][C][H][W] -> y [N][4C][H/2][W/2]   (bands ll | lh | hl | hh)
@@ -127,6 +129,64 @@ __global__ void haar_kernel(const float* __restrict__ src, float* __restrict__ d
   }
 }
 
+// ---- per-pixel label embedding (PaletteDenoiseFn.compute_cond, palette_denoise_fn.py:118-136) --------------------------
+// out[row][col0 + e] = bf16(table[idx[row]][e]) for an NHWC bf16 tensor with channel stride ld: the mask-embedding
+// channels that the reference concatenates to the UNet input.  idx is the int64 / fp32 semantic mask.
+__global__ void embed_rows_kernel(const float* __restrict__ table, const float* __restrict__ idxf,
+                                  const long long* __restrict__ idxi, __nv_bfloat16* __restrict__ out, int ld, int col0,
+                                  long long rows, int E, int K) {
+  // (col0 = 6 for the Palette input: [y_cond | y_noisy | mask embedding] — only 4-byte aligned: bf16 pairs)
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int e2 = E / 2;
+  if (i >= rows * e2) return;
+  const long long row = i / e2;
+  const int v = (int)(i % e2);
+  long long k = idxi ? idxi[row] : (long long)idxf[row];  // (.to(torch.int32) truncates)
+  k = k < 0 ? 0 : (k >= K ? K - 1 : k);                   // an out-of-range label is an error upstream; stay in bounds
+  const float2 a = *reinterpret_cast<const float2*>(table + (size_t)k * E + v * 2);
+  *reinterpret_cast<__nv_bfloat162*>(out + row * ld + col0 + v * 2) = __floats2bfloat162_rn(a.x, a.y);
+}
+
+// dtable[k][e] += sum over rows with idx[row] == k of d[row][col0 + e]; counts[k] += number of such rows
+// (scale_grad_by_freq divides afterwards).  One warp walks a contiguous chunk of rows; lane <-> channel (e, e+32, ..);
+// every warp owns a private [K][E] accumulator in shared memory (no atomics inside the block), one fp32 atomic per
+// (class, channel) and block at the end.
+constexpr int kEmbWarps = 8;
+__global__ void __launch_bounds__(kEmbWarps * 32)
+embed_rows_bwd_kernel(const __nv_bfloat16* __restrict__ d, int ld, int col0, const float* __restrict__ idxf,
+                      const long long* __restrict__ idxi, long long rows, int E, int K, long long rows_per_warp,
+                      float* __restrict__ dtable, float* __restrict__ counts) {
+  extern __shared__ float sacc[];  // [warps][K][E] then [warps][K] counts
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* acc = sacc + (size_t)warp * K * E;
+  float* cnt = sacc + (size_t)kEmbWarps * K * E + warp * K;
+  for (int i = lane; i < K * E; i += 32) acc[i] = 0.f;
+  for (int i = lane; i < K; i += 32) cnt[i] = 0.f;
+  __syncwarp();
+  const long long w = blockIdx.x * (long long)kEmbWarps + warp;
+  const long long r0 = w * rows_per_warp;
+  const long long r1 = r0 + rows_per_warp < rows ? r0 + rows_per_warp : rows;
+  for (long long r = r0; r < r1; ++r) {
+    long long k = idxi ? idxi[r] : (long long)idxf[r];
+    k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+    for (int e = lane; e < E; e += 32) acc[k * E + e] += __bfloat162float(d[r * ld + col0 + e]);
+    if (lane == 0) cnt[k] += 1.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * E; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < kEmbWarps; ++ww) t += sacc[(size_t)ww * K * E + i];
+    if (t != 0.f) atomicAdd(&dtable[i], t);
+  }
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < kEmbWarps; ++ww) t += sacc[(size_t)kEmbWarps * K * E + ww * K + i];
+    if (t != 0.f) atomicAdd(&counts[i], t);
+  }
+}
+
 }  // namespace jg
 
 using namespace jg;
@@ -175,6 +235,44 @@ extern "C" int jg_haar(const float* src, float* dst, int N, int C, int h, int w,
   JG_CHECK(src && dst && N > 0 && C > 0 && h > 0 && w > 0 && mode >= 0 && mode <= 3, JG_ERR_INVALID, "haar: bad args");
   const long long total = (long long)N * C * h * w;
   haar_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, dst, C, h, w, total, mode);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
+extern "C" int jg_embed_rows(const float* table, const float* idx_f32, const int64_t* idx_i64, void* out, int ld,
+                             int col0, int64_t rows, int E, int K, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  JG_CHECK(table && out && (idx_f32 || idx_i64) && rows > 0 && K > 0, JG_ERR_INVALID, "embed_rows: bad args");
+  JG_CHECK(E > 0 && E % 2 == 0 && ld % 8 == 0 && col0 % 2 == 0 && col0 + E <= ld, JG_ERR_INVALID,
+           "embed_rows: E=%d and col0=%d must be even, ld=%d a multiple of 8, col0 + E <= ld", E, col0, ld);
+  const long long total = (long long)rows * (E / 2);
+  embed_rows_kernel<<<grid_for(total, 256), 256, 0, stream>>>(table, idx_f32,
+                                                             reinterpret_cast<const long long*>(idx_i64),
+                                                             static_cast<__nv_bfloat16*>(out), ld, col0, rows, E, K);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
+extern "C" int jg_embed_rows_bwd(const void* d, int ld, int col0, const float* idx_f32, const int64_t* idx_i64,
+                                 int64_t rows, int E, int K, float* dtable, float* counts, jg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  JG_CHECK(d && (idx_f32 || idx_i64) && dtable && counts && rows > 0 && K > 0 && E > 0, JG_ERR_INVALID,
+           "embed_rows_bwd: bad args");
+  const size_t smem = (size_t)kEmbWarps * K * (E + 1) * sizeof(float);
+  JG_CHECK(smem <= 96 * 1024, JG_ERR_INVALID, "embed_rows_bwd: %d classes x %d channels exceed the accumulator", K, E);
+  JG_CUDA(cudaMemsetAsync(dtable, 0, sizeof(float) * (size_t)K * E, stream));
+  JG_CUDA(cudaMemsetAsync(counts, 0, sizeof(float) * (size_t)K, stream));
+  static bool attr_done = false;
+  if (!attr_done) {
+    JG_CUDA(cudaFuncSetAttribute(embed_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_done = true;
+  }
+  const int blocks = num_sms() * 2;
+  const long long warps = (long long)blocks * kEmbWarps;
+  const long long rpw = (rows + warps - 1) / warps;
+  embed_rows_bwd_kernel<<<blocks, kEmbWarps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(d), ld, col0, idx_f32,
+                                                                 reinterpret_cast<const long long*>(idx_i64), rows, E, K,
+                                                                 rpw, dtable, counts);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }

@@ -638,3 +638,21 @@ def haar(x, mode):
         out = torch.empty((n, c_img, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
     L.call("jg_haar", L.ptr(x), L.ptr(out), n, c_img, h, w, mode, L.stream())
     return out
+
+
+def embed_rows(table, idx, out, col0):
+    """out[..., col0:col0+E] = bf16(table[idx]) for an NHWC bf16 tensor `out` ([N,H,W,ld]); idx [N,1,H,W] int64/fp32."""
+    k, e = table.shape
+    mf, mi = _mask_ptrs(idx.contiguous())
+    L.call("jg_embed_rows", L.ptr(table), mf, mi, L.ptr(out), _ld(out), col0, idx.numel(), e, k, L.stream())
+    return out
+
+
+def embed_rows_bwd(d, idx, col0, k, e):
+    """-> (dtable [K,E] = scatter-sum of d[..., col0:col0+E] by label, counts [K])"""
+    dtable = torch.empty((k, e), dtype=torch.float32, device=d.device)
+    counts = torch.empty((k,), dtype=torch.float32, device=d.device)
+    mf, mi = _mask_ptrs(idx.contiguous())
+    L.call("jg_embed_rows_bwd", L.ptr(d), _ld(d), col0, mf, mi, idx.numel(), e, k, L.ptr(dtable), L.ptr(counts),
+           L.stream())
+    return dtable, counts

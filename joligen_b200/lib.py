@@ -63,6 +63,8 @@ _SIGNATURES = {
     "jg_u8_to_f32_normalized": [c_p, c_p, c_int, c_int, c_int, c_int, c_f, c_f, c_p],
     "jg_mask_class_dropout": [c_p, c_p, c_p, c_f, c_i64, c_p, c_p, c_int, c_i64, c_p],
     "jg_haar": [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_embed_rows": [c_p, c_p, c_p, c_p, c_int, c_int, c_i64, c_int, c_int, c_p],
+    "jg_embed_rows_bwd": [c_p, c_int, c_int, c_p, c_p, c_i64, c_int, c_int, c_p, c_p, c_p],
     "jg_linear_batched_tiles": [c_int],
     "jg_linear_batched_fwd": [c_p, c_p, c_p, c_int, c_int, c_p, c_int, c_int, c_int, c_p],
     "jg_linear_batched_bwd": [c_p, c_p, c_p, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p],

@@ -547,24 +547,64 @@ def gamma_embedding(gammas, dim, max_period=10000):
     return emb
 
 
+class LabelEmbedder(nn.Module):
+    """palette_denoise_fn.LabelEmbedder (:14-31): nn.Embedding(num_classes, hidden, max_norm=1, scale_grad_by_freq)."""
+
+    def __init__(self, num_classes, hidden_size):
+        super().__init__()
+        self.embedding_table = nn.Embedding(num_classes, hidden_size, max_norm=1.0, scale_grad_by_freq=True)
+        self.num_classes = num_classes
+
+    def forward(self, labels):
+        return ops.label_embed(self.embedding_table.weight, labels)
+
+
 class PaletteDenoiseFn(nn.Module):
-    """palette_denoise_fn.PaletteDenoiseFn restricted to conditioning == "" (no class / mask / ref embedding).  A
-    UNet whose forward takes three arguments (UNetGeneratorRefAttn) receives the dataloader's reference image
-    (palette_denoise_fn.py:40-41, 111-114)."""
+    """palette_denoise_fn.PaletteDenoiseFn with conditioning "" / "class" / "mask" / "class_mask" (the "ref" image
+    embedding needs a frozen CLIP / ImageBind backbone: third-party, out of scope).  A UNet whose forward takes three
+    arguments (UNetGeneratorRefAttn) receives the dataloader's reference image (palette_denoise_fn.py:40-41, 111-114)."""
 
     def __init__(self, model, cond_embed_dim, ref_embed_net="", conditioning="", nclasses=2):
         super().__init__()
-        if conditioning:
-            raise NotImplementedError("B200 PaletteDenoiseFn: conditioning %r is not supported yet" % conditioning)
+        if "ref" in conditioning:
+            raise NotImplementedError("B200 PaletteDenoiseFn: conditioning %r needs the frozen %s backbone"
+                                      % (conditioning, ref_embed_net or "clip"))
         self.model = model
         self.model_nargs = len(inspect.signature(model.forward).parameters)
         self.cond_embed_dim = cond_embed_dim
         self.conditioning = conditioning
+        if "class" in conditioning:
+            self.netl_embedder_class = LabelEmbedder(nclasses, cond_embed_dim // 2)
+            nn.init.normal_(self.netl_embedder_class.embedding_table.weight, std=0.02)
+        if "mask" in conditioning:
+            self.netl_embedder_mask = LabelEmbedder(nclasses, cond_embed_dim)
+            nn.init.normal_(self.netl_embedder_mask.embedding_table.weight, std=0.02)
+
+    def mask_embed_channels(self):
+        """extra input channels the mask embedding occupies (diffusion_networks.py:112-113)"""
+        return self.cond_embed_dim if "mask" in self.conditioning else 0
+
+    def embedding(self, embed_noise_level, cls):
+        """(:96-100) the class embedding shares the embedding vector with the noise level"""
+        if "class" in self.conditioning:
+            if cls is None:
+                raise RuntimeError('PaletteDenoiseFn: conditioning "class" needs the class labels (cls)')
+            return torch.cat((embed_noise_level, self.netl_embedder_class(cls)), dim=1)
+        return embed_noise_level
 
     def forward(self, input, embed_noise_level, cls=None, mask=None, ref=None):
+        """Drop-in NCHW signature of the reference (:95-115)."""
+        emb = self.embedding(embed_noise_level, cls)
+        if "mask" in self.conditioning:
+            e = self.cond_embed_dim
+            c = input.shape[1]
+            x = ops.to_nhwc(torch.cat([input, input.new_zeros((input.shape[0], e) + tuple(input.shape[2:]))], dim=1))
+            x = ops.embed_rows_into(self.netl_embedder_mask.embedding_table.weight, mask.contiguous(), x, c)
+            return ops.to_nchw(self.forward_nhwc(x, emb, self.pack_ref(ref) if self.model_nargs == 3 else None),
+                               self.model.out_channel)
         if self.model_nargs == 3:
-            return self.model(input, embed_noise_level, ref)
-        return self.model(input, embed_noise_level)
+            return self.model(input, emb, ref)
+        return self.model(input, emb)
 
     def pack_ref(self, ref):
         """ref NCHW fp32 -> what the UNet's NHWC path consumes (None for two-argument UNets)."""
@@ -595,9 +635,11 @@ class DiffusionGenerator(nn.Module):
         set_new_noise_schedule(self.denoise_fn.model, "test")
         e = self.denoise_fn.cond_embed_dim
         self.cond_embed_dim = e
-        self.cond_embed_gammas = e
-        self.cond_embed_gammas_in = e
-        self.cond_embed = nn.Sequential(nn.Linear(e, e), nn.SiLU(), nn.Linear(e, e))
+        # the gamma embedding is half as wide when a class / ref embedding shares the vector (:63-76)
+        eg = e // 2 if any(c in getattr(self.denoise_fn, "conditioning", "") for c in ("class", "ref")) else e
+        self.cond_embed_gammas = eg
+        self.cond_embed_gammas_in = eg
+        self.cond_embed = nn.Sequential(nn.Linear(eg, eg), nn.SiLU(), nn.Linear(eg, eg))
 
     def compute_gammas(self, gammas):
         emb = gamma_embedding(gammas, self.cond_embed_gammas_in)
@@ -621,7 +663,7 @@ class DiffusionGenerator(nn.Module):
         w = torch.stack([snr, 5.0 * torch.ones_like(t)], dim=1).min(dim=1)[0] / snr
         return t, sample_gammas, w
 
-    def forward_nhwc(self, y_0, y_cond, mask, noise, t=None, u=None, ref=None):
+    def forward_nhwc(self, y_0, y_cond, mask, noise, t=None, u=None, ref=None, cls=None):
         """Returns (noise, noise_hat NHWC bf16 [N,H,W,8], min_snr_w [B]).  Video clips [B,F,C,H,W] (UNetVid,
         diffusion_generator.py:460-463, 497-500) are folded to N = B*F frames: one (t, gamma) draw per clip, the
         per-frame work is identical to the image path; noise is returned in the folded [N,C,H,W] layout."""
@@ -641,30 +683,39 @@ class DiffusionGenerator(nn.Module):
         g_per_image = sample_gammas.reshape(b)
         if frames:
             g_per_image = g_per_image.repeat_interleave(frames)
+        dn = self.denoise_fn
+        e_mask = dn.mask_embed_channels() if hasattr(dn, "mask_embed_channels") else 0
         x = K.noise_pack(y_0.contiguous().float(), y_cond.contiguous().float(), noise.contiguous().float(),
                          None if mask is None else mask.contiguous(), g_per_image.contiguous(),
-                         ld=(2 * y_0.shape[1] + 7) // 8 * 8)
-        noise_hat = self.denoise_fn.forward_nhwc(x, emb, self.denoise_fn.pack_ref(ref))
+                         ld=(2 * y_0.shape[1] + e_mask + 7) // 8 * 8)
+        if e_mask:  # cat([input, mask_embed]) (palette_denoise_fn.py:104-108): the embedding lands behind the 2C images
+            if frames:
+                raise NotImplementedError("B200 DiffusionGenerator: mask conditioning with video clips")
+            x = ops.embed_rows_into(dn.netl_embedder_mask.embedding_table.weight, mask.contiguous(), x,
+                                    2 * y_0.shape[1])
+        if hasattr(dn, "embedding"):
+            emb = dn.embedding(emb, cls)
+        noise_hat = dn.forward_nhwc(x, emb, dn.pack_ref(ref))
         return noise, noise_hat, w
 
     def forward(self, y_0, y_cond, mask, noise, cls=None, ref=None, dropout_prob=0.0, t=None, u=None):
-        if cls is not None or dropout_prob:
-            raise NotImplementedError("B200 DiffusionGenerator: class conditioning / conditioning dropout")
+        # (dropout_prob is accepted and unused, like the reference's: the conditioning dropout happens in
+        # PaletteModel.compute_palette_loss, palette_model.py:565-584 -> PaletteTrainer)
         shape5 = tuple(y_0.shape) if y_0.dim() == 5 else None
         c = y_0.shape[2] if shape5 else y_0.shape[1]
-        noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u, ref=ref)
+        noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u, ref=ref, cls=cls)
         noise_hat = ops.to_nchw(noise_hat, c)
         if shape5:
             noise, noise_hat = noise.reshape(shape5), noise_hat.reshape(shape5)
         return noise, noise_hat, w.view(-1, 1, 1, 1)
 
     def forward_loss(self, y_0, y_cond, mask, noise=None, lambda_G=1.0, use_minsnr=False, l1=False, t=None, u=None,
-                     ref=None):
+                     ref=None, cls=None):
         """compute_palette_loss fused: the UNet output stays NHWC bf16 and feeds the eps-loss kernel directly."""
         if y_0.dim() == 5 and use_minsnr:
             raise NotImplementedError("B200 DiffusionGenerator: min-SNR weighting with video clips")
         b5 = y_0.shape[0] * y_0.shape[1] if y_0.dim() == 5 else None
-        noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u, ref=ref)
+        noise, noise_hat, w = self.forward_nhwc(y_0, y_cond, mask, noise, t, u, ref=ref, cls=cls)
         if b5 is not None and mask is not None:
             mask = mask.reshape((b5,) + tuple(mask.shape[2:]))
         return ops.palette_loss(noise_hat, noise.contiguous().float(), None if mask is None else mask.contiguous(),
@@ -679,8 +730,8 @@ class DiffusionGenerator(nn.Module):
         posterior mean, the noise injection, the mask blend and the next step's NHWC bf16 input pack.
         noise_fn(i, shape) -> fp32 NCHW noise for step i (default torch.randn on the device; the tests replay the
         reference's CPU draws).  Returns (y_t, ret_arr) like the reference."""
-        if cls is not None or guidance_scale:
-            raise NotImplementedError("B200 restoration_ddpm: class conditioning and guidance")
+        if cls is not None or guidance_scale or getattr(self.denoise_fn, "conditioning", ""):
+            raise NotImplementedError("B200 restoration_ddpm: class / mask conditioning and guidance")
         model = self.denoise_fn.model
         ref_p = self.denoise_fn.pack_ref(ref)
         T = model.num_timesteps_test
@@ -720,8 +771,8 @@ class DiffusionGenerator(nn.Module):
         """diffusion_generator.restoration_ddim (:286-347) with ddim_p_sample / ddim_p_mean_variance (:349-456):
         num_steps UNet forwards on the linear t sequence; the update is deterministic (the reference draws a noise
         tensor and does not use it), one fused kernel per step."""
-        if cls is not None or guidance_scale:
-            raise NotImplementedError("B200 restoration_ddim: class conditioning and guidance")
+        if cls is not None or guidance_scale or getattr(self.denoise_fn, "conditioning", ""):
+            raise NotImplementedError("B200 restoration_ddim: class / mask conditioning and guidance")
         model = self.denoise_fn.model
         ref_p = self.denoise_fn.pack_ref(ref)
         T = model.num_timesteps_test
@@ -768,13 +819,15 @@ class DiffusionGenerator(nn.Module):
 def build_palette_generator(image_size=256, in_channel=6, inner_channel=64, out_channel=3, res_blocks=(2, 2, 2, 2),
                             attn_res=(16,), channel_mults=(1, 2, 4, 8), num_heads=1, num_head_channels=32,
                             group_norm_size=32, cond_embed_dim=32, n_timestep_train=2000, n_timestep_test=1000,
-                            efficient=False):
+                            efficient=False, conditioning="", nclasses=2):
     """What diffusion_networks.define_G(model_type="palette", G_netG="unet_mha", ...) builds
     (models/diffusion_networks.py:114-139, 361-376), on the B200 modules."""
+    if "mask" in conditioning:
+        in_channel += cond_embed_dim  # diffusion_networks.py:112-113
     unet = UNet(image_size=image_size, in_channel=in_channel, inner_channel=inner_channel, out_channel=out_channel,
                 res_blocks=list(res_blocks), attn_res=list(attn_res), tanh=False, n_timestep_train=n_timestep_train,
                 n_timestep_test=n_timestep_test, norm="groupnorm", group_norm_size=group_norm_size,
                 cond_embed_dim=cond_embed_dim, channel_mults=tuple(channel_mults), num_heads=num_heads,
                 num_head_channels=num_head_channels, efficient=efficient)
-    dn = PaletteDenoiseFn(model=unet, cond_embed_dim=cond_embed_dim, conditioning="")
+    dn = PaletteDenoiseFn(model=unet, cond_embed_dim=cond_embed_dim, conditioning=conditioning, nclasses=nclasses)
     return DiffusionGenerator(denoise_fn=dn, sampling_method="ddpm", image_size=image_size, G_ngf=inner_channel)

@@ -30,8 +30,10 @@ def _needs(ctx, i):
 # ---------------------------------------------------------------------------------------------------------------------
 import os as _os
 
-# JG_FUSE_GN: "1" (default) both reductions, "stats" / "sums" one of them, "0" none (diagnostics)
-_FUSE_MODE = _os.environ.get("JG_FUSE_GN", "1")
+# JG_FUSE_GN: "stats" (default) / "sums" one of the two reductions, "1" both, "0" none
+# Default "stats": measured on B200 (profiles/r02_gn_fusion_ab.md) the statistics fused into the forward convs win
+# ~1 ms per step, while the backward sums in the dgrad epilogue cost the convs more than the pass they remove.
+_FUSE_MODE = _os.environ.get("JG_FUSE_GN", "stats")
 FUSE_GN = [_FUSE_MODE != "0"]
 FUSE_STATS = [_FUSE_MODE in ("1", "stats")]
 FUSE_SUMS = [_FUSE_MODE in ("1", "sums")]
@@ -899,3 +901,64 @@ def haar_dwt(x):
 
 def haar_iwt(x):
     return HaarFn.apply(x, True)
+
+
+# ---- label embeddings of PaletteDenoiseFn (palette_denoise_fn.py:14-31, 118-136) ---------------------------------------
+@torch.no_grad()
+def _embedding_renorm_(table, idx, max_norm=1.0):
+    """nn.Embedding(max_norm=...): the rows that are looked up are rescaled in place to norm <= max_norm
+    (torch.embedding_renorm_: scale = max_norm / (norm + 1e-7)).  Static shapes only (CUDA-graph capturable)."""
+    k = table.shape[0]
+    present = torch.zeros(k, dtype=torch.bool, device=table.device)
+    present.index_fill_(0, idx.reshape(-1).long().clamp_(0, k - 1), True)
+    norms = table.norm(dim=1)
+    scale = torch.where(present & (norms > max_norm), max_norm / (norms + 1e-7), torch.ones_like(norms))
+    table.mul_(scale[:, None])
+
+
+class LabelEmbedFn(torch.autograd.Function):
+    """Class-label lookup [B] -> [B, E] fp32 with nn.Embedding(max_norm=1, scale_grad_by_freq=True) semantics.  O(B):
+    plain torch gathers with static shapes (like the t / gamma gathers of the noising prologue)."""
+
+    @staticmethod
+    def forward(ctx, table, labels):
+        _embedding_renorm_(table, labels)
+        ctx.save_for_backward(labels)
+        ctx.k = table.shape[0]
+        return table.detach().index_select(0, labels)
+
+    @staticmethod
+    def backward(ctx, d):
+        (labels,) = ctx.saved_tensors
+        g = torch.zeros((ctx.k, d.shape[1]), dtype=d.dtype, device=d.device).index_add_(0, labels, d)
+        counts = torch.zeros(ctx.k, dtype=d.dtype, device=d.device).index_add_(0, labels, torch.ones_like(d[:, 0]))
+        return g / counts.clamp(min=1.0)[:, None], None
+
+
+class EmbedRowsFn(torch.autograd.Function):
+    """Per-pixel label embedding written INTO channels [col0, col0+E) of the NHWC bf16 UNet input (the reference
+    concatenates mask_embed to the input, palette_denoise_fn.py:104-108).  Same nn.Embedding semantics as above."""
+
+    @staticmethod
+    def forward(ctx, table, mask, x, col0):
+        _embedding_renorm_(table, mask)
+        K.embed_rows(table.detach(), mask, x, col0)
+        ctx.save_for_backward(mask)
+        ctx.cfg = (col0, table.shape[0], table.shape[1])
+        ctx.mark_dirty(x)
+        return x
+
+    @staticmethod
+    def backward(ctx, d):
+        (mask,) = ctx.saved_tensors
+        col0, k, e = ctx.cfg
+        dtable, counts = K.embed_rows_bwd(_rows(d), mask, col0, k, e)
+        return dtable / counts.clamp(min=1.0)[:, None], None, None, None
+
+
+def label_embed(table, labels):
+    return LabelEmbedFn.apply(table, labels)
+
+
+def embed_rows_into(table, mask, x, col0):
+    return EmbedRowsFn.apply(table, mask, x, col0)

@@ -125,7 +125,7 @@ class PaletteTrainer:
     def __init__(self, netG_A, lr=2e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, optim="adamw",
                  ema=True, ema_beta=0.999, iter_size=1, lambda_G=1.0, use_minsnr=False, loss="MSE",
                  device=None, process_group=None, cuda_graph=False, graph_warmup=3, overlap_comm=True,
-                 comm_buckets=8):
+                 comm_buckets=8, dropout_prob=0.0, num_classes=None):
         if not torch.cuda.is_available():
             raise RuntimeError("joligen_b200.PaletteTrainer needs a CUDA device (there is no CPU path)")
         self.device = torch.device(device if device is not None else "cuda")
@@ -152,6 +152,14 @@ class PaletteTrainer:
             raise NotImplementedError("alg_palette_loss %r" % loss)
         self.use_ref = getattr(getattr(self.netG_A, "denoise_fn", None), "model_nargs", 2) == 3
         self.ref_A = None
+        # class / mask conditioning (alg_diffusion_cond_embed) and its dropout (palette_model.py:565-584: the dropped
+        # samples get the highest class = "unconditioned")
+        self.conditioning = getattr(getattr(self.netG_A, "denoise_fn", None), "conditioning", "")
+        self.dropout_prob = float(dropout_prob)
+        self.num_classes = num_classes
+        if self.dropout_prob > 0.0 and num_classes is None:
+            raise ValueError("PaletteTrainer: dropout_prob > 0 needs num_classes (palette_model.py:148)")
+        self.cls = None
         self.pg = process_group
         self.world = dp.world_size(process_group)
         # gradient exchange: the library's own NCCL communicator; buckets of the flat gradient leave as soon as the
@@ -210,11 +218,17 @@ class PaletteTrainer:
                 st["M"].copy_(m, non_blocking=non_blocking)
             if r is not None:
                 st["R"].copy_(r, non_blocking=non_blocking)
+            if st["C"] is not None:
+                st["C"].copy_(data["B_label_cls"], non_blocking=non_blocking)
             return
         self.y_t = data["A"].to(self.device, non_blocking=non_blocking)
         self.gt_image = data["B"].to(self.device, non_blocking=non_blocking)
         self.mask = None if m is None else m.to(self.device, non_blocking=non_blocking)
         self.ref_A = None if r is None else r.to(self.device, non_blocking=non_blocking)
+        c = data.get("B_label_cls") if "class" in self.conditioning else None
+        if "class" in self.conditioning and c is None:
+            raise RuntimeError('PaletteTrainer: conditioning "class" needs data["B_label_cls"]')
+        self.cls = None if c is None else c.to(self.device, non_blocking=non_blocking).long()
         self.cond_image = self.y_t
 
     def broadcast_parameters(self):
@@ -233,10 +247,20 @@ class PaletteTrainer:
         return st
 
     # -- step -----------------------------------------------------------------------------------
-    def compute_palette_loss(self, noise=None, t=None, u=None):
-        self.loss_G_tot = self.netG_A.forward_loss(self.gt_image, self.cond_image, self.mask, noise=noise,
+    def compute_palette_loss(self, noise=None, t=None, u=None, drop_u=None):
+        mask, cls = self.mask, self.cls
+        if self.dropout_prob > 0.0:
+            # palette_model.py:565-584; drop_u = the torch.rand(B) draw (explicit in the tests)
+            if drop_u is None:
+                drop_u = torch.rand(self.gt_image.shape[0], device=self.device)
+            if mask is not None:
+                mask = K.mask_class_dropout(mask, drop_u, self.dropout_prob, self.num_classes - 1)
+            if cls is not None:
+                cls = torch.where(drop_u < self.dropout_prob, torch.full_like(cls, self.num_classes - 1), cls)
+        kw = {"cls": cls} if cls is not None else {}
+        self.loss_G_tot = self.netG_A.forward_loss(self.gt_image, self.cond_image, mask, noise=noise,
                                                    lambda_G=self.lambda_G, use_minsnr=self.use_minsnr, l1=self.l1,
-                                                   t=t, u=u, ref=self.ref_A)
+                                                   t=t, u=u, ref=self.ref_A, **kw)
         return self.loss_G_tot
 
     @staticmethod
@@ -315,11 +339,13 @@ class PaletteTrainer:
         """Capture the step into CUDA graphs (called once, after `graph_warmup` eager steps)."""
         self._static = {"A": self.y_t.clone(), "B": self.gt_image.clone(),
                         "M": None if self.mask is None else self.mask.clone(),
-                        "R": None if self.ref_A is None else self.ref_A.clone()}
+                        "R": None if self.ref_A is None else self.ref_A.clone(),
+                        "C": None if self.cls is None else self.cls.clone()}
         self.y_t = self.cond_image = self._static["A"]
         self.gt_image = self._static["B"]
         self.mask = self._static["M"]
         self.ref_A = self._static["R"]
+        self.cls = self._static["C"]
         self.loss_G_tot = None
         import gc
         gc.collect()

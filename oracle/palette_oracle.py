@@ -48,6 +48,9 @@ class UNetCfg:
     n_timestep_test: int = 1000
     use_scale_shift_norm: bool = True
     efficient: bool = False
+    # PaletteDenoiseFn conditioning (palette_denoise_fn.py:35-59): "" | "class" | "mask" | "class_mask"
+    conditioning: str = ""
+    nclasses: int = 2
 
 
 @dataclass
@@ -159,10 +162,17 @@ def generator_param_shapes(cfg: UNetCfg) -> Dict[str, Tuple[int, ...]]:
     (diffusion_generator.py:63-76), in state_dict order."""
     shapes = param_shapes(cfg, "denoise_fn.model.")
     e = cfg.cond_embed_dim
-    shapes["cond_embed.0.weight"] = (e, e)
-    shapes["cond_embed.0.bias"] = (e,)
-    shapes["cond_embed.2.weight"] = (e, e)
-    shapes["cond_embed.2.bias"] = (e,)
+    # label embedders (palette_denoise_fn.py:46-59), then the gamma MLP whose width halves when a class / ref
+    # embedding shares the embedding vector (diffusion_generator.py:63-76)
+    if "class" in cfg.conditioning:
+        shapes["denoise_fn.netl_embedder_class.embedding_table.weight"] = (cfg.nclasses, e // 2)
+    if "mask" in cfg.conditioning:
+        shapes["denoise_fn.netl_embedder_mask.embedding_table.weight"] = (cfg.nclasses, e)
+    eg = e // 2 if "class" in cfg.conditioning else e
+    shapes["cond_embed.0.weight"] = (eg, eg)
+    shapes["cond_embed.0.bias"] = (eg,)
+    shapes["cond_embed.2.weight"] = (eg, eg)
+    shapes["cond_embed.2.bias"] = (eg,)
     return shapes
 
 
@@ -353,7 +363,13 @@ def sample_t_gamma(cfg: UNetCfg, batch: int, generator: Optional[torch.Generator
     return t, u
 
 
-def diffusion_forward(sd, y_0, y_cond, mask, noise, t, u, cfg: UNetCfg, unet=None):
+def label_embed(table, idx):
+    """LabelEmbedder.forward (palette_denoise_fn.py:14-31): nn.Embedding(max_norm=1.0, scale_grad_by_freq=True) — the
+    looked-up rows are renormalised IN PLACE to norm <= 1 first, gradients are divided by the index frequency."""
+    return F.embedding(idx, table, max_norm=1.0, scale_grad_by_freq=True)
+
+
+def diffusion_forward(sd, y_0, y_cond, mask, noise, t, u, cfg: UNetCfg, unet=None, cls=None):
     """DiffusionGenerator.forward for 4-D inputs with explicit randomness (t, u, noise).
     Returns (noise, noise_hat, min_snr_loss_weight) like diffusion_generator.py:521.
     unet(sd, input, emb, cfg): the denoiser (default: the plain UNet; oracle.ref_oracle.denoiser(ref) for the
@@ -368,13 +384,22 @@ def diffusion_forward(sd, y_0, y_cond, mask, noise, t, u, cfg: UNetCfg, unet=Non
     sample_gammas = sample_gammas.view(b, -1)
     g4 = sample_gammas.view(-1, 1, 1, 1)
     y_noisy = g4.sqrt() * y_0 + (1 - g4).sqrt() * noise
-    emb = gamma_embedding(sample_gammas, cfg.cond_embed_dim)
+    eg = cfg.cond_embed_dim // 2 if "class" in cfg.conditioning else cfg.cond_embed_dim
+    emb = gamma_embedding(sample_gammas, eg)
     emb = F.linear(emb, sd["cond_embed.0.weight"], sd["cond_embed.0.bias"])
     emb = F.linear(F.silu(emb), sd["cond_embed.2.weight"], sd["cond_embed.2.bias"])
     if mask is not None:
         temp_mask = torch.clamp(mask, min=0.0, max=1.0)
         y_noisy = y_noisy * temp_mask + (1.0 - temp_mask) * y_0
     inp = torch.cat([y_cond, y_noisy], dim=1)
+    # PaletteDenoiseFn.forward / compute_cond (palette_denoise_fn.py:95-136)
+    if "class" in cfg.conditioning:
+        emb = torch.cat((emb, label_embed(sd["denoise_fn.netl_embedder_class.embedding_table.weight"], cls)), dim=1)
+    if "mask" in cfg.conditioning:
+        hw = mask.shape[-1]
+        me = label_embed(sd["denoise_fn.netl_embedder_mask.embedding_table.weight"],
+                         mask.to(torch.int32).squeeze(1).flatten(1))          # [b, h*w, e]
+        inp = torch.cat([inp, me.reshape(b, -1, hw, me.shape[-1]).permute(0, 3, 1, 2)], dim=1)
     noise_hat = unet(sd, inp, emb, cfg)
     ksnr = 5.0
     snr1 = sched["sqrt_recip_gammas_train"].gather(-1, t)

@@ -1,6 +1,7 @@
 """Run one conv shape a few times (for ncu captures / quick timing).
-    python tools/gpu_conv_one.py N H W Cin Cout K [what=fwd|fwdres|wgrad] [reps]
-fwdres = forward with the residual-add epilogue; inputs rotate over 3 buffers so that nothing is L2-resident."""
+    python tools/gpu_conv_one.py N H W Cin Cout K [what=fwd|fwdres|fwdstats|dgradgn|wgrad] [reps]
+fwdres = forward with the residual-add epilogue; fwdstats = forward + the fused GroupNorm statistics; dgradgn = forward
+kernel with the fused GroupNorm-backward sums; inputs rotate over 3 buffers so that nothing is L2-resident."""
 import os
 import sys
 
@@ -21,6 +22,8 @@ wf, wd = K.pack_conv_weight(wt)
 dy = torch.randn(n, h, w, cout, device="cuda", generator=g).to(torch.bfloat16)
 xs = [x, x.clone(), x.clone()]
 dys = [dy, dy.clone(), dy.clone()]
+stats = torch.zeros(n, cout, 2, device="cuda")
+ab = torch.stack([1 + 0.1 * torch.randn(n, cout, device="cuda"), 0.1 * torch.randn(n, cout, device="cuda")], -1).contiguous()
 it = [0]
 
 
@@ -31,6 +34,10 @@ def fn():
         return K.conv2d_fwd(xi, wf, bias, cout, k, k)
     if what == "fwdres":
         return K.conv2d_fwd(xi, wf, bias, cout, k, k, residual=di)
+    if what == "fwdstats":
+        return K.conv2d_fwd(xi, wf, bias, cout, k, k, stats=stats)
+    if what == "dgradgn":
+        return K.conv2d_fwd(xi, wf, None, cout, k, k, gn=(di, ab, 4, stats))
     return K.conv2d_wgrad(xi, di, cout, k, k)
 
 
