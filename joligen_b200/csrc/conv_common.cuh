@@ -374,6 +374,10 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
 int launch_conv_halo(const jg_conv_desc* d, const jg_conv_epilogue* e, const void* x, const void* w_packed,
                      const float* bias, const void* residual, void* y, cudaStream_t stream, bool* fused);
 
+// CTA-pair (tcgen05.mma.cta_group::2) variant of the halo kernel (conv_halo2.cu); same contract.
+int launch_conv_halo2(const jg_conv_desc* d, const jg_conv_epilogue* e, const void* x, const void* w_packed,
+                      const float* bias, const void* residual, void* y, cudaStream_t stream, bool* fused);
+
 // Fills the fused-GroupNorm fields of the kernel parameters from the C-ABI structs; returns the operand that travels
 // through the residual plumbing (the residual itself, or the GroupNorm input x of the gn_sums mode).
 inline const void* conv_apply_epilogue(ConvFwdParams& p, const jg_conv_desc* d, const jg_conv_epilogue* e,

@@ -524,6 +524,16 @@ extern "C" int jg_conv2d_fwd_ex(const jg_conv_desc* d, const jg_conv_epilogue* e
 
   // stride-1 spatial filters on 8x16-tileable outputs: halo-reuse kernel (conv_halo.cu)
   static const bool no_halo = getenv("JG_NO_HALO") != nullptr;
+  // CTA pairs (M = 256 across the two SMs of a TPC): JG_CONV_2CTA=0 turns them off
+  static const bool pairs = getenv("JG_CONV_2CTA") == nullptr || atoi(getenv("JG_CONV_2CTA")) != 0;
+  if (!no_halo && pairs) {
+    bool fused = false;
+    rc = launch_conv_halo2(d, e, x, w_packed, bias, residual, y, stream, &fused);
+    if (rc != JG_ERR_UNSUPPORTED) {
+      if (rc == JG_OK && e && !fused) rc = conv_epilogue_fallback(d, e, y, stream);
+      return rc;
+    }
+  }
   if (!no_halo) {
     bool fused = false;
     rc = launch_conv_halo(d, e, x, w_packed, bias, residual, y, stream, &fused);

@@ -24,9 +24,17 @@ from . import nets
 class FlatParams:
     """Re-point every parameter of `module` at a slice of one flat fp32 buffer (same for .grad)."""
 
-    def __init__(self, module):
-        self.params = [p for p in module.parameters()]
-        self.names = [n for n, _ in module.named_parameters()]
+    def __init__(self, module, late=None):
+        """late(name) -> True for parameters whose gradient only becomes final at the very END of the backward pass
+        (the timestep-embedding Linears of every ResBlock are evaluated by one batched launch, the label tables and the
+        gamma MLP sit in front of the whole net): they are placed FIRST in the flat buffers, i.e. in the LAST gradient
+        bucket, so that the other buckets can leave while the backward pass is still running.  state_dict order and
+        names are untouched (only .data / .grad are re-pointed)."""
+        named = list(module.named_parameters())
+        if late is not None:
+            named = [(n, p) for n, p in named if late(n)] + [(n, p) for n, p in named if not late(n)]
+        self.params = [p for _, p in named]
+        self.names = [n for n, _ in named]
         # 64-element (256 B) aligned slices keep every tensor 16-byte aligned for vector / TMA access
         self.offsets = []
         off = 0
@@ -125,12 +133,13 @@ class PaletteTrainer:
     def __init__(self, netG_A, lr=2e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, optim="adamw",
                  ema=True, ema_beta=0.999, iter_size=1, lambda_G=1.0, use_minsnr=False, loss="MSE",
                  device=None, process_group=None, cuda_graph=False, graph_warmup=3, overlap_comm=True,
-                 comm_buckets=8, dropout_prob=0.0, num_classes=None):
+                 comm_buckets=8, comm_min_bucket=1 << 20, dropout_prob=0.0, num_classes=None):
         if not torch.cuda.is_available():
             raise RuntimeError("joligen_b200.PaletteTrainer needs a CUDA device (there is no CPU path)")
         self.device = torch.device(device if device is not None else "cuda")
         self.netG_A = netG_A.to(self.device)
-        self.flat = FlatParams(self.netG_A)
+        self.flat = FlatParams(self.netG_A, late=lambda n: ("emb_layers" in n or n.startswith("cond_embed")
+                                                             or "embedder" in n))
         # all conv weights: one batched bf16 re-pack after each optimizer step, one batched wgrad unpack per backward
         self.packset = nets.WeightPackSet(self.netG_A)
         self.wstage = WgradStage(self.netG_A)
@@ -171,7 +180,7 @@ class PaletteTrainer:
             sl.index = self._index[id(sl.param)]
         self._sizes = [(p.numel() + 63) // 64 * 64 for p in self.flat.params]
         self.buckets = dp.GradBuckets(self.flat.offsets, self._sizes, self.flat.total, self._reduce_bucket,
-                                      n_buckets=comm_buckets)
+                                      n_buckets=comm_buckets, min_elems=comm_min_bucket)
         self._bucket_slots = [[sl for sl in self.wstage.slots if self.buckets.bucket_of[sl.index] == b]
                               for b in range(len(self.buckets.buckets))]
         self._bucket_loose = [[(p, v) for p, v in self._loose if self.buckets.bucket_of[self._index[id(p)]] == b]

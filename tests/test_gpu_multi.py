@@ -56,7 +56,7 @@ def _worker(rank, world, port, out):
         net = nets.build_palette_generator(**CFG)
         net.load_state_dict(O.init_params(cfg, seed), strict=False)
         return PaletteTrainer(net, lr=1e-3, optim="adamw", ema=True, ema_beta=0.9, device="cuda:%d" % rank,
-                              process_group=pg, cuda_graph=graph, graph_warmup=1)
+                              process_group=pg, cuda_graph=graph, graph_warmup=1, comm_min_bucket=1 << 16)
 
     def feed(tr, parts):
         cat = lambda xs: torch.cat(xs, dim=0)  # noqa: E731
@@ -75,8 +75,26 @@ def _worker(rank, world, port, out):
     if rank == 0:
         solo = trainer(50, pg=solo_groups[0])
         g_one = solo.reduced_gradient(**feed(solo, shards)).clone()
+        g_two = solo.reduced_gradient(**feed(solo, shards)).clone()   # the same evaluation again: run-to-run floor
         res["grad_rel"] = _rel_l2(g_dp.cpu(), g_one.cpu())
+        res["grad_floor"] = _rel_l2(g_two.cpu(), g_one.cpu())
         res["grad_norm"] = float(g_one.norm())
+    # ---- the exchange itself, exactly: known per-rank values through the bucket machinery (unpack / fold / one
+    # all-reduce per bucket on the communication stream / wait) must come back as their sum over the ranks, bit for bit
+    known = torch.arange(tr.flat.total, device="cuda", dtype=torch.float32).remainder_(1013.0) * (rank + 1)
+    tr.flat.rebind_grads()
+    tr.flat.grad.copy_(known)
+    tr.buckets.begin()
+    for i in reversed(range(len(tr.flat.params))):
+        tr.buckets.ready(i)
+    tr.buckets.finish()
+    tr.comm.wait()
+    torch.cuda.synchronize()
+    want = torch.arange(tr.flat.total, device="cuda", dtype=torch.float32).remainder_(1013.0) * sum(
+        r + 1 for r in range(world))
+    res["exchange_exact"] = bool(torch.equal(tr.flat.grad, want))
+    res["buckets"] = len(tr.buckets.buckets)
+    tr.flat.grad.zero_()
     # ---- three optimizer steps, eager
     for step in range(3):
         tr.optimize_parameters(**feed(tr, [_draws(O, cfg, 2000 + 10 * step + rank)]))
@@ -116,8 +134,11 @@ def test_two_gpu_gradient_and_replicas():
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     a, b = out[0], out[1]
     assert a["grad_norm"] > 0
-    # N-rank mean gradient == 1-rank gradient on the concatenated batch (split-K / statistics atomics reorder fp32 sums)
-    assert a["grad_rel"] < 2e-3, a["grad_rel"]
+    assert a["exchange_exact"] and b["exchange_exact"] and a["buckets"] > 1
+    # N-rank mean gradient == 1-rank gradient on the concatenated batch.  Not bit for bit: split-K / statistics atomics
+    # reorder fp32 sums, a flipped bf16 ulp is then amplified by the (chaotic, random-init) net — the bound is the
+    # run-to-run difference of the SAME one-GPU evaluation, measured here
+    assert a["grad_rel"] < max(2e-3, 3.0 * a["grad_floor"]), (a["grad_rel"], a["grad_floor"])
     for k in ("params", "exp_avg", "ema", "graph_params"):
         assert torch.equal(a[k], b[k]), "replicas differ in %s" % k
     assert a["graph_used"] and b["graph_used"] and a["finite"] and b["finite"]
