@@ -378,6 +378,11 @@ int launch_conv_halo(const jg_conv_desc* d, const jg_conv_epilogue* e, const voi
 int launch_conv_halo2(const jg_conv_desc* d, const jg_conv_epilogue* e, const void* x, const void* w_packed,
                       const float* bias, const void* residual, void* y, cudaStream_t stream, bool* fused);
 
+// Weight gradient of 3x3 convolutions on CTA pairs (conv_halo2.cu): raw accumulation into acc [9][Cin][Cout].
+int launch_wgrad_halo2(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* acc, cudaStream_t stream);
+// [R*S][Cin][Cout] accumulator -> OIHW gradient, dst = beta * dst + src (conv_halo.cu)
+int launch_unpack_hwio(const float* src, float* dst, int Cout, int Cin, int RS, float beta, cudaStream_t stream);
+
 // Fills the fused-GroupNorm fields of the kernel parameters from the C-ABI structs; returns the operand that travels
 // through the residual plumbing (the residual itself, or the GroupNorm input x of the gn_sums mode).
 inline const void* conv_apply_epilogue(ConvFwdParams& p, const jg_conv_desc* d, const jg_conv_epilogue* e,

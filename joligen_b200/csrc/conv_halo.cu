@@ -650,6 +650,13 @@ __global__ void unpack_hwio_kernel(const float* __restrict__ src, float* __restr
   dst[i] = beta == 0.f ? v : beta * dst[i] + v;
 }
 
+int launch_unpack_hwio(const float* src, float* dst, int Cout, int Cin, int RS, float beta, cudaStream_t stream) {
+  const long long total = (long long)Cout * Cin * RS;
+  unpack_hwio_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, dst, Cout, Cin, RS, beta);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
 template <int STAGES, int NCO>
 static int launch_wgrad_halo_one(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradHaloParams& p,
                                  cudaStream_t stream) {

@@ -447,4 +447,272 @@ int launch_conv_halo2(const jg_conv_desc* d, const jg_conv_epilogue* e, const vo
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient on CTA pairs (3x3 filters)
+// ------------------------------------------------------------------------------------------------
+// dW[tap][ci][co] += sum_pixels X[pixel + tap][ci] * dY[pixel][co]        (cf. wgrad_halo_kernel, conv_halo.cu)
+// Single-CTA limit this kernel removes: with a 128-channel co block (the MMA shape that runs at the full tensor rate)
+// a 3x3 filter needs 5 tap-pair accumulators x 128 columns = 640 > 512 TMEM columns, i.e. TWO passes over the
+// activations, the short second one L2-bound (profiles/r01_wgrad_taps.log).  A CTA pair has 2 x 512 columns.
+//
+// One tcgen05.mma.cta_group::2 carries ONE A descriptor that each CTA applies to its own shared memory.  So the two
+// CTAs stage the SAME 10 x 10 pixel halo-patch shape, but CTA 1's patch starts ONE IMAGE ROW LOWER: the window that is
+// filter tap (r, s) in CTA 0 is tap (r + 1, s) in CTA 1.  Per 64-pixel k-block, three M = 256 groups
+//     group     CTA 0 rows 0..63 | 64..127        CTA 1 rows 0..63 | 64..127      window origin, second-window distance
+//       0       (0,0)   (0,1)                      (1,0)   (1,1)                   0,  1 pixel
+//       1       (0,2)   (1,2)                      (1,2)*  (2,2)                   2,  10 pixels (one patch row)
+//       2       (2,0)   (2,1)                      (3,0)-  (3,1)-                  20, 1 pixel
+//   (* computed twice, CTA 1's copy is dropped; - outside the filter, dropped) cover all 9 taps in ONE pass with
+//   3 x 128 = 384 TMEM columns per CTA.  Each CTA stages HALF of the dY tile (64 of the 128 output channels: the B
+//   operand of cta_group::2 is split over the pair) — 20.8 KB per k-block and CTA instead of 28.8 KB.
+// Work item = (64-channel ci block, 128-channel co block, pixel range); split-K over pixel blocks; fp32
+// red.global.add.v4 into the [R*S][Cin][Cout] accumulator (layout code 0, like wgrad_halo_kernel).
+struct WgradHalo2Params {
+  int Cin, Cout, pad;
+  int x_stage_bytes;
+  int tiles_w, tiles_h, pix_blocks;
+  int cib, cob;
+  int ksplit, kb_per_split, total_items;
+  float* acc;
+};
+
+constexpr int kW2PW = 10, kW2PH = 10;  // 8 x 8 pixel k-block + the 3x3 halo
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgradThreads, 1)
+wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                   const WgradHalo2Params p) {
+  constexpr int NCO = 128;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr int DY_BYTES = 8192;  // 64 pixels x 64 channels (this CTA's half of the 128-channel dY tile)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = DY_BYTES + p.x_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(STAGES) * stage_bytes);
+  uint64_t* full = bars;            // the leader's are waited on
+  uint64_t* empty = bars + STAGES;  // per CTA (multicast commit)
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = tfull + 1;     // the leader's: 4 epilogue warps of each CTA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_ptr, TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t bytes = static_cast<uint32_t>(DY_BYTES + kW2PW * kW2PH * 128);
+      for (int item = pair_id; item < p.total_items; item += num_pairs) {
+        const int split = item % p.ksplit;
+        const int cob = (item / p.ksplit) % p.cob;
+        const int cib = item / (p.ksplit * p.cob);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.pix_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int tw = kb % p.tiles_w;
+          const int th = (kb / p.tiles_w) % p.tiles_h;
+          const int tn = kb / (p.tiles_w * p.tiles_h);
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * bytes);
+          const uint32_t lead = mapa_u32(smem_u32(&full[stage]), 0);
+          uint8_t* st = smem + static_cast<size_t>(stage) * stage_bytes;
+          tma_load_4d_2cta(st, &tmDY, lead, cob * NCO + static_cast<int>(rank) * 64, tw * 8, th * 8, tn);
+          // CTA 1's patch starts one image row lower (see the header): same shape, same shared-memory offsets
+          tma_load_4d_2cta(st + DY_BYTES, &tmX, lead, cib * 64, tw * 8 - p.pad, th * 8 - p.pad + static_cast<int>(rank), tn);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, NCO, 1, 1);
+      const uint32_t sbo_x = static_cast<uint32_t>(kW2PW * 128);
+      const uint64_t dy_desc0 = make_smem_desc_sw128(smem_u32(smem), 8192, 1024);
+      const uint64_t x_desc0 = make_smem_desc_sw128(smem_u32(smem) + DY_BYTES, 0, sbo_x);
+      // (window origin, distance to the second window) of the three groups, in pixels of the patch
+      const int g_off[3] = {0, 2, 2 * kW2PW};
+      const int g_lbo[3] = {1, kW2PW, 1};
+      uint64_t group_delta[3];
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+        group_delta[g] = static_cast<uint64_t>(g_off[g] * 8) | (static_cast<uint64_t>((g_lbo[g] * 8) & 0x3FFF) << 16);
+      const uint32_t kstep_x = (2 * sbo_x) >> 4;  // 16 pixels = two patch rows
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int item = pair_id; item < p.total_items; item += num_pairs) {
+        const int split = item % p.ksplit;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.pix_blocks);
+        mbar_wait(tempty, acc_phase ^ 1);
+        tc_fence_after();
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t st16 = static_cast<uint32_t>(stage * stage_bytes) >> 4;
+          const uint64_t dy_desc = dy_desc0 + st16;
+          const uint64_t x_desc = x_desc0 + st16;
+          const uint32_t first = kb > kb0 ? 1u : 0u;
+          if (elect_one()) {
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+              const uint64_t a_desc = x_desc + group_delta[g];
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_2cta(tmem_base + g * NCO, a_desc + k * kstep_x, dy_desc + k * 128, idesc,
+                               (first | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2cta(&empty[stage], 0x3);
+          }
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (elect_one()) umma_commit_2cta(tfull, 0x3);
+        __syncwarp();
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t acc_phase = 0;
+    const uint32_t tempty_lead = mapa_u32(smem_u32(tempty), 0);
+    // filter tap (r*3 + s) held by (group, cluster rank, row half); -1 = dropped (duplicate / outside the filter)
+    const int tap_of[3][2][2] = {{{0, 1}, {3, 4}}, {{2, 5}, {-1, 8}}, {{6, 7}, {-1, -1}}};
+    for (int item = pair_id; item < p.total_items; item += num_pairs) {
+      const int split = item % p.ksplit;
+      const int cob = (item / p.ksplit) % p.cob;
+      const int cib = item / (p.ksplit * p.cob);
+      const bool has_work = split * p.kb_per_split < p.pix_blocks;
+      const int ci = cib * 64 + (row & 63);
+      const int co0 = cob * NCO;
+      mbar_wait(tfull, acc_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        const int tap = tap_of[g][rank][row >> 6];
+        const bool ok = has_work && tap >= 0 && ci < p.Cin;
+        // (warp-uniform: rows 0..63 / 64..127 are whole warps) skip the TMEM reads of dropped windows altogether
+        if (tap_of[g][rank][0] < 0 && tap_of[g][rank][1] < 0) continue;
+        float* dst = p.acc + (static_cast<size_t>(tap < 0 ? 0 : tap) * p.Cin + ci) * p.Cout + co0;
+#pragma unroll 1
+        for (int c = 0; c < NCO; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * NCO + c, v);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int gg = 0; gg < 8; ++gg) {
+              if (co0 + c + gg * 4 < p.Cout)
+                red_add_v4f(dst + c + gg * 4, __uint_as_float(v[gg * 4]), __uint_as_float(v[gg * 4 + 1]),
+                            __uint_as_float(v[gg * 4 + 2]), __uint_as_float(v[gg * 4 + 3]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(tempty);
+        else mbar_arrive_cluster_relaxed(tempty_lead);
+      }
+      acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+  }
+}
+
+// Raw accumulation only (jg_conv2d_wgrad_acc semantics: acc is the caller's [9][Cin][Cout] fp32 accumulator, neither
+// zeroed nor unpacked here).  JG_ERR_UNSUPPORTED when the shape does not qualify.
+int launch_wgrad_halo2(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* acc,
+                       cudaStream_t stream) {
+  if (d->stride != 1 || d->R != 3 || d->S != 3 || d->pad != 1) return JG_ERR_UNSUPPORTED;
+  if (d->Wo % 8 != 0 || d->Ho % 8 != 0 || d->Cout < 128) return JG_ERR_UNSUPPORTED;
+  WgradHalo2Params p{};
+  p.Cin = d->Cin; p.Cout = d->Cout; p.pad = d->pad;
+  p.x_stage_bytes = (kW2PW * kW2PH * 128 + 1023) / 1024 * 1024;
+  p.tiles_w = d->Wo / 8;
+  p.tiles_h = d->Ho / 8;
+  p.pix_blocks = p.tiles_w * p.tiles_h * d->N;
+  p.cib = ceil_div(d->Cin, 64);
+  p.cob = ceil_div(d->Cout, 128);
+  const int items = p.cib * p.cob;
+  const int pairs = num_sms() / 2;
+  int ksplit = pairs / items;
+  if (ksplit < 1) ksplit = 1;
+  const int max_split = p.pix_blocks / 8 > 0 ? p.pix_blocks / 8 : 1;
+  if (ksplit > max_split) ksplit = max_split;
+  p.kb_per_split = ceil_div(p.pix_blocks, ksplit);
+  p.ksplit = ceil_div(p.pix_blocks, p.kb_per_split);
+  p.total_items = items * p.ksplit;
+  p.acc = acc;
+
+  CUtensorMap tmDY, tmX;
+  int rc;
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
+    uint64_t strides[3] = {(uint64_t)lddy * 2, (uint64_t)d->Wo * lddy * 2, (uint64_t)d->Ho * d->Wo * lddy * 2};
+    uint32_t box[4] = {64, 8, 8, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    rc = make_tmap_bf16(&tmDY, dy, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t strides[3] = {(uint64_t)d->ldx * 2, (uint64_t)d->W * d->ldx * 2, (uint64_t)d->H * d->W * d->ldx * 2};
+    uint32_t box[4] = {64, (uint32_t)kW2PW, (uint32_t)kW2PH, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    rc = make_tmap_bf16(&tmX, x, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  constexpr int STAGES = 9;
+  const int smem = STAGES * (8192 + p.x_stage_bytes) + (2 * STAGES + 2) * 8 + 16 + 1024;
+  JG_CHECK(smem <= 232448, JG_ERR_INVALID, "wgrad_halo2: smem %d too large", smem);
+  static bool attr_done = false;
+  if (!attr_done) {
+    JG_CUDA(cudaFuncSetAttribute(wgrad_halo2_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  int grid_pairs = pairs < p.total_items ? pairs : p.total_items;
+  wgrad_halo2_kernel<STAGES><<<2 * grid_pairs, kWgradThreads, smem, stream>>>(tmDY, tmX, p);
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
 }  // namespace jg

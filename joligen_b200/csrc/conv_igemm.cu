@@ -611,6 +611,17 @@ static int conv2d_wgrad_impl(const jg_conv_desc* d, const void* x, const void* d
   JG_CHECK(x && dy && ws, JG_ERR_INVALID, "conv_wgrad: null pointer");
   JG_CHECK(lddy % 8 == 0 && lddy >= d->Cout, JG_ERR_INVALID, "conv_wgrad: bad lddy %d", lddy);
   static const bool no_halo = getenv("JG_NO_HALO") != nullptr;
+  // 3x3, Cout >= 128: CTA pairs cover all 9 taps in one pass at the 128-channel MMA shape (JG_WGRAD_2CTA=0: off)
+  static const bool wpairs = getenv("JG_WGRAD_2CTA") == nullptr || atoi(getenv("JG_WGRAD_2CTA")) != 0;
+  if (!no_halo && wpairs) {
+    if (dw_oihw) JG_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)d->R * d->S * d->Cin * d->Cout, stream));
+    rc = launch_wgrad_halo2(d, x, dy, lddy, ws, stream);
+    if (rc != JG_ERR_UNSUPPORTED) {
+      if (layout) *layout = 0;
+      if (rc == JG_OK && dw_oihw) rc = launch_unpack_hwio(ws, dw_oihw, d->Cout, d->Cin, d->R * d->S, beta, stream);
+      return rc;
+    }
+  }
   if (!no_halo) {
     rc = launch_wgrad_halo(d, x, dy, lddy, ws, dw_oihw, beta, stream);
     if (rc != JG_ERR_UNSUPPORTED) {

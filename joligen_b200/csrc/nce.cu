@@ -239,236 +239,276 @@ patch_nce_bwd_k_kernel(const float* __restrict__ q, const float* __restrict__ k,
 //   C_ij = <q_i, k_j>, diagonal -10;  K = exp(C);  u = v = 1;  repeat: u_i = 1 / sum_j K_ij v_j,  v_j = 1 / sum_i u_i K_ij
 //   f_ij = u_i K_ij v_j (popt - 1) + 1e-8;   out_i = [ <q_i, k_i> / T,  C_ij / T + log f_ij (diagonal: -10 / T) ]
 //   loss_i = logsumexp(out_i) - out_i[0]
-// The reference differentiates through the iterations w.r.t. q (k is detached inside the OT): the backward kernel runs
-// the reverse sweep over the stored u^t, v^t.  One CTA per group (image); C, K (and, backward, the adjoint of K and the
-// direct softmax weights) live in an L2-resident workspace of P x P floats each.  STATUS: compiled, NOT yet run on
-// hardware; the algorithm (forward + reverse sweep) was checked against autograd on the CPU in fp64.
+// The reference differentiates through the iterations w.r.t. q (k is detached inside the OT): the backward runs the
+// reverse sweep over the stored u^t, v^t.  C, K (and, backward, the adjoint of K and the direct softmax weights) live
+// in an L2-resident workspace of P x P floats per group (image).
+//
+// Launch structure: the first version ran ONE CTA per image through all 50 iterations (two dependent P x P mat-vec
+// products each, K streamed from L2 by 256 threads): 5.4 ms forward and 13.3 ms backward per call, 187 of the 229 ms of
+// a CUT step (profiles/r02_bench_cfg3.json).  Now every phase is its own grid-wide launch — a warp per matrix row for
+// the row products, a block per 32 columns for the column products — so each of the ~100 sequential half-iterations
+// costs one small launch (~3 us) instead of a latency-bound sweep by a single CTA, and the backward no longer updates
+// the P x P adjoint in every iteration: Kbar = Kbar_0 + sum_t (u^t (x) sbar^t + rbar^t (x) v^{t-1}) is assembled once,
+// in the final pass that consumes it, from the stored vectors.
 constexpr int kMonceThreads = 256;
+constexpr int kMonceWarps = kMonceThreads / 32;
 
-__device__ __forceinline__ float row_dot_K(const float* __restrict__ row, const float* __restrict__ vec, int P, int lane) {
-  float s = 0.f;
-  for (int j = lane; j < P; j += 32) s = fmaf(row[j], vec[j], s);
-  return warp_sum_nce(s);
-}
-
+// C = q k^T (diagonal kept: the loss pass overrides it), K = exp(C) with exp(-10) on the diagonal; V[0] = 1.
+// grid (ceil(P / warps), G): one warp per row i.
 __global__ void __launch_bounds__(kMonceThreads)
-monce_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, int P, int D, float invT, float popt1,
-                 int iters, float* __restrict__ Cmat, float* __restrict__ Kmat, float* __restrict__ U,
-                 float* __restrict__ V, float* __restrict__ loss, float* __restrict__ lse) {
-  extern __shared__ float sm[];  // u [P], v [P]
-  float* su = sm;
-  float* sv = sm + P;
-  const int g = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kMonceThreads / 32;
+monce_ck_kernel(const float* __restrict__ q, const float* __restrict__ k, int P, int D, int iters,
+                float* __restrict__ Cmat, float* __restrict__ Kmat, float* __restrict__ V) {
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * kMonceWarps + warp;
   const int per = D / 32;
+  if (i >= P) return;
   const float* qg = q + (size_t)g * P * D;
   const float* kg = k + (size_t)g * P * D;
-  float* Cg = Cmat + (size_t)g * P * P;
-  float* Kg = Kmat + (size_t)g * P * P;
-  float* Ug = U + (size_t)g * iters * P;
-  float* Vg = V + (size_t)g * (iters + 1) * P;
-  // C and K
-  for (int i = warp; i < P; i += nwarps) {
-    float qr[kNceMaxPerLane], kr[kNceMaxPerLane];
+  float qr[kNceMaxPerLane], kr[kNceMaxPerLane];
 #pragma unroll
-    for (int e = 0; e < kNceMaxPerLane; ++e)
-      if (e < per) qr[e] = qg[(size_t)i * D + lane + 32 * e];
-    for (int j = 0; j < P; ++j) {
-      const float c = nce_dot(qr, kg + (size_t)j * D, kr, per, lane);
-      if (lane == 0) {
-        Cg[(size_t)i * P + j] = c;
-        Kg[(size_t)i * P + j] = __expf(j == i ? -10.f : c);
-      }
-    }
-  }
-  for (int j = threadIdx.x; j < P; j += kMonceThreads) {
-    su[j] = 1.f;
-    sv[j] = 1.f;
-    Vg[j] = 1.f;
-  }
-  __syncthreads();
-  // Sinkhorn scalings
-  for (int t = 0; t < iters; ++t) {
-    for (int i = warp; i < P; i += nwarps) {
-      const float r = row_dot_K(Kg + (size_t)i * P, sv, P, lane);
-      if (lane == 0) {
-        su[i] = 1.f / r;
-        Ug[(size_t)t * P + i] = 1.f / r;
-      }
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < P; j += kMonceThreads) {
-      float s = 0.f;
-      for (int i = 0; i < P; ++i) s = fmaf(su[i], Kg[(size_t)i * P + j], s);
-      sv[j] = 1.f / s;
-      Vg[(size_t)(t + 1) * P + j] = 1.f / s;
-    }
-    __syncthreads();
-  }
-  // loss
-  for (int i = warp; i < P; i += nwarps) {
-    float qr[kNceMaxPerLane], kr[kNceMaxPerLane];
-#pragma unroll
-    for (int e = 0; e < kNceMaxPerLane; ++e)
-      if (e < per) qr[e] = qg[(size_t)i * D + lane + 32 * e];
-    const float pos = nce_dot(qr, kg + (size_t)i * D, kr, per, lane) * invT;
-    const float ui = su[i];
-    float m = pos;
-    for (int j = lane; j < P; j += 32) {
-      const float f = ui * Kg[(size_t)i * P + j] * sv[j] * popt1 + 1e-8f;
-      const float l = (j == i) ? -10.f * invT : Cg[(size_t)i * P + j] * invT + __logf(f);
-      m = fmaxf(m, l);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float s = 0.f;
-    for (int j = lane; j < P; j += 32) {
-      const float f = ui * Kg[(size_t)i * P + j] * sv[j] * popt1 + 1e-8f;
-      const float l = (j == i) ? -10.f * invT : Cg[(size_t)i * P + j] * invT + __logf(f);
-      s += __expf(l - m);
-    }
-    s = warp_sum_nce(s) + __expf(pos - m);
-    const float lz = m + __logf(s);
+  for (int e = 0; e < kNceMaxPerLane; ++e)
+    if (e < per) qr[e] = qg[(size_t)i * D + lane + 32 * e];
+  float* Cg = Cmat + ((size_t)g * P + i) * P;
+  float* Kg = Kmat + ((size_t)g * P + i) * P;
+  for (int j = 0; j < P; ++j) {
+    const float c = nce_dot(qr, kg + (size_t)j * D, kr, per, lane);
     if (lane == 0) {
-      lse[(size_t)g * P + i] = lz;
-      loss[(size_t)g * P + i] = lz - pos;
+      Cg[j] = c;
+      Kg[j] = __expf(j == i ? -10.f : c);
+    }
+  }
+  if (lane == 0) V[(size_t)g * (iters + 1) * P + i] = 1.f;
+}
+
+// out[g][i] = post( sum_j M[g][i][j] * vec[g][j] ), one warp per row.  mode 0 (forward u-step): out = 1 / sum.
+// mode 1 (backward): vec_j = -vbar_j * vt_j^2 (= sbar^t, also stored), out = rbar_i = -(ubar_i + sum) * ut_i^2.
+__global__ void __launch_bounds__(kMonceThreads)
+monce_rows_kernel(const float* __restrict__ Kmat, int P, int mode, const float* __restrict__ vec,
+                  const float* __restrict__ vt, const float* __restrict__ ut, const float* __restrict__ ubar,
+                  float* __restrict__ sbar_out, float* __restrict__ out, size_t vec_stride, size_t vt_stride,
+                  size_t ut_stride, size_t out_stride) {
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * kMonceWarps + warp;
+  if (i >= P) return;
+  const float* row = Kmat + ((size_t)g * P + i) * P;
+  const float* v = vec + (size_t)g * vec_stride;
+  float s = 0.f;
+  if (mode == 0) {
+    for (int j = lane; j < P; j += 32) s = fmaf(row[j], v[j], s);
+    s = warp_sum_nce(s);
+    if (lane == 0) out[(size_t)g * out_stride + i] = 1.f / s;
+  } else {
+    const float* vtg = vt + (size_t)g * vt_stride;
+    for (int j = lane; j < P; j += 32) {
+      const float sb = -v[j] * vtg[j] * vtg[j];
+      if (i == 0) sbar_out[(size_t)g * out_stride + j] = sb;  // (row 0's warp records sbar^t for the final pass)
+      s = fmaf(row[j], sb, s);
+    }
+    s = warp_sum_nce(s);
+    if (lane == 0) {
+      const float ui = ut[(size_t)g * ut_stride + i];
+      const float ub = ubar ? ubar[(size_t)g * P + i] : 0.f;
+      out[(size_t)g * out_stride + i] = -(ub + s) * ui * ui;
     }
   }
 }
 
+// out[g][j] = post( sum_i vec[g][i] * M[g][i][j] ): block (32 columns x 8 row slices).  mode 0: out = 1 / sum; 1: sum.
 __global__ void __launch_bounds__(kMonceThreads)
-monce_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ lse,
-                 const float* __restrict__ gout, int P, int D, float invT, float popt1, int iters,
-                 const float* __restrict__ Cmat, const float* __restrict__ Kmat, const float* __restrict__ U,
-                 const float* __restrict__ V, float* __restrict__ Kbar, float* __restrict__ Wmat,
-                 float* __restrict__ dq, float* __restrict__ dk) {
-  extern __shared__ float sm[];  // ubar, vbar, sbar, rbar, p0 : 5 * P
-  float* ubar = sm;
-  float* vbar = sm + P;
-  float* sbar = sm + 2 * P;
-  float* rbar = sm + 3 * P;
-  float* p0s = sm + 4 * P;
-  const int g = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kMonceThreads / 32;
+monce_cols_kernel(const float* __restrict__ Kmat, int P, int mode, const float* __restrict__ vec, float* __restrict__ out,
+                  size_t vec_stride, size_t out_stride) {
+  __shared__ float part[kMonceWarps][32];
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  const float* M = Kmat + (size_t)g * P * P;
+  const float* v = vec + (size_t)g * vec_stride;
+  float s = 0.f;
+  if (j < P)
+    for (int i = slice; i < P; i += kMonceWarps) s = fmaf(v[i], M[(size_t)i * P + j], s);
+  part[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && j < P) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kMonceWarps; ++w) t += part[w][lane];
+    out[(size_t)g * out_stride + j] = mode == 0 ? 1.f / t : t;
+  }
+}
+
+// loss_i = logsumexp([pos_i, C_ij / T + log f_ij (j != i), -10 / T (j == i)]) - pos_i, f = u_i K_ij v_j (popt-1) + 1e-8
+__global__ void __launch_bounds__(kMonceThreads)
+monce_loss_kernel(const float* __restrict__ q, const float* __restrict__ k, int P, int D, float invT, float popt1,
+                  const float* __restrict__ Cmat, const float* __restrict__ Kmat, const float* __restrict__ uF,
+                  const float* __restrict__ vF, size_t u_stride, size_t v_stride, float* __restrict__ loss,
+                  float* __restrict__ lse) {
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * kMonceWarps + warp;
   const int per = D / 32;
+  if (i >= P) return;
   const float* qg = q + (size_t)g * P * D;
   const float* kg = k + (size_t)g * P * D;
-  const float* Cg = Cmat + (size_t)g * P * P;
-  const float* Kg = Kmat + (size_t)g * P * P;
+  const float* Cg = Cmat + ((size_t)g * P + i) * P;
+  const float* Kg = Kmat + ((size_t)g * P + i) * P;
+  const float* sv = vF + (size_t)g * v_stride;
+  float qr[kNceMaxPerLane], kr[kNceMaxPerLane];
+#pragma unroll
+  for (int e = 0; e < kNceMaxPerLane; ++e)
+    if (e < per) qr[e] = qg[(size_t)i * D + lane + 32 * e];
+  const float pos = nce_dot(qr, kg + (size_t)i * D, kr, per, lane) * invT;
+  const float ui = uF[(size_t)g * u_stride + i];
+  float m = pos;
+  for (int j = lane; j < P; j += 32) {
+    const float f = ui * Kg[j] * sv[j] * popt1 + 1e-8f;
+    const float l = (j == i) ? -10.f * invT : Cg[j] * invT + __logf(f);
+    m = fmaxf(m, l);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int j = lane; j < P; j += 32) {
+    const float f = ui * Kg[j] * sv[j] * popt1 + 1e-8f;
+    const float l = (j == i) ? -10.f * invT : Cg[j] * invT + __logf(f);
+    s += __expf(l - m);
+  }
+  s = warp_sum_nce(s) + __expf(pos - m);
+  const float lz = m + __logf(s);
+  if (lane == 0) {
+    lse[(size_t)g * P + i] = lz;
+    loss[(size_t)g * P + i] = lz - pos;
+  }
+}
+
+// Backward, first pass (warp per row): direct softmax weights W_ij = g_i p_ij / T, Kbar_0 = Fbar_ij u_i v_j with
+// Fbar_ij = g_i p_ij (popt-1) / f_ij, ubar_i = sum_j Fbar_ij K_ij v_j, vbar_j += Fbar_ij u_i K_ij (global atomics),
+// p0_i = exp(pos_i - lse_i).
+__global__ void __launch_bounds__(kMonceThreads)
+monce_bwd_init_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ lse,
+                      const float* __restrict__ gout, int P, int D, float invT, float popt1,
+                      const float* __restrict__ Cmat, const float* __restrict__ Kmat, const float* __restrict__ uF,
+                      const float* __restrict__ vF, size_t u_stride, size_t v_stride, float* __restrict__ Kbar,
+                      float* __restrict__ Wmat, float* __restrict__ ubar, float* __restrict__ vbar,
+                      float* __restrict__ p0s) {
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * kMonceWarps + warp;
+  const int per = D / 32;
+  if (i >= P) return;
+  const float* qg = q + (size_t)g * P * D;
+  const float* kg = k + (size_t)g * P * D;
+  const size_t rowoff = ((size_t)g * P + i) * P;
+  const float* sv = vF + (size_t)g * v_stride;
+  float qr[kNceMaxPerLane], kr[kNceMaxPerLane];
+#pragma unroll
+  for (int e = 0; e < kNceMaxPerLane; ++e)
+    if (e < per) qr[e] = qg[(size_t)i * D + lane + 32 * e];
+  const float pos = nce_dot(qr, kg + (size_t)i * D, kr, per, lane) * invT;
+  const float ui = uF[(size_t)g * u_stride + i], gi = gout[(size_t)g * P + i], lzi = lse[(size_t)g * P + i];
+  float ub = 0.f;
+  for (int j = lane; j < P; j += 32) {
+    const float kij = Kmat[rowoff + j];
+    const float f = ui * kij * sv[j] * popt1 + 1e-8f;
+    float w = 0.f, fb = 0.f;
+    if (j != i) {
+      const float pij = __expf(Cmat[rowoff + j] * invT + __logf(f) - lzi);
+      w = gi * pij * invT;
+      fb = gi * pij * popt1 / f;
+    }
+    Wmat[rowoff + j] = w;
+    Kbar[rowoff + j] = fb * ui * sv[j];
+    ub = fmaf(fb * kij, sv[j], ub);
+    atomicAdd(&vbar[(size_t)g * P + j], fb * ui * kij);
+  }
+  ub = warp_sum_nce(ub);
+  if (lane == 0) {
+    ubar[(size_t)g * P + i] = ub;
+    p0s[(size_t)g * P + i] = __expf(pos - lzi);
+  }
+}
+
+// Backward, last pass (warp per row i): Kbar_ij = Kbar_0 + sum_t (u^t_i sbar^t_j + rbar^t_i v^{t}_j),
+// dq_i = g_i (p0_i - 1) / T k_i + sum_{j != i} (W_ij + Kbar_ij K_ij) k_j
+__global__ void __launch_bounds__(kMonceThreads)
+monce_bwd_dq_kernel(const float* __restrict__ k, const float* __restrict__ gout, int P, int D, float invT, int iters,
+                    const float* __restrict__ Kmat, const float* __restrict__ Kbar, const float* __restrict__ Wmat,
+                    const float* __restrict__ U, const float* __restrict__ V, const float* __restrict__ SB,
+                    const float* __restrict__ RB, const float* __restrict__ p0s, float* __restrict__ dq) {
+  extern __shared__ float sm[];  // per warp: u^t_i and rbar^t_i for all t: 2 * iters floats
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * kMonceWarps + warp;
+  const int per = D / 32;
+  if (i >= P) return;
+  float* ui_t = sm + (size_t)warp * 2 * iters;
+  float* rb_t = ui_t + iters;
   const float* Ug = U + (size_t)g * iters * P;
   const float* Vg = V + (size_t)g * (iters + 1) * P;
-  float* Kb = Kbar + (size_t)g * P * P;
-  float* Wg = Wmat + (size_t)g * P * P;
-  const float* lz = lse + (size_t)g * P;
-  const float* go = gout + (size_t)g * P;
-  const float* uF = Ug + (size_t)(iters - 1) * P;  // final u, v
-  const float* vF = Vg + (size_t)iters * P;
-  for (int j = threadIdx.x; j < P; j += kMonceThreads) vbar[j] = 0.f;
-  __syncthreads();
-  // softmax weights: W_ij = g_i p_ij / T (direct term), Fbar_ij = g_i p_ij (popt-1) / f_ij; ubar, Kbar initialised
-  for (int i = warp; i < P; i += nwarps) {
-    float qr[kNceMaxPerLane], kr[kNceMaxPerLane];
-#pragma unroll
-    for (int e = 0; e < kNceMaxPerLane; ++e)
-      if (e < per) qr[e] = qg[(size_t)i * D + lane + 32 * e];
-    const float pos = nce_dot(qr, kg + (size_t)i * D, kr, per, lane) * invT;
-    const float ui = uF[i], gi = go[i], lzi = lz[i];
-    float ub = 0.f;
-    for (int j = lane; j < P; j += 32) {
-      const float kij = Kg[(size_t)i * P + j];
-      const float f = ui * kij * vF[j] * popt1 + 1e-8f;
-      float w = 0.f, fb = 0.f;
-      if (j != i) {
-        const float pij = __expf(Cg[(size_t)i * P + j] * invT + __logf(f) - lzi);
-        w = gi * pij * invT;
-        fb = gi * pij * popt1 / f;
-      }
-      Wg[(size_t)i * P + j] = w;
-      Kb[(size_t)i * P + j] = fb * ui * vF[j];
-      ub = fmaf(fb * kij, vF[j], ub);
-      atomicAdd(&vbar[j], fb * ui * kij);
-    }
-    ub = warp_sum_nce(ub);
-    if (lane == 0) {
-      ubar[i] = ub;
-      p0s[i] = __expf(pos - lzi);
-    }
+  const float* SBg = SB + (size_t)g * iters * P;
+  const float* RBg = RB + (size_t)g * iters * P;
+  for (int t = lane; t < iters; t += 32) {
+    ui_t[t] = Ug[(size_t)t * P + i];
+    rb_t[t] = RBg[(size_t)t * P + i];
   }
-  __syncthreads();
-  // reverse sweep over the Sinkhorn iterations
-  for (int t = iters - 1; t >= 0; --t) {
-    const float* ut = Ug + (size_t)t * P;
-    const float* vt = Vg + (size_t)(t + 1) * P;
-    const float* vp = Vg + (size_t)t * P;
-    for (int j = threadIdx.x; j < P; j += kMonceThreads) sbar[j] = -vbar[j] * vt[j] * vt[j];
-    __syncthreads();
-    for (int i = warp; i < P; i += nwarps) {
-      const float ui = ut[i];
-      float acc = 0.f;
-      for (int j = lane; j < P; j += 32) {
-        const float sb = sbar[j];
-        acc = fmaf(Kg[(size_t)i * P + j], sb, acc);
-        Kb[(size_t)i * P + j] += ui * sb;
-      }
-      acc = warp_sum_nce(acc);
-      if (lane == 0) {
-        const float ubt = ubar[i] + acc;
-        rbar[i] = -ubt * ui * ui;
-        ubar[i] = 0.f;
-      }
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < P; j += kMonceThreads) {
-      const float vpj = vp[j];
-      float acc = 0.f;
-      for (int i = 0; i < P; ++i) {
-        const float rb = rbar[i];
-        acc = fmaf(Kg[(size_t)i * P + j], rb, acc);
-        Kb[(size_t)i * P + j] += rb * vpj;
-      }
-      vbar[j] = acc;
-    }
-    __syncthreads();
-  }
-  // dq_i = g_i (p0 - 1) / T k_i + sum_j (W_ij + Kbar_ij K_ij) k_j   (the Sinkhorn branch reaches q only)
-  for (int i = warp; i < P; i += nwarps) {
-    float kr[kNceMaxPerLane], acc[kNceMaxPerLane];
-    const float c0 = go[i] * (p0s[i] - 1.f) * invT;
+  __syncwarp();
+  const float* kg = k + (size_t)g * P * D;
+  const size_t rowoff = ((size_t)g * P + i) * P;
+  float kr[kNceMaxPerLane], acc[kNceMaxPerLane];
+  const float c0 = gout[(size_t)g * P + i] * (p0s[(size_t)g * P + i] - 1.f) * invT;
 #pragma unroll
-    for (int e = 0; e < kNceMaxPerLane; ++e)
-      if (e < per) acc[e] = c0 * kg[(size_t)i * D + lane + 32 * e];
-    for (int j = 0; j < P; ++j) {
-      if (j == i) continue;
-      const float c = Wg[(size_t)i * P + j] + Kb[(size_t)i * P + j] * Kg[(size_t)i * P + j];
+  for (int e = 0; e < kNceMaxPerLane; ++e)
+    if (e < per) acc[e] = c0 * kg[(size_t)i * D + lane + 32 * e];
+  // each lane assembles the coefficient of 1 of every 32 columns, then the warp walks the columns together
+  for (int j0 = 0; j0 < P; j0 += 32) {
+    const int jl = j0 + lane;
+    float c = 0.f;
+    if (jl < P && jl != i) {
+      float kb = Kbar[rowoff + jl];
+      for (int t = 0; t < iters; ++t)
+        kb = fmaf(ui_t[t], SBg[(size_t)t * P + jl], fmaf(rb_t[t], Vg[(size_t)t * P + jl], kb));
+      c = Wmat[rowoff + jl] + kb * Kmat[rowoff + jl];
+    }
+    for (int l = 0; l < 32 && j0 + l < P; ++l) {
+      const float cj = __shfl_sync(0xffffffffu, c, l);
+      if (cj == 0.f) continue;
 #pragma unroll
       for (int e = 0; e < kNceMaxPerLane; ++e) {
         if (e < per) {
-          kr[e] = kg[(size_t)j * D + lane + 32 * e];
-          acc[e] = fmaf(c, kr[e], acc[e]);
+          kr[e] = kg[(size_t)(j0 + l) * D + lane + 32 * e];
+          acc[e] = fmaf(cj, kr[e], acc[e]);
         }
       }
     }
+  }
+#pragma unroll
+  for (int e = 0; e < kNceMaxPerLane; ++e)
+    if (e < per) dq[((size_t)g * P + i) * D + lane + 32 * e] = acc[e];
+}
+
+// dk_j = sum_i W_ij q_i (warp per column j)
+__global__ void __launch_bounds__(kMonceThreads)
+monce_bwd_dk_kernel(const float* __restrict__ q, int P, int D, const float* __restrict__ Wmat, float* __restrict__ dk) {
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * kMonceWarps + warp;
+  const int per = D / 32;
+  if (j >= P) return;
+  const float* qg = q + (size_t)g * P * D;
+  const float* Wg = Wmat + (size_t)g * P * P;
+  float acc[kNceMaxPerLane];
+#pragma unroll
+  for (int e = 0; e < kNceMaxPerLane; ++e) acc[e] = 0.f;
+  for (int i = 0; i < P; ++i) {
+    const float w = Wg[(size_t)i * P + j];
 #pragma unroll
     for (int e = 0; e < kNceMaxPerLane; ++e)
-      if (e < per) dq[((size_t)g * P + i) * D + lane + 32 * e] = acc[e];
+      if (e < per) acc[e] = fmaf(w, qg[(size_t)i * D + lane + 32 * e], acc[e]);
   }
-  // dk_j = sum_i W_ij q_i
-  if (dk) {
-    for (int j = warp; j < P; j += nwarps) {
-      float acc[kNceMaxPerLane];
 #pragma unroll
-      for (int e = 0; e < kNceMaxPerLane; ++e) acc[e] = 0.f;
-      for (int i = 0; i < P; ++i) {
-        const float w = Wg[(size_t)i * P + j];
-#pragma unroll
-        for (int e = 0; e < kNceMaxPerLane; ++e)
-          if (e < per) acc[e] = fmaf(w, qg[(size_t)i * D + lane + 32 * e], acc[e]);
-      }
-#pragma unroll
-      for (int e = 0; e < kNceMaxPerLane; ++e)
-        if (e < per) dk[((size_t)g * P + j) * D + lane + 32 * e] = acc[e];
-    }
-  }
+  for (int e = 0; e < kNceMaxPerLane; ++e)
+    if (e < per) dk[((size_t)g * P + j) * D + lane + 32 * e] = acc[e];
 }
 
 }  // namespace
@@ -566,17 +606,17 @@ extern "C" int jg_patch_nce_bwd(const float* q, const float* k, const float* lse
 
 static int monce_check(const float* q, const float* k, int G, int P, int D, float T, int iters, const char* what) {
   if (int rc = nce_check(q, k, G, P, D, T, what)) return rc;
-  JG_CHECK(P <= 1024 && iters > 0 && iters <= 1000, JG_ERR_UNSUPPORTED,
-           "%s: P=%d (one CTA per group: at most 1024 patches) iters=%d", what, P, iters);
+  JG_CHECK(P <= 4096 && iters > 0 && iters <= 1000, JG_ERR_UNSUPPORTED, "%s: P=%d iters=%d", what, P, iters);
   return JG_OK;
 }
 
+// ws layout: C [G,P,P] | K [G,P,P] | U [G,iters,P] | V [G,iters+1,P] | (backward) Kbar [G,P,P] | W [G,P,P] |
+//            SB [G,iters,P] | RB [G,iters,P] | ubar [G,P] | vbar [G,P] | p0 [G,P]
 extern "C" size_t jg_monce_ws_floats(int G, int P, int iters, int backward) {
   const size_t pp = (size_t)G * P * P;
-  return (backward ? 4 : 2) * pp + (size_t)G * (2 * iters + 1) * P;
+  return (backward ? 4 : 2) * pp + (size_t)G * (2 * iters + 1) * P + (backward ? (size_t)G * (2 * iters + 3) * P : 0);
 }
 
-// ws layout: C [G,P,P] | K [G,P,P] | U [G,iters,P] | V [G,iters+1,P] | (backward only) Kbar [G,P,P] | W [G,P,P]
 extern "C" int jg_monce_fwd(const float* q, const float* k, int G, int P, int D, float T, int num_patches_opt, int iters,
                             float* ws, float* loss, float* lse, jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -587,9 +627,21 @@ extern "C" int jg_monce_fwd(const float* q, const float* k, int G, int P, int D,
   float* Km = ws + pp;
   float* U = ws + 2 * pp;
   float* V = U + (size_t)G * iters * P;
-  monce_fwd_kernel<<<G, kMonceThreads, 2 * P * sizeof(float), stream>>>(q, k, P, D, 1.f / T,
-                                                                        (float)(num_patches_opt - 1), iters, Cm, Km, U,
-                                                                        V, loss, lse);
+  const dim3 rows(ceil_div(P, kMonceWarps), G), cols(ceil_div(P, 32), G);
+  const size_t us = (size_t)iters * P, vs = (size_t)(iters + 1) * P;
+  monce_ck_kernel<<<rows, kMonceThreads, 0, stream>>>(q, k, P, D, iters, Cm, Km, V);
+  JG_LAUNCH_CHECK();
+  for (int t = 0; t < iters; ++t) {
+    // u^t = 1 / (K v^t);  v^{t+1} = 1 / (K^T u^t)
+    monce_rows_kernel<<<rows, kMonceThreads, 0, stream>>>(Km, P, 0, V + (size_t)t * P, nullptr, nullptr, nullptr, nullptr,
+                                                         U + (size_t)t * P, vs, 0, 0, us);
+    JG_LAUNCH_CHECK();
+    monce_cols_kernel<<<cols, kMonceThreads, 0, stream>>>(Km, P, 0, U + (size_t)t * P, V + (size_t)(t + 1) * P, us, vs);
+    JG_LAUNCH_CHECK();
+  }
+  monce_loss_kernel<<<rows, kMonceThreads, 0, stream>>>(q, k, P, D, 1.f / T, (float)(num_patches_opt - 1), Cm, Km,
+                                                       U + (size_t)(iters - 1) * P, V + (size_t)iters * P, us, vs, loss,
+                                                       lse);
   JG_LAUNCH_CHECK();
   return JG_OK;
 }
@@ -607,9 +659,38 @@ extern "C" int jg_monce_bwd(const float* q, const float* k, const float* lse, co
   float* V = U + (size_t)G * iters * P;
   float* Kb = V + (size_t)G * (iters + 1) * P;
   float* Wm = Kb + pp;
-  monce_bwd_kernel<<<G, kMonceThreads, 5 * P * sizeof(float), stream>>>(q, k, lse, grad_loss, P, D, 1.f / T,
-                                                                        (float)(num_patches_opt - 1), iters, Cm, Km, U,
-                                                                        V, Kb, Wm, dq, dk);
+  float* SB = Wm + pp;
+  float* RB = SB + (size_t)G * iters * P;
+  float* ubar = RB + (size_t)G * iters * P;
+  float* vbar = ubar + (size_t)G * P;
+  float* p0s = vbar + (size_t)G * P;
+  const dim3 rows(ceil_div(P, kMonceWarps), G), cols(ceil_div(P, 32), G);
+  const size_t us = (size_t)iters * P, vs = (size_t)(iters + 1) * P;
+  JG_CUDA(cudaMemsetAsync(vbar, 0, sizeof(float) * (size_t)G * P, stream));
+  monce_bwd_init_kernel<<<rows, kMonceThreads, 0, stream>>>(q, k, lse, grad_loss, P, D, 1.f / T,
+                                                           (float)(num_patches_opt - 1), Cm, Km,
+                                                           U + (size_t)(iters - 1) * P, V + (size_t)iters * P, us, vs, Kb,
+                                                           Wm, ubar, vbar, p0s);
   JG_LAUNCH_CHECK();
+  // reverse sweep: sbar^t = -vbar v^{t+1}^2;  rbar^t = -(ubar + K sbar^t) u^t^2 (ubar only in the first step);
+  // vbar <- K^T rbar^t.  The rank-1 updates of Kbar are applied in the final pass from the stored sbar^t / rbar^t.
+  for (int t = iters - 1; t >= 0; --t) {
+    monce_rows_kernel<<<rows, kMonceThreads, 0, stream>>>(Km, P, 1, vbar, V + (size_t)(t + 1) * P, U + (size_t)t * P,
+                                                         t == iters - 1 ? ubar : nullptr, SB + (size_t)t * P,
+                                                         RB + (size_t)t * P, (size_t)P, vs, us, us);
+    JG_LAUNCH_CHECK();
+    monce_cols_kernel<<<cols, kMonceThreads, 0, stream>>>(Km, P, 1, RB + (size_t)t * P, vbar, us, (size_t)P);
+    JG_LAUNCH_CHECK();
+  }
+  const size_t smem = (size_t)kMonceWarps * 2 * iters * sizeof(float);
+  if (smem > 48 * 1024)
+    JG_CUDA(cudaFuncSetAttribute(monce_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  monce_bwd_dq_kernel<<<rows, kMonceThreads, smem, stream>>>(k, grad_loss, P, D, 1.f / T, iters, Km, Kb, Wm, U, V, SB, RB,
+                                                           p0s, dq);
+  JG_LAUNCH_CHECK();
+  if (dk) {
+    monce_bwd_dk_kernel<<<rows, kMonceThreads, 0, stream>>>(q, P, D, Wm, dk);
+    JG_LAUNCH_CHECK();
+  }
   return JG_OK;
 }

@@ -109,11 +109,12 @@ def test_trainer_with_class_conditioning_and_dropout(golden_dir):
     for mode in ("dropout", "by_hand"):
         net = nets.build_palette_generator(conditioning="class", nclasses=4, **BASE)
         net.load_state_dict(params, strict=False)
-        cls = data["cls"].clone()
-        if mode == "by_hand":
+        cls, mask = data["cls"].clone(), data["mask"].clone()
+        if mode == "by_hand":   # the reference fills BOTH the class and the mask of a dropped sample (:571-583)
             cls[drop_u < 0.1] = 3
+            mask[drop_u < 0.1] = 3
         tr = PaletteTrainer(net, lr=1e-3, device="cuda", dropout_prob=0.1 if mode == "dropout" else 0.0, num_classes=4)
-        tr.set_input({"A": data["cond"], "B": data["gt"], "B_label_mask": data["mask"], "B_label_cls": cls})
+        tr.set_input({"A": data["cond"], "B": data["gt"], "B_label_mask": mask, "B_label_cls": cls})
         losses.append(float(tr.compute_palette_loss(noise=noise.cuda(), t=t.cuda(), u=u.cuda(),
                                                     drop_u=drop_u.cuda() if mode == "dropout" else None)))
     assert losses[0] == losses[1]
