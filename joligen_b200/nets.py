@@ -298,8 +298,12 @@ class ResBlock(EmbedBlock):
         if self.use_scale_shift_norm:
             h = self.out_layers[0].forward_nhwc(h, film=emb_out, act=L.ACT_SILU)
         else:
-            # h + emb_out then GN -> SiLU: express the add as FiLM-free shift before the norm
-            raise NotImplementedError("B200 ResBlock: use_scale_shift_norm=False is not supported yet")
+            # h + emb_out, then GN -> SiLU (:259-261).  No option of the reference reaches this branch
+            # (diffusion_networks.py:70/:231 pass use_scale_shift_norm=True), so the per-(n, c) add is a plain
+            # broadcast add in front of the fused norm rather than another epilogue mode of the convolution.
+            e = emb_out if emb_out.shape[1] == h.shape[-1] else F.pad(emb_out, (0, h.shape[-1] - emb_out.shape[1]))
+            h = (h.float() + e[:, None, None, :].float()).to(h.dtype)
+            h = self.out_layers[0].forward_nhwc(h, film=None, act=L.ACT_SILU)
         skipw = 1.0 / math.sqrt(2) if (self.efficient and self.apply_skipw) else 1.0
         if self._pack_skip is not None:
             x = _conv(x, self.skip_connection, self._pack_skip)
@@ -819,7 +823,7 @@ class DiffusionGenerator(nn.Module):
 def build_palette_generator(image_size=256, in_channel=6, inner_channel=64, out_channel=3, res_blocks=(2, 2, 2, 2),
                             attn_res=(16,), channel_mults=(1, 2, 4, 8), num_heads=1, num_head_channels=32,
                             group_norm_size=32, cond_embed_dim=32, n_timestep_train=2000, n_timestep_test=1000,
-                            efficient=False, conditioning="", nclasses=2):
+                            efficient=False, conditioning="", nclasses=2, use_scale_shift_norm=True):
     """What diffusion_networks.define_G(model_type="palette", G_netG="unet_mha", ...) builds
     (models/diffusion_networks.py:114-139, 361-376), on the B200 modules."""
     if "mask" in conditioning:
@@ -828,6 +832,6 @@ def build_palette_generator(image_size=256, in_channel=6, inner_channel=64, out_
                 res_blocks=list(res_blocks), attn_res=list(attn_res), tanh=False, n_timestep_train=n_timestep_train,
                 n_timestep_test=n_timestep_test, norm="groupnorm", group_norm_size=group_norm_size,
                 cond_embed_dim=cond_embed_dim, channel_mults=tuple(channel_mults), num_heads=num_heads,
-                num_head_channels=num_head_channels, efficient=efficient)
+                num_head_channels=num_head_channels, efficient=efficient, use_scale_shift_norm=use_scale_shift_norm)
     dn = PaletteDenoiseFn(model=unet, cond_embed_dim=cond_embed_dim, conditioning=conditioning, nclasses=nclasses)
     return DiffusionGenerator(denoise_fn=dn, sampling_method="ddpm", image_size=image_size, G_ngf=inner_channel)

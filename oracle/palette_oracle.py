@@ -290,7 +290,7 @@ def res_block(sd, name, x, emb, b: BlockSpec, cfg: UNetCfg):
         h = group_norm(h, gn_w, gn_b, cfg.group_norm_size) * (1 + scale) + shift
         h = _r(F.silu(h))
     else:
-        h = h + emb_out
+        h = _r(h + emb_out)  # (identity in fp32; the B200 path stores the sum as bf16)
         h = _r(F.silu(group_norm(h, gn_w, gn_b, cfg.group_norm_size)))
     h = _conv2d(h, sd[name + ".out_layers.3.weight"], sd[name + ".out_layers.3.bias"], padding=1)
     if b.cin != b.cout:

@@ -35,7 +35,8 @@ def env():
 def build(nets, O, cfg, params):
     g = nets.build_palette_generator(image_size=cfg.image_size, inner_channel=cfg.inner_channel,
                                      res_blocks=cfg.res_blocks, attn_res=cfg.attn_res,
-                                     channel_mults=cfg.channel_mults, num_head_channels=cfg.num_head_channels)
+                                     channel_mults=cfg.channel_mults, num_head_channels=cfg.num_head_channels,
+                                     use_scale_shift_norm=cfg.use_scale_shift_norm)
     missing, unexpected = g.load_state_dict(params, strict=False)
     assert not unexpected and all("gammas" in m or "posterior" in m for m in missing)
     return g.cuda()
@@ -59,12 +60,14 @@ def _blocks(O, cfg, unet):
             yield "denoise_fn.model.output_blocks.%d.%d" % (i, j), b, unet.output_blocks[i][j]
 
 
-def test_every_block_matches_bf16_emulated_oracle_fwd_bwd(env):
-    """(A): block-wise forward + backward parity with identical inputs."""
+@pytest.mark.parametrize("film", [True, False])
+def test_every_block_matches_bf16_emulated_oracle_fwd_bwd(env, film):
+    """(A): block-wise forward + backward parity with identical inputs (film=False: the ResBlock's
+    use_scale_shift_norm=False branch, unet_generator_attn.py:259-261)."""
     nets, O = env
     from joligen_b200 import ops
     cfg = O.UNetCfg(image_size=32, inner_channel=32, channel_mults=(1, 2, 4), res_blocks=(1, 1, 1), attn_res=(2,),
-                    num_head_channels=16)
+                    num_head_channels=16, use_scale_shift_norm=film)
     params = O.init_params(cfg, 17)
     net = build(nets, O, cfg, params)
     unet = net.denoise_fn.model
