@@ -486,7 +486,7 @@ def main():
                          "what": "STEP-LEVEL: %s FLOPs of one step (%.2f TFLOP) / device time of the whole step"
                                  % ("algorithmic (SURVEY.md 8d, 3 x forward)" if alg_flops_step is not None
                                     else "issued implicit-GEMM", step_flops / 1e12),
-                         "kernel": "conv_halo / conv_fwd / wgrad_halo / conv_wgrad kernels (%d implicit-GEMM calls per "
+                         "kernel": "conv_halo(2) / conv_fwd / wgrad_halo(2) / conv_wgrad kernels (%d implicit-GEMM calls per "
                                    "step)" % len(recs),
                          "conv": {"achieved": conv_tf, "frac_conv": conv_tf / peaks["bf16_tflops"],
                                   "flops_issued_per_step": conv_flops_issued, "ms_per_step": conv_ms,

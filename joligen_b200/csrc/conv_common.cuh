@@ -71,9 +71,10 @@ __device__ __forceinline__ TileRange conv_tile_range(const ConvFwdParams& p) {
 __device__ __forceinline__ void conv_flush_sums(const ConvFwdParams& p, float* s_acc, int img) {
   bar_sync(2, kEpiThreads);
   float* dst = (p.stats ? p.stats : p.gn_sums) + static_cast<size_t>(img) * p.Cout * 2;
+  const uint32_t acc_a = smem_u32(s_acc);
   for (int i = (static_cast<int>(threadIdx.x) - 64) * 4; i < 2 * p.Cout; i += kEpiThreads * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(s_acc + i);
-    *reinterpret_cast<float4*>(s_acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 v = lds_f4(acc_a + i * 4);
+    sts_v4(acc_a + i * 4, make_uint4(0u, 0u, 0u, 0u));
     if (p.dbg & 1) *reinterpret_cast<float4*>(dst + i) = v;  // (wrong sums: timing experiments only)
     else red_add_v4f(dst + i, v.x, v.y, v.z, v.w);
   }
@@ -212,6 +213,16 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
   const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16);
   const int row = q * 32 + (threadIdx.x & 31);
   const int swz = row & 7;
+  // every shared-memory access below goes by shared-space address (LDS / STS, see ptx.cuh)
+  const uint32_t stage_a = smem_u32(stage);
+  const uint32_t bias_a = s_bias ? smem_u32(s_bias) : 0u;
+  const uint32_t res_a = res_tile ? smem_u32(res_tile) + row * 128 : 0u;
+  const uint32_t acc_a = s_acc ? smem_u32(s_acc) : 0u;
+  // Fused GroupNorm reductions run as a COLUMN pass over the staged slab after the slab barrier.  Epilogue warp w8
+  // owns the channel pairs 4*w8 .. 4*w8+3 of the slab; lane = (row lane rl, pair pp) reads rows rl, rl+8, ..: the 32
+  // lanes of a load hit 32 different banks (the 128B swizzle XORs the 16-byte chunk index w8 with row mod 8 = rl).
+  const int w8 = (static_cast<int>(threadIdx.x) - 64) >> 5;
+  const int pp = threadIdx.x & 3, rl = (threadIdx.x & 31) >> 2;
 #pragma unroll 1
   for (int c = half * 32; c < BLOCK_N; c += 64) {
     const int co0 = n_tile * BLOCK_N + c;
@@ -219,21 +230,19 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
     if (slab_co >= p.Cout) break;                // uniform over all 8 warps: the rest of the tile is channel padding
     uint32_t v[32];
     tmem_ld_32x32(t_row + c, v);
-    // While the TMEM load is in flight: bias (shared memory, zero-padded past Cout) and residual.  Straight-line code:
-    // the four 8-channel groups are independent, the two epilogue warps of an SM sub-partition have little else to
-    // hide latency with.  Channels >= Cout hold don't-care values that the TMA store clips.
-    float4 bias4[8];
+    // While the TMEM load is in flight: the first half of the bias (shared memory, zero-padded past Cout) and the
+    // residual.  Channels >= Cout hold don't-care values that the TMA store clips.
+    float4 bias4[4];
     if (s_bias) {
 #pragma unroll
-      for (int g = 0; g < 8; ++g) bias4[g] = *reinterpret_cast<const float4*>(s_bias + co0 + g * 4);
+      for (int g = 0; g < 4; ++g) bias4[g] = lds_f4(bias_a + (co0 + g * 4) * 4);
     }
     uint4 rcur[4];
     const bool has_res = p.res != nullptr;
     if (res_tile) {
       // residual slab staged in shared memory by TMA (same 128B-swizzled layout as the output staging)
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-        rcur[g] = *reinterpret_cast<const uint4*>(res_tile + row * 128 + (((half * 4 + g) ^ swz) << 4));
+      for (int g = 0; g < 4; ++g) rcur[g] = lds_v4(res_a + (((half * 4 + g) ^ swz) << 4));
     } else if (has_res && p.res_mode == 0) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) rcur[g] = pf.r[g];
@@ -244,13 +253,6 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
           if (co0 + 64 + g * 8 < p.Cout) pf.r[g] = *reinterpret_cast<const uint4*>(rn + g * 8);
       }
     }
-    // Fused GroupNorm reductions run as a COLUMN pass over the staged slab after the slab barrier.  Epilogue warp w8
-    // owns the channel pairs 4*w8 .. 4*w8+3 of the slab; lane = (row lane rl, pair pp) reads rows rl, rl+8, ..: the 32
-    // lanes of a load hit 32 different banks (the 128B swizzle XORs the 16-byte chunk index w8 with row mod 8 = rl).
-    // The 8 row lanes are combined with 3 shuffle steps; lane (0, pp) then adds into the CTA's shared-memory sums —
-    // it is the only thread that ever touches that address, so no atomics (fp32 shared atomics are CAS loops).
-    const int w8 = (static_cast<int>(threadIdx.x) - 64) >> 5;
-    const int pp = threadIdx.x & 3, rl = (threadIdx.x & 31) >> 2;
     const int colco = slab_co + 2 * (4 * w8 + pp);
     tmem_ld_wait();
     float f[32];
@@ -258,9 +260,16 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
     if (s_bias) {
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < 4; ++g) {
         f[g * 4 + 0] += bias4[g].x; f[g * 4 + 1] += bias4[g].y;
         f[g * 4 + 2] += bias4[g].z; f[g * 4 + 3] += bias4[g].w;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) bias4[g] = lds_f4(bias_a + (co0 + 16 + g * 4) * 4);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        f[16 + g * 4 + 0] += bias4[g].x; f[16 + g * 4 + 1] += bias4[g].y;
+        f[16 + g * 4 + 2] += bias4[g].z; f[16 + g * 4 + 3] += bias4[g].w;
       }
     }
     if (has_res && p.res_mode == 0 && (res_tile || valid)) {
@@ -280,7 +289,7 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
     }
-    uint8_t* buf = stage + stage_idx * kStageBytes + row * 128;
+    const uint32_t buf_a = stage_a + stage_idx * kStageBytes;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {  // 8 channels per 16-byte chunk; 128B swizzle: chunk index XOR (row mod 8)
       uint4 o;
@@ -288,7 +297,7 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
       o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
       o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
       o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
-      *reinterpret_cast<uint4*>(buf + (((half * 4 + g) ^ swz) << 4)) = o;
+      sts_v4(buf_a + row * 128 + (((half * 4 + g) ^ swz) << 4), o);
     }
     // x words of the first XB rows, issued here (the accumulator registers are dead by now) so that the loads fly
     // during the fence / slab barrier / store issue below.  XB = 16 rows at once where registers allow (BLOCK_N = 64,
@@ -321,18 +330,29 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
       // (this buffer is rewritten two slabs from now, behind the next slab's barrier: every thread has left by then)
       // The two modes are separate loops (the mode test is NOT inside the row loop): only the code of the active mode
       // is ever fetched — with both interleaved, ncu showed the kernel stalling on instruction-cache misses.
-      const uint8_t* colbase = stage + stage_idx * kStageBytes + rl * 128 + (((w8 ^ rl) << 4) | (pp << 2));
+      const uint32_t col_a = buf_a + rl * 128 + (((w8 ^ rl) << 4) | (pp << 2));
       float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
       if (p.stats) {
-        // statistics of the STORED values for the GroupNorm that reads y next: sum, sum of squares
-#pragma unroll 4
-        for (int k = 0; k < 16; ++k) {
-          const int rr = rl + 8 * k;
-          float2 yv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(colbase + k * 1024));
-          if (RAGGED && !((c1 + rr % tile_w < p.Wo) && (c2 + rr / tile_w < p.Ho))) yv = make_float2(0.f, 0.f);
-          s0 += yv.x; t0 = fmaf(yv.x, yv.x, t0);
-          s1 += yv.y; t1 = fmaf(yv.y, yv.y, t1);
+        // statistics of the STORED values for the GroupNorm that reads y next: sum, sum of squares.  All 16 row words
+        // are loaded before the first add (16 independent LDS in flight), two accumulator chains per sum.
+        uint32_t yw[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) yw[k] = lds_u32(col_a + k * 1024);
+        float s0b = 0.f, s1b = 0.f, t0b = 0.f, t1b = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+          float2 ya = unpack_bf16x2(yw[k]), yb = unpack_bf16x2(yw[k + 1]);
+          if (RAGGED) {
+            const int ra = rl + 8 * k, rb = ra + 8;
+            if (!((c1 + ra % tile_w < p.Wo) && (c2 + ra / tile_w < p.Ho))) ya = make_float2(0.f, 0.f);
+            if (!((c1 + rb % tile_w < p.Wo) && (c2 + rb / tile_w < p.Ho))) yb = make_float2(0.f, 0.f);
+          }
+          s0 += ya.x; t0 = fmaf(ya.x, ya.x, t0);
+          s1 += ya.y; t1 = fmaf(ya.y, ya.y, t1);
+          s0b += yb.x; t0b = fmaf(yb.x, yb.x, t0b);
+          s1b += yb.y; t1b = fmaf(yb.y, yb.y, t1b);
         }
+        s0 += s0b; t0 += t0b; s1 += s1b; t1 += t1b;
       } else {
         // GroupNorm-backward sums: y is dL/d(act output); du = y * act'(a*x + b); A = sum du, B = sum du * x
 #pragma unroll
@@ -341,7 +361,7 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
 #pragma unroll
           for (int k = 0; k < XB; ++k) {
             const int rr = rl + 8 * (k0 + k);
-            const float2 yv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(colbase + (k0 + k) * 1024));
+            const float2 yv = unpack_bf16x2(lds_u32(col_a + (k0 + k) * 1024));
             const float2 xv = unpack_bf16x2(xw[k]);
             const bool live = !RAGGED || ((c1 + rr % tile_w < p.Wo) && (c2 + rr / tile_w < p.Ho));
             const float du0 = live ? yv.x * act_grad_rt(fmaf(xv.x, ab4.x, ab4.y), p.gn_act) : 0.f;
@@ -351,18 +371,18 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
           }
         }
       }
-#pragma unroll
-      for (int off = 4; off <= 16; off <<= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, off);
-        t0 += __shfl_xor_sync(0xffffffffu, t0, off);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-        t1 += __shfl_xor_sync(0xffffffffu, t1, off);
-      }
-      if (rl == 0) {  // CTA-local sums of the current image; conv_flush_sums ships them once per image
-        float4* acc = reinterpret_cast<float4*>(s_acc + 2 * colco);
-        float4 a = *acc;
-        a.x += s0; a.y += t0; a.z += s1; a.w += t1;
-        *acc = a;
+      // Sum over the 8 row lanes (lane bits 2..4) as a transpose-reduction: 4 shuffles instead of 12.  After the xor-16
+      // step a lane keeps one channel's (sum, sum2), after xor-8 one of the two, xor-4 finishes it: the four lanes
+      // (bit 4, bit 3) with bit 2 clear each own one of the pair's four sums and are the only threads that ever touch
+      // that shared-memory word (no atomics: fp32 shared atomics are CAS loops).
+      const bool b4 = (threadIdx.x & 16) != 0, b3 = (threadIdx.x & 8) != 0;
+      const float ka = (b4 ? s1 : s0) + __shfl_xor_sync(0xffffffffu, b4 ? s0 : s1, 16);
+      const float kb = (b4 ? t1 : t0) + __shfl_xor_sync(0xffffffffu, b4 ? t0 : t1, 16);
+      float val = (b3 ? kb : ka) + __shfl_xor_sync(0xffffffffu, b3 ? ka : kb, 8);
+      val += __shfl_xor_sync(0xffffffffu, val, 4);
+      if ((threadIdx.x & 4) == 0) {  // CTA-local sums of the current image; conv_flush_sums ships them once per image
+        const uint32_t a = acc_a + (2 * colco + (b4 ? 2 : 0) + (b3 ? 1 : 0)) * 4;
+        sts_f32(a, lds_f32(a) + val);
       }
     }
     stage_idx ^= 1;

@@ -574,41 +574,67 @@ extern "C" int jg_groupnorm_bwd(const void* x, int ldx, const void* dy, int lddy
   if (sums_pre) AB = const_cast<float*>(sums_pre);
   else JG_CUDA(cudaMemsetAsync(AB, 0, sizeof(float) * (size_t)N * C * 2, stream));
   if (dx_colsum) JG_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, stream));
-  const int rpb1 = rows_per_block_for(HW, N, 2);
-  const int rpb = rows_per_block_for(HW, N, 2);
-  dim3 grid1((HW + rpb1 - 1) / rpb1, N);
-  dim3 grid((HW + rpb - 1) / rpb, N);
-  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
-  const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(dy);
-  const __nv_bfloat16* addb = static_cast<const __nv_bfloat16*>(addend);
-  const __nv_bfloat16* addb2 = static_cast<const __nv_bfloat16*>(addend2);
-  __nv_bfloat16* dxb = static_cast<__nv_bfloat16*>(dx);
-  if (!sums_pre) {
-    JG_ACT_DISPATCH(act, gn_bwd_sums_kernel<ACT><<<grid1, kNormThreads, (2 * kPartFloats + 2 * C) * sizeof(float), stream>>>(
-                             xb, ldx, dyb, lddy, HW, C, rpb1, ab, AB));
+  const __nv_bfloat16* xb0 = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* dyb0 = static_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* addb0 = static_cast<const __nv_bfloat16*>(addend);
+  const __nv_bfloat16* addb20 = static_cast<const __nv_bfloat16*>(addend2);
+  __nv_bfloat16* dxb0 = static_cast<__nv_bfloat16*>(dx);
+  // Image chunks: the sums pass and the apply pass both read x and dy.  When the whole batch is several times the L2
+  // (268 MB for 32 x 256^2 x 64 against 126 MB) the second read comes from HBM again; run in chunks of images whose
+  // x + dy fit the L2 budget and the apply pass of a chunk finds what the sums pass just read.  Everything between the
+  // two passes is per image, so a chunk is the same three launches on offset pointers.  JG_GN_BWD_L2_MB (default 0 =
+  // one chunk).
+  static const int l2_mb = getenv("JG_GN_BWD_L2_MB") ? atoi(getenv("JG_GN_BWD_L2_MB")) : 0;
+  int NC = N;
+  if (l2_mb > 0 && !sums_pre) {
+    const size_t per_image = (size_t)HW * C * 2 * 2;
+    NC = (int)std::max<size_t>(1, ((size_t)l2_mb << 20) / per_image);
+    if (NC >= N) NC = N;
+    else NC = (N + (N + NC - 1) / NC - 1) / ((N + NC - 1) / NC);  // equal chunks
+  }
+  for (int n0 = 0; n0 < N; n0 += NC) {
+    const int nc = std::min(NC, N - n0);
+    const int rpb1 = rows_per_block_for(HW, nc, 2);
+    const int rpb = rows_per_block_for(HW, nc, 2);
+    dim3 grid1((HW + rpb1 - 1) / rpb1, nc);
+    dim3 grid((HW + rpb - 1) / rpb, nc);
+    const __nv_bfloat16* xb = xb0 + (size_t)n0 * HW * ldx;
+    const __nv_bfloat16* dyb = dyb0 + (size_t)n0 * HW * lddy;
+    const __nv_bfloat16* addb = addb0 ? addb0 + (size_t)n0 * HW * ldadd : nullptr;
+    const __nv_bfloat16* addb2 = addb20 ? addb20 + (size_t)n0 * HW * ldadd2 : nullptr;
+    __nv_bfloat16* dxb = dxb0 + (size_t)n0 * HW * lddx;
+    const float* ab_c = ab + (size_t)n0 * C * 2;
+    float* AB_c = AB + (size_t)n0 * C * 2;
+    float* k1_c = k1 + (size_t)n0 * C;
+    float* k23_c = k23 + (size_t)n0 * groups * 2;
+    if (!sums_pre) {
+      JG_ACT_DISPATCH(act, gn_bwd_sums_kernel<ACT><<<grid1, kNormThreads, (2 * kPartFloats + 2 * C) * sizeof(float), stream>>>(
+                               xb, ldx, dyb, lddy, HW, C, rpb1, ab_c, AB_c));
+      JG_LAUNCH_CHECK();
+    }
+    gn_finalize_bwd_kernel<<<nc, 256, 2 * C * sizeof(float), stream>>>(
+        AB_c, HW, C, groups, gamma, beta, film ? film + (size_t)n0 * 2 * C : nullptr, stats + (size_t)n0 * groups * 2, k1_c,
+        k23_c, dfilm ? dfilm + (size_t)n0 * 2 * C : nullptr, gAB + (size_t)n0 * C * 2);
+    JG_LAUNCH_CHECK();
+    const size_t smem = dx_colsum ? (kPartFloats + C) * sizeof(float) : 0;
+    if (addend2) {
+      JG_ACT_DISPATCH(act, gn_bwd_apply_kernel<2, ACT, 2><<<grid, kNormThreads, smem, stream>>>(
+                               xb, ldx, dyb, lddy, dxb, lddx, HW, C, groups, rpb, ab_c, k1_c, k23_c, addb, ldadd, addb2,
+                               ldadd2, dx_colsum));
+    } else if (addend) {
+      JG_ACT_DISPATCH(act, gn_bwd_apply_kernel<1, ACT, 3><<<grid, kNormThreads, smem, stream>>>(
+                               xb, ldx, dyb, lddy, dxb, lddx, HW, C, groups, rpb, ab_c, k1_c, k23_c, addb, ldadd, nullptr, 0,
+                               dx_colsum));
+    } else {
+      JG_ACT_DISPATCH(act, gn_bwd_apply_kernel<0, ACT, 4><<<grid, kNormThreads, smem, stream>>>(
+                               xb, ldx, dyb, lddy, dxb, lddx, HW, C, groups, rpb, ab_c, k1_c, k23_c, nullptr, 0, nullptr, 0,
+                               dx_colsum));
+    }
     JG_LAUNCH_CHECK();
   }
-  gn_finalize_bwd_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(AB, HW, C, groups, gamma, beta, film, stats, k1,
-                                                                    k23, dfilm, gAB);
-  JG_LAUNCH_CHECK();
   if (dgamma || dbeta) {
     gn_param_grad_kernel<<<(C + 127) / 128, 128, 0, stream>>>(gAB, N, C, dgamma, dbeta);
     JG_LAUNCH_CHECK();
   }
-  const size_t smem = dx_colsum ? (kPartFloats + C) * sizeof(float) : 0;
-  if (addend2) {
-    JG_ACT_DISPATCH(act, gn_bwd_apply_kernel<2, ACT, 2><<<grid, kNormThreads, smem, stream>>>(
-                             xb, ldx, dyb, lddy, dxb, lddx, HW, C, groups, rpb, ab, k1, k23, addb, ldadd, addb2, ldadd2,
-                             dx_colsum));
-  } else if (addend) {
-    JG_ACT_DISPATCH(act, gn_bwd_apply_kernel<1, ACT, 3><<<grid, kNormThreads, smem, stream>>>(
-                             xb, ldx, dyb, lddy, dxb, lddx, HW, C, groups, rpb, ab, k1, k23, addb, ldadd, nullptr, 0,
-                             dx_colsum));
-  } else {
-    JG_ACT_DISPATCH(act, gn_bwd_apply_kernel<0, ACT, 4><<<grid, kNormThreads, smem, stream>>>(
-                             xb, ldx, dyb, lddy, dxb, lddx, HW, C, groups, rpb, ab, k1, k23, nullptr, 0, nullptr, 0,
-                             dx_colsum));
-  }
-  JG_LAUNCH_CHECK();
   return JG_OK;
 }

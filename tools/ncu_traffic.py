@@ -35,7 +35,7 @@ print("one training step: %d launches, %.2f ms summed device time (ncu: serialis
 print("%7s %10s %6s %10s %8s  %s" % ("share", "us", "n", "DRAM MB", "GB/s", "kernel"))
 for k, (n, us, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("%6.2f%% %10.1f %6d %10.1f %8.0f  %s" % (100 * us / tot_us, us, n, by / 1e6, by / us / 1e3 if us else 0, k))
-gemm = [(n, us, by) for k, (n, us, by) in agg.items() if re.search(r"conv_halo_kernel|conv_fwd_kernel|wgrad", k)
+gemm = [(n, us, by) for k, (n, us, by) in agg.items() if re.search(r"conv_halo2?_kernel|conv_fwd_kernel|wgrad", k)
         and "unpack" not in k]
 n = sum(g[0] for g in gemm)
 out = {"source": sys.argv[1], "launches": n, "dram_bytes_total": sum(g[2] for g in gemm),
