@@ -202,13 +202,34 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvFwdParams& p, EpiPr
 // slab to the TMA engine.  One named barrier per slab: before it, the issuing thread has waited for the previous
 // slab's store to finish reading the other buffer.
 // RAGGED: output tiles may hang over the image border (generic kernel); the halo kernel tiles its output exactly.
+// Residual slabs fetched by TMA INTO the output staging buffers (BLOCK_N >= 128 halo kernels: no shared memory left for
+// separate residual tiles).  A thread reads the residual of exactly the 16-byte chunks it overwrites with its outputs, so
+// the buffer needs no extra hand-over: the load of slab s+1 goes into the other staging buffer as soon as the store of
+// slab s-1 has finished reading it (the wait the issuer does anyway), i.e. right behind the barrier of slab s; the
+// load for the first slab of the NEXT tile is issued behind the last slab's barrier and flies during the mainloop.
+struct ResInplace {
+  const CUtensorMap* tmR;
+  uint64_t* rfull;      // one mbarrier per staging buffer
+  uint32_t phase;       // bit b = parity to wait for on buffer b
+  bool has_next;        // coordinates of the next tile's first slab
+  int nco, n1, n2, n3;
+};
+
+template <int BLOCK_N>
+__device__ __forceinline__ void conv_res_prefetch_rest(const ConvFwdParams& p, const CUtensorMap* tmR, int co, int a1,
+                                                       int a2, int a3) {
+#pragma unroll
+  for (int j = 1; j < BLOCK_N / 64; ++j)
+    if (co + 64 * j < p.Cout) tma_prefetch_l2_4d(tmR, co + 64 * j, a1, a2, a3);
+}
+
 template <int BLOCK_N, bool RAGGED = true>
 __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, EpiPrefetch& pf, const float* s_bias,
                                                        uint32_t t_acc, int q, int half, int n_tile, bool valid,
                                                        size_t pix, uint8_t* stage, int& stage_idx,
                                                        const CUtensorMap* tmY, int c1, int c2, int c3, bool issuer,
                                                        const uint8_t* res_tile = nullptr, int tile_w = 8,
-                                                       float* s_acc = nullptr) {
+                                                       float* s_acc = nullptr, ResInplace* rin = nullptr) {
   static_assert(BLOCK_N % 64 == 0, "TMA-store epilogue works on 64-channel slabs");
   const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16);
   const int row = q * 32 + (threadIdx.x & 31);
@@ -239,7 +260,14 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
     }
     uint4 rcur[4];
     const bool has_res = p.res != nullptr;
-    if (res_tile) {
+    if (rin) {
+      // residual slab fetched into THIS slab's staging buffer (see ResInplace)
+      mbar_wait(&rin->rfull[stage_idx], (rin->phase >> stage_idx) & 1u);
+      rin->phase ^= 1u << stage_idx;
+      const uint32_t ra = stage_a + stage_idx * kStageBytes + row * 128;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) rcur[g] = lds_v4(ra + (((half * 4 + g) ^ swz) << 4));
+    } else if (res_tile && p.res_mode == 0) {
       // residual slab staged in shared memory by TMA (same 128B-swizzled layout as the output staging)
 #pragma unroll
       for (int g = 0; g < 4; ++g) rcur[g] = lds_v4(res_a + (((half * 4 + g) ^ swz) << 4));
@@ -272,7 +300,7 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
         f[16 + g * 4 + 2] += bias4[g].z; f[16 + g * 4 + 3] += bias4[g].w;
       }
     }
-    if (has_res && p.res_mode == 0 && (res_tile || valid)) {
+    if (has_res && p.res_mode == 0 && (rin || res_tile || valid)) {
       const float rs = p.res_scale;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -315,14 +343,28 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
                     : 0u;
       }
     };
+    // gn_sums with res_tile: the GroupNorm input tile was fetched by TMA (64-channel kernels) — read it like the slab
+    const bool x_smem = res_tile != nullptr && p.res_mode == 1;
     if (p.gn_sums && colco < p.Cout) {
       ab4 = *reinterpret_cast<const float4*>(p.gn_ab + (static_cast<size_t>(c3) * p.Cout + colco) * 2);
-      load_x(0);
+      if (!x_smem) load_x(0);
     }
     fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA (async proxy)
     if (issuer) bulk_wait_read<0>();     // the previous slab's store has released the other buffer
     bar_sync(1, kEpiThreads);
     if (issuer) {
+      if (rin) {  // the other buffer is free (wait above): fetch the next slab's residual into it
+        const bool more = c + 64 < BLOCK_N && slab_co + 64 < p.Cout;
+        if (more || rin->has_next) {
+          uint64_t* rb = &rin->rfull[stage_idx ^ 1];
+          mbar_arrive_expect_tx(rb, kStageBytes);
+          tma_load_4d(stage + (stage_idx ^ 1) * kStageBytes, rin->tmR, rb, more ? slab_co + 64 : rin->nco,
+                      more ? c1 : rin->n1, more ? c2 : rin->n2, more ? c3 : rin->n3);
+          // The slabs AFTER the first of the next tile are loaded one slab ahead only (their buffer is busy until then):
+          // too short for DRAM latency.  Pull them into L2 now, a whole mainloop ahead.
+          if (!more) conv_res_prefetch_rest<BLOCK_N>(p, rin->tmR, rin->nco, rin->n1, rin->n2, rin->n3);
+        }
+      }
       tma_store_4d(tmY, stage + stage_idx * kStageBytes, slab_co, c1, c2, c3);
       bulk_commit();
     }
@@ -353,6 +395,23 @@ __device__ __forceinline__ void conv_epilogue_tile_tma(const ConvFwdParams& p, E
           s1b += yb.y; t1b = fmaf(yb.y, yb.y, t1b);
         }
         s0 += s0b; t0 += t0b; s1 += s1b; t1 += t1b;
+      } else if (x_smem) {
+        // GroupNorm-backward sums, x tile in shared memory (same swizzled layout as the slab)
+        const uint32_t xcol_a = smem_u32(res_tile) + rl * 128 + (((w8 ^ rl) << 4) | (pp << 2));
+        uint32_t yw[16], xs[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          yw[k] = lds_u32(col_a + k * 1024);
+          xs[k] = lds_u32(xcol_a + k * 1024);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float2 yv = unpack_bf16x2(yw[k]), xv = unpack_bf16x2(xs[k]);
+          const float du0 = yv.x * act_grad_rt(fmaf(xv.x, ab4.x, ab4.y), p.gn_act);
+          const float du1 = yv.y * act_grad_rt(fmaf(xv.y, ab4.z, ab4.w), p.gn_act);
+          s0 += du0; t0 = fmaf(du0, xv.x, t0);
+          s1 += du1; t1 = fmaf(du1, xv.y, t1);
+        }
       } else {
         // GroupNorm-backward sums: y is dL/d(act output); du = y * act'(a*x + b); A = sum du, B = sum du * x
 #pragma unroll

@@ -49,7 +49,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int b_tiles = B_RESIDENT ? p.RS * k_slabs : SB;
   uint8_t* stage = smB + static_cast<size_t>(b_tiles) * B_BYTES;  // 2 x 16 KB output staging (1024-byte aligned)
   uint8_t* res_stage = stage + (TMA_STORE ? 2 * kStageBytes : 0);  // 2 x 16 KB residual tiles (RES_TMA)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(res_stage + ((RES_TMA && p.res && p.res_mode == 0) ? 2 * kStageBytes : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(res_stage + ((RES_TMA && p.res) ? 2 * kStageBytes : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + SA;
   uint64_t* b_full = bars + 2 * SA;           // SB entries (entry 0 only when resident)
@@ -72,7 +72,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (TMA_STORE) tma_prefetch_desc(&tmY);
-    if (RES_TMA && p.res && p.res_mode == 0) tma_prefetch_desc(&tmR);
+    if (p.res && (RES_TMA || (BLOCK_N >= 128 && p.res_mode == 0))) tma_prefetch_desc(&tmR);
     for (int i = 0; i < SA; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
@@ -243,7 +243,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     int stage_idx = 0;
     uint32_t acc_phase = 0;
-    const bool res_tma = RES_TMA && p.res != nullptr && p.res_mode == 0;
+    // (res_mode 1: the tile is the GroupNorm input x of the fused backward sums, not a residual)
+    const bool res_tma = RES_TMA && p.res != nullptr;
+    // BLOCK_N >= 128: residual slabs travel through the output staging buffers (ResInplace, conv_common.cuh)
+    const bool res_inplace = TMA_STORE && BLOCK_N >= 128 && p.res != nullptr && p.res_mode == 0 && !(p.dbg & 4);
+    ResInplace rin{&tmR, rfull, 0u, false, 0, 0, 0, 0};
+    auto tile_coords = [&](int tile, int& co, int& a1, int& a2, int& a3) {
+      const int m_tile = tile / p.n_tiles;
+      co = (tile % p.n_tiles) * BLOCK_N;
+      a1 = (m_tile % p.tiles_w) * kHaloTW;
+      a2 = ((m_tile / p.tiles_w) % p.tiles_h) * kHaloTH;
+      a3 = m_tile / (p.tiles_w * p.tiles_h);
+    };
+    if (res_inplace && issuer && tr.begin < tr.end) {
+      int co, a1, a2, a3;
+      tile_coords(tr.begin, co, a1, a2, a3);
+      mbar_arrive_expect_tx(&rfull[0], kStageBytes);
+      tma_load_4d(stage, &tmR, &rfull[0], co, a1, a2, a3);
+      conv_res_prefetch_rest<BLOCK_N>(p, &tmR, co, a1, a2, a3);
+    }
     // residual tile of this CTA's (i)th tile -> res_stage[i & 1]; issued two tiles ahead by the issuer thread
     auto load_res_tile = [&](int tile, int buf) {
       const int n_tile = tile % p.n_tiles;
@@ -272,7 +290,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int ph = th * kHaloTH + (row / kHaloTW);
       const bool valid = (pw < p.Wo) && (ph < p.Ho);
       const size_t pix = (static_cast<size_t>(tn) * p.Ho + ph) * p.Wo + pw;
-      if (!res_tma) conv_epilogue_prefetch<BLOCK_N>(p, pf, half, n_tile, valid, pix);
+      if (!res_tma && !res_inplace) conv_epilogue_prefetch<BLOCK_N>(p, pf, half, n_tile, valid, pix);
+      if (res_inplace) {
+        rin.has_next = tile + tr.step < tr.end;
+        if (rin.has_next) tile_coords(tile + tr.step, rin.nco, rin.n1, rin.n2, rin.n3);
+      }
       if (fused && tn != cur_img) {  // the chunk of tiles moved on to the next image: ship the finished one's sums
         if (cur_img >= 0) conv_flush_sums(p, s_acc, cur_img);
         cur_img = tn;
@@ -284,7 +306,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (res_tma) mbar_wait(&rfull[rbuf], rphase);
         conv_epilogue_tile_tma<BLOCK_N, false>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half,
                                                n_tile, valid, pix, stage, stage_idx, &tmY, tw * kHaloTW, th * kHaloTH, tn, issuer,
-                                        res_tma ? res_stage + rbuf * kStageBytes : nullptr, kHaloTW, s_acc);
+                                        res_tma ? res_stage + rbuf * kStageBytes : nullptr, kHaloTW, s_acc,
+                                        res_inplace ? &rin : nullptr);
         if (res_tma) {
           // the slab barrier inside the epilogue ordered every thread's reads of this residual buffer before here
           if (issuer && tile + 2 * tr.step < tr.end) load_res_tile(tile + 2 * tr.step, rbuf);
@@ -320,7 +343,7 @@ template <int BLOCK_N, int SA, int SB, bool B_RESIDENT>
 static int halo_smem_bytes(const HaloParams& hp) {
   const int b_tiles = B_RESIDENT ? hp.c.RS * hp.c.kc_blocks : SB;
   return SA * hp.a_stage_bytes + b_tiles * BLOCK_N * 128 + (BLOCK_N >= 64 ? 2 * kStageBytes : 0) +
-         ((BLOCK_N == 64 && hp.c.res && hp.c.res_mode == 0) ? 2 * kStageBytes : 0) + (2 * SA + 2 * SB + 8) * 8 +
+         ((BLOCK_N == 64 && hp.c.res) ? 2 * kStageBytes : 0) + (2 * SA + 2 * SB + 8) * 8 +
          (((hp.c.Cout + 64) * 4 + 127) / 128) * 128 + ((hp.c.stats || hp.c.gn_sums) ? 2 * hp.c.Cout * 4 : 0) + 1024;
 }
 
@@ -408,7 +431,7 @@ int launch_conv_halo(const jg_conv_desc* d, const jg_conv_epilogue* e, const voi
     if (rc) return rc;
   }
   CUtensorMap tmR = tmA;  // residual tiles (64-channel kernels with a residual)
-  if (block_n == 64 && residual && p.res_mode == 0) {
+  if (block_n >= 64 && residual && (p.res_mode == 0 || block_n == 64)) {
     uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
     uint64_t strides[3] = {(uint64_t)p.ldres * 2, (uint64_t)d->Wo * p.ldres * 2,
                            (uint64_t)d->Ho * d->Wo * p.ldres * 2};

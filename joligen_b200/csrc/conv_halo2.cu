@@ -78,7 +78,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmY);
-    if (res_tma) tma_prefetch_desc(&tmR);
+    if (res_tma || (BLOCK_N >= 128 && p.res && p.res_mode == 0)) tma_prefetch_desc(&tmR);
     for (int i = 0; i < SA; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
@@ -258,6 +258,15 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int stage_idx = 0;
     uint32_t acc_phase = 0;
     const uint32_t tempty_lead[2] = {mapa_u32(smem_u32(&tempty[0]), 0), mapa_u32(smem_u32(&tempty[1]), 0)};
+    const bool res_inplace = BLOCK_N >= 128 && p.res != nullptr && p.res_mode == 0 && !(p.dbg & 4);
+    ResInplace rin{&tmR, rfull, 0u, false, 0, 0, 0, 0};
+    if (res_inplace && issuer && pair_id < p.total_tiles) {
+      int n_tile, tw, th, tn;
+      decode(pair_id, n_tile, tw, th, tn);
+      mbar_arrive_expect_tx(&rfull[0], kStageBytes);
+      tma_load_4d(stage, &tmR, &rfull[0], n_tile * BLOCK_N, tw * kH2TW, th * kH2TH, tn);
+      conv_res_prefetch_rest<BLOCK_N>(p, &tmR, n_tile * BLOCK_N, tw * kH2TW, th * kH2TH, tn);
+    }
     auto load_res_tile = [&](int pt, int buf) {
       int n_tile, tw, th, tn;
       decode(pt, n_tile, tw, th, tn);
@@ -279,7 +288,15 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int ph = th * kH2TH + (row / kH2TW);
       const bool valid = (pw < p.Wo) && (ph < p.Ho);
       const size_t pix = (static_cast<size_t>(tn) * p.Ho + ph) * p.Wo + pw;
-      if (!res_tma) conv_epilogue_prefetch<BLOCK_N>(p, pf, half, n_tile, valid, pix);
+      if (!res_tma && !res_inplace) conv_epilogue_prefetch<BLOCK_N>(p, pf, half, n_tile, valid, pix);
+      if (res_inplace) {
+        rin.has_next = pt + num_pairs < p.total_tiles;
+        if (rin.has_next) {
+          int n2, tw2, th2, tn2;
+          decode(pt + num_pairs, n2, tw2, th2, tn2);
+          rin.nco = n2 * BLOCK_N; rin.n1 = tw2 * kH2TW; rin.n2 = th2 * kH2TH; rin.n3 = tn2;
+        }
+      }
       if (fused && tn != cur_img) {
         if (cur_img >= 0) conv_flush_sums(p, s_acc, cur_img);
         cur_img = tn;
@@ -289,7 +306,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (res_tma) mbar_wait(&rfull[rbuf], rphase);
       conv_epilogue_tile_tma<BLOCK_N, false>(p, pf, p.bias ? s_bias : nullptr, tmem_base + acc * BLOCK_N, q, half,
                                              n_tile, valid, pix, stage, stage_idx, &tmY, tw * kH2TW, th * kH2TH, tn, issuer,
-                                             res_tma ? res_stage + rbuf * kStageBytes : nullptr, kH2TW, s_acc);
+                                             res_tma ? res_stage + rbuf * kStageBytes : nullptr, kH2TW, s_acc,
+                                             res_inplace ? &rin : nullptr);
       if (res_tma) {
         if (issuer && pt + 2 * num_pairs < p.total_tiles) load_res_tile(pt + 2 * num_pairs, rbuf);
         if (++rbuf == 2) {
@@ -424,7 +442,7 @@ int launch_conv_halo2(const jg_conv_desc* d, const jg_conv_epilogue* e, const vo
     if (rc) return rc;
   }
   CUtensorMap tmR = tmA;
-  if (block_n == 64 && residual && p.res_mode == 0) {
+  if (block_n >= 64 && residual && p.res_mode == 0) {
     uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
     uint64_t strides[3] = {(uint64_t)p.ldres * 2, (uint64_t)d->Wo * p.ldres * 2, (uint64_t)d->Ho * d->Wo * p.ldres * 2};
     uint32_t box[4] = {64, (uint32_t)kH2TW, (uint32_t)kH2TH, 1};

@@ -149,6 +149,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// L2 prefetch of a tensor-map box (no shared memory, no barrier): a later TMA load of the same box finds it in L2
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the bulk stores of all but the N most recent groups have finished READING shared memory
 template <int N>

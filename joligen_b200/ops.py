@@ -39,6 +39,9 @@ FUSE_STATS = [_FUSE_MODE in ("1", "stats")]
 FUSE_SUMS = [_FUSE_MODE in ("1", "sums")]
 # the dgrad epilogue takes the GroupNorm-backward sums only for GroupNorms with at least this many channels
 FUSE_SUMS_MIN_C = [int(_os.environ.get("JG_FUSE_SUMS_MIN_C", "0"))]
+# ... and at most this many: the 64-channel kernels get the GroupNorm input tile by TMA next to the output staging; the
+# wider ones have no shared memory left for it and read x with per-lane loads, which costs more than the pass it saves
+FUSE_SUMS_MAX_C = [int(_os.environ.get("JG_FUSE_SUMS_MAX_C", "64"))]
 
 
 def _stamp(t, name):
@@ -530,7 +533,7 @@ def conv2d(x, weight, bias, packed, stride=1, pad=None, residual=None, res_scale
     if FUSE_GN[0]:
         # the GroupNorm that produced x rides along for the dgrad; a 3x3 conv feeding a GroupNorm emits its statistics
         gn = _stamp(x, "_jg_gn") if (FUSE_SUMS[0] and stride == 1 and x.requires_grad
-                                     and x.shape[-1] >= FUSE_SUMS_MIN_C[0]) else None
+                                     and FUSE_SUMS_MIN_C[0] <= x.shape[-1] <= FUSE_SUMS_MAX_C[0]) else None
         want_stats = bool(want_stats) and FUSE_STATS[0]
         if gn is not None or want_stats:
             aux = {"want_stats": want_stats, "gn": None if gn is None else gn[:3]}
