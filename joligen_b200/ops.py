@@ -40,7 +40,8 @@ FUSE_SUMS = [_FUSE_MODE in ("1", "sums")]
 # the dgrad epilogue takes the GroupNorm-backward sums only for GroupNorms with at least this many channels
 FUSE_SUMS_MIN_C = [int(_os.environ.get("JG_FUSE_SUMS_MIN_C", "0"))]
 # ... and at most this many: the 64-channel kernels get the GroupNorm input tile by TMA next to the output staging; the
-# wider ones have no shared memory left for it and read x with per-lane loads, which costs more than the pass it saves
+# wider ones read x with per-lane loads.  (Only with JG_FUSE_GN=1/sums: measured on B200 the fused sums lose in both
+# forms — the derivative recompute makes the epilogue the bottleneck)
 FUSE_SUMS_MAX_C = [int(_os.environ.get("JG_FUSE_SUMS_MAX_C", "64"))]
 
 
