@@ -15,6 +15,9 @@
 
 namespace jg {
 
+int launch_attn_fwd_tc(const void* qkv, int ldqkv, void* out, int ldo, float* lse, int N, int T, int heads, int ch,
+                       int hstride, int koff, int voff, float scale_log2, cudaStream_t stream);
+
 constexpr int kAttnThreads = 128;
 constexpr int kBM = 64;  // rows per CTA (4 warps x 16)
 constexpr int kBN = 64;  // columns per inner block
@@ -431,6 +434,12 @@ extern "C" int jg_attn_fwd(const void* qkv, int ldqkv, void* out, int ldo, float
   JG_ATTN_LAYOUT(layout, heads, ch)
   const float scale = 1.f / sqrtf((float)ch);  // (ch^-1/4)^2
   const float scale_log2 = scale * 1.4426950408889634f;
+  // tcgen05 forward (attention_tc.cu) where the shape qualifies (ch 32 / 64, T a multiple of 256); JG_ATTN_TC=0: off
+  static const bool use_tc = getenv("JG_ATTN_TC") == nullptr || atoi(getenv("JG_ATTN_TC")) != 0;
+  if (use_tc) {
+    rc = launch_attn_fwd_tc(qkv, ldqkv, out, ldo, lse, N, T, heads, ch, hstride, koff, voff, scale_log2, stream);
+    if (rc != JG_ERR_UNSUPPORTED) return rc;
+  }
   dim3 grid(T / kBM, N * heads);
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
