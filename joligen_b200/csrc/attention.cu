@@ -18,6 +18,10 @@ namespace jg {
 int launch_attn_fwd_tc(const void* qkv, int ldqkv, void* out, int ldo, float* lse, int N, int T, int heads, int ch,
                        int hstride, int koff, int voff, float scale_log2, cudaStream_t stream);
 
+int launch_attn_bwd_tc(const void* qkv, int ldqkv, const void* d_out, int lddo, const float* lse, const float* D,
+                       void* dqkv, int lddqkv, int N, int T, int heads, int ch, int hstride, int koff, int voff,
+                       float scale_log2, float scale, cudaStream_t stream);
+
 constexpr int kAttnThreads = 128;
 constexpr int kBM = 64;  // rows per CTA (4 warps x 16)
 constexpr int kBN = 64;  // columns per inner block
@@ -468,6 +472,12 @@ extern "C" int jg_attn_bwd(const void* qkv, int ldqkv, const void* out, int ldo,
       static_cast<const __nv_bfloat16*>(out), ldo, static_cast<const __nv_bfloat16*>(d_out), lddo, ws, T, heads, ch,
       total);
   JG_LAUNCH_CHECK();
+  static const bool use_tc = getenv("JG_ATTN_TC") == nullptr || atoi(getenv("JG_ATTN_TC")) != 0;
+  if (use_tc) {
+    rc = launch_attn_bwd_tc(qkv, ldqkv, d_out, lddo, lse, ws, dqkv, lddqkv, N, T, heads, ch, hstride, koff, voff,
+                            scale_log2, scale, stream);
+    if (rc != JG_ERR_UNSUPPORTED) return rc;
+  }
   dim3 grid(T / kBM, N * heads);
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
   const __nv_bfloat16* d = static_cast<const __nv_bfloat16*>(d_out);

@@ -200,82 +200,116 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams
     const uint32_t p_a = smem_u32(sP + g * 2 * kTileBytes) + row * 128;
     const int swz = row & 7;
     float m_used = -INFINITY, l = 0.f;
+    float c_pend = 1.f;   // rescale of O_g decided in block j, applied at the start of block j+1 (or in the epilogue)
     uint32_t ph = 0;
+    auto rescale_o = [&](float c) {  // whole warp; c per row
+      uint32_t o[32];
+#pragma unroll
+      for (int cc = 0; cc < HD / 32; ++cc) {
+        tmem_ld_32x32(tO[g] + lane_off + cc * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * c);
+        tmem_st_32x32(tO[g] + lane_off + cc * 32, o);
+      }
+      tmem_st_wait();
+    };
     for (int j = 0; j < nb; ++j) {
       mbar_wait(&s_full[g], ph);
       tc_fence_after();
-      // pass 1 over the 128 scores of this row (TMEM reads are cheap; keeping all 128 in registers is not): the max
-      float mx;
-      {
+      if (j > 0) {
+        // P_g / O_g of block j-1 are consumed / final (PV_g(j-1) was issued before S_g(j): this wait does not stall)
+        mbar_wait(&pv_done[g], ph ^ 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, c_pend != 1.f)) rescale_o(c_pend);
+        c_pend = 1.f;
+      } else {
+        // first block: the exact row max (a second pass over TMEM; later blocks use the running reference)
+        float mx8[8];
         uint32_t v[32];
         tmem_ld_32x32(tS[g] + lane_off, v);
         tmem_ld_wait();
-        mx = __uint_as_float(v[0]);
 #pragma unroll
-        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(v[i]);
+#pragma unroll
+        for (int i = 8; i < 32; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(v[i]));
 #pragma unroll
         for (int c = 1; c < 4; ++c) {
           tmem_ld_32x32(tS[g] + lane_off + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(v[i]));
         }
-        mx *= p.scale_log2;  // into the exp2 domain (scale > 0)
+        m_used = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                       fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * p.scale_log2;
       }
-      // P_g and O_g of block j-1 must be consumed / final before they are touched
-      if (j > 0) {
-        mbar_wait(&pv_done[g], ph ^ 1);
-        tc_fence_after();
-      }
-      const bool grow = mx > m_used + kRescaleThreshold;
-      if (__any_sync(0xffffffffu, grow)) {
-        const float m_new = grow ? mx : m_used;
-        const float c = (j > 0) ? fast_exp2(m_used - m_new) : 0.f;
-        if (j > 0) {
-          uint32_t o[32];
-          tmem_ld_32x32(tO[g] + lane_off, o);
-          tmem_ld_wait();
+      // One pass: p = 2^(s * scale - m_used) against the RUNNING reference m_used (any reference gives the same
+      // softmax as long as O and l use the same one), row sum, row max relative to the reference, bf16 P into the
+      // swizzled K-major tile.  Independent accumulator chains (8 sums / 8 maxima); the TMEM load of chunk c+1 flies
+      // while chunk c is processed.
+      float rs, mrel;
+#pragma unroll 1
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        const float nm = -m_used;
+        float rs8[8], mx8[8];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * c);
-          tmem_st_32x32(tO[g] + lane_off, o);
-          if (HD == 64) {
-            tmem_ld_32x32(tO[g] + lane_off + 32, o);
-            tmem_ld_wait();
+        for (int i = 0; i < 8; ++i) {
+          rs8[i] = 0.f;
+          mx8[i] = -INFINITY;
+        }
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(tS[g] + lane_off, va);
+        auto chunk = [&](const uint32_t (&v)[32], int c) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * c);
-            tmem_st_32x32(tO[g] + lane_off + 32, o);
+          for (int i4 = 0; i4 < 4; ++i4) {  // 8 keys per 16-byte chunk
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float t = fmaf(__uint_as_float(v[i4 * 8 + i]), p.scale_log2, nm);
+              mx8[i] = fmaxf(mx8[i], t);
+              e[i] = fast_exp2(t);
+              rs8[i] += e[i];
+            }
+            uint4 o;
+            o.x = pack_bf16x2(e[0], e[1]);
+            o.y = pack_bf16x2(e[2], e[3]);
+            o.z = pack_bf16x2(e[4], e[5]);
+            o.w = pack_bf16x2(e[6], e[7]);
+            const int c8 = c * 4 + i4;
+            sts_v4(p_a + (c8 >> 3) * kTileBytes + (((c8 & 7) ^ swz) << 4), o);
           }
-          tmem_st_wait();
-        }
-        l *= c;
-        m_used = m_new;
-      }
-      // pass 2: p = 2^(s * scale - m), row sum, bf16 P into the swizzled K-major tile
-      float rs = 0.f;
-      const float nm = -m_used;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS[g] + lane_off + c * 32, v);
+        };
         tmem_ld_wait();
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {  // 8 keys per 16-byte chunk
-          float e[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            e[i] = fast_exp2(fmaf(__uint_as_float(v[i4 * 8 + i]), p.scale_log2, nm));
-            rs += e[i];
-          }
-          uint4 o;
-          o.x = pack_bf16x2(e[0], e[1]);
-          o.y = pack_bf16x2(e[2], e[3]);
-          o.z = pack_bf16x2(e[4], e[5]);
-          o.w = pack_bf16x2(e[6], e[7]);
-          const int c8 = c * 4 + i4;
-          sts_v4(p_a + (c8 >> 3) * kTileBytes + (((c8 & 7) ^ swz) << 4), o);
+        tmem_ld_32x32(tS[g] + lane_off + 32, vb);
+        chunk(va, 0);
+        tmem_ld_wait();
+        tmem_ld_32x32(tS[g] + lane_off + 64, va);
+        chunk(vb, 1);
+        tmem_ld_wait();
+        tmem_ld_32x32(tS[g] + lane_off + 96, vb);
+        chunk(va, 2);
+        tmem_ld_wait();
+        chunk(vb, 3);
+        rs = ((rs8[0] + rs8[1]) + (rs8[2] + rs8[3])) + ((rs8[4] + rs8[5]) + (rs8[6] + rs8[7]));
+        mrel = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                     fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+        // a row whose scores outgrew the reference by more than 2^64 would overflow: adopt the new max NOW (rescale
+        // O_g, which nobody is accumulating into at this point) and redo the pass.  Practically never taken.
+        if (attempt == 0 && __any_sync(0xffffffffu, mrel > 64.f)) {
+          const float c = mrel > 64.f ? fast_exp2(-mrel) : 1.f;
+          if (j > 0) rescale_o(c);
+          l *= c;
+          if (mrel > 64.f) m_used += mrel;
+          continue;
         }
+        break;
       }
       l += rs;
+      if (mrel > kRescaleThreshold) {  // adopt the larger max; O_g is rescaled when PV_g(j) has landed (next block)
+        c_pend = fast_exp2(-mrel);
+        l *= c_pend;
+        m_used += mrel;
+      }
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -285,7 +319,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams
     // epilogue: O / l -> bf16, lse
     mbar_wait(&pv_done[g], ph ^ 1);
     tc_fence_after();
-    const float inv = 1.f / l;
+    const float inv = c_pend / l;   // (a rescale still pending from the last block folds into the normalisation)
     const int t = q0 + g * 128 + row;
     __nv_bfloat16* op = p.out + (static_cast<size_t>(n) * p.T + t) * p.ldo + h * HD;
 #pragma unroll
@@ -306,6 +340,432 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams
     p.lse[static_cast<size_t>(bh) * p.T + t] = m_used + log2f(l);
   }
 
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Backward on tcgen05.  With P_ij = 2^(s_ij * scale_log2 - lse_i), dP = dO V^T, dS = P o (dP - D_i) (D = rowsum(dO o O),
+// attn_bwd_prep_kernel):   dV = P^T dO,   dK = scale * dS^T Q,   dQ = scale * dS K.
+// Two kernels, as the mma.sync version (no atomics): dK / dV per 128-key tile looping over the query blocks, dQ per
+// 128-query tile looping over the key blocks.  320 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9
+// elementwise: thread = (accumulator row, column half) — two warps share a TMEM lane quarter and split the 128 columns.
+// Per block two "score" MMAs (K = ch) fill S and dP in TMEM, the elementwise warps turn them into bf16 P / dS tiles in
+// shared memory (128B-swizzled K-major, the conflict-free 16-byte stores of the forward), two (dK/dV) or one (dQ)
+// accumulation MMAs (K = 128) consume them.  Every global operand tile is the same (64 channels x 128 rows) TMA box as in
+// the forward and serves as K-major operand of the score MMAs AND as MN-major operand of the accumulation MMAs.
+// ----------------------------------------------------------------------------------------------------------------------
+struct AttnBwdParams {
+  const float* lse;   // [N*heads][T], log2 domain
+  const float* D;     // [N*heads][T]
+  __nv_bfloat16* dqkv;
+  int lddqkv, T, heads, hstride, koff, voff;
+  float scale_log2, scale;
+};
+
+// P / dS tile writer: row r of a [128 rows][128 cols] bf16 K-major tile (two 64-column slabs), columns [hc*64, +64)
+__device__ __forceinline__ void store_row_half(uint32_t tile_a, int r, int hc, int c, const float (&e)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(e[0], e[1]);
+  o.y = pack_bf16x2(e[2], e[3]);
+  o.z = pack_bf16x2(e[4], e[5]);
+  o.w = pack_bf16x2(e[6], e[7]);
+  sts_v4(tile_a + hc * kTileBytes + r * 128 + ((c ^ (r & 7)) << 4), o);
+}
+
+// ---- dK, dV: CTA = (128-key tile, image, head); loop over query blocks ------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                       const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + kTileBytes;
+  uint8_t* sQD = smem + 2 * kTileBytes;            // 2 stages x (Q_i tile, dO_i tile)
+  uint8_t* sPT = sQD + 4 * kTileBytes;             // P^T  [keys][queries], 2 slabs
+  uint8_t* sDS = sPT + 2 * kTileBytes;             // dS^T [keys][queries], 2 slabs
+  float* sVec = reinterpret_cast<float*>(sDS + 2 * kTileBytes);  // 2 x (lse[128] | D[128])
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sVec + 2 * 256);
+  uint64_t* kv_full = bars;          // 1
+  uint64_t* st_full = bars + 1;      // 2
+  uint64_t* st_empty = bars + 3;     // 2
+  uint64_t* sdp_full = bars + 5;     // 1
+  uint64_t* pds_full = bars + 6;     // 1 (8 warps)
+  uint64_t* acc_done = bars + 7;     // 1
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int n = bh / p.heads, h = bh % p.heads;
+  const int k0 = blockIdx.x * 128;
+  const int nq = p.T / 128;
+  const int row0 = n * p.T;
+  const int cq = h * p.hstride, ck = cq + p.koff, cv = cq + p.voff;
+  const int cdo = h * HD;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&st_full[i], 1);
+      mbar_init(&st_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 8);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(kv_full, 2 * kTileBytes);
+      tma_load_2d(sK, &tmQKV, kv_full, ck, row0 + k0);
+      tma_load_2d(sV, &tmQKV, kv_full, cv, row0 + k0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nq; ++i) {
+        mbar_wait(&st_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&st_full[stage], 2 * kTileBytes);
+        uint8_t* st = sQD + stage * 2 * kTileBytes;
+        tma_load_2d(st, &tmQKV, &st_full[stage], cq, row0 + i * 128);
+        tma_load_2d(st + kTileBytes, &tmDO, &st_full[stage], cdo, row0 + i * 128);
+        if (++stage == 2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
+    const uint64_t k_desc = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+    const uint64_t v_desc = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
+    const uint64_t pt_desc = make_smem_desc_sw128(smem_u32(sPT), 16, 1024);
+    const uint64_t ds_desc = make_smem_desc_sw128(smem_u32(sDS), 16, 1024);
+    auto issue_scores = [&](int stage) {
+      const uint32_t st = smem_u32(sQD + stage * 2 * kTileBytes);
+      const uint64_t q_desc = make_smem_desc_sw128(st, 16, 1024);
+      const uint64_t do_desc = make_smem_desc_sw128(st + kTileBytes, 16, 1024);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tS, k_desc + 2 * k, q_desc + 2 * k, idesc_s, k != 0);    // S^T = K Q^T
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tDP, v_desc + 2 * k, do_desc + 2 * k, idesc_s, k != 0);  // dP^T = V dO^T
+        umma_commit(sdp_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    mbar_wait(&st_full[0], 0);
+    tc_fence_after();
+    issue_scores(0);
+    int stage = 0;
+    uint32_t phase = 0, eph = 0;
+    for (int i = 0; i < nq; ++i) {
+      mbar_wait(pds_full, eph);
+      tc_fence_after();
+      const uint32_t st = smem_u32(sQD + stage * 2 * kTileBytes);
+      const uint64_t q_mn = make_smem_desc_sw128(st, 8192, 1024);                 // Q_i  [queries][ch] as MN-major B
+      const uint64_t do_mn = make_smem_desc_sw128(st + kTileBytes, 8192, 1024);   // dO_i
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t off = ((k >> 2) * (kTileBytes >> 4)) + 2 * (k & 3);
+          umma_bf16(tDV, pt_desc + off, do_mn + k * 128, idesc_acc, (i > 0 || k != 0) ? 1u : 0u);  // dV += P^T dO
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t off = ((k >> 2) * (kTileBytes >> 4)) + 2 * (k & 3);
+          umma_bf16(tDK, ds_desc + off, q_mn + k * 128, idesc_acc, (i > 0 || k != 0) ? 1u : 0u);   // dK += dS^T Q
+        }
+        umma_commit(acc_done);
+        umma_commit(&st_empty[stage]);
+      }
+      __syncwarp();
+      if (++stage == 2) {
+        stage = 0;
+        phase ^= 1;
+      }
+      eph ^= 1;
+      if (i + 1 < nq) {
+        mbar_wait(&st_full[stage], phase);
+        tc_fence_after();
+        issue_scores(stage);
+      }
+    }
+  } else {
+    // elementwise warps: thread = (key row r, query-column half hc)
+    const int q = warp & 3;
+    const int hc = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const int vi = threadIdx.x - 64;  // 0..255: which float of (lse | D) this thread stages
+    const float* vsrc = (vi < 128 ? p.lse : p.D) + static_cast<size_t>(bh) * p.T + (vi & 127);
+    const uint32_t pt_a = smem_u32(sPT), ds_a = smem_u32(sDS);
+    uint32_t ph = 0;
+    for (int i = 0; i < nq; ++i) {
+      const float myv = vsrc[i * 128];
+      float* vec = sVec + (i & 1) * 256;
+      vec[vi] = myv;
+      mbar_wait(sdp_full, ph);
+      tc_fence_after();
+      if (i > 0) {  // the accumulation MMAs of block i-1 have read P^T / dS^T (they were issued before S, dP of block i)
+        mbar_wait(acc_done, ph ^ 1);
+      }
+      bar_sync(1, 256);  // lse / D of this query block are staged
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tS + lane_off + hc * 64 + c * 32, sv);
+        tmem_ld_32x32(tDP + lane_off + hc * 64 + c * 32, dv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          float pe[8], de[8];
+          const int col = hc * 64 + c * 32 + i4 * 8;
+          const float4 l0 = *reinterpret_cast<const float4*>(vec + col), l1 = *reinterpret_cast<const float4*>(vec + col + 4);
+          const float4 d0 = *reinterpret_cast<const float4*>(vec + 128 + col);
+          const float4 d1 = *reinterpret_cast<const float4*>(vec + 128 + col + 4);
+          const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+          const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            pe[k] = fast_exp2(fmaf(__uint_as_float(sv[i4 * 8 + k]), p.scale_log2, -ls[k]));
+            de[k] = pe[k] * (__uint_as_float(dv[i4 * 8 + k]) - dd[k]);
+          }
+          store_row_half(pt_a, r, hc, c * 4 + i4, pe);
+          store_row_half(ds_a, r, hc, c * 4 + i4, de);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      ph ^= 1;
+    }
+    // epilogue: warps of half 0 write dV, half 1 write dK (* scale)
+    mbar_wait(acc_done, ph ^ 1);
+    tc_fence_after();
+    const float mul = hc == 0 ? 1.f : p.scale;
+    __nv_bfloat16* op = p.dqkv + (static_cast<size_t>(n) * p.T + k0 + r) * p.lddqkv + (hc == 0 ? cv : ck);
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32((hc == 0 ? tDV : tDK) + lane_off + c * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(o[i * 8 + 0]) * mul, __uint_as_float(o[i * 8 + 1]) * mul);
+        w.y = pack_bf16x2(__uint_as_float(o[i * 8 + 2]) * mul, __uint_as_float(o[i * 8 + 3]) * mul);
+        w.z = pack_bf16x2(__uint_as_float(o[i * 8 + 4]) * mul, __uint_as_float(o[i * 8 + 5]) * mul);
+        w.w = pack_bf16x2(__uint_as_float(o[i * 8 + 6]) * mul, __uint_as_float(o[i * 8 + 7]) * mul);
+        *reinterpret_cast<uint4*>(op + c * 32 + i * 8) = w;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---- dQ: CTA = (128-query tile, image, head); loop over key blocks -----------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                      const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sDO = smem + kTileBytes;
+  uint8_t* sKV = smem + 2 * kTileBytes;            // 2 stages x (K_j, V_j)
+  uint8_t* sDS = sKV + 4 * kTileBytes;             // dS [queries][keys], 2 slabs
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * kTileBytes);
+  uint64_t* qd_full = bars;          // 1
+  uint64_t* st_full = bars + 1;      // 2
+  uint64_t* st_empty = bars + 3;     // 2
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* ds_full = bars + 6;      // 8 warps
+  uint64_t* acc_done = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int n = bh / p.heads, h = bh % p.heads;
+  const int q0 = blockIdx.x * 128;
+  const int nk = p.T / 128;
+  const int row0 = n * p.T;
+  const int cq = h * p.hstride, ck = cq + p.koff, cv = cq + p.voff;
+  const int cdo = h * HD;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(qd_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&st_full[i], 1);
+      mbar_init(&st_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(ds_full, 8);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDQ = tmem + 256;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(qd_full, 2 * kTileBytes);
+      tma_load_2d(sQ, &tmQKV, qd_full, cq, row0 + q0);
+      tma_load_2d(sDO, &tmDO, qd_full, cdo, row0 + q0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nk; ++j) {
+        mbar_wait(&st_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&st_full[stage], 2 * kTileBytes);
+        uint8_t* st = sKV + stage * 2 * kTileBytes;
+        tma_load_2d(st, &tmQKV, &st_full[stage], ck, row0 + j * 128);
+        tma_load_2d(st + kTileBytes, &tmQKV, &st_full[stage], cv, row0 + j * 128);
+        if (++stage == 2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
+    const uint64_t q_desc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t do_desc = make_smem_desc_sw128(smem_u32(sDO), 16, 1024);
+    const uint64_t ds_desc = make_smem_desc_sw128(smem_u32(sDS), 16, 1024);
+    auto issue_scores = [&](int stage) {
+      const uint32_t st = smem_u32(sKV + stage * 2 * kTileBytes);
+      const uint64_t k_desc = make_smem_desc_sw128(st, 16, 1024);
+      const uint64_t v_desc = make_smem_desc_sw128(st + kTileBytes, 16, 1024);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tS, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);     // S = Q K^T
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tDP, do_desc + 2 * k, v_desc + 2 * k, idesc_s, k != 0);   // dP = dO V^T
+        umma_commit(sdp_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(qd_full, 0);
+    mbar_wait(&st_full[0], 0);
+    tc_fence_after();
+    issue_scores(0);
+    int stage = 0;
+    uint32_t phase = 0, eph = 0;
+    for (int j = 0; j < nk; ++j) {
+      mbar_wait(ds_full, eph);
+      tc_fence_after();
+      const uint64_t k_mn = make_smem_desc_sw128(smem_u32(sKV + stage * 2 * kTileBytes), 8192, 1024);  // K_j as MN-major B
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t off = ((k >> 2) * (kTileBytes >> 4)) + 2 * (k & 3);
+          umma_bf16(tDQ, ds_desc + off, k_mn + k * 128, idesc_acc, (j > 0 || k != 0) ? 1u : 0u);  // dQ += dS K
+        }
+        umma_commit(acc_done);
+        umma_commit(&st_empty[stage]);
+      }
+      __syncwarp();
+      if (++stage == 2) {
+        stage = 0;
+        phase ^= 1;
+      }
+      eph ^= 1;
+      if (j + 1 < nk) {
+        mbar_wait(&st_full[stage], phase);
+        tc_fence_after();
+        issue_scores(stage);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int hc = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float nl = -p.lse[static_cast<size_t>(bh) * p.T + q0 + r];
+    const float Dr = p.D[static_cast<size_t>(bh) * p.T + q0 + r];
+    const uint32_t ds_a = smem_u32(sDS);
+    uint32_t ph = 0;
+    for (int j = 0; j < nk; ++j) {
+      mbar_wait(sdp_full, ph);
+      tc_fence_after();
+      if (j > 0) mbar_wait(acc_done, ph ^ 1);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tS + lane_off + hc * 64 + c * 32, sv);
+        tmem_ld_32x32(tDP + lane_off + hc * 64 + c * 32, dv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          float de[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float pe = fast_exp2(fmaf(__uint_as_float(sv[i4 * 8 + k]), p.scale_log2, nl));
+            de[k] = pe * (__uint_as_float(dv[i4 * 8 + k]) - Dr);
+          }
+          store_row_half(ds_a, r, hc, c * 4 + i4, de);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+      ph ^= 1;
+    }
+    mbar_wait(acc_done, ph ^ 1);
+    tc_fence_after();
+    if (hc == 0) {
+      __nv_bfloat16* op = p.dqkv + (static_cast<size_t>(n) * p.T + q0 + r) * p.lddqkv + cq;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32(tDQ + lane_off + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[i * 8 + 0]) * p.scale, __uint_as_float(o[i * 8 + 1]) * p.scale);
+          w.y = pack_bf16x2(__uint_as_float(o[i * 8 + 2]) * p.scale, __uint_as_float(o[i * 8 + 3]) * p.scale);
+          w.z = pack_bf16x2(__uint_as_float(o[i * 8 + 4]) * p.scale, __uint_as_float(o[i * 8 + 5]) * p.scale);
+          w.w = pack_bf16x2(__uint_as_float(o[i * 8 + 6]) * p.scale, __uint_as_float(o[i * 8 + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(op + c * 32 + i * 8) = w;
+        }
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -353,6 +813,54 @@ int launch_attn_fwd_tc(const void* qkv, int ldqkv, void* out, int ldo, float* ls
       attr = true;
     }
     attn_fwd_tc_kernel<64><<<grid, kTcThreads, smem, stream>>>(tm, p);
+  }
+  JG_LAUNCH_CHECK();
+  return JG_OK;
+}
+
+// Backward (dq, dk, dv into dqkv) after attn_bwd_prep_kernel has filled D; JG_ERR_UNSUPPORTED -> mma.sync kernels.
+int launch_attn_bwd_tc(const void* qkv, int ldqkv, const void* d_out, int lddo, const float* lse, const float* D,
+                       void* dqkv, int lddqkv, int N, int T, int heads, int ch, int hstride, int koff, int voff,
+                       float scale_log2, float scale, cudaStream_t stream) {
+  if (!(ch == 32 || ch == 64) || T % 128 != 0 || ldqkv % 8 != 0 || lddo % 8 != 0 || lddqkv % 8 != 0)
+    return JG_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15) ||
+      (reinterpret_cast<uintptr_t>(dqkv) & 15))
+    return JG_ERR_UNSUPPORTED;
+  CUtensorMap tmQ, tmD;
+  {
+    uint64_t dims[2] = {(uint64_t)ldqkv, (uint64_t)N * T};
+    uint64_t strides[1] = {(uint64_t)ldqkv * 2};
+    uint32_t box[2] = {64, 128};
+    uint32_t es[2] = {1, 1};
+    int rc = make_tmap_bf16(&tmQ, qkv, 2, dims, strides, box, es);
+    if (rc) return rc;
+    uint64_t dims2[2] = {(uint64_t)lddo, (uint64_t)N * T};
+    uint64_t strides2[1] = {(uint64_t)lddo * 2};
+    rc = make_tmap_bf16(&tmD, d_out, 2, dims2, strides2, box, es);
+    if (rc) return rc;
+  }
+  AttnBwdParams p;
+  p.lse = lse; p.D = D; p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.lddqkv = lddqkv; p.T = T; p.heads = heads; p.hstride = hstride; p.koff = koff; p.voff = voff;
+  p.scale_log2 = scale_log2; p.scale = scale;
+  const int smem_kv = 10 * kTileBytes + 2 * 256 * 4 + 16 * 8 + 1024;
+  const int smem_q = 8 * kTileBytes + 16 * 8 + 1024;
+  dim3 grid(T / 128, N * heads);
+  static bool attr = false;
+  if (!attr) {
+    JG_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
+    JG_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
+    JG_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q));
+    JG_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q));
+    attr = true;
+  }
+  if (ch == 32) {
+    attn_bwd_dq_tc_kernel<32><<<grid, kTcThreads, smem_q, stream>>>(tmQ, tmD, p);
+    attn_bwd_dkv_tc_kernel<32><<<grid, kTcThreads, smem_kv, stream>>>(tmQ, tmD, p);
+  } else {
+    attn_bwd_dq_tc_kernel<64><<<grid, kTcThreads, smem_q, stream>>>(tmQ, tmD, p);
+    attn_bwd_dkv_tc_kernel<64><<<grid, kTcThreads, smem_kv, stream>>>(tmQ, tmD, p);
   }
   JG_LAUNCH_CHECK();
   return JG_OK;
