@@ -353,13 +353,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams
 // Backward on tcgen05.  With P_ij = 2^(s_ij * scale_log2 - lse_i), dP = dO V^T, dS = P o (dP - D_i) (D = rowsum(dO o O),
 // attn_bwd_prep_kernel):   dV = P^T dO,   dK = scale * dS^T Q,   dQ = scale * dS K.
 // Two kernels, as the mma.sync version (no atomics): dK / dV per 128-key tile looping over the query blocks, dQ per
-// 128-query tile looping over the key blocks.  320 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9
+// 128-query tile looping over the key blocks.  576 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2..17
 // elementwise: thread = (accumulator row, column half) — two warps share a TMEM lane quarter and split the 128 columns.
 // Per block two "score" MMAs (K = ch) fill S and dP in TMEM, the elementwise warps turn them into bf16 P / dS tiles in
 // shared memory (128B-swizzled K-major, the conflict-free 16-byte stores of the forward), two (dK/dV) or one (dQ)
 // accumulation MMAs (K = 128) consume them.  Every global operand tile is the same (64 channels x 128 rows) TMA box as in
 // the forward and serves as K-major operand of the score MMAs AND as MN-major operand of the accumulation MMAs.
 // ----------------------------------------------------------------------------------------------------------------------
+// 16 elementwise warps: thread = (accumulator row, column quarter of 32) — four warps per SM sub-partition hide the
+// MUFU / TMEM-load latencies that two could not (ncu on the forward: issue slots 36 % busy with 8 softmax warps).
+constexpr int kBwdThreads = 64 + 16 * 32;
+
 struct AttnBwdParams {
   const float* lse;   // [N*heads][T], log2 domain
   const float* D;     // [N*heads][T]
@@ -368,8 +372,9 @@ struct AttnBwdParams {
   float scale_log2, scale;
 };
 
-// P / dS tile writer: row r of a [128 rows][128 cols] bf16 K-major tile (two 64-column slabs), columns [hc*64, +64)
-__device__ __forceinline__ void store_row_half(uint32_t tile_a, int r, int hc, int c, const float (&e)[8]) {
+// P / dS tile writer: row r of a [128 rows][128 cols] bf16 K-major tile (two 64-column slabs), columns [hq*32 + c4*8, +8)
+__device__ __forceinline__ void store_row_quarter(uint32_t tile_a, int r, int hq, int c4, const float (&e)[8]) {
+  const int hc = hq >> 1, c = (hq & 1) * 4 + c4;  // slab of 64 columns, 16-byte chunk inside the slab's 128-byte row
   uint4 o;
   o.x = pack_bf16x2(e[0], e[1]);
   o.y = pack_bf16x2(e[2], e[3]);
@@ -380,7 +385,7 @@ __device__ __forceinline__ void store_row_half(uint32_t tile_a, int r, int hc, i
 
 // ---- dK, dV: CTA = (128-key tile, image, head); loop over query blocks ------------------------------------------------
 template <int HD>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                        const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -418,7 +423,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       mbar_init(&st_empty[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 8);
+    mbar_init(pds_full, 16);
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -510,48 +515,45 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       }
     }
   } else {
-    // elementwise warps: thread = (key row r, query-column half hc)
+    // elementwise warps: thread = (key row r, query-column quarter hq)
     const int q = warp & 3;
-    const int hc = (warp - 2) >> 2;
+    const int hq = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const int vi = threadIdx.x - 64;  // 0..255: which float of (lse | D) this thread stages
+    const int vi = threadIdx.x - 64;  // 0..511: threads 0..255 stage one float of (lse | D) each
     const float* vsrc = (vi < 128 ? p.lse : p.D) + static_cast<size_t>(bh) * p.T + (vi & 127);
     const uint32_t pt_a = smem_u32(sPT), ds_a = smem_u32(sDS);
+    const uint32_t vec_a = smem_u32(sVec);
     uint32_t ph = 0;
+    float myv = vi < 256 ? vsrc[0] : 0.f;  // (fetched one block ahead: ncu had 10 % of the samples on this store's load)
     for (int i = 0; i < nq; ++i) {
-      const float myv = vsrc[i * 128];
-      float* vec = sVec + (i & 1) * 256;
-      vec[vi] = myv;
+      if (vi < 256) sts_f32(vec_a + ((i & 1) * 256 + vi) * 4, myv);
+      if (vi < 256 && i + 1 < nq) myv = vsrc[(i + 1) * 128];
       mbar_wait(sdp_full, ph);
       tc_fence_after();
       if (i > 0) {  // the accumulation MMAs of block i-1 have read P^T / dS^T (they were issued before S, dP of block i)
         mbar_wait(acc_done, ph ^ 1);
       }
-      bar_sync(1, 256);  // lse / D of this query block are staged
+      bar_sync(1, 512);  // lse / D of this query block are staged
+      uint32_t sv[32], dv[32];
+      tmem_ld_32x32(tS + lane_off + hq * 32, sv);
+      tmem_ld_32x32(tDP + lane_off + hq * 32, dv);
+      const uint32_t va = vec_a + ((i & 1) * 256 + hq * 32) * 4;
+      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tS + lane_off + hc * 64 + c * 32, sv);
-        tmem_ld_32x32(tDP + lane_off + hc * 64 + c * 32, dv);
-        tmem_ld_wait();
+      for (int i4 = 0; i4 < 4; ++i4) {
+        float pe[8], de[8];
+        const float4 l0 = lds_f4(va + i4 * 32), l1 = lds_f4(va + i4 * 32 + 16);
+        const float4 d0 = lds_f4(va + 512 + i4 * 32), d1 = lds_f4(va + 512 + i4 * 32 + 16);
+        const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          float pe[8], de[8];
-          const int col = hc * 64 + c * 32 + i4 * 8;
-          const float4 l0 = *reinterpret_cast<const float4*>(vec + col), l1 = *reinterpret_cast<const float4*>(vec + col + 4);
-          const float4 d0 = *reinterpret_cast<const float4*>(vec + 128 + col);
-          const float4 d1 = *reinterpret_cast<const float4*>(vec + 128 + col + 4);
-          const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-          const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            pe[k] = fast_exp2(fmaf(__uint_as_float(sv[i4 * 8 + k]), p.scale_log2, -ls[k]));
-            de[k] = pe[k] * (__uint_as_float(dv[i4 * 8 + k]) - dd[k]);
-          }
-          store_row_half(pt_a, r, hc, c * 4 + i4, pe);
-          store_row_half(ds_a, r, hc, c * 4 + i4, de);
+        for (int k = 0; k < 8; ++k) {
+          pe[k] = fast_exp2(fmaf(__uint_as_float(sv[i4 * 8 + k]), p.scale_log2, -ls[k]));
+          de[k] = pe[k] * (__uint_as_float(dv[i4 * 8 + k]) - dd[k]);
         }
+        store_row_quarter(pt_a, r, hq, i4, pe);
+        store_row_quarter(ds_a, r, hq, i4, de);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -559,13 +561,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       if (lane == 0) mbar_arrive(pds_full);
       ph ^= 1;
     }
+    const int hc = hq;  // epilogue roles: quarter 0 writes dV, quarter 1 dK; 2 and 3 are done
     // epilogue: warps of half 0 write dV, half 1 write dK (* scale)
     mbar_wait(acc_done, ph ^ 1);
     tc_fence_after();
     const float mul = hc == 0 ? 1.f : p.scale;
     __nv_bfloat16* op = p.dqkv + (static_cast<size_t>(n) * p.T + k0 + r) * p.lddqkv + (hc == 0 ? cv : ck);
 #pragma unroll
-    for (int c = 0; c < HD / 32; ++c) {
+    for (int c = 0; c < (hc < 2 ? HD / 32 : 0); ++c) {
       uint32_t o[32];
       tmem_ld_32x32((hc == 0 ? tDV : tDK) + lane_off + c * 32, o);
       tmem_ld_wait();
@@ -590,7 +593,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
 
 // ---- dQ: CTA = (128-query tile, image, head); loop over key blocks -----------------------------------------------------
 template <int HD>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                       const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -626,7 +629,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       mbar_init(&st_empty[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(ds_full, 8);
+    mbar_init(ds_full, 16);
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -711,7 +714,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     }
   } else {
     const int q = warp & 3;
-    const int hc = (warp - 2) >> 2;
+    const int hq = (warp - 2) >> 2;   // column quarter
+    const int hc = hq;
     const int r = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float nl = -p.lse[static_cast<size_t>(bh) * p.T + q0 + r];
@@ -722,22 +726,19 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       mbar_wait(sdp_full, ph);
       tc_fence_after();
       if (j > 0) mbar_wait(acc_done, ph ^ 1);
+      uint32_t sv[32], dv[32];
+      tmem_ld_32x32(tS + lane_off + hq * 32, sv);
+      tmem_ld_32x32(tDP + lane_off + hq * 32, dv);
+      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tS + lane_off + hc * 64 + c * 32, sv);
-        tmem_ld_32x32(tDP + lane_off + hc * 64 + c * 32, dv);
-        tmem_ld_wait();
+      for (int i4 = 0; i4 < 4; ++i4) {
+        float de[8];
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          float de[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float pe = fast_exp2(fmaf(__uint_as_float(sv[i4 * 8 + k]), p.scale_log2, nl));
-            de[k] = pe * (__uint_as_float(dv[i4 * 8 + k]) - Dr);
-          }
-          store_row_half(ds_a, r, hc, c * 4 + i4, de);
+        for (int k = 0; k < 8; ++k) {
+          const float pe = fast_exp2(fmaf(__uint_as_float(sv[i4 * 8 + k]), p.scale_log2, nl));
+          de[k] = pe * (__uint_as_float(dv[i4 * 8 + k]) - Dr);
         }
+        store_row_quarter(ds_a, r, hq, i4, de);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -856,11 +857,11 @@ int launch_attn_bwd_tc(const void* qkv, int ldqkv, const void* d_out, int lddo, 
     attr = true;
   }
   if (ch == 32) {
-    attn_bwd_dq_tc_kernel<32><<<grid, kTcThreads, smem_q, stream>>>(tmQ, tmD, p);
-    attn_bwd_dkv_tc_kernel<32><<<grid, kTcThreads, smem_kv, stream>>>(tmQ, tmD, p);
+    attn_bwd_dq_tc_kernel<32><<<grid, kBwdThreads, smem_q, stream>>>(tmQ, tmD, p);
+    attn_bwd_dkv_tc_kernel<32><<<grid, kBwdThreads, smem_kv, stream>>>(tmQ, tmD, p);
   } else {
-    attn_bwd_dq_tc_kernel<64><<<grid, kTcThreads, smem_q, stream>>>(tmQ, tmD, p);
-    attn_bwd_dkv_tc_kernel<64><<<grid, kTcThreads, smem_kv, stream>>>(tmQ, tmD, p);
+    attn_bwd_dq_tc_kernel<64><<<grid, kBwdThreads, smem_q, stream>>>(tmQ, tmD, p);
+    attn_bwd_dkv_tc_kernel<64><<<grid, kBwdThreads, smem_kv, stream>>>(tmQ, tmD, p);
   }
   JG_LAUNCH_CHECK();
   return JG_OK;
