@@ -17,7 +17,9 @@ UNetVid 8 x 128^2 (1 clip/GPU): same step definition through their trainers.
   roofline: bound "tensor".  `frac` is STEP-LEVEL: algorithmic FLOPs of the whole step / step
             time / measured sustained cuBLAS bf16 peak.  `conv` carries the implicit-GEMM family alone: FLOPs actually
             issued by the conv launches (de-padded) / their summed CUDA-event duration in an instrumented eager pass.
-            `traffic` is null: DRAM bytes cannot be measured inside the run (ncu captures live under profiles/).
+            `traffic` = DRAM read + write bytes of the implicit-GEMM launches of ONE step from the committed ncu launch
+            list of the same step (profiles/r02_conv_traffic.json, config 2 only; null otherwise): DRAM bytes cannot be
+            measured inside a timed run.
   cpu_baseline / --impl reference: the UNMODIFIED reference (baseline/_ref, staged by baseline/install_ref.py) driven
             through options -> create_model -> optimize_parameters() on the host cores (kind "reference"); the oracle
             port only if the staged reference is missing (kind "port").
@@ -343,6 +345,19 @@ def build_workload(args, rank, world):
     return tr, host, B, name, None
 
 
+def ncu_conv_traffic(args):
+    """DRAM bytes per step of the implicit-GEMM launches (ncu launch list committed under profiles/), config 2 at the
+    default size only; None when there is no capture for the workload."""
+    if args.config != 2 or tuple(args.size) != tuple(CONFIG_INFO[2]["size"]):
+        return None
+    path = os.path.join(ROOT, "profiles", "r02_conv_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_total"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -482,7 +497,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": ncu_conv_traffic(args),
                          "what": "STEP-LEVEL: %s FLOPs of one step (%.2f TFLOP) / device time of the whole step"
                                  % ("algorithmic (SURVEY.md 8d, 3 x forward)" if alg_flops_step is not None
                                     else "issued implicit-GEMM", step_flops / 1e12),
@@ -493,7 +508,9 @@ def main():
                                   "share_of_step": conv_ms / ms,
                                   "what": "FLOPs issued by the implicit-GEMM launches (de-padded shapes) / their summed "
                                           "CUDA-event time in an instrumented eager pass"},
-                         "traffic_note": "DRAM bytes come from ncu captures (profiles/), not from this run",
+                         "traffic_note": "DRAM read+write bytes of the implicit-GEMM launches of one step, from the "
+                                         "committed ncu launch list profiles/r02_step_launches.csv (tools/ncu_traffic.py)"
+                                         "; algorithmic operand bytes of the same launches: see DESIGN.md 3.1",
                          "peak_source": peaks["source"]},
         }
         if world > 1 and getattr(tr, "comm_stats", None):

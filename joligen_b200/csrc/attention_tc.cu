@@ -784,9 +784,10 @@ int launch_attn_fwd_tc(const void* qkv, int ldqkv, void* out, int ldo, float* ls
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return JG_ERR_UNSUPPORTED;
   CUtensorMap tm;
   {
-    // channels x rows; a box may reach past the last channel of the buffer row (zero fill) but never past ldqkv's
-    // logical width: dims[0] is the row width in channels
-    uint64_t dims[2] = {(uint64_t)ldqkv, (uint64_t)N * T};
+    // channels x rows.  dims[0] is the LOGICAL width (3 * heads * ch), not the row stride: the operand may be a channel
+    // slice of a wider buffer, and a 64-channel box of the last head must end in the TMA unit's zero fill, not in the
+    // neighbour's channels (or, on the last row, past the allocation)
+    uint64_t dims[2] = {(uint64_t)3 * heads * ch, (uint64_t)N * T};
     uint64_t strides[1] = {(uint64_t)ldqkv * 2};
     uint32_t box[2] = {64, 128};
     uint32_t es[2] = {1, 1};
@@ -830,13 +831,13 @@ int launch_attn_bwd_tc(const void* qkv, int ldqkv, const void* d_out, int lddo, 
     return JG_ERR_UNSUPPORTED;
   CUtensorMap tmQ, tmD;
   {
-    uint64_t dims[2] = {(uint64_t)ldqkv, (uint64_t)N * T};
+    uint64_t dims[2] = {(uint64_t)3 * heads * ch, (uint64_t)N * T};   // logical widths (see the forward)
     uint64_t strides[1] = {(uint64_t)ldqkv * 2};
     uint32_t box[2] = {64, 128};
     uint32_t es[2] = {1, 1};
     int rc = make_tmap_bf16(&tmQ, qkv, 2, dims, strides, box, es);
     if (rc) return rc;
-    uint64_t dims2[2] = {(uint64_t)lddo, (uint64_t)N * T};
+    uint64_t dims2[2] = {(uint64_t)heads * ch, (uint64_t)N * T};
     uint64_t strides2[1] = {(uint64_t)lddo * 2};
     rc = make_tmap_bf16(&tmD, d_out, 2, dims2, strides2, box, es);
     if (rc) return rc;

@@ -235,6 +235,32 @@ def test_attention_fwd_bwd(K, case):
     assert rel(K.nhwc_to_nchw(dqkv).reshape(n, 3 * c, t), qr.grad) < 1.5e-2
 
 
+def test_attention_sliced_operands_tc_path(K):
+    """The tcgen05 path with out / d_out as the SECOND channel half of a wider buffer that ends exactly at its
+    allocation (AttentionBlockRef writes both attentions into the halves of one tensor, unet_generator_attn.py:1098-1130):
+    the TMA boxes of the last head must end in zero fill, never past the slice (regression: illegal memory access in the
+    cfg 4 step)."""
+    from oracle.palette_oracle import qkv_attention_legacy
+    n, t, heads, ch = 2, 256, 4, 32
+    c = heads * ch
+    g = torch.Generator().manual_seed(5)
+    qkv = bf16_round(torch.randn(n, 3 * c, t, generator=g))
+    qr = qkv.clone().requires_grad_(True)
+    ref = qkv_attention_legacy(qr, heads)
+    do = bf16_round(torch.randn(ref.shape, generator=g))
+    ref.backward(do)
+    qkv_d = K.nchw_to_nhwc(qkv.reshape(n, 3 * c, 16, 16).cuda())
+    wide = torch.zeros(n, 16, 16, 2 * c, dtype=torch.bfloat16, device="cuda")
+    out, lse = K.attn_fwd(qkv_d, heads, ch, out=wide[..., c:])
+    assert rel(K.nhwc_to_nchw(out.contiguous()).reshape(n, c, t), ref.detach()) < 1e-2
+    assert float(wide[..., :c].abs().max()) == 0.0
+    dwide = torch.zeros(n, 16, 16, 2 * c, dtype=torch.bfloat16, device="cuda")
+    dwide[..., c:] = K.nchw_to_nhwc(do.reshape(n, c, 16, 16).cuda())
+    dqkv = K.attn_bwd(qkv_d, out, dwide[..., c:], lse, heads, ch)
+    torch.cuda.synchronize()
+    assert rel(K.nhwc_to_nchw(dqkv).reshape(n, 3 * c, t), qr.grad) < 1.5e-2
+
+
 def test_layout_resample_concat_bit_exact(K):
     g = torch.Generator().manual_seed(1)
     x = bf16_round(torch.randn(2, 24, 16, 16, generator=g))
