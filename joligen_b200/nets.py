@@ -725,19 +725,57 @@ class DiffusionGenerator(nn.Module):
         return ops.palette_loss(noise_hat, noise.contiguous().float(), None if mask is None else mask.contiguous(),
                                 w.contiguous() if use_minsnr else None, lambda_G, l1)
 
+    def _sampling_conditioner(self, cls, mask):
+        """What the samplers need of PaletteDenoiseFn's conditioning (palette_denoise_fn.py:95-108, called once per
+        reverse step by p_mean_variance, diffusion_generator.py:213-246): the class embedding appended to the
+        noise-level embedding, and the per-pixel mask embedding behind the (y_cond | y_t) channels of every step's
+        UNet input (the step kernel writes the images; the embedding channels are refilled by `fill`)."""
+        dn = self.denoise_fn
+        conditioning = getattr(dn, "conditioning", "")
+        if "class" in conditioning and cls is None:
+            raise RuntimeError('restoration: conditioning "class" needs the class labels (cls)')
+        if "mask" in conditioning and mask is None:
+            raise RuntimeError('restoration: conditioning "mask" needs the mask')
+
+        class _Cond:
+            extra = dn.mask_embed_channels() if hasattr(dn, "mask_embed_channels") else 0
+
+            @staticmethod
+            def first_input(y_cond, y_t):
+                parts = [y_cond, y_t]
+                if _Cond.extra:
+                    parts.append(y_cond.new_zeros((y_cond.shape[0], _Cond.extra) + tuple(y_cond.shape[2:])))
+                _Cond.col0 = y_cond.shape[1] + y_t.shape[1]
+                return ops.to_nhwc(torch.cat(parts, dim=1))
+
+            @staticmethod
+            def fill(x):
+                if _Cond.extra:
+                    x = ops.embed_rows_into(dn.netl_embedder_mask.embedding_table.weight, mask.contiguous(), x, _Cond.col0)
+                return x
+
+            @staticmethod
+            def embedding(emb):
+                return dn.embedding(emb, cls) if hasattr(dn, "embedding") else emb
+
+        return _Cond
+
     @torch.no_grad()
     def restoration_ddpm(self, y_cond, y_t=None, y_0=None, mask=None, sample_num=2, cls=None, guidance_scale=0.0,
                          ref=None, noise_fn=None):
-        """diffusion_generator.restoration_ddpm (:122-177) for conditioning "" (no class, no guidance; `ref` is the
-        reference image of a UNetGeneratorRefAttn denoiser):
+        """diffusion_generator.restoration_ddpm (:122-177), class / mask conditioning included, no guidance (`ref` is
+        the reference image of a UNetGeneratorRefAttn denoiser):
         num_timesteps_test UNet forwards; per step ONE fused kernel does predict_start_from_noise, the clamp, the
         posterior mean, the noise injection, the mask blend and the next step's NHWC bf16 input pack.
         noise_fn(i, shape) -> fp32 NCHW noise for step i (default torch.randn on the device; the tests replay the
         reference's CPU draws).  Returns (y_t, ret_arr) like the reference."""
-        if cls is not None or guidance_scale or getattr(self.denoise_fn, "conditioning", ""):
-            raise NotImplementedError("B200 restoration_ddpm: class / mask conditioning and guidance")
+        if guidance_scale:
+            # (the reference's guidance branch calls the denoiser with cls=None, mask=None, which its own
+            # PaletteDenoiseFn.forward cannot evaluate for class / mask conditioning: palette_denoise_fn.py:95-108)
+            raise NotImplementedError("B200 restoration_ddpm: classifier-free guidance")
         model = self.denoise_fn.model
         ref_p = self.denoise_fn.pack_ref(ref)
+        cond_in = self._sampling_conditioner(cls, mask)
         T = model.num_timesteps_test
         assert T > sample_num, "num_timesteps must greater than sample_num"
         sample_inter = T // sample_num
@@ -752,16 +790,16 @@ class DiffusionGenerator(nn.Module):
         if mask is not None:
             y_0 = y_0.contiguous().float()
             mask = mask.contiguous()
-        ld = (y_cond.shape[1] + c + 7) // 8 * 8
+        ld = (y_cond.shape[1] + c + cond_in.extra + 7) // 8 * 8
         sigma = torch.exp(0.5 * model.posterior_log_variance_clipped_test)
         table = torch.stack([model.sqrt_recip_gammas_test, model.sqrt_recipm1_gammas_test,
                              model.posterior_mean_coef1_test, model.posterior_mean_coef2_test, sigma], dim=1)
         # first input: cat([y_cond, y_t]) (every later one comes out of the step kernel)
-        x = ops.to_nhwc(torch.cat([y_cond, y_t], dim=1))
+        x = cond_in.first_input(y_cond, y_t)
         ret_arr = y_t
         for i in reversed(range(T)):
             gam = model.gammas_test[i].reshape(1, 1).expand(b, 1)
-            eps = self.denoise_fn.forward_nhwc(x, self.compute_gammas(gam), ref_p)
+            eps = self.denoise_fn.forward_nhwc(cond_in.fill(x), cond_in.embedding(self.compute_gammas(gam)), ref_p)
             noise = noise_fn(i, tuple(y_t.shape)).contiguous().float() if i > 0 else None
             coef = table[i].reshape(1, 5).expand(b, 5).contiguous()
             y_t, x = K.ddpm_step(eps, y_t, y_cond, y_0, mask, noise, coef, ld=ld, want_next_input=i > 0)
@@ -775,10 +813,11 @@ class DiffusionGenerator(nn.Module):
         """diffusion_generator.restoration_ddim (:286-347) with ddim_p_sample / ddim_p_mean_variance (:349-456):
         num_steps UNet forwards on the linear t sequence; the update is deterministic (the reference draws a noise
         tensor and does not use it), one fused kernel per step."""
-        if cls is not None or guidance_scale or getattr(self.denoise_fn, "conditioning", ""):
-            raise NotImplementedError("B200 restoration_ddim: class / mask conditioning and guidance")
+        if guidance_scale:
+            raise NotImplementedError("B200 restoration_ddim: classifier-free guidance")
         model = self.denoise_fn.model
         ref_p = self.denoise_fn.pack_ref(ref)
+        cond_in = self._sampling_conditioner(cls, mask)
         T = model.num_timesteps_test
         assert T > sample_num, "num_timesteps must greater than sample_num"
         sample_inter = T // sample_num
@@ -789,9 +828,9 @@ class DiffusionGenerator(nn.Module):
         if mask is not None:
             y_0 = y_0.contiguous().float()
             mask = mask.contiguous()
-        ld = (y_cond.shape[1] + c + 7) // 8 * 8
+        ld = (y_cond.shape[1] + c + cond_in.extra + 7) // 8 * 8
         tseq = list(np.linspace(0, T - 1, num_steps).astype(int))
-        x = ops.to_nhwc(torch.cat([y_cond, y_t], dim=1))
+        x = cond_in.first_input(y_cond, y_t)
         ret_arr = y_t
         for i in range(num_steps):
             t = int(tseq[-1 - i])
@@ -803,7 +842,8 @@ class DiffusionGenerator(nn.Module):
             c1 = torch.sqrt(g_p) / torch.sqrt(g_t)
             c2 = coef_eps - torch.sqrt(g_p) * torch.sqrt(1.0 - g_t) / torch.sqrt(g_t)
             coef = torch.stack([c1, c2, c1 * 0, c1 * 0, c1 * 0]).reshape(1, 5).expand(b, 5).contiguous().float()
-            eps = self.denoise_fn.forward_nhwc(x, self.compute_gammas(g_t.reshape(1, 1).expand(b, 1)), ref_p)
+            eps = self.denoise_fn.forward_nhwc(cond_in.fill(x),
+                                               cond_in.embedding(self.compute_gammas(g_t.reshape(1, 1).expand(b, 1))), ref_p)
             y_t, x = K.ddpm_step(eps, y_t, y_cond, y_0, mask, None, coef, ld=ld, want_next_input=i != num_steps - 1,
                                  ddim=True)
             if i % sample_inter == 0:

@@ -87,6 +87,46 @@ def main():
                "grads": {k: p.grad.detach().clone() for k, p in net.named_parameters()
                          if any(t in k for t in ("embedding_table", "cond_embed", "input_blocks.0.0", "out.2"))},
                "tables_after": {k: v.detach().clone() for k, v in net.state_dict().items() if "embedding_table" in k}}
+        if conditioning == "class_mask":
+            # sampling with both conditionings (row (f)-1): DDPM over the 8 test steps and DDIM (4 steps) of the
+            # unmodified reference, the random draws recorded by replaying the seed (as oracle/gen_golden.py)
+            scfg = O.UNetCfg(in_channel=cfg.in_channel, conditioning=conditioning, nclasses=cfg.nclasses,
+                             n_timestep_test=8, **BASE)
+            sunet = UNet(image_size=scfg.image_size, in_channel=scfg.in_channel, inner_channel=scfg.inner_channel,
+                         out_channel=scfg.out_channel, res_blocks=list(scfg.res_blocks), attn_res=list(scfg.attn_res),
+                         tanh=False, n_timestep_train=scfg.n_timestep_train, n_timestep_test=scfg.n_timestep_test,
+                         norm="groupnorm", group_norm_size=scfg.group_norm_size, cond_embed_dim=scfg.cond_embed_dim,
+                         channel_mults=scfg.channel_mults, num_heads=scfg.num_heads,
+                         num_head_channels=scfg.num_head_channels, efficient=scfg.efficient)
+            sdn = PaletteDenoiseFn(model=sunet, cond_embed_dim=scfg.cond_embed_dim, ref_embed_net="",
+                                   conditioning=conditioning, nclasses=scfg.nclasses)
+            snet = DiffusionGenerator(denoise_fn=sdn, sampling_method="ddpm", image_size=scfg.image_size,
+                                      G_ngf=scfg.inner_channel, loading_backward_compatibility=False)
+            snet.load_state_dict(params, strict=False)
+            srseed, sample_num = 61, 2
+            torch.manual_seed(srseed)
+            with torch.no_grad():
+                y, ret = snet.restoration(data["cond"], y_t=None, y_0=data["gt"], mask=data["mask"],
+                                          sample_num=sample_num, cls=data["cls"])
+            torch.manual_seed(srseed)
+            y_t0 = torch.randn_like(data["gt"])
+            noises = {i: torch.randn_like(data["gt"]) for i in reversed(range(1, scfg.n_timestep_test))}
+            sparams = {k: v.clone() for k, v in snet.state_dict().items()}   # (tables renormalised by the lookups)
+            with torch.no_grad():
+                yo, reto = O.restoration_ddpm(sparams, data["cond"], y_t0, data["gt"], data["mask"], noises, scfg,
+                                              sample_num, cls=data["cls"])
+            print("conditioned DDPM oracle vs reference: y %.2e ret %.2e" % (
+                float((yo - y).abs().max() / y.abs().max()), float((reto - ret).abs().max() / ret.abs().max())))
+            snet.sampling_method = "ddim"
+            with torch.no_grad():
+                yd, retd = snet.restoration(data["cond"], y_t=y_t0.clone(), y_0=data["gt"], mask=data["mask"],
+                                            sample_num=sample_num, cls=data["cls"], ddim_num_steps=4, ddim_eta=0.5)
+                ydo, _ = O.restoration_ddim(sparams, data["cond"], y_t0.clone(), data["gt"], data["mask"], scfg,
+                                            sample_num, num_steps=4, eta=0.5, cls=data["cls"])
+            print("conditioned DDIM oracle vs reference: y %.2e" % float((ydo - yd).abs().max() / yd.abs().max()))
+            out["sampling"] = {"n_timestep_test": 8, "rseed": srseed, "sample_num": sample_num, "y": y.clone(),
+                               "ret_arr": ret.clone(), "ddim_steps": 4, "ddim_eta": 0.5, "y_ddim": yd.clone(),
+                               "ret_arr_ddim": retd.clone()}
         torch.save(out, os.path.join(GOLDEN, "palette_cond_%s.pt" % conditioning))
         print(conditioning, "loss", out["loss"], "noise_hat absmax", float(noise_hat.abs().max()))
 

@@ -409,10 +409,29 @@ def diffusion_forward(sd, y_0, y_cond, mask, noise, t, u, cfg: UNetCfg, unet=Non
     return noise, noise_hat, w.view(-1, 1, 1, 1)
 
 
-def restoration_ddpm(sd, y_cond, y_t, y_0, mask, noises, cfg: UNetCfg, sample_num=2, unet=None):
+def _sampler_denoise(sd, y_cond, y_t, noise_level, mask, cls, cfg, unet):
+    """p_mean_variance's denoiser call (diffusion_generator.py:213-246) through PaletteDenoiseFn.forward
+    (palette_denoise_fn.py:95-108): noise-level embedding (+ class embedding), input (+ per-pixel mask embedding)."""
+    b = y_cond.shape[0]
+    eg = cfg.cond_embed_dim // 2 if "class" in cfg.conditioning else cfg.cond_embed_dim
+    emb = gamma_embedding(noise_level, eg)
+    emb = F.linear(emb, sd["cond_embed.0.weight"], sd["cond_embed.0.bias"])
+    emb = F.linear(F.silu(emb), sd["cond_embed.2.weight"], sd["cond_embed.2.bias"])
+    inp = torch.cat([y_cond, y_t], dim=1)
+    if "class" in cfg.conditioning:
+        emb = torch.cat((emb, label_embed(sd["denoise_fn.netl_embedder_class.embedding_table.weight"], cls)), dim=1)
+    if "mask" in cfg.conditioning:
+        hw = mask.shape[-1]
+        me = label_embed(sd["denoise_fn.netl_embedder_mask.embedding_table.weight"],
+                         mask.to(torch.int32).squeeze(1).flatten(1))
+        inp = torch.cat([inp, me.reshape(b, -1, hw, me.shape[-1]).permute(0, 3, 1, 2)], dim=1)
+    return unet(sd, inp, emb, cfg)
+
+
+def restoration_ddpm(sd, y_cond, y_t, y_0, mask, noises, cfg: UNetCfg, sample_num=2, unet=None, cls=None):
     """DiffusionGenerator.restoration_ddpm (diffusion_generator.py:122-177) with p_sample / p_mean_variance
-    (:192-283), predict_start_from_noise and q_posterior (diffusion_utils.py:122-137), conditioning "" and no
-    guidance.  `noises[i]` is the randn_like draw of step i (i > 0), in the reference's order.
+    (:192-283), predict_start_from_noise and q_posterior (diffusion_utils.py:122-137), class / mask conditioning
+    included, no guidance.  `noises[i]` is the randn_like draw of step i (i > 0), in the reference's order.
     Returns (y_t, ret_arr)."""
     unet = unet or unet_forward
     sched = schedule_buffers(cfg, "test")
@@ -423,10 +442,7 @@ def restoration_ddpm(sd, y_cond, y_t, y_0, mask, noises, cfg: UNetCfg, sample_nu
     for i in reversed(range(T)):
         t = torch.full((b,), i, dtype=torch.long)
         noise_level = sched["gammas_test"].gather(-1, t).reshape(b, 1)
-        emb = gamma_embedding(noise_level, cfg.cond_embed_dim)
-        emb = F.linear(emb, sd["cond_embed.0.weight"], sd["cond_embed.0.bias"])
-        emb = F.linear(F.silu(emb), sd["cond_embed.2.weight"], sd["cond_embed.2.bias"])
-        eps = unet(sd, torch.cat([y_cond, y_t], dim=1), emb, cfg)
+        eps = _sampler_denoise(sd, y_cond, y_t, noise_level, mask, cls, cfg, unet)
 
         def ex(name):
             return sched[name + "_test"].gather(-1, t).reshape(b, 1, 1, 1)
@@ -443,7 +459,8 @@ def restoration_ddpm(sd, y_cond, y_t, y_0, mask, noises, cfg: UNetCfg, sample_nu
     return y_t, ret_arr
 
 
-def restoration_ddim(sd, y_cond, y_t, y_0, mask, cfg: UNetCfg, sample_num=8, num_steps=10, eta=0.5, unet=None):
+def restoration_ddim(sd, y_cond, y_t, y_0, mask, cfg: UNetCfg, sample_num=8, num_steps=10, eta=0.5, unet=None,
+                     cls=None):
     """DiffusionGenerator.restoration_ddim / ddim_p_sample / ddim_p_mean_variance (diffusion_generator.py:286-456),
     conditioning "" and no guidance.  Deterministic given y_t (the reference's per-step noise draw is unused)."""
     unet = unet or unet_forward
@@ -458,10 +475,7 @@ def restoration_ddim(sd, y_cond, y_t, y_0, mask, cfg: UNetCfg, sample_num=8, num
         t = torch.full((b,), int(tseq[-1 - i]), dtype=torch.long)
         prevt = torch.full((b,), int(tseq[-2 - i]) if i != num_steps - 1 else -1, dtype=torch.long)
         noise_level = sched["gammas_test"].gather(-1, t).reshape(b, 1)
-        emb = gamma_embedding(noise_level, cfg.cond_embed_dim)
-        emb = F.linear(emb, sd["cond_embed.0.weight"], sd["cond_embed.0.bias"])
-        emb = F.linear(F.silu(emb), sd["cond_embed.2.weight"], sd["cond_embed.2.bias"])
-        e = unet(sd, torch.cat([y_cond, y_t], dim=1), emb, cfg).clamp(-1.0, 1.0)
+        e = _sampler_denoise(sd, y_cond, y_t, noise_level, mask, cls, cfg, unet).clamp(-1.0, 1.0)
         g_t = sched["gammas_test"].gather(-1, t).reshape(b, 1, 1, 1)
         g_p = gammas_prev.gather(-1, prevt + 1).reshape(b, 1, 1, 1)
         sigma = eta * torch.sqrt((1 - g_p) / (1 - g_t) * (1 - g_t / g_p))

@@ -122,3 +122,57 @@ def test_trainer_with_class_conditioning_and_dropout(golden_dir):
     assert abs(losses[0] - losses[1]) < 1e-3 * abs(losses[1])
     loss = tr.optimize_parameters(noise=noise.cuda(), t=t.cuda(), u=u.cuda())
     assert torch.isfinite(loss)
+
+
+def test_conditioned_samplers_vs_reference_golden(golden_dir):
+    """Row (f)-1 with conditioning: restoration_ddpm (8 reverse steps) and restoration_ddim (4 steps) of a class + mask
+    conditioned generator against the unmodified reference's samplers with replayed draws.  Outside the mask y_0 is
+    copied exactly; inside, the bf16 UNet error is fed back every step: bounded by the bf16-emulating oracle's own
+    distance to the fp32 golden."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from joligen_b200 import nets
+    from oracle import palette_oracle as O
+    from oracle.gen_golden_cond import BASE, cond_batch, cond_cfg, cond_params
+    g = torch.load(os.path.join(golden_dir, "palette_cond_class_mask.pt"))
+    s = g["sampling"]
+    cfg0 = cond_cfg("class_mask", g["nclasses"])
+    cfg = O.UNetCfg(in_channel=cfg0.in_channel, conditioning="class_mask", nclasses=g["nclasses"],
+                    n_timestep_test=s["n_timestep_test"], **BASE)
+    params = cond_params(cfg, g["wseed"])
+    for k, v in g["tables_after"].items():
+        params[k] = v.clone()
+    data = cond_batch(cfg, g["batch"], g["dseed"])
+    torch.manual_seed(s["rseed"])
+    y_t0 = torch.randn_like(data["gt"])
+    noises = {i: torch.randn_like(data["gt"]) for i in reversed(range(1, cfg.n_timestep_test))}
+    net = nets.build_palette_generator(conditioning="class_mask", nclasses=g["nclasses"],
+                                       n_timestep_test=s["n_timestep_test"], **BASE)
+    net.load_state_dict(params, strict=False)
+    net = net.cuda()
+    y, ret = net.restoration_ddpm(data["cond"].cuda(), y_t=y_t0.cuda(), y_0=data["gt"].cuda(), mask=data["mask"].cuda(),
+                                  sample_num=s["sample_num"], cls=data["cls"].cuda(),
+                                  noise_fn=lambda i, shape: noises[i].cuda())
+    assert ret.shape == s["ret_arr"].shape
+    m = data["mask"].clamp(0, 1).bool().expand_as(data["gt"])
+    assert torch.equal(y.cpu()[~m], data["gt"][~m])
+    O.EMULATE_BF16[0] = True
+    try:
+        with torch.no_grad():
+            yo, _ = O.restoration_ddpm(params, data["cond"], y_t0, data["gt"], data["mask"], noises, cfg,
+                                       s["sample_num"], cls=data["cls"])
+            ydo, _ = O.restoration_ddim(params, data["cond"], y_t0.clone(), data["gt"], data["mask"], cfg,
+                                        s["sample_num"], num_steps=s["ddim_steps"], eta=s["ddim_eta"], cls=data["cls"])
+    finally:
+        O.EMULATE_BF16[0] = False
+    assert rel_l2(y, s["y"]) < max(3e-2, 2.5 * rel_l2(yo, s["y"])), (rel_l2(y, s["y"]), rel_l2(yo, s["y"]))
+    net.sampling_method = "ddim"
+    yd, retd = net.restoration(data["cond"].cuda(), y_t=y_t0.cuda(), y_0=data["gt"].cuda(), mask=data["mask"].cuda(),
+                               sample_num=s["sample_num"], cls=data["cls"].cuda(), ddim_num_steps=s["ddim_steps"],
+                               ddim_eta=s["ddim_eta"])
+    assert retd.shape == s["ret_arr_ddim"].shape
+    assert torch.equal(yd.cpu()[~m], data["gt"][~m])
+    assert rel_l2(yd, s["y_ddim"]) < max(3e-2, 2.5 * rel_l2(ydo, s["y_ddim"]))
+    # an unconditioned call of a conditioned net is an error, like the reference's (cls / mask embeddings missing)
+    with pytest.raises(RuntimeError):
+        net.restoration(data["cond"].cuda(), y_t=y_t0.cuda(), y_0=data["gt"].cuda(), mask=data["mask"].cuda())

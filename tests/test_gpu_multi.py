@@ -142,3 +142,72 @@ def test_two_gpu_gradient_and_replicas():
     for k in ("params", "exp_avg", "ema", "graph_params"):
         assert torch.equal(a[k], b[k]), "replicas differ in %s" % k
     assert a["graph_used"] and b["graph_used"] and a["finite"] and b["finite"]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The drop-in path of INTEGRATION.md section 2: the B200 modules inside torch's DistributedDataParallel (what
+# BaseModel.parallelize builds, base_model.py:725-737) with gradient accumulation (train_iter_size = 2: the first
+# micro-step under no_sync, base_model.py:1313-1315).  Two ranks share ONE GPU over gloo, so it runs on the one-GPU box.
+# What it pins: every parameter's gradient reaches autograd's AccumulateGrad — so DDP's reducer hooks fire for
+# the convolution weights too, on the first AND the second micro-step (when .grad already exists).
+# ---------------------------------------------------------------------------------------------------------------------
+def _ddp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from joligen_b200 import nets
+    from oracle import palette_oracle as O
+    cfg = O.UNetCfg(**CFG)
+
+    def make():
+        net = nets.build_palette_generator(**CFG)
+        net.load_state_dict(O.init_params(cfg, 50), strict=False)
+        return net.cuda()
+
+    def loss_of(model, draw):
+        data, noise, t, u = draw
+        _, noise_hat, _ = model(data["gt"].cuda(), data["cond"].cuda(), data["mask"].cuda(), noise.cuda(),
+                                t=t.cuda(), u=u.cuda())
+        return torch.nn.functional.mse_loss(noise_hat, noise.cuda())
+
+    draws = {(r, m): _draws(O, cfg, 5000 + 10 * r + m) for r in range(world) for m in range(2)}
+    ddp = DDP(make(), device_ids=[0])
+    with ddp.no_sync():
+        (loss_of(ddp, draws[(rank, 0)]) / 2).backward()
+    (loss_of(ddp, draws[(rank, 1)]) / 2).backward()   # .grad exists now: must still go through AccumulateGrad
+    torch.cuda.synchronize()
+    got = {k: p.grad.detach().float().cpu() for k, p in ddp.module.named_parameters() if p.grad is not None}
+    res = {"n_grads": len(got), "n_params": sum(1 for _ in ddp.module.parameters())}
+    if rank == 0:
+        solo = make()
+        for r in range(world):
+            for m in range(2):
+                (loss_of(solo, draws[(r, m)]) / (2 * world)).backward()
+        torch.cuda.synchronize()
+        worst, worst_k = 0.0, None
+        for k, p in solo.named_parameters():
+            ref = p.grad.detach().float().cpu()
+            e = float((got[k].double() - ref.double()).norm() / (ref.double().norm() + 1e-12))
+            if e > worst and float(ref.norm()) > 1e-6:
+                worst, worst_k = e, k
+        res["worst"], res["worst_k"] = worst, worst_k
+    out[rank] = res
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ddp_wrapped_modules_with_gradient_accumulation():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_ddp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    a, b = out[0], out[1]
+    assert a["n_grads"] == a["n_params"] == b["n_grads"]
+    # DDP's mean over ranks of the accumulated micro-step gradients == the plain sum / (2 * world) on one model; a
+    # parameter whose gradient skipped the reducer would hold its rank-local value (different data: error ~ 1)
+    assert a["worst"] < 5e-2, (a["worst_k"], a["worst"])
