@@ -420,6 +420,44 @@ int jg_monce_fwd(const float* q, const float* k, int G, int P, int D, float T, i
 int jg_monce_bwd(const float* q, const float* k, const float* lse, const float* grad_loss, int G, int P, int D, float T,
                  int num_patches_opt, int iters, float* ws, float* dq, float* dk, jg_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * b2b video backbone, JiTViD (models/modules/vit/vit_vid.py).  Tokens are rows of bf16
+ * [rows][ld] tensors, rows = N * T (N = B * F frames, T tokens per frame); modulation vectors are fp32 slices
+ * [N][.] (row stride ldm) of the adaLN Linear's output.  The Linears are jg_conv2d_* (1x1) on the same tensors.
+ *   jg_rmsnorm_mod_*     RMSNorm (util/model_util.py:165-179, eps 1e-6, weight w) + modulate x*(1+scale)+shift
+ *                        (vit_vid.py:47-48, JiTBlock :249-280, FinalLayer :283-308); shift = scale = NULL: plain RMSNorm.
+ *                        rstd [rows] saved.  bwd: dx; dw [C] (overwritten); dshift / dscale [N][.] (row stride lddm).
+ *   jg_qknorm_rope_*     Attention.forward :205-231: per-head RMSNorm of q and k (weights wq, wk [hd]) + rotary embedding
+ *                        (cos / sin fp32 [T][hd], rotate_half on interleaved pairs, util/model_util.py:97-162) of the q and
+ *                        k parts of qkv [rows][(q | k | v) each heads*hd]; out [rows][2*heads*hd]; rstd [rows][heads][2].
+ *   jg_attn_small_*      softmax(q k^T / sqrt(hd)) v over the T <= 128 tokens of each frame, fp32; lse [N*heads][T].
+ *   jg_swiglu_*          SwiGLUFFN :234-246: x = (x1 | x2) [rows][2H] -> silu(x1) * x2.
+ *   jg_gated_residual_*  out = x + gate * y (:270-279); bwd: dy = gate * d, dgate [N][.] = sum_t d * y.
+ * hd in {16, 32, 64}. */
+int jg_rmsnorm_mod_fwd(const void* x, int ldx, void* y, int ldy, int64_t rows, int C, int T, float eps, const float* w,
+                       const float* shift, const float* scale, int ldm, float* rstd, jg_stream_t stream);
+int jg_rmsnorm_mod_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int64_t rows, int C, int T,
+                       const float* w, const float* scale, int ldm, const float* rstd, float* dw, float* dshift,
+                       float* dscale, int lddm, jg_stream_t stream);
+int jg_qknorm_rope_fwd(const void* qkv, int ldq, void* out, int ldo, int64_t rows, int T, int heads, int hd, float eps,
+                       const float* wq, const float* wk, const float* cosb, const float* sinb, float* rstd,
+                       jg_stream_t stream);
+int jg_qknorm_rope_bwd(const void* qkv, int ldq, const void* dout, int lddo, void* dqkv, int lddq, int64_t rows, int T,
+                       int heads, int hd, const float* wq, const float* wk, const float* cosb, const float* sinb,
+                       const float* rstd, float* dwq, float* dwk, jg_stream_t stream);
+int jg_attn_small_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, float* lse,
+                      int N, int T, int heads, int hd, jg_stream_t stream);
+int jg_attn_small_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* o, int ldo,
+                      const void* d_o, int lddo, const float* lse, void* dq, int lddq, void* dk, int lddk, void* dv,
+                      int lddv, int N, int T, int heads, int hd, jg_stream_t stream);
+int jg_swiglu_fwd(const void* x, int ldx, void* y, int ldy, int64_t rows, int H, jg_stream_t stream);
+int jg_swiglu_bwd(const void* x, int ldx, const void* dy, int lddy, void* dx, int lddx, int64_t rows, int H,
+                  jg_stream_t stream);
+int jg_gated_residual_fwd(const void* x, int ldx, const void* y, int ldy, const float* gate, int ldm, void* out, int ldo,
+                          int64_t rows, int C, int T, jg_stream_t stream);
+int jg_gated_residual_bwd(const void* d, int ldd, const void* y, int ldy, const float* gate, int ldm, void* dy, int lddy,
+                          float* dgate, int lddm, int64_t rows, int C, int T, jg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

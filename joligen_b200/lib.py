@@ -100,6 +100,19 @@ _SIGNATURES = {
     "jg_temporal_attn_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
     "jg_ddpm_step": [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int,
                      c_p],
+    "jg_rmsnorm_mod_fwd": [c_p, c_int, c_p, c_int, c_i64, c_int, c_int, c_f, c_p, c_p, c_p, c_int, c_p, c_p],
+    "jg_rmsnorm_mod_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_int, c_p, c_p, c_int, c_p, c_p, c_p, c_p,
+                           c_int, c_p],
+    "jg_qknorm_rope_fwd": [c_p, c_int, c_p, c_int, c_i64, c_int, c_int, c_int, c_f, c_p, c_p, c_p, c_p, c_p, c_p],
+    "jg_qknorm_rope_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p,
+                           c_p, c_p],
+    "jg_attn_small_fwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_p],
+    "jg_attn_small_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_p, c_int, c_p, c_int, c_p,
+                          c_int, c_int, c_int, c_int, c_int, c_p],
+    "jg_swiglu_fwd": [c_p, c_int, c_p, c_int, c_i64, c_int, c_p],
+    "jg_swiglu_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_p],
+    "jg_gated_residual_fwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_int, c_p],
+    "jg_gated_residual_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_int, c_p],
     "jg_geglu_fwd": [c_p, c_int, c_p, c_int, c_i64, c_int, c_p],
     "jg_geglu_bwd": [c_p, c_int, c_p, c_int, c_p, c_int, c_i64, c_int, c_p],
     "jg_linear_fwd": [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],

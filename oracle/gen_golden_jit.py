@@ -46,7 +46,15 @@ def inputs(cfg, batch, frames, seed):
     return gt, cond, mask, label
 
 
-def main():
+# a second configuration whose head sizes the B200 kernels take (JiT head dim 32, temporal head dim 16): the CUDA side is
+# tested against it (tests/test_gpu_jit.py)
+# (hidden 192: SwiGLU width int(4 * 192 * 2 / 3) = 512, JiT head dim 32, temporal head dim 24 — all multiples of 8)
+CFG_B200 = dict(input_size=32, patch_size=8, in_channels=6, out_channels=3, hidden_size=192, depth=4, num_heads=6,
+                num_classes=1, in_context_len=4, in_context_start=2, max_frames=8, motion_num_heads=8,
+                motion_num_layers=1)
+
+
+def main(name="jit_small.pt", CFG=CFG):
     ref_stubs.install()
     from models.modules.b2b_generator import B2BGenerator
     cfg = J.JitCfg(**CFG)
@@ -92,7 +100,7 @@ def main():
     torch.save({"cfg": CFG, "restored": restored.clone(), "denoise_timesteps": 3, "batch": batch, "frames": frames, "wseed": 12, "dseed": 14, "rseed": rseed,
                 "t_base": t_base, "torch_version": str(torch.__version__), "shapes": shapes, "frozen": frozen,
                 "x_pred": x_pred.detach().clone(), "loss": float(loss.detach()), "grads": grads},
-               os.path.join(GOLDEN, "jit_small.pt"))
+               os.path.join(GOLDEN, name))
     # the restatement against the reference, right here
     leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     sd = J.add_buffers({**leaves, **frozen}, cfg)
@@ -106,7 +114,7 @@ def main():
     named = dict(net.named_parameters())
     gerr = max(float((zero(leaves[k].grad, leaves[k]) - zero(named[k].grad, named[k])).norm() /
                      (zero(named[k].grad, named[k]).norm() + 1e-9)) for k in leaves)
-    print("jit_small.pt: %d parameter tensors, loss %.6f (oracle %.6f), x_pred rel max err %.2e, v err %.2e, "
+    print(name + ": %d parameter tensors, loss %.6f (oracle %.6f), x_pred rel max err %.2e, v err %.2e, "
           "worst grad rel L2 err %.2e, params without grad %d" % (
               len(shapes), float(loss), float(lo), float((xp2 - x_pred).abs().max() / x_pred.abs().max()),
               float((v2 - v).abs().max()), gerr, sum(g["none"] for g in grads.values())))
@@ -114,3 +122,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    main("jit_b200.pt", CFG_B200)

@@ -9,9 +9,13 @@ from oracle import jit_oracle as J
 from oracle.vid_oracle import init_params_from_shapes
 
 
-def test_jit_b2b_oracle_matches_reference(golden_dir):
+import pytest
+
+
+@pytest.mark.parametrize("name", ["jit_small.pt", "jit_b200.pt"])
+def test_jit_b2b_oracle_matches_reference(golden_dir, name):
     from oracle.gen_golden_jit import inputs
-    gold = torch.load(os.path.join(golden_dir, "jit_small.pt"))
+    gold = torch.load(os.path.join(golden_dir, name))
     cfg = J.JitCfg(**gold["cfg"])
     params = init_params_from_shapes(gold["shapes"], gold["wseed"])
     gt, cond, mask, label = inputs(cfg, gold["batch"], gold["frames"], gold["dseed"])
