@@ -47,6 +47,7 @@ CONFIG_INFO = {
     3: dict(metric="train-step images/sec CUT resnet_9blocks G + NLayerD 256^2 bf16", batch=4, size=(256, 256)),
     4: dict(metric="train-step images/sec Palette UNet-ref (ref attention) bf16", batch=16, size=(128, 128)),
     5: dict(metric="train-step frames/sec UNetVid 8-frame 128^2 bf16", batch=1, size=(128, 128)),
+    6: dict(metric="train-step frames/sec b2b JiTVid-B/16 8-frame 128^2 bf16", batch=1, size=(128, 128)),
 }
 
 
@@ -56,7 +57,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5, 6])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the configuration's)")
     ap.add_argument("--size", default="", help="H or HxW (default: the configuration's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -323,6 +324,23 @@ def build_workload(args, rank, world):
         gmac = 862.63 * (h / 128.0) ** 2
         name = "palette_model video UNet (unet_vid, MotionModule) %d-frame %dx%d bf16, %d clip(s)/GPU" % (frames, h, w, B)
         return tr, host, B * frames, name, 3 * 2 * gmac * 1e9 * B
+    if args.config == 6:
+        # BASELINE.json config 5 as written: b2b_model + vit_vid (example_b2b_vid_mario.json): JiTVid-B/16, 8 frames
+        from joligen_b200 import nets_jit
+        from joligen_b200.trainer_b2b import B2BTrainer
+        frames = 8
+        net = nets_jit.B2BGenerator(nets_jit.JiTViD(input_size=h, patch_size=16, in_channels=3, hidden_size=768, depth=12,
+                                                    num_heads=12, in_context_len=32, in_context_start=4, max_frames=8,
+                                                    motion_num_heads=8, motion_num_layers=2))
+        synthetic.dezero_init_(net, 5)
+        tr = B2BTrainer(net, lr=1e-4, beta1=0.9, beta2=0.95, ema=True, ema_beta=0.999)
+        g = torch.Generator().manual_seed(1234 + rank)
+        gt = (0.5 * torch.randn(B, frames, 3, h, w, generator=g)).clamp(-1, 1)
+        mask = (torch.rand(B, frames, 1, h, w, generator=g) > 0.6).float()
+        host = {"A": gt * (1 - mask) + torch.randn(gt.shape, generator=g) * mask, "B": gt, "B_label_mask": mask}
+        name = "b2b_model JiTVid-B/16 (vit_vid, 156 M parameters) %d-frame %dx%d bf16, %d clip(s)/GPU, eager" % (
+            frames, h, w, B)
+        return tr, host, B * frames, name, None
     # config 3: CUT
     from joligen_b200 import nets_cut, nets_gan
     from joligen_b200.trainer_cut import CutTrainer
@@ -482,8 +500,9 @@ def main():
         achieved = step_flops / (ms / 1000.0) / 1e12
         conv_tf = conv_flops_issued / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
         info = CONFIG_INFO[args.config]
+        unit = "frames/s" if args.config in (5, 6) else "images/s"   # (video configurations count frames)
         line = {
-            "metric": info["metric"], "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "metric": info["metric"], "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "baseline_config": args.config,
@@ -492,7 +511,7 @@ def main():
                        "optimizer": "fused Adam(W)+EMA", "loss_last": last_loss,
                        "launch": "CUDA graph replay (fwd+bwd graph incl. the bucketed gradient all-reduce, optimizer "
                                  "graph)" if getattr(tr, "_graph_fb", None) is not None else "eager"},
-            "e2e": {"value": imgs / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": h2d,
+            "e2e": {"value": imgs / (ms_e2e / 1000.0), "unit": unit, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "clocks": clocks,

@@ -460,7 +460,7 @@ static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const C
   return JG_OK;
 }
 
-static int check_desc(const jg_conv_desc* d) {
+static int check_desc(const jg_conv_desc* d, bool forward = true) {
   JG_CHECK(d != nullptr, JG_ERR_INVALID, "conv: null descriptor");
   JG_CHECK(d->N > 0 && d->H > 0 && d->W > 0 && d->Ho > 0 && d->Wo > 0, JG_ERR_INVALID, "conv: bad dims");
   JG_CHECK(d->Cin > 0 && d->Cin % 8 == 0 && d->ldx % 8 == 0 && d->ldx >= d->Cin, JG_ERR_INVALID,
@@ -468,7 +468,8 @@ static int check_desc(const jg_conv_desc* d) {
   JG_CHECK(d->Cout > 0 && d->Cout % 8 == 0 && d->ldy % 8 == 0 && d->ldy >= d->Cout, JG_ERR_INVALID,
            "conv: Cout=%d ldy=%d must be multiples of 8 with ldy >= Cout", d->Cout, d->ldy);
   JG_CHECK(d->R > 0 && d->S > 0 && d->R * d->S <= 64, JG_ERR_INVALID, "conv: bad filter %dx%d", d->R, d->S);
-  JG_CHECK(d->Cout <= kMaxCout, JG_ERR_INVALID, "conv: Cout %d > %d (bias staging buffer)", d->Cout, kMaxCout);
+  // (the forward kernels stage the bias vector in shared memory; the weight gradient has no such buffer)
+  JG_CHECK(!forward || d->Cout <= kMaxCout, JG_ERR_INVALID, "conv: Cout %d > %d (bias staging buffer)", d->Cout, kMaxCout);
   JG_CHECK(d->stride == 1 || d->stride == 2, JG_ERR_INVALID, "conv: stride %d unsupported", d->stride);
   JG_CHECK(d->up2x == 0, JG_ERR_INVALID, "conv: up2x is reserved");
   const int ho = (d->H + 2 * d->pad - d->R) / d->stride + 1;
@@ -606,7 +607,7 @@ extern "C" int jg_conv2d_fwd_ex(const jg_conv_desc* d, const jg_conv_epilogue* e
 static int conv2d_wgrad_impl(const jg_conv_desc* d, const void* x, const void* dy, int lddy, float* ws, float* dw_oihw,
                              float beta, int* layout, jg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int rc = check_desc(d);
+  int rc = check_desc(d, /*forward=*/false);
   if (rc) return rc;
   JG_CHECK(x && dy && ws, JG_ERR_INVALID, "conv_wgrad: null pointer");
   JG_CHECK(lddy % 8 == 0 && lddy >= d->Cout, JG_ERR_INVALID, "conv_wgrad: bad lddy %d", lddy);

@@ -74,6 +74,9 @@ def _rows(t):
     return t.contiguous()
 
 
+_MAX_FWD_COUT = 4096  # kMaxCout of csrc/conv_common.cuh (bias staging buffer of the forward kernels)
+
+
 class Conv2dFn(torch.autograd.Function):
     """y = conv(x, W) + b (+ res_scale*residual).  x NHWC bf16 with channels padded to a multiple of 8;
     W fp32 OIHW (its bf16 packed copies wf / wd and the 8-padded bias are passed in).  The output has
@@ -90,8 +93,18 @@ class Conv2dFn(torch.autograd.Function):
             stats = torch.zeros((x.shape[0], cout8, 2), dtype=torch.float32, device=x.device)
             aux["stats"] = stats
         # out: optional destination (a channel slice of a wider NHWC buffer, e.g. the next block's concat input)
-        y = K.conv2d_fwd(x, wf, bias_p, cout8, r, s, stride=stride, pad=pad, residual=residual, res_scale=res_scale,
-                         out=out, stats=stats)
+        if cout8 > _MAX_FWD_COUT and residual is None and stats is None:
+            # wider than the kernels' bias staging (the b2b backbone's GEGLU projection: 768 -> 6144): output-channel
+            # chunks of the same packed weights (rows of wf), each written into its slice of y
+            y = out if out is not None else torch.empty(tuple(x.shape[:-1]) + (cout8,), dtype=torch.bfloat16,
+                                                        device=x.device)
+            for c0 in range(0, cout8, _MAX_FWD_COUT):
+                c1 = min(cout8, c0 + _MAX_FWD_COUT)
+                K.conv2d_fwd(x, wf[c0:c1], None if bias_p is None else bias_p[c0:c1], c1 - c0, r, s, stride=stride,
+                             pad=pad, out=y[..., c0:c1])
+        else:
+            y = K.conv2d_fwd(x, wf, bias_p, cout8, r, s, stride=stride, pad=pad, residual=residual,
+                             res_scale=res_scale, out=out, stats=stats)
         if out is not None:
             y = y.view(y.shape)  # a fresh tensor object: autograd must not see an input returned as an output
         gn = aux.get("gn") if aux is not None else None

@@ -1,0 +1,66 @@
+"""B2BModel.optimize_parameters for the b2b video backbone (/root/reference/models/b2b_model.py: set_input,
+compute_b2b_loss :1081-1168 without the perceptual terms, compute_step / ema_step of base_model.py:1250-1297):
+flow-matching forward of nets_jit.B2BGenerator + masked pseudo-Huber loss + backward + ONE fused AdamW(+EMA) launch over
+flat fp32 buffers.  Mirrors the reference's quirk that `set_requires_grad` makes the "fixed" sin-cos `pos_embed`
+trainable (pinned by tests/golden/b2b_plumbing.pt)."""
+import torch
+
+from . import kernels as K
+from . import nets
+from .trainer import FlatParams
+
+
+class B2BTrainer:
+    def __init__(self, net, lr=1e-4, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.0, optim="adamw", ema=True,
+                 ema_beta=0.999, lambda_G=1.0, use_cond=False, device="cuda", train_pos_embed=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("B2BTrainer needs a CUDA device (the B200 kernels have no CPU fallback)")
+        if optim not in ("adamw", "adam"):
+            raise NotImplementedError("optimizer %r (adam / adamw are implemented)" % optim)
+        self.device = torch.device(device)
+        self.net = net.to(self.device)
+        if train_pos_embed:
+            self.net.b2b_model.pos_embed.requires_grad_(True)
+        self.flat = FlatParams(self.net)
+        self.exp_avg = torch.zeros_like(self.flat.data)
+        self.exp_avg_sq = torch.zeros_like(self.flat.data)
+        self.ema = torch.zeros_like(self.flat.data) if ema else None
+        self.ema_started = False
+        self.ema_beta = ema_beta
+        self.hp = dict(lr=lr, beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay, adamw=(optim == "adamw"))
+        self.step = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.lambda_G = lambda_G
+        self.use_cond = use_cond
+        self.loss_G_tot = None
+
+    def set_input(self, data):
+        """data["B"] clip [B, F, 3, H, W], data["B_label_mask"] [B, F, 1, H, W], data["A"] the conditioning clip."""
+        dev = self.device
+        self.gt = data["B"].to(dev, non_blocking=True).float()
+        self.mask = data["B_label_mask"].to(dev, non_blocking=True).float()
+        self.cond = data["A"].to(dev, non_blocking=True).float() if self.use_cond else None
+        self.label = torch.zeros(self.gt.shape[0], dtype=torch.long, device=dev)
+
+    def optimize_parameters(self, t_base=None, e=None):
+        self.flat.rebind_grads()
+        loss = self.net.forward_loss(self.gt, self.mask, self.cond, self.label, t_base=t_base, e=e, lambda_G=self.lambda_G)
+        loss.backward()
+        self.step += 1
+        K.adamw_ema_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.ema, step=self.step,
+                         step_dev=self.step_dev, grad_scale=1.0, ema_beta=self.ema_beta, ema_init=not self.ema_started,
+                         **self.hp)
+        self.ema_started = True
+        self.flat.grad.zero_()
+        nets.invalidate_packed_weights()   # the fused optimizer wrote the masters through raw pointers
+        self.loss_G_tot = loss.detach()
+        return self.loss_G_tot
+
+    def eager_step(self):
+        return self.optimize_parameters()
+
+    def params(self):
+        return self.flat.unflatten(self.flat.data)
+
+    def ema_state_dict(self):
+        return self.flat.unflatten(self.ema) if self.ema is not None else None

@@ -164,3 +164,35 @@ def test_b2b_generator_vs_reference_golden(env, golden_dir):
                 float((got.flatten()[:16].cpu() - g["head"]).abs().max()) > tol:
             bad[k] = (float(got.double().norm()), g["l2"])
     assert not bad, bad
+
+
+def test_b2b_trainer_two_steps_vs_reference_plumbing(env, golden_dir):
+    """BASELINE.json config 5 as written (b2b_model + vit_vid, JiTVid-B/16, 156 M parameters): two optimize_parameters()
+    of the unmodified reference (AdamW(0.9, 0.95) + EMA) with its random draws replayed — losses, parameter and EMA norms
+    after the two steps (tests/golden/b2b_plumbing.pt, oracle/gen_golden_b2b_plumbing.py)."""
+    OJ, J = env
+    from joligen_b200 import nets_jit
+    from joligen_b200.trainer_b2b import B2BTrainer
+    from oracle.gen_golden_b2b_plumbing import batch, draws
+    from oracle.vid_oracle import init_params_from_shapes
+    gold = torch.load(os.path.join(golden_dir, "b2b_plumbing.pt"))
+    gen = gold["gen"]
+    c = gold["cfg"]
+    net = nets_jit.B2BGenerator(nets_jit.JiTViD(**c), t_eps=gen["t_eps"], noise_scale=gen["noise_scale"])
+    params = init_params_from_shapes(gold["shapes"], gold["wseed"])
+    missing, unexpected = net.load_state_dict({**params, **gold["frozen"]}, strict=False)
+    assert not unexpected and all(m.endswith("pos_encoder.pe") for m in missing), (missing, unexpected)
+    o = gold["optim"]
+    tr = B2BTrainer(net, lr=o["lr"], beta1=o["beta1"], beta2=o["beta2"], eps=o["eps"], weight_decay=o["weight_decay"],
+                    optim=o["kind"], ema=True, ema_beta=o["ema_beta"], lambda_G=gold["lambda_G"])
+    for step in range(2):
+        tr.set_input(batch(gold["data_seeds"][step]))
+        t_base, e = draws(gold["rng_seeds"][step], gen["P_mean"], gen["P_std"], gen["mix"])
+        loss = tr.optimize_parameters(t_base=t_base.cuda(), e=e.cuda())
+        assert abs(float(loss) - gold["losses"][step]) < 3e-2 * gold["losses"][step], (step, float(loss))
+    torch.cuda.synchronize()
+    got, ema = tr.params(), tr.ema_state_dict()
+    for k, (s, nrm) in gold["param_stats"].items():
+        assert abs(float(got[k].double().norm()) - nrm) <= 2e-3 * nrm + 1e-6, k
+    for k, (s, nrm) in gold["ema_stats"].items():
+        assert abs(float(ema[k].double().norm()) - nrm) <= 2e-3 * nrm + 1e-6, k
