@@ -316,3 +316,47 @@ class B2BGenerator(nn.Module):
     def forward_loss(self, x, mask, x_cond, label, t_base=None, e=None, lambda_G=1.0):
         v_pred, v, _ = self.forward(x, mask, x_cond, label, t_base, e)
         return lambda_G * self.masked_region_loss(v_pred, v, torch.clamp(mask, min=0, max=1))
+
+    @torch.no_grad()
+    def restoration(self, y, y_cond, denoise_timesteps, mask=None, labels=None, init_noise=None, clip_denoised=False,
+                    disable_inference_clipping=True):
+        """b2b_generator.B2BGenerator.restoration (:406-500) with guidance neutral (cfg_scale 1): Heun steps on the
+        linspace(0, 1, steps + 1) grid, a final Euler step, known pixels re-projected after every step, final clamp."""
+        b, f = y.shape[:2]
+        steps = int(denoise_timesteps)
+        if mask is not None:
+            mask = torch.clamp(mask, 0.0, 1.0)
+        if labels is None:
+            labels = torch.zeros(b, dtype=torch.long, device=y.device)
+        if init_noise is None:
+            init_noise = torch.randn_like(y)
+
+        def project(v):
+            return v if mask is None else v * mask + y * (1.0 - mask)
+
+        x = project((y * (1.0 - mask) if mask is not None else y) + init_noise * self.noise_scale)
+        ts = torch.linspace(0.0, 1.0, steps + 1, device=y.device)
+
+        def velocity(xc, t):
+            x_in = project(xc)
+            inp = x_in if y_cond is None else torch.cat([y_cond, x_in], dim=2)
+            xp = self.b2b_model(inp, torch.full((b * f,), float(t), device=y.device), labels)
+            xp = project(xp[:, :, -x_in.shape[2]:])
+            den = 1.0 - t
+            if not disable_inference_clipping:
+                den = den.clamp_min(self.t_eps)
+            return (xp - x_in) / den
+
+        for i in range(steps - 1):
+            t, tn = ts[i], ts[i + 1]
+            v_t = velocity(x, t)
+            v_n = velocity(x + (tn - t) * v_t, tn)
+            x = x + (tn - t) * 0.5 * (v_t + v_n)
+            if clip_denoised:
+                x = x.clamp(-1.0, 1.0)
+            x = project(x)
+        x = x + (ts[-1] - ts[-2]) * velocity(x, ts[-2])
+        if clip_denoised:
+            x = x.clamp(-1.0, 1.0)
+        return project(x).clamp(-1.0, 1.0)
+

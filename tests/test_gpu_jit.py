@@ -196,3 +196,30 @@ def test_b2b_trainer_two_steps_vs_reference_plumbing(env, golden_dir):
         assert abs(float(got[k].double().norm()) - nrm) <= 2e-3 * nrm + 1e-6, k
     for k, (s, nrm) in gold["ema_stats"].items():
         assert abs(float(ema[k].double().norm()) - nrm) <= 2e-3 * nrm + 1e-6, k
+
+
+def test_b2b_restoration_vs_reference_golden(env, golden_dir):
+    """B2BGenerator.restoration (2 Heun steps + the final Euler step on the flow ODE) vs the unmodified reference; known
+    pixels are re-projected exactly."""
+    OJ, J = env
+    from joligen_b200 import nets_jit
+    from oracle.gen_golden_jit import inputs
+    from oracle.vid_oracle import init_params_from_shapes
+    gold = torch.load(os.path.join(golden_dir, "jit_b200.pt"))
+    cfg = J.JitCfg(**gold["cfg"])
+    net = nets_jit.B2BGenerator(nets_jit.JiTViD(
+        input_size=cfg.input_size, patch_size=cfg.patch_size, in_channels=cfg.in_channels, out_channels=cfg.out_channels,
+        hidden_size=cfg.hidden_size, depth=cfg.depth, num_heads=cfg.num_heads, num_classes=cfg.num_classes,
+        in_context_len=cfg.in_context_len, in_context_start=cfg.in_context_start, max_frames=cfg.max_frames,
+        motion_num_heads=cfg.motion_num_heads, motion_num_layers=cfg.motion_num_layers), t_eps=cfg.t_eps,
+        noise_scale=cfg.noise_scale)
+    net.load_state_dict({**init_params_from_shapes(gold["shapes"], gold["wseed"]), **gold["frozen"]}, strict=False)
+    net = net.cuda()
+    gt, cond, mask, label = inputs(cfg, gold["batch"], gold["frames"], gold["dseed"])
+    torch.manual_seed(gold["rseed"] + 1)
+    init_noise = torch.randn_like(gt)
+    out = net.restoration(gt.cuda(), cond.cuda(), gold["denoise_timesteps"], mask=mask.cuda(), labels=label.cuda(),
+                          init_noise=init_noise.cuda())
+    m = mask.bool().expand_as(gt)
+    assert torch.equal(out.cpu()[~m], gt[~m].clamp(-1, 1))
+    assert rel(out, gold["restored"]) < 3e-2
