@@ -333,12 +333,12 @@ def build_workload(args, rank, world):
                                                     num_heads=12, in_context_len=32, in_context_start=4, max_frames=8,
                                                     motion_num_heads=8, motion_num_layers=2))
         synthetic.dezero_init_(net, 5)
-        tr = B2BTrainer(net, lr=1e-4, beta1=0.9, beta2=0.95, ema=True, ema_beta=0.999)
+        tr = B2BTrainer(net, lr=1e-4, beta1=0.9, beta2=0.95, ema=True, ema_beta=0.999, cuda_graph=graph, graph_warmup=2)
         g = torch.Generator().manual_seed(1234 + rank)
         gt = (0.5 * torch.randn(B, frames, 3, h, w, generator=g)).clamp(-1, 1)
         mask = (torch.rand(B, frames, 1, h, w, generator=g) > 0.6).float()
         host = {"A": gt * (1 - mask) + torch.randn(gt.shape, generator=g) * mask, "B": gt, "B_label_mask": mask}
-        name = "b2b_model JiTVid-B/16 (vit_vid, 156 M parameters) %d-frame %dx%d bf16, %d clip(s)/GPU, eager" % (
+        name = "b2b_model JiTVid-B/16 (vit_vid, 156 M parameters) %d-frame %dx%d bf16, %d clip(s)/GPU" % (
             frames, h, w, B)
         return tr, host, B * frames, name, None
     # config 3: CUT
@@ -510,7 +510,9 @@ def main():
                        "l2": "per-step activations (GBs) exceed the 126 MB L2; no explicit flush",
                        "optimizer": "fused Adam(W)+EMA", "loss_last": last_loss,
                        "launch": "CUDA graph replay (fwd+bwd graph incl. the bucketed gradient all-reduce, optimizer "
-                                 "graph)" if getattr(tr, "_graph_fb", None) is not None else "eager"},
+                                 "graph)" if getattr(tr, "_graph_fb", None) is not None else
+                                 ("CUDA graph replay (one graph: forward, backward, optimizer)"
+                                  if getattr(tr, "_graph", None) is not None else "eager")},
             "e2e": {"value": imgs / (ms_e2e / 1000.0), "unit": unit, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches,

@@ -12,7 +12,8 @@ from .trainer import FlatParams
 
 class B2BTrainer:
     def __init__(self, net, lr=1e-4, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.0, optim="adamw", ema=True,
-                 ema_beta=0.999, lambda_G=1.0, use_cond=False, device="cuda", train_pos_embed=True):
+                 ema_beta=0.999, lambda_G=1.0, use_cond=False, device="cuda", train_pos_embed=True, cuda_graph=False,
+                 graph_warmup=2):
         if not torch.cuda.is_available():
             raise RuntimeError("B2BTrainer needs a CUDA device (the B200 kernels have no CPU fallback)")
         if optim not in ("adamw", "adam"):
@@ -33,16 +34,30 @@ class B2BTrainer:
         self.lambda_G = lambda_G
         self.use_cond = use_cond
         self.loss_G_tot = None
+        # CUDA-graph replay of the whole step (implicit random draws only): one clip per GPU is ~700 small launches
+        self.use_graph = bool(cuda_graph)
+        self.graph_warmup = int(graph_warmup)
+        self._graph = None
+        self._eager_steps = 0
+        self._static = None
+        self.launches_per_step = 0
 
     def set_input(self, data):
         """data["B"] clip [B, F, 3, H, W], data["B_label_mask"] [B, F, 1, H, W], data["A"] the conditioning clip."""
         dev = self.device
-        self.gt = data["B"].to(dev, non_blocking=True).float()
-        self.mask = data["B_label_mask"].to(dev, non_blocking=True).float()
-        self.cond = data["A"].to(dev, non_blocking=True).float() if self.use_cond else None
+        gt = data["B"].to(dev, non_blocking=True).float()
+        mask = data["B_label_mask"].to(dev, non_blocking=True).float()
+        cond = data["A"].to(dev, non_blocking=True).float() if self.use_cond else None
+        if self._static is not None:   # the captured graph reads these buffers
+            self._static["B"].copy_(gt)
+            self._static["M"].copy_(mask)
+            if cond is not None:
+                self._static["A"].copy_(cond)
+            return
+        self.gt, self.mask, self.cond = gt, mask, cond
         self.label = torch.zeros(self.gt.shape[0], dtype=torch.long, device=dev)
 
-    def optimize_parameters(self, t_base=None, e=None):
+    def _step(self, t_base=None, e=None):
         self.flat.rebind_grads()
         loss = self.net.forward_loss(self.gt, self.mask, self.cond, self.label, t_base=t_base, e=e, lambda_G=self.lambda_G)
         loss.backward()
@@ -53,11 +68,40 @@ class B2BTrainer:
         self.ema_started = True
         self.flat.grad.zero_()
         nets.invalidate_packed_weights()   # the fused optimizer wrote the masters through raw pointers
-        self.loss_G_tot = loss.detach()
+        return loss.detach()
+
+    def _capture(self):
+        self._static = {"B": self.gt.clone(), "M": self.mask.clone(), "A": None if self.cond is None else self.cond.clone()}
+        self.gt, self.mask, self.cond = self._static["B"], self._static["M"], self._static["A"]
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self._step()
+        self.step -= 1   # the capture did not execute
+
+    def optimize_parameters(self, t_base=None, e=None):
+        from . import lib as L
+        explicit = t_base is not None or e is not None
+        if self.use_graph and not explicit:
+            if self._graph is None and self._eager_steps >= self.graph_warmup:
+                self._capture()
+            if self._graph is not None:
+                self._graph.replay()
+                self.step += 1
+                L.launch_count[0] += self.launches_per_step
+                self.loss_G_tot = self._static_loss
+                return self._static_loss
+        n0 = L.launch_count[0]
+        self.loss_G_tot = self._step(t_base, e)
+        self._eager_steps += 1
+        self.launches_per_step = L.launch_count[0] - n0
         return self.loss_G_tot
 
     def eager_step(self):
-        return self.optimize_parameters()
+        self.loss_G_tot = self._step()
+        return self.loss_G_tot
 
     def params(self):
         return self.flat.unflatten(self.flat.data)

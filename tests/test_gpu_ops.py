@@ -261,6 +261,33 @@ def test_attention_sliced_operands_tc_path(K):
     assert rel(K.nhwc_to_nchw(dqkv).reshape(n, 3 * c, t), qr.grad) < 1.5e-2
 
 
+def test_linear_as_conv_wider_than_the_bias_staging(K):
+    """nn.Linear on tokens [N, T, 1, I] with 4608 outputs (> 4096: the b2b backbone's 768 -> 6144 GEGLU projection takes
+    this path): forward in output-channel chunks, one dgrad, one wgrad — vs fp32 torch on the bf16-rounded operands."""
+    from joligen_b200 import nets, ops
+    g = torch.Generator().manual_seed(2)
+    n, t, i, o = 2, 24, 64, 4608
+    lin = torch.nn.Linear(i, o).cuda()
+    with torch.no_grad():
+        lin.weight.copy_(bf16_round(torch.randn(o, i, generator=g) / 8).cuda())
+        lin.bias.copy_(torch.randn(o, generator=g).cuda())
+    x = bf16_round(torch.randn(n, t, i, generator=g))
+    dy = bf16_round(torch.randn(n, t, o, generator=g))
+    xr = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.linear(xr, lin.weight.detach().cpu(), lin.bias.detach().cpu())
+    ref.backward(dy)
+    wref = torch.einsum("nto,nti->oi", dy, x)
+    pack = nets.ConvPack(lin)
+    xd = x.to(torch.bfloat16).cuda()[:, :, None, :].contiguous().requires_grad_(True)
+    y = ops.conv2d(xd, lin.weight[:, :, None, None], lin.bias, pack.get(), stride=1, pad=0)
+    assert tuple(y.shape) == (n, t, 1, o)
+    y.backward(dy.to(torch.bfloat16).cuda()[:, :, None, :].contiguous())
+    assert rel(y[:, :, 0].float().cpu(), ref.detach()) < 6e-3
+    assert rel(xd.grad[:, :, 0].float().cpu(), xr.grad) < 1e-2
+    assert rel(lin.weight.grad.cpu(), wref) < 6e-3
+    assert rel(lin.bias.grad.cpu(), dy.sum(dim=(0, 1))) < 6e-3
+
+
 def test_layout_resample_concat_bit_exact(K):
     g = torch.Generator().manual_seed(1)
     x = bf16_round(torch.randn(2, 24, 16, 16, generator=g))
