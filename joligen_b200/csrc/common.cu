@@ -52,6 +52,15 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims,
                   gstrides, gbox, ges, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT) {
+    // Driver-API call on a thread whose primary context is not current yet: autograd's worker thread when a TMA kernel
+    // of this library is the FIRST CUDA work of a backward pass (every other entry point starts with a runtime call,
+    // which binds the context).  Bind it through the runtime and encode again.
+    cudaFree(nullptr);
+    r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstrides, gbox, ges,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u] "
               "stride0 %llu base %p",

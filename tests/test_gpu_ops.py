@@ -266,7 +266,7 @@ def test_linear_as_conv_wider_than_the_bias_staging(K):
     this path): forward in output-channel chunks, one dgrad, one wgrad — vs fp32 torch on the bf16-rounded operands."""
     from joligen_b200 import nets, ops
     g = torch.Generator().manual_seed(2)
-    n, t, i, o = 2, 24, 64, 4608
+    n, t, i, o = 6, 36, 128, 4608
     lin = torch.nn.Linear(i, o).cuda()
     with torch.no_grad():
         lin.weight.copy_(bf16_round(torch.randn(o, i, generator=g) / 8).cuda())
