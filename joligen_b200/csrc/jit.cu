@@ -161,11 +161,21 @@ __global__ void qknorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, in
     dn[j] = d0 * cs[j] + d1 * sn[j + 1];
     dn[j + 1] = d1 * cs[j + 1] - d0 * sn[j];
   }
+  // dw: lanes of equal parity share `which` (idx % 2): sum them by shuffles first — per-thread atomics onto the 2 * HD
+  // addresses (rows * heads * 2 threads) serialised in L2 and cost more than the rest of the block's backward
+  const bool tail_warp = ((idx | 31) >= rows * heads * 2);   // (a partially filled last warp keeps per-thread atomics)
 #pragma unroll
   for (int i = 0; i < HD; ++i) {
     xv[i] = b2f(src[i]);
     dot = fmaf(dn[i] * w[i], xv[i], dot);
-    atomicAdd(&dwp[i], dn[i] * xv[i] * r);
+    float g = dn[i] * xv[i] * r;
+    if (!tail_warp) {
+#pragma unroll
+      for (int o = 2; o < 32; o <<= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+      if ((threadIdx.x & 31) < 2) atomicAdd(&dwp[i], g);
+    } else {
+      atomicAdd(&dwp[i], g);
+    }
   }
   const float k = r * r * r * dot / (float)HD;
   __nv_bfloat16* dst = dqkv + row * lddq + which * D + h * HD;

@@ -30,6 +30,16 @@ def _lin(x, lin, pack, weight=None):
     return ops.conv2d(x, w, lin.bias, pack.get(), stride=1, pad=0)
 
 
+def _lin_vec(v, lin, pack, silu=False):
+    """nn.Linear on the O(B) fp32 conditioning vectors [N, I] -> fp32 [N, O] through the same 1x1 tensor-core path (one
+    token per frame).  The thread-per-output fp32 kernels of ops.linear are meant for 32-wide embeddings: at 768 -> 4608
+    their backward took 1.6 ms per adaLN Linear, 25 of the 47 ms of a step (profiles/r02_breakdown_cfg6.json)."""
+    if silu:
+        v = torch.nn.functional.silu(v)
+    y = _lin(v.to(torch.bfloat16)[:, None, None, :].contiguous(), lin, pack)
+    return y.float().reshape(v.shape[0], -1)
+
+
 class _AsLinear:
     """A k x k stride-k patch convolution seen as the Linear it is on patchified tokens: weight [O, C*k*k]."""
 
@@ -103,10 +113,12 @@ class TimestepEmbedder(nn.Module):
         self.mlp = nn.Sequential(nn.Linear(frequency_embedding_size, hidden_size, bias=True), nn.SiLU(),
                                  nn.Linear(hidden_size, hidden_size, bias=True))
         self.frequency_embedding_size = frequency_embedding_size
+        self._pack0 = ConvPack(self.mlp[0])
+        self._pack2 = ConvPack(self.mlp[2])
 
     def forward(self, t):
-        h = ops.linear(timestep_embedding(t, self.frequency_embedding_size), self.mlp[0].weight, self.mlp[0].bias)
-        return ops.linear(h, self.mlp[2].weight, self.mlp[2].bias, act_in=L.ACT_SILU)
+        h = _lin_vec(timestep_embedding(t, self.frequency_embedding_size), self.mlp[0], self._pack0)
+        return _lin_vec(h, self.mlp[2], self._pack2, silu=True)
 
 
 class LabelEmbedder(nn.Module):
@@ -165,10 +177,11 @@ class JiTBlock(nn.Module):
         self.norm2 = RMSNorm(hidden_size)
         self.mlp = SwiGLUFFN(hidden_size, int(hidden_size * mlp_ratio))
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 6 * hidden_size, bias=True))
+        self._pack_ada = ConvPack(self.adaLN_modulation[1])
 
     def forward_tokens(self, x, c, cos, sin):
         d = x.shape[-1]
-        mod = ops.linear(c, self.adaLN_modulation[1].weight, self.adaLN_modulation[1].bias, act_in=L.ACT_SILU)
+        mod = _lin_vec(c, self.adaLN_modulation[1], self._pack_ada, silu=True)
         shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = [mod[:, i * d:(i + 1) * d] for i in range(6)]
         a = self.attn.forward_tokens(J.rmsnorm_mod(x, self.norm1.weight, shift_msa, scale_msa, self.norm1.eps), cos, sin)
         x = J.gated_residual(x, a, gate_msa)
@@ -185,10 +198,11 @@ class FinalLayer(nn.Module):
         self.linear = nn.Linear(hidden_size, patch_size * patch_size * out_channels, bias=True)
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 2 * hidden_size, bias=True))
         self._pack = ConvPack(self.linear)
+        self._pack_ada = ConvPack(self.adaLN_modulation[1])
 
     def forward_tokens(self, x, c):
         d = x.shape[-1]
-        mod = ops.linear(c, self.adaLN_modulation[1].weight, self.adaLN_modulation[1].bias, act_in=L.ACT_SILU)
+        mod = _lin_vec(c, self.adaLN_modulation[1], self._pack_ada, silu=True)
         h = J.rmsnorm_mod(x, self.norm_final.weight, mod[:, :d], mod[:, d:], self.norm_final.eps)
         return _lin(h, self.linear, self._pack)
 
