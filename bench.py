@@ -357,7 +357,7 @@ def build_workload(args, rank, world):
     netF.data_dependent_initialize(netG.get_feats(host["A"][:1].cuda(), nce_layers))
     synthetic.dezero_init_(netF, 13)
     tr = CutTrainer(netG, netF, netD, nce_layers=nce_layers, num_patches=256, nce_loss="monce", gan_mode="lsgan",
-                    G_lr=2e-4, D_lr=1e-4, optim="adam")
+                    G_lr=2e-4, D_lr=1e-4, optim="adam", cuda_graph=False)
     name = "cut_model resnet_9blocks G + NLayerDiscriminator (basic) %dx%d bf16 batch=%d/GPU, MoNCE + identity NCE, " \
            "lsgan (projected-D backbone out of scope)" % (h, w, B)
     return tr, host, B, name, None

@@ -89,7 +89,12 @@ class PatchSampleF(nn.Module):
             if patch_ids is not None:
                 patch_id = patch_ids[feat_id].reshape(-1)
             else:
-                patch_id = torch.randperm(hw, device=feat.device)[: int(min(num_patches, hw))]
+                k = int(min(num_patches, hw))
+                if torch.cuda.is_current_stream_capturing():
+                    # (graph-safe draw of k distinct positions: randperm's CUDA path may synchronise)
+                    patch_id = torch.rand(hw, device=feat.device).argsort()[:k]
+                else:
+                    patch_id = torch.randperm(hw, device=feat.device)[:k]
             x = ops.gather_rows(feat, patch_id.contiguous())
             if self.use_mlp:
                 x = self._mlp(getattr(self, "mlp_%d" % feat_id), x)

@@ -25,7 +25,7 @@ class CutTrainer:
     def __init__(self, netG_A, netF, netD_B, nce_layers=(0, 4, 8, 12, 16), num_patches=256, nce_T=0.07, lambda_NCE=1.0,
                  nce_idt=True, nce_loss="patchnce", nce_includes_all_negatives_from_minibatch=False, gan_mode="lsgan",
                  lambda_gan=1.0, G_lr=2e-4, D_lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, optim="adam",
-                 device=None, process_group=None):
+                 device=None, process_group=None, cuda_graph=False, graph_warmup=2):
         if not torch.cuda.is_available():
             raise RuntimeError("joligen_b200.CutTrainer needs a CUDA device (there is no CPU path)")
         if nce_loss not in ("patchnce", "monce"):
@@ -52,11 +52,26 @@ class CutTrainer:
         self.pg = process_group
         self.niter = 0
         self.loss_G_tot = self.loss_G_GAN = self.loss_G_NCE = self.loss_G_NCE_Y = self.loss_D_tot = None
+        # CUDA-graph replay of the whole step (both optimizer groups): ~3 900 small launches per step are launch-bound
+        # when issued from Python.  EXPERIMENTAL, off by default: on the B200 the capture of the (G, F) backward currently
+        # ends in cudaErrorStreamCaptureImplicit (an autograd gradient accumulation reaches the legacy stream;
+        # profiles/r02_cut_graph_capture_error.log) — the eager path is the tested one.  Single process only.
+        self.use_graph = bool(cuda_graph) and process_group is None
+        self.graph_warmup = int(graph_warmup)
+        self._graph = None
+        self._static = None
+        self._eager_steps = 0
+        self.launches_per_step = 0
 
     def set_input(self, data, non_blocking=True):
         """data: {"A": source-domain images, "B": target-domain images} NCHW fp32 in [-1, 1]"""
-        self.real_A = data["A"].to(self.device, non_blocking=non_blocking)
-        self.real_B = data["B"].to(self.device, non_blocking=non_blocking)
+        a = data["A"].to(self.device, non_blocking=non_blocking)
+        b = data["B"].to(self.device, non_blocking=non_blocking)
+        if self._static is not None:   # the captured graph reads these buffers
+            self._static["A"].copy_(a)
+            self._static["B"].copy_(b)
+            return
+        self.real_A, self.real_B = a, b
 
     @staticmethod
     def set_requires_grad(net, flag):
@@ -78,8 +93,51 @@ class CutTrainer:
             total = total + (self.crit_nce(feat_q=fq, feat_k=fk, current_batch=b) * self.lambda_NCE).mean()
         return total / len(self.nce_layers)
 
+    def _capture(self):
+        self._static = {"A": self.real_A.clone(), "B": self.real_B.clone()}
+        self.real_A, self.real_B = self._static["A"], self._static["B"]
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        # one more real step on the side stream the capture will use: autograd's gradient accumulators then belong to that
+        # stream (on the legacy default stream they would make it wait on the capturing stream, which CUDA refuses)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._step(None, None)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph, stream=side):
+            self._static_losses = self._step(None, None)
+        for o in (self.optG, self.optF, self.optD):
+            o.step -= 1   # the capture did not execute
+        self.niter -= 1
+
     def optimize_parameters(self, patch_ids_A=None, patch_ids_B=None):
         """patch_ids_*: optional explicit positions (one LongTensor per NCE layer) instead of torch.randperm draws."""
+        from . import lib as L
+        if self.use_graph and patch_ids_A is None and patch_ids_B is None:
+            if self._graph is None and self._eager_steps >= self.graph_warmup:
+                self._capture()
+            if self._graph is not None:
+                self._graph.replay()
+                self.niter += 1
+                for o in (self.optG, self.optF, self.optD):
+                    o.step += 1
+                L.launch_count[0] += self.launches_per_step
+                self.loss_G_tot, self.loss_D_tot = self._static_losses
+                return self._static_losses
+        n0 = L.launch_count[0]
+        out = self._step(patch_ids_A, patch_ids_B)
+        self._eager_steps += 1
+        self.launches_per_step = L.launch_count[0] - n0
+        return out
+
+    def eager_step(self):
+        return self._step(None, None)
+
+    def _step(self, patch_ids_A=None, patch_ids_B=None):
         self.niter += 1
         a = ops.to_nhwc(self.real_A)
         b = ops.to_nhwc(self.real_B)

@@ -31,12 +31,14 @@ class _FlatAdam:
         self.ema_beta = ema_beta if ema_beta is not None else 0.0
         self.hp = dict(lr=lr, beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay, adamw=adamw)
         self.step = 0
+        # the step count lives on the device too, so that a CUDA graph holding this update stays valid when replayed
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.flat.data.device)
 
     def apply(self, pg):
         scale = dp.allreduce_sum_(self.flat.grad, pg)
         self.step += 1
-        K.adamw_ema_step(self.flat.data, self.flat.grad, self.m, self.v, self.ema, step=self.step, grad_scale=scale,
-                         ema_beta=self.ema_beta, ema_init=(self.step == 1), **self.hp)
+        K.adamw_ema_step(self.flat.data, self.flat.grad, self.m, self.v, self.ema, step=self.step, step_dev=self.step_dev,
+                         grad_scale=scale, ema_beta=self.ema_beta, ema_init=(self.step == 1), **self.hp)
         self.flat.grad.zero_()
         nets.invalidate_packed_weights()
 
