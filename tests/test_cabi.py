@@ -57,6 +57,23 @@ def test_no_cpu_fallback():
         g(torch.zeros(1, 3, 32, 32), torch.zeros(1, 3, 32, 32), None, torch.zeros(1, 3, 32, 32))
 
 
+def test_no_cpu_fallback_in_the_widening_rows():
+    """The b2b backbone and its trainer, the CUT trainer and the new autograd ops: hard errors without a CUDA device."""
+    import pytest
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from joligen_b200 import nets_jit, ops_jit
+    from joligen_b200.trainer_b2b import B2BTrainer
+    net = nets_jit.B2BGenerator(nets_jit.JiTViD(input_size=32, patch_size=8, hidden_size=192, depth=1, num_heads=6,
+                                                in_context_len=0, in_context_start=0, motion_num_layers=1))
+    with pytest.raises(RuntimeError):
+        B2BTrainer(net)
+    with pytest.raises(Exception):
+        net(torch.zeros(1, 2, 3, 32, 32), torch.ones(1, 2, 1, 32, 32), None, torch.zeros(1, dtype=torch.long))
+    with pytest.raises(Exception):
+        ops_jit.swiglu(torch.zeros(1, 4, 1, 16, dtype=torch.bfloat16))
+
+
 def test_b200_modules_have_reference_state_dict_keys():
     from joligen_b200 import nets
     from oracle import palette_oracle as O
