@@ -18,6 +18,7 @@ import math
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import kernels as K
 from . import lib as L

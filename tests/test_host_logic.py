@@ -93,3 +93,22 @@ def test_denoise_fn_argument_count_drives_the_reference_image_path():
     with pytest.raises(RuntimeError):
         dn.pack_ref(None)                     # the three-argument UNet needs the reference image
     assert nets.PaletteDenoiseFn(nets.UNet(**kw), 32).pack_ref(None) is None
+
+
+def test_no_undefined_names_in_the_package():
+    """A forgotten import in a rarely taken branch is exactly what no GPU test reaches (nets.py once used `F.pad`
+    without importing `F`): tools/undefined_names.py resolves every loaded name of every product module."""
+    import glob
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("undefined_names", os.path.join(root, "tools", "undefined_names.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    files = sorted(glob.glob(os.path.join(root, "joligen_b200", "*.py"))) + [
+        os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py"),
+        os.path.join(root, "baseline", "ref_runner.py"), os.path.join(root, "baseline", "install_ref.py")]
+    bad = []
+    for f in files:
+        bad += ["%s:%d %s" % (os.path.relpath(f, root), line, name) for line, name in mod.check_source(open(f).read(), f)]
+    assert not bad, bad
