@@ -674,16 +674,21 @@ class DiffusionGenerator(nn.Module):
         per-frame work is identical to the image path; noise is returned in the folded [N,C,H,W] layout."""
         b = y_0.shape[0]
         frames = 0
+        # random draws in the reference's order (diffusion_generator.py:467-480): t, then u, then the noise — a run
+        # seeded like the reference's sees the same (t, gamma, noise)
+        _, sample_gammas, w = self.sample_noise_level(b, y_0.device, t, u)
         if y_0.dim() == 5:
             frames = y_0.shape[1]
             if noise is None:
-                noise = torch.randn_like(y_0)
+                # the reference draws on the folded "b c (f h) w" tensor (rearrange_5dto4d_fh, :460-463)
+                _, _, c, hh, ww = y_0.shape
+                noise = torch.randn((b, c, frames * hh, ww), dtype=y_0.dtype, device=y_0.device)
+                noise = noise.reshape(b, c, frames, hh, ww).permute(0, 2, 1, 3, 4)
             fold = lambda v: None if v is None else v.reshape((b * frames,) + tuple(v.shape[2:]))  # noqa: E731
             y_0, y_cond, mask, noise = fold(y_0), fold(y_cond), fold(mask), fold(noise)
             self.denoise_fn.model._clip["frames"] = frames
         if noise is None:
             noise = torch.randn_like(y_0)
-        _, sample_gammas, w = self.sample_noise_level(b, y_0.device, t, u)
         emb = self.compute_gammas(sample_gammas)
         g_per_image = sample_gammas.reshape(b)
         if frames:

@@ -559,6 +559,11 @@ def conv2d(x, weight, bias, packed, stride=1, pad=None, residual=None, res_scale
 
 
 def _gn_apply(fn, x, gamma, beta, film, groups, act, eps):
+    if gamma is not None and gamma.numel() != x.shape[-1]:
+        # a width that is not a multiple of 8 is stored zero-padded: the kernel would normalise over the padded
+        # channels (wrong groups) and read gamma / beta past their end
+        raise NotImplementedError("GroupNorm over %d channels stored as %d (channel counts must be multiples of 8)"
+                                  % (gamma.numel(), x.shape[-1]))
     st = _stamp(x, "_jg_stats") if FUSE_GN[0] else None
     aux = {} if FUSE_GN[0] else None
     out = fn.apply(x, gamma, beta, film, groups, act, eps, None if st is None else st[0], aux)

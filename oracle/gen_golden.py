@@ -88,8 +88,8 @@ def module_golden(name, cfgd, batch, wseed, dseed, rseed, full_grads):
     print(name, "loss", out["loss"], "noise_hat absmax", float(noise_hat.abs().max()))
 
 
-def plumbing_golden(name):
-    """The reference's own control path: options -> create_model -> optimize_parameters (train.py:183-281)."""
+def create_reference_model(size=32, batch=2):
+    """options -> create_model -> setup of the reference's PaletteModel on CPU (train.py:183-281) -> (model, opt)"""
     import train as ref_train
     from models import create_model
     from options.train_options import TrainOptions
@@ -108,7 +108,6 @@ def plumbing_golden(name):
 
     flat = flatten(nested)
     tmp = tempfile.mkdtemp()
-    size, batch = 32, 2
     flat.update({
         "gpu_ids": "-1", "data_crop_size": size, "data_load_size": size, "train_batch_size": batch,
         "dataroot": tmp, "checkpoints_dir": tmp, "name": "golden",
@@ -127,6 +126,13 @@ def plumbing_golden(name):
     model = create_model(opt, 0)
     model.setup(opt)
     model.use_temporal = False
+    return model, opt
+
+
+def plumbing_golden(name):
+    """The reference's own control path: options -> create_model -> optimize_parameters (train.py:183-281)."""
+    size, batch = 32, 2
+    model, opt = create_reference_model(size, batch)
     cfg = O.UNetCfg(**SMALL)
     wseed = 21
     params = O.init_params(cfg, wseed)

@@ -1,0 +1,543 @@
+"""TEST DOUBLE for `joligen_b200.kernels` — test infrastructure, never shipped, never measured.
+
+The product has no CPU path (every op raises without the CUDA library).  That leaves the HOST logic above the C ABI —
+`ops.py` (autograd plumbing: which tensor goes into which kernel argument, stamps, taps, concat slices), `nets.py`
+(module mirrors), `accelerate.py` (the swap under the reference's `BaseModel`) — untestable where there is no GPU.
+`install()` replaces the allocation-only wrappers of `joligen_b200/kernels.py` (the ONE place that crosses the C ABI)
+by torch-CPU restatements of each kernel's documented contract (`include/jg_b200.h`): same arguments, same layouts
+(NHWC bf16 channel slices, packed bf16 weights `[Cout8][R*S][Cin8]` / flipped `[Cin8][R*S][Cout8]`, fp32 `stats` /
+`ab` / `chan_stats`), bf16 rounding where the kernels store bf16, fp32 arithmetic in between.  With it the whole
+host stack runs on the CPU and is compared with the reference's golden vectors (tests/test_host_double.py) — and the
+UNMODIFIED reference's `PaletteModel.optimize_parameters()` runs with `accelerate(netG_A)` swapped in.
+
+Only `tests/` may import this module (it is a checker, like `oracle/`).  It says nothing about the CUDA kernels: those
+are held to the oracle by the `-m gpu` tests.
+"""
+import contextlib
+
+import torch
+import torch.nn.functional as F
+
+from joligen_b200 import kernels as K
+from joligen_b200 import lib as L
+
+BF = torch.bfloat16
+
+
+def _act(u, act):
+    if act == L.ACT_NONE:
+        return u
+    if act == L.ACT_RELU:
+        return torch.relu(u)
+    if act == L.ACT_LRELU02:
+        return F.leaky_relu(u, 0.2)
+    if act == L.ACT_TANH:
+        return torch.tanh(u)
+    if act == L.ACT_SILU:
+        return F.silu(u)
+    raise ValueError(act)
+
+
+def _nchw(x):
+    return x.float().permute(0, 3, 1, 2)
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1)
+
+
+def _check_rows(t):
+    K._ld(t)  # the real wrappers assert that every operand is an NHWC channel slice
+    assert t.dtype == BF
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# convolution
+# ---------------------------------------------------------------------------------------------------------------------
+def pack_conv_weight(w_oihw, want_dgrad=True, out=None):
+    cout, cin, r, s = w_oihw.shape
+    w = w_oihw.detach().float()
+    cin8, cout8 = (cin + 7) // 8 * 8, (cout + 7) // 8 * 8
+    wf = torch.zeros((cout8, r * s, cin8), dtype=BF)
+    wf[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, r * s, cin).to(BF)
+    wd = None
+    if want_dgrad:
+        wd = torch.zeros((cin8, r * s, cout8), dtype=BF)
+        wd[:cin, :, :cout] = w.permute(1, 2, 3, 0).reshape(cin, r * s, cout).flip(1).to(BF)
+    if out is not None:
+        out[0].copy_(wf)
+        if wd is not None and out[1] is not None:
+            out[1].copy_(wd)
+        return out
+    return wf, wd
+
+
+def _weight_oihw(w_packed, cout, r, s):
+    rows, rs, cin8 = w_packed.shape
+    assert rs == r * s and rows >= cout, (w_packed.shape, cout, r, s)
+    return w_packed[:cout].float().reshape(cout, r, s, cin8).permute(0, 3, 1, 2)
+
+
+def conv2d_fwd(x, w_packed, bias, cout, r, s, stride=1, pad=None, act=L.ACT_NONE, residual=None, res_scale=1.0,
+               out=None, stats=None, gn=None):
+    _check_rows(x)
+    n, h, w, cin = x.shape
+    if pad is None:
+        pad = (r - 1) // 2
+    assert cin == w_packed.shape[2], "x channels %d vs packed Cin8 %d" % (cin, w_packed.shape[2])
+    assert cin % 8 == 0 and w_packed.dtype == BF
+    ho, wo = K.conv_out_size(h, w, r, s, stride, pad)
+    y = F.conv2d(_nchw(x), _weight_oihw(w_packed, cout, r, s), None, stride=stride, padding=pad)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= cout
+        y = y + bias[:cout].float().view(1, -1, 1, 1)
+    if residual is not None:
+        _check_rows(residual)
+        assert gn is None, "gn_sums is not combinable with a residual operand"
+        assert tuple(residual.shape) == (n, ho, wo, cout), (residual.shape, (n, ho, wo, cout))
+        y = y + float(res_scale) * _nchw(residual)
+    y = _nhwc(_act(y, act)).to(BF)
+    if out is None:
+        out = torch.empty((n, ho, wo, cout), dtype=BF)
+    _check_rows(out)
+    assert tuple(out.shape) == (n, ho, wo, cout), (out.shape, (n, ho, wo, cout))
+    out.copy_(y)
+    if stats is not None:
+        assert stats.is_contiguous() and stats.dtype == torch.float32 and stats.numel() == n * cout * 2
+        yf = out.float().reshape(n, -1, cout)
+        stats.view(n, cout, 2).add_(torch.stack([yf.sum(1), (yf * yf).sum(1)], dim=-1))
+    if gn is not None:
+        x_gn, ab, gn_act, sums = gn
+        assert tuple(x_gn.shape) == (n, ho, wo, cout) and ab.numel() == n * cout * 2 and sums.numel() == n * cout * 2
+        a = ab.view(n, 1, 1, cout, 2)[..., 0]
+        b = ab.view(n, 1, 1, cout, 2)[..., 1]
+        u = (a * x_gn.float() + b).requires_grad_(True)
+        with torch.enable_grad():
+            v = _act(u, gn_act)
+        (du,) = torch.autograd.grad(v, u, out.float())
+        sums.view(n, cout, 2).add_(torch.stack([du.reshape(n, -1, cout).sum(1),
+                                                (du * x_gn.float()).reshape(n, -1, cout).sum(1)], dim=-1))
+    return out
+
+
+def chan_stats(x):
+    _check_rows(x)
+    n, h, w, c = x.shape
+    xf = x.float().reshape(n, -1, c)
+    return torch.stack([xf.sum(1), (xf * xf).sum(1)], dim=-1).contiguous()
+
+
+def conv2d_cropped(x, w_packed, bias, cout, r, s, pad, out_hw, act=L.ACT_NONE):
+    _check_rows(x)
+    y = F.conv2d(_nchw(x), _weight_oihw(w_packed, cout, r, s), None, stride=1, padding=pad)
+    if bias is not None:
+        y = y + bias[:cout].float().view(1, -1, 1, 1)
+    ho, wo = out_hw
+    assert y.shape[2] >= ho and y.shape[3] >= wo
+    return _nhwc(_act(y[:, :, :ho, :wo], act)).to(BF).contiguous()
+
+
+def conv2d_wgrad(x, dy, cout, r, s, stride=1, pad=None, out=None, beta=0.0):
+    _check_rows(x)
+    _check_rows(dy)
+    if pad is None:
+        pad = (r - 1) // 2
+    cin = x.shape[-1]
+    assert dy.shape[-1] >= cout
+    dw = torch.nn.grad.conv2d_weight(_nchw(x).contiguous(), (cout, cin, r, s), _nchw(dy[..., :cout]).contiguous(),
+                                     stride=stride, padding=pad)
+    if out is None:
+        return dw.contiguous()
+    out.mul_(beta).add_(dw)
+    return out
+
+
+def conv2d_wgrad_acc(x, dy, cout, r, s, acc, stride=1, pad=None):
+    """layout 1 ([Cout][R*S][Cin]) accumulator, like the halo wgrad kernels report."""
+    dw = conv2d_wgrad(x, dy, cout, r, s, stride=stride, pad=pad)
+    acc.view(cout, r * s, x.shape[-1]).add_(dw.permute(0, 2, 3, 1).reshape(cout, r * s, x.shape[-1]))
+    return 1
+
+
+def bias_grad(dy):
+    _check_rows(dy)
+    return dy.float().reshape(-1, dy.shape[-1]).sum(0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# layout
+# ---------------------------------------------------------------------------------------------------------------------
+def nchw_to_nhwc(x, ld=None):
+    n, c, h, w = x.shape
+    if ld is None:
+        ld = (c + 7) // 8 * 8
+    out = torch.zeros((n, h, w, ld), dtype=BF)
+    out[..., :c] = x.float().permute(0, 2, 3, 1).to(BF)
+    return out
+
+
+def nhwc_to_nchw(x, c=None):
+    _check_rows(x)
+    if c is None:
+        c = x.shape[-1]
+    return x[..., :c].float().permute(0, 3, 1, 2).contiguous()
+
+
+def copy_channels(src, dst, accumulate=False):
+    _check_rows(src)
+    _check_rows(dst)
+    assert dst.shape == src.shape
+    if accumulate:
+        dst.copy_((dst.float() + src.float()).to(BF))
+    else:
+        dst.copy_(src)
+    return dst
+
+
+def resample2x(x, mode):
+    _check_rows(x)
+    xf = _nchw(x)
+    if mode == 0:      # F.interpolate(scale_factor=2, mode="nearest")
+        y = F.interpolate(xf, scale_factor=2, mode="nearest")
+    elif mode == 1:    # nn.AvgPool2d(2, 2)
+        y = F.avg_pool2d(xf, 2, 2)
+    elif mode == 2:    # backward of mode 0: sum over each 2x2 block
+        y = F.avg_pool2d(xf, 2, 2) * 4.0
+    elif mode == 3:    # backward of mode 1: 0.25 * nearest upsample
+        y = F.interpolate(xf, scale_factor=2, mode="nearest") * 0.25
+    else:
+        raise ValueError(mode)
+    return _nhwc(y).to(BF).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GroupNorm (+FiLM)(+act)
+# ---------------------------------------------------------------------------------------------------------------------
+_EPS = 1e-5
+
+
+def _gn_forward(x32, gamma, beta, groups, film, act, mean=None, rstd=None):
+    """fp32 [N,H,W,C] -> act(((x - mean) * rstd * gamma + beta) * (1 + scale) + shift); differentiable."""
+    n, h, w, c = x32.shape
+    cg = c // groups
+    xg = x32.reshape(n, h * w, groups, cg)
+    if mean is None:
+        mean = xg.mean(dim=(1, 3), keepdim=True)
+        var = ((xg - mean) ** 2).mean(dim=(1, 3), keepdim=True)
+        rstd = (var + _EPS).rsqrt()
+    xh = ((xg - mean) * rstd).reshape(n, h, w, c)
+    if gamma is not None:
+        xh = xh * gamma.view(1, 1, 1, c) + beta.view(1, 1, 1, c)
+    if film is not None:
+        xh = xh * (1.0 + film[:, :c].reshape(n, 1, 1, c)) + film[:, c:].reshape(n, 1, 1, c)
+    return _act(xh, act), mean.reshape(n, groups), rstd.reshape(n, groups)
+
+
+def groupnorm_fwd(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5, out=None, chan_stats=None):
+    _check_rows(x)
+    assert abs(eps - _EPS) < 1e-12
+    n, h, w, c = x.shape
+    assert c % groups == 0
+    x32 = x.float()
+    mean = rstd = None
+    if chan_stats is not None:
+        # the statistics pass is skipped: (mean, rstd) come from the producer's per-(image, channel) sums — which must
+        # therefore describe THIS tensor (a stale or mis-routed stamp shows up as a parity failure here)
+        assert chan_stats.is_contiguous() and chan_stats.dtype == torch.float32 and chan_stats.numel() == n * c * 2
+        cs = chan_stats.view(n, groups, c // groups, 2).sum(2)
+        cnt = float(h * w * (c // groups))
+        m = cs[..., 0] / cnt
+        var = (cs[..., 1] / cnt - m * m).clamp_min(0.0)
+        mean, rstd = m.view(n, 1, groups, 1), (var + _EPS).rsqrt().view(n, 1, groups, 1)
+    if film is not None:
+        assert film.dtype == torch.float32 and tuple(film.shape) == (n, 2 * c), (film.shape, (n, 2 * c))
+    y, mean, rstd = _gn_forward(x32, None if gamma is None else gamma.detach().float(),
+                                None if beta is None else beta.detach().float(), groups,
+                                None if film is None else film.detach(), act, mean, rstd)
+    y = y.to(BF)
+    if out is None:
+        out = y.contiguous()
+    else:
+        _check_rows(out)
+        out.copy_(y)
+    stats = torch.stack([mean, rstd], dim=-1).contiguous()
+    cg = c // groups
+    g = torch.ones(c) if gamma is None else gamma.detach().float()
+    bt = torch.zeros(c) if beta is None else beta.detach().float()
+    a = rstd.repeat_interleave(cg, dim=1) * g
+    b = bt - mean.repeat_interleave(cg, dim=1) * a
+    if film is not None:
+        sc, sh = film[:, :c], film[:, c:]
+        a, b = a * (1 + sc), b * (1 + sc) + sh
+    return out, stats, torch.stack([a, b], dim=-1).contiguous()
+
+
+def groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab, need_param_grads=True, need_film_grad=False,
+                  dx=None, addend=None, colsum=None, addend2=None, sums_pre=None, dfilm_out=None):
+    _check_rows(x)
+    _check_rows(dy)
+    n, h, w, c = x.shape
+    assert tuple(dy.shape) == tuple(x.shape), (dy.shape, x.shape)
+    assert tuple(stats.shape) == (n, groups, 2) and tuple(ab.shape) == (n, c, 2)
+    x32 = x.float().requires_grad_(True)
+    leaves = [x32]
+    g32 = b32 = f32 = None
+    if gamma is not None:
+        g32, b32 = gamma.detach().float().requires_grad_(True), beta.detach().float().requires_grad_(True)
+        leaves += [g32, b32]
+    if film is not None:
+        f32 = film.detach().float().requires_grad_(True)
+        leaves.append(f32)
+    with torch.enable_grad():
+        y, mean, rstd = _gn_forward(x32, g32, b32, groups, f32, act)
+    # the saved statistics must be the ones of this x (they are what the real kernel differentiates with)
+    assert torch.allclose(mean, stats[..., 0], rtol=1e-3, atol=1e-3), "groupnorm_bwd: stats do not belong to x"
+    if sums_pre is not None:
+        a = ab[..., 0].view(n, 1, 1, c)
+        b = ab[..., 1].view(n, 1, 1, c)
+        u = (a * x.float() + b).requires_grad_(True)
+        with torch.enable_grad():
+            v = _act(u, act)
+        (du,) = torch.autograd.grad(v, u, dy.float())
+        ref = torch.stack([du.reshape(n, -1, c).sum(1), (du * x.float()).reshape(n, -1, c).sum(1)], dim=-1)
+        assert torch.allclose(sums_pre.view(n, c, 2), ref, rtol=2e-2, atol=1e-2 * float(ref.abs().max())), \
+            "groupnorm_bwd: sums_pre do not belong to (x, dy)"
+    grads = torch.autograd.grad(y, leaves, dy.float(), allow_unused=True)
+    d = grads[0]
+    if addend is not None:
+        _check_rows(addend)
+        d = d + addend.float()
+    if addend2 is not None:
+        assert addend is not None, "addend2 requires addend"
+        _check_rows(addend2)
+        d = d + addend2.float()
+    dxo = d.to(BF)
+    if dx is None:
+        dx = dxo.contiguous()
+    else:
+        dx.copy_(dxo)
+    if colsum is not None:
+        colsum.copy_(d.reshape(-1, c).sum(0))
+    dgamma = dbeta = dfilm = None
+    i = 1
+    if gamma is not None:
+        if need_param_grads:
+            dgamma, dbeta = grads[1].contiguous(), grads[2].contiguous()
+        i = 3
+    if film is not None and need_film_grad:
+        df = grads[i]
+        ok = dfilm_out is not None and dfilm_out.is_contiguous() and tuple(dfilm_out.shape) == (n, 2 * c)
+        if ok:
+            dfilm_out.copy_(df)
+            dfilm = dfilm_out
+        else:
+            dfilm = df.contiguous()
+    return dx, dgamma, dbeta, dfilm
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------------------------------
+def _attn(qkv32, heads, ch, layout):
+    n, h, w, c3 = qkv32.shape
+    t = h * w
+    assert c3 == 3 * heads * ch
+    z = qkv32.reshape(n, t, c3)
+    if layout == 0:   # QKVAttentionLegacy: per head (q | k | v)
+        z = z.reshape(n, t, heads, 3, ch)
+        q, k, v = z[:, :, :, 0], z[:, :, :, 1], z[:, :, :, 2]
+    else:             # QKVAttention: (q | k | v), each heads * ch wide
+        z = z.reshape(n, t, 3, heads, ch)
+        q, k, v = z[:, :, 0], z[:, :, 1], z[:, :, 2]
+    scale = ch ** -0.25
+    s = torch.einsum("nthc,nshc->nhts", q * scale, k * scale)
+    p = torch.softmax(s, dim=-1)
+    o = torch.einsum("nhts,nshc->nthc", p, v)
+    return o.reshape(n, h, w, heads * ch), torch.logsumexp(s, dim=-1).reshape(n * heads, t)
+
+
+def attn_fwd(qkv, heads, ch, layout=0, out=None):
+    _check_rows(qkv)
+    o, lse = _attn(qkv.float(), heads, ch, layout)
+    o = o.to(BF)
+    if out is None:
+        out = o.contiguous()
+    else:
+        _check_rows(out)
+        out.copy_(o)
+    return out, lse.contiguous()
+
+
+def attn_bwd(qkv, out, d_out, lse, heads, ch, layout=0):
+    _check_rows(qkv)
+    _check_rows(d_out)
+    z = qkv.float().requires_grad_(True)
+    with torch.enable_grad():
+        o, _ = _attn(z, heads, ch, layout)
+    (d,) = torch.autograd.grad(o, z, d_out.float())
+    return d.to(BF).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# small fp32 Linears
+# ---------------------------------------------------------------------------------------------------------------------
+def linear_fwd(x, w, b, act_in=L.ACT_NONE, act_out=L.ACT_NONE):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    return _act(F.linear(_act(x, act_in), w.detach(), None if b is None else b.detach()), act_out)
+
+
+def linear_bwd(x, w, dy, act_in=L.ACT_NONE, need_dx=True):
+    x32 = x.detach().requires_grad_(True)
+    w32 = w.detach().requires_grad_(True)
+    with torch.enable_grad():
+        y = F.linear(_act(x32, act_in), w32)
+    dx, dw = torch.autograd.grad(y, [x32, w32], dy)
+    return (dx if need_dx else None), dw, dy.sum(0)
+
+
+class LinearBank:
+    """kernels.LinearBank without the device table: keeps the Linear modules themselves."""
+
+    def __init__(self, linears, device):
+        self.linears = list(linears)
+        self.widths = [lin.weight.shape[0] for lin in linears]
+        self.in_features = linears[0].weight.shape[1]
+        self.offsets, off = [], 0
+        for lin in linears:
+            assert lin.weight.dtype == torch.float32 and lin.weight.is_contiguous()
+            self.offsets.append(off)
+            off += lin.weight.shape[0]
+        self.total_out, self.n = off, len(linears)
+        self.key = tuple((lin.weight.data_ptr(), 0 if lin.bias is None else lin.bias.data_ptr()) for lin in linears)
+
+
+def linear_batched_fwd(x, bank, act_in=L.ACT_NONE):
+    bsz = x.shape[0]
+    y = torch.empty((bsz * bank.total_out,), dtype=torch.float32)
+    for lin, off, o in zip(bank.linears, bank.offsets, bank.widths):
+        y[bsz * off:bsz * (off + o)] = linear_fwd(x, lin.weight, lin.bias, act_in).reshape(-1)
+    return y
+
+
+def linear_batched_bwd(x, bank, dy, act_in=L.ACT_NONE, need_dx=True):
+    bsz, i = x.shape
+    dw = torch.empty((bank.total_out, i), dtype=torch.float32)
+    db = torch.empty((bank.total_out,), dtype=torch.float32)
+    dx = torch.zeros_like(x) if need_dx else None
+    for lin, off, o in zip(bank.linears, bank.offsets, bank.widths):
+        d = dy[bsz * off:bsz * (off + o)].view(bsz, o)
+        dxi, dwi, dbi = linear_bwd(x, lin.weight, d, act_in, need_dx)
+        dw[off:off + o], db[off:off + o] = dwi, dbi
+        if need_dx:
+            dx += dxi
+    return dx, dw, db
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# prologue / loss / optimizer
+# ---------------------------------------------------------------------------------------------------------------------
+def _mask01(mask):
+    if mask is None:
+        return None
+    assert mask.is_contiguous() and mask.dtype in (torch.int64, torch.float32), "mask must be int64 or float32"
+    return mask.float().clamp(0.0, 1.0)
+
+
+def noise_pack(y0, ycond, noise, mask, gammas, ld=8):
+    b, c, h, w = y0.shape
+    g = gammas.reshape(b, 1, 1, 1).float()
+    yn = g.sqrt() * y0 + (1 - g).sqrt() * noise
+    m = _mask01(mask)
+    if m is not None:
+        m = m.reshape(b, 1, h, w)
+        yn = yn * m + (1 - m) * y0
+    out = torch.zeros((b, h, w, ld), dtype=BF)
+    out[..., :c] = ycond.permute(0, 2, 3, 1).to(BF)
+    out[..., c:2 * c] = yn.permute(0, 2, 3, 1).to(BF)
+    return out
+
+
+def _loss_terms(noise, noise_hat, mask, w_b):
+    b, c, h, w = noise.shape
+    diff = noise - noise_hat[..., :c].float().permute(0, 3, 1, 2)
+    m = _mask01(mask)
+    scale = torch.ones((b, 1, 1, 1))
+    if m is not None:
+        scale = scale * m.reshape(b, 1, h, w)
+    if w_b is not None:
+        scale = scale * w_b.reshape(b, 1, 1, 1)
+    return diff, scale
+
+
+def palette_loss_fwd(noise, noise_hat, mask, w_b, lambda_g=1.0, l1=False):
+    _check_rows(noise_hat)
+    diff, scale = _loss_terms(noise, noise_hat, mask, w_b)
+    e = scale * diff
+    return float(lambda_g) * (e.abs().mean() if l1 else (e * e).mean())
+
+
+def palette_loss_bwd(noise, noise_hat, mask, w_b, grad_out, lambda_g=1.0, l1=False):
+    diff, scale = _loss_terms(noise, noise_hat, mask, w_b)
+    e = scale * diff
+    coef = float(lambda_g) / e.numel() * grad_out.reshape(())
+    de = torch.sign(e) if l1 else 2.0 * e
+    dnh = -(coef * de * scale)  # d/d noise_hat
+    d = torch.zeros(noise_hat.shape, dtype=BF)
+    d[..., :noise.shape[1]] = dnh.permute(0, 2, 3, 1).to(BF)
+    return d
+
+
+def adamw_ema_step(p, g, m, v, ema, lr, beta1, beta2, eps, weight_decay, adamw, step, grad_scale=1.0, ema_beta=0.999,
+                   ema_init=False, step_dev=None):
+    if step_dev is not None:
+        step_dev.add_(1)
+        step = int(step_dev.reshape(-1)[0])
+        ema_init = step == 1
+    gr = g * grad_scale
+    if adamw:
+        p.mul_(1.0 - lr * weight_decay)
+    elif weight_decay:
+        gr = gr + weight_decay * p
+    m.mul_(beta1).add_(gr, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(gr, gr, value=1 - beta2)
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    p.addcdiv_(m, (v.sqrt() / (bc2 ** 0.5)).add_(eps), value=-lr / bc1)
+    if ema is not None:
+        if ema_init:
+            ema.copy_(p)
+        else:
+            ema.mul_(ema_beta).add_(p, alpha=1 - ema_beta)
+
+
+_DOUBLES = dict(pack_conv_weight=pack_conv_weight, conv2d_fwd=conv2d_fwd, chan_stats=chan_stats,
+                conv2d_cropped=conv2d_cropped, conv2d_wgrad=conv2d_wgrad, conv2d_wgrad_acc=conv2d_wgrad_acc,
+                bias_grad=bias_grad, nchw_to_nhwc=nchw_to_nhwc, nhwc_to_nchw=nhwc_to_nchw, copy_channels=copy_channels,
+                resample2x=resample2x, groupnorm_fwd=groupnorm_fwd, groupnorm_bwd=groupnorm_bwd, attn_fwd=attn_fwd,
+                attn_bwd=attn_bwd, linear_fwd=linear_fwd, linear_bwd=linear_bwd, LinearBank=LinearBank,
+                linear_batched_fwd=linear_batched_fwd, linear_batched_bwd=linear_batched_bwd, noise_pack=noise_pack,
+                palette_loss_fwd=palette_loss_fwd, palette_loss_bwd=palette_loss_bwd, adamw_ema_step=adamw_ema_step)
+
+
+def _refuse(name):
+    def f(*a, **k):
+        raise AssertionError("kernel double: kernels.%s has no CPU restatement (host test reached an unexpected op)"
+                             % name)
+    return f
+
+
+@contextlib.contextmanager
+def installed():
+    """Swap every public callable of joligen_b200.kernels: the restated ones by their doubles, the rest by a refusal
+    (so that nothing can reach the CUDA library by accident)."""
+    saved = {}
+    keep = {"conv_out_size", "make_conv_desc", "_ld", "_device_table", "_mask_ptrs"}
+    for name, obj in list(vars(K).items()):
+        if name.startswith("__") or name in keep or not (callable(obj)) or getattr(obj, "__module__", "") != K.__name__:
+            continue
+        saved[name] = obj
+        setattr(K, name, _DOUBLES.get(name, _refuse(name)))
+    try:
+        yield
+    finally:
+        for name, obj in saved.items():
+            setattr(K, name, obj)

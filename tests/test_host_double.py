@@ -1,0 +1,166 @@
+"""Host logic above the C ABI, on the CPU, through the kernel TEST DOUBLE (tests/kernel_double.py).
+
+What this proves (and what it does not): `ops.py` / `nets.py` / `accelerate.py` route the right tensors into the right
+kernel arguments — packed weights, channel-slice destinations, residual / FiLM / tap / concat plumbing, statistics
+stamps, gradient hand-offs — so that, with every kernel replaced by a torch-CPU restatement of its documented contract,
+the stack reproduces the unmodified reference's golden vectors, and the reference's own `PaletteModel` trains with
+`accelerate(netG_A)` swapped in.  The CUDA kernels themselves are NOT exercised here (that is `-m gpu`).
+"""
+import os
+
+import pytest
+import torch
+
+import kernel_double as KD
+
+REF = "/root/reference"
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _build(cfg, params):
+    from joligen_b200 import nets
+    g = nets.build_palette_generator(image_size=cfg.image_size, inner_channel=cfg.inner_channel,
+                                     res_blocks=cfg.res_blocks, attn_res=cfg.attn_res,
+                                     channel_mults=cfg.channel_mults, num_head_channels=cfg.num_head_channels,
+                                     use_scale_shift_norm=cfg.use_scale_shift_norm)
+    missing, unexpected = g.load_state_dict(params, strict=False)
+    assert not unexpected and all("gammas" in m or "posterior" in m for m in missing)
+    return g
+
+
+def _golden_case(golden_dir, name):
+    from oracle import palette_oracle as O
+    gold = torch.load(os.path.join(golden_dir, name))
+    cfg = O.UNetCfg(**gold["cfg"])
+    net = _build(cfg, O.init_params(cfg, gold["wseed"]))
+    data = O.synthetic_batch(gold["batch"], cfg.image_size, gold["dseed"])
+    torch.manual_seed(gold["rseed"])
+    t, u = O.sample_t_gamma(cfg, gold["batch"])
+    noise = torch.randn_like(data["gt"])
+    return gold, net, data, t, u, noise
+
+
+def _check_against_golden(gold, net, data, t, u, noise):
+    _, noise_hat, w = net(data["gt"], data["cond"], data["mask"], noise, t=t, u=u)
+    assert rel_l2(w, gold["min_snr_w"]) < 1e-6
+    assert rel_l2(noise_hat, gold["noise_hat"]) < 3e-2  # bf16 storage floor of the deep net (tests/test_gpu_palette.py)
+    loss = net.forward_loss(data["gt"], data["cond"], data["mask"], noise=noise, t=t, u=u)
+    assert abs(float(loss.detach()) - gold["loss"]) < 1e-2 * abs(gold["loss"])
+    loss.backward()
+    floor = 1e-3 * max(n for _, n in gold["grad_stats"].values())
+    err = ref = 0.0
+    for k, p in net.named_parameters():
+        assert p.grad is not None, k
+        g = p.grad.detach().double()
+        _, gnorm = gold["grad_stats"][k]
+        assert abs(float(g.norm()) - gnorm) <= 6e-2 * gnorm + floor, k
+        if "grads" in gold:
+            eb = float((g - gold["grads"][k].double()).norm())
+            assert eb <= 6e-2 * gnorm + floor, (k, eb, gnorm)
+            err += eb * eb
+            ref += gnorm * gnorm
+    if "grads" in gold:
+        assert (err / ref) ** 0.5 < 3e-2
+
+
+@pytest.mark.parametrize("name", ["palette_small.pt", "palette_mid.pt"])
+def test_generator_host_stack_vs_reference_golden(golden_dir, name):
+    """DiffusionGenerator -> PaletteDenoiseFn -> UNet (ResBlocks with FiLM, up / down, attention, concat-in-place, taps,
+    fused-statistics stamps, batched emb Linears) on the double == the reference's fp32 vectors at the bf16 floor."""
+    gold, net, data, t, u, noise = _golden_case(golden_dir, name)
+    with KD.installed():
+        _check_against_golden(gold, net, data, t, u, noise)
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_groupnorm_fusion_modes_route_the_right_sums(golden_dir, mode, monkeypatch):
+    """JG_FUSE_GN=0 (no stamps) and =1 (statistics AND backward sums ride in the conv epilogues): the double checks
+    inside groupnorm_fwd / _bwd that the sums handed over describe the tensor they are applied to."""
+    from joligen_b200 import ops
+    monkeypatch.setattr(ops, "FUSE_GN", [mode != "0"])
+    monkeypatch.setattr(ops, "FUSE_STATS", [mode == "1"])
+    monkeypatch.setattr(ops, "FUSE_SUMS", [mode == "1"])
+    monkeypatch.setattr(ops, "FUSE_SUMS_MAX_C", [1 << 20])
+    gold, net, data, t, u, noise = _golden_case(golden_dir, "palette_small.pt")
+    with KD.installed():
+        _check_against_golden(gold, net, data, t, u, noise)
+
+
+def test_modulewise_dropin_signatures_nchw():
+    """ResBlock / AttentionBlock / UNet keep the reference's NCHW fp32 call signatures (module-wise drop-in)."""
+    from joligen_b200 import nets
+    torch.manual_seed(0)
+    with KD.installed():
+        rb = nets.ResBlock(16, 32, 0.0, "groupnorm8", out_channel=24, use_scale_shift_norm=True)
+        x = torch.randn(2, 16, 8, 8, requires_grad=True)
+        emb = torch.randn(2, 32)
+        y = rb(x, emb)
+        assert y.shape == (2, 24, 8, 8) and y.dtype == torch.float32
+        y.sum().backward()
+        assert x.grad is not None and x.grad.shape == x.shape
+        # the non-FiLM branch (h + emb_out, then GN -> SiLU)
+        rb2 = nets.ResBlock(16, 32, 0.0, "groupnorm4", out_channel=24, use_scale_shift_norm=False)
+        y2 = rb2(torch.randn(2, 16, 8, 8), emb)
+        assert y2.shape == (2, 24, 8, 8)
+        # a width the NHWC layout has to pad (20 -> 24 channels) is refused, not normalised over the padding
+        rb3 = nets.ResBlock(16, 32, 0.0, "groupnorm4", out_channel=20, use_scale_shift_norm=False)
+        with pytest.raises(NotImplementedError, match="multiples of 8"):
+            rb3(torch.randn(2, 16, 8, 8), emb)
+        ab = nets.AttentionBlock(16, num_head_channels=8)
+        ya = ab(torch.randn(2, 16, 8, 8))
+        assert ya.shape == (2, 16, 8, 8)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_reference_palette_model_trains_with_accelerated_generator(golden_dir):
+    """THE drop-in claim: the UNMODIFIED reference's control path (options -> create_model -> setup -> set_input ->
+    optimize_parameters(): compute_palette_loss, loss.backward(), AdamW, ema_step with its copy.deepcopy) with
+    `model.netG_A = joligen_b200.accelerate(model.netG_A)` — INTEGRATION.md section 2 — reproduces the losses, weights
+    and EMA weights of the reference's own two steps (tests/golden/palette_plumbing.pt), seeded identically."""
+    from oracle import ref_stubs
+    ref_stubs.install()
+    from oracle import gen_golden
+    from oracle import palette_oracle as O
+    import joligen_b200
+    from joligen_b200 import nets
+    gold = torch.load(os.path.join(golden_dir, "palette_plumbing.pt"))
+    model, _ = gen_golden.create_reference_model(gold["size"], gold["batch"])
+    cfg = O.UNetCfg(**gold["cfg"])
+    model.netG_A.load_state_dict(O.init_params(cfg, gold["wseed"]), strict=False)
+    ref_params = dict(model.netG_A.named_parameters())
+    model.netG_A = joligen_b200.accelerate(model.netG_A)
+    assert isinstance(model.netG_A, nets.DiffusionGenerator)
+    assert all(p is ref_params[k] for k, p in model.netG_A.named_parameters())  # the optimizer keeps its tensors
+    losses = []
+    with KD.installed():
+        for step in range(2):
+            data = O.synthetic_batch(gold["batch"], gold["size"], gold["data_seeds"][step])
+            model.set_input({"A": data["cond"], "B": data["gt"], "B_label_mask": data["mask"],
+                             "B_label_cls": torch.zeros(gold["batch"], dtype=torch.long),
+                             "A_img_paths": ["a"] * gold["batch"]})
+            torch.manual_seed(gold["rng_seeds"][step])
+            model.optimize_parameters()
+            losses.append(float(model.loss_G_tot.detach()))
+    # same seeds => same (t, gamma, noise) draws as the reference (the generator draws in the reference's order)
+    for got, want in zip(losses, gold["losses"]):
+        assert abs(got - want) < 2e-2 * abs(want), (losses, gold["losses"])
+    sd = model.netG_A.state_dict()
+    for k, (_, n) in gold["param_stats"].items():
+        assert abs(float(sd[k].double().norm()) - n) <= 2e-2 * n + 1e-6, k
+    assert isinstance(model.netG_A_ema, nets.DiffusionGenerator)  # ema_step's deepcopy of the accelerated tree
+    ema = model.netG_A_ema.state_dict()
+    for k, (_, n) in gold["ema_stats"].items():
+        assert abs(float(ema[k].double().norm()) - n) <= 2e-2 * n + 1e-6, k
+    assert rel_l2(sd["denoise_fn.model.middle_block.1.qkv.weight"], gold["sample_param"]) < 2e-2
+
+
+def test_double_refuses_ops_it_does_not_restate():
+    from joligen_b200 import kernels as K
+    with KD.installed():
+        with pytest.raises(AssertionError, match="no CPU restatement"):
+            K.monce_fwd(None, None, 1, 0.07, 256)
+    assert K.monce_fwd.__module__ == "joligen_b200.kernels"  # restored
