@@ -133,6 +133,63 @@ def _unetref_from_reference(ref):
     return nets_ref.UNetGeneratorRefAttn(use_new_attention_order=new_order, **kw, **_common_unet_kwargs(ref))
 
 
+def _layer_kinds(seq):
+    """Class names of a Sequential's layers, ResnetBlocks expanded: the GAN mirrors must hold the SAME layer sequence as
+    the reference net (a BatchNorm / Dropout / spectral-norm / separable-conv variant must not be swapped silently)."""
+    out = []
+    for m in seq:
+        if type(m).__name__ == "ResnetBlock":
+            out.append(["ResnetBlock"] + _layer_kinds(m.conv_block))
+        else:
+            out.append(type(m).__name__)
+    return out
+
+
+def _same_layers(dst_seq, src_seq, what):
+    a, b = _layer_kinds(dst_seq), _layer_kinds(src_seq)
+    if a != b:
+        raise NotImplementedError("accelerate: %s layer sequence of the reference is not the one the B200 mirror "
+                                  "implements (reference %s)" % (what, b[:6]))
+    for d, r in zip(dst_seq.modules(), src_seq.modules()):
+        if isinstance(r, (nn.Conv2d, nn.ConvTranspose2d)):
+            if (r.kernel_size, r.stride, r.padding, r.dilation, r.groups) != \
+                    (d.kernel_size, d.stride, d.padding, d.dilation, d.groups) or hasattr(r, "weight_orig"):
+                raise NotImplementedError("accelerate: %s convolution geometry / parametrisation differs" % what)
+        if isinstance(r, nn.InstanceNorm2d) and (r.affine or r.track_running_stats):
+            raise NotImplementedError("accelerate: InstanceNorm2d with affine / running statistics")
+        if isinstance(r, nn.LeakyReLU) and abs(r.negative_slope - d.negative_slope) > 1e-12:
+            raise NotImplementedError("accelerate: LeakyReLU slope differs")
+
+
+def _resnet_generator_from_reference(ref):
+    """models/modules/resnet_architecture/resnet_generator.py:98-164 (gan_networks.define_G, G_netG resnet_*blocks):
+    the class keeps no hyper-parameters, they are read off its layers."""
+    from . import nets_gan
+    enc_convs = [m for m in ref.encoder.model if isinstance(m, nn.Conv2d)]
+    dec_convs = [m for m in ref.decoder.model if isinstance(m, nn.Conv2d)]
+    if not enc_convs or not dec_convs:
+        raise NotImplementedError("accelerate: ResnetGenerator without plain nn.Conv2d stem / head (mobile variant)")
+    n_blocks = sum(type(m).__name__ == "ResnetBlock" for m in ref.encoder.model)
+    new = nets_gan.ResnetGenerator(enc_convs[0].in_channels, dec_convs[-1].out_channels, enc_convs[0].out_channels,
+                                   n_blocks=n_blocks)
+    _same_layers(new.encoder.model, ref.encoder.model, "ResnetGenerator encoder")
+    _same_layers(new.decoder.model, ref.decoder.model, "ResnetGenerator decoder")
+    return new
+
+
+def _nlayer_discriminator_from_reference(ref):
+    """models/modules/discriminators.py:10-117 (gan_networks.define_D, D_netDs basic / n_layers)."""
+    from . import nets_gan
+    if getattr(ref, "freq_space", False):
+        raise NotImplementedError("accelerate: NLayerDiscriminator in wavelet space (D_freq_space)")
+    convs = [m for m in ref.model if isinstance(m, nn.Conv2d)]
+    if len(convs) < 3:
+        raise NotImplementedError("accelerate: NLayerDiscriminator with %d convolutions" % len(convs))
+    new = nets_gan.NLayerDiscriminator(convs[0].in_channels, convs[0].out_channels, n_layers=len(convs) - 2)
+    _same_layers(new.model, ref.model, "NLayerDiscriminator")
+    return new
+
+
 def accelerate(module: nn.Module) -> nn.Module:
     """Returns the accelerated module (the same object with children swapped, or a new root when the
     root itself is a hot-path class)."""
@@ -172,6 +229,16 @@ def accelerate(module: nn.Module) -> nn.Module:
         return new
     if cls == "UNetGeneratorRefAttn" and hasattr(module, "input_blocks_ref"):
         new = _unetref_from_reference(module)
+        _adopt(new, module)
+        new.train(module.training)
+        return new
+    if cls == "ResnetGenerator" and hasattr(module, "encoder") and hasattr(module, "decoder"):
+        new = _resnet_generator_from_reference(module)
+        _adopt(new, module)
+        new.train(module.training)
+        return new
+    if cls == "NLayerDiscriminator" and isinstance(getattr(module, "model", None), nn.Sequential):
+        new = _nlayer_discriminator_from_reference(module)
         _adopt(new, module)
         new.train(module.training)
         return new

@@ -47,9 +47,9 @@ def seeded(net, seed):
     return shapes, init_params_from_shapes(shapes, seed)
 
 
-def main(nce_loss=None):
-    """nce_loss None: the example's own --alg_cut_nce_loss (monce) -> cut_plumbing.pt;
-    "patchnce" -> cut_plumbing_patchnce.pt (the variant the CUDA path implements)."""
+def create_reference_model(nce_loss=None):
+    """options -> create_model -> data_dependent_initialize -> setup of the reference's cut_model on CPU, seeded weights
+    loaded -> (model, opt, seeded parameter dicts)"""
     ref_stubs.install()
     import train as ref_train
     from models import create_model
@@ -93,6 +93,13 @@ def main(nce_loss=None):
     model.netG_A.load_state_dict(pG)
     model.netF.load_state_dict(pF)
     model.netD_B_basic.load_state_dict(pD)
+    return model, opt, a0, (shapes_G, pG), (shapes_F, pF), (shapes_D, pD)
+
+
+def main(nce_loss=None):
+    """nce_loss None: the example's own --alg_cut_nce_loss (monce) -> cut_plumbing.pt;
+    "patchnce" -> cut_plumbing_patchnce.pt (the variant the CUDA path implements)."""
+    model, opt, a0, (shapes_G, pG), (shapes_F, pF), (shapes_D, pD) = create_reference_model(nce_loss)
     nce_layers = list(model.nce_layers)
     with torch.no_grad():
         hw = [f.shape[2] * f.shape[3] for f in model.netG_A.get_feats(a0, nce_layers)]

@@ -509,13 +509,87 @@ def adamw_ema_step(p, g, m, v, ema, lr, beta1, beta2, eps, weight_decay, adamw, 
             ema.mul_(ema_beta).add_(p, alpha=1 - ema_beta)
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GAN generator / discriminator helpers
+# ---------------------------------------------------------------------------------------------------------------------
+def pad2d(x, pad, mode=0):
+    _check_rows(x)
+    return _nhwc(F.pad(_nchw(x), (pad,) * 4, mode="reflect" if mode == 0 else "replicate")).to(BF).contiguous()
+
+
+def pad2d_bwd(dpad, pad, mode=0):
+    _check_rows(dpad)
+    n, hp, wp, c = dpad.shape
+    x = torch.zeros((n, c, hp - 2 * pad, wp - 2 * pad), requires_grad=True)
+    with torch.enable_grad():
+        y = F.pad(x, (pad,) * 4, mode="reflect" if mode == 0 else "replicate")
+    (d,) = torch.autograd.grad(y, x, _nchw(dpad))
+    return _nhwc(d).to(BF).contiguous()
+
+
+def dilate2x(x):
+    _check_rows(x)
+    n, h, w, c = x.shape
+    out = torch.zeros((n, 2 * h, 2 * w, c), dtype=BF)
+    out[:, ::2, ::2] = x
+    return out
+
+
+def undilate2x(x):
+    _check_rows(x)
+    return x[:, ::2, ::2].contiguous()
+
+
+def act_bwd(y, dy, act):
+    _check_rows(y)
+    _check_rows(dy)
+    yf = y.float()
+    if act == L.ACT_TANH:
+        g = 1.0 - yf * yf
+    elif act == L.ACT_LRELU02:
+        g = torch.where(yf > 0, 1.0, 0.2)
+    elif act == L.ACT_RELU:
+        g = (yf > 0).float()
+    else:
+        raise ValueError(act)
+    return (dy.float() * g).to(BF).contiguous()
+
+
+def _gan_terms(pred, c_real, mode, target, sign):
+    p = pred[..., :c_real].float().requires_grad_(True)
+    with torch.enable_grad():
+        if mode == K.GAN_LSGAN:
+            loss = ((p - target) ** 2).mean()
+        elif mode == K.GAN_HINGE:
+            loss = torch.relu(1.0 - sign * p).mean()
+        else:
+            loss = (-sign * p).mean()
+    return p, loss
+
+
+def gan_loss_fwd(pred, c_real, mode, target, sign):
+    _check_rows(pred)
+    return _gan_terms(pred, c_real, mode, target, sign)[1].detach()
+
+
+def gan_loss_bwd(pred, c_real, mode, target, sign, grad_out):
+    p, loss = _gan_terms(pred, c_real, mode, target, sign)
+    (d,) = torch.autograd.grad(loss, p, grad_out.reshape(()).float())
+    out = torch.zeros(pred.shape, dtype=BF)
+    out[..., :c_real] = d.to(BF)
+    return out
+
+
 _DOUBLES = dict(pack_conv_weight=pack_conv_weight, conv2d_fwd=conv2d_fwd, chan_stats=chan_stats,
                 conv2d_cropped=conv2d_cropped, conv2d_wgrad=conv2d_wgrad, conv2d_wgrad_acc=conv2d_wgrad_acc,
                 bias_grad=bias_grad, nchw_to_nhwc=nchw_to_nhwc, nhwc_to_nchw=nhwc_to_nchw, copy_channels=copy_channels,
                 resample2x=resample2x, groupnorm_fwd=groupnorm_fwd, groupnorm_bwd=groupnorm_bwd, attn_fwd=attn_fwd,
                 attn_bwd=attn_bwd, linear_fwd=linear_fwd, linear_bwd=linear_bwd, LinearBank=LinearBank,
                 linear_batched_fwd=linear_batched_fwd, linear_batched_bwd=linear_batched_bwd, noise_pack=noise_pack,
-                palette_loss_fwd=palette_loss_fwd, palette_loss_bwd=palette_loss_bwd, adamw_ema_step=adamw_ema_step)
+                palette_loss_fwd=palette_loss_fwd, palette_loss_bwd=palette_loss_bwd, adamw_ema_step=adamw_ema_step,
+                pad2d=pad2d, pad2d_bwd=pad2d_bwd, dilate2x=dilate2x, undilate2x=undilate2x, act_bwd=act_bwd,
+                gan_loss_fwd=gan_loss_fwd, gan_loss_bwd=gan_loss_bwd)
 
 
 def _refuse(name):

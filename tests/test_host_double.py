@@ -164,3 +164,154 @@ def test_double_refuses_ops_it_does_not_restate():
         with pytest.raises(AssertionError, match="no CPU restatement"):
             K.monce_fwd(None, None, 1, 0.07, 256)
     assert K.monce_fwd.__module__ == "joligen_b200.kernels"  # restored
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GAN generator / discriminator (config 3)
+# ---------------------------------------------------------------------------------------------------------------------
+def _emulated_grads(fn, shapes, wseed, x, dy, *args):
+    """What bf16 STORAGE alone does to the gradients: the oracle in bf16-storage emulation (leaf gradients)."""
+    from oracle import gan_oracle as G
+    from oracle import palette_oracle as O
+    leaves = {k: v.requires_grad_(True) for k, v in G.init_from_shapes(shapes, wseed).items()}
+    O.EMULATE_BF16[0] = True
+    try:
+        fn(leaves, x, *args).backward(dy)
+    finally:
+        O.EMULATE_BF16[0] = False
+    return {k: v.grad for k, v in leaves.items()}
+
+
+def _check_grads_at_bf16_floor(named_grads, ref_grads, emu_grads):
+    """InstanceNorm backward on these small random nets is ill-conditioned under bf16 storage (the oracle's own
+    emulation is ~15 % off the fp32 gradients on the early layers): like tests/test_gpu_gan.py, the path under test must
+    be no worse than that floor warrants."""
+    gmax = max(float(v.double().norm()) for v in ref_grads.values())
+    for k, g in named_grads:
+        gref = ref_grads[k].double()
+        if float(gref.norm()) < 1e-3 * gmax:  # conv biases in front of an InstanceNorm: true gradient 0
+            assert float(g.double().norm()) < 5e-2 * gmax, k
+            continue
+        e = float((g.double() - gref).norm() / gref.norm())
+        e_emu = float((emu_grads[k].double() - gref).norm() / gref.norm())
+        assert e <= 1.5 * e_emu + 2e-2, (k, e, e_emu)
+
+
+def test_gan_nets_host_stack_vs_reference_golden(golden_dir):
+    """nets_gan.ResnetGenerator / NLayerDiscriminator / GANLoss on the double vs gan_resnet.pt / gan_nlayerd.pt."""
+    from joligen_b200 import nets_gan, ops
+    from oracle import gan_oracle as G
+    gold = torch.load(os.path.join(golden_dir, "gan_resnet.pt"))
+    net = nets_gan.ResnetGenerator(3, 3, gold["ngf"], n_blocks=gold["n_blocks"])
+    shapes = G.resnet_param_shapes(3, 3, gold["ngf"], gold["n_blocks"])
+    net.load_state_dict(G.init_from_shapes(shapes, gold["wseed"]))
+    with KD.installed():
+        y = net(gold["x"])
+        assert rel_l2(y, gold["y"]) < 3e-2
+        y.backward(gold["dy"])
+        feats = net.get_feats(gold["x"], gold["feat_ids"])
+    emu = _emulated_grads(G.resnet_generator, shapes, gold["wseed"], gold["x"], gold["dy"], gold["n_blocks"])
+    _check_grads_at_bf16_floor([(k, p.grad) for k, p in net.named_parameters()], gold["grads"], emu)
+    for f, fref in zip(feats, gold["feats"]):
+        assert tuple(f.shape) == tuple(fref.shape) and rel_l2(f, fref) < 3e-2
+    gold = torch.load(os.path.join(golden_dir, "gan_nlayerd.pt"))
+    netd = nets_gan.NLayerDiscriminator(3, gold["ndf"], n_layers=3)
+    netd.load_state_dict(G.init_from_shapes(G.nlayer_d_param_shapes(3, gold["ndf"], 3), gold["wseed"]))
+    with KD.installed():
+        pred = netd(gold["x"])
+        assert rel_l2(pred, gold["pred"]) < 3e-2
+        crit = nets_gan.GANLoss("lsgan")
+        logits = netd.forward_nhwc(ops.to_nhwc(gold["x"]))
+        loss_real = crit.forward_nhwc(logits, True)
+        assert abs(float(loss_real.detach()) - gold["loss_real"]) < 2e-2 * gold["loss_real"]
+        assert abs(float(crit.forward_nhwc(logits, False).detach()) - gold["loss_fake"]) < 2e-2 * gold["loss_fake"]
+        hinge = nets_gan.GANLoss("projected")
+        assert abs(float(hinge.forward_nhwc(logits, True).detach()) - gold["hinge_real"]) < 2e-2 * gold["hinge_real"]
+        loss_real.backward()
+    floor = 1e-3 * max(float(v.double().norm()) for v in gold["grads"].values())
+    for k, p in netd.named_parameters():
+        gref = gold["grads"][k].double()
+        assert float((p.grad.double() - gref).norm()) <= 8e-2 * float(gref.norm()) + floor, k
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_accelerate_swaps_reference_gan_nets_and_matches_their_forward():
+    """accelerate() on the reference's own ResnetGenerator / NLayerDiscriminator objects: parameters adopted, same
+    state_dict keys, and (on the double) the outputs, encoder features and every gradient of the reference modules
+    evaluating themselves in fp32, at the bf16-storage floor."""
+    import copy
+    from oracle import ref_stubs
+    ref_stubs.install()
+    import functools
+    import torch.nn as nn
+    from models.modules.discriminators import NLayerDiscriminator
+    from models.modules.resnet_architecture.resnet_generator import ResnetGenerator
+    import joligen_b200
+    from joligen_b200 import nets_gan
+    from oracle import gan_oracle as G
+    norm = functools.partial(nn.InstanceNorm2d, affine=False, track_running_stats=False)
+    cases = ((ResnetGenerator(3, 3, 16, norm_layer=norm, use_dropout=False, n_blocks=2), nets_gan.ResnetGenerator,
+              G.resnet_param_shapes(3, 3, 16, 2), G.resnet_generator, (2,)),
+             (NLayerDiscriminator(3, 16, n_layers=3, norm_layer=norm), nets_gan.NLayerDiscriminator,
+              G.nlayer_d_param_shapes(3, 16, 3), G.nlayer_discriminator, (3,)))
+    for ref, kind, shapes, oracle_fn, oargs in cases:
+        ref.load_state_dict(G.init_from_shapes(shapes, 77))
+        keep = copy.deepcopy(ref)
+        params, keys = dict(ref.named_parameters()), list(ref.state_dict().keys())
+        fast = joligen_b200.accelerate(ref)
+        assert isinstance(fast, kind) and list(fast.state_dict().keys()) == keys
+        assert all(p is params[k] for k, p in fast.named_parameters())
+        x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(1))
+        yr = keep(x)
+        dy = torch.randn(yr.shape, generator=torch.Generator().manual_seed(2))
+        yr.backward(dy)
+        with KD.installed():
+            yf = fast(x)
+            assert tuple(yf.shape) == tuple(yr.shape) and rel_l2(yf, yr) < 3e-2
+            yf.backward(dy)
+            if kind is nets_gan.ResnetGenerator:
+                ff = fast.get_feats(x, [0, 4, 8, 11])
+                for a, b in zip(ff, keep.get_feats(x, [0, 4, 8, 11])):
+                    assert tuple(a.shape) == tuple(b.shape) and rel_l2(a, b) < 3e-2
+        emu = _emulated_grads(oracle_fn, shapes, 77, x, dy, *oargs)
+        _check_grads_at_bf16_floor([(k, p.grad) for k, p in fast.named_parameters()],
+                                   {k: p.grad for k, p in keep.named_parameters()}, emu)
+    # variants the mirrors do not implement are refused, not swapped silently
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        joligen_b200.accelerate(ResnetGenerator(3, 3, 16, norm_layer=nn.BatchNorm2d, n_blocks=2))
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        joligen_b200.accelerate(NLayerDiscriminator(3, 16, n_layers=3, norm_layer=norm, use_spectral=True))
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        joligen_b200.accelerate(NLayerDiscriminator(3, 16, n_layers=3, norm_layer=norm, use_dropout=True))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("nce", [None, "patchnce"])
+def test_reference_cut_model_trains_with_accelerated_nets(golden_dir, nce):
+    """The reference's cut_model (example_gan_horse2zebra.json, reduced) through its own optimize_parameters() — GAN +
+    NCE + identity NCE for (G, F), then D — with netG_A and netD_B_basic swapped by accelerate(): losses of both steps
+    vs the reference's own (cut_plumbing*.pt)."""
+    from oracle import gen_golden_cut_plumbing as P
+    import joligen_b200
+    from joligen_b200 import nets_gan
+    gold = torch.load(os.path.join(golden_dir, "cut_plumbing.pt" if nce is None else "cut_plumbing_%s.pt" % nce))
+    model, _, _, _, _, _ = P.create_reference_model(nce)
+    model.netG_A = joligen_b200.accelerate(model.netG_A)
+    model.netD_B_basic = joligen_b200.accelerate(model.netD_B_basic)
+    assert isinstance(model.netG_A, nets_gan.ResnetGenerator)
+    assert isinstance(model.netD_B_basic, nets_gan.NLayerDiscriminator)
+    names = ["G_tot", "G_GAN_D_B_basic", "G_NCE", "G_NCE_Y", "D_tot"]
+    with KD.installed():
+        for step in range(2):
+            a, b = P.batch(gold["data_seeds"][step])
+            model.set_input({"A": a, "B": b, "A_img_paths": ["a"] * P.BATCH, "B_img_paths": ["b"] * P.BATCH})
+            torch.manual_seed(gold["rng_seeds"][step])
+            model.optimize_parameters()
+            for n in names:
+                got, want = float(getattr(model, "loss_" + n).detach()), gold["losses"][step][n]
+                # step 0 is a pure forward comparison; step 1 sits behind one Adam update of a GAN (sign-like steps
+                # from near-zero gradients): the bounds of tests/test_gpu_widen_cut.py
+                assert abs(got - want) < (3e-2 if step == 0 else 7e-2) * abs(want) + 1e-3, (step, n, got, want)
+    for k, (_, n) in gold["stats_D"].items():
+        if not k.endswith(".bias"):
+            assert abs(float(model.netD_B_basic.state_dict()[k].double().norm()) - n) <= 2e-2 * n, k
