@@ -46,6 +46,14 @@ def _nhwc(x):
     return x.permute(0, 2, 3, 1)
 
 
+
+def _raw(dst):
+    """The kernels write their outputs through raw pointers: torch's version counters never see it (a producer writes
+    a channel slice of a buffer other views of which autograd already holds).  Every write of the double into a
+    caller-provided tensor happens under this guard, so that the host logic sees exactly that behaviour."""
+    return torch.autograd._unsafe_preserve_version_counter(dst)
+
+
 def _check_rows(t):
     K._ld(t)  # the real wrappers assert that every operand is an NHWC channel slice
     assert t.dtype == BF
@@ -65,9 +73,11 @@ def pack_conv_weight(w_oihw, want_dgrad=True, out=None):
         wd = torch.zeros((cin8, r * s, cout8), dtype=BF)
         wd[:cin, :, :cout] = w.permute(1, 2, 3, 0).reshape(cin, r * s, cout).flip(1).to(BF)
     if out is not None:
-        out[0].copy_(wf)
+        with _raw(out[0]):
+            out[0].copy_(wf)
         if wd is not None and out[1] is not None:
-            out[1].copy_(wd)
+            with _raw(out[1]):
+                out[1].copy_(wd)
         return out
     return wf, wd
 
@@ -101,11 +111,13 @@ def conv2d_fwd(x, w_packed, bias, cout, r, s, stride=1, pad=None, act=L.ACT_NONE
         out = torch.empty((n, ho, wo, cout), dtype=BF)
     _check_rows(out)
     assert tuple(out.shape) == (n, ho, wo, cout), (out.shape, (n, ho, wo, cout))
-    out.copy_(y)
+    with _raw(out):
+        out.copy_(y)
     if stats is not None:
         assert stats.is_contiguous() and stats.dtype == torch.float32 and stats.numel() == n * cout * 2
         yf = out.float().reshape(n, -1, cout)
-        stats.view(n, cout, 2).add_(torch.stack([yf.sum(1), (yf * yf).sum(1)], dim=-1))
+        with _raw(stats):
+            stats.view(n, cout, 2).add_(torch.stack([yf.sum(1), (yf * yf).sum(1)], dim=-1))
     if gn is not None:
         x_gn, ab, gn_act, sums = gn
         assert tuple(x_gn.shape) == (n, ho, wo, cout) and ab.numel() == n * cout * 2 and sums.numel() == n * cout * 2
@@ -115,8 +127,9 @@ def conv2d_fwd(x, w_packed, bias, cout, r, s, stride=1, pad=None, act=L.ACT_NONE
         with torch.enable_grad():
             v = _act(u, gn_act)
         (du,) = torch.autograd.grad(v, u, out.float())
-        sums.view(n, cout, 2).add_(torch.stack([du.reshape(n, -1, cout).sum(1),
-                                                (du * x_gn.float()).reshape(n, -1, cout).sum(1)], dim=-1))
+        with _raw(sums):
+            sums.view(n, cout, 2).add_(torch.stack([du.reshape(n, -1, cout).sum(1),
+                                                    (du * x_gn.float()).reshape(n, -1, cout).sum(1)], dim=-1))
     return out
 
 
@@ -148,14 +161,16 @@ def conv2d_wgrad(x, dy, cout, r, s, stride=1, pad=None, out=None, beta=0.0):
                                      stride=stride, padding=pad)
     if out is None:
         return dw.contiguous()
-    out.mul_(beta).add_(dw)
+    with _raw(out):
+        out.mul_(beta).add_(dw)
     return out
 
 
 def conv2d_wgrad_acc(x, dy, cout, r, s, acc, stride=1, pad=None):
     """layout 1 ([Cout][R*S][Cin]) accumulator, like the halo wgrad kernels report."""
     dw = conv2d_wgrad(x, dy, cout, r, s, stride=stride, pad=pad)
-    acc.view(cout, r * s, x.shape[-1]).add_(dw.permute(0, 2, 3, 1).reshape(cout, r * s, x.shape[-1]))
+    with _raw(acc):
+        acc.view(cout, r * s, x.shape[-1]).add_(dw.permute(0, 2, 3, 1).reshape(cout, r * s, x.shape[-1]))
     return 1
 
 
@@ -187,10 +202,11 @@ def copy_channels(src, dst, accumulate=False):
     _check_rows(src)
     _check_rows(dst)
     assert dst.shape == src.shape
-    if accumulate:
-        dst.copy_((dst.float() + src.float()).to(BF))
-    else:
-        dst.copy_(src)
+    with _raw(dst):
+        if accumulate:
+            dst.copy_((dst.float() + src.float()).to(BF))
+        else:
+            dst.copy_(src)
     return dst
 
 
@@ -216,15 +232,16 @@ def resample2x(x, mode):
 _EPS = 1e-5
 
 
-def _gn_forward(x32, gamma, beta, groups, film, act, mean=None, rstd=None):
-    """fp32 [N,H,W,C] -> act(((x - mean) * rstd * gamma + beta) * (1 + scale) + shift); differentiable."""
+def _gn_forward(x32, gamma, beta, groups, film, act, mean=None, rstd=None, eps=_EPS):
+    """fp32 [N,H,W,C] -> act(((x - mean) * rstd * gamma + beta) * (1 + scale) + shift); differentiable.
+    eps: a float, or a [N,1,G,1] tensor (the backward recovers it from the saved rstd)."""
     n, h, w, c = x32.shape
     cg = c // groups
     xg = x32.reshape(n, h * w, groups, cg)
     if mean is None:
         mean = xg.mean(dim=(1, 3), keepdim=True)
         var = ((xg - mean) ** 2).mean(dim=(1, 3), keepdim=True)
-        rstd = (var + _EPS).rsqrt()
+        rstd = (var + eps).rsqrt()
     xh = ((xg - mean) * rstd).reshape(n, h, w, c)
     if gamma is not None:
         xh = xh * gamma.view(1, 1, 1, c) + beta.view(1, 1, 1, c)
@@ -235,7 +252,6 @@ def _gn_forward(x32, gamma, beta, groups, film, act, mean=None, rstd=None):
 
 def groupnorm_fwd(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5, out=None, chan_stats=None):
     _check_rows(x)
-    assert abs(eps - _EPS) < 1e-12
     n, h, w, c = x.shape
     assert c % groups == 0
     x32 = x.float()
@@ -248,18 +264,19 @@ def groupnorm_fwd(x, gamma, beta, groups, film=None, act=L.ACT_NONE, eps=1e-5, o
         cnt = float(h * w * (c // groups))
         m = cs[..., 0] / cnt
         var = (cs[..., 1] / cnt - m * m).clamp_min(0.0)
-        mean, rstd = m.view(n, 1, groups, 1), (var + _EPS).rsqrt().view(n, 1, groups, 1)
+        mean, rstd = m.view(n, 1, groups, 1), (var + eps).rsqrt().view(n, 1, groups, 1)
     if film is not None:
         assert film.dtype == torch.float32 and tuple(film.shape) == (n, 2 * c), (film.shape, (n, 2 * c))
     y, mean, rstd = _gn_forward(x32, None if gamma is None else gamma.detach().float(),
                                 None if beta is None else beta.detach().float(), groups,
-                                None if film is None else film.detach(), act, mean, rstd)
+                                None if film is None else film.detach(), act, mean, rstd, eps)
     y = y.to(BF)
     if out is None:
         out = y.contiguous()
     else:
         _check_rows(out)
-        out.copy_(y)
+        with _raw(out):
+            out.copy_(y)
     stats = torch.stack([mean, rstd], dim=-1).contiguous()
     cg = c // groups
     g = torch.ones(c) if gamma is None else gamma.detach().float()
@@ -288,10 +305,16 @@ def groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab, need_param_g
     if film is not None:
         f32 = film.detach().float().requires_grad_(True)
         leaves.append(f32)
+    # eps is not an argument of the backward: it is whatever the saved rstd was made with
+    with torch.no_grad():
+        xg = x.float().reshape(n, h * w, groups, c // groups)
+        var = ((xg - xg.mean(dim=(1, 3), keepdim=True)) ** 2).mean(dim=(1, 3), keepdim=True)
+        eps = (stats[..., 1].view(n, 1, groups, 1) ** -2 - var).clamp_min(0.0)
     with torch.enable_grad():
-        y, mean, rstd = _gn_forward(x32, g32, b32, groups, f32, act)
+        y, mean, rstd = _gn_forward(x32, g32, b32, groups, f32, act, eps=eps)
     # the saved statistics must be the ones of this x (they are what the real kernel differentiates with)
     assert torch.allclose(mean, stats[..., 0], rtol=1e-3, atol=1e-3), "groupnorm_bwd: stats do not belong to x"
+    assert torch.allclose(rstd, stats[..., 1], rtol=2e-2), "groupnorm_bwd: stats do not belong to x"
     if sums_pre is not None:
         a = ab[..., 0].view(n, 1, 1, c)
         b = ab[..., 1].view(n, 1, 1, c)
@@ -315,9 +338,11 @@ def groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab, need_param_g
     if dx is None:
         dx = dxo.contiguous()
     else:
-        dx.copy_(dxo)
+        with _raw(dx):
+            dx.copy_(dxo)
     if colsum is not None:
-        colsum.copy_(d.reshape(-1, c).sum(0))
+        with _raw(colsum):
+            colsum.copy_(d.reshape(-1, c).sum(0))
     dgamma = dbeta = dfilm = None
     i = 1
     if gamma is not None:
@@ -328,7 +353,8 @@ def groupnorm_bwd(x, dy, gamma, beta, groups, film, act, stats, ab, need_param_g
         df = grads[i]
         ok = dfilm_out is not None and dfilm_out.is_contiguous() and tuple(dfilm_out.shape) == (n, 2 * c)
         if ok:
-            dfilm_out.copy_(df)
+            with _raw(dfilm_out):
+                dfilm_out.copy_(df)
             dfilm = dfilm_out
         else:
             dfilm = df.contiguous()
@@ -364,7 +390,8 @@ def attn_fwd(qkv, heads, ch, layout=0, out=None):
         out = o.contiguous()
     else:
         _check_rows(out)
-        out.copy_(o)
+        with _raw(out):
+            out.copy_(o)
     return out, lse.contiguous()
 
 
@@ -581,6 +608,148 @@ def gan_loss_bwd(pred, c_real, mode, target, sign, grad_out):
     return out
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# MotionModule (video UNet): LayerNorm (+ frame positional encoding), temporal attention, GEGLU
+# ---------------------------------------------------------------------------------------------------------------------
+def _ln(x32, gamma, beta, pe, frames, eps=1e-5):
+    n, h, w, c = x32.shape
+    mean = x32.mean(-1, keepdim=True)
+    var = ((x32 - mean) ** 2).mean(-1, keepdim=True)
+    rstd = (var + eps).rsqrt()
+    y = (x32 - mean) * rstd * gamma.view(1, 1, 1, c) + beta.view(1, 1, 1, c)
+    if pe is not None:
+        assert tuple(pe.shape) == (frames, c) and n % frames == 0
+        y = y + pe.float()[torch.arange(n) % frames].view(n, 1, 1, c)  # frame index = n % F
+    return y, mean, rstd
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5, pe=None, frames=1):
+    _check_rows(x)
+    y, mean, rstd = _ln(x.float(), gamma.detach().float(), beta.detach().float(), pe, frames, eps)
+    return y.to(BF).contiguous(), torch.cat([mean, rstd], dim=-1).reshape(-1, 2).contiguous()
+
+
+def layernorm_bwd(x, dy, gamma, stats, addend=None, colsum=None):
+    _check_rows(x)
+    _check_rows(dy)
+    n, h, w, c = x.shape
+    x32 = x.float().requires_grad_(True)
+    g32 = gamma.detach().float().requires_grad_(True)
+    b32 = torch.zeros(c, requires_grad=True)
+    with torch.enable_grad():
+        y, mean, _ = _ln(x32, g32, b32, None, 1)
+    assert torch.allclose(mean.reshape(-1), stats[:, 0], rtol=1e-3, atol=1e-3), "layernorm_bwd: stats do not belong to x"
+    dx, dg, db = torch.autograd.grad(y, [x32, g32, b32], dy.float())
+    if addend is not None:
+        _check_rows(addend)
+        dx = dx + addend.float()
+    if colsum is not None:
+        with _raw(colsum):
+            colsum.copy_(dx.reshape(-1, c).sum(0))
+    return dx.to(BF).contiguous(), dg.contiguous(), db.contiguous()
+
+
+def _tattn(qkv32, frames, heads):
+    n, h, w, c3 = qkv32.shape
+    c = c3 // 3
+    ch = c // heads
+    b = n // frames
+    z = qkv32.reshape(b, frames, h * w, 3, heads, ch)
+    q, k, v = z[:, :, :, 0], z[:, :, :, 1], z[:, :, :, 2]                 # [b, f, p, heads, ch]
+    s = torch.einsum("bfphc,bgphc->bphfg", q, k) * (ch ** -0.5)
+    o = torch.einsum("bphfg,bgphc->bfphc", torch.softmax(s, dim=-1), v)
+    return o.reshape(n, h, w, c)
+
+
+def temporal_attn_fwd(qkv, frames, heads):
+    _check_rows(qkv)
+    return _tattn(qkv.float(), frames, heads).to(BF).contiguous()
+
+
+def temporal_attn_bwd(qkv, d_out, frames, heads):
+    _check_rows(qkv)
+    _check_rows(d_out)
+    z = qkv.float().requires_grad_(True)
+    with torch.enable_grad():
+        o = _tattn(z, frames, heads)
+    (d,) = torch.autograd.grad(o, z, d_out.float())
+    return d.to(BF).contiguous()
+
+
+def _geglu(x32):
+    c = x32.shape[-1] // 2
+    return x32[..., :c] * F.gelu(x32[..., c:])
+
+
+def geglu_fwd(x):
+    _check_rows(x)
+    return _geglu(x.float()).to(BF).contiguous()
+
+
+def geglu_bwd(x, dy):
+    _check_rows(x)
+    _check_rows(dy)
+    z = x.float().requires_grad_(True)
+    with torch.enable_grad():
+        y = _geglu(z)
+    (d,) = torch.autograd.grad(y, z, dy.float())
+    return d.to(BF).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# conditioning embeddings, reverse-diffusion step
+# ---------------------------------------------------------------------------------------------------------------------
+def _labels(idx, k):
+    assert idx.dtype in (torch.int64, torch.float32)
+    return idx.reshape(-1).to(torch.int64).clamp(0, k - 1)  # (.to(torch.int32) of the reference truncates)
+
+
+def embed_rows(table, idx, out, col0):
+    _check_rows(out)
+    k, e = table.shape
+    n, h, w, ld = out.shape
+    assert e % 2 == 0 and col0 % 2 == 0 and col0 + e <= ld and idx.numel() == n * h * w
+    with _raw(out):
+        out[..., col0:col0 + e] = table.detach().float()[_labels(idx, k)].reshape(n, h, w, e).to(BF)
+    return out
+
+
+def embed_rows_bwd(d, idx, col0, k, e):
+    _check_rows(d)
+    lab = _labels(idx, k)
+    rows = d[..., col0:col0 + e].float().reshape(-1, e)
+    dtable = torch.zeros((k, e)).index_add_(0, lab, rows)
+    counts = torch.zeros((k,)).index_add_(0, lab, torch.ones(lab.numel()))
+    return dtable, counts
+
+
+def ddpm_step(eps, y_t, y_cond, y_0, mask, noise, coef, ld=8, want_next_input=True, ddim=False):
+    """include/jg_b200.h jg_ddpm_step: coef [B][5] = (sqrt_recip_gammas, sqrt_recipm1_gammas, posterior_mean_coef1,
+    posterior_mean_coef2, exp(0.5 * posterior_log_variance_clipped)) gathered at t."""
+    _check_rows(eps)
+    b, c, h, w = y_t.shape
+    e = eps[..., :c].float().permute(0, 3, 1, 2)
+    cf = coef.reshape(b, 5, 1, 1, 1).float()
+    if ddim:
+        y = (cf[:, 0] * y_t + cf[:, 1] * e.clamp(-1, 1)).clamp(-1, 1)
+    else:
+        y0_hat = (cf[:, 0] * y_t - cf[:, 1] * e).clamp(-1, 1)
+        y = cf[:, 2] * y0_hat + cf[:, 3] * y_t
+        if noise is not None:
+            y = y + noise * cf[:, 4]
+    m = _mask01(mask)
+    if m is not None:
+        m = m.reshape(b, 1, h, w)
+        y = y_0 * (1.0 - m) + m * y
+    x_next = None
+    if want_next_input:
+        x_next = torch.zeros((b, h, w, ld), dtype=BF)
+        x_next[..., :c] = y_cond.permute(0, 2, 3, 1).to(BF)
+        x_next[..., c:2 * c] = y.permute(0, 2, 3, 1).to(BF)
+    return y.contiguous(), x_next
+
+
 _DOUBLES = dict(pack_conv_weight=pack_conv_weight, conv2d_fwd=conv2d_fwd, chan_stats=chan_stats,
                 conv2d_cropped=conv2d_cropped, conv2d_wgrad=conv2d_wgrad, conv2d_wgrad_acc=conv2d_wgrad_acc,
                 bias_grad=bias_grad, nchw_to_nhwc=nchw_to_nhwc, nhwc_to_nchw=nhwc_to_nchw, copy_channels=copy_channels,
@@ -589,7 +758,10 @@ _DOUBLES = dict(pack_conv_weight=pack_conv_weight, conv2d_fwd=conv2d_fwd, chan_s
                 linear_batched_fwd=linear_batched_fwd, linear_batched_bwd=linear_batched_bwd, noise_pack=noise_pack,
                 palette_loss_fwd=palette_loss_fwd, palette_loss_bwd=palette_loss_bwd, adamw_ema_step=adamw_ema_step,
                 pad2d=pad2d, pad2d_bwd=pad2d_bwd, dilate2x=dilate2x, undilate2x=undilate2x, act_bwd=act_bwd,
-                gan_loss_fwd=gan_loss_fwd, gan_loss_bwd=gan_loss_bwd)
+                gan_loss_fwd=gan_loss_fwd, gan_loss_bwd=gan_loss_bwd, layernorm_fwd=layernorm_fwd,
+                layernorm_bwd=layernorm_bwd, temporal_attn_fwd=temporal_attn_fwd, temporal_attn_bwd=temporal_attn_bwd,
+                geglu_fwd=geglu_fwd, geglu_bwd=geglu_bwd, embed_rows=embed_rows, embed_rows_bwd=embed_rows_bwd,
+                ddpm_step=ddpm_step)
 
 
 def _refuse(name):

@@ -315,3 +315,83 @@ def test_reference_cut_model_trains_with_accelerated_nets(golden_dir, nce):
     for k, (_, n) in gold["stats_D"].items():
         if not k.endswith(".bias"):
             assert abs(float(model.netD_B_basic.state_dict()[k].double().norm()) - n) <= 2e-2 * n, k
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# INTEGRATION.md section 2 under DistributedDataParallel (what BaseModel.parallelize builds, base_model.py:725-737) with
+# gradient accumulation (train_iter_size = 2: the first micro-step under no_sync, base_model.py:1313-1315), two gloo
+# ranks on the CPU through the double.  Pins that EVERY parameter gradient of the B200 modules reaches
+# autograd's AccumulateGrad — on the first and on the second micro-step, when .grad already exists — so the reducer
+# hooks fire for the convolution weights too.  (tests/test_gpu_multi.py runs the same on the real kernels.)
+# ---------------------------------------------------------------------------------------------------------------------
+_DDP_CFG = dict(image_size=32, inner_channel=32, channel_mults=(1, 2), res_blocks=(1, 1), attn_res=(2,),
+                num_head_channels=16)
+
+
+def _ddp_double_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from joligen_b200 import nets
+    from oracle import palette_oracle as O
+    cfg = O.UNetCfg(**_DDP_CFG)
+
+    def make():
+        net = nets.build_palette_generator(**_DDP_CFG)
+        net.load_state_dict(O.init_params(cfg, 50), strict=False)
+        return net
+
+    def draw(seed):
+        data = O.synthetic_batch(2, cfg.image_size, seed)
+        torch.manual_seed(seed + 7)
+        t, u = O.sample_t_gamma(cfg, 2)
+        return data, torch.randn_like(data["gt"]), t, u
+
+    def loss_of(model, d):
+        data, noise, t, u = d
+        _, noise_hat, _ = model(data["gt"], data["cond"], data["mask"], noise, t=t, u=u)
+        return torch.nn.functional.mse_loss(noise_hat, noise)
+
+    draws = {(r, m): draw(5000 + 10 * r + m) for r in range(world) for m in range(2)}
+    with KD.installed():
+        ddp = DDP(make())
+        with ddp.no_sync():
+            (loss_of(ddp, draws[(rank, 0)]) / 2).backward()
+        (loss_of(ddp, draws[(rank, 1)]) / 2).backward()
+        got = {k: p.grad.detach().clone() for k, p in ddp.module.named_parameters() if p.grad is not None}
+        res = {"n_grads": len(got), "n_params": sum(1 for _ in ddp.module.parameters())}
+        if rank == 0:
+            solo = make()
+            for r in range(world):
+                for m in range(2):
+                    (loss_of(solo, draws[(r, m)]) / (2 * world)).backward()
+            worst, worst_k = 0.0, None
+            for k, p in solo.named_parameters():
+                ref = p.grad.detach().double()
+                e = float((got[k].double() - ref).norm() / (ref.norm() + 1e-12))
+                if e > worst and float(ref.norm()) > 1e-6:
+                    worst, worst_k = e, k
+            res["worst"], res["worst_k"] = worst, worst_k
+    out[rank] = res
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ddp_wrapped_modules_with_gradient_accumulation_on_the_double():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_ddp_double_worker, args=(2, port, out), nprocs=2, join=True)
+    a, b = out[0], out[1]
+    assert a["n_grads"] == a["n_params"] == b["n_grads"]
+    # DDP's mean over ranks of the accumulated micro-step gradients == the plain sum / (2 * world) on one model; a
+    # parameter whose gradient skipped the reducer would hold its rank-local value (different data: error ~ 1)
+    assert a["worst"] < 1e-3, (a["worst_k"], a["worst"])
