@@ -71,7 +71,9 @@ def oracle_forward(which, cfg, data, noise, t, u):
                                               unet=R.denoiser(data["ref_A"]))
 
 
-def run(which):
+def create_reference_model(which):
+    """options -> create_model -> setup of the reference's palette_model for cfg 4 ("ref") / cfg 5 ("vid") on CPU, seeded
+    weights loaded -> (model, opt, shapes, params, wseed)"""
     import train as ref_train
     from models import create_model
     from options.train_options import TrainOptions
@@ -111,6 +113,11 @@ def run(which):
     params = init_params_from_shapes(shapes, wseed)
     missing, unexpected = model.netG_A.load_state_dict(params, strict=False)
     assert not unexpected
+    return model, opt, shapes, params, wseed
+
+
+def run(which):
+    model, opt, shapes, params, wseed = create_reference_model(which)
     cfg = oracle_cfg(which)
     cfg.n_timestep_train, cfg.n_timestep_test = opt.G_diff_n_timestep_train, opt.G_diff_n_timestep_test
     losses = []

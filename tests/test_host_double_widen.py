@@ -175,3 +175,38 @@ def test_video_unet_on_the_double(golden_dir):
     floor = rel_l2(yo, gold["y"])
     assert rel_l2(y, gold["y"]) < max(3e-2, 2 * floor) and rel_l2(y, yo) < max(3e-2, 2 * floor)
     _check_unet_grads(dict(net.named_parameters()), leaves, gold)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("which", ["ref", "vid"])
+def test_reference_palette_model_cfg4_cfg5_trains_with_accelerated_generator(golden_dir, which):
+    """The unmodified reference's control path for BASELINE config 4 (unet_mha_ref_attn with ref_A) and config 5
+    (unet_vid, 3-frame clips) with `accelerate(netG_A)`: two optimize_parameters() vs the reference's own
+    (refattn_plumbing.pt / vid_plumbing.pt), seeded identically (the video noise is drawn on the folded clip)."""
+    from oracle import ref_stubs
+    ref_stubs.install()
+    from oracle import gen_golden_plumbing45 as P
+    import joligen_b200
+    from joligen_b200 import nets, nets_ref, nets_vid
+    gold = torch.load(os.path.join(golden_dir, "vid_plumbing.pt" if which == "vid" else "refattn_plumbing.pt"))
+    model, _, _, _, _ = P.create_reference_model(which)
+    ref_params = dict(model.netG_A.named_parameters())
+    model.netG_A = joligen_b200.accelerate(model.netG_A)
+    assert isinstance(model.netG_A, nets.DiffusionGenerator)
+    assert isinstance(model.netG_A.denoise_fn.model, nets_vid.UNetVid if which == "vid" else nets_ref.UNetGeneratorRefAttn)
+    assert all(p is ref_params[k] for k, p in model.netG_A.named_parameters())
+    losses = []
+    with KD.installed():
+        for step in range(2):
+            data = P.batch(which, gold["data_seeds"][step])
+            model.set_input(dict(data, A_img_paths=["a"] * P.BATCH, B_label_cls=torch.zeros(P.BATCH, dtype=torch.long)))
+            torch.manual_seed(gold["rng_seeds"][step])
+            model.optimize_parameters()
+            losses.append(float(model.loss_G_tot.detach()))
+    for got, want in zip(losses, gold["losses"]):
+        assert abs(got - want) < 3e-2 * abs(want), (losses, gold["losses"])
+    sd, ema = model.netG_A.state_dict(), model.netG_A_ema.state_dict()
+    for k, (_, n) in gold["param_stats"].items():
+        assert abs(float(sd[k].double().norm()) - n) <= 2e-2 * n + 1e-6, k
+    for k, (_, n) in gold["ema_stats"].items():
+        assert abs(float(ema[k].double().norm()) - n) <= 2e-2 * n + 1e-6, k
