@@ -32,6 +32,15 @@ def invalidate_packed_weights():
     _PACK_EPOCH[0] += 1
 
 
+# The batched pack / staged wgrad tables hold raw DEVICE pointers: only CUDA weights take part.  (Cleared only by the
+# kernel test double of tests/, which follows the same pointers in host memory.)
+_DEVICE_WEIGHTS_ONLY = [True]
+
+
+def on_device(w):
+    return w.is_cuda or not _DEVICE_WEIGHTS_ONLY[0]
+
+
 class ConvPack:
     """bf16 implicit-GEMM copies of one conv's fp32 master weight, refreshed when the weight changes.
     A trainer may take over (`managed`): it owns persistent packed buffers and refreshes ALL convolutions of the
@@ -109,7 +118,7 @@ class WeightPackSet:
     persistent; call refresh() after the master weights changed (the trainer does, after every optimizer step)."""
 
     def __init__(self, module):
-        self.packs = [p for p in conv_packs(module) if p.conv.weight.is_cuda]
+        self.packs = [p for p in conv_packs(module) if on_device(p.conv.weight)]
         items, dims = [], []
         for p in self.packs:
             w4 = p._weight4()

@@ -90,7 +90,7 @@ class WgradStage:
             w = pack.conv.weight
             w4 = pack._weight4()
             cout, cin, r, s = w4.shape
-            if cout % 8 or cin % 8 or not w.is_cuda:
+            if cout % 8 or cin % 8 or not nets.on_device(w):
                 continue  # padded channels: Conv2dFn uses its immediate path for these
             slots.append((w, (cout, cin, r * s), total))
             total += (w.numel() + 63) // 64 * 64

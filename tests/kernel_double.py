@@ -516,6 +516,16 @@ def palette_loss_bwd(noise, noise_hat, mask, w_b, grad_out, lambda_g=1.0, l1=Fal
 
 def adamw_ema_step(p, g, m, v, ema, lr, beta1, beta2, eps, weight_decay, adamw, step, grad_scale=1.0, ema_beta=0.999,
                    ema_init=False, step_dev=None):
+    import contextlib as _cl
+    with _cl.ExitStack() as st:
+        for t in (p, m, v, ema, step_dev):
+            if t is not None:
+                st.enter_context(_raw(t))
+        _adamw(p, g, m, v, ema, lr, beta1, beta2, eps, weight_decay, adamw, step, grad_scale, ema_beta, ema_init,
+               step_dev)
+
+
+def _adamw(p, g, m, v, ema, lr, beta1, beta2, eps, weight_decay, adamw, step, grad_scale, ema_beta, ema_init, step_dev):
     if step_dev is not None:
         step_dev.add_(1)
         step = int(step_dev.reshape(-1)[0])
@@ -750,6 +760,52 @@ def ddpm_step(eps, y_t, y_cond, y_0, mask, noise, coef, ld=8, want_next_input=Tr
     return y.contiguous(), x_next
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# trainer-side batched weight kernels: the item tables hold RAW POINTERS (here: host addresses) — follow them
+# ---------------------------------------------------------------------------------------------------------------------
+def _at(ptr, shape, dtype):
+    """the tensor living at a raw address (what a kernel sees of a jg_pack_item / jg_unpack_item field)"""
+    import ctypes
+    n = 1
+    for v in shape:
+        n *= v
+    buf = (ctypes.c_char * (n * torch.empty((), dtype=dtype).element_size())).from_address(ptr)
+    return torch.frombuffer(buf, dtype=dtype).view(shape)
+
+
+class WeightTable:
+    """kernels.WeightTable without the device copy: keeps the ctypes items (jg_pack_item / jg_unpack_item)."""
+
+    def __init__(self, items, dims, device):
+        self.structs = list(items)
+        self.n = len(items)
+        self.total_tiles = sum(L.load().jg_weight_tiles(cout, cin, rs) for cout, cin, rs in dims)
+
+
+def pack_conv_weights_batched(table):
+    for it in table.structs:
+        w = _at(it.w, (it.Cout, it.Cin, it.RS), torch.float32)
+        wf = _at(it.wf, (it.Cout8, it.RS, it.Cin8), BF)
+        wf[:it.Cout, :, :it.Cin] = w.permute(0, 2, 1).to(BF)
+        if it.wd:
+            wd = _at(it.wd, (it.Cin8, it.RS, it.Cout8), BF)
+            wd[:it.Cin, :, :it.Cout] = w.permute(1, 2, 0).flip(1).to(BF)
+
+
+def wgrad_unpack_batched(table):
+    """dw_oihw += acc (permuted from its layout), then acc = 0"""
+    for it in table.structs:
+        dw = _at(it.dw, (it.Cout, it.Cin, it.RS), torch.float32)
+        if it.layout == 1:
+            acc = _at(it.acc, (it.Cout, it.RS, it.Cin), torch.float32)
+            dw += acc.permute(0, 2, 1)
+        else:
+            acc = _at(it.acc, (it.RS, it.Cin, it.Cout), torch.float32)
+            dw += acc.permute(2, 1, 0)
+        acc.zero_()
+
+
 _DOUBLES = dict(pack_conv_weight=pack_conv_weight, conv2d_fwd=conv2d_fwd, chan_stats=chan_stats,
                 conv2d_cropped=conv2d_cropped, conv2d_wgrad=conv2d_wgrad, conv2d_wgrad_acc=conv2d_wgrad_acc,
                 bias_grad=bias_grad, nchw_to_nhwc=nchw_to_nhwc, nhwc_to_nchw=nhwc_to_nchw, copy_channels=copy_channels,
@@ -761,7 +817,8 @@ _DOUBLES = dict(pack_conv_weight=pack_conv_weight, conv2d_fwd=conv2d_fwd, chan_s
                 gan_loss_fwd=gan_loss_fwd, gan_loss_bwd=gan_loss_bwd, layernorm_fwd=layernorm_fwd,
                 layernorm_bwd=layernorm_bwd, temporal_attn_fwd=temporal_attn_fwd, temporal_attn_bwd=temporal_attn_bwd,
                 geglu_fwd=geglu_fwd, geglu_bwd=geglu_bwd, embed_rows=embed_rows, embed_rows_bwd=embed_rows_bwd,
-                ddpm_step=ddpm_step)
+                ddpm_step=ddpm_step, WeightTable=WeightTable, pack_conv_weights_batched=pack_conv_weights_batched,
+                wgrad_unpack_batched=wgrad_unpack_batched)
 
 
 def _refuse(name):
@@ -775,7 +832,9 @@ def _refuse(name):
 def installed():
     """Swap every public callable of joligen_b200.kernels: the restated ones by their doubles, the rest by a refusal
     (so that nothing can reach the CUDA library by accident)."""
+    from joligen_b200 import nets
     saved = {}
+    device_only, nets._DEVICE_WEIGHTS_ONLY[0] = nets._DEVICE_WEIGHTS_ONLY[0], False
     keep = {"conv_out_size", "make_conv_desc", "_ld", "_device_table", "_mask_ptrs"}
     for name, obj in list(vars(K).items()):
         if name.startswith("__") or name in keep or not (callable(obj)) or getattr(obj, "__module__", "") != K.__name__:
@@ -785,5 +844,6 @@ def installed():
     try:
         yield
     finally:
+        nets._DEVICE_WEIGHTS_ONLY[0] = device_only
         for name, obj in saved.items():
             setattr(K, name, obj)
