@@ -334,6 +334,7 @@ def build_workload(args, rank, world):
                                                     motion_num_heads=8, motion_num_layers=2))
         synthetic.dezero_init_(net, 5)
         tr = B2BTrainer(net, lr=1e-4, beta1=0.9, beta2=0.95, ema=True, ema_beta=0.999, cuda_graph=graph, graph_warmup=2)
+        tr.broadcast_parameters()
         g = torch.Generator().manual_seed(1234 + rank)
         gt = (0.5 * torch.randn(B, frames, 3, h, w, generator=g)).clamp(-1, 1)
         mask = (torch.rand(B, frames, 1, h, w, generator=g) > 0.6).float()

@@ -5,6 +5,7 @@ flat fp32 buffers.  Mirrors the reference's quirk that `set_requires_grad` makes
 trainable (pinned by tests/golden/b2b_plumbing.pt)."""
 import torch
 
+from . import dp
 from . import kernels as K
 from . import nets
 from .trainer import FlatParams
@@ -13,7 +14,7 @@ from .trainer import FlatParams
 class B2BTrainer:
     def __init__(self, net, lr=1e-4, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.0, optim="adamw", ema=True,
                  ema_beta=0.999, lambda_G=1.0, use_cond=False, device="cuda", train_pos_embed=True, cuda_graph=False,
-                 graph_warmup=2):
+                 graph_warmup=2, process_group=None):
         if not torch.cuda.is_available():
             raise RuntimeError("B2BTrainer needs a CUDA device (the B200 kernels have no CPU fallback)")
         if optim not in ("adamw", "adam"):
@@ -23,6 +24,12 @@ class B2BTrainer:
         if train_pos_embed:
             self.net.b2b_model.pos_embed.requires_grad_(True)
         self.flat = FlatParams(self.net)
+        # data parallel (DDP's mean gradient, base_model.py:725-737): the flat gradient is summed over the ranks on the
+        # library's communicator (dp.Comm: NCCL on its own stream, capturable; torch.distributed on the CPU) and 1/world
+        # is folded into the optimizer kernel.  One clip's gradient is 0.6 GB of fp32 for JiTVid-B/16: one exchange.
+        self.pg = process_group
+        self.world = dp.world_size(process_group)
+        self.comm = dp.Comm(process_group, self.device)
         self.exp_avg = torch.zeros_like(self.flat.data)
         self.exp_avg_sq = torch.zeros_like(self.flat.data)
         self.ema = torch.zeros_like(self.flat.data) if ema else None
@@ -41,6 +48,11 @@ class B2BTrainer:
         self._eager_steps = 0
         self._static = None
         self.launches_per_step = 0
+
+    def broadcast_parameters(self):
+        """rank 0's weights everywhere (what DistributedDataParallel does at construction)"""
+        self.comm.broadcast(self.flat.data, root=0)
+        nets.invalidate_packed_weights()
 
     def set_input(self, data):
         """data["B"] clip [B, F, 3, H, W], data["B_label_mask"] [B, F, 1, H, W], data["A"] the conditioning clip."""
@@ -61,10 +73,13 @@ class B2BTrainer:
         self.flat.rebind_grads()
         loss = self.net.forward_loss(self.gt, self.mask, self.cond, self.label, t_base=t_base, e=e, lambda_G=self.lambda_G)
         loss.backward()
+        if self.world > 1:
+            self.comm.allreduce_async(self.flat.grad)
+            self.comm.wait()
         self.step += 1
         K.adamw_ema_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.ema, step=self.step,
-                         step_dev=self.step_dev, grad_scale=1.0, ema_beta=self.ema_beta, ema_init=not self.ema_started,
-                         **self.hp)
+                         step_dev=self.step_dev, grad_scale=1.0 / self.world, ema_beta=self.ema_beta,
+                         ema_init=not self.ema_started, **self.hp)
         self.ema_started = True
         self.flat.grad.zero_()
         nets.invalidate_packed_weights()   # the fused optimizer wrote the masters through raw pointers

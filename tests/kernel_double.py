@@ -806,6 +806,66 @@ def wgrad_unpack_batched(table):
         acc.zero_()
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# b2b video backbone (csrc/jit.cu): ops_jit.py calls the C ABI directly, so these doubles stand in for its public
+# functions (differentiable torch expressions, bf16 where the kernels store bf16); nets_jit / trainer_b2b are what runs.
+# ---------------------------------------------------------------------------------------------------------------------
+def _j_rmsnorm_mod(x, w, shift=None, scale=None, eps=1e-6):
+    xf = x.float()
+    y = w * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps))
+    if scale is not None:
+        n, c = x.shape[0], x.shape[-1]
+        assert tuple(scale.shape) == (n, c) and tuple(shift.shape) == (n, c) and scale.dtype == torch.float32
+        y = y * (1.0 + scale[:, None, None, :]) + shift[:, None, None, :]
+    return y.to(BF)
+
+
+def _rotate_half(x):
+    x1, x2 = x.reshape(*x.shape[:-1], -1, 2).unbind(dim=-1)
+    return torch.stack((-x2, x1), dim=-1).reshape(x.shape)
+
+
+def _j_qknorm_rope(qkv, wq, wk, cos, sin, heads, eps=1e-6):
+    n, t, _, c3 = qkv.shape
+    d = c3 // 3
+    hd = d // heads
+    assert tuple(cos.shape) == (t, hd) and tuple(sin.shape) == (t, hd), (cos.shape, (t, hd))
+    out = []
+    for part, w in ((qkv[..., :d], wq), (qkv[..., d:2 * d], wk)):
+        z = part.float().reshape(n, t, heads, hd)
+        z = w * (z * torch.rsqrt(z.pow(2).mean(-1, keepdim=True) + eps))
+        z = z * cos[None, :, None, :] + _rotate_half(z) * sin[None, :, None, :]
+        out.append(z.reshape(n, t, 1, d))
+    return torch.cat(out, dim=-1).to(BF)
+
+
+def _j_attn_small(qk, qkv, heads):
+    n, t, _, d2 = qk.shape
+    d = d2 // 2
+    hd = d // heads
+    q = qk[..., :d].float().reshape(n, t, heads, hd)
+    k = qk[..., d:].float().reshape(n, t, heads, hd)
+    v = qkv[..., 2 * d:].float().reshape(n, t, heads, hd)
+    p = torch.softmax(torch.einsum("nthc,nshc->nhts", q, k) / (hd ** 0.5), dim=-1)
+    return torch.einsum("nhts,nshc->nthc", p, v).reshape(n, t, 1, d).to(BF)
+
+
+def _j_swiglu(x):
+    h = x.shape[-1] // 2
+    return (F.silu(x[..., :h].float()) * x[..., h:].float()).to(BF)
+
+
+def _j_gated_residual(x, y, gate):
+    n, c = x.shape[0], x.shape[-1]
+    assert tuple(gate.shape) == (n, c) and gate.dtype == torch.float32
+    return (x.float() + gate[:, None, None, :] * y.float()).to(BF)
+
+
+_JIT_DOUBLES = dict(rmsnorm_mod=_j_rmsnorm_mod, qknorm_rope=_j_qknorm_rope, attn_small=_j_attn_small, swiglu=_j_swiglu,
+                    gated_residual=_j_gated_residual)
+
+
 _DOUBLES = dict(pack_conv_weight=pack_conv_weight, conv2d_fwd=conv2d_fwd, chan_stats=chan_stats,
                 conv2d_cropped=conv2d_cropped, conv2d_wgrad=conv2d_wgrad, conv2d_wgrad_acc=conv2d_wgrad_acc,
                 bias_grad=bias_grad, nchw_to_nhwc=nchw_to_nhwc, nhwc_to_nchw=nhwc_to_nchw, copy_channels=copy_channels,
@@ -841,9 +901,15 @@ def installed():
             continue
         saved[name] = obj
         setattr(K, name, _DOUBLES.get(name, _refuse(name)))
+    from joligen_b200 import ops_jit
+    saved_jit = {name: getattr(ops_jit, name) for name in _JIT_DOUBLES}
+    for name, fn in _JIT_DOUBLES.items():
+        setattr(ops_jit, name, fn)
     try:
         yield
     finally:
         nets._DEVICE_WEIGHTS_ONLY[0] = device_only
         for name, obj in saved.items():
             setattr(K, name, obj)
+        for name, obj in saved_jit.items():
+            setattr(ops_jit, name, obj)
