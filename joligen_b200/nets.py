@@ -266,8 +266,6 @@ class ResBlock(EmbedBlock):
         self.up, self.down = up, down
         self.updown = up or down
         self.efficient = efficient
-        if efficient and up:
-            raise NotImplementedError("B200 ResBlock: efficient up-blocks are not supported")
         self.in_layers = nn.Sequential(normalization(channels, norm), nn.SiLU(),
                                        nn.Conv2d(channels, self.out_channel, 3, padding=1))
         if up or down:
@@ -294,10 +292,17 @@ class ResBlock(EmbedBlock):
             h, x, tap2 = self.in_layers[0].forward_tap2_nhwc(x, act=L.ACT_SILU)
         else:
             h, x = self.in_layers[0].forward_tap_nhwc(x, act=L.ACT_SILU)
-        if self.updown:
+        if self.updown and self.efficient and self.up:
+            # (:239-242) --G_unet_mha_vit_efficient: convolve at the low resolution, upsample afterwards (the
+            # statistics of the upsampled tensor are taken by the GroupNorm's own pass)
+            h = _conv(h, self.in_layers[2], self._pack_in)
             h = self.h_upd.forward_nhwc(h)
             x = self.x_upd.forward_nhwc(x)
-        h = _conv(h, self.in_layers[2], self._pack_in, want_stats=True)
+        else:
+            if self.updown:
+                h = self.h_upd.forward_nhwc(h)
+                x = self.x_upd.forward_nhwc(x)
+            h = _conv(h, self.in_layers[2], self._pack_in, want_stats=True)
         lin = self.emb_layers[1]
         emb_out, self._film_pre = self._film_pre, None  # computed for all blocks at once by the UNet (EmbBank)
         if emb_out is None:

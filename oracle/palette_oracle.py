@@ -275,13 +275,19 @@ def res_block(sd, name, x, emb, b: BlockSpec, cfg: UNetCfg):
     """ResBlock._forward, unet_generator_attn.py:233-266."""
     h = _r(F.silu(group_norm(x, sd[name + ".in_layers.0.norm.weight"], sd[name + ".in_layers.0.norm.bias"],
                              cfg.group_norm_size)))
-    if b.up:
+    if b.up and cfg.efficient:
+        # (:239-242) efficient up-blocks convolve at the low resolution and upsample afterwards
+        h = _r(_conv2d(h, sd[name + ".in_layers.2.weight"], sd[name + ".in_layers.2.bias"], padding=1))
         h = F.interpolate(h, scale_factor=2, mode="nearest")
         x = F.interpolate(x, scale_factor=2, mode="nearest")
-    elif b.down:
-        h = _r(F.avg_pool2d(h, 2, 2))
-        x = _r(F.avg_pool2d(x, 2, 2))
-    h = _r(_conv2d(h, sd[name + ".in_layers.2.weight"], sd[name + ".in_layers.2.bias"], padding=1))
+    else:
+        if b.up:
+            h = F.interpolate(h, scale_factor=2, mode="nearest")
+            x = F.interpolate(x, scale_factor=2, mode="nearest")
+        elif b.down:
+            h = _r(F.avg_pool2d(h, 2, 2))
+            x = _r(F.avg_pool2d(x, 2, 2))
+        h = _r(_conv2d(h, sd[name + ".in_layers.2.weight"], sd[name + ".in_layers.2.bias"], padding=1))
     emb_out = F.linear(F.silu(emb), sd[name + ".emb_layers.1.weight"], sd[name + ".emb_layers.1.bias"])
     emb_out = emb_out[:, :, None, None]
     gn_w, gn_b = sd[name + ".out_layers.0.norm.weight"], sd[name + ".out_layers.0.norm.bias"]

@@ -395,3 +395,81 @@ def test_ddp_wrapped_modules_with_gradient_accumulation_on_the_double():
     # DDP's mean over ranks of the accumulated micro-step gradients == the plain sum / (2 * world) on one model; a
     # parameter whose gradient skipped the reducer would hold its rank-local value (different data: error ~ 1)
     assert a["worst"] < 1e-3, (a["worst_k"], a["worst"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# --G_unet_mha_vit_efficient (efficient=True: skip weight 1/sqrt(2), up-blocks convolve BEFORE upsampling) and the
+# non-FiLM ResBlock: the oracle vs the reference directly, the host stack vs the oracle and vs the reference
+# ---------------------------------------------------------------------------------------------------------------------
+_VARIANT_BASE = dict(image_size=32, inner_channel=32, channel_mults=(1, 2), res_blocks=(1, 1), attn_res=(2,),
+                     num_head_channels=16)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("variant", [dict(efficient=True), dict(use_scale_shift_norm=False)])
+def test_unet_variants_oracle_host_stack_and_reference_agree(variant):
+    from oracle import ref_stubs
+    ref_stubs.install()
+    from oracle import palette_oracle as O
+    from models.modules.diffusion_generator import DiffusionGenerator
+    from models.modules.palette_denoise_fn import PaletteDenoiseFn
+    from models.modules.unet_generator_attn.unet_generator_attn import UNet
+    import joligen_b200
+    cfg = O.UNetCfg(**_VARIANT_BASE, **variant)
+    params = O.init_params(cfg, 5)
+    unet = UNet(image_size=cfg.image_size, in_channel=cfg.in_channel, inner_channel=cfg.inner_channel,
+                out_channel=cfg.out_channel, res_blocks=list(cfg.res_blocks), attn_res=list(cfg.attn_res), tanh=False,
+                n_timestep_train=cfg.n_timestep_train, n_timestep_test=cfg.n_timestep_test, norm="groupnorm",
+                group_norm_size=cfg.group_norm_size, cond_embed_dim=cfg.cond_embed_dim, channel_mults=cfg.channel_mults,
+                num_heads=cfg.num_heads, num_head_channels=cfg.num_head_channels, efficient=cfg.efficient,
+                use_scale_shift_norm=cfg.use_scale_shift_norm)
+    ref = DiffusionGenerator(denoise_fn=PaletteDenoiseFn(model=unet, cond_embed_dim=cfg.cond_embed_dim, ref_embed_net="",
+                                                         conditioning="", nclasses=2),
+                             sampling_method="ddpm", image_size=cfg.image_size, G_ngf=cfg.inner_channel,
+                             loading_backward_compatibility=False)
+    assert [(k, tuple(v.shape)) for k, v in ref.named_parameters()] == list(O.generator_param_shapes(cfg).items())
+    ref.load_state_dict(params, strict=False)
+    data = O.synthetic_batch(2, cfg.image_size, 9)
+    torch.manual_seed(1)
+    t, u = O.sample_t_gamma(cfg, 2)
+    noise = torch.randn_like(data["gt"])
+    # the reference itself, with the same draws (its forward draws t, u; replay them through the generator's RNG order)
+    torch.manual_seed(1)
+    noise_r, nh_r, _ = ref(data["gt"], data["cond"], data["mask"], None, None, None)
+    assert torch.equal(noise_r, noise)
+    torch.nn.functional.mse_loss(noise_r * data["mask"].clamp(0, 1), nh_r * data["mask"].clamp(0, 1)).backward()
+    # (1) the oracle restates the reference (fp32)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    _, nh_o, _ = O.diffusion_forward(leaves, data["gt"], data["cond"], data["mask"], noise, t, u, cfg)
+    assert rel_l2(nh_o, nh_r) < 1e-4
+    O.palette_loss(noise, nh_o, data["mask"]).backward()
+    for k, p in ref.named_parameters():
+        assert rel_l2(leaves[k].grad, p.grad) < 1e-3 or float(p.grad.norm()) < 1e-6, k
+    # (2) the accelerated reference net on the double, seeded the same way, at the bf16 floor of THIS net (measured: the
+    # oracle with the CUDA path's rounding points vs fp32; the 1/sqrt(2) skip weight makes the efficient variant noisier)
+    emu = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    O.EMULATE_BF16[0] = True
+    try:
+        _, nh_e, _ = O.diffusion_forward(emu, data["gt"], data["cond"], data["mask"], noise, t, u, cfg)
+        O.palette_loss(noise, nh_e, data["mask"]).backward()
+    finally:
+        O.EMULATE_BF16[0] = False
+    floor = rel_l2(nh_e, nh_r)
+    gerr = gnrm = 0.0
+    for k, q in ref.named_parameters():
+        gerr += float((emu[k].grad.double() - q.grad.double()).norm()) ** 2
+        gnrm += float(q.grad.double().norm()) ** 2
+    gfloor = (gerr / gnrm) ** 0.5
+    import copy
+    fast = joligen_b200.accelerate(copy.deepcopy(ref))
+    fast.zero_grad()
+    with KD.installed():
+        torch.manual_seed(1)
+        noise_f, nh_f, _ = fast(data["gt"], data["cond"], data["mask"], None, None, None)
+        assert torch.equal(noise_f, noise) and rel_l2(nh_f, nh_r) < max(3e-2, 1.5 * floor), (rel_l2(nh_f, nh_r), floor)
+        torch.nn.functional.mse_loss(noise_f * data["mask"].clamp(0, 1), nh_f * data["mask"].clamp(0, 1)).backward()
+    err = nrm = 0.0
+    for (k, p), (_, q) in zip(fast.named_parameters(), ref.named_parameters()):
+        err += float((p.grad.double() - q.grad.double()).norm()) ** 2
+        nrm += float(q.grad.double().norm()) ** 2
+    assert (err / nrm) ** 0.5 < max(4e-2, 1.5 * gfloor), ((err / nrm) ** 0.5, gfloor)
