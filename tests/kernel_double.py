@@ -862,6 +862,68 @@ def _j_gated_residual(x, y, gate):
     return (x.float() + gate[:, None, None, :] * y.float()).to(BF)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# CUT contrastive path (csrc/nce.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+def gather_rows(feat, ids):
+    _check_rows(feat)
+    b, h, w, c = feat.shape
+    assert ids.dtype == torch.int64 and ids.dim() == 1
+    return feat.reshape(b, h * w, c)[:, ids].reshape(b * ids.numel(), c).contiguous()
+
+
+def gather_rows_bwd(d_out, ids, shape):
+    b, h, w, c = shape
+    d = torch.zeros((b, h * w, c), dtype=BF)
+    d[:, ids] = d_out.reshape(b, ids.numel(), c).to(BF)   # the positions are distinct
+    return d.reshape(b, h, w, c)
+
+
+def l2norm_fwd(x, eps=1e-7):
+    assert x.dtype == BF and x.dim() == 2
+    xf = x.float()
+    norms = xf.norm(dim=1)
+    return xf / norms.clamp_min(eps)[:, None], norms
+
+
+def l2norm_bwd(y, dy, norms, eps=1e-7):
+    return ((dy - y * (y * dy).sum(1, keepdim=True)) / norms.clamp_min(eps)[:, None]).to(BF)
+
+
+def _nce(q, k, groups, temperature, kind, num_patches_opt=256):
+    """oracle/cut_oracle.patch_nce_loss restates PatchNCELoss / MoNCELoss (pinned on the reference's cut_plumbing*.pt)"""
+    from oracle import cut_oracle as C
+    return C.patch_nce_loss(q, k, groups, T=temperature, all_negatives_from_minibatch=False, kind=kind,
+                            num_patches_opt=num_patches_opt)
+
+
+def patch_nce_fwd(q, k, groups, temperature):
+    loss = _nce(q, k, groups, temperature, "patchnce")
+    return loss, torch.zeros_like(loss)
+
+
+def _nce_bwd(q, k, grad_loss, groups, temperature, kind, num_patches_opt, need_dq, need_dk):
+    q, k = q.detach().requires_grad_(True), k.detach().requires_grad_(True)
+    with torch.enable_grad():
+        loss = _nce(q, k, groups, temperature, kind, num_patches_opt)
+    dq, dk = torch.autograd.grad(loss, [q, k], grad_loss)
+    return (dq if need_dq else None), (dk if need_dk else None)
+
+
+def patch_nce_bwd(q, k, lse, grad_loss, groups, temperature, need_dq=True, need_dk=True):
+    return _nce_bwd(q, k, grad_loss, groups, temperature, "patchnce", 256, need_dq, need_dk)
+
+
+def monce_fwd(q, k, groups, temperature, num_patches_opt, iters=50):
+    assert iters == 50
+    loss = _nce(q, k, groups, temperature, "monce", num_patches_opt)
+    return loss, torch.zeros_like(loss), torch.zeros(1)
+
+
+def monce_bwd(q, k, lse, grad_loss, ws, groups, temperature, num_patches_opt, iters=50, need_dk=True):
+    return _nce_bwd(q, k, grad_loss, groups, temperature, "monce", num_patches_opt, True, need_dk)
+
+
 _JIT_DOUBLES = dict(rmsnorm_mod=_j_rmsnorm_mod, qknorm_rope=_j_qknorm_rope, attn_small=_j_attn_small, swiglu=_j_swiglu,
                     gated_residual=_j_gated_residual)
 
@@ -878,7 +940,9 @@ _DOUBLES = dict(pack_conv_weight=pack_conv_weight, conv2d_fwd=conv2d_fwd, chan_s
                 layernorm_bwd=layernorm_bwd, temporal_attn_fwd=temporal_attn_fwd, temporal_attn_bwd=temporal_attn_bwd,
                 geglu_fwd=geglu_fwd, geglu_bwd=geglu_bwd, embed_rows=embed_rows, embed_rows_bwd=embed_rows_bwd,
                 ddpm_step=ddpm_step, WeightTable=WeightTable, pack_conv_weights_batched=pack_conv_weights_batched,
-                wgrad_unpack_batched=wgrad_unpack_batched)
+                wgrad_unpack_batched=wgrad_unpack_batched, gather_rows=gather_rows, gather_rows_bwd=gather_rows_bwd,
+                l2norm_fwd=l2norm_fwd, l2norm_bwd=l2norm_bwd, patch_nce_fwd=patch_nce_fwd, patch_nce_bwd=patch_nce_bwd,
+                monce_fwd=monce_fwd, monce_bwd=monce_bwd)
 
 
 def _refuse(name):
