@@ -162,8 +162,8 @@ def test_double_refuses_ops_it_does_not_restate():
     from joligen_b200 import kernels as K
     with KD.installed():
         with pytest.raises(AssertionError, match="no CPU restatement"):
-            K.monce_fwd(None, None, 1, 0.07, 256)
-    assert K.monce_fwd.__module__ == "joligen_b200.kernels"  # restored
+            K.haar(torch.zeros(1, 1, 2, 2), 0)
+    assert K.haar.__module__ == "joligen_b200.kernels"  # restored
 
 
 # ---------------------------------------------------------------------------------------------------------------------
