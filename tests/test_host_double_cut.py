@@ -118,3 +118,126 @@ def test_cut_trainer_two_ranks_over_gloo(golden_dir):
     assert a["losses"] != b["losses"]
     for x, y in zip(a["flat"], b["flat"]):
         assert torch.equal(x, y)
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def test_patch_sample_and_nce_on_the_double(golden_dir):
+    """PatchSampleF (gather -> MLP as 1x1 convolutions -> L2 norm) + PatchNCELoss vs the reference's golden vectors:
+    pooled features, total loss, d loss / d query features and the MLP gradients (incl. the part through the keys)."""
+    from types import SimpleNamespace
+    from joligen_b200 import nets_cut
+    from oracle import cut_oracle as C
+    from oracle import palette_oracle as O
+    from oracle.gen_golden_cut import feature_maps
+    from oracle.vid_oracle import init_params_from_shapes
+    gold = torch.load(os.path.join(golden_dir, "cut_nce.pt"))
+    params = init_params_from_shapes(gold["shapes"], gold["wseed"])
+    netF = nets_cut.PatchSampleF(use_mlp=True, nc=gold["nc"])
+    feat_k = list(feature_maps(gold["kseed"]))
+    feat_q = [f.requires_grad_(True) for f in feature_maps(gold["qseed"])]
+    opt = SimpleNamespace(alg_cut_nce_T=gold["T"], alg_cut_nce_includes_all_negatives_from_minibatch=False,
+                          alg_cut_num_patches=gold["num_patches"])
+    with KD.installed():
+        netF.data_dependent_initialize(feat_k)
+        assert [(k, tuple(v.shape)) for k, v in netF.named_parameters()] == [(k, tuple(s)) for k, s in gold["shapes"]]
+        netF.load_state_dict(params)
+        crit = nets_cut.PatchNCELoss(opt)
+        k_pool, ids_out = netF(feat_k, gold["num_patches"], list(gold["ids"]))
+        q_pool, _ = netF(feat_q, gold["num_patches"], ids_out)
+        for mine, ref in zip(k_pool + q_pool, gold["k_pool"] + gold["q_pool"]):
+            assert rel(mine, ref) < 2e-2
+        total = sum((crit(feat_q=fq, feat_k=fk, current_batch=gold["batch"]) * gold["lambda_NCE"]).mean()
+                    for fq, fk in zip(q_pool, k_pool)) / len(q_pool)
+        assert abs(float(total.detach()) - gold["loss"]) < 2e-2 * abs(gold["loss"])
+        total.backward()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    fk = feature_maps(gold["kseed"])
+    fq = [f.requires_grad_(True) for f in feature_maps(gold["qseed"])]
+    O.EMULATE_BF16[0] = True
+    try:
+        kp = C.patch_sample(leaves, fk, gold["num_patches"], gold["ids"])
+        qp = C.patch_sample(leaves, fq, gold["num_patches"], gold["ids"])
+        C.nce_loss_total(qp, kp, gold["batch"], gold["T"], gold["lambda_NCE"]).backward()
+    finally:
+        O.EMULATE_BF16[0] = False
+    for mine, emu, ref in zip(feat_q, fq, gold["dfeat_q"]):
+        assert rel(mine.grad, ref) < max(5e-2, 2.5 * rel(emu.grad, ref)), (rel(mine.grad, ref), rel(emu.grad, ref))
+    named = dict(netF.named_parameters())
+    for k, ref in gold["grads"].items():
+        assert abs(float(named[k].grad.double().norm()) - ref["l2"]) < 5e-2 * ref["l2"] + 1e-6, k
+
+
+def test_multi_scale_d_on_the_double(golden_dir):
+    """nets_projd.MultiScaleD (spectral-norm 4x4 stride-2 convs incl. the power iteration, GroupNorm(c/2) + LeakyReLU,
+    4x4 valid conv) vs the reference's golden: logits, hinge loss, parameter and feature gradients, u / v after."""
+    import torch.nn.functional as F
+    from joligen_b200 import nets_projd
+    from oracle import palette_oracle as O
+    from oracle import projd_oracle as P
+    from oracle.gen_golden_projd import features, seeded_state
+    gold = torch.load(os.path.join(golden_dir, "projd_small.pt"))
+    net = nets_projd.MultiScaleD(channels=gold["channels"], resolutions=gold["resolutions"], conv=True, feats=None,
+                                 num_discs=len(gold["channels"]))
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(s)) for k, s in gold["shapes"]]
+    net.load_state_dict(seeded_state(gold["shapes"], gold["wseed"]))
+    net = net.train()
+    feats = {k: v.requires_grad_(True) for k, v in features(gold["fseed"]).items()}
+    with KD.installed():
+        logits = net(feats)
+        assert logits.shape == gold["logits"].shape and rel(logits, gold["logits"]) < 2e-2
+        loss = F.relu(torch.ones_like(logits) - logits).mean()
+        assert abs(float(loss.detach()) - gold["loss"]) < 2e-2 * abs(gold["loss"])
+        loss.backward()
+    named = dict(net.named_parameters())
+    scale = max(g["l2"] for g in gold["grads"].values())
+    for k, g in gold["grads"].items():
+        assert abs(float(named[k].grad.double().norm()) - g["l2"]) < 5e-2 * max(g["l2"], 1e-2 * scale), k
+    sd0 = seeded_state(gold["shapes"], gold["wseed"])
+    emu_feats = {k: v.requires_grad_(True) for k, v in features(gold["fseed"]).items()}
+    O.EMULATE_BF16[0] = True
+    try:
+        lg = P.multi_scale_d(sd0, emu_feats, gold["channels"], gold["resolutions"], training=True)
+        F.relu(1 - lg).mean().backward()
+    finally:
+        O.EMULATE_BF16[0] = False
+    for k, ref in gold["dfeats"].items():
+        floor = rel(emu_feats[k].grad, ref)
+        assert rel(feats[k].grad, ref) < max(5e-2, 2.5 * floor), (k, rel(feats[k].grad, ref), floor)
+    sd = net.state_dict()
+    for k, ref in gold["uv_after"].items():     # the power iteration is fp32 torch arithmetic: tight
+        assert float((sd[k] - ref).abs().max()) < 1e-5, k
+
+
+def test_gan_trainer_matches_oracle_on_the_double():
+    """trainer_gan.GanTrainer: two optimize_parameters() of the (G) and (D) groups (lsgan, Adam) vs the oracle."""
+    from joligen_b200 import nets_gan
+    from joligen_b200.trainer_gan import GanTrainer
+    from oracle import gan_oracle as G
+    from oracle import palette_oracle as O
+    ngf, nb, ndf = 16, 2, 16
+    gshapes, dshapes = G.resnet_param_shapes(3, 3, ngf, nb), G.nlayer_d_param_shapes(3, ndf, 3)
+    gp, dpar = G.init_from_shapes(gshapes, 41), G.init_from_shapes(dshapes, 42)
+    netG = nets_gan.ResnetGenerator(3, 3, ngf, n_blocks=nb)
+    netD = nets_gan.NLayerDiscriminator(3, ndf, n_layers=3)
+    netG.load_state_dict(gp)
+    netD.load_state_dict(dpar)
+    sG = O.TrainState(params={k: v.clone() for k, v in gp.items()})
+    sD = O.TrainState(params={k: v.clone() for k, v in dpar.items()})
+    ocG = O.OptimCfg(lr=2e-4, kind="adam", ema_beta=0.999)
+    ocD = O.OptimCfg(lr=1e-4, kind="adam", ema_beta=0.999)
+    g = torch.Generator().manual_seed(3)
+    with KD.installed():
+        with mock.patch("torch.cuda.is_available", return_value=True):
+            tr = GanTrainer(netG, netD, gan_mode="lsgan", G_lr=2e-4, D_lr=1e-4, optim="adam", device="cpu")
+        for step in range(2):
+            a = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+            b = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+            tr.set_input({"A": a, "B": b})
+            lg, ld = tr.optimize_parameters()
+            rg, rd = G.gan_train_step(sG, sD, ocG, ocD, a, b, n_blocks=nb)
+            assert abs(float(lg) - float(rg)) < 3e-2 * abs(float(rg)), (step, float(lg), float(rg))
+            assert abs(float(ld) - float(rd)) < 3e-2 * abs(float(rd)), (step, float(ld), float(rd))
