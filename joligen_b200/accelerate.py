@@ -36,6 +36,29 @@ def _adopt(dst: nn.Module, src: nn.Module):
     nets.invalidate_packed_weights()
 
 
+def _adopt_b2b(dst, src):
+    """_adopt for the b2b backbone: the mirror derives the MotionModule's sinusoidal `pe` buffers itself (the reference
+    registers them non-persistently or not at all depending on the version), every Parameter is the reference's."""
+    src_params = dict(src.named_parameters())
+    dst_names = [n for n, _ in dst.named_parameters()]
+    if sorted(dst_names) != sorted(src_params):
+        raise RuntimeError("accelerate: parameter names differ between the reference B2BGenerator and the B200 mirror: "
+                           "%s" % sorted(set(src_params) ^ set(dst_names))[:6])
+    for name in dst_names:
+        mod, leaf = _resolve(dst, name)
+        if mod._parameters[leaf].shape != src_params[name].shape:
+            raise RuntimeError("accelerate: shape mismatch for %s" % name)
+        mod._parameters[leaf] = src_params[name]
+    dst_bufs = dict(dst.named_buffers())
+    for name, buf in src.named_buffers():
+        if name in dst_bufs:
+            if dst_bufs[name].shape != buf.shape:
+                raise RuntimeError("accelerate: buffer shape mismatch for %s" % name)
+            mod, leaf = _resolve(dst, name)
+            mod._buffers[leaf] = buf
+    nets.invalidate_packed_weights()
+
+
 def _resolve(root, name, create=False):
     parts = name.split(".")
     mod = root
@@ -190,6 +213,39 @@ def _nlayer_discriminator_from_reference(ref):
     return new
 
 
+def _b2b_generator_from_reference(ref):
+    """models/modules/b2b_generator.py B2BGenerator around models/modules/vit/vit_vid.py JiTViD (`model_type b2b`,
+    `G_netG vit_vid`): hyper-parameters from the attributes the reference keeps and from its layers."""
+    from . import nets_jit
+    m = ref.b2b_model
+    if type(m).__name__ != "JiTViD":
+        raise NotImplementedError("accelerate: B2BGenerator backbone %s is not on the B200 path" % type(m).__name__)
+    unsupported = [k for k in ("mask_size_conditioning", "temporal_frame_step_conditioning", "global_context_conditioning")
+                   if getattr(m, k, False)]
+    if getattr(m, "num_register_tokens", 0) or getattr(m, "object_ref_num_images", 0) or getattr(m, "motion_every", 0):
+        unsupported.append("register tokens / object references / per-layer motion modules")
+    if unsupported:
+        raise NotImplementedError("accelerate: JiTViD options not on the B200 path: %s" % unsupported)
+    hidden = m.hidden_size
+    ffn = m.blocks[0].mlp.w12.out_features // 2                    # = int(int(hidden * mlp_ratio) * 2 / 3)
+    wide = [h for h in range(int(ffn * 1.5) - 2, int(ffn * 1.5) + 4) if int(h * 2 / 3) == ffn]
+    if not wide:
+        raise NotImplementedError("accelerate: cannot recover JiTViD's mlp_ratio from its SwiGLU width %d" % ffn)
+    mlp_ratio = 4.0 if int(int(hidden * 4.0) * 2 / 3) == ffn else wide[0] / hidden
+    tblocks = m.motion_module.temporal_transformer.transformer_blocks
+    net = nets_jit.JiTViD(input_size=m.input_size, patch_size=m.patch_size, in_channels=m.in_channels,
+                          out_channels=m.out_channels, hidden_size=hidden, depth=len(m.blocks), num_heads=m.num_heads,
+                          mlp_ratio=mlp_ratio, num_classes=m.y_embedder.embedding_table.num_embeddings - 1,
+                          bottleneck_dim=m.x_embedder.proj1.out_channels, in_context_len=m.in_context_len,
+                          in_context_start=m.in_context_start, max_frames=m.max_frames,
+                          motion_num_heads=tblocks[0].attention_blocks[0].heads, motion_num_layers=len(tblocks))
+    return nets_jit.B2BGenerator(net, t_eps=ref.t_eps, noise_scale=ref.noise_scale, P_mean=ref.P_mean, P_std=ref.P_std,
+                                 timestep_uniform_mix_prob=getattr(ref, "timestep_uniform_mix_prob", 0.0),
+                                 label_drop_prob=getattr(ref, "label_drop_prob", 0.0),
+                                 num_classes=getattr(ref, "num_classes", 1),
+                                 denoise_timesteps=getattr(ref, "denoise_timesteps", 50))
+
+
 def accelerate(module: nn.Module) -> nn.Module:
     """Returns the accelerated module (the same object with children swapped, or a new root when the
     root itself is a hot-path class)."""
@@ -230,6 +286,11 @@ def accelerate(module: nn.Module) -> nn.Module:
     if cls == "UNetGeneratorRefAttn" and hasattr(module, "input_blocks_ref"):
         new = _unetref_from_reference(module)
         _adopt(new, module)
+        new.train(module.training)
+        return new
+    if cls == "B2BGenerator" and hasattr(module, "b2b_model"):
+        new = _b2b_generator_from_reference(module)
+        _adopt_b2b(new, module)
         new.train(module.training)
         return new
     if cls == "ResnetGenerator" and hasattr(module, "encoder") and hasattr(module, "decoder"):

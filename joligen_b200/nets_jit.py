@@ -289,36 +289,78 @@ class B2BGenerator(nn.Module):
     (t_base [B], e = randn_like(x)) and the masked pseudo-Huber loss of B2BModel._masked_region_loss
     (/root/reference/models/b2b_model.py:1201-1217, incl. its one-channel-mask broadcast quirk)."""
 
-    def __init__(self, b2b_model, t_eps=0.05, noise_scale=1.0, P_mean=-0.8, P_std=0.8):
+    def __init__(self, b2b_model, t_eps=0.05, noise_scale=1.0, P_mean=-0.8, P_std=0.8, timestep_uniform_mix_prob=0.0,
+                 label_drop_prob=0.0, num_classes=1, denoise_timesteps=50):
         super().__init__()
         self.b2b_model = b2b_model
         self.t_eps, self.noise_scale, self.P_mean, self.P_std = t_eps, noise_scale, P_mean, P_std
+        self.timestep_uniform_mix_prob = float(timestep_uniform_mix_prob)   # --alg_b2b_timestep_uniform_mix_prob
+        self.label_drop_prob = min(max(float(label_drop_prob), 0.0), 1.0)   # --alg_diffusion_dropout_prob (:81-84)
+        self.num_classes = num_classes
+        self.denoise_timesteps = denoise_timesteps
 
     def sample_t(self, n, device):
-        """(:192-199) logit-normal"""
-        return torch.sigmoid(torch.randn(n, device=device) * self.P_std + self.P_mean)
+        """(:192-210) logit-normal, optionally mixed with uniform draws; the draws come in the reference's order"""
+        t = torch.sigmoid(torch.randn(n, device=device) * self.P_std + self.P_mean)
+        if self.timestep_uniform_mix_prob <= 0.0:
+            return t
+        if self.timestep_uniform_mix_prob >= 1.0:
+            return torch.rand_like(t)
+        t_uniform = torch.rand_like(t)
+        return torch.where(torch.rand_like(t) < self.timestep_uniform_mix_prob, t_uniform, t)
 
-    def forward(self, x, mask, x_cond, label, t_base=None, e=None):
-        """Returns (v_pred, v, x_pred)."""
+    def drop_labels(self, labels):
+        """(:212-216) classifier-free label dropout: the dropped samples get the extra class `num_classes`"""
+        if self.label_drop_prob <= 0.0:
+            return labels
+        drop = torch.rand(labels.shape, device=labels.device) < self.label_drop_prob
+        return torch.where(drop, torch.full_like(labels, self.num_classes), labels)
+
+    def forward_flow(self, x, mask, x_cond, label, t_base=None, e=None, use_gt=None, ref_idx=None):
+        """b2b_forward + forward (:238-348) for clips [B, F, C, H, W] -> (v_pred, v, x_pred, raw x_pred).  Random draws
+        in the reference's order: label dropout, t, then the noise."""
         b, f = x.shape[:2]
+        if label is None:
+            label = torch.zeros(b, dtype=torch.long, device=x.device)
+        elif self.training:
+            label = self.drop_labels(label)
         if t_base is None:
             t_base = self.sample_t(b, x.device)
         if e is None:
             e = torch.randn_like(x)
-        t = t_base[:, None].repeat(1, f).view(b, f, 1, 1, 1)
+        t_cont = t_base[:, None].repeat(1, f)
+        if use_gt is not None and ref_idx is not None and bool(use_gt.any()):
+            b_idx = torch.arange(b, device=x.device)      # autoregressive training: the reference frame is clean (:266-268)
+            t_cont[b_idx[use_gt], ref_idx[use_gt]] = 1.0
+        t = t_cont.view(b, f, 1, 1, 1)
         if mask is not None:
             mask = torch.clamp(mask, min=0.0, max=1.0)
         z_t = t * x + (1.0 - t) * (e * self.noise_scale)
         z = z_t * mask + (1.0 - mask) * x if mask is not None else z_t
         z_model = z if x_cond is None else torch.cat([x_cond, z], dim=2)
         v = (x - z) / (1.0 - t).clamp_min(self.t_eps)
-        x_pred = self.b2b_model(z_model, t.reshape(b * f), label)
-        if x_pred.shape[2] > x.shape[2]:
-            x_pred = x_pred[:, :, -x.shape[2]:]
-        if mask is not None:
-            x_pred = x_pred * mask + (1 - mask) * x
+        raw = self.b2b_model(z_model, t_cont.reshape(b * f), label)
+        if raw.shape[2] > x.shape[2]:
+            raw = raw[:, :, -x.shape[2]:]
+        x_pred = raw * mask + (1 - mask) * x if mask is not None else raw
         v_pred = (x_pred - z) / (1 - t).clamp_min(self.t_eps)
-        return v_pred, v, x_pred
+        return v_pred, v, x_pred, raw
+
+    def forward(self, x, mask=None, x_cond=None, label=None, use_gt=None, ref_idx=None, temporal_frame_step=None,
+                global_context=None, object_refs=None, return_x_pred=False, return_raw_x_pred=False, t_base=None,
+                e=None):
+        """The reference's call signature (b2b_model.py:1112-1122 calls it with keywords): (v_pred, v) [, x_pred
+        [, raw x_pred]].  t_base / e: explicit random draws (tests)."""
+        if temporal_frame_step is not None or global_context is not None or object_refs is not None:
+            raise NotImplementedError("B200 B2BGenerator: frame-step / global-context / object-reference conditioning")
+        if x.dim() != 5:
+            raise NotImplementedError("B200 B2BGenerator: clips [B, F, C, H, W] only (the vit_vid backbone)")
+        v_pred, v, x_pred, raw = self.forward_flow(x, mask, x_cond, label, t_base, e, use_gt, ref_idx)
+        if return_raw_x_pred:
+            return v_pred, v, x_pred, raw
+        if return_x_pred:
+            return v_pred, v, x_pred
+        return v_pred, v
 
     @staticmethod
     def masked_region_loss(pred, target, mask, eps=1e-8):
@@ -328,7 +370,7 @@ class B2BGenerator(nn.Module):
         return ((le * mask).sum(dim=dims) / mask.sum(dim=dims).clamp_min(eps)).mean()
 
     def forward_loss(self, x, mask, x_cond, label, t_base=None, e=None, lambda_G=1.0):
-        v_pred, v, _ = self.forward(x, mask, x_cond, label, t_base, e)
+        v_pred, v, _, _ = self.forward_flow(x, mask, x_cond, label, t_base, e)
         return lambda_G * self.masked_region_loss(v_pred, v, torch.clamp(mask, min=0, max=1))
 
     @torch.no_grad()

@@ -49,9 +49,10 @@ def draws(seed, p_mean, p_std, mix):
     return t, e
 
 
-def main():
+def create_reference_model():
+    """options -> create_model -> setup of the reference's b2b_model on CPU, seeded weights loaded
+    -> (model, opt, shapes, params, frozen)"""
     ref_stubs.install()
-    torch.set_num_threads(8)
     import train as ref_train
     from models import create_model
     from options.train_options import TrainOptions
@@ -88,6 +89,13 @@ def main():
     missing, unexpected = net.load_state_dict(params, strict=False)
     assert not unexpected
     frozen = {k: v.detach().clone() for k, v in net.named_parameters() if not v.requires_grad}
+    return model, opt, shapes, params, frozen
+
+
+def main():
+    torch.set_num_threads(8)
+    model, opt, shapes, params, frozen = create_reference_model()
+    net = model.netG_A
     gen = dict(P_mean=net.P_mean, P_std=net.P_std, mix=net.timestep_uniform_mix_prob, noise_scale=net.noise_scale,
                t_eps=net.t_eps)
     losses = []

@@ -146,7 +146,8 @@ def test_b2b_generator_vs_reference_golden(env, golden_dir):
     torch.manual_seed(gold["rseed"])
     t_base = torch.sigmoid(torch.randn(gold["batch"]) * 0.8 - 0.8)
     e = torch.randn_like(gt)
-    v_pred, v, x_pred = net(gt.cuda(), mask.cuda(), cond.cuda(), label.cuda(), t_base=t_base.cuda(), e=e.cuda())
+    v_pred, v, x_pred = net(gt.cuda(), mask.cuda(), cond.cuda(), label.cuda(), return_x_pred=True, t_base=t_base.cuda(),
+                            e=e.cuda())
     assert rel(x_pred, gold["x_pred"]) < 3e-2
     m = mask.bool().expand_as(gt)
     assert torch.equal(x_pred.cpu()[~m], gt[~m])

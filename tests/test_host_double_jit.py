@@ -45,7 +45,7 @@ def test_b2b_generator_and_sampler_on_the_double(golden_dir):
     e = torch.randn_like(gt)
     m = mask.bool().expand_as(gt)
     with KD.installed():
-        v_pred, v, x_pred = net(gt, mask, cond, label, t_base=t_base, e=e)
+        v_pred, v, x_pred = net(gt, mask, cond, label, return_x_pred=True, t_base=t_base, e=e)
         assert rel(x_pred, gold["x_pred"]) < 3e-2
         assert torch.equal(x_pred[~m], gt[~m])
         loss = net.masked_region_loss(v_pred, v, torch.clamp(mask, 0, 1))
@@ -173,5 +173,40 @@ def test_b2b_trainer_two_steps_vs_reference_plumbing_on_the_double(golden_dir):
         got, ema = tr.params(), tr.ema_state_dict()
     for k, (_, nrm) in gold["param_stats"].items():
         assert abs(float(got[k].double().norm()) - nrm) <= 2e-3 * nrm + 1e-6, k
+    for k, (_, nrm) in gold["ema_stats"].items():
+        assert abs(float(ema[k].double().norm()) - nrm) <= 2e-3 * nrm + 1e-6, k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present (GPU box)")
+def test_reference_b2b_model_trains_with_accelerated_generator(golden_dir):
+    """BASELINE.json config 5 as written, as a DROP-IN: the unmodified reference's b2b_model control path
+    (example_b2b_vid_mario.json: create_model -> set_input -> optimize_parameters(): compute_b2b_loss with its keyword
+    call of netG_A, backward, AdamW(0.9, 0.95), ema_step) with `accelerate(netG_A)` — B2BGenerator(JiTVid-B/16), 156 M
+    parameters — vs the reference's own two steps (b2b_plumbing.pt), seeded identically."""
+    from oracle import gen_golden_b2b_plumbing as P
+    import joligen_b200
+    from joligen_b200 import nets_jit
+    gold = torch.load(os.path.join(golden_dir, "b2b_plumbing.pt"))
+    model, _, _, _, _ = P.create_reference_model()
+    ref_params = dict(model.netG_A.named_parameters())
+    keys = [k for k in model.netG_A.state_dict()]
+    model.netG_A = joligen_b200.accelerate(model.netG_A)
+    assert isinstance(model.netG_A, nets_jit.B2BGenerator)
+    assert all(p is ref_params[k] for k, p in model.netG_A.named_parameters()) and len(ref_params) == len(list(model.netG_A.parameters()))
+    assert set(keys) <= set(model.netG_A.state_dict())
+    losses = []
+    with KD.installed():
+        for step in range(2):
+            data = P.batch(gold["data_seeds"][step])
+            model.set_input(dict(data, A_img_paths=["a"] * P.BATCH, B_label_cls=torch.zeros(P.BATCH, dtype=torch.long)))
+            torch.manual_seed(gold["rng_seeds"][step])
+            model.optimize_parameters()
+            losses.append(float(model.loss_G_tot.detach()))
+    for got, want in zip(losses, gold["losses"]):
+        assert abs(got - want) < 3e-2 * abs(want), (losses, gold["losses"])
+    sd = dict(model.netG_A.named_parameters())
+    for k, (_, nrm) in gold["param_stats"].items():
+        assert abs(float(sd[k].double().norm()) - nrm) <= 2e-3 * nrm + 1e-6, k
+    ema = dict(model.netG_A_ema.named_parameters())
     for k, (_, nrm) in gold["ema_stats"].items():
         assert abs(float(ema[k].double().norm()) - nrm) <= 2e-3 * nrm + 1e-6, k
