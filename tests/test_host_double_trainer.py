@@ -188,3 +188,50 @@ def test_two_rank_trainer_gradient_and_replicas_on_the_double():
     assert a["grad_rel"] < 1e-4, a["grad_rel"]
     for k in ("params", "exp_avg", "ema"):
         assert torch.equal(a[k], b[k]), "replicas differ in %s" % k
+
+
+def test_production_architecture_train_step_vs_oracle_on_the_double():
+    """The config-2 ARCHITECTURE (ngf 64, mults 1-2-4-8, two ResBlocks per level, attention at ds 16: 59 M parameters,
+    22 batched emb Linears, 75 managed convolutions, four concat levels) at 128^2, one PaletteTrainer step vs the oracle
+    in fp32 and in bf16-storage emulation — tests/test_gpu_config2_full.py's comparison, sized for the CPU."""
+    from joligen_b200 import nets
+    from oracle import palette_oracle as O
+    cfg = O.UNetCfg(image_size=128)
+    assert (cfg.inner_channel, tuple(cfg.channel_mults), tuple(cfg.res_blocks), tuple(cfg.attn_res)) == \
+        (64, (1, 2, 4, 8), (2, 2, 2, 2), (16,))
+    params = O.init_params(cfg, 2024)
+    net = nets.build_palette_generator(image_size=128)
+    missing, unexpected = net.load_state_dict(params, strict=False)
+    assert not unexpected and all("gammas" in m or "posterior" in m for m in missing)
+    data = O.synthetic_batch(1, 128, 31)
+    torch.manual_seed(77)
+    t, u = O.sample_t_gamma(cfg, 1)
+    noise = torch.randn_like(data["gt"])
+    with KD.installed():
+        tr = _trainer(net, lr=1e-4, optim="adamw", ema=True, ema_beta=0.999)
+        assert len(tr.packset.packs) == 75 and len(tr.wstage.slots) >= 70
+        with torch.no_grad():
+            _, nh, _ = tr.netG_A(data["gt"], data["cond"], data["mask"], noise, t=t, u=u)
+        tr.set_input({"A": data["cond"], "B": data["gt"], "B_label_mask": data["mask"]})
+        loss = tr.optimize_parameters(noise=noise, t=t, u=u)
+        sd = {k: v.clone() for k, v in tr.netG_A.state_dict().items()}
+    oc = O.OptimCfg(lr=1e-4, ema_beta=0.999)
+    fp = O.TrainState(params={k: v.clone() for k, v in params.items()})
+    fp_loss, fp_hat, _ = O.train_step(fp, cfg, oc, data["gt"], data["cond"], data["mask"], noise, t, u)
+    emu = O.TrainState(params={k: v.clone() for k, v in params.items()})
+    O.EMULATE_BF16[0] = True
+    try:
+        emu_loss, emu_hat, _ = O.train_step(emu, cfg, oc, data["gt"], data["cond"], data["mask"], noise, t, u)
+    finally:
+        O.EMULATE_BF16[0] = False
+    assert abs(float(loss) - float(emu_loss)) < 2e-2 * abs(float(emu_loss)), (float(loss), float(emu_loss))
+    assert abs(float(loss) - float(fp_loss)) < 2e-2 * abs(float(fp_loss)), (float(loss), float(fp_loss))
+    floor = rel_l2(emu_hat, fp_hat)
+    assert rel_l2(nh, fp_hat) < max(3e-2, 2.5 * floor), (rel_l2(nh, fp_hat), floor)
+    num = den = 0.0
+    for k in params:
+        upd = sd[k].double() - params[k].double()
+        upd_ref = emu.params[k].double() - params[k].double()
+        num += float((upd - upd_ref).norm()) ** 2
+        den += float(upd_ref.norm()) ** 2
+    assert (num / den) ** 0.5 < 0.35
