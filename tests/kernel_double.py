@@ -924,6 +924,14 @@ def monce_bwd(q, k, lse, grad_loss, ws, groups, temperature, num_patches_opt, it
     return _nce_bwd(q, k, grad_loss, groups, temperature, "monce", num_patches_opt, True, need_dk)
 
 
+
+def mask_class_dropout(mask, drop_u, prob, fill):
+    """palette_model.py:565-584: samples with drop_u[n] < prob get the unconditioned class `fill` everywhere"""
+    mask = mask.contiguous()
+    drop = (drop_u.float() < prob).view(-1, *([1] * (mask.dim() - 1)))
+    return torch.where(drop, torch.full_like(mask, fill), mask)
+
+
 _JIT_DOUBLES = dict(rmsnorm_mod=_j_rmsnorm_mod, qknorm_rope=_j_qknorm_rope, attn_small=_j_attn_small, swiglu=_j_swiglu,
                     gated_residual=_j_gated_residual)
 
@@ -942,7 +950,7 @@ _DOUBLES = dict(pack_conv_weight=pack_conv_weight, conv2d_fwd=conv2d_fwd, chan_s
                 ddpm_step=ddpm_step, WeightTable=WeightTable, pack_conv_weights_batched=pack_conv_weights_batched,
                 wgrad_unpack_batched=wgrad_unpack_batched, gather_rows=gather_rows, gather_rows_bwd=gather_rows_bwd,
                 l2norm_fwd=l2norm_fwd, l2norm_bwd=l2norm_bwd, patch_nce_fwd=patch_nce_fwd, patch_nce_bwd=patch_nce_bwd,
-                monce_fwd=monce_fwd, monce_bwd=monce_bwd)
+                monce_fwd=monce_fwd, monce_bwd=monce_bwd, mask_class_dropout=mask_class_dropout)
 
 
 def _refuse(name):

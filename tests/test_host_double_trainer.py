@@ -235,3 +235,76 @@ def test_production_architecture_train_step_vs_oracle_on_the_double():
         num += float((upd - upd_ref).norm()) ** 2
         den += float(upd_ref.norm()) ** 2
     assert (num / den) ** 0.5 < 0.35
+
+
+def _build_cfg45(which, gold, params):
+    from joligen_b200 import nets, nets_ref, nets_vid
+    kw = dict(tanh=False, n_timestep_train=gold["n_timestep_train"], n_timestep_test=gold["n_timestep_test"],
+              norm="groupnorm", group_norm_size=32, cond_embed_dim=32, num_heads=1, **gold["net"])
+    kw["res_blocks"], kw["attn_res"] = list(kw["res_blocks"]), list(kw["attn_res"])
+    unet = (nets_vid.UNetVid if which == "vid" else nets_ref.UNetGeneratorRefAttn)(**kw)
+    g = nets.DiffusionGenerator(nets.PaletteDenoiseFn(unet, 32), image_size=gold["size"], G_ngf=gold["net"]["inner_channel"])
+    missing, unexpected = g.load_state_dict(params, strict=False)
+    assert not unexpected and not [m for m in missing if not any(t in m for t in ("gammas", "posterior", "pos_encoder.pe"))]
+    return g
+
+
+@pytest.mark.parametrize("which", ["ref", "vid"])
+def test_trainer_cfg4_cfg5_match_reference_plumbing_on_the_double(golden_dir, which):
+    """PaletteTrainer with the reference-image UNet (`ref_A` through set_input) and with the video UNet (5-D clips folded
+    to B*F frames, per-clip draws) vs the reference's own two steps (refattn_plumbing.pt / vid_plumbing.pt)."""
+    from oracle.gen_golden_plumbing45 import batch, draws, oracle_cfg
+    from oracle.vid_oracle import init_params_from_shapes
+    gold = torch.load(os.path.join(golden_dir, "vid_plumbing.pt" if which == "vid" else "refattn_plumbing.pt"))
+    p0 = init_params_from_shapes(gold["shapes"], gold["wseed"])
+    net = _build_cfg45(which, gold, p0)
+    assert [(k, tuple(v.shape)) for k, v in net.named_parameters()] == [(k, tuple(s)) for k, s in gold["shapes"]]
+    oc = gold["optim"]
+    cfg = oracle_cfg(which)
+    cfg.n_timestep_train, cfg.n_timestep_test = gold["n_timestep_train"], gold["n_timestep_test"]
+    with KD.installed():
+        tr = _trainer(net, lr=oc["lr"], beta1=oc["beta1"], beta2=oc["beta2"], eps=oc["eps"],
+                      weight_decay=oc["weight_decay"], optim=oc["kind"], ema=True, ema_beta=oc["ema_beta"],
+                      iter_size=oc["iter_size"], lambda_G=gold["lambda_G"])
+        for step in range(2):
+            data = batch(which, gold["data_seeds"][step])
+            t, u, noise = draws(which, cfg, gold["rng_seeds"][step])
+            tr.set_input(data)
+            loss = tr.optimize_parameters(noise=noise, t=t, u=u)
+            assert abs(float(loss) - gold["losses"][step]) < 2e-2 * abs(gold["losses"][step]), step
+        sd, ema = net.state_dict(), tr.ema_state_dict()
+    for k, (_, n) in gold["param_stats"].items():
+        assert abs(float(sd[k].double().norm()) - n) <= (1e-2 if sd[k].dim() > 1 else 2e-2) * n + 1e-6, k
+    for k, (_, n) in gold["ema_stats"].items():
+        assert abs(float(ema[k].double().norm()) - n) <= (1e-2 if ema[k].dim() > 1 else 2e-2) * n + 1e-6, k
+
+
+def test_trainer_with_class_conditioning_and_dropout_on_the_double():
+    """cond_embed "class": B_label_cls travels through set_input; conditioning dropout (palette_model.py:565-584)
+    replaces the dropped samples' class (and mask) by num_classes - 1 — equal to the same step with the labels edited by
+    hand (exactly: the double is deterministic)."""
+    from joligen_b200 import nets
+    from oracle import palette_oracle as O
+    from oracle.gen_golden_cond import BASE, cond_batch, cond_cfg, cond_params
+    cfg = cond_cfg("class", 4)
+    params = cond_params(cfg, 3)
+    data = cond_batch(cfg, 4, 9)
+    torch.manual_seed(1)
+    t, u = O.sample_t_gamma(cfg, 4)
+    noise = torch.randn_like(data["gt"])
+    drop_u = torch.tensor([0.01, 0.9, 0.05, 0.5])
+    losses = []
+    with KD.installed():
+        for mode in ("dropout", "by_hand"):
+            net = nets.build_palette_generator(conditioning="class", nclasses=4, **BASE)
+            net.load_state_dict(params, strict=False)
+            cls, mask = data["cls"].clone(), data["mask"].clone()
+            if mode == "by_hand":   # the reference fills BOTH the class and the mask of a dropped sample (:571-583)
+                cls[drop_u < 0.1] = 3
+                mask[drop_u < 0.1] = 3
+            tr = _trainer(net, lr=1e-3, dropout_prob=0.1 if mode == "dropout" else 0.0, num_classes=4)
+            tr.set_input({"A": data["cond"], "B": data["gt"], "B_label_mask": mask, "B_label_cls": cls})
+            losses.append(float(tr.compute_palette_loss(noise=noise, t=t, u=u,
+                                                        drop_u=drop_u if mode == "dropout" else None).detach()))
+        assert losses[0] == losses[1]
+        assert torch.isfinite(tr.optimize_parameters(noise=noise, t=t, u=u))
