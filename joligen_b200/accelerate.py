@@ -67,9 +67,20 @@ def _resolve(root, name, create=False):
     return mod, parts[-1]
 
 
-def _norm_spec(gn_wrapper):
-    g = gn_wrapper.norm
-    return "groupnorm%d" % g.num_groups
+def _norm_spec(ref_unet):
+    """The `norm` argument that rebuilds the net's normalisation wrappers (unet_attn_utils.normalization :94-113), read
+    off ALL of them: "instancenorm" is GroupNorm(C, C) — a group count that follows each block's width — "layernorm"
+    GroupNorm(1, C), "groupnormN" a fixed count (which coincides with the width of the narrowest block for N = ngf)."""
+    wrapped = [m.norm for m in ref_unet.modules() if type(m).__name__ == "GroupNorm" and hasattr(m, "norm")]
+    if not wrapped:
+        raise NotImplementedError("accelerate: no GroupNorm wrapper in the reference UNet (batchnorm / switchablenorm?)")
+    counts = {g.num_groups for g in wrapped}
+    if len(counts) == 1:
+        n = counts.pop()
+        return "layernorm" if n == 1 and any(g.num_channels > 1 for g in wrapped) else "groupnorm%d" % n
+    if all(g.num_groups == g.num_channels for g in wrapped):
+        return "instancenorm"
+    raise NotImplementedError("accelerate: mixed GroupNorm group counts %s" % sorted(counts))
 
 
 def _has_tanh(ref):
@@ -85,6 +96,16 @@ def _check_structure(dst: nn.Module, src: nn.Module):
     count = lambda root: {k: sum(is_kind(m, k) for m in root.modules()) for k in kinds}  # noqa: E731
     if count(dst) != count(src):
         raise RuntimeError("accelerate: block structure differs: reference %s vs B200 %s" % (count(src), count(dst)))
+    gn = lambda root: [(m.num_groups, m.num_channels, m.eps, m.affine) for m in root.modules()  # noqa: E731
+                       if isinstance(m, nn.GroupNorm)]
+    if gn(dst) != gn(src):
+        raise RuntimeError("accelerate: the normalisation layers of the reference net (groups, width, eps, affine) are "
+                           "not the ones the B200 mirror was built with")
+    other = sorted({type(m).__name__ for m in src.modules()
+                    if isinstance(m, (nn.modules.batchnorm._BatchNorm, nn.LayerNorm)) or "SwitchNorm" in type(m).__name__}
+                   - {type(m).__name__ for m in dst.modules()})
+    if other:
+        raise NotImplementedError("accelerate: normalisation %s is not on the B200 path" % other)
     drops = sorted({float(m.p) for m in src.modules() if isinstance(m, nn.Dropout) and m.p > 0})
     if drops:
         raise NotImplementedError("accelerate: the reference net uses dropout %s (not supported on the B200 path)" % drops)
@@ -97,7 +118,7 @@ def _check_structure(dst: nn.Module, src: nn.Module):
 
 def _unet_from_reference(ref):
     first_res = ref.input_blocks[1][0]
-    norm = _norm_spec(first_res.in_layers[0])
+    norm = _norm_spec(ref)
     return nets.UNet(
         image_size=ref.image_size, in_channel=ref.in_channel, inner_channel=ref.inner_channel,
         out_channel=ref.out_channel, res_blocks=list(ref.res_blocks), attn_res=list(ref.attn_res),
@@ -118,7 +139,7 @@ def _common_unet_kwargs(ref):
         out_channel=ref.out_channel, res_blocks=list(ref.res_blocks), attn_res=list(ref.attn_res),
         tanh=_has_tanh(ref), dropout=getattr(ref, "dropout", 0),
         n_timestep_train=ref.beta_schedule["train"]["n_timestep"],
-        n_timestep_test=ref.beta_schedule["test"]["n_timestep"], norm=_norm_spec(first_res.in_layers[0]),
+        n_timestep_test=ref.beta_schedule["test"]["n_timestep"], norm=_norm_spec(ref),
         group_norm_size=first_res.in_layers[0].norm.num_groups, cond_embed_dim=ref.cond_embed_dim,
         channel_mults=tuple(ref.channel_mults),
         use_scale_shift_norm=first_res.use_scale_shift_norm, efficient=first_res.efficient,

@@ -473,3 +473,34 @@ def test_unet_variants_oracle_host_stack_and_reference_agree(variant):
         err += float((p.grad.double() - q.grad.double()).norm()) ** 2
         nrm += float(q.grad.double().norm()) ** 2
     assert (err / nrm) ** 0.5 < max(4e-2, 1.5 * gfloor), ((err / nrm) ** 0.5, gfloor)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("norm", ["instancenorm", "layernorm", "groupnorm"])
+def test_accelerate_rebuilds_the_reference_norm_variant(norm):
+    """--G_unet_mha_norm_layer instancenorm (GroupNorm(C, C): the group count follows each block's width) / layernorm
+    (GroupNorm(1, C)) / groupnorm N: accelerate() must rebuild every block's normalisation, not the first block's group
+    count everywhere — checked structurally and against the reference's own forward."""
+    import copy
+    from oracle import ref_stubs
+    ref_stubs.install()
+    import torch.nn as nn
+    from models.modules.unet_generator_attn.unet_generator_attn import UNet
+    import joligen_b200
+    torch.manual_seed(0)
+    ref = UNet(image_size=32, in_channel=6, inner_channel=32, out_channel=3, res_blocks=[1, 1], attn_res=[2], tanh=False,
+               n_timestep_train=2000, n_timestep_test=1000, norm=norm, group_norm_size=8, cond_embed_dim=32,
+               channel_mults=(1, 2), num_heads=1, num_head_channels=16)
+    with torch.no_grad():   # the reference zero-initialises the second conv of every block: de-zero for a real check
+        for p in ref.parameters():
+            if float(p.abs().max()) == 0.0:
+                p.normal_(0.0, 0.05)
+    fast = joligen_b200.accelerate(copy.deepcopy(ref))
+    groups = lambda m: [(g.num_groups, g.num_channels) for g in m.modules() if isinstance(g, nn.GroupNorm)]  # noqa: E731
+    assert groups(fast) == groups(ref)
+    x = torch.randn(2, 6, 32, 32)
+    emb = torch.randn(2, 32)
+    want = ref(x, emb)
+    with KD.installed():
+        got = fast(x, emb)
+    assert rel_l2(got, want) < 4e-2, rel_l2(got, want)
