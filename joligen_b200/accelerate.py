@@ -109,6 +109,12 @@ def _check_structure(dst: nn.Module, src: nn.Module):
     drops = sorted({float(m.p) for m in src.modules() if isinstance(m, nn.Dropout) and m.p > 0})
     if drops:
         raise NotImplementedError("accelerate: the reference net uses dropout %s (not supported on the B200 path)" % drops)
+    att = lambda root: [m for m in root.modules() if is_kind(m, "AttentionBlock") or is_kind(m, "AttentionBlockRef")]  # noqa: E731
+    for a, b in zip(att(src), att(dst)):
+        new_order = type(getattr(a, "attention", None)).__name__ == "QKVAttention"
+        if a.num_heads != b.num_heads or a.channels != b.channels or int(new_order) != int(b.attention_layout):
+            raise RuntimeError("accelerate: attention configuration (heads / width / q-k-v channel order) differs between "
+                               "the reference block and its B200 mirror")
     for a, b in zip((m for m in src.modules() if is_kind(m, "ResBlock")),
                     (m for m in dst.modules() if is_kind(m, "ResBlock"))):
         if (bool(a.updown), bool(a.use_scale_shift_norm), bool(getattr(a, "efficient", False))) != \
