@@ -266,11 +266,16 @@ def _b2b_generator_from_reference(ref):
                           bottleneck_dim=m.x_embedder.proj1.out_channels, in_context_len=m.in_context_len,
                           in_context_start=m.in_context_start, max_frames=m.max_frames,
                           motion_num_heads=tblocks[0].attention_blocks[0].heads, motion_num_layers=len(tblocks))
-    return nets_jit.B2BGenerator(net, t_eps=ref.t_eps, noise_scale=ref.noise_scale, P_mean=ref.P_mean, P_std=ref.P_std,
-                                 timestep_uniform_mix_prob=getattr(ref, "timestep_uniform_mix_prob", 0.0),
-                                 label_drop_prob=getattr(ref, "label_drop_prob", 0.0),
-                                 num_classes=getattr(ref, "num_classes", 1),
-                                 denoise_timesteps=getattr(ref, "denoise_timesteps", 50))
+    if abs(float(getattr(ref, "cfg_scale", 1.0)) - 1.0) > 1e-12:
+        raise NotImplementedError("accelerate: B2BGenerator with classifier-free guidance (alg_b2b_cfg_scale != 1)")
+    gen = nets_jit.B2BGenerator(net, t_eps=ref.t_eps, noise_scale=ref.noise_scale, P_mean=ref.P_mean, P_std=ref.P_std,
+                                timestep_uniform_mix_prob=getattr(ref, "timestep_uniform_mix_prob", 0.0),
+                                label_drop_prob=getattr(ref, "label_drop_prob", 0.0),
+                                num_classes=getattr(ref, "num_classes", 1),
+                                denoise_timesteps=getattr(ref, "denoise_timesteps", 50))
+    gen.clip_denoised_default = bool(getattr(ref, "clip_denoised_default", False))
+    gen.disable_inference_clipping = bool(getattr(ref, "disable_inference_clipping", False))
+    return gen
 
 
 def accelerate(module: nn.Module) -> nn.Module:

@@ -660,6 +660,10 @@ class DiffusionGenerator(nn.Module):
         self.cond_embed_gammas_in = eg
         self.cond_embed = nn.Sequential(nn.Linear(eg, eg), nn.SiLU(), nn.Linear(eg, eg))
 
+    def set_new_sampling_method(self, sampling_method):
+        """diffusion_generator.py:523-524 (PaletteModel.inference switches to --alg_palette_sampling_method_test)"""
+        self.sampling_method = sampling_method
+
     def compute_gammas(self, gammas):
         emb = gamma_embedding(gammas, self.cond_embed_gammas_in)
         emb = ops.linear(emb, self.cond_embed[0].weight, self.cond_embed[0].bias)

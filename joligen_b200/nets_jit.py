@@ -298,6 +298,11 @@ class B2BGenerator(nn.Module):
         self.label_drop_prob = min(max(float(label_drop_prob), 0.0), 1.0)   # --alg_diffusion_dropout_prob (:81-84)
         self.num_classes = num_classes
         self.denoise_timesteps = denoise_timesteps
+        # sampler options (b2b_generator.py:46-55); accelerate() copies the reference generator's values.  The velocity
+        # denominator 1 - t is clamped at t_eps during sampling unless disable_inference_clipping (this mirror's
+        # historical default; the two coincide whenever 1 / steps >= t_eps)
+        self.clip_denoised_default = False
+        self.disable_inference_clipping = True
 
     def sample_t(self, n, device):
         """(:192-210) logit-normal, optionally mixed with uniform draws; the draws come in the reference's order"""
@@ -374,11 +379,25 @@ class B2BGenerator(nn.Module):
         return lambda_G * self.masked_region_loss(v_pred, v, torch.clamp(mask, min=0, max=1))
 
     @torch.no_grad()
-    def restoration(self, y, y_cond, denoise_timesteps, mask=None, labels=None, init_noise=None, clip_denoised=False,
-                    disable_inference_clipping=True):
-        """b2b_generator.B2BGenerator.restoration (:406-500) with guidance neutral (cfg_scale 1): Heun steps on the
+    def restoration(self, y, y_cond=None, denoise_timesteps=None, mask=None, labels=None, clip_denoised=None,
+                    use_gt=None, ref_idx=None, init_noise=None, temporal_frame_step=None, global_context=None,
+                    object_refs=None, disable_inference_clipping=None):
+        """b2b_generator.B2BGenerator.restoration (:406-500, same argument order: b2b_model.py:1312-1349 calls it
+        positionally up to `labels` and by keyword after) with guidance neutral (cfg_scale 1): Heun steps on the
         linspace(0, 1, steps + 1) grid, a final Euler step, known pixels re-projected after every step, final clamp."""
+        if temporal_frame_step is not None or global_context is not None or object_refs is not None:
+            raise NotImplementedError("B200 B2BGenerator: frame-step / global-context / object-reference conditioning")
+        if use_gt is not None and ref_idx is not None and bool(use_gt.any()):
+            raise NotImplementedError("B200 B2BGenerator.restoration: autoregressive reference frames")
         b, f = y.shape[:2]
+        if denoise_timesteps is None:
+            denoise_timesteps = self.denoise_timesteps
+        if isinstance(denoise_timesteps, (list, tuple)):
+            denoise_timesteps = denoise_timesteps[0]
+        if clip_denoised is None:
+            clip_denoised = self.clip_denoised_default              # --alg_b2b_clip_denoised
+        if disable_inference_clipping is None:
+            disable_inference_clipping = self.disable_inference_clipping   # --alg_b2b_disable_inference_clipping
         steps = int(denoise_timesteps)
         if mask is not None:
             mask = torch.clamp(mask, 0.0, 1.0)

@@ -88,7 +88,7 @@ def module_golden(name, cfgd, batch, wseed, dseed, rseed, full_grads):
     print(name, "loss", out["loss"], "noise_hat absmax", float(noise_hat.abs().max()))
 
 
-def create_reference_model(size=32, batch=2):
+def create_reference_model(size=32, batch=2, extra=None):
     """options -> create_model -> setup of the reference's PaletteModel on CPU (train.py:183-281) -> (model, opt)"""
     import train as ref_train
     from models import create_model
@@ -116,6 +116,7 @@ def create_reference_model(size=32, batch=2):
         "train_optim": "adamw", "train_G_lr": 1e-3, "train_G_ema": True, "train_G_ema_beta": 0.9,
         "train_optim_weight_decay": 0.01, "output_no_html": True,
     })
+    flat.update(extra or {})
     opt = TrainOptions().parse_json(flat, save_config=False)
     opt.use_cuda = False
     opt.optim = ref_train.optim

@@ -504,3 +504,32 @@ def test_accelerate_rebuilds_the_reference_norm_variant(norm):
     with KD.installed():
         got = fast(x, emb)
     assert rel_l2(got, want) < 4e-2, rel_l2(got, want)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_reference_palette_inference_with_accelerated_generator():
+    """PaletteModel.inference (palette_model.py:622-760: set_new_noise_schedule on the denoiser, set_new_sampling_method,
+    netG.restoration(y_cond=, y_t=, y_0=, mask=, sample_num=, cls=, ddim_num_steps=, ddim_eta=)) on the accelerated
+    generator == the reference sampling itself with the same seeds (8 reverse steps)."""
+    from oracle import ref_stubs
+    ref_stubs.install()
+    from oracle import gen_golden
+    from oracle import palette_oracle as O
+    import contextlib
+    import joligen_b200
+    outs = []
+    for fast in (False, True):
+        model, _ = gen_golden.create_reference_model(32, 2, extra={"G_diff_n_timestep_test": 8})
+        model.netG_A.load_state_dict(O.init_params(O.UNetCfg(**gen_golden.SMALL), 21), strict=False)
+        if fast:
+            model.netG_A = joligen_b200.accelerate(model.netG_A)
+        data = O.synthetic_batch(2, 32, 100)
+        torch.manual_seed(7)
+        model.set_input({"A": data["cond"], "B": data["gt"], "B_label_mask": data["mask"],
+                         "B_label_cls": torch.zeros(2, dtype=torch.long), "A_img_paths": ["a"] * 2})
+        with (KD.installed() if fast else contextlib.nullcontext()), torch.no_grad():
+            torch.manual_seed(8)
+            model.inference(2)
+        outs.append((model.output.clone(), model.visuals.clone()))
+    assert outs[0][0].shape == outs[1][0].shape and outs[0][1].shape == outs[1][1].shape
+    assert rel_l2(outs[1][0], outs[0][0]) < 3e-2 and rel_l2(outs[1][1], outs[0][1]) < 3e-2

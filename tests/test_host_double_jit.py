@@ -210,3 +210,23 @@ def test_reference_b2b_model_trains_with_accelerated_generator(golden_dir):
     ema = dict(model.netG_A_ema.named_parameters())
     for k, (_, nrm) in gold["ema_stats"].items():
         assert abs(float(ema[k].double().norm()) - nrm) <= 2e-3 * nrm + 1e-6, k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present (GPU box)")
+def test_reference_b2b_inference_with_accelerated_generator():
+    """B2BModel.inference (b2b_model.py:1230-1360: netG.restoration(y_t, y_cond, steps, mask, labels, use_gt=, ref_idx=,
+    init_noise=, ...)) on the accelerated generator == the reference's own sampling with the same seed."""
+    import contextlib
+    from oracle import gen_golden_b2b_plumbing as P
+    import joligen_b200
+    outs = []
+    for fast in (False, True):
+        model, _, _, _, _ = P.create_reference_model()
+        if fast:
+            model.netG_A = joligen_b200.accelerate(model.netG_A)
+        model.set_input(dict(P.batch(300), A_img_paths=["a"] * P.BATCH, B_label_cls=torch.zeros(P.BATCH, dtype=torch.long)))
+        with (KD.installed() if fast else contextlib.nullcontext()), torch.no_grad():
+            torch.manual_seed(8)
+            model.inference(2)
+        outs.append(model.fake_B.clone())
+    assert outs[0].shape == outs[1].shape and rel(outs[1], outs[0]) < 3e-2, rel(outs[1], outs[0])
