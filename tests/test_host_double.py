@@ -533,3 +533,44 @@ def test_reference_palette_inference_with_accelerated_generator():
         outs.append((model.output.clone(), model.visuals.clone()))
     assert outs[0][0].shape == outs[1][0].shape and outs[0][1].shape == outs[1][1].shape
     assert rel_l2(outs[1][0], outs[0][0]) < 3e-2 and rel_l2(outs[1][1], outs[0][1]) < 3e-2
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_reference_checkpoints_interchange_with_accelerated_nets():
+    """BaseModel.save_networks / load_networks (base_model.py:824-868, 957-1103) on a model whose netG_A was accelerated:
+    the files load into an UNMODIFIED reference net (all keys matched), and into another accelerated model — whose
+    convolutions then run on the loaded weights (the bf16 copies are re-packed)."""
+    from oracle import ref_stubs
+    ref_stubs.install()
+    from oracle import gen_golden
+    from oracle import palette_oracle as O
+    import joligen_b200
+    model, _ = gen_golden.create_reference_model(32, 2)
+    model.netG_A.load_state_dict(O.init_params(O.UNetCfg(**gen_golden.SMALL), 21), strict=False)
+    model.netG_A = joligen_b200.accelerate(model.netG_A)
+    data = O.synthetic_batch(2, 32, 100)
+    batch = {"A": data["cond"], "B": data["gt"], "B_label_mask": data["mask"],
+             "B_label_cls": torch.zeros(2, dtype=torch.long), "A_img_paths": ["a"] * 2}
+    x, emb = torch.randn(2, 6, 32, 32), torch.randn(2, 32)
+    with KD.installed():
+        model.set_input(batch)
+        model.optimize_parameters()
+        os.makedirs(model.save_dir, exist_ok=True)
+        model.save_networks("latest")
+        assert sorted(os.listdir(model.save_dir)) == ["latest_net_G_A.pth", "latest_net_G_A_ema.pth"]
+        plain, _ = gen_golden.create_reference_model(32, 2)
+        for name in ("latest_net_G_A.pth", "latest_net_G_A_ema.pth"):
+            res = plain.netG_A.load_state_dict(torch.load(os.path.join(model.save_dir, name)))
+            assert not res.missing_keys and not res.unexpected_keys
+        other, _ = gen_golden.create_reference_model(32, 2)
+        other.netG_A = joligen_b200.accelerate(other.netG_A)
+        before = other.netG_A.denoise_fn.model(x, emb)       # packs the (different) initial weights
+        other.save_dir = model.save_dir
+        other.load_networks("latest")
+        after = other.netG_A.denoise_fn.model(x, emb)
+        want = model.netG_A.denoise_fn.model(x, emb)
+    assert torch.equal(after, want) and not torch.equal(before, want)
+    # the reference net evaluating the same checkpoint itself, fp32
+    plain.netG_A.load_state_dict(torch.load(os.path.join(model.save_dir, "latest_net_G_A.pth")))
+    with torch.no_grad():
+        assert rel_l2(want, plain.netG_A.denoise_fn.model(x, emb)) < 3e-2
