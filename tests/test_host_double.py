@@ -574,3 +574,33 @@ def test_reference_checkpoints_interchange_with_accelerated_nets():
     plain.netG_A.load_state_dict(torch.load(os.path.join(model.save_dir, "latest_net_G_A.pth")))
     with torch.no_grad():
         assert rel_l2(want, plain.netG_A.denoise_fn.model(x, emb)) < 3e-2
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_train_launcher_hook_accelerates_the_models_train_py_creates():
+    """joligen_b200.train: the create_model hook (what `python -m joligen_b200.train` installs in every rank) swaps the
+    nets of the models joliGEN's own train.py builds — palette_model and cut_model — and leaves the rest alone."""
+    from oracle import ref_stubs
+    ref_stubs.install()
+    import train as ref_train
+    import models
+    from joligen_b200 import nets, nets_gan
+    from joligen_b200 import train as launcher
+    saved = ref_train.create_model, models.create_model
+    try:
+        launcher.install_hook()
+        launcher.install_hook()   # idempotent
+        from oracle import gen_golden, gen_golden_cut_plumbing
+        model, _ = gen_golden.create_reference_model(32, 2)           # its `from models import create_model` is hooked
+        assert isinstance(model.netG_A, nets.DiffusionGenerator)
+        opt_params = {id(p) for g in model.optimizer_G.param_groups for p in g["params"]}
+        assert {id(p) for p in model.netG_A.parameters()} == opt_params   # the optimizer built before the swap still applies
+        with KD.installed():   # cut_model's data_dependent_initialize runs the (now accelerated) generator
+            cut, _, _, _, _, _ = gen_golden_cut_plumbing.create_reference_model("patchnce")
+        assert isinstance(cut.netG_A, nets_gan.ResnetGenerator) and isinstance(cut.netD_B_basic, nets_gan.NLayerDiscriminator)
+        assert type(cut.netF).__module__.startswith("models.")          # no mirror: stays the reference's
+        # the spawn target resolves to the reference's train_gpu in a fresh interpreter (no recursion on itself)
+        assert launcher._ORIG_TRAIN_GPU is None and ref_train.train_gpu.__module__ == "train"
+    finally:
+        ref_train.create_model, models.create_model = saved
+        ref_train._jg_hooked = False
