@@ -803,13 +803,20 @@ class DiffusionGenerator(nn.Module):
         T = model.num_timesteps_test
         assert T > sample_num, "num_timesteps must greater than sample_num"
         sample_inter = T // sample_num
-        b, c = y_cond.shape[0], model.out_channel
+        c = model.out_channel
         dev = y_cond.device
-        y_cond = y_cond.contiguous().float()
         if noise_fn is None:
             noise_fn = lambda i, shape: torch.randn(shape, device=dev)  # noqa: E731
+        # clips [B, F, C, H, W] (UNetVid; the reference folds them inside p_mean_variance, :213-218): B*F frames through
+        # the UNet and the step kernel, one noise level per clip; random draws keep the reference's 5-D shape
+        clip = self._fold_clip(y_cond, cls, mask)
+        bq = y_cond.shape[0]                      # rows of the noise-level embedding (clips, or images)
         if y_t is None:
-            y_t = noise_fn(T, (b, c) + tuple(y_cond.shape[2:]))
+            y_t = noise_fn(T, ((bq, clip, c) if clip else (bq, c)) + tuple(y_cond.shape[-2:]))
+        shape_out = tuple(y_t.shape)
+        y_cond, y_t, y_0, mask = (self._fold(v) for v in (y_cond, y_t, y_0, mask))
+        b = y_cond.shape[0]
+        y_cond = y_cond.contiguous().float()
         y_t = y_t.contiguous().float()
         if mask is not None:
             y_0 = y_0.contiguous().float()
@@ -820,16 +827,31 @@ class DiffusionGenerator(nn.Module):
                              model.posterior_mean_coef1_test, model.posterior_mean_coef2_test, sigma], dim=1)
         # first input: cat([y_cond, y_t]) (every later one comes out of the step kernel)
         x = cond_in.first_input(y_cond, y_t)
-        ret_arr = y_t
+        ret_arr = [y_t]
         for i in reversed(range(T)):
-            gam = model.gammas_test[i].reshape(1, 1).expand(b, 1)
+            gam = model.gammas_test[i].reshape(1, 1).expand(bq, 1)
             eps = self.denoise_fn.forward_nhwc(cond_in.fill(x), cond_in.embedding(self.compute_gammas(gam)), ref_p)
-            noise = noise_fn(i, tuple(y_t.shape)).contiguous().float() if i > 0 else None
+            noise = self._fold(noise_fn(i, shape_out)).contiguous().float() if i > 0 else None
             coef = table[i].reshape(1, 5).expand(b, 5).contiguous()
             y_t, x = K.ddpm_step(eps, y_t, y_cond, y_0, mask, noise, coef, ld=ld, want_next_input=i > 0)
             if i % sample_inter == 0:
-                ret_arr = torch.cat([ret_arr, y_t], dim=0)
-        return y_t, ret_arr
+                ret_arr.append(y_t)
+        return y_t.reshape(shape_out), torch.cat([r.reshape(shape_out) for r in ret_arr], dim=0)
+
+    @staticmethod
+    def _fold(v):
+        """[B, F, ...] -> [B*F, ...] for 5-D tensors, anything else unchanged"""
+        return v.reshape((v.shape[0] * v.shape[1],) + tuple(v.shape[2:])) if (v is not None and v.dim() == 5) else v
+
+    def _fold_clip(self, y_cond, cls, mask):
+        """frames per clip (0 for images); tells the video UNet how many frames its temporal layers see"""
+        if y_cond.dim() != 5:
+            return 0
+        if getattr(self.denoise_fn, "conditioning", ""):
+            raise NotImplementedError("B200 samplers: class / mask conditioning with video clips")
+        frames = y_cond.shape[1]
+        self.denoise_fn.model._clip["frames"] = frames
+        return frames
 
     @torch.no_grad()
     def restoration_ddim(self, y_cond, y_t=None, y_0=None, mask=None, sample_num=8, cls=None, guidance_scale=0.0,
@@ -845,9 +867,14 @@ class DiffusionGenerator(nn.Module):
         T = model.num_timesteps_test
         assert T > sample_num, "num_timesteps must greater than sample_num"
         sample_inter = T // sample_num
+        self._fold_clip(y_cond, cls, mask)
+        bq = y_cond.shape[0]
+        y_t = torch.randn_like(y_cond) if y_t is None else y_t
+        shape_out = tuple(y_t.shape)
+        y_cond, y_t, y_0, mask = (self._fold(v) for v in (y_cond, y_t, y_0, mask))
         b = y_cond.shape[0]
         y_cond = y_cond.contiguous().float()
-        y_t = (torch.randn_like(y_cond) if y_t is None else y_t).contiguous().float()
+        y_t = y_t.contiguous().float()
         c = y_t.shape[1]
         if mask is not None:
             y_0 = y_0.contiguous().float()
@@ -855,7 +882,7 @@ class DiffusionGenerator(nn.Module):
         ld = (y_cond.shape[1] + c + cond_in.extra + 7) // 8 * 8
         tseq = list(np.linspace(0, T - 1, num_steps).astype(int))
         x = cond_in.first_input(y_cond, y_t)
-        ret_arr = y_t
+        ret_arr = [y_t]
         for i in range(num_steps):
             t = int(tseq[-1 - i])
             prevt = int(tseq[-2 - i]) if i != num_steps - 1 else -1
@@ -867,12 +894,12 @@ class DiffusionGenerator(nn.Module):
             c2 = coef_eps - torch.sqrt(g_p) * torch.sqrt(1.0 - g_t) / torch.sqrt(g_t)
             coef = torch.stack([c1, c2, c1 * 0, c1 * 0, c1 * 0]).reshape(1, 5).expand(b, 5).contiguous().float()
             eps = self.denoise_fn.forward_nhwc(cond_in.fill(x),
-                                               cond_in.embedding(self.compute_gammas(g_t.reshape(1, 1).expand(b, 1))), ref_p)
+                                               cond_in.embedding(self.compute_gammas(g_t.reshape(1, 1).expand(bq, 1))), ref_p)
             y_t, x = K.ddpm_step(eps, y_t, y_cond, y_0, mask, None, coef, ld=ld, want_next_input=i != num_steps - 1,
                                  ddim=True)
             if i % sample_inter == 0:
-                ret_arr = torch.cat([ret_arr, y_t], dim=0)
-        return y_t, ret_arr
+                ret_arr.append(y_t)
+        return y_t.reshape(shape_out), torch.cat([r.reshape(shape_out) for r in ret_arr], dim=0)
 
     def restoration(self, y_cond, y_t=None, y_0=None, mask=None, sample_num=8, cls=None, ref=None,
                     guidance_scale=0.0, ddim_num_steps=10, ddim_eta=0.5):

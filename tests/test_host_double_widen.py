@@ -210,3 +210,33 @@ def test_reference_palette_model_cfg4_cfg5_trains_with_accelerated_generator(gol
         assert abs(float(sd[k].double().norm()) - n) <= 2e-2 * n + 1e-6, k
     for k, (_, n) in gold["ema_stats"].items():
         assert abs(float(ema[k].double().norm()) - n) <= 2e-2 * n + 1e-6, k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("which", ["ref", "vid"])
+def test_reference_inference_cfg4_cfg5_with_accelerated_generator(which):
+    """PaletteModel.inference for the reference-image UNet (its `use_ref` branch: restoration(..., ref=cur_ref)) and for
+    video clips (5-D y_cond / y_t / mask: B*F frames through the UNet and the step kernel, one noise level per clip, the
+    draws in the reference's 5-D shape) on the accelerated generator == the reference's own sampling, same seeds."""
+    import contextlib
+    from oracle import ref_stubs
+    ref_stubs.install()
+    from oracle import gen_golden_plumbing45 as P
+    from models.modules.diffusion_utils import set_new_noise_schedule
+    import joligen_b200
+    outs = []
+    for fast in (False, True):
+        model, _, _, _, _ = P.create_reference_model(which)
+        model.netG_A.denoise_fn.model.beta_schedule["test"]["n_timestep"] = 6
+        set_new_noise_schedule(model.netG_A.denoise_fn.model, "test")
+        if fast:
+            model.netG_A = joligen_b200.accelerate(model.netG_A)
+        torch.manual_seed(7)
+        model.set_input(dict(P.batch(which, 200), A_img_paths=["a"] * P.BATCH,
+                             B_label_cls=torch.zeros(P.BATCH, dtype=torch.long)))
+        with (KD.installed() if fast else contextlib.nullcontext()), torch.no_grad():
+            torch.manual_seed(8)
+            model.inference(2)
+        outs.append(model.fake_B.clone())
+    assert outs[0].shape == outs[1].shape and outs[0].dim() == (5 if which == "vid" else 4)
+    assert rel_l2(outs[1], outs[0]) < 3e-2, rel_l2(outs[1], outs[0])
