@@ -240,3 +240,45 @@ def test_reference_inference_cfg4_cfg5_with_accelerated_generator(which):
         outs.append(model.fake_B.clone())
     assert outs[0].shape == outs[1].shape and outs[0].dim() == (5 if which == "vid" else 4)
     assert rel_l2(outs[1], outs[0]) < 3e-2, rel_l2(outs[1], outs[0])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("cond", ["class", "class_mask"])
+def test_reference_palette_model_with_conditioning_trains_with_accelerated_generator(cond):
+    """--alg_diffusion_cond_embed class / class_mask (example_ddpm_mario.json ships `class`) through the reference's own
+    optimize_parameters(): B_label_cls / the semantic mask reach the accelerated generator's label embeddings; two steps
+    of the accelerated model == two steps of the untouched one, same seeds."""
+    import contextlib
+    import copy
+    from oracle import ref_stubs
+    ref_stubs.install()
+    from oracle import gen_golden
+    from oracle import palette_oracle as O
+    import joligen_b200
+    losses = []
+    for fast in (False, True):
+        torch.manual_seed(3)
+        model, _ = gen_golden.create_reference_model(32, 2, extra={"alg_diffusion_cond_embed": cond,
+                                                                   "f_s_semantic_nclasses": 4, "cls_semantic_nclasses": 4,
+                                                                   "alg_diffusion_dropout_prob": 0.0})
+        with torch.no_grad():   # de-zero the reference's zero-initialised convolutions
+            g = torch.Generator().manual_seed(11)
+            for p in model.netG_A.parameters():
+                if float(p.abs().max()) == 0.0:
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+        if fast:
+            model.netG_A = joligen_b200.accelerate(model.netG_A)
+            assert model.netG_A.denoise_fn.conditioning == cond
+        ls = []
+        with (KD.installed() if fast else contextlib.nullcontext()):
+            for step in range(2):
+                data = O.synthetic_batch(2, 32, 100 + step)
+                mask = (data["mask"] * torch.tensor([1, 2]).view(2, 1, 1, 1)).long()
+                model.set_input({"A": data["cond"], "B": data["gt"], "B_label_mask": mask,
+                                 "B_label_cls": torch.tensor([1, 2]), "A_img_paths": ["a"] * 2})
+                torch.manual_seed(1000 + step)
+                model.optimize_parameters()
+                ls.append(float(model.loss_G_tot.detach()))
+        losses.append(ls)
+    for got, want in zip(losses[1], losses[0]):
+        assert abs(got - want) < 2e-2 * abs(want), losses
