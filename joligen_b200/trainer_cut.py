@@ -53,9 +53,10 @@ class CutTrainer:
         self.niter = 0
         self.loss_G_tot = self.loss_G_GAN = self.loss_G_NCE = self.loss_G_NCE_Y = self.loss_D_tot = None
         # CUDA-graph replay of the whole step (both optimizer groups): ~3 900 small launches per step are launch-bound
-        # when issued from Python.  EXPERIMENTAL, off by default: on the B200 the capture of the (G, F) backward currently
-        # ends in cudaErrorStreamCaptureImplicit (an autograd gradient accumulation reaches the legacy stream;
-        # profiles/r02_cut_graph_capture_error.log) — the eager path is the tested one.  Single process only.
+        # when issued from Python.  EXPERIMENTAL, off by default: the one capture attempted on a B200 ended in
+        # cudaErrorStreamCaptureImplicit (profiles/r02_cut_graph_capture_error.log) — the stored, un-detached losses kept
+        # the warm-up's autograd graph and its default-stream AccumulateGrad nodes alive; they are detached now, but the
+        # capture has NOT been re-run on hardware since.  The eager path is the tested one.  Single process only.
         self.use_graph = bool(cuda_graph) and process_group is None
         self.graph_warmup = int(graph_warmup)
         self._graph = None
@@ -162,7 +163,12 @@ class CutTrainer:
         loss_G.backward()
         self.optG.apply(self.pg)
         self.optF.apply(self.pg)
+        # keep VALUES only: a stored loss with its graph keeps the whole iteration's autograd graph alive — memory, and
+        # the AccumulateGrad nodes of the eager warm-up (made on the default stream) would be reused inside a later
+        # CUDA-graph capture (cudaErrorStreamCaptureImplicit, profiles/r02_cut_graph_capture_error.log)
         self.loss_G_tot = loss_G.detach()
+        self.loss_G_GAN, self.loss_G_NCE = self.loss_G_GAN.detach(), self.loss_G_NCE.detach()
+        self.loss_G_NCE_Y = self.loss_G_NCE_Y.detach()
         # ---- D group
         self.set_requires_grad(self.netD_B, True)
         self.optD.flat.rebind_grads()
@@ -172,4 +178,5 @@ class CutTrainer:
         loss_D.backward()
         self.optD.apply(self.pg)
         self.loss_D_tot = loss_D.detach()
+        self.fake_B = fake_B.detach()
         return self.loss_G_tot, self.loss_D_tot
