@@ -94,4 +94,5 @@ class GanTrainer:
         loss_D.backward()
         self.optD.apply(self.pg)
         self.loss_D_tot = loss_D.detach()
+        self.fake_B = fake.detach()   # the value only: the generator's graph is not kept across steps
         return self.loss_G_tot, self.loss_D_tot
