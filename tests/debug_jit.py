@@ -1,4 +1,5 @@
-"""Stage-by-stage comparison of nets_jit.JiTViD with the oracle on the jit_b200 golden inputs (debug aid)."""
+"""Debug aid (test infrastructure: it lives under tests/ because it calls the oracle).  Stage-by-stage comparison of
+nets_jit.JiTViD with the oracle on the jit_b200 golden inputs.        python tests/debug_jit.py"""
 import os
 import sys
 
