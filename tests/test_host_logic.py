@@ -112,3 +112,25 @@ def test_no_undefined_names_in_the_package():
     for f in files:
         bad += ["%s:%d %s" % (os.path.relpath(f, root), line, name) for line, name in mod.check_source(open(f).read(), f)]
     assert not bad, bad
+
+
+def test_checkers_are_imported_only_where_the_contract_allows():
+    """oracle/ (the CPU restatement) and tests/kernel_double.py are CHECKERS: only tests/, __graft_entry__.smoke() and
+    bench.py's CPU-baseline legs may import them — never the product package, the tools, or the reference arm's runner."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    allowed = {"bench.py", "__graft_entry__.py"}
+    bad = []
+    for f in glob.glob(os.path.join(root, "**", "*.py"), recursive=True):
+        rel = os.path.relpath(f, root)
+        if rel.startswith(("tests" + os.sep, "oracle" + os.sep, "baseline" + os.sep + "_ref")) or rel in allowed:
+            continue
+        src = open(f).read()
+        if re.search(r"^\s*(from|import)\s+(oracle|kernel_double)\b", src, re.M):
+            bad.append(rel)
+    assert not bad, bad
+    # the product package never mentions the double
+    for f in glob.glob(os.path.join(root, "joligen_b200", "*.py")):
+        assert "kernel_double" not in open(f).read(), f
