@@ -220,8 +220,11 @@ def _resnet_generator_from_reference(ref):
     if not enc_convs or not dec_convs:
         raise NotImplementedError("accelerate: ResnetGenerator without plain nn.Conv2d stem / head (mobile variant)")
     n_blocks = sum(type(m).__name__ == "ResnetBlock" for m in ref.encoder.model)
+    # --G_padding_type: the pad layer in front of the decoder's 7x7 convolution (none = "zeros")
+    kinds = {type(m).__name__ for m in ref.decoder.model}
+    padding_type = "reflect" if "ReflectionPad2d" in kinds else ("replicate" if "ReplicationPad2d" in kinds else "zeros")
     new = nets_gan.ResnetGenerator(enc_convs[0].in_channels, dec_convs[-1].out_channels, enc_convs[0].out_channels,
-                                   n_blocks=n_blocks)
+                                   n_blocks=n_blocks, padding_type=padding_type)
     _same_layers(new.encoder.model, ref.encoder.model, "ResnetGenerator encoder")
     _same_layers(new.decoder.model, ref.decoder.model, "ResnetGenerator decoder")
     return new

@@ -60,6 +60,8 @@ class _SeqRunner:
             consumed = 1
             if isinstance(m, nn.ReflectionPad2d):
                 x = ops.reflection_pad(x, m.padding[0])
+            elif isinstance(m, nn.ReplicationPad2d):
+                x = ops.replication_pad(x, m.padding[0])
             elif isinstance(m, nn.Conv2d):
                 act = _act_code(nxt) if isinstance(nxt, (nn.LeakyReLU, nn.Tanh)) else None
                 x = ops.conv_act(x, m.weight, m.bias, self.pack(m), stride=m.stride[0], pad=m.padding[0],
@@ -102,6 +104,17 @@ def get_norm_layer(norm_type="instance"):
     raise NotImplementedError("B200 GAN path: norm %r (instance is implemented)" % norm_type)
 
 
+def _pad_layers(padding_type, n):
+    """--G_padding_type (resnet_generator.py:42-50, 328-336) -> ([pad layer], conv padding)"""
+    if padding_type == "reflect":
+        return [nn.ReflectionPad2d(n)], 0
+    if padding_type == "replicate":
+        return [nn.ReplicationPad2d(n)], 0
+    if padding_type == "zeros":
+        return [], n
+    raise NotImplementedError("padding [%s] is not implemented" % padding_type)
+
+
 def _uses_bias(norm_layer):
     f = norm_layer.func if isinstance(norm_layer, functools.partial) else norm_layer
     return f == nn.InstanceNorm2d
@@ -110,12 +123,13 @@ def _uses_bias(norm_layer):
 class ResnetBlock(nn.Module):
     def __init__(self, dim, padding_type, norm_layer, use_dropout, use_bias, use_spectral=False, conv=nn.Conv2d):
         super().__init__()
-        if padding_type != "reflect" or use_dropout or use_spectral:
-            raise NotImplementedError("B200 ResnetBlock: reflect padding, no dropout / spectral norm")
+        if use_dropout or use_spectral:
+            raise NotImplementedError("B200 ResnetBlock: no dropout / spectral norm")
+        pad, p = _pad_layers(padding_type, 1)
+        pad2, _ = _pad_layers(padding_type, 1)
         self.conv_block = nn.Sequential(
-            nn.ReflectionPad2d(1), nn.Conv2d(dim, dim, kernel_size=3, padding=0, bias=use_bias), norm_layer(dim),
-            nn.ReLU(True),
-            nn.ReflectionPad2d(1), nn.Conv2d(dim, dim, kernel_size=3, padding=0, bias=use_bias), norm_layer(dim))
+            *pad, nn.Conv2d(dim, dim, kernel_size=3, padding=p, bias=use_bias), norm_layer(dim), nn.ReLU(True),
+            *pad2, nn.Conv2d(dim, dim, kernel_size=3, padding=p, bias=use_bias), norm_layer(dim))
 
 
 class ResnetEncoder(nn.Module):
@@ -147,9 +161,8 @@ class ResnetDecoder(nn.Module):
             model += [nn.ConvTranspose2d(ngf * mult, ngf * mult // 2, kernel_size=3, stride=2, padding=1,
                                          output_padding=1, bias=use_bias),
                       norm_layer(ngf * mult // 2), nn.ReLU(True)]
-        if padding_type != "reflect":
-            raise NotImplementedError("B200 ResnetDecoder: reflect padding only")
-        model += [nn.ReflectionPad2d(3), nn.Conv2d(ngf, output_nc, kernel_size=7, padding=0), nn.Tanh()]
+        pad, p = _pad_layers(padding_type, 3)
+        model += pad + [nn.Conv2d(ngf, output_nc, kernel_size=7, padding=p), nn.Tanh()]
         self.model = nn.Sequential(*model)
 
 

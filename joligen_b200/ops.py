@@ -760,14 +760,16 @@ class ConvTranspose2dFn(torch.autograd.Function):
 
 
 class Pad2dFn(torch.autograd.Function):
+    """nn.ReflectionPad2d (mode 0) / nn.ReplicationPad2d (mode 1)"""
+
     @staticmethod
-    def forward(ctx, x, pad):
-        ctx.pad = pad
-        return K.pad2d(x, pad, 0)
+    def forward(ctx, x, pad, mode=0):
+        ctx.pad, ctx.mode = pad, mode
+        return K.pad2d(x, pad, mode)
 
     @staticmethod
     def backward(ctx, d):
-        return K.pad2d_bwd(d.contiguous(), ctx.pad, 0), None
+        return K.pad2d_bwd(d.contiguous(), ctx.pad, ctx.mode), None, None
 
 
 class AddFn(torch.autograd.Function):
@@ -809,7 +811,11 @@ def conv_transpose2d(x, weight, bias, packed, pad=1):
 
 
 def reflection_pad(x, pad):
-    return Pad2dFn.apply(x, pad)
+    return Pad2dFn.apply(x, pad, 0)
+
+
+def replication_pad(x, pad):
+    return Pad2dFn.apply(x, pad, 1)
 
 
 def add(a, b):

@@ -604,3 +604,39 @@ def test_train_launcher_hook_accelerates_the_models_train_py_creates():
     finally:
         ref_train.create_model, models.create_model = saved
         ref_train._jg_hooked = False
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("padding_type", ["replicate", "zeros"])
+def test_accelerate_resnet_generator_padding_types(padding_type):
+    """--G_padding_type replicate / zeros (resnet_generator.py:42-50, 328-336): accelerate() reads it off the layers,
+    the mirror runs nn.ReplicationPad2d through jg_pad2d (mode 1) / the zero padding inside the convolution — output,
+    encoder features and input gradient vs the reference module itself."""
+    import copy
+    import functools
+    from oracle import ref_stubs
+    ref_stubs.install()
+    import torch.nn as nn
+    from models.modules.resnet_architecture.resnet_generator import ResnetGenerator
+    import joligen_b200
+    from joligen_b200 import nets_gan
+    from oracle import gan_oracle as G
+    norm = functools.partial(nn.InstanceNorm2d, affine=False, track_running_stats=False)
+    ref = ResnetGenerator(3, 3, 16, norm_layer=norm, use_dropout=False, n_blocks=2, padding_type=padding_type)
+    seeded = list(G.init_from_shapes(G.resnet_param_shapes(3, 3, 16, 2), 77).values())
+    ref.load_state_dict(dict(zip(ref.state_dict().keys(), seeded)))   # (the layer indices shift without pad layers)
+    fast = joligen_b200.accelerate(copy.deepcopy(ref))
+    assert isinstance(fast, nets_gan.ResnetGenerator)
+    assert [type(m).__name__ for m in fast.decoder.model] == [type(m).__name__ for m in ref.decoder.model]
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(1))
+    xr, xf = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    yr = ref(xr)
+    dy = torch.randn(yr.shape, generator=torch.Generator().manual_seed(2))
+    yr.backward(dy)
+    with KD.installed():
+        yf = fast(xf)
+        assert rel_l2(yf, yr) < 3e-2
+        yf.backward(dy)
+        for a, b in zip(fast.get_feats(x, [0, 4, 8, 11]), ref.get_feats(x, [0, 4, 8, 11])):
+            assert tuple(a.shape) == tuple(b.shape) and rel_l2(a, b) < 3e-2
+    assert rel_l2(xf.grad, xr.grad) < 0.3   # (InstanceNorm backward under bf16 storage: see the floor tests above)
