@@ -121,5 +121,29 @@ class B2BTrainer:
     def params(self):
         return self.flat.unflatten(self.flat.data)
 
+    def state_dict(self):
+        """What a resumed run needs beyond net.state_dict(): Adam moments, step counter, EMA copy (by parameter name)."""
+        sd = {"step": self.step, "ema_started": self.ema_started,
+              "exp_avg": {k: v.clone() for k, v in self.flat.unflatten(self.exp_avg).items()},
+              "exp_avg_sq": {k: v.clone() for k, v in self.flat.unflatten(self.exp_avg_sq).items()}}
+        if self.ema is not None:
+            sd["ema"] = {k: v.clone() for k, v in self.flat.unflatten(self.ema).items()}
+        return sd
+
+    def load_state_dict(self, sd):
+        for name, flat in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq), ("ema", self.ema)):
+            if flat is None or name not in sd:
+                continue
+            views = self.flat.unflatten(flat)
+            missing = set(views) - set(sd[name])
+            if missing:
+                raise KeyError("B2BTrainer.load_state_dict: %s lacks %s" % (name, sorted(missing)[:3]))
+            for k, v in views.items():
+                v.copy_(sd[name][k])
+        self.step = int(sd["step"])
+        self.ema_started = bool(sd.get("ema_started", self.step > 0))
+        self.step_dev.fill_(self.step)
+        nets.invalidate_packed_weights()
+
     def ema_state_dict(self):
         return self.flat.unflatten(self.ema) if self.ema is not None else None

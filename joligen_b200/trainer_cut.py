@@ -138,6 +138,17 @@ class CutTrainer:
     def eager_step(self):
         return self._step(None, None)
 
+    def state_dict(self):
+        """optimizer-side state of the three groups (the nets' weights travel in their own state_dicts)"""
+        return {"niter": self.niter, "G": self.optG.state_dict(), "F": self.optF.state_dict(), "D": self.optD.state_dict()}
+
+    def load_state_dict(self, sd):
+        if self._graph is not None:
+            raise RuntimeError("CutTrainer.load_state_dict after the CUDA graph was captured")
+        self.niter = int(sd["niter"])
+        for key, opt in (("G", self.optG), ("F", self.optF), ("D", self.optD)):
+            opt.load_state_dict(sd[key])
+
     def _step(self, patch_ids_A=None, patch_ids_B=None):
         self.niter += 1
         a = ops.to_nhwc(self.real_A)

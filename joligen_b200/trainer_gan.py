@@ -42,6 +42,29 @@ class _FlatAdam:
         self.flat.grad.zero_()
         nets.invalidate_packed_weights()
 
+    # -- checkpoint state beyond the net's own state_dict (base_model.save_networks :824-868 stores the nets AND the
+    #    optimizers): Adam moments, step counters, the EMA copy, keyed by parameter name ---------------------------------
+    def state_dict(self):
+        sd = {"step": self.step, "exp_avg": {k: v.clone() for k, v in self.flat.unflatten(self.m).items()},
+              "exp_avg_sq": {k: v.clone() for k, v in self.flat.unflatten(self.v).items()}}
+        if self.ema is not None:
+            sd["ema"] = {k: v.clone() for k, v in self.flat.unflatten(self.ema).items()}
+        return sd
+
+    def load_state_dict(self, sd):
+        for name, flat in (("exp_avg", self.m), ("exp_avg_sq", self.v), ("ema", self.ema)):
+            if flat is None or name not in sd:
+                continue
+            views = self.flat.unflatten(flat)
+            missing = set(views) - set(sd[name])
+            if missing:
+                raise KeyError("load_state_dict: %s lacks %s" % (name, sorted(missing)[:3]))
+            for k, v in views.items():
+                v.copy_(sd[name][k])
+        self.step = int(sd["step"])
+        self.step_dev.fill_(self.step)
+        nets.invalidate_packed_weights()
+
 
 class GanTrainer:
     def __init__(self, netG_A, netD_B, gan_mode="lsgan", lambda_gan=1.0, G_lr=2e-4, D_lr=1e-4, beta1=0.9, beta2=0.999,
@@ -96,3 +119,12 @@ class GanTrainer:
         self.loss_D_tot = loss_D.detach()
         self.fake_B = fake.detach()   # the value only: the generator's graph is not kept across steps
         return self.loss_G_tot, self.loss_D_tot
+
+    def state_dict(self):
+        """optimizer-side state of both groups (the nets' weights travel in their own state_dicts)"""
+        return {"niter": self.niter, "G": self.optG.state_dict(), "D": self.optD.state_dict()}
+
+    def load_state_dict(self, sd):
+        self.niter = int(sd["niter"])
+        self.optG.load_state_dict(sd["G"])
+        self.optD.load_state_dict(sd["D"])

@@ -241,3 +241,37 @@ def test_gan_trainer_matches_oracle_on_the_double():
             rg, rd = G.gan_train_step(sG, sD, ocG, ocD, a, b, n_blocks=nb)
             assert abs(float(lg) - float(rg)) < 3e-2 * abs(float(rg)), (step, float(lg), float(rg))
             assert abs(float(ld) - float(rd)) < 3e-2 * abs(float(rd)), (step, float(ld), float(rd))
+
+
+def test_cut_trainer_checkpoint_resume_is_exact(golden_dir):
+    """nets' state_dicts + CutTrainer.state_dict() into FRESH nets / a fresh trainer continue exactly like the
+    uninterrupted run (Adam moments and step counters of the G, F and D groups)."""
+    from oracle.gen_golden_cut_plumbing import batch, patch_ids
+
+    def step(tr, hw, seed):
+        a, b = batch(seed)
+        ids_a, ids_b = patch_ids(seed + 1, hw)
+        tr.set_input({"A": a, "B": b})
+        tr.optimize_parameters(patch_ids_A=ids_a, patch_ids_B=ids_b)
+        return float(tr.loss_G_tot), float(tr.loss_D_tot)
+
+    with KD.installed():
+        gold, tr, nets_ = _build(golden_dir, "cut_plumbing_patchnce.pt")
+        hw = gold["cut"]["hw"]
+        for s in (500, 510):
+            step(tr, hw, s)
+        saved = [{k: v.clone() for k, v in n.state_dict().items()} for n in nets_], tr.state_dict()
+        want = step(tr, hw, 520)
+        _, tr2, nets2 = _build(golden_dir, "cut_plumbing_patchnce.pt")
+        with torch.no_grad():
+            for n in nets2:
+                for p in n.parameters():
+                    p.mul_(1.01)     # start elsewhere: everything must come from the checkpoint
+        for n, sd in zip(nets2, saved[0]):
+            n.load_state_dict(sd)
+        tr2.load_state_dict(saved[1])
+        got = step(tr2, hw, 520)
+        assert got == want
+        for n, m in zip(nets_, nets2):
+            for (k, v), (_, w) in zip(n.state_dict().items(), m.state_dict().items()):
+                assert torch.equal(v, w), k

@@ -230,3 +230,30 @@ def test_reference_b2b_inference_with_accelerated_generator():
             model.inference(2)
         outs.append(model.fake_B.clone())
     assert outs[0].shape == outs[1].shape and rel(outs[1], outs[0]) < 3e-2, rel(outs[1], outs[0])
+
+
+def test_b2b_trainer_checkpoint_resume_is_exact(golden_dir):
+    from oracle.gen_golden_jit import inputs
+
+    def step(tr, cfg, gold, seed):
+        gt, cond, mask, _ = inputs(cfg, gold["batch"], gold["frames"], seed)
+        torch.manual_seed(seed)
+        t_base, e = torch.sigmoid(torch.randn(gold["batch"]) * 0.8 - 0.8), torch.randn_like(gt)
+        tr.set_input({"A": cond, "B": gt, "B_label_mask": mask})
+        return float(tr.optimize_parameters(t_base=t_base, e=e))
+
+    with KD.installed():
+        gold, cfg, net = _small_net(golden_dir)
+        tr = _b2b_trainer(net, lr=1e-3, ema_beta=0.9, use_cond=True)
+        for s in (40, 41):
+            step(tr, cfg, gold, s)
+        net_sd, tr_sd = {k: v.clone() for k, v in net.state_dict().items()}, tr.state_dict()
+        want = step(tr, cfg, gold, 42)
+        _, _, net2 = _small_net(golden_dir)
+        tr2 = _b2b_trainer(net2, lr=1e-3, ema_beta=0.9, use_cond=True)
+        with torch.no_grad():
+            tr2.flat.data.mul_(1.01)
+        net2.load_state_dict(net_sd)
+        tr2.load_state_dict(tr_sd)
+        assert step(tr2, cfg, gold, 42) == want
+        assert torch.equal(tr.flat.data, tr2.flat.data) and torch.equal(tr.ema, tr2.ema) and tr.step == tr2.step == 3
