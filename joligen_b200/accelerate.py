@@ -233,12 +233,12 @@ def _resnet_generator_from_reference(ref):
 def _nlayer_discriminator_from_reference(ref):
     """models/modules/discriminators.py:10-117 (gan_networks.define_D, D_netDs basic / n_layers)."""
     from . import nets_gan
-    if getattr(ref, "freq_space", False):
-        raise NotImplementedError("accelerate: NLayerDiscriminator in wavelet space (D_freq_space)")
+    freq = bool(getattr(ref, "freq_space", False))
     convs = [m for m in ref.model if isinstance(m, nn.Conv2d)]
     if len(convs) < 3:
         raise NotImplementedError("accelerate: NLayerDiscriminator with %d convolutions" % len(convs))
-    new = nets_gan.NLayerDiscriminator(convs[0].in_channels, convs[0].out_channels, n_layers=len(convs) - 2)
+    new = nets_gan.NLayerDiscriminator(convs[0].in_channels // (4 if freq else 1), convs[0].out_channels,
+                                       n_layers=len(convs) - 2, freq_space=freq)
     _same_layers(new.model, ref.model, "NLayerDiscriminator")
     return new
 

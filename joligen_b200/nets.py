@@ -223,15 +223,49 @@ class EmbedSequential(nn.Sequential, EmbedBlock):
         return None if c is None else (h, w, (c + 7) // 8 * 8)
 
 
-class _Resample(nn.Module):
-    """Upsample / Downsample with use_conv=False (what ResBlock(up=/down=) instantiates)."""
+class _Haar(nn.Module):
+    """freq_utils.HaarTransform / InverseHaarTransform (:21-59): holds the reference's four 2x2 filter buffers (they are
+    part of its state_dict); the transform itself is jg_haar on fp32 NCHW tensors (csrc/prep.cu, bit-exact taps)."""
 
-    def __init__(self, up):
+    def __init__(self, inverse):
+        super().__init__()
+        self.inverse = inverse
+        s = 1 / (2 ** 0.5)
+        low, high = s * torch.ones(1, 2), s * torch.ones(1, 2)
+        high[0, 0] = -high[0, 0]
+        sign = -1.0 if inverse else 1.0
+        self.register_buffer("ll", low.T * low)
+        self.register_buffer("lh", sign * (high.T * low))
+        self.register_buffer("hl", sign * (low.T * high))
+        self.register_buffer("hh", high.T * high)
+
+    def forward(self, x):
+        return ops.haar_iwt(x) if self.inverse else ops.haar_dwt(x)
+
+
+class _Resample(nn.Module):
+    """Upsample / Downsample with use_conv=False (what ResBlock(up=/down=) instantiates).  freq_space
+    (--train_feat_wavelet, :69-96, 113-140): the tensor holds the four Haar bands of a 2x larger map with C/4 channels;
+    resampling happens in pixel space: inverse transform -> resample -> transform."""
+
+    def __init__(self, up, freq_space=False, channels=None):
         super().__init__()
         self.up = up
+        self.freq_space = freq_space
+        self.channels = channels
+        if freq_space:
+            if channels is None or channels % 4:
+                raise ValueError("freq_space resampling needs a channel count that is a multiple of 4")
+            self.iwt = _Haar(True)
+            self.dwt = _Haar(False)
 
     def forward_nhwc(self, x):
-        return ops.upsample2x(x) if self.up else ops.avgpool2x(x)
+        if not self.freq_space:
+            return ops.upsample2x(x) if self.up else ops.avgpool2x(x)
+        # (a composition of existing kernels through the fp32 NCHW layout the Haar kernel takes: correct, not tuned)
+        pix = ops.to_nhwc(self.iwt(ops.to_nchw(x, self.channels)))
+        pix = ops.upsample2x(pix) if self.up else ops.avgpool2x(pix)
+        return ops.to_nhwc(self.dwt(ops.to_nchw(pix, self.channels // 4)))
 
 
 class ConvIn(nn.Conv2d):
@@ -255,8 +289,8 @@ class ResBlock(EmbedBlock):
                  use_scale_shift_norm=False, use_checkpoint=False, up=False, down=False, efficient=False,
                  freq_space=False):
         super().__init__()
-        if freq_space or use_conv or use_checkpoint:
-            raise NotImplementedError("B200 ResBlock: freq_space / use_conv / use_checkpoint are not supported")
+        if use_conv or use_checkpoint:
+            raise NotImplementedError("B200 ResBlock: use_conv / use_checkpoint are not supported")
         if dropout:
             raise NotImplementedError("B200 ResBlock: dropout > 0 is not supported")
         self.channels = channels
@@ -268,9 +302,10 @@ class ResBlock(EmbedBlock):
         self.efficient = efficient
         self.in_layers = nn.Sequential(normalization(channels, norm), nn.SiLU(),
                                        nn.Conv2d(channels, self.out_channel, 3, padding=1))
+        self.freq_space = freq_space
         if up or down:
-            self.h_upd = _Resample(up)
-            self.x_upd = _Resample(up)
+            self.h_upd = _Resample(up, freq_space, channels)
+            self.x_upd = _Resample(up, freq_space, channels)
         else:
             self.h_upd = self.x_upd = nn.Identity()
         self.emb_layers = nn.Sequential(
@@ -407,8 +442,9 @@ class UNet(nn.Module):
                  num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=True, resblock_updown=True,
                  use_new_attention_order=False, efficient=False, freq_space=False):
         super().__init__()
-        if tanh or freq_space or not resblock_updown or use_fp16:
-            raise NotImplementedError("B200 UNet: tanh / freq_space / conv resampling / fp16 are not supported")
+        if tanh or not resblock_updown or use_fp16:
+            raise NotImplementedError("B200 UNet: tanh / conv resampling / fp16 are not supported")
+        self.freq_space = freq_space
         if num_heads_upsample == -1:
             num_heads_upsample = num_heads
         self.image_size = image_size
@@ -421,9 +457,13 @@ class UNet(nn.Module):
         self.num_heads = num_heads
         self.num_head_channels = num_head_channels
         self.cond_embed_dim = cond_embed_dim
+        if freq_space:   # (:467-473) the layers work on the Haar bands of the input / output: 4x the channels at half
+            self.iwt = _Haar(True)   # the resolution (the attributes above keep the pixel-space counts, like the reference)
+            self.dwt = _Haar(False)
+            in_channel, out_channel = in_channel * 4, out_channel * 4
         if norm == "groupnorm":
             norm = norm + str(group_norm_size)
-        rb = dict(use_scale_shift_norm=use_scale_shift_norm, norm=norm, efficient=efficient)
+        rb = dict(use_scale_shift_norm=use_scale_shift_norm, norm=norm, efficient=efficient, freq_space=freq_space)
         ch = input_ch = int(channel_mults[0] * inner_channel)
         self.input_blocks = nn.ModuleList([EmbedSequential(ConvIn(in_channel, ch, 3, padding=1))])
         input_block_chans = [ch]
@@ -470,6 +510,13 @@ class UNet(nn.Module):
     # -- NHWC bf16 fast path -------------------------------------------------------------------
     def forward_nhwc(self, x, emb):
         """x: NHWC bf16 [N,H,W,round_up(in_channel,8)] -> NHWC bf16 [N,H,W,round_up(out_channel,8)]."""
+        if getattr(self, "freq_space", False):   # (:672, :692) Haar bands in, Haar bands out — through the fp32 NCHW layout of jg_haar
+            bands = ops.to_nhwc(self.dwt(ops.to_nchw(x, self.in_channel)))
+            out = self._forward_bands(bands, emb)
+            return ops.to_nhwc(self.iwt(ops.to_nchw(out, 4 * self.out_channel)))
+        return self._forward_bands(x, emb)
+
+    def _forward_bands(self, x, emb):
         # Skip tensors: every encoder output h_k is consumed by the next block AND by the decoder's concat.  The
         # decoder reads a hand-through ("tap") of h_k made by the next block's first GroupNorm, so the two gradients
         # meet inside that GroupNorm's backward pass instead of in a separate (strided) add kernel.
@@ -518,7 +565,7 @@ class UNet(nn.Module):
         if embed_gammas is None:
             embed_gammas = torch.ones((input.shape[0], self.cond_embed_dim), device=input.device)
         hs = []
-        h = ops.to_nhwc(input)
+        h = ops.to_nhwc(self.dwt(input.float()) if getattr(self, "freq_space", False) else input)
         for module in self.input_blocks:
             h = module.forward_nhwc(h, embed_gammas)
             hs.append(h)

@@ -206,8 +206,15 @@ class NLayerDiscriminator(nn.Module):
     def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=None, use_dropout=False, use_spectral=False,
                  freq_space=False):
         super().__init__()
-        if use_dropout or use_spectral or freq_space:
-            raise NotImplementedError("B200 NLayerDiscriminator: dropout / spectral / wavelet variants")
+        if use_dropout or use_spectral:
+            raise NotImplementedError("B200 NLayerDiscriminator: dropout / spectral variants")
+        self.freq_space = freq_space
+        self.input_nc = input_nc
+        if freq_space:   # (discriminators.py:40-46) the PatchGAN sees the four Haar bands of the image
+            from .nets import _Haar
+            self.iwt = _Haar(True)
+            self.dwt = _Haar(False)
+            input_nc *= 4
         norm_layer = norm_layer or get_norm_layer("instance")
         use_bias = _uses_bias(norm_layer)
         kw, padw = 4, 1
@@ -226,9 +233,13 @@ class NLayerDiscriminator(nn.Module):
 
     def forward_nhwc(self, x):
         """-> logits NHWC bf16 [N, h, w, 8] (channel 0 is the prediction, 1..7 are zero padding)."""
+        if self.freq_space:
+            x = ops.to_nhwc(self.dwt(ops.to_nchw(x, self.input_nc)))
         return self._runner.run(self.model, x)
 
     def forward(self, input):
+        if self.freq_space:
+            return ops.to_nchw(self._runner.run(self.model, ops.to_nhwc(self.dwt(input.float()))), 1)
         return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(input)), 1)
 
 

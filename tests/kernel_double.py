@@ -932,6 +932,24 @@ def mask_class_dropout(mask, drop_u, prob, fill):
     return torch.where(drop, torch.full_like(mask, fill), mask)
 
 
+
+def haar(x, mode):
+    """mode 0: DWT forward, 1: its backward, 2: IWT forward, 3: its backward (oracle/prep_oracle.py restates
+    freq_utils.HaarTransform / InverseHaarTransform, pinned on the reference's prep_small.pt)"""
+    from oracle import prep_oracle as P
+    x = x.contiguous().float()
+    if mode == 0:
+        return P.haar_dwt(x)
+    if mode == 2:
+        return P.haar_iwt(x)
+    n, c, h, w = x.shape
+    src = torch.zeros((n, c // 4, 2 * h, 2 * w) if mode == 1 else (n, 4 * c, h // 2, w // 2), requires_grad=True)
+    with torch.enable_grad():
+        y = P.haar_dwt(src) if mode == 1 else P.haar_iwt(src)
+    (d,) = torch.autograd.grad(y, src, x)
+    return d
+
+
 _JIT_DOUBLES = dict(rmsnorm_mod=_j_rmsnorm_mod, qknorm_rope=_j_qknorm_rope, attn_small=_j_attn_small, swiglu=_j_swiglu,
                     gated_residual=_j_gated_residual)
 
@@ -950,7 +968,7 @@ _DOUBLES = dict(pack_conv_weight=pack_conv_weight, conv2d_fwd=conv2d_fwd, chan_s
                 ddpm_step=ddpm_step, WeightTable=WeightTable, pack_conv_weights_batched=pack_conv_weights_batched,
                 wgrad_unpack_batched=wgrad_unpack_batched, gather_rows=gather_rows, gather_rows_bwd=gather_rows_bwd,
                 l2norm_fwd=l2norm_fwd, l2norm_bwd=l2norm_bwd, patch_nce_fwd=patch_nce_fwd, patch_nce_bwd=patch_nce_bwd,
-                monce_fwd=monce_fwd, monce_bwd=monce_bwd, mask_class_dropout=mask_class_dropout)
+                monce_fwd=monce_fwd, monce_bwd=monce_bwd, mask_class_dropout=mask_class_dropout, haar=haar)
 
 
 def _refuse(name):

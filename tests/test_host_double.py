@@ -162,8 +162,8 @@ def test_double_refuses_ops_it_does_not_restate():
     from joligen_b200 import kernels as K
     with KD.installed():
         with pytest.raises(AssertionError, match="no CPU restatement"):
-            K.haar(torch.zeros(1, 1, 2, 2), 0)
-    assert K.haar.__module__ == "joligen_b200.kernels"  # restored
+            K.fill_mask_random(torch.zeros(1, 1, 2, 2), torch.zeros(1, 1, 2, 2), torch.zeros(1, 1, 2, 2))
+    assert K.fill_mask_random.__module__ == "joligen_b200.kernels"  # restored
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -640,3 +640,67 @@ def test_accelerate_resnet_generator_padding_types(padding_type):
         for a, b in zip(fast.get_feats(x, [0, 4, 8, 11]), ref.get_feats(x, [0, 4, 8, 11])):
             assert tuple(a.shape) == tuple(b.shape) and rel_l2(a, b) < 3e-2
     assert rel_l2(xf.grad, xr.grad) < 0.3   # (InstanceNorm backward under bf16 storage: see the floor tests above)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_accelerate_wavelet_space_unet_vs_reference():
+    """--train_feat_wavelet (UNet(freq_space=True), unet_generator_attn.py:467-473, 69-96, 113-140): the net works on
+    the Haar bands of its input / output and resamples in pixel space (inverse transform -> resample -> transform).
+    The mirror composes jg_haar with the layout / resample kernels; accelerate() adopts the filter buffers — output and
+    input gradient vs the reference's own forward / backward."""
+    import copy
+    from oracle import ref_stubs
+    ref_stubs.install()
+    from models.modules.unet_generator_attn.unet_generator_attn import UNet
+    import joligen_b200
+    from joligen_b200 import nets
+    torch.manual_seed(0)
+    ref = UNet(image_size=32, in_channel=6, inner_channel=32, out_channel=3, res_blocks=[1, 1], attn_res=[2], tanh=False,
+               n_timestep_train=2000, n_timestep_test=1000, norm="groupnorm", group_norm_size=8, cond_embed_dim=32,
+               channel_mults=(1, 2), num_heads=1, num_head_channels=16, freq_space=True)
+    with torch.no_grad():
+        for p in ref.parameters():
+            if float(p.abs().max()) == 0.0:
+                p.normal_(0.0, 0.05)
+    keys = list(ref.state_dict().keys())
+    fast = joligen_b200.accelerate(copy.deepcopy(ref))
+    assert isinstance(fast, nets.UNet) and fast.freq_space and list(fast.state_dict().keys()) == keys
+    assert (fast.in_channel, fast.out_channel) == (ref.in_channel, ref.out_channel) == (6, 3)
+    x = torch.randn(1, 6, 32, 32)
+    emb = torch.randn(1, 32)
+    xr, xf = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    want = ref(xr, emb)
+    dy = torch.randn_like(want)
+    want.backward(dy)
+    with KD.installed():
+        got = fast(xf, emb)
+        assert tuple(got.shape) == tuple(want.shape) == (1, 3, 32, 32)
+        assert rel_l2(got, want) < 4e-2, rel_l2(got, want)
+        got.backward(dy)
+    assert rel_l2(xf.grad, xr.grad) < 0.1, rel_l2(xf.grad, xr.grad)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_accelerate_wavelet_space_discriminator_vs_reference():
+    """NLayerDiscriminator(freq_space=True) (discriminators.py:40-46, 112-117): the PatchGAN reads the Haar bands."""
+    import copy
+    import functools
+    from oracle import ref_stubs
+    ref_stubs.install()
+    import torch.nn as nn
+    from models.modules.discriminators import NLayerDiscriminator
+    import joligen_b200
+    from joligen_b200 import nets_gan
+    norm = functools.partial(nn.InstanceNorm2d, affine=False, track_running_stats=False)
+    torch.manual_seed(1)
+    ref = NLayerDiscriminator(3, 16, n_layers=3, norm_layer=norm, freq_space=True)
+    keys = list(ref.state_dict().keys())
+    fast = joligen_b200.accelerate(copy.deepcopy(ref))
+    assert isinstance(fast, nets_gan.NLayerDiscriminator) and fast.freq_space and list(fast.state_dict().keys()) == keys
+    x = torch.randn(2, 3, 128, 128)
+    want = ref(x)
+    with KD.installed():
+        got = fast(x)
+        from joligen_b200 import ops
+        got2 = ops.to_nchw(fast.forward_nhwc(ops.to_nhwc(x)), 1)     # the trainers' NHWC entry point
+    assert tuple(got.shape) == tuple(want.shape) and rel_l2(got, want) < 3e-2 and rel_l2(got2, want) < 3e-2
