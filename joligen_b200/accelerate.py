@@ -203,7 +203,8 @@ def _same_layers(dst_seq, src_seq, what):
     for d, r in zip(dst_seq.modules(), src_seq.modules()):
         if isinstance(r, (nn.Conv2d, nn.ConvTranspose2d)):
             if (r.kernel_size, r.stride, r.padding, r.dilation, r.groups) != \
-                    (d.kernel_size, d.stride, d.padding, d.dilation, d.groups) or hasattr(r, "weight_orig"):
+                    (d.kernel_size, d.stride, d.padding, d.dilation, d.groups) or \
+                    hasattr(r, "weight_orig") != hasattr(d, "weight_orig"):
                 raise NotImplementedError("accelerate: %s convolution geometry / parametrisation differs" % what)
         if isinstance(r, nn.InstanceNorm2d) and (r.affine or r.track_running_stats):
             raise NotImplementedError("accelerate: InstanceNorm2d with affine / running statistics")
@@ -238,7 +239,8 @@ def _nlayer_discriminator_from_reference(ref):
     if len(convs) < 3:
         raise NotImplementedError("accelerate: NLayerDiscriminator with %d convolutions" % len(convs))
     new = nets_gan.NLayerDiscriminator(convs[0].in_channels // (4 if freq else 1), convs[0].out_channels,
-                                       n_layers=len(convs) - 2, freq_space=freq)
+                                       n_layers=len(convs) - 2, freq_space=freq,
+                                       use_spectral=all(hasattr(c, "weight_orig") for c in convs))
     _same_layers(new.model, ref.model, "NLayerDiscriminator")
     return new
 

@@ -64,8 +64,14 @@ class _SeqRunner:
                 x = ops.replication_pad(x, m.padding[0])
             elif isinstance(m, nn.Conv2d):
                 act = _act_code(nxt) if isinstance(nxt, (nn.LeakyReLU, nn.Tanh)) else None
-                x = ops.conv_act(x, m.weight, m.bias, self.pack(m), stride=m.stride[0], pad=m.padding[0],
-                                 act=act if act is not None else L.ACT_NONE)
+                if hasattr(m, "weight_orig"):
+                    # torch's spectral_norm wrapper (--D_spectral): its pre-forward hook never runs here; one power
+                    # iteration + the normalised weight are parameter preprocessing (nets_projd._sn_weight)
+                    from .nets_projd import _sn_conv
+                    x = _sn_conv(x, m, act=act if act is not None else L.ACT_NONE)
+                else:
+                    x = ops.conv_act(x, m.weight, m.bias, self.pack(m), stride=m.stride[0], pad=m.padding[0],
+                                     act=act if act is not None else L.ACT_NONE)
                 if act is not None:
                     consumed = 2
             elif isinstance(m, nn.ConvTranspose2d):
@@ -206,8 +212,9 @@ class NLayerDiscriminator(nn.Module):
     def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=None, use_dropout=False, use_spectral=False,
                  freq_space=False):
         super().__init__()
-        if use_dropout or use_spectral:
-            raise NotImplementedError("B200 NLayerDiscriminator: dropout / spectral variants")
+        if use_dropout:
+            raise NotImplementedError("B200 NLayerDiscriminator: dropout")
+        sn = nn.utils.spectral_norm if use_spectral else (lambda conv: conv)   # (discriminators.py:51-108)
         self.freq_space = freq_space
         self.input_nc = input_nc
         if freq_space:   # (discriminators.py:40-46) the PatchGAN sees the four Haar bands of the image
@@ -218,16 +225,16 @@ class NLayerDiscriminator(nn.Module):
         norm_layer = norm_layer or get_norm_layer("instance")
         use_bias = _uses_bias(norm_layer)
         kw, padw = 4, 1
-        seq = [nn.Conv2d(input_nc, ndf, kernel_size=kw, stride=2, padding=padw), nn.LeakyReLU(0.2, True)]
+        seq = [sn(nn.Conv2d(input_nc, ndf, kernel_size=kw, stride=2, padding=padw)), nn.LeakyReLU(0.2, True)]
         nf_mult = 1
         for n in range(1, n_layers):
             nf_prev, nf_mult = nf_mult, min(2 ** n, 8)
-            seq += [nn.Conv2d(ndf * nf_prev, ndf * nf_mult, kernel_size=kw, stride=2, padding=padw, bias=use_bias),
+            seq += [sn(nn.Conv2d(ndf * nf_prev, ndf * nf_mult, kernel_size=kw, stride=2, padding=padw, bias=use_bias)),
                     norm_layer(ndf * nf_mult), nn.LeakyReLU(0.2, True)]
         nf_prev, nf_mult = nf_mult, min(2 ** n_layers, 8)
-        seq += [nn.Conv2d(ndf * nf_prev, ndf * nf_mult, kernel_size=kw, stride=1, padding=padw, bias=use_bias),
+        seq += [sn(nn.Conv2d(ndf * nf_prev, ndf * nf_mult, kernel_size=kw, stride=1, padding=padw, bias=use_bias)),
                 norm_layer(ndf * nf_mult), nn.LeakyReLU(0.2, True)]
-        seq += [nn.Conv2d(ndf * nf_mult, 1, kernel_size=kw, stride=1, padding=padw)]
+        seq += [sn(nn.Conv2d(ndf * nf_mult, 1, kernel_size=kw, stride=1, padding=padw))]
         self.model = nn.Sequential(*seq)
         self._runner = _SeqRunner()
 

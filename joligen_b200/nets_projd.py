@@ -10,9 +10,8 @@ path: 4x4 stride-2 implicit GEMM (the NLayerDiscriminator's), GroupNorm(c/2 grou
 matrix per step — is parameter preprocessing (two matrix-vector products per layer), done with torch ops on the device.
 The frozen timm feature network in front of MultiScaleD is third-party and stays the reference's.
 
-STATUS: written at the end of round 1; one run on a B200 (profiles/r01_cut_tests_first_run.log): logits, hinge loss and
-all parameter gradients match the reference's golden vectors; the feature-gradient bound is not calibrated yet
-(tests/test_gpu_widen_cut.py, `unverified` marker).
+Parity on the B200 (tests/test_gpu_widen_cut.py, no markers left): logits, hinge loss, parameter gradients and the
+power-iteration state vs the reference's golden vectors, feature gradients at the measured bf16 floor.
 """
 import torch
 import torch.nn as nn

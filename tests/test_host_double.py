@@ -280,7 +280,7 @@ def test_accelerate_swaps_reference_gan_nets_and_matches_their_forward():
     with pytest.raises((NotImplementedError, RuntimeError)):
         joligen_b200.accelerate(ResnetGenerator(3, 3, 16, norm_layer=nn.BatchNorm2d, n_blocks=2))
     with pytest.raises((NotImplementedError, RuntimeError)):
-        joligen_b200.accelerate(NLayerDiscriminator(3, 16, n_layers=3, norm_layer=norm, use_spectral=True))
+        joligen_b200.accelerate(ResnetGenerator(3, 3, 16, norm_layer=norm, n_blocks=2, use_spectral=True))
     with pytest.raises((NotImplementedError, RuntimeError)):
         joligen_b200.accelerate(NLayerDiscriminator(3, 16, n_layers=3, norm_layer=norm, use_dropout=True))
 
@@ -704,3 +704,40 @@ def test_accelerate_wavelet_space_discriminator_vs_reference():
         from joligen_b200 import ops
         got2 = ops.to_nchw(fast.forward_nhwc(ops.to_nhwc(x)), 1)     # the trainers' NHWC entry point
     assert tuple(got.shape) == tuple(want.shape) and rel_l2(got, want) < 3e-2 and rel_l2(got2, want) < 3e-2
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_accelerate_spectral_norm_discriminator_vs_reference():
+    """--D_spectral: NLayerDiscriminator of torch-spectral_norm-wrapped convolutions (`weight_orig`, `weight_u`,
+    `weight_v` in the state_dict).  The wrapper's pre-forward hook never runs on the B200 path: the mirror does the power
+    iteration and the normalisation itself (nets_projd._sn_weight) — logits, every gradient and the u / v buffers after
+    one training-mode forward vs the reference module."""
+    import copy
+    import functools
+    from oracle import ref_stubs
+    ref_stubs.install()
+    import torch.nn as nn
+    from models.modules.discriminators import NLayerDiscriminator
+    import joligen_b200
+    from joligen_b200 import nets_gan
+    norm = functools.partial(nn.InstanceNorm2d, affine=False, track_running_stats=False)
+    torch.manual_seed(2)
+    ref = NLayerDiscriminator(3, 16, n_layers=3, norm_layer=norm, use_spectral=True).train()
+    keys = list(ref.state_dict().keys())
+    fast = joligen_b200.accelerate(copy.deepcopy(ref))
+    assert isinstance(fast, nets_gan.NLayerDiscriminator) and list(fast.state_dict().keys()) == keys
+    assert any(k.endswith("weight_orig") for k in keys) and any(k.endswith("weight_u") for k in keys)
+    x = torch.randn(2, 3, 96, 96)
+    want = ref(x)
+    dy = torch.randn_like(want)
+    want.backward(dy)
+    with KD.installed():
+        got = fast(x)
+        assert rel_l2(got, want) < 3e-2, rel_l2(got, want)
+        got.backward(dy)
+    for (k, a), (_, b) in zip(fast.state_dict().items(), ref.state_dict().items()):
+        if k.endswith(("weight_u", "weight_v")):   # the power iteration is fp32 torch arithmetic on both sides
+            assert float((a - b).abs().max()) < 1e-5, k
+    named = dict(ref.named_parameters())
+    last = [k for k in named if k.endswith("weight_orig")][-1]
+    assert rel_l2(dict(fast.named_parameters())[last].grad, named[last].grad) < 3e-2
