@@ -225,7 +225,8 @@ def _resnet_generator_from_reference(ref):
     kinds = {type(m).__name__ for m in ref.decoder.model}
     padding_type = "reflect" if "ReflectionPad2d" in kinds else ("replicate" if "ReplicationPad2d" in kinds else "zeros")
     new = nets_gan.ResnetGenerator(enc_convs[0].in_channels, dec_convs[-1].out_channels, enc_convs[0].out_channels,
-                                   n_blocks=n_blocks, padding_type=padding_type)
+                                   n_blocks=n_blocks, padding_type=padding_type,
+                                   use_spectral=hasattr(enc_convs[0], "weight_orig"))
     _same_layers(new.encoder.model, ref.encoder.model, "ResnetGenerator encoder")
     _same_layers(new.decoder.model, ref.decoder.model, "ResnetGenerator decoder")
     return new

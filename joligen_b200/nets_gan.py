@@ -77,7 +77,11 @@ class _SeqRunner:
             elif isinstance(m, nn.ConvTranspose2d):
                 if m.kernel_size != (3, 3) or m.stride != (2, 2) or m.padding != (1, 1) or m.output_padding != (1, 1):
                     raise NotImplementedError("ConvTranspose2d other than k3 s2 p1 op1")
-                x = ops.conv_transpose2d(x, m.weight, m.bias, self.pack(m), pad=1)
+                if hasattr(m, "weight_orig"):   # --G_spectral
+                    from .nets_projd import _sn_conv_transpose
+                    x = _sn_conv_transpose(x, m)
+                else:
+                    x = ops.conv_transpose2d(x, m.weight, m.bias, self.pack(m), pad=1)
             elif isinstance(m, nn.InstanceNorm2d):
                 if m.affine or m.track_running_stats:
                     raise NotImplementedError("InstanceNorm2d with affine / running stats")
@@ -121,6 +125,11 @@ def _pad_layers(padding_type, n):
     raise NotImplementedError("padding [%s] is not implemented" % padding_type)
 
 
+def _sn(use_spectral):
+    """models/modules/utils.spectral_norm(module, mode) (:201-204)"""
+    return nn.utils.spectral_norm if use_spectral else (lambda m: m)
+
+
 def _uses_bias(norm_layer):
     f = norm_layer.func if isinstance(norm_layer, functools.partial) else norm_layer
     return f == nn.InstanceNorm2d
@@ -129,13 +138,14 @@ def _uses_bias(norm_layer):
 class ResnetBlock(nn.Module):
     def __init__(self, dim, padding_type, norm_layer, use_dropout, use_bias, use_spectral=False, conv=nn.Conv2d):
         super().__init__()
-        if use_dropout or use_spectral:
-            raise NotImplementedError("B200 ResnetBlock: no dropout / spectral norm")
+        if use_dropout:
+            raise NotImplementedError("B200 ResnetBlock: dropout")
+        sn = _sn(use_spectral)
         pad, p = _pad_layers(padding_type, 1)
         pad2, _ = _pad_layers(padding_type, 1)
         self.conv_block = nn.Sequential(
-            *pad, nn.Conv2d(dim, dim, kernel_size=3, padding=p, bias=use_bias), norm_layer(dim), nn.ReLU(True),
-            *pad2, nn.Conv2d(dim, dim, kernel_size=3, padding=p, bias=use_bias), norm_layer(dim))
+            *pad, sn(nn.Conv2d(dim, dim, kernel_size=3, padding=p, bias=use_bias)), norm_layer(dim), nn.ReLU(True),
+            *pad2, sn(nn.Conv2d(dim, dim, kernel_size=3, padding=p, bias=use_bias)), norm_layer(dim))
 
 
 class ResnetEncoder(nn.Module):
@@ -144,13 +154,16 @@ class ResnetEncoder(nn.Module):
         super().__init__()
         norm_layer = norm_layer or get_norm_layer("instance")
         use_bias = _uses_bias(norm_layer)
-        model = [nn.ReflectionPad2d(3), nn.Conv2d(input_nc, ngf, kernel_size=7, padding=0, bias=use_bias),
+        sn = _sn(use_spectral)
+        model = [nn.ReflectionPad2d(3), sn(nn.Conv2d(input_nc, ngf, kernel_size=7, padding=0, bias=use_bias)),
                  norm_layer(ngf), nn.ReLU(True)]
         for i in range(2):
             mult = 2 ** i
-            model += [nn.Conv2d(ngf * mult, ngf * mult * 2, kernel_size=3, stride=2, padding=1, bias=use_bias),
+            model += [sn(nn.Conv2d(ngf * mult, ngf * mult * 2, kernel_size=3, stride=2, padding=1, bias=use_bias)),
                       norm_layer(ngf * mult * 2), nn.ReLU(True)]
         for _ in range(n_blocks):
+            # (the reference's encoder does NOT hand use_spectral to its ResnetBlocks, resnet_generator.py:237-246: with
+            # --G_spectral the stem, the down- and the up-sampling layers are wrapped, the blocks are not)
             model += [ResnetBlock(ngf * 4, padding_type, norm_layer, use_dropout, use_bias)]
         self.model = nn.Sequential(*model)
 
@@ -164,8 +177,8 @@ class ResnetDecoder(nn.Module):
         model = []
         for i in range(2):
             mult = 2 ** (2 - i)
-            model += [nn.ConvTranspose2d(ngf * mult, ngf * mult // 2, kernel_size=3, stride=2, padding=1,
-                                         output_padding=1, bias=use_bias),
+            model += [_sn(use_spectral)(nn.ConvTranspose2d(ngf * mult, ngf * mult // 2, kernel_size=3, stride=2,
+                                                            padding=1, output_padding=1, bias=use_bias)),
                       norm_layer(ngf * mult // 2), nn.ReLU(True)]
         pad, p = _pad_layers(padding_type, 3)
         model += pad + [nn.Conv2d(ngf, output_nc, kernel_size=7, padding=p), nn.Tanh()]
@@ -178,11 +191,13 @@ class ResnetGenerator(nn.Module):
     def __init__(self, input_nc, output_nc, ngf=64, norm_layer=None, use_dropout=False, n_blocks=6,
                  padding_type="reflect", use_spectral=False, mobile=False):
         super().__init__()
-        if mobile or use_spectral:
-            raise NotImplementedError("B200 ResnetGenerator: mobile / spectral variants")
+        if mobile:
+            raise NotImplementedError("B200 ResnetGenerator: the mobile (separable convolution) variant")
         self.output_nc = output_nc
-        self.encoder = ResnetEncoder(input_nc, output_nc, ngf, norm_layer, use_dropout, n_blocks, padding_type)
-        self.decoder = ResnetDecoder(input_nc, output_nc, ngf, norm_layer, use_dropout, n_blocks, padding_type)
+        self.encoder = ResnetEncoder(input_nc, output_nc, ngf, norm_layer, use_dropout, n_blocks, padding_type,
+                                     use_spectral)
+        self.decoder = ResnetDecoder(input_nc, output_nc, ngf, norm_layer, use_dropout, n_blocks, padding_type,
+                                     use_spectral)
         self._runner = _SeqRunner()
 
     def forward_nhwc(self, x):

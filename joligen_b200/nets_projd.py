@@ -29,13 +29,15 @@ def sn_conv2d(*args, **kwargs):
     return spectral_norm(nn.Conv2d(*args, **kwargs))
 
 
-def _sn_weight(conv, eps=1e-12):
+def _sn_weight(conv, eps=1e-12, dim=0):
     """What torch's SpectralNorm.compute_weight does in its forward pre-hook (which never runs here, because the conv's
     own forward is not called): in training mode one power iteration updates the u / v buffers in place, then
-    W = W_orig / (u^T W_mat v) with u, v constants for autograd."""
+    W = W_orig / (u^T W_mat v) with u, v constants for autograd.  dim: the weight dimension that forms the matrix rows
+    (0 for nn.Conv2d, 1 for nn.ConvTranspose2d — torch.nn.utils.spectral_norm's own default per module type)."""
     w = conv.weight_orig
     u, v = conv.weight_u, conv.weight_v
-    wm = w.reshape(w.shape[0], -1)
+    wm = w if dim == 0 else w.permute(dim, *[d for d in range(w.dim()) if d != dim])
+    wm = wm.reshape(wm.shape[0], -1)
     if conv.training:
         with torch.no_grad():
             v.copy_(F.normalize(torch.mv(wm.t(), u), dim=0, eps=eps))
@@ -55,6 +57,18 @@ def _sn_conv(x, conv, act=L.ACT_NONE):
         bias_p = torch.zeros(cout8, dtype=torch.float32, device=w.device)
         bias_p[: w.shape[0]] = conv.bias.detach()
     return ops.conv_act(x, w, conv.bias, (wf, wd, bias_p), stride=conv.stride[0], pad=conv.padding[0], act=act)
+
+
+def _sn_conv_transpose(x, convt):
+    """spectral_norm(nn.ConvTranspose2d(k=3, s=2, p=1, op=1)) (--G_spectral, resnet_generator.py:306-318)"""
+    w = _sn_weight(convt, dim=1)                      # [Cin, Cout, 3, 3]
+    wf, wd = K.pack_conv_weight(w.detach())
+    cout = w.shape[1]
+    bias_p = None
+    if convt.bias is not None:
+        bias_p = torch.zeros((cout + 7) // 8 * 8, dtype=torch.float32, device=w.device)
+        bias_p[:cout] = convt.bias.detach()
+    return ops.conv_transpose2d(x, w, convt.bias, (wf, wd, bias_p), pad=convt.padding[0])
 
 
 class DownBlock(nn.Module):

@@ -280,7 +280,7 @@ def test_accelerate_swaps_reference_gan_nets_and_matches_their_forward():
     with pytest.raises((NotImplementedError, RuntimeError)):
         joligen_b200.accelerate(ResnetGenerator(3, 3, 16, norm_layer=nn.BatchNorm2d, n_blocks=2))
     with pytest.raises((NotImplementedError, RuntimeError)):
-        joligen_b200.accelerate(ResnetGenerator(3, 3, 16, norm_layer=norm, n_blocks=2, use_spectral=True))
+        joligen_b200.accelerate(ResnetGenerator(3, 3, 16, norm_layer=norm, n_blocks=2, mobile=True))
     with pytest.raises((NotImplementedError, RuntimeError)):
         joligen_b200.accelerate(NLayerDiscriminator(3, 16, n_layers=3, norm_layer=norm, use_dropout=True))
 
@@ -741,3 +741,41 @@ def test_accelerate_spectral_norm_discriminator_vs_reference():
     named = dict(ref.named_parameters())
     last = [k for k in named if k.endswith("weight_orig")][-1]
     assert rel_l2(dict(fast.named_parameters())[last].grad, named[last].grad) < 3e-2
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_accelerate_spectral_norm_generator_vs_reference():
+    """--G_spectral: ResnetGenerator whose convolutions AND transposed convolutions are spectral_norm-wrapped (the matrix
+    rows of a ConvTranspose2d are its OUTPUT channels: dim 1) — output, the u / v buffers after one training-mode
+    forward and the gradient of a transposed-convolution weight vs the reference module."""
+    import copy
+    import functools
+    from oracle import ref_stubs
+    ref_stubs.install()
+    import torch.nn as nn
+    from models.modules.resnet_architecture.resnet_generator import ResnetGenerator
+    import joligen_b200
+    from joligen_b200 import nets_gan
+    norm = functools.partial(nn.InstanceNorm2d, affine=False, track_running_stats=False)
+    torch.manual_seed(4)
+    ref = ResnetGenerator(3, 3, 16, norm_layer=norm, use_dropout=False, n_blocks=2, use_spectral=True).train()
+    keys = list(ref.state_dict().keys())
+    fast = joligen_b200.accelerate(copy.deepcopy(ref))
+    assert isinstance(fast, nets_gan.ResnetGenerator) and list(fast.state_dict().keys()) == keys
+    # wrapped: stem, down- and up-sampling layers; NOT wrapped: the ResnetBlocks (a reference quirk) and the 7x7 head
+    assert "decoder.model.0.weight_orig" in keys and "decoder.model.7.weight" in keys
+    assert "encoder.model.10.conv_block.1.weight" in keys
+    x = torch.randn(2, 3, 64, 64)
+    want = ref(x)
+    dy = torch.randn_like(want)
+    want.backward(dy)
+    with KD.installed():
+        got = fast(x)
+        assert rel_l2(got, want) < 3e-2, rel_l2(got, want)
+        got.backward(dy)
+    for (k, a), (_, b) in zip(fast.state_dict().items(), ref.state_dict().items()):
+        if k.endswith(("weight_u", "weight_v")):
+            assert float((a - b).abs().max()) < 1e-5, k
+    gf = dict(fast.named_parameters())["decoder.model.3.weight_orig"].grad
+    gr = dict(ref.named_parameters())["decoder.model.3.weight_orig"].grad
+    assert rel_l2(gf, gr) < 0.15, rel_l2(gf, gr)
