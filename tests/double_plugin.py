@@ -43,7 +43,8 @@ def pytest_configure(config):
     _stack.enter_context(mock.patch("torch.device", _Dev))
     for target, value in (("torch.cuda.is_available", lambda: True), ("torch.cuda.synchronize", lambda *a, **k: None),
                           ("torch.cuda.set_device", lambda *a, **k: None), ("torch.cuda.device_count", lambda: 1),
-                          ("torch.cuda.manual_seed", lambda *a, **k: None)):
+                          ("torch.cuda.manual_seed", lambda *a, **k: None),
+                          ("torch.cuda.is_current_stream_capturing", lambda: False)):
         _stack.enter_context(mock.patch(target, value))
     _stack.enter_context(mock.patch.object(torch.Tensor, "cuda", fresh))
     _stack.enter_context(mock.patch.object(torch.nn.Module, "cuda", ident))
