@@ -31,3 +31,15 @@ def test_bench_gpu_arm_runs_end_to_end_on_the_double(args):
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["scaling"] == "weak" and d["dtype"] == "bf16"
     assert d["value"] > 0 and d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
     assert d["roofline"]["bound"] == "tensor" and "workload" in d["config"]
+
+
+def test_graft_entry_smoke_runs_on_the_double():
+    """__graft_entry__.smoke() (what the driver runs on the B200 before the bench): its host side — build the net, the
+    trainer, one explicit-draw step, the oracle comparison at 2e-2 — executes on the double."""
+    code = "\n".join([
+        "import sys; sys.path[:0] = [%r, %r]" % (ROOT, os.path.join(ROOT, "tests")),
+        "import double_plugin; double_plugin.pytest_configure(None)",
+        "from joligen_b200 import lib as L; L.load().jg_check_device = lambda: 0",
+        "import __graft_entry__ as g; g.smoke()"])
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
