@@ -367,7 +367,7 @@ int jg_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, 
 /* ---------------------------------------------------------------------------------------------
  * GAN generator / discriminator helpers (NHWC bf16, HBM-bound).
  *   jg_pad2d_*    nn.ReflectionPad2d / ReplicationPad2d (resnet_generator.py:52-55, 207, 326-331); mode 0 reflect,
- *                 1 replicate (forward only)
+ *                 1 replicate
  *   jg_dilate2x   mode 0: zero insertion dst[2h][2w] = src[h][w] (dst is Hd x Wd = 2H x 2W) — prologue of
  *                 nn.ConvTranspose2d(k=3, s=2, p=1, output_padding=1) (resnet_generator.py:306-318) and of the
  *                 dgrad of stride-2 convolutions, both then run as stride-1 implicit GEMMs;

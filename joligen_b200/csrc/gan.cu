@@ -36,6 +36,47 @@ __global__ void pad2d_fwd_kernel(const __nv_bfloat16* __restrict__ src, int lds,
   }
 }
 
+// Replication padding backward: the border rows / columns of the source also feed the `pad` padded rows / columns
+// next to them, every other source position feeds its interior copy only.  (Not exercised on hardware yet: the
+// reference's default --G_padding_type is reflect.)
+__global__ void pad2d_bwd_replicate_kernel(const __nv_bfloat16* __restrict__ dpad, int ldp,
+                                           __nv_bfloat16* __restrict__ dsrc, int lds, int N, int H, int W, int C,
+                                           int pad) {
+  const int vecs = C / 8;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const long long total = (long long)N * H * W * vecs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vecs);
+    long long pix = i / vecs;
+    const int w = (int)(pix % W);
+    pix /= W;
+    const int h = (int)(pix % H);
+    const int n = (int)(pix / H);
+    // padded rows [h0, h1] and columns [w0, w1] that read source (h, w); a 1-wide source is both borders at once
+    const int h0 = h == 0 ? 0 : h + pad, h1 = h == H - 1 ? Hp - 1 : h + pad;
+    const int w0 = w == 0 ? 0 : w + pad, w1 = w == W - 1 ? Wp - 1 : w + pad;
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int a = h0; a <= h1; ++a)
+      for (int b = w0; b <= w1; ++b) {
+        const uint4 u = *reinterpret_cast<const uint4*>(dpad + (((long long)n * Hp + a) * Wp + b) * ldp + v * 8);
+        const uint32_t* pu = &u.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 x = unpack_bf16x2(pu[j]);
+          f[2 * j] += x.x;
+          f[2 * j + 1] += x.y;
+        }
+      }
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(dsrc + (((long long)n * H + h) * W + w) * lds + v * 8) = o;
+  }
+}
+
 // dsrc[N,H,W,C] = sum of dpad over the padded positions that read (h,w)   (reflection padding, pad < min(H,W))
 __global__ void pad2d_bwd_kernel(const __nv_bfloat16* __restrict__ dpad, int ldp, __nv_bfloat16* __restrict__ dsrc,
                                  int lds, int N, int H, int W, int C, int pad) {
@@ -215,11 +256,16 @@ extern "C" int jg_pad2d_bwd(const void* dpad, int ldp, void* dsrc, int lds, int 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   JG_CHECK(dpad && dsrc && N > 0 && C > 0 && C % 8 == 0 && ldp % 8 == 0 && lds % 8 == 0, JG_ERR_INVALID,
            "pad2d_bwd: bad args");
-  JG_CHECK(mode == 0, JG_ERR_INVALID, "pad2d_bwd: only reflection padding is implemented");
+  JG_CHECK(mode == 0 || mode == 1, JG_ERR_INVALID, "pad2d_bwd: mode %d (0 reflect, 1 replicate)", mode);
   JG_CHECK(pad >= 0 && pad < H && pad < W, JG_ERR_INVALID, "pad2d_bwd: pad %d", pad);
   const long long total = (long long)N * H * W * (C / 8);
-  pad2d_bwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dpad), ldp,
-                                                            static_cast<__nv_bfloat16*>(dsrc), lds, N, H, W, C, pad);
+  if (mode == 0) {
+    pad2d_bwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dpad), ldp,
+                                                              static_cast<__nv_bfloat16*>(dsrc), lds, N, H, W, C, pad);
+  } else {
+    pad2d_bwd_replicate_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(dpad), ldp, static_cast<__nv_bfloat16*>(dsrc), lds, N, H, W, C, pad);
+  }
   JG_LAUNCH_CHECK();
   return JG_OK;
 }
