@@ -331,6 +331,19 @@ def accelerate(module: nn.Module) -> nn.Module:
         _adopt_b2b(new, module)
         new.train(module.training)
         return new
+    if cls == "MultiScaleD" and isinstance(getattr(module, "mini_discs", None), nn.ModuleDict):
+        # the trainable heads of the projected discriminator (models/modules/projected_d/discriminator.py:166-230); the
+        # frozen timm feature network in front of them is third-party and stays the reference's
+        from . import nets_projd
+        kinds = {type(d).__name__ for d in module.mini_discs.values()}
+        if kinds != {"SingleDisc"}:
+            raise NotImplementedError("accelerate: MultiScaleD mini-discriminators %s (SingleDisc is implemented)"
+                                      % sorted(kinds))
+        new = nets_projd.MultiScaleD(channels=list(module.disc_in_channels), resolutions=list(module.disc_in_res),
+                                     conv=True, feats=None, num_discs=len(module.mini_discs))
+        _adopt(new, module)
+        new.train(module.training)
+        return new
     if cls == "ResnetGenerator" and hasattr(module, "encoder") and hasattr(module, "decoder"):
         new = _resnet_generator_from_reference(module)
         _adopt(new, module)

@@ -275,3 +275,38 @@ def test_cut_trainer_checkpoint_resume_is_exact(golden_dir):
         for n, m in zip(nets_, nets2):
             for (k, v), (_, w) in zip(n.state_dict().items(), m.state_dict().items()):
                 assert torch.equal(v, w), k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present (GPU box)")
+def test_accelerate_swaps_the_projected_discriminator_heads(golden_dir):
+    """accelerate() on a module that HOLDS the reference's MultiScaleD (as ProjectedDiscriminator does next to its frozen
+    timm feature network): the heads are swapped, parameters and the spectral-norm buffers adopted, logits and the
+    power-iteration state after one training-mode forward == the reference heads themselves."""
+    import copy
+    from oracle import ref_stubs
+    ref_stubs.install()
+    from models.modules.projected_d.discriminator import MultiScaleD
+    import joligen_b200
+    from joligen_b200 import nets_projd
+    from oracle.gen_golden_projd import CHANNELS, RESOLUTIONS, features, seeded_state
+    gold = torch.load(os.path.join(golden_dir, "projd_small.pt"))
+    ref = MultiScaleD(channels=CHANNELS, resolutions=RESOLUTIONS, conv=True, feats=None, num_discs=2, proj_type=2, cond=0)
+    ref.load_state_dict(seeded_state(gold["shapes"], gold["wseed"]))
+    ref.train()
+    holder = torch.nn.Module()
+    holder.feature_network = torch.nn.Identity()          # (stands for the frozen backbone)
+    holder.discriminator = copy.deepcopy(ref)
+    params = dict(holder.discriminator.named_parameters())
+    joligen_b200.accelerate(holder)
+    fast = holder.discriminator
+    assert isinstance(fast, nets_projd.MultiScaleD) and isinstance(holder.feature_network, torch.nn.Identity)
+    assert list(fast.state_dict().keys()) == list(ref.state_dict().keys())
+    assert all(p is params[k] for k, p in fast.named_parameters())
+    feats = features(gold["fseed"])
+    want = ref(feats)
+    with KD.installed():
+        got = fast(feats)
+    assert rel(got, want) < 2e-2 and rel(got, gold["logits"]) < 2e-2
+    for (k, a), (_, b) in zip(fast.state_dict().items(), ref.state_dict().items()):
+        if k.endswith(("weight_u", "weight_v")):
+            assert float((a - b).abs().max()) < 1e-5, k
